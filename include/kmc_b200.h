@@ -1,0 +1,143 @@
+/* include/kmc_b200.h -- C ABI of the B200-native KMC sweep (drop-in boundary).
+ *
+ * The reference (xiaopuren/KMC-with-a-diffusion-reaction-algorithm, main.cpp) exposes no plugin or
+ * FFI interface: its "API" is (i) the parameter globals main.cpp:39-99, (ii) the state arrays
+ * main.cpp:102-118 and (iii) the output files written every 5000 steps (main.cpp:2206-2305).
+ * This header carries exactly that parameter set, the state in the reference's own array shapes,
+ * and the quantities the reference writes, so that main.cpp's time-step loop (main.cpp:461-2308)
+ * can be replaced by
+ *
+ *     kmc_set_state(h, 0, R_x, R_y, R_z, protein_status, res_nei, step, protein_num_in_Max_Complex);
+ *     kmc_step(h, n);
+ *     kmc_get_state(h, 0, R_x, R_y, R_z, protein_status, res_nei);   kmc_get_series(h, 0, &s);
+ *
+ * (binding shown in INTEGRATION.md). Plain pointers and sizes only; no CUDA or torch types.
+ * All functions return 0 on success or a negative kmc_status; kmc_last_error() gives the text.
+ * A handle is owned by one host thread at a time. There is NO CPU fallback: every entry point that
+ * computes requires a CUDA device of compute capability 10.0 (sm_100a cubin) and fails otherwise.
+ */
+#ifndef KMC_B200_H
+#define KMC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMC_ABI_VERSION 1
+
+typedef enum kmc_status {
+    KMC_OK = 0,
+    KMC_ERR_INVALID = -1,     /* bad argument */
+    KMC_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+    KMC_ERR_CAPACITY = -3,    /* an internal device buffer overflowed (reported, never silently dropped) */
+    KMC_ERR_STATE = -4,       /* inconsistent state handed in (bond table asymmetric, ...) */
+    KMC_ERR_IO = -5
+} kmc_status;
+
+/* Update order of the diffusion sweep (main.cpp:577, S2). */
+#define KMC_MODE_REPLAY 0      /* molecule-index order: reproduces the reference's sequential Gauss-Seidel
+                                  sweep exactly (decisions bit-exact, positions to libm rounding) */
+#define KMC_MODE_PRODUCTION 1  /* checkerboard order: units are swept colour by colour of their cell
+                                  (2x2 colouring), statistically equivalent; same kernels */
+
+typedef struct kmc_params {
+    /* 1:1 with the reference globals ------------------------------------------ main.cpp */
+    double box[3];                 /* cell_range_x, cell_range_y, cell_range_z      43-45 */
+    double dt;                     /* time_step (ns)                                   40 */
+    double pai;                    /* 3.1415926 (the reference's own pi)               71 */
+    double rA, DA, DrotA;          /* RB_A_radius, RB_A_D, RB_A_rot_D               72-74 */
+    double rB, DB, DrotB;          /* RB_B_radius, RB_B_D, RB_B_rot_D               76-78 */
+    double mono_cis_on, mono_cis_off;             /* mono_cis_Ass_Rate / _Diss_Rate 80-81 */
+    double cis_D, cis_Drot, cis_on, cis_off;      /* cis_*                          83-86 */
+    double bond_D, bond_Drot, on, off;            /* bond_D, bond_rot_D, Ass_Rate, Diss_Rate 88-91 */
+    double bond_dist_cut;          /* bond_dist_cutoff                                 93 */
+    double thetapd_cut;            /* bond_thetapd_cutoff                              95 */
+    double thetaot_cut;            /* bond_thetaot_cutoff                              97 */
+    double cis_thetaot_cut;        /* cis_thetaot_cutoff                               98 */
+    double cis_dist_cut;           /* cis_dist_cutoff                                  99 */
+    int32_t n_receptor;            /* protein_A_tot_num (per replica)                  48 */
+    int32_t n_ligand;              /* protein_B_tot_num (per replica)                  57 */
+    /* build-side additions ------------------------------------------------------------- */
+    int32_t n_replicas;            /* independent copies of the system advanced together (>=1) */
+    int32_t mode;                  /* KMC_MODE_* */
+    uint64_t seed;                 /* Philox key; replica r uses seed + r */
+    double cell_edge;              /* neighbour-grid cell edge in Angstrom; 0 = automatic */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t reserved;
+} kmc_params;
+
+/* the bond.dat columns, main.cpp:2251 (plus the step they belong to) */
+typedef struct kmc_series {
+    int64_t step;                  /* mc_time_step of the last completed step */
+    int32_t bond_num_rl;           /* receptor-ligand bonds                  */
+    int32_t bond_num_mono_cis;     /* cis bonds between two ligand-free receptors */
+    int32_t bond_num_cis;          /* cis bonds with >=1 ligand-bound receptor */
+    int32_t bond_num;              /* all bonds                              */
+    int32_t max_complex;           /* protein_num_in_Max_Complex: running max, never reset (main.cpp:896-898) */
+    int32_t n_complexes;           /* tot_cluster_num: ligand-rooted complexes of size > 1 at the last step */
+    int32_t n_in_complexes;        /* tot_proteins_in_cluster */
+    int32_t reserved;
+    double cluster_size;           /* main.cpp:2200-2202 */
+} kmc_series;
+
+typedef struct kmc_handle kmc_handle;
+
+int kmc_abi_version(void);
+/* fills the reference's shipped defaults, main.cpp:39-99 */
+void kmc_default_params(kmc_params *p);
+int kmc_create(const kmc_params *p, kmc_handle **out);
+void kmc_destroy(kmc_handle *h);
+const char *kmc_last_error(const kmc_handle *h);     /* h may be NULL: error of the last failed kmc_create */
+
+/* Scalable equivalent of the random sequential insertion main.cpp:273-456 (same exclusion radii and
+ * orientation distributions; O(N) with a cell grid). Replica r is seeded with init_seed + r.
+ * sort_cells != 0 numbers the molecules in cell-major order (memory locality for large membranes). */
+int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_cells);
+
+/* State in the reference's array shapes (main.cpp:102-118), one replica at a time:
+ *   R_x, R_y, R_z  double[N+1][5][5]   (1-based; receptor uses [1..4][1..4], ligand [1..4][1..2])
+ *   protein_status int[N+1][5],  res_nei int[N+1][7]       N = n_receptor + n_ligand
+ * step_done = number of completed steps (mc_time_step of the last one), max_complex = running max. */
+int kmc_set_state(kmc_handle *h, int32_t replica, const double *R_x, const double *R_y, const double *R_z,
+                  const int32_t *protein_status, const int32_t *res_nei, int64_t step_done, int32_t max_complex);
+int kmc_get_state(kmc_handle *h, int32_t replica, double *R_x, double *R_y, double *R_z,
+                  int32_t *protein_status, int32_t *res_nei);
+
+/* Compact pose exchange for large systems (all replicas): receptors double[n][6] = centre xy, site-2 xy,
+ * site-3 xy; ligands double[n][24] = points (1,1),(2,1),(3,1),(4,1),(1,2),(2,2),(3,2),(4,2) x xyz;
+ * bonds int32: rec_lig[n] (0-based ligand index or -1), rec_site[n] (2..4 or 0), rec_cis[n] (receptor index or -1). */
+int kmc_get_packed(kmc_handle *h, double *rec_pose, double *lig_pose, int32_t *rec_lig, int32_t *rec_site, int32_t *rec_cis);
+int kmc_set_packed(kmc_handle *h, const double *rec_pose, const double *lig_pose, const int32_t *rec_lig,
+                   const int32_t *rec_site, const int32_t *rec_cis, int64_t step_done);
+
+/* Advance n time steps (main.cpp:461-2202 each). Asynchronous on the handle's stream except for the
+ * conflict-resolution count it reads back each step; kmc_sync waits for completion. */
+int kmc_step(kmc_handle *h, int64_t n);
+int kmc_sync(kmc_handle *h);
+
+/* Outputs the reference writes at its output cadence */
+int kmc_get_series(kmc_handle *h, int32_t replica, kmc_series *out);
+/* rows of `results` (main.cpp:2294-2301): for each ligand l (0-based) row_len[l] members (reference 1-based
+ * molecule ids, member order as left by the last step incl. its shuffles), concatenated in `members`.
+ * returns total number of members or a negative status. */
+int64_t kmc_get_complexes(kmc_handle *h, int32_t replica, int32_t *row_len, int32_t *members, int64_t cap);
+/* histogram of ligand-rooted complex sizes over replica (or all replicas if replica < 0): hist[s] = number of
+ * complexes with s members, sizes >= nbins-1 are accumulated in the last bin */
+int kmc_get_oligomer_hist(kmc_handle *h, int32_t replica, int64_t *hist, int32_t nbins);
+/* replay diagnostics: accepted[N+1] (1-based): 1 if the molecule's unit kept its move in the last step */
+int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
+/* ev[16] accumulated since creation: [0] R-L on, [1] mono-cis on, [2] cis on, [3] R-L off, [4] mono-cis off,
+ * [5] cis off, [6] unit moves reverted, [7] unit moves tried, [8] far movers, [9] conflict-resolution passes,
+ * [10] complex-table rebuilds, [11] kernels launched */
+int kmc_get_events(kmc_handle *h, int64_t *ev);
+
+/* Byte-compatible writers for the reference's output files (append one record, main.cpp:2247-2253, 2291-2305) */
+int kmc_write_bond_dat(kmc_handle *h, int32_t replica, const char *path);
+int kmc_write_cluster_log(kmc_handle *h, int32_t replica, const char *path);
+/* the reference's own main loop: n_steps steps with records every output_every steps into directory `dir` */
+int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, const char *dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

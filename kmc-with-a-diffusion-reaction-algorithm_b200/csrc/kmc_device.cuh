@@ -1,0 +1,91 @@
+// csrc/kmc_device.cuh -- device-resident state of one kmc_handle (SoA in HBM) and access helpers.
+#pragma once
+#include "kmc_geom.cuh"
+#include "kmc_philox.cuh"
+
+namespace kmc {
+
+enum Scalar {
+    S_MEMBER_CURSOR = 0,  // next free slot in members[]
+    S_NCX,                // number of complexes (size > 1) in cxRoots[]
+    S_NFAR,               // far movers this step
+    S_NUNKNOWN,           // units still undecided after a resolve pass
+    S_NCAND_RL, S_NCAND_CIS,
+    S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
+    S_OVERFLOW,           // a device buffer overflowed (bitmask)
+    S_COUNT = 16
+};
+enum UnitState : unsigned char { U_UNKNOWN = 0, U_ACCEPT = 1, U_REJECT = 2 };
+enum Event { EV_RL_ON = 0, EV_MONO_ON, EV_CIS_ON, EV_RL_OFF, EV_MONO_OFF, EV_CIS_OFF, EV_REVERTED, EV_TRIED, EV_FAR,
+             EV_PASSES, EV_REBUILDS, EV_LAUNCHES, EV_COUNT = 16 };
+
+// Molecule numbering on the device: receptors gid = [0, NAt), ligands gid = NAt + h. Replica r owns
+// receptors [r*NA, (r+1)*NA) and ligands [r*NB, (r+1)*NB). Reference id (1-based, main.cpp) of receptor a
+// is a%NA + 1, of ligand h it is NA + h%NB + 1.
+struct Dev {
+    // poses: cur = committed state of the previous step (R_*), nxt = proposals / new state (R_*_new)
+    double2 *recC, *recS2, *recS3, *recCn, *recS2n, *recS3n;
+    double *lig, *lign;                    // [NBt][24]
+    // bond table (res_nei / protein_status, main.cpp:115-118): -1 = free
+    int *recLig, *recSite, *recCis;        // ligand index, ligand site 0..2, cis partner
+    int *ligRec;                           // [NBt][3] receptor on site s
+    // complexes (S1, main.cpp:514-562)
+    int *ufParent;                         // union-find over uid: ligands [0,NBt), receptors NBt + a
+    int *unitOf;                           // [NT] gid of the head of the moving unit this molecule belongs to
+    int *cxSize, *cxOff, *cxRoots;         // per root ligand: members, offset into members[]; list of roots with size>1
+    int *members, *rowWork;                // member gids in BFS order / working copy permuted by the shuffles
+    int *bfsMark;
+    unsigned char *unitState, *farFlag, *movedFlag;
+    // neighbour grid
+    int *cellCount, *cellStart, *scanTmp;  // [ncell+1]
+    int *sorted;                           // [2*NT] entries gid | ghost bit
+    int *molSlot;                          // [NT]
+    int4 *farList;                         // [NT] (gid, cell, slot, -)
+    // reaction candidates (successful draws only)
+    unsigned long long *candRL, *candCis;
+    int candCap;
+    int *scal;
+    int *maxComplex;                       // [R]
+    unsigned long long *events;
+    int ncell;
+};
+
+#define GHOST_BIT 0x40000000
+
+KD Rec load_rec(const double2 *C, const double2 *S2, const double2 *S3, int a) {
+    double2 c = C[a], s2 = S2[a], s3 = S3[a];
+    Rec r; r.cx = c.x; r.cy = c.y; r.s2x = s2.x; r.s2y = s2.y; r.s3x = s3.x; r.s3y = s3.y; return r;
+}
+KD void store_rec(double2 *C, double2 *S2, double2 *S3, int a, const Rec &r) {
+    C[a] = make_double2(r.cx, r.cy); S2[a] = make_double2(r.s2x, r.s2y); S3[a] = make_double2(r.s3x, r.s3y);
+}
+KD void load_lig(const double *base, int h, Lig &l) {
+    const double2 *p = reinterpret_cast<const double2 *>(base + (size_t)h * 24);
+    double *d = &l.p[0][0];
+#pragma unroll
+    for (int q = 0; q < 12; q++) { double2 v = p[q]; d[2 * q] = v.x; d[2 * q + 1] = v.y; }
+}
+// centre + three beads only (first 96 bytes): all an overlap test needs
+KD void load_lig_beads(const double *base, int h, Lig &l) {
+    const double2 *p = reinterpret_cast<const double2 *>(base + (size_t)h * 24);
+    double *d = &l.p[0][0];
+#pragma unroll
+    for (int q = 0; q < 6; q++) { double2 v = p[q]; d[2 * q] = v.x; d[2 * q + 1] = v.y; }
+}
+KD void store_lig(double *base, int h, const Lig &l) {
+    double2 *p = reinterpret_cast<double2 *>(base + (size_t)h * 24);
+    const double *d = &l.p[0][0];
+#pragma unroll
+    for (int q = 0; q < 12; q++) p[q] = make_double2(d[2 * q], d[2 * q + 1]);
+}
+
+KD int cell_of(const Consts &K, int replica, double x, double y) {
+    int cx = (int)floor((x - K.gx0) * K.cellInv), cy = (int)floor((y - K.gy0) * K.cellInv);
+    cx = min(max(cx, 0), K.ncx - 1); cy = min(max(cy, 0), K.ncy - 1);
+    return (replica * K.ncy + cy) * K.ncx + cx;
+}
+KD int replica_of_gid(const Consts &K, int gid) { return gid < K.NAt ? gid / K.NA : (gid - K.NAt) / K.NB; }
+// reference molecule id (1-based) used to key the random stream
+KD uint32_t ref_id(const Consts &K, int gid) { return gid < K.NAt ? (uint32_t)(gid % K.NA + 1) : (uint32_t)(K.NA + (gid - K.NAt) % K.NB + 1); }
+
+}  // namespace kmc

@@ -1,0 +1,665 @@
+// csrc/kmc_engine.cu -- host side of the C ABI (include/kmc_b200.h): device memory, the per-step launch
+// sequence, state import/export in the reference's array shapes, and the reference's output records.
+// There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
+#include "../../include/kmc_b200.h"
+#include "kmc_kernels.cu"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace kmc;
+
+static thread_local std::string g_create_error;
+
+struct kmc_handle {
+    kmc_params P;
+    Consts K;
+    Dev D;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int R = 1, NA = 0, NB = 0, N = 0, NAt = 0, NBt = 0, NT = 0;
+    int64_t step_done = 0;
+    bool stepped = false;            // complexes/accept data of a completed step are available
+    std::vector<void *> allocs;
+    int *d_series = nullptr;
+    int scanBlocks = 0;
+    int64_t launches = 0, passes = 0;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return KMC_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+template <class T> static cudaError_t dalloc(kmc_handle *h, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) { h->allocs.push_back(q); e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)); }
+    *p = (T *)q;
+    return e;
+}
+
+extern "C" int kmc_abi_version(void) { return KMC_ABI_VERSION; }
+
+extern "C" void kmc_default_params(kmc_params *p) {
+    memset(p, 0, sizeof *p);
+    p->box[0] = 5773; p->box[1] = 5773; p->box[2] = 1000; p->dt = 10; p->pai = 3.1415926;
+    p->rA = 20; p->DA = 1; p->DrotA = 0.0174; p->rB = 30; p->DB = 7.2614; p->DrotB = 0.0061209;
+    p->mono_cis_on = 0.000047; p->mono_cis_off = 0.000000000000112;
+    p->cis_D = 0.5; p->cis_Drot = 0.005; p->cis_on = 0.00096; p->cis_off = 0.000000000000112;
+    p->bond_D = 0.5; p->bond_Drot = 0.005; p->on = 0.04; p->off = 0.000000000000348;
+    p->bond_dist_cut = 18; p->thetapd_cut = 45; p->thetaot_cut = 90; p->cis_thetaot_cut = 10; p->cis_dist_cut = 15;
+    p->n_receptor = 150; p->n_ligand = 50; p->n_replicas = 1; p->mode = KMC_MODE_REPLAY; p->seed = 1;
+    p->cell_edge = 0; p->device = 0;
+}
+
+// derived constants with the reference's own expressions (host doubles, no contraction: see build flags)
+static void fill_consts(const kmc_params &P, Consts &K) {
+    memset(&K, 0, sizeof K);
+    K.Lx = P.box[0]; K.Ly = P.box[1]; K.Lz = P.box[2]; K.dt = P.dt; K.pai = P.pai; K.rA = P.rA; K.rB = P.rB;
+    K.ampA = 2 * sqrt(P.DA * P.dt / 6); K.ampB = 2 * sqrt(P.DB * P.dt / 6);
+    K.ampCis = 2 * sqrt(P.cis_D * P.dt / 6); K.ampBond = 2 * sqrt(P.bond_D * P.dt / 6);
+    K.rotA = sqrt(P.DrotA * P.dt); K.rotB = sqrt(P.DrotB * P.dt); K.rotCis = sqrt(P.cis_Drot * P.dt); K.rotBond = sqrt(P.bond_Drot * P.dt);
+    K.pOn = P.on * P.dt; K.pMonoCisOn = P.mono_cis_on * P.dt; K.pCisOn = P.cis_on * P.dt;
+    K.pOff = P.off * P.dt; K.pMonoCisOff = P.mono_cis_off * P.dt; K.pCisOff = P.cis_off * P.dt;
+    K.bondCut = P.bond_dist_cut; K.thetaPdCut = P.thetapd_cut; K.thetaOtCut = P.thetaot_cut;
+    K.cisThetaCut = P.cis_thetaot_cut; K.cisCut = P.cis_dist_cut;
+    K.ovAA = P.rA + P.rA; K.ovAB = P.rA + P.rB; K.ovBB = P.rB + P.rB;
+    K.rlD1 = P.bond_dist_cut / 2 + P.rA + P.rB; K.rlD2 = P.bond_dist_cut / 2;
+    K.cisD1 = P.cis_dist_cut / 2 + P.rA + P.rA; K.cisD2 = P.cis_dist_cut / 2;
+    K.fRL1 = (P.bond_dist_cut / 2 + P.rA) / P.rB; K.fRL3 = (P.bond_dist_cut / 2 + 2 * P.rA) / P.rB; K.fRL2 = (P.bond_dist_cut / 2) / P.rB;
+    K.fC1 = (P.cis_dist_cut / 2 + P.rA) / P.rA; K.fC3 = (P.cis_dist_cut / 2) / P.rA; K.fC2 = (P.cis_dist_cut / 2 + 2 * P.rA) / P.rA;
+    K.fSeat = (P.bond_dist_cut / 2 + P.rB * 2 / sqrt(3) + P.rB) / P.rA;
+    const double rB = P.rB;
+    const double g[8][2] = {{0, 0}, {0, rB * 2 / sqrt(3)}, {-rB, -rB / sqrt(3)}, {rB, -rB / sqrt(3)}, {0, 0},
+                            {0, rB * (2 / sqrt(3) + 1)}, {-rB * (sqrt(3) / 2 + 1), -rB / sqrt(3) - rB / 2},
+                            {rB * (sqrt(3) / 2 + 1), -rB / sqrt(3) - rB / 2}};
+    memcpy(K.ghost, g, sizeof g);
+    K.conv = 180 / 3.14159;
+    const double rs = rB * 2 / sqrt(3.0);
+    K.reachRR = 2 * P.rA + 1e-3; K.reachRL = P.rA + P.rB + rs + 1e-3; K.reachLL = 2 * P.rB + 2 * rs + 1e-3;
+    K.reachOn = P.rA + P.bond_dist_cut + rs + P.rB + 1e-3; K.reachCis = 2 * P.rA + P.cis_dist_cut + 1e-3;
+    K.skin = 48.0;
+    K.NA = P.n_receptor; K.NB = P.n_ligand; K.R = P.n_replicas; K.mode = P.mode;
+    K.NAt = K.NA * K.R; K.NBt = K.NB * K.R; K.NT = K.NAt + K.NBt; K.seed = P.seed;
+    double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + K.skin + 1.0;
+    if (P.cell_edge > edge) edge = P.cell_edge;
+    else if (P.cell_edge == 0) edge = std::max(edge, 256.0);
+    K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
+    K.ncx = (int)ceil((P.box[0] + 2 * edge) / edge); K.ncy = (int)ceil((P.box[1] + 2 * edge) / edge);
+    K.cellInv = 1.0 / edge;
+}
+
+extern "C" void kmc_destroy(kmc_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->P.device);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *kmc_last_error(const kmc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
+    if (!p || !out) { g_create_error = "null argument"; return KMC_ERR_INVALID; }
+    *out = nullptr;
+    if (p->n_receptor < 0 || p->n_ligand < 1 || p->n_replicas < 1 || p->box[0] <= 0 || p->box[1] <= 0 || p->box[2] <= 0 ||
+        p->rA <= 0 || p->rB <= 0 || p->dt <= 0) { g_create_error = "invalid parameters"; return KMC_ERR_INVALID; }
+    if ((int64_t)(p->n_receptor + p->n_ligand) * p->n_replicas >= (1LL << 30)) { g_create_error = "too many molecules"; return KMC_ERR_INVALID; }
+    kmc_handle *h = new kmc_handle;
+    h->P = *p;
+    auto fail = [&](int code, const std::string &m) { g_create_error = m; kmc_destroy(h); return code; };
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(KMC_ERR_CUDA, std::string("no CUDA device: this library has no CPU path (") + cudaGetErrorString(e) + ")");
+    if (p->device < 0 || p->device >= ndev) return fail(KMC_ERR_INVALID, "bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || cudaSetDevice(p->device) != cudaSuccess) return fail(KMC_ERR_CUDA, "cannot select device");
+    if (prop.major != 10) return fail(KMC_ERR_CUDA, "device is not compute capability 10.x: the kernels are built for sm_100a only");
+    fill_consts(*p, h->K);
+    const Consts &K = h->K;
+    h->R = K.R; h->NA = K.NA; h->NB = K.NB; h->N = K.NA + K.NB; h->NAt = K.NAt; h->NBt = K.NBt; h->NT = K.NT;
+    if ((int64_t)K.R * K.ncx * K.ncy >= (1LL << 31) - 2) return fail(KMC_ERR_INVALID, "neighbour grid too large: raise cell_edge");
+    Dev &D = h->D; memset(&D, 0, sizeof D);
+    D.ncell = K.R * K.ncx * K.ncy;
+    D.candCap = std::max(1 << 14, K.NAt / 8);
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+#define A(ptr, n) ok = ok && dalloc(h, &D.ptr, (size_t)(n)) == cudaSuccess
+    A(recC, K.NAt); A(recS2, K.NAt); A(recS3, K.NAt); A(recCn, K.NAt); A(recS2n, K.NAt); A(recS3n, K.NAt);
+    A(lig, (size_t)K.NBt * 24); A(lign, (size_t)K.NBt * 24);
+    A(recLig, K.NAt); A(recSite, K.NAt); A(recCis, K.NAt); A(ligRec, (size_t)K.NBt * 3);
+    A(ufParent, K.NT); A(unitOf, K.NT); A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
+    A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT);
+    A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
+    A(cellCount, (size_t)D.ncell + 1); A(cellStart, (size_t)D.ncell + 1);
+    h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    A(scanTmp, (size_t)h->scanBlocks + 1);
+    A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT); A(farList, K.NT);
+    A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
+    A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
+#undef A
+    ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 4) == cudaSuccess;
+    if (!ok) return fail(KMC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    // empty bond table
+    ok = cudaMemset(D.recLig, 0xff, sizeof(int) * K.NAt) == cudaSuccess && cudaMemset(D.recSite, 0xff, sizeof(int) * K.NAt) == cudaSuccess &&
+         cudaMemset(D.recCis, 0xff, sizeof(int) * K.NAt) == cudaSuccess && cudaMemset(D.ligRec, 0xff, sizeof(int) * 3 * (size_t)K.NBt) == cudaSuccess;
+    int one = 1;
+    ok = ok && cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) return fail(KMC_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    *out = h;
+    return KMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state exchange
+// ------------------------------------------------------------------------------------------------
+static inline size_t RI(int i, int j, int k) { return (size_t)i * 25 + j * 5 + k; }
+
+static int select_device(kmc_handle *h) { CK(cudaSetDevice(h->P.device)); return KMC_OK; }
+
+extern "C" int kmc_set_state(kmc_handle *h, int32_t rep, const double *Rx, const double *Ry, const double *Rz,
+                             const int32_t *status, const int32_t *res_nei, int64_t step_done, int32_t max_complex) {
+    if (!h) return KMC_ERR_INVALID;
+    if (rep < 0 || rep >= h->R || !Rx || !Ry || !Rz || !status || !res_nei) { h->err = "kmc_set_state: bad argument"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    const int NA = h->NA, NB = h->NB, N = h->N;
+    const double rA = h->P.rA;
+    std::vector<double2> c(NA), s2(NA), s3(NA);
+    std::vector<double> lig((size_t)NB * 24);
+    std::vector<int> rl(NA), rs(NA), rc_(NA), lr((size_t)NB * 3);
+    for (int a = 0; a < NA; a++) {
+        const int i = a + 1;
+        for (int j = 1; j <= 4; j++) {
+            bool same = Rx[RI(i, j, 1)] == Rx[RI(i, 1, 1)] && Ry[RI(i, j, 1)] == Ry[RI(i, 1, 1)] && Rx[RI(i, j, 2)] == Rx[RI(i, 1, 2)] &&
+                        Ry[RI(i, j, 2)] == Ry[RI(i, 1, 2)] && Rx[RI(i, j, 3)] == Rx[RI(i, 1, 3)] && Ry[RI(i, j, 3)] == Ry[RI(i, 1, 3)] &&
+                        Rx[RI(i, j, 4)] == Rx[RI(i, 1, 1)] && Ry[RI(i, j, 4)] == Ry[RI(i, 1, 1)];
+            bool zt = Rz[RI(i, j, 1)] == (j * 2 - 2) * rA && Rz[RI(i, j, 2)] == (j * 2 - 2) * rA && Rz[RI(i, j, 3)] == (j * 2 - 2) * rA &&
+                      Rz[RI(i, j, 4)] == (j * 2 - 1) * rA;
+            if (!same || !zt) {
+                h->err = "kmc_set_state: receptor " + std::to_string(i) + " is not a stack of identical beads at z=(2j-2)*rA (main.cpp:298-316)";
+                return KMC_ERR_STATE;
+            }
+        }
+        c[a] = make_double2(Rx[RI(i, 1, 1)], Ry[RI(i, 1, 1)]);
+        s2[a] = make_double2(Rx[RI(i, 1, 2)], Ry[RI(i, 1, 2)]);
+        s3[a] = make_double2(Rx[RI(i, 1, 3)], Ry[RI(i, 1, 3)]);
+        int l = res_nei[i * 7 + 2], st = res_nei[i * 7 + 4], cp = res_nei[i * 7 + 3];
+        if ((l != 0) != (status[i * 5 + 2] != 0) || (cp != 0) != (status[i * 5 + 3] != 0) || (l != 0 && (l <= NA || l > N || st < 2 || st > 4)) ||
+            (cp != 0 && (cp < 1 || cp > NA || cp == i))) { h->err = "kmc_set_state: bad bond entry for receptor " + std::to_string(i); return KMC_ERR_STATE; }
+        if (l != 0 && res_nei[l * 7 + st] != i) { h->err = "kmc_set_state: asymmetric R-L bond at receptor " + std::to_string(i); return KMC_ERR_STATE; }
+        if (cp != 0 && res_nei[cp * 7 + 3] != i) { h->err = "kmc_set_state: asymmetric cis bond at receptor " + std::to_string(i); return KMC_ERR_STATE; }
+        rl[a] = l ? rep * NB + (l - NA - 1) : -1; rs[a] = l ? st - 2 : -1; rc_[a] = cp ? rep * NA + (cp - 1) : -1;
+    }
+    for (int b = 0; b < NB; b++) {
+        const int i = NA + 1 + b;
+        for (int j = 1; j <= 4; j++)
+            for (int k = 1; k <= 2; k++) {
+                int q = k == 1 ? (j == 1 ? 0 : j - 1) : (j == 1 ? 4 : j + 3);
+                lig[(size_t)b * 24 + q * 3 + 0] = Rx[RI(i, j, k)]; lig[(size_t)b * 24 + q * 3 + 1] = Ry[RI(i, j, k)]; lig[(size_t)b * 24 + q * 3 + 2] = Rz[RI(i, j, k)];
+            }
+        for (int s = 0; s < 3; s++) {
+            int r = res_nei[i * 7 + s + 2];
+            if ((r != 0) != (status[i * 5 + s + 2] != 0) || (r != 0 && (r < 1 || r > NA || res_nei[r * 7 + 2] != i || res_nei[r * 7 + 4] != s + 2))) {
+                h->err = "kmc_set_state: bad bond entry for ligand " + std::to_string(i); return KMC_ERR_STATE;
+            }
+            lr[(size_t)b * 3 + s] = r ? rep * NA + (r - 1) : -1;
+        }
+    }
+    Dev &D = h->D;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(D.recC + (size_t)rep * NA, c.data(), sizeof(double2) * NA, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recS2 + (size_t)rep * NA, s2.data(), sizeof(double2) * NA, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recS3 + (size_t)rep * NA, s3.data(), sizeof(double2) * NA, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.lig + (size_t)rep * NB * 24, lig.data(), sizeof(double) * 24 * NB, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recLig + (size_t)rep * NA, rl.data(), sizeof(int) * NA, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recSite + (size_t)rep * NA, rs.data(), sizeof(int) * NA, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recCis + (size_t)rep * NA, rc_.data(), sizeof(int) * NA, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.ligRec + (size_t)rep * NB * 3, lr.data(), sizeof(int) * 3 * NB, cudaMemcpyHostToDevice));
+    int one = 1;
+    CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.maxComplex + rep, &max_complex, sizeof(int), cudaMemcpyHostToDevice));
+    h->step_done = step_done; h->stepped = false;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_state(kmc_handle *h, int32_t rep, double *Rx, double *Ry, double *Rz, int32_t *status, int32_t *res_nei) {
+    if (!h) return KMC_ERR_INVALID;
+    if (rep < 0 || rep >= h->R || !Rx || !Ry || !Rz || !status || !res_nei) { h->err = "kmc_get_state: bad argument"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    const int NA = h->NA, NB = h->NB, N = h->N;
+    const double rA = h->P.rA;
+    std::vector<double2> c(NA), s2(NA), s3(NA);
+    std::vector<double> lig((size_t)NB * 24);
+    std::vector<int> rl(NA), rs(NA), rcis(NA), lr((size_t)NB * 3);
+    Dev &D = h->D;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(c.data(), D.recC + (size_t)rep * NA, sizeof(double2) * NA, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(s2.data(), D.recS2 + (size_t)rep * NA, sizeof(double2) * NA, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(s3.data(), D.recS3 + (size_t)rep * NA, sizeof(double2) * NA, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lig.data(), D.lig + (size_t)rep * NB * 24, sizeof(double) * 24 * NB, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rl.data(), D.recLig + (size_t)rep * NA, sizeof(int) * NA, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rs.data(), D.recSite + (size_t)rep * NA, sizeof(int) * NA, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rcis.data(), D.recCis + (size_t)rep * NA, sizeof(int) * NA, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lr.data(), D.ligRec + (size_t)rep * NB * 3, sizeof(int) * 3 * NB, cudaMemcpyDeviceToHost));
+    memset(Rx, 0, sizeof(double) * 25 * (N + 1)); memset(Ry, 0, sizeof(double) * 25 * (N + 1)); memset(Rz, 0, sizeof(double) * 25 * (N + 1));
+    memset(status, 0, sizeof(int32_t) * 5 * (N + 1)); memset(res_nei, 0, sizeof(int32_t) * 7 * (N + 1));
+    for (int a = 0; a < NA; a++) {
+        const int i = a + 1;
+        for (int j = 1; j <= 4; j++) {
+            double zj = (j * 2 - 2) * rA;
+            Rx[RI(i, j, 1)] = c[a].x; Ry[RI(i, j, 1)] = c[a].y; Rz[RI(i, j, 1)] = zj;
+            Rx[RI(i, j, 2)] = s2[a].x; Ry[RI(i, j, 2)] = s2[a].y; Rz[RI(i, j, 2)] = zj;
+            Rx[RI(i, j, 3)] = s3[a].x; Ry[RI(i, j, 3)] = s3[a].y; Rz[RI(i, j, 3)] = zj;
+            Rx[RI(i, j, 4)] = c[a].x; Ry[RI(i, j, 4)] = c[a].y; Rz[RI(i, j, 4)] = (j * 2 - 1) * rA;
+        }
+        if (rl[a] >= 0) { status[i * 5 + 2] = 1; res_nei[i * 7 + 2] = NA + 1 + (rl[a] - rep * NB); res_nei[i * 7 + 4] = rs[a] + 2; }
+        if (rcis[a] >= 0) { status[i * 5 + 3] = 1; res_nei[i * 7 + 3] = 1 + (rcis[a] - rep * NA); }
+    }
+    for (int b = 0; b < NB; b++) {
+        const int i = NA + 1 + b;
+        for (int j = 1; j <= 4; j++)
+            for (int k = 1; k <= 2; k++) {
+                int q = k == 1 ? (j == 1 ? 0 : j - 1) : (j == 1 ? 4 : j + 3);
+                Rx[RI(i, j, k)] = lig[(size_t)b * 24 + q * 3 + 0]; Ry[RI(i, j, k)] = lig[(size_t)b * 24 + q * 3 + 1]; Rz[RI(i, j, k)] = lig[(size_t)b * 24 + q * 3 + 2];
+            }
+        for (int s = 0; s < 3; s++)
+            if (lr[(size_t)b * 3 + s] >= 0) { status[i * 5 + s + 2] = 1; res_nei[i * 7 + s + 2] = 1 + (lr[(size_t)b * 3 + s] - rep * NA); }
+    }
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_packed(kmc_handle *h, double *rec_pose, double *lig_pose, int32_t *rec_lig, int32_t *rec_site, int32_t *rec_cis) {
+    if (!h) return KMC_ERR_INVALID;
+    int rc = select_device(h); if (rc) return rc;
+    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt;
+    CK(cudaStreamSynchronize(h->stream));
+    if (rec_pose) {
+        std::vector<double2> c(NAt), s2(NAt), s3(NAt);
+        CK(cudaMemcpy(c.data(), D.recC, sizeof(double2) * NAt, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(s2.data(), D.recS2, sizeof(double2) * NAt, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(s3.data(), D.recS3, sizeof(double2) * NAt, cudaMemcpyDeviceToHost));
+        for (int a = 0; a < NAt; a++) {
+            double *o = rec_pose + (size_t)a * 6;
+            o[0] = c[a].x; o[1] = c[a].y; o[2] = s2[a].x; o[3] = s2[a].y; o[4] = s3[a].x; o[5] = s3[a].y;
+        }
+    }
+    if (lig_pose) CK(cudaMemcpy(lig_pose, D.lig, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyDeviceToHost));
+    if (rec_lig) CK(cudaMemcpy(rec_lig, D.recLig, sizeof(int) * NAt, cudaMemcpyDeviceToHost));
+    if (rec_site) {
+        CK(cudaMemcpy(rec_site, D.recSite, sizeof(int) * NAt, cudaMemcpyDeviceToHost));
+        for (int a = 0; a < NAt; a++) rec_site[a] = rec_site[a] >= 0 ? rec_site[a] + 2 : 0;
+    }
+    if (rec_cis) CK(cudaMemcpy(rec_cis, D.recCis, sizeof(int) * NAt, cudaMemcpyDeviceToHost));
+    return KMC_OK;
+}
+
+extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const double *lig_pose, const int32_t *rec_lig,
+                              const int32_t *rec_site, const int32_t *rec_cis, int64_t step_done) {
+    if (!h || !rec_pose || !lig_pose) { if (h) h->err = "kmc_set_packed: null pose"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt, NA = h->NA, NB = h->NB;
+    std::vector<double2> c(NAt), s2(NAt), s3(NAt);
+    for (int a = 0; a < NAt; a++) {
+        const double *o = rec_pose + (size_t)a * 6;
+        c[a] = make_double2(o[0], o[1]); s2[a] = make_double2(o[2], o[3]); s3[a] = make_double2(o[4], o[5]);
+    }
+    std::vector<int> rl(NAt, -1), rs(NAt, -1), rcis(NAt, -1), lr((size_t)NBt * 3, -1);
+    for (int a = 0; a < NAt; a++) {
+        int l = rec_lig ? rec_lig[a] : -1, st = rec_site ? rec_site[a] : 0, cp = rec_cis ? rec_cis[a] : -1;
+        if (l >= 0) {
+            if (l >= NBt || l / NB != a / NA || st < 2 || st > 4 || lr[(size_t)l * 3 + st - 2] >= 0) { h->err = "kmc_set_packed: bad R-L bond at receptor " + std::to_string(a); return KMC_ERR_STATE; }
+            rl[a] = l; rs[a] = st - 2; lr[(size_t)l * 3 + st - 2] = a;
+        }
+        if (cp >= 0) {
+            if (cp >= NAt || cp == a || cp / NA != a / NA || !rec_cis || rec_cis[cp] != a) { h->err = "kmc_set_packed: bad cis bond at receptor " + std::to_string(a); return KMC_ERR_STATE; }
+            rcis[a] = cp;
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(D.recC, c.data(), sizeof(double2) * NAt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recS2, s2.data(), sizeof(double2) * NAt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recS3, s3.data(), sizeof(double2) * NAt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.lig, lig_pose, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recLig, rl.data(), sizeof(int) * NAt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recSite, rs.data(), sizeof(int) * NAt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.recCis, rcis.data(), sizeof(int) * NAt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D.ligRec, lr.data(), sizeof(int) * 3 * (size_t)NBt, cudaMemcpyHostToDevice));
+    int one = 1;
+    CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
+    h->step_done = step_done; h->stepped = false;
+    return KMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweep
+// ------------------------------------------------------------------------------------------------
+static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+__global__ void k_step_begin(const __grid_constant__ Args A) {
+    KARGS
+    // per-step scalar reset; complexes are rebuilt only if the bond table changed (S_TOPO_DIRTY)
+    D.scal[S_NFAR] = 0; D.scal[S_NUNKNOWN] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
+}
+__global__ void k_rebuild_gate_clear(const __grid_constant__ Args A) {
+    KARGS D.scal[S_TOPO_DIRTY] = 0; }
+__global__ void k_zero_unknown(const __grid_constant__ Args A) {
+    KARGS D.scal[S_NUNKNOWN] = 0; }
+
+extern "C" int kmc_step(kmc_handle *h, int64_t n) {
+    if (!h) return KMC_ERR_INVALID;
+    if (n < 0) { h->err = "kmc_step: negative step count"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    Dev &D = h->D; cudaStream_t st = h->stream;
+    const int B = 128, NT = h->NT, NAt = h->NAt, NBt = h->NBt;
+    for (int64_t it = 0; it < n; it++) {
+        const uint64_t step = (uint64_t)(h->step_done + 1);
+        const Args A{D, h->K};
+        k_step_begin<<<1, 1, 0, st>>>(A);
+        // S1 (gated on device: no host round trip)
+        k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A);
+        k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A);
+        k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A);
+        k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A);
+        k_rebuild_gate_clear<<<1, 1, 0, st>>>(A);
+        // S2 proposals
+        k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A, step);
+        k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A, step);
+        // grid
+        CK(cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st));
+        k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A);
+        k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.ncell + 1);
+        k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks);
+        k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1);
+        k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A);
+        h->launches += 14;
+        // S2g: resolve until every unit is decided
+        int scal[S_COUNT];
+        for (int pass = 0;; pass++) {
+            if (pass) { k_zero_unknown<<<1, 1, 0, st>>>(A); h->launches++; }
+            k_resolve<<<nblk(NT, B), B, 0, st>>>(A);
+            h->launches++; h->passes++;
+            CK(cudaMemcpyAsync(scal, D.scal, sizeof scal, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (scal[S_OVERFLOW]) { h->err = "device buffer overflow (mask " + std::to_string(scal[S_OVERFLOW]) + ")"; return KMC_ERR_CAPACITY; }
+            if (scal[S_NUNKNOWN] == 0) break;
+            if (pass > NT + 8) { h->err = "conflict resolution did not converge"; return KMC_ERR_CUDA; }
+        }
+        k_restore<<<nblk(NT, 256), 256, 0, st>>>(A);
+        // S3
+        k_react_candidates<<<nblk(std::max(NAt, 1), B), B, 0, st>>>(A, step);
+        k_react_resolve<<<1, 1024, 0, st>>>(A);
+        k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, step);
+        h->launches += 4;
+        // S4: the new buffers become the committed state
+        std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign);
+        h->step_done++; h->stepped = true;
+    }
+    CK(cudaGetLastError());
+    return KMC_OK;
+}
+
+extern "C" int kmc_sync(kmc_handle *h) {
+    if (!h) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaStreamSynchronize(h->stream));
+    int scal[S_COUNT];
+    CK(cudaMemcpy(scal, h->D.scal, sizeof scal, cudaMemcpyDeviceToHost));
+    if (scal[S_OVERFLOW]) { h->err = "device buffer overflow (mask " + std::to_string(scal[S_OVERFLOW]) + ")"; return KMC_ERR_CAPACITY; }
+    return KMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// outputs
+// ------------------------------------------------------------------------------------------------
+struct HostComplexes { std::vector<int> unitOf, cxSize, cxOff, rowWork; };
+static int fetch_complexes(kmc_handle *h, HostComplexes &hc) {
+    Dev &D = h->D;
+    hc.unitOf.resize(h->NT); hc.cxSize.resize(h->NBt); hc.cxOff.resize(h->NBt); hc.rowWork.resize(h->NT);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(hc.unitOf.data(), D.unitOf, sizeof(int) * h->NT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hc.cxSize.data(), D.cxSize, sizeof(int) * h->NBt, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hc.cxOff.data(), D.cxOff, sizeof(int) * h->NBt, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hc.rowWork.data(), D.rowWork, sizeof(int) * h->NT, cudaMemcpyDeviceToHost));
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_series(kmc_handle *h, int32_t rep, kmc_series *out) {
+    if (!h || !out) return KMC_ERR_INVALID;
+    if (rep < 0 || rep >= h->R) { h->err = "kmc_get_series: bad replica"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    Dev &D = h->D;
+    CK(cudaMemsetAsync(h->d_series, 0, sizeof(int) * 4 * h->R, h->stream));
+    const Args A{D, h->K};
+    k_series<<<nblk(std::max(h->NAt, 1), 256), 256, 0, h->stream>>>(A, h->d_series);
+    h->launches++;
+    int s4[4], mx = 0;
+    CK(cudaMemcpyAsync(s4, h->d_series + 4 * rep, sizeof s4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&mx, D.maxComplex + rep, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof *out);
+    out->step = h->step_done; out->bond_num_rl = s4[0]; out->bond_num_mono_cis = s4[1]; out->bond_num_cis = s4[2];
+    out->bond_num = s4[0] + s4[1] + s4[2]; out->max_complex = mx;
+    if (h->stepped) {
+        HostComplexes hc; rc = fetch_complexes(h, hc); if (rc) return rc;
+        for (int b = rep * h->NB; b < (rep + 1) * h->NB; b++)
+            if (hc.unitOf[h->NAt + b] == h->NAt + b && hc.cxSize[b] > 1) { out->n_complexes++; out->n_in_complexes += hc.cxSize[b]; }
+        if (out->n_complexes) out->cluster_size = (double)out->n_in_complexes / out->n_complexes;     // main.cpp:2200-2202
+    }
+    return KMC_OK;
+}
+
+extern "C" int64_t kmc_get_complexes(kmc_handle *h, int32_t rep, int32_t *row_len, int32_t *members, int64_t cap) {
+    if (!h || !row_len) return KMC_ERR_INVALID;
+    if (rep < 0 || rep >= h->R) { h->err = "kmc_get_complexes: bad replica"; return KMC_ERR_INVALID; }
+    if (!h->stepped) { h->err = "kmc_get_complexes: no completed step yet (the reference lists complexes of the last step)"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    HostComplexes hc; rc = fetch_complexes(h, hc); if (rc) return rc;
+    int64_t tot = 0;
+    auto ref_id_host = [&](int gid) { return gid < h->NAt ? gid % h->NA + 1 : h->NA + (gid - h->NAt) % h->NB + 1; };
+    for (int l = 0; l < h->NB; l++) {
+        int b = rep * h->NB + l;
+        if (hc.unitOf[h->NAt + b] != h->NAt + b) { row_len[l] = 0; continue; }
+        int size = hc.cxSize[b]; row_len[l] = size;
+        for (int i = 0; i < size; i++) {
+            int gid = size > 1 ? hc.rowWork[hc.cxOff[b] + i] : h->NAt + b;
+            if (members && tot < cap) members[tot] = ref_id_host(gid);
+            tot++;
+        }
+    }
+    return tot;
+}
+
+extern "C" int kmc_get_oligomer_hist(kmc_handle *h, int32_t rep, int64_t *hist, int32_t nbins) {
+    if (!h || !hist || nbins < 2) return KMC_ERR_INVALID;
+    if (rep >= h->R) { h->err = "kmc_get_oligomer_hist: bad replica"; return KMC_ERR_INVALID; }
+    if (!h->stepped) { h->err = "kmc_get_oligomer_hist: no completed step yet"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    HostComplexes hc; rc = fetch_complexes(h, hc); if (rc) return rc;
+    for (int i = 0; i < nbins; i++) hist[i] = 0;
+    int b0 = rep < 0 ? 0 : rep * h->NB, b1 = rep < 0 ? h->NBt : (rep + 1) * h->NB;
+    for (int b = b0; b < b1; b++)
+        if (hc.unitOf[h->NAt + b] == h->NAt + b) hist[std::min(hc.cxSize[b], nbins - 1)]++;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_accept(kmc_handle *h, int32_t rep, int32_t *accepted) {
+    if (!h || !accepted) return KMC_ERR_INVALID;
+    if (rep < 0 || rep >= h->R) { h->err = "kmc_get_accept: bad replica"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    std::vector<int> unitOf(h->NT); std::vector<unsigned char> st(h->NT);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(unitOf.data(), h->D.unitOf, sizeof(int) * h->NT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st.data(), h->D.unitState, h->NT, cudaMemcpyDeviceToHost));
+    accepted[0] = 1;
+    for (int a = 0; a < h->NA; a++) accepted[a + 1] = st[unitOf[rep * h->NA + a]] == U_ACCEPT;
+    for (int b = 0; b < h->NB; b++) accepted[h->NA + 1 + b] = st[unitOf[h->NAt + rep * h->NB + b]] == U_ACCEPT;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_events(kmc_handle *h, int64_t *ev) {
+    if (!h || !ev) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long d[EV_COUNT];
+    CK(cudaMemcpy(d, h->D.events, sizeof d, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < EV_COUNT; i++) ev[i] = (int64_t)d[i];
+    ev[EV_PASSES] = h->passes; ev[EV_LAUNCHES] = h->launches;
+    return KMC_OK;
+}
+
+// ---- the reference's output records ----
+extern "C" int kmc_write_bond_dat(kmc_handle *h, int32_t rep, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    kmc_series s; int rc = kmc_get_series(h, rep, &s); if (rc) return rc;
+    FILE *f = fopen(path, "a");
+    if (!f) { h->err = std::string("cannot open ") + path; return KMC_ERR_IO; }
+    // main.cpp:2249-2251: fixed, precision 3, widths 15 5 5 10 10 10 10
+    fprintf(f, "%15.3f%5d%5d%10d%10d%10.3f%10d\n", (double)s.step * h->P.dt, s.bond_num_rl, s.bond_num_mono_cis, s.bond_num_cis,
+            s.bond_num, s.cluster_size, s.max_complex);
+    fclose(f);
+    return KMC_OK;
+}
+extern "C" int kmc_write_cluster_log(kmc_handle *h, int32_t rep, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    std::vector<int32_t> len(h->NB), mem(h->N + 1);
+    int64_t tot = kmc_get_complexes(h, rep, len.data(), mem.data(), (int64_t)mem.size());
+    if (tot < 0) return (int)tot;
+    FILE *f = fopen(path, "a");
+    if (!f) { h->err = std::string("cannot open ") + path; return KMC_ERR_IO; }
+    // main.cpp:2293-2301: default ostream float format (%g), members followed by two blanks, one line per ligand
+    fprintf(f, "Hello Cluster!, t=%g\n", (double)h->step_done * h->P.dt);
+    int64_t o = 0;
+    for (int l = 0; l < h->NB; l++) {
+        for (int i = 0; i < len[l]; i++) fprintf(f, "%d  ", mem[o + i]);
+        o += len[l];
+        fputc('\n', f);
+    }
+    fclose(f);
+    return KMC_OK;
+}
+extern "C" int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, const char *dir) {
+    if (!h || !dir || output_every < 1) return KMC_ERR_INVALID;
+    std::string d(dir);
+    const int64_t end = h->step_done + n_steps;
+    while (h->step_done < end) {
+        int64_t next = std::min<int64_t>(end, (h->step_done / output_every + 1) * output_every);
+        int rc = kmc_step(h, next - h->step_done); if (rc) return rc;
+        if (h->step_done % output_every == 0)                                   // main.cpp:2247, 2291
+            for (int r = 0; r < h->R; r++) {
+                std::string suf = h->R > 1 ? "." + std::to_string(r) : "";
+                rc = kmc_write_bond_dat(h, r, (d + "/bond.dat" + suf).c_str()); if (rc) return rc;
+                rc = kmc_write_cluster_log(h, r, (d + "/cluster.log" + suf).c_str()); if (rc) return rc;
+            }
+    }
+    return KMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalable initial configuration (replaces the O(N^2) insertion of main.cpp:273-456)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// host-side cell grid (linked lists, about one molecule per cell) used only by the initial-configuration generator
+struct HostGrid {
+    double edge, x0, y0; int nx, ny; std::vector<int> head, next;
+    HostGrid(double Lx, double Ly, double reach, int n) : x0(-Lx / 2), y0(-Ly / 2) {
+        double e = std::max(reach, sqrt(Lx * Ly / std::max(n, 1)));
+        nx = std::max(1, (int)(Lx / e)); ny = std::max(1, (int)(Ly / e));
+        edge = std::max(Lx / nx, Ly / ny);
+        head.assign((size_t)nx * ny, -1); next.assign(std::max(n, 1), -1);
+    }
+    int cx(double x) const { return std::min(std::max((int)((x - x0) / edge), 0), nx - 1); }
+    int cy(double y) const { return std::min(std::max((int)((y - y0) / edge), 0), ny - 1); }
+    template <class F> bool any_near(double x, double y, F f) const {
+        int a = cx(x), b = cy(y);
+        for (int yy = std::max(b - 1, 0); yy <= std::min(b + 1, ny - 1); yy++)
+            for (int xx = std::max(a - 1, 0); xx <= std::min(a + 1, nx - 1); xx++)
+                for (int id = head[(size_t)yy * nx + xx]; id >= 0; id = next[id]) if (f(id)) return true;
+        return false;
+    }
+    void put(double x, double y, int id) { size_t c = (size_t)cy(y) * nx + cx(x); next[id] = head[c]; head[c] = id; }
+};
+}  // namespace
+
+extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_cells) {
+    if (!h) return KMC_ERR_INVALID;
+    const kmc_params &P = h->P;
+    const int NA = h->NA, NB = h->NB;
+    const double rs = P.rB * 2 / sqrt(3.0);
+    const double exRR = P.rA + P.rA, exRL = P.rA + rs + P.rB, exLL = rs + rs + 2 * P.rB;      // main.cpp:293, 368, 380
+    std::vector<double> rec((size_t)h->NAt * 6), lig((size_t)h->NBt * 24);
+    for (int rep = 0; rep < h->R; rep++) {
+        const uint64_t seed = init_seed + (uint64_t)rep;
+        uint32_t ctr = 0;
+        auto U = [&](uint32_t mol) { return keyed_uniform(seed, mol, ctr++, 0, SLOT_INIT); };
+        std::vector<double> ax(NA), ay(NA), bx(NB), by(NB), bz(NB);
+        HostGrid ga(P.box[0], P.box[1], exRR, NA), gb(P.box[0], P.box[1], exLL, NB), gab(P.box[0], P.box[1], exRL, NA);
+        for (int a = 0; a < NA; a++) {
+            for (int tries = 0;; tries++) {
+                if (tries > 100000) { h->err = "kmc_init_random: cannot place receptors (box too dense)"; return KMC_ERR_INVALID; }
+                double x = U(a + 1) * P.box[0] - P.box[0] / 2, y = U(a + 1) * P.box[1] - P.box[1] / 2;
+                bool clash = ga.any_near(x, y, [&](int j) { double dx = x - ax[j], dy = y - ay[j]; return sqrt(dx * dx + dy * dy) <= exRR; });
+                if (!clash) { ax[a] = x; ay[a] = y; ga.put(x, y, a); gab.put(x, y, a); break; }
+            }
+        }
+        for (int b = 0; b < NB; b++) {
+            for (int tries = 0;; tries++) {
+                if (tries > 100000) { h->err = "kmc_init_random: cannot place ligands (box too dense)"; return KMC_ERR_INVALID; }
+                double x = U(NA + b + 1) * P.box[0] - P.box[0] / 2, y = U(NA + b + 1) * P.box[1] - P.box[1] / 2, z = U(NA + b + 1) * P.box[2];
+                bool clash = gab.any_near(x, y, [&](int j) {
+                    for (int k = 0; k < 4; k++) { double dx = x - ax[j], dy = y - ay[j], dz = z - 2 * k * P.rA; if (sqrt(dx * dx + dy * dy + dz * dz) <= exRL) return true; }
+                    return false; });
+                clash = clash || gb.any_near(x, y, [&](int j) { double dx = x - bx[j], dy = y - by[j], dz = z - bz[j]; return sqrt(dx * dx + dy * dy + dz * dz) <= exLL; });
+                if (!clash) { bx[b] = x; by[b] = y; bz[b] = z; gb.put(x, y, b); break; }
+            }
+        }
+        // optional cell-major renumbering (memory locality of neighbour gathers on large membranes)
+        std::vector<int> oa(NA), ob(NB);
+        for (int i = 0; i < NA; i++) oa[i] = i;
+        for (int i = 0; i < NB; i++) ob[i] = i;
+        if (sort_cells) {
+            const Consts &K = h->K;
+            auto key = [&](double x, double y) {
+                long cx = (long)floor((x - K.gx0) * K.cellInv), cy = (long)floor((y - K.gy0) * K.cellInv);
+                return cy * (long)K.ncx + cx; };
+            std::stable_sort(oa.begin(), oa.end(), [&](int p, int q) { return key(ax[p], ay[p]) < key(ax[q], ay[q]); });
+            std::stable_sort(ob.begin(), ob.end(), [&](int p, int q) { return key(bx[p], by[p]) < key(bx[q], by[q]); });
+        }
+        for (int a = 0; a < NA; a++) {
+            const int src = oa[a];
+            const double psai = (2 * U(a + 1) - 1) * P.pai, x = ax[src], y = ay[src];
+            double *o = rec.data() + ((size_t)rep * NA + a) * 6;
+            o[0] = x; o[1] = y;
+            o[2] = cos(psai) * P.rA + x; o[3] = sin(psai) * P.rA + y;
+            o[4] = cos(psai) * (-P.rA) + x; o[5] = sin(psai) * (-P.rA) + y;
+        }
+        for (int b = 0; b < NB; b++) {
+            const int src = ob[b];
+            const double th = (2 * U(NA + b + 1) - 1) * P.pai, ph = (2 * U(NA + b + 1) - 1) * P.pai, ps = (2 * U(NA + b + 1) - 1) * P.pai;
+            const double t[3][3] = {{cos(ps) * cos(ph) - cos(th) * sin(ph) * sin(ps), -sin(ps) * cos(ph) - cos(th) * sin(ph) * cos(ps), sin(th) * sin(ph)},
+                                    {cos(ps) * sin(ph) + cos(th) * cos(ph) * sin(ps), -sin(ps) * sin(ph) + cos(th) * cos(ph) * cos(ps), -sin(th) * cos(ph)},
+                                    {sin(ps) * sin(th), cos(ps) * sin(th), cos(th)}};
+            const double rB = P.rB;
+            const double tpl[8][3] = {{0, 0, 0}, {0, rB * 2 / sqrt(3), 0}, {-rB, -rB / sqrt(3), 0}, {rB, -rB / sqrt(3), 0}, {0, 0, rB},
+                                      {0, rB * (2 / sqrt(3) + 1), 0}, {-rB * (sqrt(3) / 2 + 1), -rB / sqrt(3) - rB / 2, 0},
+                                      {rB * (sqrt(3) / 2 + 1), -rB / sqrt(3) - rB / 2, 0}};
+            double *o = lig.data() + ((size_t)rep * NB + b) * 24;
+            const double c[3] = {bx[src], by[src], bz[src]};
+            for (int q = 0; q < 8; q++)
+                for (int d = 0; d < 3; d++) o[q * 3 + d] = t[d][0] * tpl[q][0] + t[d][1] * tpl[q][1] + t[d][2] * tpl[q][2] + c[d];
+        }
+    }
+    int rc = kmc_set_packed(h, rec.data(), lig.data(), nullptr, nullptr, nullptr, 0);
+    if (rc) return rc;
+    std::vector<int> zero(h->R, 0);
+    CK(cudaMemcpy(h->D.maxComplex, zero.data(), sizeof(int) * h->R, cudaMemcpyHostToDevice));
+    return KMC_OK;
+}

@@ -1,0 +1,795 @@
+// csrc/kmc_kernels.cu -- hand-written sm_100a kernels of the per-timestep KMC sweep
+// (replaces /root/reference/main.cpp:461-2202).
+//
+//  step s:   [complexes]  k_uf_init -> k_uf_hook -> k_uf_flatten -> k_cx_build            (S1, 514-562; only when
+//                                                                                           the bond table changed)
+//            [propose]    k_propose_simple, k_propose_complex                              (S2a-S2f, 577-1732)
+//            [grid]       k_grid_count -> scan -> k_grid_scatter                           (cell list, new)
+//            [resolve]    k_resolve (repeated until no unit is undecided) -> k_restore     (S2g, 1759-1860 + ordering)
+//            [reactions]  k_react_candidates -> k_react_resolve -> k_dissociate            (S3, 1876-2141)
+//            pointer swap                                                                  (S4, 2164-2202)
+//
+// Sequential semantics in parallel: the reference sweeps molecules in index order and every overlap test
+// sees the already-updated positions of earlier molecules (Gauss-Seidel, main.cpp:577/642). A unit's
+// PROPOSAL depends only on its own old pose and its keyed draws, so all proposals are computed at once;
+// its accept/reject decision depends on earlier units only through their (rare) rejections, and is
+// resolved by a monotone fixed point: a unit is decided as soon as every earlier unit it could touch is.
+#include "kmc_device.cuh"
+
+namespace kmc {
+
+// kernel arguments: device pointers + constants travel by value in the kernel parameter bank
+struct Args { Dev D; Consts K; };
+#define KARGS const Dev &D = A.D; const Consts &cK = A.K; (void)D; (void)cK;
+
+// ------------------------------------------------------------------------------------------------
+// S1: complexes. Union-find over the bond graph; ligand uids are the low numbers so the root of a
+// ligand-containing component is its lowest-index ligand = the reference's BFS root (main.cpp:525).
+// ------------------------------------------------------------------------------------------------
+KD int uf_find(int *parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        int gp = parent[p];
+        if (gp != p) parent[x] = gp;   // path halving (benign race: only ever replaces by an ancestor)
+        x = p; p = gp;
+    }
+    return x;
+}
+KD void uf_union(int *parent, int a, int b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }          // hook the larger root under the smaller
+        int old = atomicCAS(&parent[b], b, a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+__global__ void k_uf_init(const __grid_constant__ Args A) {
+    KARGS
+    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cK.NT) return;
+    D.ufParent[i] = i; D.bfsMark[i] = 0;
+    if (i < cK.NBt) { D.cxSize[i] = 0; D.cxOff[i] = -1; }
+}
+// one thread per receptor: its ligand edge and (once per pair) its cis edge
+__global__ void k_uf_hook(const __grid_constant__ Args A) {
+    KARGS
+    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cK.NAt) return;
+    int ua = cK.NBt + a;
+    int l = D.recLig[a];
+    if (l >= 0) uf_union(D.ufParent, ua, l);
+    int c = D.recCis[a];
+    if (c > a) uf_union(D.ufParent, ua, cK.NBt + c);
+}
+__global__ void k_uf_flatten(const __grid_constant__ Args A) {
+    KARGS
+    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
+    int i = blockIdx.x * blockDim.x + threadIdx.x;   // uid
+    if (i >= cK.NT) return;
+    int r = uf_find(D.ufParent, i);
+    int gid = i < cK.NBt ? cK.NAt + i : i - cK.NBt;
+    int head = r < cK.NBt ? cK.NAt + r : r - cK.NBt;
+    D.unitOf[gid] = head;
+    if (r < cK.NBt) atomicAdd(&D.cxSize[r], 1);
+}
+// one thread per root ligand: breadth-first member order exactly as main.cpp:528-560
+// (receptor neighbours: its ligand then its cis partner; ligand neighbours: sites 2,3,4)
+__global__ void k_cx_build(const __grid_constant__ Args A) {
+    KARGS
+    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= cK.NBt) return;
+    if (D.unitOf[cK.NAt + h] != cK.NAt + h) return;
+    int size = D.cxSize[h];
+    atomicMax(&D.maxComplex[h / cK.NB], size);      // main.cpp:896-898
+    if (size <= 1) return;
+    int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
+    D.cxOff[h] = off;
+    D.cxRoots[atomicAdd(&D.scal[S_NCX], 1)] = h;
+    int *row = D.members + off;
+    int head = 0, tail = 0;
+    row[tail++] = cK.NAt + h; D.bfsMark[cK.NAt + h] = 1;
+    while (head < tail) {
+        int m = row[head++];
+        int cand[3], nc = 0;
+        if (m < cK.NAt) {
+            if (D.recLig[m] >= 0) cand[nc++] = cK.NAt + D.recLig[m];
+            if (D.recCis[m] >= 0) cand[nc++] = D.recCis[m];
+        } else {
+            int hh = m - cK.NAt;
+            for (int s = 0; s < 3; s++) if (D.ligRec[hh * 3 + s] >= 0) cand[nc++] = D.ligRec[hh * 3 + s];
+        }
+        for (int c = 0; c < nc; c++)
+            if (!D.bfsMark[cand[c]]) { D.bfsMark[cand[c]] = 1; if (tail < size) row[tail++] = cand[c]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2 proposals
+// ------------------------------------------------------------------------------------------------
+KD uint64_t seed_of(const Consts &cK, int replica) { return cK.seed + (uint64_t)replica; }
+
+KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny) {
+    double dx = nx - ox, dy = ny - oy;
+    D.farFlag[gid] = (dx * dx + dy * dy > cK.skin * cK.skin) ? 1 : 0;
+}
+
+// free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
+__global__ void k_propose_simple(const __grid_constant__ Args A, uint64_t step) {
+    KARGS
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= cK.NT) return;
+    if (D.unitOf[gid] != gid) return;             // not the head of a unit
+    const Consts &K = cK;
+    const int rep = replica_of_gid(K, gid);
+    const uint64_t seed = seed_of(cK, rep);
+    const uint32_t me = ref_id(K, gid);
+    if (gid < K.NAt) {
+        const int a = gid, p = D.recCis[a];
+        Rec ra = load_rec(D.recC, D.recS2, D.recS3, a);
+        const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
+                     u2 = keyed_uniform(seed, me, 0, step, 2);
+        const double phai = mul(mul(u1, 2.0), K.pai);
+        double sp, cp; sincos(phai, &sp, &cp);
+        if (p < 0) {
+            // ---- S2a ----
+            const double amp = mul(K.ampA, u0);
+            const double shx = mul(amp, cp), shy = mul(amp, sp);
+            Rec t = {add(ra.cx, shx), add(ra.cy, shy), add(ra.s2x, shx), add(ra.s2y, shy), add(ra.s3x, shx), add(ra.s3y, shy)};
+            const double PBx = mul(K.Lx, round(dvd(t.cx, K.Lx))), PBy = mul(K.Ly, round(dvd(t.cy, K.Ly)));
+            t.cx = sub(t.cx, PBx); t.s2x = sub(t.s2x, PBx); t.s3x = sub(t.s3x, PBx);
+            t.cy = sub(t.cy, PBy); t.s2y = sub(t.s2y, PBy); t.s3y = sub(t.s3y, PBy);
+            const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotA);
+            double ss, cs; sincos(psai, &ss, &cs);
+            Rec n; n.cx = t.cx; n.cy = t.cy;
+            rotz(cs, ss, t.s2x, t.s2y, t.cx, t.cy, n.s2x, n.s2y);
+            rotz(cs, ss, t.s3x, t.s3y, t.cx, t.cy, n.s3x, n.s3y);
+            store_rec(D.recCn, D.recS2n, D.recS3n, a, n);
+            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy);
+        } else {
+            // ---- S2b: this receptor is the lower index of a ligand-free cis pair ----
+            Rec rb = load_rec(D.recC, D.recS2, D.recS3, p);
+            const double amp = mul(K.ampCis, u0);
+            const double shx = mul(amp, cp), shy = mul(amp, sp);
+            Rec ta = {add(ra.cx, shx), add(ra.cy, shy), add(ra.s2x, shx), add(ra.s2y, shy), add(ra.s3x, shx), add(ra.s3y, shy)};
+            Rec tb = {add(rb.cx, shx), add(rb.cy, shy), add(rb.s2x, shx), add(rb.s2y, shy), add(rb.s3x, shx), add(rb.s3y, shy)};
+            const double PBx = mul(K.Lx, round(dvd(dvd(add(ta.cx, tb.cx), 2.0), K.Lx)));
+            const double PBy = mul(K.Ly, round(dvd(dvd(add(ta.cy, tb.cy), 2.0), K.Ly)));
+            ta.cx = sub(ta.cx, PBx); ta.s2x = sub(ta.s2x, PBx); ta.s3x = sub(ta.s3x, PBx);
+            ta.cy = sub(ta.cy, PBy); ta.s2y = sub(ta.s2y, PBy); ta.s3y = sub(ta.s3y, PBy);
+            tb.cx = sub(tb.cx, PBx); tb.s2x = sub(tb.s2x, PBx); tb.s3x = sub(tb.s3x, PBx);
+            tb.cy = sub(tb.cy, PBy); tb.s2y = sub(tb.s2y, PBy); tb.s3y = sub(tb.s3y, PBy);
+            const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotCis);
+            double ss, cs; sincos(psai, &ss, &cs);
+            // rotation centre from the PRE-translation bead centres, summed bead by bead (main.cpp:744-753)
+            double cmx = 0, cmy = 0;
+            for (int j = 0; j < 4; j++) { cmx = add(add(cmx, ra.cx), rb.cx); cmy = add(add(cmy, ra.cy), rb.cy); }
+            cmx = dvd(cmx, 8.0); cmy = dvd(cmy, 8.0);
+            Rec na, nb;
+            rotz(cs, ss, ta.cx, ta.cy, cmx, cmy, na.cx, na.cy);
+            rotz(cs, ss, ta.s2x, ta.s2y, cmx, cmy, na.s2x, na.s2y);
+            rotz(cs, ss, ta.s3x, ta.s3y, cmx, cmy, na.s3x, na.s3y);
+            rotz(cs, ss, tb.cx, tb.cy, cmx, cmy, nb.cx, nb.cy);
+            rotz(cs, ss, tb.s2x, tb.s2y, cmx, cmy, nb.s2x, nb.s2y);
+            rotz(cs, ss, tb.s3x, tb.s3y, cmx, cmy, nb.s3x, nb.s3y);
+            if (cis_misaligned(K, na, nb)) snap_cis(K, nb, na);          // "relax", main.cpp:770-799
+            store_rec(D.recCn, D.recS2n, D.recS3n, a, na);
+            store_rec(D.recCn, D.recS2n, D.recS3n, p, nb);
+            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy);
+            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy);
+        }
+        D.unitState[gid] = U_UNKNOWN;
+    } else {
+        const int h = gid - K.NAt;
+        if (D.cxSize[h] > 1) return;             // complexes: k_propose_complex
+        // ---- S2c ----
+        Lig l; load_lig(D.lig, h, l);
+        const double ox = l.p[0][0], oy = l.p[0][1];
+        const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
+                     u2 = keyed_uniform(seed, me, 0, step, 2), u3 = keyed_uniform(seed, me, 0, step, 3),
+                     u4 = keyed_uniform(seed, me, 0, step, 4), u5 = keyed_uniform(seed, me, 0, step, 5);
+        const double amp = mul(K.ampB, u0);
+        const double theta = mul(u1, K.pai), phai = mul(mul(u2, 2.0), K.pai);
+        double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
+        const double shx = mul(mul(amp, st), cp), shy = mul(mul(amp, st), sp), shz = mul(amp, ct);
+        for (int q = 0; q < 8; q++) { l.p[q][0] = add(l.p[q][0], shx); l.p[q][1] = add(l.p[q][1], shy); l.p[q][2] = add(l.p[q][2], shz); }
+        const double PBx = mul(K.Lx, round(dvd(l.p[0][0], K.Lx))), PBy = mul(K.Ly, round(dvd(l.p[0][1], K.Ly))),
+                     PBz = mul(K.Lz, round(dvd(l.p[0][2], K.Lz)));
+        if (l.p[0][2] > K.Lz || l.p[0][2] < 0)
+            for (int q = 0; q < 8; q++) l.p[q][2] = add(-l.p[q][2], mul(2.0, PBz));     // reflect, main.cpp:925-931
+        for (int q = 0; q < 8; q++) { l.p[q][0] = sub(l.p[q][0], PBx); l.p[q][1] = sub(l.p[q][1], PBy); }
+        const double rt = mul(sub(mul(2.0, u3), 1.0), K.rotB), rp = mul(sub(mul(2.0, u4), 1.0), K.rotB),
+                     rs = mul(sub(mul(2.0, u5), 1.0), K.rotB);
+        const Rot3 R3 = euler(rt, rp, rs);
+        Lig n;
+        const double c[3] = {l.p[0][0], l.p[0][1], l.p[0][2]};
+        for (int q = 0; q < 8; q++) rot3_about(R3, l.p[q], c, n.p[q]);
+        n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
+        store_lig(D.lign, h, n);
+        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1]);
+        D.unitState[gid] = U_UNKNOWN;
+    }
+}
+
+// ---- complexes: one thread per ligand-rooted complex with more than one member -------------------
+struct CxCtx {
+    const Dev &D; const Consts &K;
+    KD Rec rec(int a) const { return load_rec(D.recCn, D.recS2n, D.recS3n, a); }
+    KD void put(int a, const Rec &r) const { store_rec(D.recCn, D.recS2n, D.recS3n, a, r); }
+    KD void lig(int h, Lig &l) const { load_lig(D.lign, h, l); }
+    KD void put(int h, const Lig &l) const { store_lig(D.lign, h, l); }
+};
+
+// main.cpp:1296-1328 (also 1511-1545, 1651-1683): re-snap receptor a onto its ligand if misaligned
+KD bool resnap_rec_to_its_ligand(const CxCtx &C, int a) {
+    int h = C.D.recLig[a]; if (h < 0) return false;
+    int s = C.D.recSite[a];
+    Lig b; C.lig(h, b);
+    Rec r = C.rec(a);
+    if (!rl_misaligned(C.K, b, s, r)) return false;
+    snap_rec_to_lig(C.K, r, b, s); C.put(a, r);
+    return true;
+}
+// main.cpp:1548-1578, 1699-1728: re-snap the cis partner of a from a's axis if misaligned
+KD bool resnap_cis_partner(const CxCtx &C, int a, int a2) {
+    Rec r1 = C.rec(a), r2 = C.rec(a2);
+    if (!cis_misaligned(C.K, r1, r2)) return false;
+    snap_cis(C.K, r2, r1); C.put(a2, r2);
+    return true;
+}
+// body at `lable4`, main.cpp:1439-1585
+KD void reseat_ligand(const CxCtx &C, int h, int s, int a1) {
+    const Consts &K = C.K; const Dev &D = C.D;
+    D.movedFlag[K.NAt + h] = 1;
+    Lig b; C.lig(h, b);
+    Rec r = C.rec(a1);
+    const double zA = rec_bead_z(K, 3);
+    for (int q = 0; q < 8; q++) b.p[q][2] = zA;
+    b.p[4][2] = add(zA, K.rB);
+    const double ax1 = K.ghost[1 + s][0], ay1 = K.ghost[1 + s][1];
+    const double ax2 = sub(r.cx, r.s2x), ay2 = sub(r.cy, r.s2y);
+    const double dot = add(mul(ax1, ax2), mul(ay1, ay2)), det = sub(mul(ax1, ay2), mul(ay1, ax2));
+    const double angle = add(atan2(-det, -dot), K.pai);
+    const double cx = add(mul(K.fSeat, sub(r.s2x, r.cx)), r.s2x), cy = add(mul(K.fSeat, sub(r.s2y, r.cy)), r.s2y);
+    seat_ligand(K, b, angle, cx, cy);
+    C.put(h, b);
+    for (int m = 0; m < 3; m++) {
+        int am = D.ligRec[h * 3 + m];
+        if (am < 0) continue;
+        if (resnap_rec_to_its_ligand(C, am)) D.movedFlag[am] = 1;
+        int a2 = D.recCis[am];
+        if (a2 >= 0 && resnap_cis_partner(C, am, a2)) D.movedFlag[a2] = 1;
+    }
+}
+KD bool bridge_candidate(const CxCtx &C, int h, int s) {        // main.cpp:1420-1423
+    int a1 = C.D.ligRec[h * 3 + s]; if (a1 < 0) return false;
+    int a2 = C.D.recCis[a1]; if (a2 < 0) return false;
+    return C.D.recLig[a2] >= 0 && C.D.movedFlag[C.K.NAt + h] == 0;
+}
+KD bool lig_site_misaligned(const CxCtx &C, int h, int s, int a1) {
+    Lig b; C.lig(h, b); Rec r = C.rec(a1);
+    return rl_misaligned(C.K, b, s, r);
+}
+// std::random_shuffle(&row[1], &row[size]) with rand() (libstdc++): the last member never moves (main.cpp:1285)
+KD void shuffle_row(int *row, int size, uint64_t seed, uint32_t root, uint32_t &cnt, uint64_t step) {
+    int n = size - 1;
+    for (int i = 1; i < n; i++) {
+        int j = keyed_rand31(seed, root, cnt++, step) % (i + 1);
+        if (i != j) { int t = row[i]; row[i] = row[j]; row[j] = t; }
+    }
+}
+
+__global__ void k_propose_complex(const __grid_constant__ Args A, uint64_t step) {
+    KARGS
+    int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= D.scal[S_NCX]) return;
+    const Consts &K = cK;
+    const int h0 = D.cxRoots[ci], rootGid = K.NAt + h0;
+    const int size = D.cxSize[h0];
+    const int *rowIn = D.members + D.cxOff[h0];
+    int *row = D.rowWork + D.cxOff[h0];
+    const int rep = h0 / K.NB;
+    const uint64_t seed = seed_of(cK, rep);
+    const uint32_t me = ref_id(K, rootGid);
+    CxCtx C{D, K};
+    int nA = 0, nB = 0;
+    for (int i = 0; i < size; i++) { int m = rowIn[i]; row[i] = m; D.movedFlag[m] = 0; if (m < K.NAt) nA++; else nB++; }
+    const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
+                 u2 = keyed_uniform(seed, me, 0, step, 2);
+    // ---- S2d rigid move (main.cpp:974-1131); complexes with >= 2 ligands have D = 0 but still draw ----
+    const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
+    const double phai = mul(mul(u1, 2.0), K.pai);
+    double sp, cp; sincos(phai, &sp, &cp);
+    const double shx = mul(amp, cp), shy = mul(amp, sp);
+    double PBx = 0, PBy = 0;
+    for (int i = 0; i < size; i++) {
+        int m = row[i];
+        if (m < K.NAt) {
+            Rec r = load_rec(D.recC, D.recS2, D.recS3, m);
+            r.cx = add(r.cx, shx); r.s2x = add(r.s2x, shx); r.s3x = add(r.s3x, shx);
+            r.cy = add(r.cy, shy); r.s2y = add(r.s2y, shy); r.s3y = add(r.s3y, shy);
+            C.put(m, r); PBx = add(PBx, r.cx); PBy = add(PBy, r.cy);
+        } else {
+            Lig l; load_lig(D.lig, m - K.NAt, l);
+            for (int q = 0; q < 8; q++) { l.p[q][0] = add(l.p[q][0], shx); l.p[q][1] = add(l.p[q][1], shy); }
+            C.put(m - K.NAt, l); PBx = add(PBx, l.p[0][0]); PBy = add(PBy, l.p[0][1]);
+        }
+    }
+    PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
+    PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
+    double cmx = 0, cmy = 0, cmz = 0;
+    for (int i = 0; i < size; i++) {
+        int m = row[i];
+        if (m < K.NAt) {
+            Rec r = C.rec(m);
+            r.cx = sub(r.cx, PBx); r.s2x = sub(r.s2x, PBx); r.s3x = sub(r.s3x, PBx);
+            r.cy = sub(r.cy, PBy); r.s2y = sub(r.s2y, PBy); r.s3y = sub(r.s3y, PBy);
+            C.put(m, r);
+            for (int j = 1; j <= 4; j++) { cmx = add(cmx, r.cx); cmy = add(cmy, r.cy); cmz = add(cmz, rec_bead_z(K, j)); }
+        } else {
+            Lig l; C.lig(m - K.NAt, l);
+            for (int q = 0; q < 8; q++) { l.p[q][0] = sub(l.p[q][0], PBx); l.p[q][1] = sub(l.p[q][1], PBy); }
+            C.put(m - K.NAt, l);
+            for (int q = 0; q < 4; q++) { cmx = add(cmx, l.p[q][0]); cmy = add(cmy, l.p[q][1]); cmz = add(cmz, l.p[q][2]); }
+        }
+    }
+    const double nbeads = (double)(4 * nA + 4 * nB);
+    cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
+    const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
+    double ss, cs; sincos(psai, &ss, &cs);
+    int lastA = -1;
+    for (int i = 0; i < size; i++) {
+        int m = row[i];
+        if (m < K.NAt) {
+            Rec t = C.rec(m), n;
+            rotz(cs, ss, t.cx, t.cy, cmx, cmy, n.cx, n.cy);
+            rotz(cs, ss, t.s2x, t.s2y, cmx, cmy, n.s2x, n.s2y);
+            rotz(cs, ss, t.s3x, t.s3y, cmx, cmy, n.s3x, n.s3y);
+            C.put(m, n); lastA = m;
+        } else {
+            Lig l; C.lig(m - K.NAt, l);
+            for (int q = 0; q < 8; q++) {
+                double nx, ny; rotz(cs, ss, l.p[q][0], l.p[q][1], cmx, cmy, nx, ny);
+                l.p[q][0] = nx; l.p[q][1] = ny;
+                l.p[q][2] = add(sub(l.p[q][2], cmz), cmz);        // 1*(z-c)+c, main.cpp:1123
+            }
+            C.put(m - K.NAt, l);
+        }
+    }
+    if (nB == 1) {
+        // ---- S2e (main.cpp:1138-1274) ----
+        const int h = h0;
+        Lig b; C.lig(h, b);
+        if (b.p[4][2] != add(b.p[0][2], K.rB)) {                  // exact compare: first time only
+            const double zA = rec_bead_z(K, 3);                   // R_z_new[lastA][3][1]
+            for (int q = 0; q < 8; q++) b.p[q][2] = zA;
+            b.p[4][2] = add(zA, K.rB);
+            const double angle = add(atan2(sub(b.p[1][0], b.p[0][0]), sub(b.p[1][1], b.p[0][1])), K.pai);
+            seat_ligand(K, b, angle, b.p[0][0], b.p[0][1]);
+            C.put(h, b);
+        }
+        (void)lastA;
+        for (int s = 0; s < 3; s++) { int a1 = D.ligRec[h * 3 + s]; if (a1 >= 0) resnap_rec_to_its_ligand(C, a1); }
+        for (int s = 0; s < 3; s++) {
+            int a1 = D.ligRec[h * 3 + s];
+            if (a1 >= 0 && D.recCis[a1] >= 0) resnap_cis_partner(C, a1, D.recCis[a1]);
+        }
+    } else {
+        // ---- S2f (main.cpp:1284-1732) ----
+        uint32_t cnt = 0;
+        shuffle_row(row, size, seed, me, cnt, step);                       // pass 0
+        for (int i = 0; i < size; i++) { int a = row[i]; if (a < K.NAt && resnap_rec_to_its_ligand(C, a)) D.movedFlag[a] = 1; }
+        shuffle_row(row, size, seed, me, cnt, step);                       // pass 1
+        for (int i = 0; i < size; i++) {
+            int a = row[i];
+            if (a < K.NAt && D.recLig[a] >= 0 && D.recCis[a] >= 0 && D.recLig[D.recCis[a]] >= 0 && D.movedFlag[a] == 0) {
+                int a2 = D.recCis[a];
+                D.movedFlag[a] = 1; D.movedFlag[a2] = 1;
+                Rec r1 = C.rec(a), r2 = C.rec(a2);
+                if (cis_misaligned(K, r1, r2)) { snap_cis(K, r1, r2); C.put(a, r1); }   // a rebuilt FROM a2, 1390-1400
+            }
+        }
+        // passes 2 and 3; pass 3 re-enters pass 2's innermost block (goto lable4, main.cpp:1628 -> 1438)
+        bool resume = false; int i = 0, s = 0, h = 0, a1 = 0;
+        for (;;) {
+            if (!resume) { shuffle_row(row, size, seed, me, cnt, step); i = 0; }
+            for (; i < size; i++) {
+                if (row[i] < K.NAt) continue;
+                if (!resume) { h = row[i] - K.NAt; s = 0; }
+                for (; s < 3; s++) {
+                    bool run;
+                    if (resume) { run = true; resume = false; }
+                    else {
+                        run = false;
+                        if (bridge_candidate(C, h, s)) { a1 = D.ligRec[h * 3 + s]; run = lig_site_misaligned(C, h, s, a1); }
+                    }
+                    if (run) reseat_ligand(C, h, s, a1);
+                }
+            }
+            shuffle_row(row, size, seed, me, cnt, step);                   // pass 3
+            for (i = 0; i < size; i++) {
+                if (row[i] < K.NAt) continue;
+                h = row[i] - K.NAt;
+                for (s = 0; s < 3; s++)
+                    if (bridge_candidate(C, h, s)) {
+                        a1 = D.ligRec[h * 3 + s];
+                        if (lig_site_misaligned(C, h, s, a1)) { resume = true; break; }
+                    }
+                if (resume) break;
+            }
+            if (!resume) break;
+        }
+        for (int q = 0; q < size; q++) { int a = row[q]; if (a < K.NAt && resnap_rec_to_its_ligand(C, a)) D.movedFlag[a] = 1; }   // pass 4
+        for (int q = 0; q < size; q++) {                                                                                        // pass 5
+            int a = row[q];
+            if (a < K.NAt && D.recLig[a] >= 0 && D.recCis[a] >= 0 && D.recLig[D.recCis[a]] < 0) resnap_cis_partner(C, a, D.recCis[a]);
+        }
+    }
+    for (int q = 0; q < size; q++) {
+        int m = row[q];
+        if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
+        else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
+    }
+    D.unitState[rootGid] = U_UNKNOWN;
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbour grid: counting sort of molecule centres by cell (old centre; far movers get a second,
+// "ghost" entry at their proposed centre so that a fixed 3x3 search is exact)
+// ------------------------------------------------------------------------------------------------
+KD void centre_of(const Consts &cK, const Dev &D, int gid, bool nxt, double &x, double &y) {
+    if (gid < cK.NAt) { double2 c = nxt ? D.recCn[gid] : D.recC[gid]; x = c.x; y = c.y; }
+    else { const double *p = (nxt ? D.lign : D.lig) + (size_t)(gid - cK.NAt) * 24; x = p[0]; y = p[1]; }
+}
+__global__ void k_grid_count(const __grid_constant__ Args A) {
+    KARGS
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= cK.NT) return;
+    int rep = replica_of_gid(cK, gid);
+    double x, y; centre_of(cK, D, gid, false, x, y);
+    int c = cell_of(cK, rep, x, y);
+    D.molSlot[gid] = atomicAdd(&D.cellCount[c], 1);
+    if (D.farFlag[gid]) {
+        centre_of(cK, D, gid, true, x, y);
+        int c2 = cell_of(cK, rep, x, y);
+        int slot = atomicAdd(&D.cellCount[c2], 1);
+        int f = atomicAdd(&D.scal[S_NFAR], 1);
+        D.farList[f] = make_int4(gid, c2, slot, 0);
+    }
+}
+__global__ void k_grid_scatter(const __grid_constant__ Args A) {
+    KARGS
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < cK.NT) {
+        int rep = replica_of_gid(cK, gid);
+        double x, y; centre_of(cK, D, gid, false, x, y);
+        int c = cell_of(cK, rep, x, y);
+        D.sorted[D.cellStart[c] + D.molSlot[gid]] = gid;
+    }
+    if (gid < D.scal[S_NFAR]) { int4 f = D.farList[gid]; D.sorted[D.cellStart[f.y] + f.z] = f.x | GHOST_BIT; }
+}
+// exclusive scan of cellCount[0..n) into cellStart[0..n], three phases (reduce, scan of block sums, downsweep)
+#define SCAN_TILE 2048
+__global__ void k_scan_reduce(const int *in, int *blockSums, int n) {
+    __shared__ int sh[32];
+    int base = blockIdx.x * SCAN_TILE, s = 0;
+    for (int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x) if (base + i < n) s += in[base + i];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
+        for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) blockSums[blockIdx.x] = s;
+    }
+}
+__global__ void k_scan_sums(int *blockSums, int nb, int *total) {     // single block
+    __shared__ int carry; __shared__ int sh[1024];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        int i = base + threadIdx.x, v = i < nb ? blockSums[i] : 0;
+        sh[threadIdx.x] = v; __syncthreads();
+        for (int o = 1; o < blockDim.x; o <<= 1) {
+            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0; __syncthreads();
+            sh[threadIdx.x] += t; __syncthreads();
+        }
+        if (i < nb) blockSums[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void k_scan_down(const int *in, const int *blockSums, int *out, int n) {
+    __shared__ int sh[256]; __shared__ int carry;
+    int base = blockIdx.x * SCAN_TILE;
+    if (threadIdx.x == 0) carry = blockSums[blockIdx.x];
+    __syncthreads();
+    for (int t = 0; t < SCAN_TILE; t += blockDim.x) {
+        int i = base + t + threadIdx.x, v = i < n ? in[i] : 0;
+        sh[threadIdx.x] = v; __syncthreads();
+        for (int o = 1; o < blockDim.x; o <<= 1) {
+            int u = threadIdx.x >= o ? sh[threadIdx.x - o] : 0; __syncthreads();
+            sh[threadIdx.x] += u; __syncthreads();
+        }
+        if (i < n) out[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2g with ordering: decide accept/reject of every unit
+// ------------------------------------------------------------------------------------------------
+struct Probe { bool rec; double cx, cy; Lig l; };   // a member of the unit under test at its PROPOSED pose
+
+template <class F> KD void for_cells3x3(const Consts &cK, int rep, double x, double y, const Dev &D, F f) {
+    int cx = (int)floor((x - cK.gx0) * cK.cellInv), cy = (int)floor((y - cK.gy0) * cK.cellInv);
+    cx = min(max(cx, 0), cK.ncx - 1); cy = min(max(cy, 0), cK.ncy - 1);
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, cK.ncy - 1); yy++) {
+        int c0 = (rep * cK.ncy + yy) * cK.ncx + max(cx - 1, 0), c1 = (rep * cK.ncy + yy) * cK.ncx + min(cx + 1, cK.ncx - 1);
+        int e0 = D.cellStart[c0], e1 = D.cellStart[c1 + 1];       // the three cells of a row are contiguous
+        for (int e = e0; e < e1; e++) f(D.sorted[e]);
+    }
+}
+// does probe (proposed pose of member m) overlap molecule v taken at its old (nxt=false) or proposed pose?
+KD bool probe_hits(const Consts &K, const Dev &D, const Probe &P, int v, bool nxt) {
+    if (v < K.NAt) {
+        double2 c = nxt ? D.recCn[v] : D.recC[v];
+        if (P.rec) return hit_rec_rec(K, P.cx, P.cy, c.x, c.y);
+        double dx = c.x - P.cx, dy = c.y - P.cy;
+        if (dx * dx + dy * dy > K.reachRL * K.reachRL) return false;
+        return hit_rec_lig(K, c.x, c.y, P.l);
+    }
+    const double *base = nxt ? D.lign : D.lig;
+    const double *pc = base + (size_t)(v - K.NAt) * 24;
+    double dx = pc[0] - P.cx, dy = pc[1] - P.cy, r = P.rec ? K.reachRL : K.reachLL;
+    if (dx * dx + dy * dy > r * r) return false;
+    Lig o; load_lig_beads(base, v - K.NAt, o);
+    return P.rec ? hit_rec_lig(K, P.cx, P.cy, o) : hit_lig_lig(K, o, P.l);
+}
+
+// order of the sweep: true if unit head `v` is processed before unit head `u`
+KD bool unit_before(int v, int u) { return v < u; }
+
+// one member against everything around it; returns flags: bit0 definite overlap, bit1 overlap depends on an undecided earlier unit
+KD int test_member(const Consts &cK, const Dev &D, int u, int m, const Probe &P, int rep) {
+    int res = 0;
+    for_cells3x3(cK, rep, P.cx, P.cy, D, [&](int e) {
+        if (res & 1) return;
+        const bool ghost = (e & GHOST_BIT) != 0;
+        const int v = e & ~GHOST_BIT;
+        if (v == m) return;
+        const int uv = D.unitOf[v];
+        const bool far = D.farFlag[v] != 0;
+        if (uv == u) {                                   // co-moving member: proposed pose, once (Q20)
+            if (ghost != far) return;
+            if (probe_hits(cK, D, P, v, true)) res |= 1;
+        } else if (!unit_before(uv, u)) {                // later unit: still at its old pose
+            if (!ghost && probe_hits(cK, D, P, v, false)) res |= 1;
+        } else {                                         // earlier unit: new pose if it was accepted
+            const unsigned char s = ((volatile unsigned char *)D.unitState)[uv];
+            if (ghost) {
+                if (s != U_REJECT && probe_hits(cK, D, P, v, true)) res |= (s == U_ACCEPT) ? 1 : 2;
+            } else {
+                const bool hitOld = (s != U_ACCEPT) && probe_hits(cK, D, P, v, false);
+                const bool hitNew = (s != U_REJECT) && !far && probe_hits(cK, D, P, v, true);
+                if (s == U_ACCEPT) { if (hitNew) res |= 1; }
+                else if (s == U_REJECT) { if (hitOld) res |= 1; }
+                else if (hitOld && hitNew) res |= 1;
+                else if (hitOld || hitNew) res |= 2;
+            }
+        }
+    });
+    return res;
+}
+
+__global__ void k_resolve(const __grid_constant__ Args A) {
+    KARGS
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= cK.NT) return;
+    if (D.unitOf[gid] != gid || D.unitState[gid] != U_UNKNOWN) return;
+    const Consts &K = cK;
+    const int rep = replica_of_gid(K, gid);
+    int res = 0;
+    Probe P;
+    if (gid < K.NAt) {
+        double2 c = D.recCn[gid];
+        P.rec = true; P.cx = c.x; P.cy = c.y;
+        res |= test_member(cK, D, gid, gid, P, rep);
+        int p = D.recCis[gid];
+        if (p >= 0 && !(res & 1)) { c = D.recCn[p]; P.cx = c.x; P.cy = c.y; res |= test_member(cK, D, gid, p, P, rep); }
+    } else {
+        const int h = gid - K.NAt, size = D.cxSize[h];
+        if (size <= 1) {
+            P.rec = false; load_lig_beads(D.lign, h, P.l); P.cx = P.l.p[0][0]; P.cy = P.l.p[0][1];
+            res |= test_member(cK, D, gid, gid, P, rep);
+        } else {
+            const int *row = D.rowWork + D.cxOff[h];
+            for (int i = 0; i < size && !(res & 1); i++) {
+                int m = row[i];
+                if (m < K.NAt) { double2 c = D.recCn[m]; P.rec = true; P.cx = c.x; P.cy = c.y; }
+                else { P.rec = false; load_lig_beads(D.lign, m - K.NAt, P.l); P.cx = P.l.p[0][0]; P.cy = P.l.p[0][1]; }
+                res |= test_member(cK, D, gid, m, P, rep);
+            }
+        }
+    }
+    if (res & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); }
+    else if (res & 2) atomicAdd(&D.scal[S_NUNKNOWN], 1);
+    else D.unitState[gid] = U_ACCEPT;
+}
+
+// revert the members of rejected units (main.cpp:666-674, 851-863, 1831-1860)
+__global__ void k_restore(const __grid_constant__ Args A) {
+    KARGS
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= cK.NT) return;
+    if (D.unitState[D.unitOf[gid]] != U_REJECT) return;
+    if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
+    else {
+        const double2 *s = reinterpret_cast<const double2 *>(D.lig + (size_t)(gid - cK.NAt) * 24);
+        double2 *d = reinterpret_cast<double2 *>(D.lign + (size_t)(gid - cK.NAt) * 24);
+        for (int q = 0; q < 12; q++) d[q] = s[q];
+    }
+    D.farFlag[gid] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S3 reactions
+// ------------------------------------------------------------------------------------------------
+// entry validity after k_restore: a molecule is at its old-cell entry unless it is a far mover, then at its ghost
+KD bool entry_live(const Dev &D, int e) { return ((e & GHOST_BIT) != 0) == (D.farFlag[e & ~GHOST_BIT] != 0); }
+
+// one thread per receptor: geometric candidates whose keyed draw succeeds are appended (a failed draw never
+// changes anything, main.cpp:1921/1987/2041), ordered resolution happens in k_react_resolve
+__global__ void k_react_candidates(const __grid_constant__ Args A, uint64_t step) {
+    KARGS
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cK.NAt) return;
+    const Consts &K = cK;
+    const bool freeRL = D.recLig[a] < 0, freeCis = D.recCis[a] < 0;
+    if (!freeRL && !freeCis) return;
+    const int rep = a / K.NA;
+    const uint64_t seed = seed_of(cK, rep);
+    const uint32_t me = ref_id(K, a);
+    const Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
+    for_cells3x3(cK, rep, ra.cx, ra.cy, D, [&](int e) {
+        if (!entry_live(D, e)) return;
+        const int v = e & ~GHOST_BIT;
+        if (v >= K.NAt) {
+            if (!freeRL) return;
+            const int h = v - K.NAt;
+            const double *pc = D.lign + (size_t)h * 24;
+            double dx = pc[0] - ra.cx, dy = pc[1] - ra.cy;
+            if (dx * dx + dy * dy > K.reachOn * K.reachOn) return;
+            int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
+            if (occ[0] >= 0 && occ[1] >= 0 && occ[2] >= 0) return;
+            Lig b; load_lig(D.lign, h, b);
+            for (int s = 0; s < 3; s++) {
+                if (occ[s] >= 0 || !rl_geometry_ok(K, ra, b, s)) continue;
+                const uint32_t j = ref_id(K, v);
+                if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
+                    int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
+                    if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
+                    else atomicOr(&D.scal[S_OVERFLOW], 1);
+                }
+            }
+        } else {
+            if (!freeCis || v == a || D.recCis[v] >= 0) return;
+            const Rec rb = load_rec(D.recCn, D.recS2n, D.recS3n, v);
+            if (!cis_geometry_ok(K, ra, rb)) return;
+            const uint32_t j = ref_id(K, v);
+            const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
+            const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
+            if (okMono || okCis) {
+                int q = atomicAdd(&D.scal[S_NCAND_CIS], 1);
+                if (q < D.candCap) D.candCis[q] = ((unsigned long long)a << 32) | ((unsigned long long)v << 2) | (okMono ? 1u : 0u) | (okCis ? 2u : 0u);
+                else atomicOr(&D.scal[S_OVERFLOW], 2);
+            }
+        }
+    });
+}
+
+// single CTA: order the successful candidates as the reference's loops would meet them, then apply them
+// first-come-first-served (main.cpp:1877-1949, 1952-2003, 2007-2058)
+__global__ void k_react_resolve(const __grid_constant__ Args A) {
+    KARGS
+    unsigned long long *rl = D.candRL, *cis = D.candCis;
+    const int nRL = min(D.scal[S_NCAND_RL], D.candCap), nCis = min(D.scal[S_NCAND_CIS], D.candCap);
+    // ---- rank sort (n = successful draws of one step, tiny in practice; O(n^2/threads)) ----
+    for (int pass = 0; pass < 2; pass++) {
+        unsigned long long *k = pass == 0 ? rl : cis;
+        int n = pass == 0 ? nRL : nCis;
+        unsigned long long *tmp = k + D.candCap;        // second half of the buffer is scratch
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            unsigned long long me = k[t]; int rank = 0;
+            for (int q = 0; q < n; q++) { unsigned long long o = k[q]; rank += (o < me) || (o == me && q < t); }
+            tmp[rank] = me;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) k[t] = tmp[t];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    int ev_rl = 0, ev_mono = 0, ev_cis = 0;
+    for (int q = 0; q < nRL; q++) {
+        unsigned long long key = rl[q];
+        int a = (int)(key >> 32), h = (int)((key & 0xffffffffULL) >> 2), s = (int)(key & 3);
+        if (D.recLig[a] < 0 && D.ligRec[h * 3 + s] < 0) {
+            D.recLig[a] = h; D.recSite[a] = s; D.ligRec[h * 3 + s] = a; ev_rl++;
+        }
+    }
+    for (int variant = 1; variant <= 2; variant++)
+        for (int q = 0; q < nCis; q++) {
+            unsigned long long key = cis[q];
+            if (!(key & (unsigned)variant)) continue;
+            int a = (int)(key >> 32), b = (int)((key & 0xffffffffULL) >> 2);
+            if (D.recCis[a] >= 0 || D.recCis[b] >= 0) continue;
+            bool anyLig = D.recLig[a] >= 0 || D.recLig[b] >= 0;
+            if ((variant == 1) == anyLig) continue;      // variant 1: both ligand-free; variant 2: at least one bound
+            D.recCis[a] = b; D.recCis[b] = a;
+            if (variant == 1) ev_mono++; else ev_cis++;
+        }
+    if (ev_rl | ev_mono | ev_cis) {
+        D.scal[S_TOPO_DIRTY] = 1;
+        D.events[EV_RL_ON] += ev_rl; D.events[EV_MONO_ON] += ev_mono; D.events[EV_CIS_ON] += ev_cis;
+    }
+}
+
+// S3c, main.cpp:2062-2141. Keyed draws make the three sequential loops order free: a thread owns the R-L bond of
+// its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L outcome from the
+// partner's own keyed draw instead of waiting for it.
+__global__ void k_dissociate(const __grid_constant__ Args A, uint64_t step) {
+    KARGS
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cK.NAt) return;
+    const Consts &K = cK;
+    const int rep = a / K.NA;
+    const uint64_t seed = seed_of(cK, rep);
+    const int h = D.recLig[a], p = D.recCis[a];
+    if (h < 0 && p < 0) return;
+    const uint32_t me = ref_id(K, a);
+    bool boundAfter = false;
+    if (h >= 0) {
+        if (keyed_uniform(seed, me, 0, step, SLOT_RL_OFF) < K.pOff) {
+            int s = D.recSite[a];
+            D.recLig[a] = -1; D.recSite[a] = -1; D.ligRec[h * 3 + s] = -1;
+            atomicAdd(&D.events[EV_RL_OFF], 1ULL); D.scal[S_TOPO_DIRTY] = 1;
+        } else boundAfter = true;
+    }
+    if (p > a) {
+        const uint32_t pid = ref_id(K, p);
+        // partner's ligand state after ITS R-L dissociation trial: -1 already cleared, else apply its draw
+        bool pBoundAfter = D.recLig[p] >= 0 && !(keyed_uniform(seed, pid, 0, step, SLOT_RL_OFF) < K.pOff);
+        bool inComplex = boundAfter || pBoundAfter;
+        uint32_t slot = inComplex ? SLOT_CIS_OFF : SLOT_MONO_CIS_OFF;
+        double P = inComplex ? K.pCisOff : K.pMonoCisOff;
+        // drawn from both ends: the lower index first, the partner only if the bond survived
+        if (keyed_uniform(seed, me, 0, step, slot) < P || keyed_uniform(seed, pid, 0, step, slot) < P) {
+            D.recCis[a] = -1; D.recCis[p] = -1;
+            atomicAdd(&D.events[inComplex ? EV_CIS_OFF : EV_MONO_OFF], 1ULL); D.scal[S_TOPO_DIRTY] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// outputs (bond.dat columns, main.cpp:2251)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_series(const __grid_constant__ Args A, int *out /*[R][4]: rl, mono, cis, -*/) {
+    KARGS
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cK.NAt) return;
+    int rep = a / cK.NA;
+    if (D.recLig[a] >= 0) atomicAdd(&out[rep * 4 + 0], 1);
+    int p = D.recCis[a];
+    if (p > a) atomicAdd(&out[rep * 4 + ((D.recLig[a] >= 0 || D.recLig[p] >= 0) ? 2 : 1)], 1);
+}
+
+}  // namespace kmc

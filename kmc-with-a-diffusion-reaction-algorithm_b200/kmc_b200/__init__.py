@@ -1,0 +1,208 @@
+"""kmc_b200 -- thin ctypes binding of libkmc_b200.so (C ABI in include/kmc_b200.h).
+
+This is plumbing for tests and bench.py: the product is the shared library. There is no Python or CPU
+implementation of the sweep here; if the library or a B200 is missing every call fails loudly.
+"""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "libkmc_b200.so")
+
+MODE_REPLAY, MODE_PRODUCTION = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [("box", C.c_double * 3), ("dt", C.c_double), ("pai", C.c_double),
+                ("rA", C.c_double), ("DA", C.c_double), ("DrotA", C.c_double),
+                ("rB", C.c_double), ("DB", C.c_double), ("DrotB", C.c_double),
+                ("mono_cis_on", C.c_double), ("mono_cis_off", C.c_double),
+                ("cis_D", C.c_double), ("cis_Drot", C.c_double), ("cis_on", C.c_double), ("cis_off", C.c_double),
+                ("bond_D", C.c_double), ("bond_Drot", C.c_double), ("on", C.c_double), ("off", C.c_double),
+                ("bond_dist_cut", C.c_double), ("thetapd_cut", C.c_double), ("thetaot_cut", C.c_double),
+                ("cis_thetaot_cut", C.c_double), ("cis_dist_cut", C.c_double),
+                ("n_receptor", C.c_int32), ("n_ligand", C.c_int32), ("n_replicas", C.c_int32), ("mode", C.c_int32),
+                ("seed", C.c_uint64), ("cell_edge", C.c_double), ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Series(C.Structure):
+    _fields_ = [("step", C.c_int64), ("bond_num_rl", C.c_int32), ("bond_num_mono_cis", C.c_int32),
+                ("bond_num_cis", C.c_int32), ("bond_num", C.c_int32), ("max_complex", C.c_int32),
+                ("n_complexes", C.c_int32), ("n_in_complexes", C.c_int32), ("reserved", C.c_int32),
+                ("cluster_size", C.c_double)]
+
+
+EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
+           "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
+           "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
+           "kmc_write_cluster_log", "kmc_run"]
+
+
+class KmcError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    spec = importlib.util.spec_from_file_location("kmc_b200_build", os.path.join(PKG_DIR, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KmcError("libkmc_b200.so is missing: run __graft_entry__.build() (nvcc, sm_100a); there is no CPU path")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+        L.kmc_abi_version.restype = C.c_int
+        L.kmc_default_params.argtypes = [C.POINTER(Params)]
+        L.kmc_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+        L.kmc_destroy.argtypes = [vp]
+        L.kmc_last_error.restype = C.c_char_p
+        L.kmc_last_error.argtypes = [vp]
+        L.kmc_init_random.argtypes = [vp, u64, i32]
+        L.kmc_set_state.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, i32]
+        L.kmc_get_state.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.kmc_get_packed.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.kmc_set_packed.argtypes = [vp, vp, vp, vp, vp, vp, i64]
+        L.kmc_step.argtypes = [vp, i64]
+        L.kmc_sync.argtypes = [vp]
+        L.kmc_get_series.argtypes = [vp, i32, C.POINTER(Series)]
+        L.kmc_get_complexes.restype = i64
+        L.kmc_get_complexes.argtypes = [vp, i32, vp, vp, i64]
+        L.kmc_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
+        L.kmc_get_accept.argtypes = [vp, i32, vp]
+        L.kmc_get_events.argtypes = [vp, vp]
+        L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
+        L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
+        L.kmc_run.argtypes = [vp, i64, i32, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = Params()
+    lib().kmc_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "box":
+            p.box[0], p.box[1], p.box[2] = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def scaled_box(n_total, z=1000.0):
+    """Box edge that keeps the reference's default densities (main.cpp:43-57): L = 5773*sqrt(N/200)."""
+    L = 5773.0 * (n_total / 200.0) ** 0.5
+    return (L, L, z)
+
+
+class Kmc:
+    """One kmc_handle. Mirrors the reference's use: set parameters, (re)start from a state, step, read outputs."""
+
+    def __init__(self, params):
+        self.p = params
+        self.na, self.nb = params.n_receptor, params.n_ligand
+        self.n = self.na + self.nb
+        self.h = C.c_void_p()
+        rc = lib().kmc_create(C.byref(params), C.byref(self.h))
+        if rc != 0:
+            raise KmcError("kmc_create failed (%d): %s" % (rc, lib().kmc_last_error(None).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().kmc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise KmcError("kmc error %d: %s" % (rc, lib().kmc_last_error(self.h).decode()))
+        return rc
+
+    def init_random(self, seed=1, sort_cells=False):
+        self._ck(lib().kmc_init_random(self.h, seed, int(sort_cells)))
+
+    def set_state(self, R, status, res_nei, replica=0, step_done=0, max_complex=0):
+        X = np.ascontiguousarray(R[..., 0], dtype=np.float64); Y = np.ascontiguousarray(R[..., 1], dtype=np.float64)
+        Z = np.ascontiguousarray(R[..., 2], dtype=np.float64)
+        st = np.ascontiguousarray(status, dtype=np.int32); rn = np.ascontiguousarray(res_nei, dtype=np.int32)
+        assert X.shape == (self.n + 1, 5, 5) and st.shape == (self.n + 1, 5) and rn.shape == (self.n + 1, 7)
+        self._ck(lib().kmc_set_state(self.h, replica, X.ctypes.data, Y.ctypes.data, Z.ctypes.data, st.ctypes.data,
+                                     rn.ctypes.data, step_done, max_complex))
+
+    def get_state(self, replica=0):
+        n = self.n
+        X = np.zeros((n + 1, 5, 5)); Y = np.zeros_like(X); Z = np.zeros_like(X)
+        st = np.zeros((n + 1, 5), dtype=np.int32); rn = np.zeros((n + 1, 7), dtype=np.int32)
+        self._ck(lib().kmc_get_state(self.h, replica, X.ctypes.data, Y.ctypes.data, Z.ctypes.data, st.ctypes.data, rn.ctypes.data))
+        return np.stack([X, Y, Z], axis=-1), st, rn
+
+    def get_packed(self):
+        r = self.p.n_replicas
+        rec = np.zeros((r * self.na, 6)); lig = np.zeros((r * self.nb, 24))
+        rl = np.zeros(r * self.na, dtype=np.int32); rs = np.zeros_like(rl); rc = np.zeros_like(rl)
+        self._ck(lib().kmc_get_packed(self.h, rec.ctypes.data, lig.ctypes.data, rl.ctypes.data, rs.ctypes.data, rc.ctypes.data))
+        return rec, lig, rl, rs, rc
+
+    def set_packed(self, rec, lig, rl=None, rs=None, rc=None, step_done=0):
+        rec = np.ascontiguousarray(rec, dtype=np.float64); lig = np.ascontiguousarray(lig, dtype=np.float64)
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.int32) for a in (rl, rs, rc)]
+        ptr = [None if a is None else a.ctypes.data for a in arrs]
+        self._ck(lib().kmc_set_packed(self.h, rec.ctypes.data, lig.ctypes.data, ptr[0], ptr[1], ptr[2], step_done))
+
+    def step(self, n=1):
+        self._ck(lib().kmc_step(self.h, n))
+
+    def sync(self):
+        self._ck(lib().kmc_sync(self.h))
+
+    def series(self, replica=0):
+        s = Series()
+        self._ck(lib().kmc_get_series(self.h, replica, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Series._fields_ if k != "reserved"}
+
+    def complexes(self, replica=0):
+        rl = np.zeros(self.nb, dtype=np.int32); mem = np.zeros(self.n + 1, dtype=np.int32)
+        tot = self._ck(lib().kmc_get_complexes(self.h, replica, rl.ctypes.data, mem.ctypes.data, mem.size))
+        rows, o = [], 0
+        for l in range(self.nb):
+            rows.append(mem[o:o + rl[l]].tolist()); o += rl[l]
+        assert o == tot
+        return rows
+
+    def oligomer_hist(self, replica=-1, nbins=64):
+        hist = np.zeros(nbins, dtype=np.int64)
+        self._ck(lib().kmc_get_oligomer_hist(self.h, replica, hist.ctypes.data, nbins))
+        return hist
+
+    def accepted(self, replica=0):
+        a = np.zeros(self.n + 1, dtype=np.int32)
+        self._ck(lib().kmc_get_accept(self.h, replica, a.ctypes.data))
+        return a
+
+    def events(self):
+        e = np.zeros(16, dtype=np.int64)
+        self._ck(lib().kmc_get_events(self.h, e.ctypes.data))
+        return dict(rl_on=int(e[0]), mono_cis_on=int(e[1]), cis_on=int(e[2]), rl_off=int(e[3]), mono_cis_off=int(e[4]),
+                    cis_off=int(e[5]), reverted=int(e[6]), tried=int(e[7]), far=int(e[8]), passes=int(e[9]),
+                    rebuilds=int(e[10]), launches=int(e[11]))
+
+    def write_bond_dat(self, path, replica=0):
+        self._ck(lib().kmc_write_bond_dat(self.h, replica, os.fsencode(path)))
+
+    def write_cluster_log(self, path, replica=0):
+        self._ck(lib().kmc_write_cluster_log(self.h, replica, os.fsencode(path)))
+
+    def run(self, n_steps, output_every, directory):
+        self._ck(lib().kmc_run(self.h, n_steps, output_every, os.fsencode(directory)))

@@ -1,0 +1,41 @@
+"""Shared helpers of the test-suite: parameter sets used by both the oracle (checker) and the CUDA library
+(the thing checked), state comparison with the tolerances the north star states."""
+import json
+import os
+
+import numpy as np
+
+POS_RTOL = 1e-12      # "positions matching to within 1e-12 relative in fp64" (BASELINE.json north_star)
+
+HOT = dict(off=2e-5, cis_off=2e-5, mono_cis_off=1e-4)
+
+
+def apply_regime(p, regime, n_total=None):
+    """regime: 'default' | 'dense' | 'hot' (dense + fast dissociation). Mutates a Params struct of either binding."""
+    if regime in ("dense", "hot"):
+        p.cis_on *= 20
+        p.mono_cis_on *= 20
+    if regime == "hot":
+        for k, v in HOT.items():
+            setattr(p, k, v)
+    return p
+
+
+def load_golden_state(path):
+    z = np.load(path)
+    return dict(R=z["R"], status=z["status"], res_nei=z["res_nei"], step=int(z["step"]), max_complex=int(z["max_complex"]),
+                params=json.loads(str(z["params"])))
+
+
+def compare_states(ref, got, label=""):
+    """ref/got = (R, status, res_nei). Bond table must be identical; positions within POS_RTOL relative
+    (relative to max(|x_ref|, 1 A)). Returns max relative position error."""
+    Rr, sr, nr = ref
+    Rg, sg, ng = got
+    assert np.array_equal(sr, sg), label + ": protein_status differs"
+    assert np.array_equal(nr, ng), label + ": res_nei differs"
+    scale = np.maximum(np.abs(Rr), 1.0)
+    err = np.abs(Rr - Rg) / scale
+    worst = float(err.max())
+    assert worst <= POS_RTOL, "%s: position error %.3e exceeds %.1e at %s" % (label, worst, POS_RTOL, np.unravel_index(err.argmax(), err.shape))
+    return worst

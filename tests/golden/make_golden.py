@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""tests/golden/make_golden.py -- regenerates the golden vectors from the UNMODIFIED reference
+(oracle/_ref/kmcref_*, built by oracle/build_ref.py from /root/reference/main.cpp). Run in the build
+container only (the reference source does not exist on the GPU box); the outputs are committed.
+
+  ref_kat.json          hashes / counters of reference runs under the sequential xorshift streams of
+                        oracle/ref_harness.cpp (FNV-1a-64 over the raw bytes of R_x,R_y,R_z and of
+                        res_nei,protein_status), incl. the two known-answer vectors of SURVEY.md 8c
+  dense_step30000.npz   full reference state of the dense oligomerising system after 30000 steps
+                        (63 bonds, complexes up to 10 members): start state for GPU replay tests
+  hot40_step200000.npz  N=40 hot system (dissociation + goto lable4 exercised) after 200000 steps
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import refio  # noqa: E402
+
+DENSE = dict(sets=dict(cell_range_x=2500, cell_range_y=2500, cell_range_z=400), scales=dict(cis_Ass_Rate=20, mono_cis_Ass_Rate=20))
+HOT = dict(Diss_Rate=2e-5, cis_Diss_Rate=2e-5, mono_cis_Diss_Rate=1e-4)
+
+
+def summarize(fr):
+    R = fr["R"]
+    return dict(step=fr["step"], bond_num=fr["bond_num"], bond_num_rl=fr["bond_num_rl"], bond_num_cis=fr["bond_num_cis"],
+                bond_num_mono_cis=fr["bond_num_mono_cis"], max_complex=fr["max_complex"],
+                hash_R="%016x" % refio.fnv1a64(R[..., 0], R[..., 1], R[..., 2]),
+                hash_bonds="%016x" % refio.fnv1a64(fr["res_nei"], fr["status"]))
+
+
+def save_state(name, fr, params):
+    np.savez_compressed(os.path.join(HERE, name), R=fr["R"], status=fr["status"], res_nei=fr["res_nei"], step=fr["step"],
+                        max_complex=fr["max_complex"], params=json.dumps(params))
+
+
+def main():
+    kat = {}
+    s, fr = refio.run_ref("n200", 200, 1000)
+    kat["default_1000"] = dict(summary=s, frames=[summarize(f) for f in fr])
+    s, fr = refio.run_ref("n200", 200, 30000, frames_every=5000, **DENSE)
+    kat["dense_30000"] = dict(summary=s, frames=[summarize(f) for f in fr], sets=DENSE["sets"], scales=DENSE["scales"])
+    save_state("dense_step30000.npz", fr[-1], dict(box=[2500, 2500, 400], cis_on_scale=20, mono_cis_on_scale=20))
+    sets = dict(cell_range_x=1000, cell_range_y=1000, cell_range_z=300); sets.update(HOT)
+    s, fr = refio.run_ref("n40", 40, 200000, frames_every=50000, sets=sets, scales=DENSE["scales"])
+    kat["hot40_200000"] = dict(summary=s, frames=[summarize(f) for f in fr], sets=sets, scales=DENSE["scales"])
+    save_state("hot40_step200000.npz", fr[-1], dict(box=[1000, 1000, 300], cis_on_scale=20, mono_cis_on_scale=20, **HOT))
+    sets = dict(DENSE["sets"]); sets.update(HOT)
+    s, fr = refio.run_ref("n200", 200, 40000, frames_every=10000, sets=sets, scales=DENSE["scales"])
+    kat["hot200_40000"] = dict(summary=s, frames=[summarize(f) for f in fr], sets=sets, scales=DENSE["scales"])
+    save_state("hot200_step40000.npz", fr[-1], dict(box=[2500, 2500, 400], cis_on_scale=20, mono_cis_on_scale=20, **HOT))
+    json.dump(kat, open(os.path.join(HERE, "ref_kat.json"), "w"), indent=1)
+    print(json.dumps({k: v["frames"][-1] for k, v in kat.items()}, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""GPU (B200) parity tests proper: the CUDA sweep, called through the C ABI (libkmc_b200.so), against the
+CPU oracle (oracle/libkmc_oracle.so, itself pinned bit-for-bit to the unmodified reference) on the same inputs
+and the same keyed Philox stream. Bond formation/breakage, accept/reject decisions and complex member lists
+must be identical; positions agree to 1e-12 relative (libm sin/cos/atan2/acos of CUDA vs glibc)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import kmc_b200
+import pyoracle
+from common import apply_regime, compare_states, load_golden_state
+
+
+def make_pair(na, nb, box, regime, seed, grid=1, **kw):
+    po = apply_regime(pyoracle.default_params(box=box, n_receptor=na, n_ligand=nb, use_grid=grid, stream_mode=1, seed=seed), regime)
+    pg = apply_regime(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=seed, mode=kmc_b200.MODE_REPLAY, **kw), regime)
+    return pyoracle.Oracle(po), kmc_b200.Kmc(pg)
+
+
+def lockstep(o, k, nsteps, check_every, label, per_step_accept=False):
+    done, worst = 0, 0.0
+    while done < nsteps:
+        m = min(check_every, nsteps - done)
+        if per_step_accept:
+            for _ in range(m):
+                o.step(1); k.step(1)
+                assert np.array_equal(o.accepted()[1:], k.accepted()[1:]), "%s: accept/reject differs at step %d" % (label, done + 1)
+                done += 1
+        else:
+            o.step(m); k.step(m); done += m
+        worst = max(worst, compare_states(o.get_state(), k.get_state(), "%s step %d" % (label, done)))
+        c, s = o.counts(), k.series()
+        for key in ("bond_num", "bond_num_rl", "bond_num_cis", "bond_num_mono_cis", "max_complex"):
+            assert c[key] == s[key], (label, done, key, c[key], s[key])
+        assert c["tot_cluster_num"] == s["n_complexes"] and c["tot_proteins_in_cluster"] == s["n_in_complexes"]
+        assert c["cluster_size"] == s["cluster_size"]
+        assert o.results() == k.complexes(), "%s: complex member lists differ at step %d" % (label, done)
+    return worst
+
+
+def test_default_system_free_diffusion():
+    """configs[0] geometry: 150 receptors + 50 ligands, paper parameters; own scalable initial state."""
+    o, k = make_pair(150, 50, (5773, 5773, 1000), "default", seed=11)
+    k.init_random(seed=5)
+    R, st, rn = k.get_state()
+    o.set_state(R, st, rn)
+    lockstep(o, k, 300, 50, "default", per_step_accept=True)
+
+
+@pytest.mark.parametrize("name,regime", [("dense_step30000.npz", "dense"), ("hot200_step40000.npz", "hot")])
+def test_from_reference_state_with_complexes(golden_dir, name, regime):
+    """start from a state the REFERENCE evolved (63 / 46 bonds, multi-ligand complexes) and replay 1500 steps:
+    rigid complex moves, lay-down, alignment passes, shuffles, association, dissociation."""
+    g = load_golden_state(os.path.join(golden_dir, name))
+    o, k = make_pair(150, 50, tuple(g["params"]["box"]), regime, seed=2024)
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    lockstep(o, k, 200, 1, name, per_step_accept=True)
+    lockstep(o, k, 1300, 100, name)
+    ev_o, ev_k = o.events(), k.events()
+    assert (ev_k["rl_on"], ev_k["mono_cis_on"], ev_k["cis_on"], ev_k["rl_off"], ev_k["mono_cis_off"], ev_k["cis_off"]) == tuple(int(x) for x in ev_o[:6])
+
+
+def test_hot_from_scratch_long():
+    """dense hot system from a bond-free start, 20 000 steps: complexes form, grow, break."""
+    o, k = make_pair(150, 50, (2500, 2500, 400), "hot", seed=7)
+    k.init_random(seed=3)
+    R, st, rn = k.get_state()
+    o.set_state(R, st, rn)
+    lockstep(o, k, 20000, 1000, "hot-long")
+    assert k.series()["bond_num"] > 10
+
+
+def test_small_system_hot40(golden_dir):
+    g = load_golden_state(os.path.join(golden_dir, "hot40_step200000.npz"))
+    o, k = make_pair(30, 10, tuple(g["params"]["box"]), "hot", seed=99)
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    lockstep(o, k, 5000, 250, "hot40")
+
+
+def test_replicas_are_independent_systems():
+    """ensemble batching (configs[2]): replica r must equal a single system run with seed + r."""
+    R_ = 5
+    pg = apply_regime(kmc_b200.default_params(box=(2500, 2500, 400), seed=100, n_replicas=R_), "hot")
+    k = kmc_b200.Kmc(pg)
+    k.init_random(seed=40)
+    oracles = []
+    for r in range(R_):
+        po = apply_regime(pyoracle.default_params(box=(2500, 2500, 400), use_grid=1, stream_mode=1, seed=100 + r), "hot")
+        o = pyoracle.Oracle(po)
+        o.set_state(*k.get_state(r))
+        oracles.append(o)
+    k.step(1500)
+    for r, o in enumerate(oracles):
+        o.step(1500)
+        compare_states(o.get_state(), k.get_state(r), "replica %d" % r)
+        assert o.results() == k.complexes(r)
+
+
+def test_config2_1e5_molecules_replay():
+    """configs[1]: 1e5-molecule membrane (75 000 receptors + 25 000 ligands, default density), replay check vs the oracle."""
+    na, nb = 75000, 25000
+    box = kmc_b200.scaled_box(na + nb)
+    for regime, steps in (("default", 40), ("hot", 40)):
+        o, k = make_pair(na, nb, box, regime, seed=1)
+        k.init_random(seed=1, sort_cells=True)
+        o.set_state(*k.get_state())
+        lockstep(o, k, steps, 20, "1e5-" + regime)
+        assert np.array_equal(o.accepted()[1:], k.accepted()[1:])
+        k.close()
