@@ -114,6 +114,12 @@ int kmc_set_packed(kmc_handle *h, const double *rec_pose, const double *lig_pose
  * conflict-resolution count it reads back each step; kmc_sync waits for completion. */
 int kmc_step(kmc_handle *h, int64_t n);
 int kmc_sync(kmc_handle *h);
+/* kmc_step bracketed by CUDA events recorded on the handle's own stream; elapsed device time in ms */
+int kmc_step_timed(kmc_handle *h, int64_t n, double *elapsed_ms);
+/* per-kernel timing (CUDA events around every launch of the sweep). enable=1 resets and starts, 0 stops.
+ * kmc_profile_get(idx) returns 1 past the last kernel. */
+int kmc_profile(kmc_handle *h, int32_t enable);
+int kmc_profile_get(kmc_handle *h, int32_t idx, const char **name, double *total_ms, int64_t *launches);
 
 /* Outputs the reference writes at its output cadence */
 int kmc_get_series(kmc_handle *h, int32_t replica, kmc_series *out);

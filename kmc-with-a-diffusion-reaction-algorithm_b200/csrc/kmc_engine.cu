@@ -3,6 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
+#define KMC_NKERNELS 21
 
 #include <algorithm>
 #include <cmath>
@@ -28,7 +29,49 @@ struct kmc_handle {
     int *d_series = nullptr;
     int scanBlocks = 0;
     int64_t launches = 0, passes = 0;
+    // optional per-kernel timing with CUDA events on the handle's stream (bench.py roofline)
+    bool profiling = false;
+    struct Pending { int id; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> evpool;
+    double kms[KMC_NKERNELS] = {0};
+    int64_t kcount[KMC_NKERNELS] = {0};
 };
+
+static const char *const g_kernel_names[KMC_NKERNELS] = {
+    "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_rebuild_gate_clear", "k_propose_simple",
+    "k_propose_complex", "memset_cellCount", "k_grid_count", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
+    "k_zero_unknown", "k_resolve", "k_restore", "k_react_candidates", "k_react_resolve", "k_dissociate", "k_series"};
+enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_GATE_CLEAR, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
+       KID_MEMSET, KID_GRID_COUNT, KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_ZERO_UNKNOWN, KID_RESOLVE,
+       KID_RESTORE, KID_REACT_CAND, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES };
+
+static cudaEvent_t take_event(kmc_handle *h) {
+    if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+static void harvest(kmc_handle *h, bool all) {
+    size_t keep = 0;
+    for (auto &p : h->pending) {
+        if (all ? (cudaEventSynchronize(p.b) == cudaSuccess) : (cudaEventQuery(p.b) == cudaSuccess)) {
+            float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
+            h->kms[p.id] += ms; h->kcount[p.id]++;
+            h->evpool.push_back(p.a); h->evpool.push_back(p.b);
+        } else h->pending[keep++] = p;
+    }
+    h->pending.resize(keep);
+}
+// every kernel launch of the sweep goes through this macro: counts it, and brackets it with events when profiling
+#define LAUNCH(id, ...)                                                                              \
+    do {                                                                                             \
+        h->launches++;                                                                               \
+        if (h->profiling) {                                                                          \
+            kmc_handle::Pending p_{id, take_event(h), take_event(h)};                                \
+            cudaEventRecord(p_.a, st); __VA_ARGS__; cudaEventRecord(p_.b, st);                       \
+            h->pending.push_back(p_);                                                                \
+        } else { __VA_ARGS__; }                                                                      \
+    } while (0)
+
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -102,6 +145,8 @@ extern "C" void kmc_destroy(kmc_handle *h) {
     if (!h) return;
     cudaSetDevice(h->P.device);
     for (void *p : h->allocs) cudaFree(p);
+    for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto ev : h->evpool) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -363,42 +408,41 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     for (int64_t it = 0; it < n; it++) {
         const uint64_t step = (uint64_t)(h->step_done + 1);
         const Args A{D, h->K};
-        k_step_begin<<<1, 1, 0, st>>>(A);
+        LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A)));
         // S1 (gated on device: no host round trip)
-        k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A);
-        k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A);
-        k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A);
-        k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A);
-        k_rebuild_gate_clear<<<1, 1, 0, st>>>(A);
+        LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
+        LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+        LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
+        LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
+        LAUNCH(KID_GATE_CLEAR, (k_rebuild_gate_clear<<<1, 1, 0, st>>>(A)));
         // S2 proposals
-        k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A, step);
-        k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A, step);
+        LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A, step)));
+        LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A, step)));
         // grid
-        CK(cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st));
-        k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A);
-        k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.ncell + 1);
-        k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks);
-        k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1);
-        k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A);
-        h->launches += 14;
+        LAUNCH(KID_MEMSET, (cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st)));
+        LAUNCH(KID_GRID_COUNT, (k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A)));
+        LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.ncell + 1)));
+        LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks)));
+        LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1)));
+        LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
         // S2g: resolve until every unit is decided
         int scal[S_COUNT];
         for (int pass = 0;; pass++) {
-            if (pass) { k_zero_unknown<<<1, 1, 0, st>>>(A); h->launches++; }
-            k_resolve<<<nblk(NT, B), B, 0, st>>>(A);
-            h->launches++; h->passes++;
+            if (pass) LAUNCH(KID_ZERO_UNKNOWN, (k_zero_unknown<<<1, 1, 0, st>>>(A)));
+            LAUNCH(KID_RESOLVE, (k_resolve<<<nblk(NT, B), B, 0, st>>>(A)));
+            h->passes++;
             CK(cudaMemcpyAsync(scal, D.scal, sizeof scal, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (scal[S_OVERFLOW]) { h->err = "device buffer overflow (mask " + std::to_string(scal[S_OVERFLOW]) + ")"; return KMC_ERR_CAPACITY; }
             if (scal[S_NUNKNOWN] == 0) break;
             if (pass > NT + 8) { h->err = "conflict resolution did not converge"; return KMC_ERR_CUDA; }
         }
-        k_restore<<<nblk(NT, 256), 256, 0, st>>>(A);
+        if (h->profiling) harvest(h, false);
+        LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
         // S3
-        k_react_candidates<<<nblk(std::max(NAt, 1), B), B, 0, st>>>(A, step);
-        k_react_resolve<<<1, 1024, 0, st>>>(A);
-        k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, step);
-        h->launches += 4;
+        LAUNCH(KID_REACT_CAND, (k_react_candidates<<<nblk(std::max(NAt, 1), B), B, 0, st>>>(A, step)));
+        LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
+        LAUNCH(KID_DISSOCIATE, (k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, step)));
         // S4: the new buffers become the committed state
         std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign);
         h->step_done++; h->stepped = true;
@@ -414,6 +458,43 @@ extern "C" int kmc_sync(kmc_handle *h) {
     int scal[S_COUNT];
     CK(cudaMemcpy(scal, h->D.scal, sizeof scal, cudaMemcpyDeviceToHost));
     if (scal[S_OVERFLOW]) { h->err = "device buffer overflow (mask " + std::to_string(scal[S_OVERFLOW]) + ")"; return KMC_ERR_CAPACITY; }
+    return KMC_OK;
+}
+
+// n steps bracketed by CUDA events on the handle's stream (the stream the kernels are launched on)
+extern "C" int kmc_step_timed(kmc_handle *h, int64_t n, double *elapsed_ms) {
+    if (!h || !elapsed_ms) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(a, h->stream));
+    int rc = kmc_step(h, n);
+    if (rc == KMC_OK) {
+        CK(cudaEventRecord(b, h->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
+        *elapsed_ms = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return rc;
+}
+extern "C" int kmc_profile(kmc_handle *h, int32_t enable) {
+    if (!h) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    harvest(h, true);
+    h->profiling = enable != 0;
+    if (enable) { for (int i = 0; i < KMC_NKERNELS; i++) { h->kms[i] = 0; h->kcount[i] = 0; } }
+    return KMC_OK;
+}
+extern "C" int kmc_profile_get(kmc_handle *h, int32_t idx, const char **name, double *total_ms, int64_t *launches) {
+    if (!h || idx < 0) return KMC_ERR_INVALID;
+    if (idx >= KMC_NKERNELS) return 1;
+    CK(cudaSetDevice(h->P.device));
+    harvest(h, true);
+    if (name) *name = g_kernel_names[idx];
+    if (total_ms) *total_ms = h->kms[idx];
+    if (launches) *launches = h->kcount[idx];
     return KMC_OK;
 }
 
@@ -439,8 +520,8 @@ extern "C" int kmc_get_series(kmc_handle *h, int32_t rep, kmc_series *out) {
     Dev &D = h->D;
     CK(cudaMemsetAsync(h->d_series, 0, sizeof(int) * 4 * h->R, h->stream));
     const Args A{D, h->K};
-    k_series<<<nblk(std::max(h->NAt, 1), 256), 256, 0, h->stream>>>(A, h->d_series);
-    h->launches++;
+    cudaStream_t st = h->stream;
+    LAUNCH(KID_SERIES, (k_series<<<nblk(std::max(h->NAt, 1), 256), 256, 0, st>>>(A, h->d_series)));
     int s4[4], mx = 0;
     CK(cudaMemcpyAsync(s4, h->d_series + 4 * rep, sizeof s4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&mx, D.maxComplex + rep, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

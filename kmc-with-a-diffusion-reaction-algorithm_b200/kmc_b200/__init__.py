@@ -38,7 +38,7 @@ class Series(C.Structure):
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
-           "kmc_write_cluster_log", "kmc_run"]
+           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get"]
 
 
 class KmcError(RuntimeError):
@@ -85,6 +85,9 @@ def lib():
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
         L.kmc_run.argtypes = [vp, i64, i32, C.c_char_p]
+        L.kmc_step_timed.argtypes = [vp, i64, C.POINTER(C.c_double)]
+        L.kmc_profile.argtypes = [vp, i32]
+        L.kmc_profile_get.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(i64)]
         _lib = L
     return _lib
 
@@ -163,6 +166,26 @@ class Kmc:
 
     def step(self, n=1):
         self._ck(lib().kmc_step(self.h, n))
+
+    def step_timed(self, n=1):
+        """n steps; returns device milliseconds (CUDA events on the handle's stream)."""
+        ms = C.c_double()
+        self._ck(lib().kmc_step_timed(self.h, n, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        self._ck(lib().kmc_profile(self.h, int(enable)))
+
+    def profile_get(self):
+        """{kernel name: (total ms, launches)} since profile(True)"""
+        out, i = {}, 0
+        while True:
+            name = C.c_char_p(); ms = C.c_double(); cnt = C.c_int64()
+            rc = self._ck(lib().kmc_profile_get(self.h, i, C.byref(name), C.byref(ms), C.byref(cnt)))
+            if rc == 1:
+                return out
+            out[name.value.decode()] = (ms.value, cnt.value)
+            i += 1
 
     def sync(self):
         self._ck(lib().kmc_sync(self.h))
