@@ -137,6 +137,11 @@ int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
  * [10] complex-table rebuilds, [11] kernels launched */
 int kmc_get_events(kmc_handle *h, int64_t *ev);
 
+/* Pure host formatting of the reference's records (no device needed): one bond.dat line (main.cpp:2249-2251) and one
+ * cluster.log frame (main.cpp:2293-2301). Return the number of characters written (excluding the NUL) or a negative status. */
+int kmc_format_bond_dat(double dt, const kmc_series *s, char *buf, int32_t cap);
+int64_t kmc_format_cluster_log(double dt, int64_t step, int32_t n_ligand, const int32_t *row_len, const int32_t *members,
+                               char *buf, int64_t cap);
 /* Byte-compatible writers for the reference's output files (append one record, main.cpp:2247-2253, 2291-2305) */
 int kmc_write_bond_dat(kmc_handle *h, int32_t replica, const char *path);
 int kmc_write_cluster_log(kmc_handle *h, int32_t replica, const char *path);

@@ -598,15 +598,39 @@ extern "C" int kmc_get_events(kmc_handle *h, int64_t *ev) {
 }
 
 // ---- the reference's output records ----
+// main.cpp:2249-2251: fixed, precision 3, widths 15 5 5 10 10 10 10. Pure host formatting (no device needed).
+extern "C" int kmc_format_bond_dat(double dt, const kmc_series *s, char *buf, int32_t cap) {
+    if (!s || !buf || cap < 1) return KMC_ERR_INVALID;
+    int n = snprintf(buf, (size_t)cap, "%15.3f%5d%5d%10d%10d%10.3f%10d\n", (double)s->step * dt, s->bond_num_rl, s->bond_num_mono_cis,
+                     s->bond_num_cis, s->bond_num, s->cluster_size, s->max_complex);
+    return n < cap ? n : KMC_ERR_CAPACITY;
+}
+// main.cpp:2293-2301: header with the default ostream float format (%g), then one line per ligand: its row of `results`,
+// every member followed by two blanks (an empty line for a ligand that is not a BFS root)
+extern "C" int64_t kmc_format_cluster_log(double dt, int64_t step, int32_t n_ligand, const int32_t *row_len, const int32_t *members,
+                                          char *buf, int64_t cap) {
+    if (!row_len || !buf || cap < 1) return KMC_ERR_INVALID;
+    std::string out;
+    char tmp[64];
+    snprintf(tmp, sizeof tmp, "Hello Cluster!, t=%g\n", (double)step * dt); out += tmp;
+    int64_t o = 0;
+    for (int l = 0; l < n_ligand; l++) {
+        for (int i = 0; i < row_len[l]; i++) { snprintf(tmp, sizeof tmp, "%d  ", members[o + i]); out += tmp; }
+        o += row_len[l];
+        out += '\n';
+    }
+    if ((int64_t)out.size() + 1 > cap) return KMC_ERR_CAPACITY;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int64_t)out.size();
+}
 extern "C" int kmc_write_bond_dat(kmc_handle *h, int32_t rep, const char *path) {
     if (!h || !path) return KMC_ERR_INVALID;
     kmc_series s; int rc = kmc_get_series(h, rep, &s); if (rc) return rc;
+    char line[160];
+    rc = kmc_format_bond_dat(h->P.dt, &s, line, sizeof line); if (rc < 0) return rc;
     FILE *f = fopen(path, "a");
     if (!f) { h->err = std::string("cannot open ") + path; return KMC_ERR_IO; }
-    // main.cpp:2249-2251: fixed, precision 3, widths 15 5 5 10 10 10 10
-    fprintf(f, "%15.3f%5d%5d%10d%10d%10.3f%10d\n", (double)s.step * h->P.dt, s.bond_num_rl, s.bond_num_mono_cis, s.bond_num_cis,
-            s.bond_num, s.cluster_size, s.max_complex);
-    fclose(f);
+    fputs(line, f); fclose(f);
     return KMC_OK;
 }
 extern "C" int kmc_write_cluster_log(kmc_handle *h, int32_t rep, const char *path) {
@@ -614,17 +638,12 @@ extern "C" int kmc_write_cluster_log(kmc_handle *h, int32_t rep, const char *pat
     std::vector<int32_t> len(h->NB), mem(h->N + 1);
     int64_t tot = kmc_get_complexes(h, rep, len.data(), mem.data(), (int64_t)mem.size());
     if (tot < 0) return (int)tot;
+    std::vector<char> buf((size_t)h->N * 14 + h->NB + 128);
+    int64_t n = kmc_format_cluster_log(h->P.dt, h->step_done, h->NB, len.data(), mem.data(), buf.data(), (int64_t)buf.size());
+    if (n < 0) return (int)n;
     FILE *f = fopen(path, "a");
     if (!f) { h->err = std::string("cannot open ") + path; return KMC_ERR_IO; }
-    // main.cpp:2293-2301: default ostream float format (%g), members followed by two blanks, one line per ligand
-    fprintf(f, "Hello Cluster!, t=%g\n", (double)h->step_done * h->P.dt);
-    int64_t o = 0;
-    for (int l = 0; l < h->NB; l++) {
-        for (int i = 0; i < len[l]; i++) fprintf(f, "%d  ", mem[o + i]);
-        o += len[l];
-        fputc('\n', f);
-    }
-    fclose(f);
+    fwrite(buf.data(), 1, (size_t)n, f); fclose(f);
     return KMC_OK;
 }
 extern "C" int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, const char *dir) {

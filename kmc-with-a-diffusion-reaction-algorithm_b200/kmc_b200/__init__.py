@@ -38,7 +38,7 @@ class Series(C.Structure):
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
-           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get"]
+           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log"]
 
 
 class KmcError(RuntimeError):
@@ -85,6 +85,9 @@ def lib():
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
         L.kmc_run.argtypes = [vp, i64, i32, C.c_char_p]
+        L.kmc_format_bond_dat.argtypes = [C.c_double, C.POINTER(Series), C.c_char_p, i32]
+        L.kmc_format_cluster_log.restype = i64
+        L.kmc_format_cluster_log.argtypes = [C.c_double, i64, i32, vp, vp, C.c_char_p, i64]
         L.kmc_step_timed.argtypes = [vp, i64, C.POINTER(C.c_double)]
         L.kmc_profile.argtypes = [vp, i32]
         L.kmc_profile_get.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(i64)]
@@ -107,6 +110,29 @@ def scaled_box(n_total, z=1000.0):
     """Box edge that keeps the reference's default densities (main.cpp:43-57): L = 5773*sqrt(N/200)."""
     L = 5773.0 * (n_total / 200.0) ** 0.5
     return (L, L, z)
+
+
+def format_bond_dat(dt, step, bond_num_rl, bond_num_mono_cis, bond_num_cis, bond_num, cluster_size, max_complex):
+    """one bond.dat line exactly as main.cpp:2251 prints it (host only, no GPU)"""
+    s = Series(step=step, bond_num_rl=bond_num_rl, bond_num_mono_cis=bond_num_mono_cis, bond_num_cis=bond_num_cis,
+               bond_num=bond_num, max_complex=max_complex, cluster_size=cluster_size)
+    buf = C.create_string_buffer(256)
+    n = lib().kmc_format_bond_dat(dt, C.byref(s), buf, 256)
+    if n < 0:
+        raise KmcError("kmc_format_bond_dat failed: %d" % n)
+    return buf.value.decode()
+
+
+def format_cluster_log(dt, step, rows):
+    """one cluster.log frame exactly as main.cpp:2293-2301 prints it (host only, no GPU); rows = list of member lists per ligand"""
+    rl = np.array([len(r) for r in rows], dtype=np.int32)
+    mem = np.array([m for r in rows for m in r] + [0], dtype=np.int32)
+    cap = 64 + 16 * mem.size + rl.size
+    buf = C.create_string_buffer(cap)
+    n = lib().kmc_format_cluster_log(dt, step, rl.size, rl.ctypes.data, mem.ctypes.data, buf, cap)
+    if n < 0:
+        raise KmcError("kmc_format_cluster_log failed: %d" % n)
+    return buf.value.decode()
 
 
 class Kmc:

@@ -52,6 +52,18 @@ def main():
     s, fr = refio.run_ref("n200", 200, 40000, frames_every=10000, sets=sets, scales=DENSE["scales"])
     kat["hot200_40000"] = dict(summary=s, frames=[summarize(f) for f in fr], sets=sets, scales=DENSE["scales"])
     save_state("hot200_step40000.npz", fr[-1], dict(box=[2500, 2500, 400], cis_on_scale=20, mono_cis_on_scale=20, **HOT))
+    # the reference's own output records (bond.dat, cluster.log; main.cpp:2247-2253, 2291-2305) of the dense run
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        wd = os.path.join(td, "wd")
+        cmd = [os.path.join(refio.REF_DIR, "kmcref_n200"), "--steps", "10000", "--workdir", wd]
+        for k2, v2 in DENSE["sets"].items():
+            cmd += ["--set", "%s=%r" % (k2, float(v2))]
+        for k2, v2 in DENSE["scales"].items():
+            cmd += ["--scale", "%s=%r" % (k2, float(v2))]
+        subprocess.run(cmd, cwd=td, check=True, capture_output=True)
+        kat["ref_records"] = dict(bond_dat=open(os.path.join(wd, "bond.dat")).read(), cluster_log=open(os.path.join(wd, "cluster.log")).read(),
+                                  note="dense system, steps 5000 and 10000, written by the unmodified reference")
     json.dump(kat, open(os.path.join(HERE, "ref_kat.json"), "w"), indent=1)
     print(json.dumps({k: v["frames"][-1] for k, v in kat.items()}, indent=1))
 
