@@ -37,7 +37,7 @@ B_ALG_STEP = 232.0      # whole step, fp64 pose read+written once (2*
 B_ALG_KERNEL = {
     "k_propose_simple": 96 + 96 + 4 + 4 + 2,          # old pose in, proposed pose out, unitOf, cis/size word, state+far flags
     "k_resolve": 36 + 4 + 1 + 24 + 8,                 # proposed centre+beads (rec 16 B, lig 96 B), unitOf, state, 3 cell-row bounds, own entries
-    "k_react_candidates": 0.75 * (48 + 8 + 24 + 8),   # receptors only: pose, two bond words, 3 cell-row bounds, entries
+    "k_react_pairs": 0.1 * (48 + 96 + 16),              # pre-selected pairs only (~0.1 per molecule): both poses + bond words
     "k_grid_count": 18 + 1 + 4 + 4,
     "k_grid_scatter": 18 + 4 + 4 + 4,
     "k_restore": 4 + 1,

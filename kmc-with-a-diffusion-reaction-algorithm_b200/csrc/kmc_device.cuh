@@ -9,7 +9,8 @@ enum Scalar {
     S_MEMBER_CURSOR = 0,  // next free slot in members[]
     S_NCX,                // number of complexes (size > 1) in cxRoots[]
     S_NFAR,               // far movers this step
-    S_NUNKNOWN,           // units still undecided after a resolve pass
+    S_NUNK0, S_NUNK1,     // undecided units in list 0 / list 1 (ping-pong between resolve passes)
+    S_NPAIR,              // pre-selected reaction pairs of this step
     S_NCAND_RL, S_NCAND_CIS,
     S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
     S_OVERFLOW,           // a device buffer overflowed (bitmask)
@@ -44,6 +45,10 @@ struct Dev {
     // reaction candidates (successful draws only)
     unsigned long long *candRL, *candCis;
     int candCap;
+    unsigned long long *pairs; int pairCap;   // (receptor, neighbour) pairs that may react this step
+    int *unk;                                 // [2][NT] undecided unit heads
+    int *unitRes;                             // [NT] per unit head: bit0 definite overlap, bit1 overlap pending on an earlier unit
+    unsigned long long *step64;               // [1] mc_time_step of the step being computed
     int *scal;
     int *maxComplex;                       // [R]
     unsigned long long *events;

@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 21
+#define KMC_NKERNELS 23
 
 #include <algorithm>
 #include <cmath>
@@ -27,7 +27,7 @@ struct kmc_handle {
     bool stepped = false;            // complexes/accept data of a completed step are available
     std::vector<void *> allocs;
     int *d_series = nullptr;
-    int scanBlocks = 0;
+    int scanBlocks = 0, nTiles = 0;
     int64_t launches = 0, passes = 0;
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py roofline)
     bool profiling = false;
@@ -41,10 +41,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_rebuild_gate_clear", "k_propose_simple",
     "k_propose_complex", "memset_cellCount", "k_grid_count", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_zero_unknown", "k_resolve", "k_restore", "k_react_candidates", "k_react_resolve", "k_dissociate", "k_series"};
+    "k_resolve_tiles", "k_decide", "k_resolve_list", "k_resolve_finish", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series"};
 enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_GATE_CLEAR, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
-       KID_MEMSET, KID_GRID_COUNT, KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_ZERO_UNKNOWN, KID_RESOLVE,
-       KID_RESTORE, KID_REACT_CAND, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES };
+       KID_MEMSET, KID_GRID_COUNT, KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_DECIDE, KID_RESOLVE_LIST, KID_RESOLVE_FINISH,
+       KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -104,6 +104,15 @@ extern "C" void kmc_default_params(kmc_params *p) {
     p->cell_edge = 0; p->device = 0;
 }
 
+// smallest double T with sqrt(T) >= c, so that for every double d2:  sqrt(d2) < c  <=>  d2 < T  (IEEE sqrt is monotone and
+// correctly rounded). Lets the overlap kernels compare squared distances and still decide exactly like main.cpp:646.
+static double sq_threshold(double c) {
+    double T = c * c;
+    while (sqrt(T) >= c) T = nextafter(T, 0.0);
+    while (sqrt(T) < c) T = nextafter(T, INFINITY);
+    return T;
+}
+
 // derived constants with the reference's own expressions (host doubles, no contraction: see build flags)
 static void fill_consts(const kmc_params &P, Consts &K) {
     memset(&K, 0, sizeof K);
@@ -116,6 +125,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     K.bondCut = P.bond_dist_cut; K.thetaPdCut = P.thetapd_cut; K.thetaOtCut = P.thetaot_cut;
     K.cisThetaCut = P.cis_thetaot_cut; K.cisCut = P.cis_dist_cut;
     K.ovAA = P.rA + P.rA; K.ovAB = P.rA + P.rB; K.ovBB = P.rB + P.rB;
+    K.ovAA2 = sq_threshold(K.ovAA); K.ovAB2 = sq_threshold(K.ovAB); K.ovBB2 = sq_threshold(K.ovBB);
     K.rlD1 = P.bond_dist_cut / 2 + P.rA + P.rB; K.rlD2 = P.bond_dist_cut / 2;
     K.cisD1 = P.cis_dist_cut / 2 + P.rA + P.rA; K.cisD2 = P.cis_dist_cut / 2;
     K.fRL1 = (P.bond_dist_cut / 2 + P.rA) / P.rB; K.fRL3 = (P.bond_dist_cut / 2 + 2 * P.rA) / P.rB; K.fRL2 = (P.bond_dist_cut / 2) / P.rB;
@@ -133,7 +143,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     K.skin = 48.0;
     K.NA = P.n_receptor; K.NB = P.n_ligand; K.R = P.n_replicas; K.mode = P.mode;
     K.NAt = K.NA * K.R; K.NBt = K.NB * K.R; K.NT = K.NAt + K.NBt; K.seed = P.seed;
-    double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + K.skin + 1.0;
+    double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + 2 * K.skin + 1.0;   // walk around the OLD centre: reach + 2 skins
     if (P.cell_edge > edge) edge = P.cell_edge;
     else if (P.cell_edge == 0) edge = std::max(edge, 256.0);
     K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
@@ -186,9 +196,12 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
     A(cellCount, (size_t)D.ncell + 1); A(cellStart, (size_t)D.ncell + 1);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    h->nTiles = K.R * ((K.ncx + TS - 1) / TS) * ((K.ncy + TS - 1) / TS);
     A(scanTmp, (size_t)h->scanBlocks + 1);
     A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
+    D.pairCap = std::max(1 << 16, 4 * K.NAt);
+    A(pairs, D.pairCap); A(unk, (size_t)2 * K.NT); A(unitRes, K.NT); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
 #undef A
     ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 4) == cudaSuccess;
@@ -388,16 +401,15 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 // ------------------------------------------------------------------------------------------------
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
-__global__ void k_step_begin(const __grid_constant__ Args A) {
+__global__ void k_step_begin(const __grid_constant__ Args A, unsigned long long step) {
     KARGS
+    D.step64[0] = step;
     // per-step scalar reset; complexes are rebuilt only if the bond table changed (S_TOPO_DIRTY)
-    D.scal[S_NFAR] = 0; D.scal[S_NUNKNOWN] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+    D.scal[S_NFAR] = 0; D.scal[S_NUNK0] = 0; D.scal[S_NUNK1] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
 }
 __global__ void k_rebuild_gate_clear(const __grid_constant__ Args A) {
     KARGS D.scal[S_TOPO_DIRTY] = 0; }
-__global__ void k_zero_unknown(const __grid_constant__ Args A) {
-    KARGS D.scal[S_NUNKNOWN] = 0; }
 
 extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     if (!h) return KMC_ERR_INVALID;
@@ -408,7 +420,7 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     for (int64_t it = 0; it < n; it++) {
         const uint64_t step = (uint64_t)(h->step_done + 1);
         const Args A{D, h->K};
-        LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A)));
+        LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A, step)));
         // S1 (gated on device: no host round trip)
         LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
         LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
@@ -416,8 +428,8 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
         LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
         LAUNCH(KID_GATE_CLEAR, (k_rebuild_gate_clear<<<1, 1, 0, st>>>(A)));
         // S2 proposals
-        LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A, step)));
-        LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A, step)));
+        LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
+        LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A)));
         // grid
         LAUNCH(KID_MEMSET, (cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st)));
         LAUNCH(KID_GRID_COUNT, (k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A)));
@@ -425,24 +437,20 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
         LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks)));
         LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1)));
         LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        // S2g: resolve until every unit is decided
-        int scal[S_COUNT];
-        for (int pass = 0;; pass++) {
-            if (pass) LAUNCH(KID_ZERO_UNKNOWN, (k_zero_unknown<<<1, 1, 0, st>>>(A)));
-            LAUNCH(KID_RESOLVE, (k_resolve<<<nblk(NT, B), B, 0, st>>>(A)));
-            h->passes++;
-            CK(cudaMemcpyAsync(scal, D.scal, sizeof scal, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (scal[S_OVERFLOW]) { h->err = "device buffer overflow (mask " + std::to_string(scal[S_OVERFLOW]) + ")"; return KMC_ERR_CAPACITY; }
-            if (scal[S_NUNKNOWN] == 0) break;
-            if (pass > NT + 8) { h->err = "conflict resolution did not converge"; return KMC_ERR_CUDA; }
-        }
-        if (h->profiling) harvest(h, false);
+        // S2g: pass 1 over all units (+ reaction-pair pre-selection), pass 2 over the undecided list, then a one-CTA finish
+        // that iterates to the fixed point: no host round trip anywhere in the step
+        const int gl = std::min(nblk(NT, B), 148 * 8);
+        LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, 128, 0, st>>>(A)));
+        LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
+        LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<gl, B, 0, st>>>(A, 0)));
+        LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));
+        h->passes += 3;
         LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
         // S3
-        LAUNCH(KID_REACT_CAND, (k_react_candidates<<<nblk(std::max(NAt, 1), B), B, 0, st>>>(A, step)));
+        LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<gl, B, 0, st>>>(A)));
         LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
-        LAUNCH(KID_DISSOCIATE, (k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, step)));
+        LAUNCH(KID_DISSOCIATE, (k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+        if (h->profiling && (it & 15) == 15) harvest(h, false);
         // S4: the new buffers become the committed state
         std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign);
         h->step_done++; h->stepped = true;

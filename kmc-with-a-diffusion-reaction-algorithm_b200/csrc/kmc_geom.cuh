@@ -33,6 +33,7 @@ struct Consts {
     double pOn, pMonoCisOn, pCisOn, pOff, pMonoCisOff, pCisOff;   // rate*dt     1918, 1984, 2038, 2069, 2104, 2127
     double bondCut, thetaPdCut, thetaOtCut, cisThetaCut, cisCut;
     double ovAA, ovAB, ovBB;                  // rA+rA, rA+rB, rB+rB     main.cpp:646, 659, 1806
+    double ovAA2, ovAB2, ovBB2;               // exact squared thresholds: sqrt_rn(d2) < ov  <=>  d2 < ov2 (see sq_threshold)
     double rlD1, rlD2;                        // bondCut/2+rA+rB, bondCut/2      main.cpp:1215
     double cisD1, cisD2;                      // cisCut/2+rA+rA, cisCut/2        main.cpp:780-781
     double fRL1, fRL3, fRL2;                  // (bondCut/2+rA)/rB, (bondCut/2+2rA)/rB, (bondCut/2)/rB   1217-1227
@@ -97,14 +98,13 @@ KD bool are_same(double a, double b) { return fabs(sub(a, b)) < 1.0E-8; }   // m
 // ---- overlap predicates (main.cpp:640-664, 1768-1826) ----
 KD bool hit_rec_rec(const Consts &K, double ax, double ay, double bx, double by) {
     // bead-1 centres; both z are 0 so the z term adds an exact +0 (main.cpp:642-646)
-    return dist2d(bx, by, ax, ay) < K.ovAA;
+    return add(sq(sub(bx, ax)), sq(sub(by, ay))) < K.ovAA2;      // == sqrt(...) < ovAA, without the sqrt
 }
 KD bool hit_rec_lig(const Consts &K, double ax, double ay, const Lig &l) {
     for (int j = 1; j <= 3; j++) {
         double d2 = add(sq(sub(l.p[j][0], ax)), sq(sub(l.p[j][1], ay)));
         for (int k = 1; k <= 4; k++) {
-            double d = sqrt(add(d2, sq(sub(l.p[j][2], rec_bead_z(K, k)))));
-            if (d < K.ovAB) return true;
+            if (add(d2, sq(sub(l.p[j][2], rec_bead_z(K, k)))) < K.ovAB2) return true;
         }
     }
     return false;
@@ -112,7 +112,7 @@ KD bool hit_rec_lig(const Consts &K, double ax, double ay, const Lig &l) {
 KD bool hit_lig_lig(const Consts &K, const Lig &a, const Lig &b) {
     for (int j = 1; j <= 3; j++)
         for (int k = 1; k <= 3; k++)
-            if (dist3d(a.p[j][0], a.p[j][1], a.p[j][2], b.p[k][0], b.p[k][1], b.p[k][2]) < K.ovBB) return true;
+            if (add(add(sq(sub(a.p[j][0], b.p[k][0])), sq(sub(a.p[j][1], b.p[k][1]))), sq(sub(a.p[j][2], b.p[k][2]))) < K.ovBB2) return true;
     return false;
 }
 

@@ -120,8 +120,9 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
 }
 
 // free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
-__global__ void k_propose_simple(const __grid_constant__ Args A, uint64_t step) {
+__global__ void k_propose_simple(const __grid_constant__ Args A) {
     KARGS
+    const uint64_t step = D.step64[0];
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= cK.NT) return;
     if (D.unitOf[gid] != gid) return;             // not the head of a unit
@@ -183,7 +184,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A, uint64_t step) 
             mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy);
             mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy);
         }
-        D.unitState[gid] = U_UNKNOWN;
+        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0;
     } else {
         const int h = gid - K.NAt;
         if (D.cxSize[h] > 1) return;             // complexes: k_propose_complex
@@ -212,7 +213,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A, uint64_t step) 
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
         store_lig(D.lign, h, n);
         mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1]);
-        D.unitState[gid] = U_UNKNOWN;
+        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0;
     }
 }
 
@@ -284,8 +285,9 @@ KD void shuffle_row(int *row, int size, uint64_t seed, uint32_t root, uint32_t &
     }
 }
 
-__global__ void k_propose_complex(const __grid_constant__ Args A, uint64_t step) {
+__global__ void k_propose_complex(const __grid_constant__ Args A) {
     KARGS
+    const uint64_t step = D.step64[0];
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= D.scal[S_NCX]) return;
     const Consts &K = cK;
@@ -435,7 +437,7 @@ __global__ void k_propose_complex(const __grid_constant__ Args A, uint64_t step)
         if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
         else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
     }
-    D.unitState[rootGid] = U_UNKNOWN;
+    D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -526,18 +528,44 @@ __global__ void k_scan_down(const int *in, const int *blockSums, int *out, int n
 }
 
 // ------------------------------------------------------------------------------------------------
-// S2g with ordering: decide accept/reject of every unit
+// S2g with ordering: decide accept/reject of every unit. The same neighbour walk also collects the (few) molecule
+// pairs that can possibly react in S3, so the reaction stage never walks the grid again.
 // ------------------------------------------------------------------------------------------------
-struct Probe { bool rec; double cx, cy; Lig l; };   // a member of the unit under test at its PROPOSED pose
+// a member of the unit under test at its PROPOSED pose: receptor = centre only, ligand = centre + three beads
+struct Probe { bool rec; double cx, cy; double b[3][3]; };
 
 template <class F> KD void for_cells3x3(const Consts &cK, int rep, double x, double y, const Dev &D, F f) {
     int cx = (int)floor((x - cK.gx0) * cK.cellInv), cy = (int)floor((y - cK.gy0) * cK.cellInv);
     cx = min(max(cx, 0), cK.ncx - 1); cy = min(max(cy, 0), cK.ncy - 1);
-    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, cK.ncy - 1); yy++) {
-        int c0 = (rep * cK.ncy + yy) * cK.ncx + max(cx - 1, 0), c1 = (rep * cK.ncy + yy) * cK.ncx + min(cx + 1, cK.ncx - 1);
-        int e0 = D.cellStart[c0], e1 = D.cellStart[c1 + 1];       // the three cells of a row are contiguous
-        for (int e = e0; e < e1; e++) f(D.sorted[e]);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, cK.ncx - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, cK.ncy - 1);
+    int e0[3], e1[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {                         // the three cells of a row are contiguous in `sorted`
+        int yy = min(y0 + r, y1), base = (rep * cK.ncy + yy) * cK.ncx;
+        e0[r] = __ldg(&D.cellStart[base + x0]); e1[r] = (y0 + r <= y1) ? __ldg(&D.cellStart[base + x1 + 1]) : e0[r];
     }
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        for (int e = e0[r]; e < e1[r]; e++) f(__ldg(&D.sorted[e]));
+}
+KD bool hit_rec_beads(const Consts &K, double ax, double ay, const double b[3][3]) {
+    for (int j = 0; j < 3; j++) {
+        double d2 = add(sq(sub(b[j][0], ax)), sq(sub(b[j][1], ay)));
+        for (int k = 1; k <= 4; k++)
+            if (add(d2, sq(sub(b[j][2], rec_bead_z(K, k)))) < K.ovAB2) return true;
+    }
+    return false;
+}
+KD bool hit_beads_beads(const Consts &K, const double a[3][3], const double b[3][3]) {
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++)
+            if (add(add(sq(sub(a[j][0], b[k][0])), sq(sub(a[j][1], b[k][1]))), sq(sub(a[j][2], b[k][2]))) < K.ovBB2) return true;
+    return false;
+}
+KD void load_beads(const double *base, int h, double b[3][3]) {
+    const double *q = base + (size_t)h * 24 + 3;
+#pragma unroll
+    for (int i = 0; i < 9; i++) (&b[0][0])[i] = q[i];
 }
 // does probe (proposed pose of member m) overlap molecule v taken at its old (nxt=false) or proposed pose?
 KD bool probe_hits(const Consts &K, const Dev &D, const Probe &P, int v, bool nxt) {
@@ -546,29 +574,60 @@ KD bool probe_hits(const Consts &K, const Dev &D, const Probe &P, int v, bool nx
         if (P.rec) return hit_rec_rec(K, P.cx, P.cy, c.x, c.y);
         double dx = c.x - P.cx, dy = c.y - P.cy;
         if (dx * dx + dy * dy > K.reachRL * K.reachRL) return false;
-        return hit_rec_lig(K, c.x, c.y, P.l);
+        return hit_rec_beads(K, c.x, c.y, P.b);
     }
     const double *base = nxt ? D.lign : D.lig;
     const double *pc = base + (size_t)(v - K.NAt) * 24;
     double dx = pc[0] - P.cx, dy = pc[1] - P.cy, r = P.rec ? K.reachRL : K.reachLL;
     if (dx * dx + dy * dy > r * r) return false;
-    Lig o; load_lig_beads(base, v - K.NAt, o);
-    return P.rec ? hit_rec_lig(K, P.cx, P.cy, o) : hit_lig_lig(K, o, P.l);
+    double ob[3][3]; load_beads(base, v - K.NAt, ob);
+    return P.rec ? hit_rec_beads(K, P.cx, P.cy, ob) : hit_beads_beads(K, ob, P.b);
 }
 
 // order of the sweep: true if unit head `v` is processed before unit head `u`
 KD bool unit_before(int v, int u) { return v < u; }
 
+// S3 pre-selection: receptor a (walked as probe) and neighbour v can only react if their FINAL centres come within
+// `reach`; each final centre is the old or the proposed one, so the minimum over those combinations is a safe bound.
+KD void maybe_pair(const Consts &K, const Dev &D, int a, bool aFreeRL, bool aFreeCis, double pax, double pay, double oax, double oay,
+                   int v, bool ghost, bool vfar) {
+    const bool lig = v >= K.NAt;
+    if (lig ? !aFreeRL : (!aFreeCis || v == a)) return;
+    const double reach = lig ? K.reachOn : K.reachCis;
+    double ovx, ovy, pvx, pvy;
+    centre_of(K, D, v, ghost, ovx, ovy);                          // the position this entry stands for
+    const double lim = reach + 2 * K.skin;
+    double d2 = min((ovx - pax) * (ovx - pax) + (ovy - pay) * (ovy - pay), (ovx - oax) * (ovx - oax) + (ovy - oay) * (ovy - oay));
+    if (d2 > lim * lim) return;                                   // cheap cut with the displacement skins
+    if (!ghost && !vfar) {
+        centre_of(K, D, v, true, pvx, pvy);
+        d2 = min(d2, min((pvx - pax) * (pvx - pax) + (pvy - pay) * (pvy - pay), (pvx - oax) * (pvx - oax) + (pvy - oay) * (pvy - oay)));
+    }
+    if (d2 > reach * reach) return;
+    if (lig) { const int *o = D.ligRec + (size_t)(v - K.NAt) * 3; if (o[0] >= 0 && o[1] >= 0 && o[2] >= 0) return; }
+    else if (D.recCis[v] >= 0) return;
+    int q = atomicAdd(&D.scal[S_NPAIR], 1);
+    if (q < D.pairCap) D.pairs[q] = ((unsigned long long)a << 32) | (unsigned)v;
+    else atomicOr(&D.scal[S_OVERFLOW], 4);
+}
+
 // one member against everything around it; returns flags: bit0 definite overlap, bit1 overlap depends on an undecided earlier unit
-KD int test_member(const Consts &cK, const Dev &D, int u, int m, const Probe &P, int rep) {
+template <bool PAIRS> KD int test_member(const Consts &cK, const Dev &D, int u, int m, const Probe &P, int rep) {
     int res = 0;
+    bool aFreeRL = false, aFreeCis = false; double oax = 0, oay = 0;
+    if (PAIRS && P.rec) {
+        aFreeRL = D.recLig[m] < 0; aFreeCis = D.recCis[m] < 0;
+        double2 o = D.recC[m]; oax = o.x; oay = o.y;
+    }
+    const bool wantPairs = PAIRS && P.rec && (aFreeRL || aFreeCis);
     for_cells3x3(cK, rep, P.cx, P.cy, D, [&](int e) {
-        if (res & 1) return;
         const bool ghost = (e & GHOST_BIT) != 0;
         const int v = e & ~GHOST_BIT;
         if (v == m) return;
         const int uv = D.unitOf[v];
         const bool far = D.farFlag[v] != 0;
+        if (wantPairs) maybe_pair(cK, D, m, aFreeRL, aFreeCis, P.cx, P.cy, oax, oay, v, ghost, far);
+        if (res & 1) return;
         if (uv == u) {                                   // co-moving member: proposed pose, once (Q20)
             if (ghost != far) return;
             if (probe_hits(cK, D, P, v, true)) res |= 1;
@@ -588,42 +647,266 @@ KD int test_member(const Consts &cK, const Dev &D, int u, int m, const Probe &P,
             }
         }
     });
+    // a far mover that ends up rejected stays at its old place: its possible partners there are collected as well
+    if (wantPairs && D.farFlag[m])
+        for_cells3x3(cK, rep, oax, oay, D, [&](int e) {
+            const int v = e & ~GHOST_BIT;
+            if (v != m) maybe_pair(cK, D, m, aFreeRL, aFreeCis, P.cx, P.cy, oax, oay, v, (e & GHOST_BIT) != 0, D.farFlag[v] != 0);
+        });
     return res;
 }
 
-__global__ void k_resolve(const __grid_constant__ Args A) {
-    KARGS
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= cK.NT) return;
-    if (D.unitOf[gid] != gid || D.unitState[gid] != U_UNKNOWN) return;
-    const Consts &K = cK;
+KD void load_probe(const Consts &K, const Dev &D, int m, Probe &P) {
+    if (m < K.NAt) { double2 c = D.recCn[m]; P.rec = true; P.cx = c.x; P.cy = c.y; }
+    else {
+        const double *q = D.lign + (size_t)(m - K.NAt) * 24;
+        P.rec = false; P.cx = q[0]; P.cy = q[1];
+#pragma unroll
+        for (int i = 0; i < 9; i++) (&P.b[0][0])[i] = q[3 + i];
+    }
+}
+// evaluates unit `gid` (a head, currently undecided); writes its state if decidable; returns true if still undecided
+template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) {
     const int rep = replica_of_gid(K, gid);
     int res = 0;
     Probe P;
     if (gid < K.NAt) {
-        double2 c = D.recCn[gid];
-        P.rec = true; P.cx = c.x; P.cy = c.y;
-        res |= test_member(cK, D, gid, gid, P, rep);
+        load_probe(K, D, gid, P);
+        res |= test_member<PAIRS>(K, D, gid, gid, P, rep);
         int p = D.recCis[gid];
-        if (p >= 0 && !(res & 1)) { c = D.recCn[p]; P.cx = c.x; P.cy = c.y; res |= test_member(cK, D, gid, p, P, rep); }
+        if (p >= 0 && (PAIRS || !(res & 1))) { load_probe(K, D, p, P); res |= test_member<PAIRS>(K, D, gid, p, P, rep); }
     } else {
         const int h = gid - K.NAt, size = D.cxSize[h];
-        if (size <= 1) {
-            P.rec = false; load_lig_beads(D.lign, h, P.l); P.cx = P.l.p[0][0]; P.cy = P.l.p[0][1];
-            res |= test_member(cK, D, gid, gid, P, rep);
-        } else {
+        if (size <= 1) { load_probe(K, D, gid, P); res |= test_member<PAIRS>(K, D, gid, gid, P, rep); }
+        else {
             const int *row = D.rowWork + D.cxOff[h];
-            for (int i = 0; i < size && !(res & 1); i++) {
-                int m = row[i];
-                if (m < K.NAt) { double2 c = D.recCn[m]; P.rec = true; P.cx = c.x; P.cy = c.y; }
-                else { P.rec = false; load_lig_beads(D.lign, m - K.NAt, P.l); P.cx = P.l.p[0][0]; P.cy = P.l.p[0][1]; }
-                res |= test_member(cK, D, gid, m, P, rep);
-            }
+            for (int i = 0; i < size && (PAIRS || !(res & 1)); i++) { int m = row[i]; load_probe(K, D, m, P); res |= test_member<PAIRS>(K, D, gid, m, P, rep); }
         }
     }
-    if (res & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); }
-    else if (res & 2) atomicAdd(&D.scal[S_NUNKNOWN], 1);
+    if (res & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); return false; }
+    if (res & 2) return true;
+    D.unitState[gid] = U_ACCEPT;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2g pass 1, tile kernel: one CTA owns a TS x TS block of grid cells. The cell-sorted entries of the block and of
+// the ring of cells around it are staged in shared memory once (cooperative gather: centre old/new, unit, flags),
+// then every molecule whose entry lies in the block is tested against its 3x3 cell neighbourhood out of shared
+// memory. Receptor-receptor tests (the bulk) never touch global memory again; ligand beads are fetched only for
+// pairs whose centres are within reach. The same walk pre-selects the pairs that can react in S3.
+//
+// Walk geometry: the entry of a molecule sits in the cell of its OLD centre O; its proposal P is at most `skin` away
+// (else it is a far mover with a ghost entry at cell(P)), and so is every neighbour's, hence everything P can touch
+// has an entry within reach + 2*skin of O: the 3x3 cells around cell(O) suffice because edge >= reach + 2*skin.
+// ------------------------------------------------------------------------------------------------
+#define TS 16
+#define TCAP 896
+#define F_FAR 1
+#define F_GHOST 2
+#define F_FREE_RL 4      // receptor: no ligand bound / ligand: at least one free site
+#define F_FREE_CIS 8
+
+struct TileRec { double ox, oy, nx, ny; int gid, unit; int flg; };
+
+KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
+    TileRec r;
+    const int v = entry & ~GHOST_BIT;
+    r.gid = v; r.unit = D.unitOf[v];
+    int f = (D.farFlag[v] ? F_FAR : 0) | ((entry & GHOST_BIT) ? F_GHOST : 0);
+    if (v < K.NAt) {
+        double2 o = D.recC[v], n = D.recCn[v];
+        r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y;
+        if (D.recLig[v] < 0) f |= F_FREE_RL;
+        if (D.recCis[v] < 0) f |= F_FREE_CIS;
+    } else {
+        const int h = v - K.NAt;
+        const double *o = D.lig + (size_t)h * 24, *n = D.lign + (size_t)h * 24;
+        r.ox = o[0]; r.oy = o[1]; r.nx = n[0]; r.ny = n[1];
+        const int *occ = D.ligRec + (size_t)h * 3;
+        if (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) f |= F_FREE_RL;
+    }
+    r.flg = f;
+    return r;
+}
+
+struct TileSmem {
+    int cs[TS + 2][TS + 3];       // cellStart of the window: rows wy0..wy1, columns wx0..wx1+1
+    int rowBase[TS + 3];          // index (in staged order) of the first entry of each window row
+    int inBase[TS + 1];           // prefix of interior entries per interior row
+    double ox[TCAP], oy[TCAP], nx[TCAP], ny[TCAP];
+    int gid[TCAP], unit[TCAP];
+    unsigned char flg[TCAP];
+};
+
+// precise overlap test of probe (proposed pose) against neighbour v at old / proposed pose, centres already known
+KD bool tile_hits(const Consts &K, const Dev &D, bool prec, double px, double py, const double pb[3][3], int v, double vx, double vy, bool nxt) {
+    const bool vrec = v < K.NAt;
+    const double dx = vx - px, dy = vy - py, d2 = dx * dx + dy * dy;
+    if (prec && vrec) return hit_rec_rec(K, px, py, vx, vy);
+    const double r = (prec || vrec) ? K.reachRL : K.reachLL;
+    if (d2 > r * r) return false;
+    if (vrec) return hit_rec_beads(K, vx, vy, pb);
+    double ob[3][3]; load_beads(nxt ? D.lign : D.lig, v - K.NAt, ob);
+    return prec ? hit_rec_beads(K, px, py, ob) : hit_beads_beads(K, ob, pb);
+}
+
+__global__ void __launch_bounds__(128) k_resolve_tiles(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    __shared__ TileSmem S;
+    const int ntx = (K.ncx + TS - 1) / TS, nty = (K.ncy + TS - 1) / TS;
+    int b = blockIdx.x;
+    const int tx = b % ntx; b /= ntx;
+    const int ty = b % nty; const int rep = b / nty;
+    const int x0 = tx * TS, x1 = min(x0 + TS - 1, K.ncx - 1), y0 = ty * TS, y1 = min(y0 + TS - 1, K.ncy - 1);
+    const int wx0 = max(x0 - 1, 0), wx1 = min(x1 + 1, K.ncx - 1), wy0 = max(y0 - 1, 0), wy1 = min(y1 + 1, K.ncy - 1);
+    const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 2;
+    for (int i = threadIdx.x; i < nrow * ncol; i += blockDim.x) {
+        int r = i / ncol, c = i % ncol;
+        S.cs[r][c] = __ldg(&D.cellStart[(rep * K.ncy + wy0 + r) * K.ncx + wx0 + c]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0, in = 0;
+        for (int r = 0; r < nrow; r++) { S.rowBase[r] = acc; acc += S.cs[r][ncol - 1] - S.cs[r][0]; }
+        S.rowBase[nrow] = acc;
+        for (int r = 0; r <= y1 - y0; r++) {
+            int wr = y0 - wy0 + r;
+            S.inBase[r] = in; in += S.cs[wr][x1 + 1 - wx0] - S.cs[wr][x0 - wx0];
+        }
+        S.inBase[y1 - y0 + 1] = in;
+    }
+    __syncthreads();
+    const int total = S.rowBase[nrow];
+    // stage the window (first TCAP entries; the rest, if a tile is that crowded, is read from global memory on demand)
+    for (int i = threadIdx.x; i < min(total, TCAP); i += blockDim.x) {
+        int r = 0; while (i >= S.rowBase[r + 1]) r++;
+        TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.cs[r][0] + (i - S.rowBase[r])]));
+        S.ox[i] = t.ox; S.oy[i] = t.oy; S.nx[i] = t.nx; S.ny[i] = t.ny; S.gid[i] = t.gid; S.unit[i] = t.unit; S.flg[i] = (unsigned char)t.flg;
+    }
+    __syncthreads();
+    auto rec_at = [&](int r, int e) -> TileRec {      // entry with global index e in window row r
+        int i = S.rowBase[r] + (e - S.cs[r][0]);
+        if (i < TCAP) { TileRec t; t.ox = S.ox[i]; t.oy = S.oy[i]; t.nx = S.nx[i]; t.ny = S.ny[i]; t.gid = S.gid[i]; t.unit = S.unit[i]; t.flg = S.flg[i]; return t; }
+        return fetch_rec(K, D, __ldg(&D.sorted[e]));
+    };
+    const int nin = S.inBase[y1 - y0 + 1];
+    for (int q = threadIdx.x; q < nin; q += blockDim.x) {
+        int ir = 0; while (q >= S.inBase[ir + 1]) ir++;
+        const int wr = y0 - wy0 + ir;
+        const TileRec me = rec_at(wr, S.cs[wr][x0 - wx0] + (q - S.inBase[ir]));
+        const int m = me.gid, u = me.unit;
+        const bool ghost = me.flg & F_GHOST, far = me.flg & F_FAR, prec = m < K.NAt;
+        const bool pairsOnly = !ghost && far;           // old entry of a far mover: it is only a reaction partner here
+        // walk centre: cell of the position this entry stands for
+        const double wxp = ghost ? me.nx : me.ox, wyp = ghost ? me.ny : me.oy;
+        int cx = min(max((int)floor((wxp - K.gx0) * K.cellInv), 0), K.ncx - 1);
+        const int cxl = max(cx - 1, 0) - wx0, cxh = min(cx + 1, K.ncx - 1) + 1 - wx0;
+        // probe = proposed pose; for reaction pre-selection the final centre is P or O (ghost: P only; far old entry: O only)
+        const double px = me.nx, py = me.ny;
+        const double fax = pairsOnly ? me.ox : px, fay = pairsOnly ? me.oy : py;          // first candidate final centre
+        const double fbx = ghost ? px : me.ox, fby = ghost ? py : me.oy;                  // second candidate final centre
+        double pb[3][3];
+        if (!prec && !pairsOnly) load_beads(D.lign, m - K.NAt, pb);
+        const bool wantPairs = prec && (me.flg & (F_FREE_RL | F_FREE_CIS));
+        // measured from (fax,fay) = P, or O for the old entry of a far mover
+        const double cutR = (prec ? fmax(K.reachRL, K.reachOn) : K.reachLL) + 2 * K.skin;
+        const double cut2 = cutR * cutR;
+        int res = 0;
+        for (int dr = -1; dr <= 1; dr++) {
+            const int r = wr + dr;
+            if (r < 0 || r >= nrow) continue;
+            const int e0 = S.cs[r][cxl], e1 = S.cs[r][cxh];
+            for (int e = e0; e < e1; e++) {
+                {   // early cut on the staged centre of this entry: nothing within reach of either pose of either molecule
+                    const int i = S.rowBase[r] + (e - S.cs[r][0]);
+                    if (i < TCAP) {
+                        const bool g = S.flg[i] & F_GHOST;
+                        const double ex = (g ? S.nx[i] : S.ox[i]) - fax, ey = (g ? S.ny[i] : S.oy[i]) - fay;
+                        if (ex * ex + ey * ey > cut2) continue;
+                    }
+                }
+                const TileRec o = rec_at(r, e);
+                const int v = o.gid;
+                if (v == m) continue;
+                const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
+                if (wantPairs) {
+                    const bool vlig = v >= K.NAt;
+                    if (vlig ? ((me.flg & F_FREE_RL) && (o.flg & F_FREE_RL)) : ((me.flg & F_FREE_CIS) && (o.flg & F_FREE_CIS))) {
+                        const double reach = vlig ? K.reachOn : K.reachCis;
+                        const double vx = vghost ? o.nx : o.ox, vy = vghost ? o.ny : o.oy;
+                        double d2 = min((vx - fax) * (vx - fax) + (vy - fay) * (vy - fay), (vx - fbx) * (vx - fbx) + (vy - fby) * (vy - fby));
+                        if (!vghost && !vfar)
+                            d2 = min(d2, min((o.nx - fax) * (o.nx - fax) + (o.ny - fay) * (o.ny - fay), (o.nx - fbx) * (o.nx - fbx) + (o.ny - fby) * (o.ny - fby)));
+                        if (d2 <= reach * reach) {
+                            int p = atomicAdd(&D.scal[S_NPAIR], 1);
+                            if (p < D.pairCap) D.pairs[p] = ((unsigned long long)m << 32) | (unsigned)v;
+                            else atomicOr(&D.scal[S_OVERFLOW], 4);
+                        }
+                    }
+                }
+                if (pairsOnly || (res & 1)) continue;
+                const int uv = o.unit;
+                if (uv == u) {                                   // co-moving member: proposed pose, once (Q20)
+                    if (vghost != vfar) continue;
+                    if (tile_hits(K, D, prec, px, py, pb, v, o.nx, o.ny, true)) res |= 1;
+                } else if (!unit_before(uv, u)) {                // later unit: still at its old pose
+                    if (!vghost && tile_hits(K, D, prec, px, py, pb, v, o.ox, o.oy, false)) res |= 1;
+                } else if (vghost) {                             // earlier unit (undecided in pass 1): both poses possible
+                    if (tile_hits(K, D, prec, px, py, pb, v, o.nx, o.ny, true)) res |= 2;
+                } else {
+                    const bool hitOld = tile_hits(K, D, prec, px, py, pb, v, o.ox, o.oy, false);
+                    const bool hitNew = !vfar && tile_hits(K, D, prec, px, py, pb, v, o.nx, o.ny, true);
+                    if (hitOld && hitNew) res |= 1; else if (hitOld || hitNew) res |= 2;
+                }
+            }
+        }
+        if (res) atomicOr(&D.unitRes[u], res);
+    }
+}
+// after the tile pass: settle every unit whose members found nothing or a definite overlap; the rest (overlap only
+// with one pose of an earlier unit) goes to the undecided list and is settled in order by k_resolve_list/_finish
+__global__ void k_decide(const __grid_constant__ Args A) {
+    KARGS
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= cK.NT || D.unitOf[gid] != gid) return;
+    const int r = D.unitRes[gid];
+    if (r & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); }
+    else if (r & 2) D.unk[atomicAdd(&D.scal[S_NUNK0], 1)] = gid;
     else D.unitState[gid] = U_ACCEPT;
+}
+
+// pass 2: the undecided units of list `from` in parallel; what is still undecided goes to the other list
+__global__ void __launch_bounds__(128) k_resolve_list(const __grid_constant__ Args A, int from) {
+    KARGS
+    const int n = D.scal[S_NUNK0 + from];
+    const int *in = D.unk + (size_t)from * cK.NT; int *out = D.unk + (size_t)(1 - from) * cK.NT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int gid = in[i];
+        if (eval_unit<false>(cK, D, gid)) out[atomicAdd(&D.scal[S_NUNK0 + 1 - from], 1)] = gid;
+    }
+}
+// final pass, one CTA: iterate over list `from` until everything is decided (the lowest undecided unit is always
+// decidable, so every sweep makes progress); normally the list is empty or a handful of units
+__global__ void __launch_bounds__(256) k_resolve_finish(const __grid_constant__ Args A, int from) {
+    KARGS
+    __shared__ int remaining;
+    const int n = D.scal[S_NUNK0 + from];
+    const int *in = D.unk + (size_t)from * cK.NT;
+    for (int sweep = 0; sweep <= n; sweep++) {
+        if (threadIdx.x == 0) remaining = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int gid = in[i];
+            if (((volatile unsigned char *)D.unitState)[gid] == U_UNKNOWN && eval_unit<false>(cK, D, gid)) atomicAdd(&remaining, 1);
+        }
+        __threadfence();
+        __syncthreads();
+        if (remaining == 0) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && remaining != 0) atomicOr(&D.scal[S_OVERFLOW], 8);   // cannot happen: progress is guaranteed
 }
 
 // revert the members of rejected units (main.cpp:666-674, 851-863, 1831-1860)
@@ -644,37 +927,28 @@ __global__ void k_restore(const __grid_constant__ Args A) {
 // ------------------------------------------------------------------------------------------------
 // S3 reactions
 // ------------------------------------------------------------------------------------------------
-// entry validity after k_restore: a molecule is at its old-cell entry unless it is a far mover, then at its ghost
-KD bool entry_live(const Dev &D, int e) { return ((e & GHOST_BIT) != 0) == (D.farFlag[e & ~GHOST_BIT] != 0); }
-
-// one thread per receptor: geometric candidates whose keyed draw succeeds are appended (a failed draw never
-// changes anything, main.cpp:1921/1987/2041), ordered resolution happens in k_react_resolve
-__global__ void k_react_candidates(const __grid_constant__ Args A, uint64_t step) {
+// one thread per pre-selected pair (receptor a, neighbour v), final poses: geometric tests of main.cpp:1882-1915 /
+// 1960-1981 / 2014-2035; candidates whose keyed draw succeeds are appended (a failed draw never changes anything,
+// main.cpp:1921/1987/2041); the ordered, first-come-first-served application happens in k_react_resolve
+__global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Args A) {
     KARGS
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= cK.NAt) return;
     const Consts &K = cK;
-    const bool freeRL = D.recLig[a] < 0, freeCis = D.recCis[a] < 0;
-    if (!freeRL && !freeCis) return;
-    const int rep = a / K.NA;
-    const uint64_t seed = seed_of(cK, rep);
-    const uint32_t me = ref_id(K, a);
-    const Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
-    for_cells3x3(cK, rep, ra.cx, ra.cy, D, [&](int e) {
-        if (!entry_live(D, e)) return;
-        const int v = e & ~GHOST_BIT;
+    const uint64_t step = D.step64[0];
+    const int n = min(D.scal[S_NPAIR], D.pairCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long pr = D.pairs[i];
+        const int a = (int)(pr >> 32), v = (int)(pr & 0xffffffffu);
+        const int rep = a / K.NA;
+        const uint64_t seed = seed_of(K, rep);
+        const uint32_t me = ref_id(K, a), j = ref_id(K, v);
+        const Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
         if (v >= K.NAt) {
-            if (!freeRL) return;
+            if (D.recLig[a] >= 0) continue;
             const int h = v - K.NAt;
-            const double *pc = D.lign + (size_t)h * 24;
-            double dx = pc[0] - ra.cx, dy = pc[1] - ra.cy;
-            if (dx * dx + dy * dy > K.reachOn * K.reachOn) return;
             int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
-            if (occ[0] >= 0 && occ[1] >= 0 && occ[2] >= 0) return;
             Lig b; load_lig(D.lign, h, b);
             for (int s = 0; s < 3; s++) {
                 if (occ[s] >= 0 || !rl_geometry_ok(K, ra, b, s)) continue;
-                const uint32_t j = ref_id(K, v);
                 if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
                     int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
                     if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
@@ -682,10 +956,9 @@ __global__ void k_react_candidates(const __grid_constant__ Args A, uint64_t step
                 }
             }
         } else {
-            if (!freeCis || v == a || D.recCis[v] >= 0) return;
+            if (D.recCis[a] >= 0 || D.recCis[v] >= 0) continue;
             const Rec rb = load_rec(D.recCn, D.recS2n, D.recS3n, v);
-            if (!cis_geometry_ok(K, ra, rb)) return;
-            const uint32_t j = ref_id(K, v);
+            if (!cis_geometry_ok(K, ra, rb)) continue;
             const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
             const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
             if (okMono || okCis) {
@@ -694,7 +967,7 @@ __global__ void k_react_candidates(const __grid_constant__ Args A, uint64_t step
                 else atomicOr(&D.scal[S_OVERFLOW], 2);
             }
         }
-    });
+    }
 }
 
 // single CTA: order the successful candidates as the reference's loops would meet them, then apply them
@@ -721,6 +994,7 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
     int ev_rl = 0, ev_mono = 0, ev_cis = 0;
     for (int q = 0; q < nRL; q++) {
         unsigned long long key = rl[q];
+        if (q && key == rl[q - 1]) continue;             // the same pair can be pre-selected twice (far movers)
         int a = (int)(key >> 32), h = (int)((key & 0xffffffffULL) >> 2), s = (int)(key & 3);
         if (D.recLig[a] < 0 && D.ligRec[h * 3 + s] < 0) {
             D.recLig[a] = h; D.recSite[a] = s; D.ligRec[h * 3 + s] = a; ev_rl++;
@@ -729,7 +1003,7 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
     for (int variant = 1; variant <= 2; variant++)
         for (int q = 0; q < nCis; q++) {
             unsigned long long key = cis[q];
-            if (!(key & (unsigned)variant)) continue;
+            if (!(key & (unsigned)variant) || (q && key == cis[q - 1])) continue;
             int a = (int)(key >> 32), b = (int)((key & 0xffffffffULL) >> 2);
             if (D.recCis[a] >= 0 || D.recCis[b] >= 0) continue;
             bool anyLig = D.recLig[a] >= 0 || D.recLig[b] >= 0;
@@ -746,8 +1020,9 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
 // S3c, main.cpp:2062-2141. Keyed draws make the three sequential loops order free: a thread owns the R-L bond of
 // its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L outcome from the
 // partner's own keyed draw instead of waiting for it.
-__global__ void k_dissociate(const __grid_constant__ Args A, uint64_t step) {
+__global__ void k_dissociate(const __grid_constant__ Args A) {
     KARGS
+    const uint64_t step = D.step64[0];
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= cK.NAt) return;
     const Consts &K = cK;
