@@ -47,6 +47,7 @@ struct Dev {
     int candCap;
     unsigned long long *pairs; int pairCap;   // (receptor, neighbour) pairs that may react this step
     int *unk;                                 // [2][NT] undecided unit heads
+    int *pend;                                // [NT] single pending conflict of a unit: earlier unit | pose bit, -1 none
     int *unitRes;                             // [NT] per unit head: bit0 definite overlap, bit1 overlap pending on an earlier unit
     unsigned long long *step64;               // [1] mc_time_step of the step being computed
     int *scal;

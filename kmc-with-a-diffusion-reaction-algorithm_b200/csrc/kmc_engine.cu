@@ -201,7 +201,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
-    A(pairs, D.pairCap); A(unk, (size_t)2 * K.NT); A(unitRes, K.NT); A(step64, 1);
+    A(pairs, D.pairCap); A(unk, (size_t)2 * K.NT); A(unitRes, K.NT); A(pend, K.NT); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
 #undef A
     ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 4) == cudaSuccess;
@@ -440,7 +440,7 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
         // S2g: pass 1 over all units (+ reaction-pair pre-selection), pass 2 over the undecided list, then a one-CTA finish
         // that iterates to the fixed point: no host round trip anywhere in the step
         const int gl = std::min(nblk(NT, B), 148 * 8);
-        LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, 128, 0, st>>>(A)));
+        LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
         LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
         LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<gl, B, 0, st>>>(A, 0)));
         LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));

@@ -86,7 +86,7 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     if (h >= cK.NBt) return;
     if (D.unitOf[cK.NAt + h] != cK.NAt + h) return;
     int size = D.cxSize[h];
-    atomicMax(&D.maxComplex[h / cK.NB], size);      // main.cpp:896-898
+    if (size > D.maxComplex[h / cK.NB]) atomicMax(&D.maxComplex[h / cK.NB], size);      // main.cpp:896-898 (read first: one hot address)
     if (size <= 1) return;
     int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
     D.cxOff[h] = off;
@@ -184,7 +184,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
             mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy);
             mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy);
         }
-        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0;
+        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
     } else {
         const int h = gid - K.NAt;
         if (D.cxSize[h] > 1) return;             // complexes: k_propose_complex
@@ -213,7 +213,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
         store_lig(D.lign, h, n);
         mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1]);
-        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0;
+        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
     }
 }
 
@@ -437,7 +437,7 @@ __global__ void k_propose_complex(const __grid_constant__ Args A) {
         if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
         else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
     }
-    D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0;
+    D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0; D.pend[rootGid] = -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -700,7 +700,12 @@ template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) 
 // (else it is a far mover with a ghost entry at cell(P)), and so is every neighbour's, hence everything P can touch
 // has an entry within reach + 2*skin of O: the 3x3 cells around cell(O) suffice because edge >= reach + 2*skin.
 // ------------------------------------------------------------------------------------------------
+#ifndef TS
 #define TS 16
+#endif
+#ifndef TTHREADS
+#define TTHREADS 128
+#endif
 #define TCAP 896
 #define F_FAR 1
 #define F_GHOST 2
@@ -751,10 +756,79 @@ KD bool tile_hits(const Consts &K, const Dev &D, bool prec, double px, double py
     return prec ? hit_rec_beads(K, px, py, ob) : hit_beads_beads(K, ob, pb);
 }
 
-__global__ void __launch_bounds__(128) k_resolve_tiles(const __grid_constant__ Args A) {
+// the molecule an interior entry stands for, as a probe
+struct ProbeCtx {
+    int m, u, flg; bool ghost, far, prec, pairsOnly, wantPairs;
+    double px, py;            // proposed centre P
+    double fax, fay, fbx, fby; // the two candidate FINAL centres for S3 pre-selection (normal entry: P and O)
+};
+KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
+    ProbeCtx c;
+    c.m = me.gid; c.u = me.unit; c.flg = me.flg;
+    c.ghost = me.flg & F_GHOST; c.far = me.flg & F_FAR; c.prec = me.gid < K.NAt;
+    c.pairsOnly = !c.ghost && c.far;                 // old entry of a far mover: it is only a reaction partner here
+    c.px = me.nx; c.py = me.ny;
+    c.fax = c.pairsOnly ? me.ox : c.px; c.fay = c.pairsOnly ? me.oy : c.py;
+    c.fbx = c.ghost ? c.px : me.ox;     c.fby = c.ghost ? c.py : me.oy;
+    c.wantPairs = c.prec && (me.flg & (F_FREE_RL | F_FREE_CIS));
+    return c;
+}
+// probe against one neighbour entry that survived the distance cut: S3 pre-selection + overlap classification.
+// returns bit0 definite overlap, bit1 overlap with exactly one pose of an earlier (still undecided) unit; in that case
+// *conf = that unit (bit 30 set if the overlapping pose is its NEW one)
+KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf) {
+    const int v = o.gid;
+    const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
+    if (c.wantPairs) {
+        const bool vlig = v >= K.NAt;
+        if (vlig ? ((c.flg & F_FREE_RL) && (o.flg & F_FREE_RL)) : ((c.flg & F_FREE_CIS) && (o.flg & F_FREE_CIS))) {
+            const double reach = vlig ? K.reachOn : K.reachCis;
+            const double vx = vghost ? o.nx : o.ox, vy = vghost ? o.ny : o.oy;
+            double d2 = fmin((vx - c.fax) * (vx - c.fax) + (vy - c.fay) * (vy - c.fay), (vx - c.fbx) * (vx - c.fbx) + (vy - c.fby) * (vy - c.fby));
+            if (!vghost && !vfar)
+                d2 = fmin(d2, fmin((o.nx - c.fax) * (o.nx - c.fax) + (o.ny - c.fay) * (o.ny - c.fay), (o.nx - c.fbx) * (o.nx - c.fbx) + (o.ny - c.fby) * (o.ny - c.fby)));
+            if (d2 <= reach * reach) {
+                int p = atomicAdd(&D.scal[S_NPAIR], 1);
+                if (p < D.pairCap) D.pairs[p] = ((unsigned long long)c.m << 32) | (unsigned)v;
+                else atomicOr(&D.scal[S_OVERFLOW], 4);
+            }
+        }
+    }
+    if (c.pairsOnly) return 0;
+    double pb[3][3];
+    if (!c.prec) load_beads(D.lign, c.m - K.NAt, pb);
+    const int uv = o.unit;
+    if (uv == c.u) {                                     // co-moving member: proposed pose, once (Q20)
+        if (vghost != vfar) return 0;
+        return tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.nx, o.ny, true) ? 1 : 0;
+    }
+    if (!unit_before(uv, c.u))                           // later unit: still at its old pose
+        return (!vghost && tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.ox, o.oy, false)) ? 1 : 0;
+    if (vghost) {                                        // earlier unit (undecided in pass 1): both poses possible
+        if (!tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.nx, o.ny, true)) return 0;
+        *conf = uv | 0x40000000; return 2;
+    }
+    const bool hitOld = tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.ox, o.oy, false);
+    const bool hitNew = !vfar && tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.nx, o.ny, true);
+    if (hitOld && hitNew) return 1;
+    if (hitOld || hitNew) { *conf = uv | (hitNew ? 0x40000000 : 0); return 2; }
+    return 0;
+}
+// publishes a probe's result: definite overlaps and pending ones are OR-ed into the unit head's word; a single-molecule
+// unit with exactly one pending conflict also records WHICH earlier unit and pose, so k_decide can settle it directly
+KD void publish(const Dev &D, int u, int res, int conf) {
+    if (!res) return;
+    atomicOr(&D.unitRes[u], res);
+    if (res == 2) { int old = atomicCAS(&D.pend[u], -1, conf); if (old != -1 && old != conf) atomicOr(&D.unitRes[u], 4); }
+}
+
+#define NSURV 1536
+__global__ void __launch_bounds__(TTHREADS) k_resolve_tiles(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
     __shared__ TileSmem S;
+    __shared__ unsigned int surv[NSURV];          // (staged index of probe << 16) | staged index of neighbour
+    __shared__ int nsurv;
     const int ntx = (K.ncx + TS - 1) / TS, nty = (K.ncy + TS - 1) / TS;
     int b = blockIdx.x;
     const int tx = b % ntx; b /= ntx;
@@ -762,119 +836,101 @@ __global__ void __launch_bounds__(128) k_resolve_tiles(const __grid_constant__ A
     const int x0 = tx * TS, x1 = min(x0 + TS - 1, K.ncx - 1), y0 = ty * TS, y1 = min(y0 + TS - 1, K.ncy - 1);
     const int wx0 = max(x0 - 1, 0), wx1 = min(x1 + 1, K.ncx - 1), wy0 = max(y0 - 1, 0), wy1 = min(y1 + 1, K.ncy - 1);
     const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 2;
-    for (int i = threadIdx.x; i < nrow * ncol; i += blockDim.x) {
-        int r = i / ncol, c = i % ncol;
-        S.cs[r][c] = __ldg(&D.cellStart[(rep * K.ncy + wy0 + r) * K.ncx + wx0 + c]);
-    }
+    if (threadIdx.x == 0) nsurv = 0;
+    for (int r = threadIdx.x / 32; r < nrow; r += TTHREADS / 32)
+        for (int c = threadIdx.x & 31; c < ncol; c += 32)
+            S.cs[r][c] = __ldg(&D.cellStart[(rep * K.ncy + wy0 + r) * K.ncx + wx0 + c]);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0, in = 0;
-        for (int r = 0; r < nrow; r++) { S.rowBase[r] = acc; acc += S.cs[r][ncol - 1] - S.cs[r][0]; }
-        S.rowBase[nrow] = acc;
-        for (int r = 0; r <= y1 - y0; r++) {
-            int wr = y0 - wy0 + r;
-            S.inBase[r] = in; in += S.cs[wr][x1 + 1 - wx0] - S.cs[wr][x0 - wx0];
-        }
-        S.inBase[y1 - y0 + 1] = in;
+    if (threadIdx.x < 32) {                       // one warp: prefix of the row lengths (window rows and interior rows)
+        const int r = threadIdx.x;
+        int len = r < nrow ? S.cs[r][ncol - 1] - S.cs[r][0] : 0;
+        int lin = (r <= y1 - y0) ? S.cs[y0 - wy0 + r][x1 + 1 - wx0] - S.cs[y0 - wy0 + r][x0 - wx0] : 0;
+        int a = len, bI = lin;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, a, o), t2 = __shfl_up_sync(0xffffffffu, bI, o); if (r >= o) { a += t; bI += t2; } }
+        if (r <= nrow) S.rowBase[r] = a - len;     // exclusive; entry nrow = total (len = 0 there)
+        if (r <= y1 - y0 + 1) S.inBase[r] = bI - lin;
     }
     __syncthreads();
     const int total = S.rowBase[nrow];
     // stage the window (first TCAP entries; the rest, if a tile is that crowded, is read from global memory on demand)
-    for (int i = threadIdx.x; i < min(total, TCAP); i += blockDim.x) {
-        int r = 0; while (i >= S.rowBase[r + 1]) r++;
-        TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.cs[r][0] + (i - S.rowBase[r])]));
+    for (int i = threadIdx.x; i < min(total, TCAP); i += TTHREADS) {
+        int lo = 0, hi = nrow;                      // largest r with rowBase[r] <= i
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.rowBase[mid] <= i) lo = mid; else hi = mid; }
+        TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.cs[lo][0] + (i - S.rowBase[lo])]));
         S.ox[i] = t.ox; S.oy[i] = t.oy; S.nx[i] = t.nx; S.ny[i] = t.ny; S.gid[i] = t.gid; S.unit[i] = t.unit; S.flg[i] = (unsigned char)t.flg;
     }
     __syncthreads();
-    auto rec_at = [&](int r, int e) -> TileRec {      // entry with global index e in window row r
-        int i = S.rowBase[r] + (e - S.cs[r][0]);
-        if (i < TCAP) { TileRec t; t.ox = S.ox[i]; t.oy = S.oy[i]; t.nx = S.nx[i]; t.ny = S.ny[i]; t.gid = S.gid[i]; t.unit = S.unit[i]; t.flg = S.flg[i]; return t; }
-        return fetch_rec(K, D, __ldg(&D.sorted[e]));
-    };
+    auto staged = [&](int i) -> TileRec { TileRec t; t.ox = S.ox[i]; t.oy = S.oy[i]; t.nx = S.nx[i]; t.ny = S.ny[i]; t.gid = S.gid[i]; t.unit = S.unit[i]; t.flg = S.flg[i]; return t; };
     const int nin = S.inBase[y1 - y0 + 1];
-    for (int q = threadIdx.x; q < nin; q += blockDim.x) {
-        int ir = 0; while (q >= S.inBase[ir + 1]) ir++;
-        const int wr = y0 - wy0 + ir;
-        const TileRec me = rec_at(wr, S.cs[wr][x0 - wx0] + (q - S.inBase[ir]));
-        const int m = me.gid, u = me.unit;
-        const bool ghost = me.flg & F_GHOST, far = me.flg & F_FAR, prec = m < K.NAt;
-        const bool pairsOnly = !ghost && far;           // old entry of a far mover: it is only a reaction partner here
-        // walk centre: cell of the position this entry stands for
-        const double wxp = ghost ? me.nx : me.ox, wyp = ghost ? me.ny : me.oy;
-        int cx = min(max((int)floor((wxp - K.gx0) * K.cellInv), 0), K.ncx - 1);
+    // phase 1: every interior entry scans its 3x3 cells with a cheap distance cut; survivors go to a shared list
+    for (int q = threadIdx.x; q < nin; q += TTHREADS) {
+        int lo = 0, hi = y1 - y0 + 1;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.inBase[mid] <= q) lo = mid; else hi = mid; }
+        const int wr = y0 - wy0 + lo;
+        const int eme = S.cs[wr][x0 - wx0] + (q - S.inBase[lo]);          // global entry index of this interior entry
+        const int ime = S.rowBase[wr] + (eme - S.cs[wr][0]);               // its staged index
+        const TileRec me = ime < TCAP ? staged(ime) : fetch_rec(K, D, __ldg(&D.sorted[eme]));
+        const ProbeCtx c = make_probe(K, me);
+        const double wxp = c.ghost ? me.nx : me.ox;                        // walk centre: what this entry stands for
+        const int cx = min(max((int)floor((wxp - K.gx0) * K.cellInv), 0), K.ncx - 1);
         const int cxl = max(cx - 1, 0) - wx0, cxh = min(cx + 1, K.ncx - 1) + 1 - wx0;
-        // probe = proposed pose; for reaction pre-selection the final centre is P or O (ghost: P only; far old entry: O only)
-        const double px = me.nx, py = me.ny;
-        const double fax = pairsOnly ? me.ox : px, fay = pairsOnly ? me.oy : py;          // first candidate final centre
-        const double fbx = ghost ? px : me.ox, fby = ghost ? py : me.oy;                  // second candidate final centre
-        double pb[3][3];
-        if (!prec && !pairsOnly) load_beads(D.lign, m - K.NAt, pb);
-        const bool wantPairs = prec && (me.flg & (F_FREE_RL | F_FREE_CIS));
-        // measured from (fax,fay) = P, or O for the old entry of a far mover
-        const double cutR = (prec ? fmax(K.reachRL, K.reachOn) : K.reachLL) + 2 * K.skin;
+        const double cutR = (c.prec ? fmax(K.reachRL, K.reachOn) : K.reachLL) + 2 * K.skin;     // measured from P (O for a far old entry)
         const double cut2 = cutR * cutR;
-        int res = 0;
+        int res = 0, conf = -1, nconf = 0;
         for (int dr = -1; dr <= 1; dr++) {
             const int r = wr + dr;
             if (r < 0 || r >= nrow) continue;
-            const int e0 = S.cs[r][cxl], e1 = S.cs[r][cxh];
+            const int e0 = S.cs[r][cxl], e1 = S.cs[r][cxh], ib = S.rowBase[r] - S.cs[r][0];
             for (int e = e0; e < e1; e++) {
-                {   // early cut on the staged centre of this entry: nothing within reach of either pose of either molecule
-                    const int i = S.rowBase[r] + (e - S.cs[r][0]);
-                    if (i < TCAP) {
-                        const bool g = S.flg[i] & F_GHOST;
-                        const double ex = (g ? S.nx[i] : S.ox[i]) - fax, ey = (g ? S.ny[i] : S.oy[i]) - fay;
-                        if (ex * ex + ey * ey > cut2) continue;
-                    }
+                const int i = ib + e;
+                if (i < TCAP && ime < TCAP) {
+                    if (S.gid[i] == c.m) continue;
+                    const bool g = S.flg[i] & F_GHOST;
+                    const double ex = (g ? S.nx[i] : S.ox[i]) - c.fax, ey = (g ? S.ny[i] : S.oy[i]) - c.fay;
+                    if (ex * ex + ey * ey > cut2) continue;
+                    const int slot = atomicAdd(&nsurv, 1);
+                    if (slot < NSURV) { surv[slot] = ((unsigned)ime << 16) | (unsigned)i; continue; }
                 }
-                const TileRec o = rec_at(r, e);
-                const int v = o.gid;
-                if (v == m) continue;
-                const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
-                if (wantPairs) {
-                    const bool vlig = v >= K.NAt;
-                    if (vlig ? ((me.flg & F_FREE_RL) && (o.flg & F_FREE_RL)) : ((me.flg & F_FREE_CIS) && (o.flg & F_FREE_CIS))) {
-                        const double reach = vlig ? K.reachOn : K.reachCis;
-                        const double vx = vghost ? o.nx : o.ox, vy = vghost ? o.ny : o.oy;
-                        double d2 = min((vx - fax) * (vx - fax) + (vy - fay) * (vy - fay), (vx - fbx) * (vx - fbx) + (vy - fby) * (vy - fby));
-                        if (!vghost && !vfar)
-                            d2 = min(d2, min((o.nx - fax) * (o.nx - fax) + (o.ny - fay) * (o.ny - fay), (o.nx - fbx) * (o.nx - fbx) + (o.ny - fby) * (o.ny - fby)));
-                        if (d2 <= reach * reach) {
-                            int p = atomicAdd(&D.scal[S_NPAIR], 1);
-                            if (p < D.pairCap) D.pairs[p] = ((unsigned long long)m << 32) | (unsigned)v;
-                            else atomicOr(&D.scal[S_OVERFLOW], 4);
-                        }
-                    }
-                }
-                if (pairsOnly || (res & 1)) continue;
-                const int uv = o.unit;
-                if (uv == u) {                                   // co-moving member: proposed pose, once (Q20)
-                    if (vghost != vfar) continue;
-                    if (tile_hits(K, D, prec, px, py, pb, v, o.nx, o.ny, true)) res |= 1;
-                } else if (!unit_before(uv, u)) {                // later unit: still at its old pose
-                    if (!vghost && tile_hits(K, D, prec, px, py, pb, v, o.ox, o.oy, false)) res |= 1;
-                } else if (vghost) {                             // earlier unit (undecided in pass 1): both poses possible
-                    if (tile_hits(K, D, prec, px, py, pb, v, o.nx, o.ny, true)) res |= 2;
-                } else {
-                    const bool hitOld = tile_hits(K, D, prec, px, py, pb, v, o.ox, o.oy, false);
-                    const bool hitNew = !vfar && tile_hits(K, D, prec, px, py, pb, v, o.nx, o.ny, true);
-                    if (hitOld && hitNew) res |= 1; else if (hitOld || hitNew) res |= 2;
-                }
+                // crowded tile (entry not staged or survivor list full): evaluate in place
+                const TileRec o = i < TCAP ? staged(i) : fetch_rec(K, D, __ldg(&D.sorted[e]));
+                if (o.gid == c.m) continue;
+                int cf = -1; const int rr = pair_eval(K, D, c, o, &cf);
+                res |= rr; if (rr == 2) { nconf += (cf != conf); conf = cf; }
             }
         }
-        if (res) atomicOr(&D.unitRes[u], res);
+        if (res) publish(D, c.u, nconf > 1 ? (res | 4) : res, conf);
+    }
+    __syncthreads();
+    // phase 2: one thread per surviving (probe, neighbour) pair
+    const int ns = min(nsurv, NSURV);
+    for (int s = threadIdx.x; s < ns; s += TTHREADS) {
+        const unsigned w = surv[s];
+        const ProbeCtx c = make_probe(K, staged((int)(w >> 16)));
+        int cf = -1;
+        const int rr = pair_eval(K, D, c, staged((int)(w & 0xffffu)), &cf);
+        publish(D, c.u, rr, cf);
     }
 }
-// after the tile pass: settle every unit whose members found nothing or a definite overlap; the rest (overlap only
-// with one pose of an earlier unit) goes to the undecided list and is settled in order by k_resolve_list/_finish
+// after the tile pass: settle every unit whose members found nothing or a definite overlap. A unit whose only finding is
+// one overlap with one pose of a single earlier unit is settled from that unit's own findings when those are conclusive;
+// whatever remains (chains of such dependencies) goes to the undecided list for k_resolve_list/_finish (in order).
 __global__ void k_decide(const __grid_constant__ Args A) {
     KARGS
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= cK.NT || D.unitOf[gid] != gid) return;
     const int r = D.unitRes[gid];
-    if (r & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); }
-    else if (r & 2) D.unk[atomicAdd(&D.scal[S_NUNK0], 1)] = gid;
-    else D.unitState[gid] = U_ACCEPT;
+    int st = U_UNKNOWN;
+    if (r & 1) st = U_REJECT;
+    else if (r == 0) st = U_ACCEPT;
+    else if (r == 2) {                                   // exactly one pending conflict (bit 2 = several)
+        const int cf = D.pend[gid], v = cf & 0x3fffffff; const bool onNew = cf & 0x40000000;
+        const int rv = D.unitRes[v];
+        if (rv & 1) st = onNew ? U_ACCEPT : U_REJECT;    // v is rejected: it stays at its old pose
+        else if (rv == 0) st = onNew ? U_REJECT : U_ACCEPT;   // v is accepted: it sits at its new pose
+    }
+    if (st == U_REJECT) atomicAdd(&D.events[EV_REVERTED], 1ULL);
+    if (st != U_UNKNOWN) D.unitState[gid] = (unsigned char)st;
+    else D.unk[atomicAdd(&D.scal[S_NUNK0], 1)] = gid;
 }
 
 // pass 2: the undecided units of list `from` in parallel; what is still undecided goes to the other list
