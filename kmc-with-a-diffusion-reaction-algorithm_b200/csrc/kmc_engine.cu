@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 23
+#define KMC_NKERNELS 22
 
 #include <algorithm>
 #include <cmath>
@@ -28,6 +28,9 @@ struct kmc_handle {
     std::vector<void *> allocs;
     int *d_series = nullptr;
     int scanBlocks = 0, nTiles = 0;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int parity = 0, launches_per_step = 0;
+    bool use_graph = true;
     int64_t launches = 0, passes = 0;
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py roofline)
     bool profiling = false;
@@ -39,10 +42,10 @@ struct kmc_handle {
 };
 
 static const char *const g_kernel_names[KMC_NKERNELS] = {
-    "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_rebuild_gate_clear", "k_propose_simple",
+    "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_simple",
     "k_propose_complex", "memset_cellCount", "k_grid_count", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
     "k_resolve_tiles", "k_decide", "k_resolve_list", "k_resolve_finish", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series"};
-enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_GATE_CLEAR, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
+enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_MEMSET, KID_GRID_COUNT, KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_DECIDE, KID_RESOLVE_LIST, KID_RESOLVE_FINISH,
        KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES };
 
@@ -157,6 +160,7 @@ extern "C" void kmc_destroy(kmc_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto ev : h->evpool) cudaEventDestroy(ev);
+    for (int p = 0; p < 2; p++) if (h->gexec[p]) cudaGraphExecDestroy(h->gexec[p]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -285,6 +289,7 @@ extern "C" int kmc_set_state(kmc_handle *h, int32_t rep, const double *Rx, const
     CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D.maxComplex + rep, &max_complex, sizeof(int), cudaMemcpyHostToDevice));
     h->step_done = step_done; h->stepped = false;
+    { unsigned long long s64 = (unsigned long long)step_done; CK(cudaMemcpy(D.step64, &s64, sizeof s64, cudaMemcpyHostToDevice)); }
     return KMC_OK;
 }
 
@@ -393,6 +398,7 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
     int one = 1;
     CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
     h->step_done = step_done; h->stepped = false;
+    { unsigned long long s64 = (unsigned long long)step_done; CK(cudaMemcpy(D.step64, &s64, sizeof s64, cudaMemcpyHostToDevice)); }
     return KMC_OK;
 }
 
@@ -401,59 +407,87 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 // ------------------------------------------------------------------------------------------------
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
-__global__ void k_step_begin(const __grid_constant__ Args A, unsigned long long step) {
+// first kernel of a step: advances the device-side step counter, resets the per-step scalars; complexes are rebuilt by
+// the gated kernels that follow only if the bond table changed (S_TOPO_DIRTY, cleared by k_propose_simple)
+__global__ void k_step_begin(const __grid_constant__ Args A) {
     KARGS
-    D.step64[0] = step;
-    // per-step scalar reset; complexes are rebuilt only if the bond table changed (S_TOPO_DIRTY)
+    D.step64[0] += 1;
     D.scal[S_NFAR] = 0; D.scal[S_NUNK0] = 0; D.scal[S_NUNK1] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
 }
-__global__ void k_rebuild_gate_clear(const __grid_constant__ Args A) {
-    KARGS D.scal[S_TOPO_DIRTY] = 0; }
+
+// all launches of one time step (main.cpp:461-2202) on stream st; no host synchronisation anywhere
+static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
+    const Dev &D = A.D;
+    const int B = 128, NT = h->NT, NAt = h->NAt, NBt = h->NBt;
+    LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A)));
+    // S1 (gated on a device flag)
+    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
+    // S2 proposals
+    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
+    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A)));
+    // neighbour grid
+    LAUNCH(KID_MEMSET, (cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st)));
+    LAUNCH(KID_GRID_COUNT, (k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.ncell + 1)));
+    LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks)));
+    LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1)));
+    LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    // S2g: tile pass over all molecules (+ reaction-pair pre-selection), settle, then the (rare) dependency chains in order
+    const int gl = std::min(nblk(NT, B), 148 * 8);
+    LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
+    LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<std::min(gl, 148), B, 0, st>>>(A, 0)));
+    LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));
+    LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    // S3
+    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<gl, B, 0, st>>>(A)));
+    LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
+    LAUNCH(KID_DISSOCIATE, (k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+}
+static void swap_buffers(Dev &D) { std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign); }
+
+// the step as a CUDA graph, one per buffer parity (the committed/new buffers alternate, S4 is a pointer swap)
+static int ensure_graphs(kmc_handle *h) {
+    if (h->gexec[0]) return KMC_OK;
+    const int64_t saved = h->launches;
+    for (int p = 0; p < 2; p++) {
+        Dev Dp = h->D;
+        if (p != h->parity) swap_buffers(Dp);
+        const Args A{Dp, h->K};
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        issue_step(h, A, h->stream);
+        CK(cudaStreamEndCapture(h->stream, &g));
+        CK(cudaGraphInstantiate(&h->gexec[p], g, 0));
+        cudaGraphDestroy(g);
+    }
+    h->launches_per_step = (int)((h->launches - saved) / 2);
+    h->launches = saved;
+    return KMC_OK;
+}
 
 extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     if (!h) return KMC_ERR_INVALID;
     if (n < 0) { h->err = "kmc_step: negative step count"; return KMC_ERR_INVALID; }
     int rc = select_device(h); if (rc) return rc;
-    Dev &D = h->D; cudaStream_t st = h->stream;
-    const int B = 128, NT = h->NT, NAt = h->NAt, NBt = h->NBt;
+    cudaStream_t st = h->stream;
+    if (!h->profiling && h->use_graph && n > 0) { rc = ensure_graphs(h); if (rc) return rc; }
     for (int64_t it = 0; it < n; it++) {
-        const uint64_t step = (uint64_t)(h->step_done + 1);
-        const Args A{D, h->K};
-        LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A, step)));
-        // S1 (gated on device: no host round trip)
-        LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
-        LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
-        LAUNCH(KID_GATE_CLEAR, (k_rebuild_gate_clear<<<1, 1, 0, st>>>(A)));
-        // S2 proposals
-        LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
-        LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A)));
-        // grid
-        LAUNCH(KID_MEMSET, (cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st)));
-        LAUNCH(KID_GRID_COUNT, (k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.ncell + 1)));
-        LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks)));
-        LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1)));
-        LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        // S2g: pass 1 over all units (+ reaction-pair pre-selection), pass 2 over the undecided list, then a one-CTA finish
-        // that iterates to the fixed point: no host round trip anywhere in the step
-        const int gl = std::min(nblk(NT, B), 148 * 8);
-        LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
-        LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<gl, B, 0, st>>>(A, 0)));
-        LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));
-        h->passes += 3;
-        LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
-        // S3
-        LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<gl, B, 0, st>>>(A)));
-        LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
-        LAUNCH(KID_DISSOCIATE, (k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
-        if (h->profiling && (it & 15) == 15) harvest(h, false);
+        if (h->profiling || !h->use_graph) {
+            const Args A{h->D, h->K};
+            issue_step(h, A, st);
+            if (h->profiling && (it & 15) == 15) harvest(h, false);
+        } else {
+            CK(cudaGraphLaunch(h->gexec[h->parity], st));
+            h->launches += h->launches_per_step;
+        }
         // S4: the new buffers become the committed state
-        std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign);
-        h->step_done++; h->stepped = true;
+        swap_buffers(h->D); h->parity ^= 1;
+        h->passes += 3; h->step_done++; h->stepped = true;
     }
     CK(cudaGetLastError());
     return KMC_OK;

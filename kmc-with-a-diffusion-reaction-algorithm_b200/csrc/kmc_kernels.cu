@@ -125,6 +125,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
     const uint64_t step = D.step64[0];
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= cK.NT) return;
+    if (gid == 0) D.scal[S_TOPO_DIRTY] = 0;       // the gated rebuild kernels of this step are done; S3 sets it again
     if (D.unitOf[gid] != gid) return;             // not the head of a unit
     const Consts &K = cK;
     const int rep = replica_of_gid(K, gid);
@@ -706,7 +707,7 @@ template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) 
 #ifndef TTHREADS
 #define TTHREADS 128
 #endif
-#define TCAP 896
+#define TCAP 384
 #define F_FAR 1
 #define F_GHOST 2
 #define F_FREE_RL 4      // receptor: no ligand bound / ligand: at least one free site
@@ -822,8 +823,8 @@ KD void publish(const Dev &D, int u, int res, int conf) {
     if (res == 2) { int old = atomicCAS(&D.pend[u], -1, conf); if (old != -1 && old != conf) atomicOr(&D.unitRes[u], 4); }
 }
 
-#define NSURV 1536
-__global__ void __launch_bounds__(TTHREADS) k_resolve_tiles(const __grid_constant__ Args A) {
+#define NSURV 512
+__global__ void __launch_bounds__(TTHREADS, 8) k_resolve_tiles(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
     __shared__ TileSmem S;
