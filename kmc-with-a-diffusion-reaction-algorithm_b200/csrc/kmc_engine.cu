@@ -3,11 +3,12 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 22
+#define KMC_NKERNELS 20
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,10 +44,10 @@ struct kmc_handle {
 
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_simple",
-    "k_propose_complex", "memset_cellCount", "k_grid_count", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
+    "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
     "k_resolve_tiles", "k_decide", "k_resolve_list", "k_resolve_finish", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series"};
 enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
-       KID_MEMSET, KID_GRID_COUNT, KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_DECIDE, KID_RESOLVE_LIST, KID_RESOLVE_FINISH,
+       KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_DECIDE, KID_RESOLVE_LIST, KID_RESOLVE_FINISH,
        KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES };
 
 static cudaEvent_t take_event(kmc_handle *h) {
@@ -143,12 +144,13 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     const double rs = rB * 2 / sqrt(3.0);
     K.reachRR = 2 * P.rA + 1e-3; K.reachRL = P.rA + P.rB + rs + 1e-3; K.reachLL = 2 * P.rB + 2 * rs + 1e-3;
     K.reachOn = P.rA + P.bond_dist_cut + rs + P.rB + 1e-3; K.reachCis = 2 * P.rA + P.cis_dist_cut + 1e-3;
-    K.skin = 48.0;
+    K.skin = 48.0;                               // far-mover threshold; KMC_SKIN overrides (tuning knob, any value is exact)
+    if (const char *sk = getenv("KMC_SKIN")) { double v = atof(sk); if (v > 0) K.skin = v; }
     K.NA = P.n_receptor; K.NB = P.n_ligand; K.R = P.n_replicas; K.mode = P.mode;
     K.NAt = K.NA * K.R; K.NBt = K.NB * K.R; K.NT = K.NAt + K.NBt; K.seed = P.seed;
     double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + 2 * K.skin + 1.0;   // walk around the OLD centre: reach + 2 skins
     if (P.cell_edge > edge) edge = P.cell_edge;
-    else if (P.cell_edge == 0) edge = std::max(edge, 256.0);
+    else if (P.cell_edge == 0) edge = std::max(edge, getenv("KMC_EDGE") ? atof(getenv("KMC_EDGE")) : 256.0);
     K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
     K.ncx = (int)ceil((P.box[0] + 2 * edge) / edge); K.ncy = (int)ceil((P.box[1] + 2 * edge) / edge);
     K.cellInv = 1.0 / edge;
@@ -198,8 +200,8 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(ufParent, K.NT); A(unitOf, K.NT); A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
     A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT);
     A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
-    A(cellCount, (size_t)D.ncell + 1); A(cellStart, (size_t)D.ncell + 1);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
     h->nTiles = K.R * ((K.ncx + TS - 1) / TS) * ((K.ncy + TS - 1) / TS);
     A(scanTmp, (size_t)h->scanBlocks + 1);
     A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT); A(farList, K.NT);
@@ -428,13 +430,11 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     // S2 proposals
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
-    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<nblk(NBt, 64), 64, 0, st>>>(A)));
-    // neighbour grid
-    LAUNCH(KID_MEMSET, (cudaMemsetAsync(D.cellCount, 0, sizeof(int) * ((size_t)D.ncell + 1), st)));
-    LAUNCH(KID_GRID_COUNT, (k_grid_count<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.ncell + 1)));
-    LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks, D.scanTmp + h->scanBlocks)));
-    LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>(D.cellCount, D.scanTmp, D.cellStart, D.ncell + 1)));
+    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, 64), 148 * 4), 64, 0, st>>>(A)));
+    // neighbour grid: the histogram was accumulated by the propose kernels (cellCount is zero at step start: k_scan_down clears it)
+    LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>((const int4 *)D.cellCount, D.scanTmp)));
+    LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks)));
+    LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>((int4 *)D.cellCount, D.scanTmp, (int4 *)D.cellStart)));
     LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
     // S2g: tile pass over all molecules (+ reaction-pair pre-selection), settle, then the (rare) dependency chains in order
     const int gl = std::min(nblk(NT, B), 148 * 8);

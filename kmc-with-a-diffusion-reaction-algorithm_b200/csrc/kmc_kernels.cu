@@ -114,9 +114,19 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
 // ------------------------------------------------------------------------------------------------
 KD uint64_t seed_of(const Consts &cK, int replica) { return cK.seed + (uint64_t)replica; }
 
+// called once per molecule per step by whoever computed its proposal: far-mover flag + the counting-sort histogram of the
+// neighbour grid (entry in the cell of the OLD centre; a far mover gets a second, ghost entry in the cell of its proposal)
 KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny) {
-    double dx = nx - ox, dy = ny - oy;
-    D.farFlag[gid] = (dx * dx + dy * dy > cK.skin * cK.skin) ? 1 : 0;
+    const double dx = nx - ox, dy = ny - oy;
+    const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
+    D.farFlag[gid] = far ? 1 : 0;
+    const int rep = replica_of_gid(cK, gid);
+    D.molSlot[gid] = atomicAdd(&D.cellCount[cell_of(cK, rep, ox, oy)], 1);
+    if (far) {
+        const int c2 = cell_of(cK, rep, nx, ny);
+        const int slot = atomicAdd(&D.cellCount[c2], 1);
+        D.farList[atomicAdd(&D.scal[S_NFAR], 1)] = make_int4(gid, c2, slot, 0);
+    }
 }
 
 // free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
@@ -289,9 +299,9 @@ KD void shuffle_row(int *row, int size, uint64_t seed, uint32_t root, uint32_t &
 __global__ void k_propose_complex(const __grid_constant__ Args A) {
     KARGS
     const uint64_t step = D.step64[0];
-    int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= D.scal[S_NCX]) return;
     const Consts &K = cK;
+    const int ncx = D.scal[S_NCX];
+    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < ncx; ci += gridDim.x * blockDim.x) {
     const int h0 = D.cxRoots[ci], rootGid = K.NAt + h0;
     const int size = D.cxSize[h0];
     const int *rowIn = D.members + D.cxOff[h0];
@@ -439,6 +449,7 @@ __global__ void k_propose_complex(const __grid_constant__ Args A) {
         else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
     }
     D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0; D.pend[rootGid] = -1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,22 +459,6 @@ __global__ void k_propose_complex(const __grid_constant__ Args A) {
 KD void centre_of(const Consts &cK, const Dev &D, int gid, bool nxt, double &x, double &y) {
     if (gid < cK.NAt) { double2 c = nxt ? D.recCn[gid] : D.recC[gid]; x = c.x; y = c.y; }
     else { const double *p = (nxt ? D.lign : D.lig) + (size_t)(gid - cK.NAt) * 24; x = p[0]; y = p[1]; }
-}
-__global__ void k_grid_count(const __grid_constant__ Args A) {
-    KARGS
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= cK.NT) return;
-    int rep = replica_of_gid(cK, gid);
-    double x, y; centre_of(cK, D, gid, false, x, y);
-    int c = cell_of(cK, rep, x, y);
-    D.molSlot[gid] = atomicAdd(&D.cellCount[c], 1);
-    if (D.farFlag[gid]) {
-        centre_of(cK, D, gid, true, x, y);
-        int c2 = cell_of(cK, rep, x, y);
-        int slot = atomicAdd(&D.cellCount[c2], 1);
-        int f = atomicAdd(&D.scal[S_NFAR], 1);
-        D.farList[f] = make_int4(gid, c2, slot, 0);
-    }
 }
 __global__ void k_grid_scatter(const __grid_constant__ Args A) {
     KARGS
@@ -476,56 +471,56 @@ __global__ void k_grid_scatter(const __grid_constant__ Args A) {
     }
     if (gid < D.scal[S_NFAR]) { int4 f = D.farList[gid]; D.sorted[D.cellStart[f.y] + f.z] = f.x | GHOST_BIT; }
 }
-// exclusive scan of cellCount[0..n) into cellStart[0..n], three phases (reduce, scan of block sums, downsweep)
+// exclusive scan of cellCount into cellStart in three phases (tile sums, scan of the sums, per-tile scan). Arrays are padded
+// to a multiple of SCAN_TILE; 8 consecutive ints per thread (two int4), warp shuffles, one shared word per warp. The last
+// phase also zeroes cellCount: the histogram of the NEXT step is accumulated by the propose kernels.
 #define SCAN_TILE 2048
-__global__ void k_scan_reduce(const int *in, int *blockSums, int n) {
-    __shared__ int sh[32];
-    int base = blockIdx.x * SCAN_TILE, s = 0;
-    for (int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x) if (base + i < n) s += in[base + i];
+KD int warp_incl_scan(int v) {
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v += t; }
+    return v;
+}
+__global__ void __launch_bounds__(256) k_scan_reduce(const int4 *in, int *blockSums) {
+    __shared__ int sh[8];
+    const int4 a = in[(size_t)blockIdx.x * (SCAN_TILE / 4) + threadIdx.x * 2], b = in[(size_t)blockIdx.x * (SCAN_TILE / 4) + threadIdx.x * 2 + 1];
+    int s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
     for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
-        for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) blockSums[blockIdx.x] = s;
-    }
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = sh[0] + sh[1] + sh[2] + sh[3] + sh[4] + sh[5] + sh[6] + sh[7];
 }
-__global__ void k_scan_sums(int *blockSums, int nb, int *total) {     // single block
-    __shared__ int carry; __shared__ int sh[1024];
+__global__ void __launch_bounds__(1024) k_scan_sums(int *blockSums, int nb) {     // single block, exclusive, in place
+    __shared__ int sh[32]; __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < nb; base += blockDim.x) {
-        int i = base + threadIdx.x, v = i < nb ? blockSums[i] : 0;
-        sh[threadIdx.x] = v; __syncthreads();
-        for (int o = 1; o < blockDim.x; o <<= 1) {
-            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0; __syncthreads();
-            sh[threadIdx.x] += t; __syncthreads();
-        }
-        if (i < nb) blockSums[i] = carry + sh[threadIdx.x] - v;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x, v = i < nb ? blockSums[i] : 0;
+        int inc = warp_incl_scan(v);
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
+        if (threadIdx.x < 32) sh[threadIdx.x] = warp_incl_scan(sh[threadIdx.x]);
+        __syncthreads();
+        const int wofs = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+        if (i < nb) blockSums[i] = carry + wofs + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += wofs + inc;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
 }
-__global__ void k_scan_down(const int *in, const int *blockSums, int *out, int n) {
-    __shared__ int sh[256]; __shared__ int carry;
-    int base = blockIdx.x * SCAN_TILE;
-    if (threadIdx.x == 0) carry = blockSums[blockIdx.x];
+__global__ void __launch_bounds__(256) k_scan_down(int4 *in, const int *blockSums, int4 *out) {
+    __shared__ int sh[8];
+    const size_t q = (size_t)blockIdx.x * (SCAN_TILE / 4) + threadIdx.x * 2;
+    const int4 a = in[q], b = in[q + 1];
+    const int tot = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    const int inc = warp_incl_scan(tot);
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
     __syncthreads();
-    for (int t = 0; t < SCAN_TILE; t += blockDim.x) {
-        int i = base + t + threadIdx.x, v = i < n ? in[i] : 0;
-        sh[threadIdx.x] = v; __syncthreads();
-        for (int o = 1; o < blockDim.x; o <<= 1) {
-            int u = threadIdx.x >= o ? sh[threadIdx.x - o] : 0; __syncthreads();
-            sh[threadIdx.x] += u; __syncthreads();
-        }
-        if (i < n) out[i] = carry + sh[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
-        __syncthreads();
-    }
+    int ofs = blockSums[blockIdx.x] + inc - tot;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) ofs += sh[w];
+    int4 oa, ob;
+    oa.x = ofs; oa.y = oa.x + a.x; oa.z = oa.y + a.y; oa.w = oa.z + a.z;
+    ob.x = oa.w + a.w; ob.y = ob.x + b.x; ob.z = ob.y + b.y; ob.w = ob.z + b.z;
+    out[q] = oa; out[q + 1] = ob;
+    in[q] = make_int4(0, 0, 0, 0); in[q + 1] = make_int4(0, 0, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
