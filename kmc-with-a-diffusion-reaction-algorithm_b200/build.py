@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "libkmc_b200.so")
+LIB = os.environ.get("KMC_LIB_OUT") or os.path.join(HERE, "libkmc_b200.so")
 SRC = [os.path.join(HERE, "csrc", "kmc_engine.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in ("kmc_engine.cu", "kmc_kernels.cu", "kmc_device.cuh", "kmc_geom.cuh", "kmc_philox.cuh")] + \
        [os.path.join(HERE, "..", "include", "kmc_b200.h")]
@@ -23,6 +23,9 @@ def build(force=False, verbose=False):
         return LIB
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-o", LIB] + SRC
+    for k in ("TS", "TTHREADS", "TCAP", "NSURV", "TMINB", "KMC_TILE_TIMING"):          # tile-kernel tuning knobs (experiments only)
+        if os.environ.get("KMC_" + k):
+            cmd.insert(1, "-D%s=%s" % (k, os.environ["KMC_" + k]))
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -144,7 +144,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     const double rs = rB * 2 / sqrt(3.0);
     K.reachRR = 2 * P.rA + 1e-3; K.reachRL = P.rA + P.rB + rs + 1e-3; K.reachLL = 2 * P.rB + 2 * rs + 1e-3;
     K.reachOn = P.rA + P.bond_dist_cut + rs + P.rB + 1e-3; K.reachCis = 2 * P.rA + P.cis_dist_cut + 1e-3;
-    K.skin = 48.0;                               // far-mover threshold; KMC_SKIN overrides (tuning knob, any value is exact)
+    K.skin = 24.0;                               // far-mover threshold; KMC_SKIN overrides (tuning knob, any value is exact)
     if (const char *sk = getenv("KMC_SKIN")) { double v = atof(sk); if (v > 0) K.skin = v; }
     K.NA = P.n_receptor; K.NB = P.n_ligand; K.R = P.n_replicas; K.mode = P.mode;
     K.NAt = K.NA * K.R; K.NBt = K.NB * K.R; K.NT = K.NAt + K.NBt; K.seed = P.seed;

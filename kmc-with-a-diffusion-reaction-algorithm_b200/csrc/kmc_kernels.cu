@@ -702,7 +702,9 @@ template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) 
 #ifndef TTHREADS
 #define TTHREADS 128
 #endif
+#ifndef TCAP
 #define TCAP 384
+#endif
 #define F_FAR 1
 #define F_GHOST 2
 #define F_FREE_RL 4      // receptor: no ligand bound / ligand: at least one free site
@@ -735,7 +737,9 @@ struct TileSmem {
     int cs[TS + 2][TS + 3];       // cellStart of the window: rows wy0..wy1, columns wx0..wx1+1
     int rowBase[TS + 3];          // index (in staged order) of the first entry of each window row
     int inBase[TS + 1];           // prefix of interior entries per interior row
+    int rowStart[TS + 3];         // index in `sorted` of the first entry of each window row
     double ox[TCAP], oy[TCAP], nx[TCAP], ny[TCAP];
+    float sx[TCAP], sy[TCAP];     // window-relative fp32 copy of the centre the entry stands for (distance cut only)
     int gid[TCAP], unit[TCAP];
     unsigned char flg[TCAP];
 };
@@ -774,6 +778,7 @@ KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
 // *conf = that unit (bit 30 set if the overlapping pose is its NEW one)
 KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf) {
     const int v = o.gid;
+    if (v == c.m) return 0;                              // the other (old/ghost) entry of the probe itself
     const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
     if (c.wantPairs) {
         const bool vlig = v >= K.NAt;
@@ -818,8 +823,13 @@ KD void publish(const Dev &D, int u, int res, int conf) {
     if (res == 2) { int old = atomicCAS(&D.pend[u], -1, conf); if (old != -1 && old != conf) atomicOr(&D.unitRes[u], 4); }
 }
 
+#ifndef NSURV
 #define NSURV 512
-__global__ void __launch_bounds__(TTHREADS, 8) k_resolve_tiles(const __grid_constant__ Args A) {
+#endif
+#ifndef TMINB
+#define TMINB 8
+#endif
+__global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
     __shared__ TileSmem S;
@@ -831,72 +841,120 @@ __global__ void __launch_bounds__(TTHREADS, 8) k_resolve_tiles(const __grid_cons
     const int ty = b % nty; const int rep = b / nty;
     const int x0 = tx * TS, x1 = min(x0 + TS - 1, K.ncx - 1), y0 = ty * TS, y1 = min(y0 + TS - 1, K.ncy - 1);
     const int wx0 = max(x0 - 1, 0), wx1 = min(x1 + 1, K.ncx - 1), wy0 = max(y0 - 1, 0), wy1 = min(y1 + 1, K.ncy - 1);
-    const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 2;
-    if (threadIdx.x == 0) nsurv = 0;
-    for (int r = threadIdx.x / 32; r < nrow; r += TTHREADS / 32)
-        for (int c = threadIdx.x & 31; c < ncol; c += 32)
-            S.cs[r][c] = __ldg(&D.cellStart[(rep * K.ncy + wy0 + r) * K.ncx + wx0 + c]);
-    __syncthreads();
-    if (threadIdx.x < 32) {                       // one warp: prefix of the row lengths (window rows and interior rows)
+    const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 2, nir = y1 - y0 + 1;
+#ifdef KMC_TILE_TIMING
+    long long tq[6]; int tqi = 0;
+#define TICK() do { if (threadIdx.x == 0) tq[tqi++] = clock64(); } while (0)
+#else
+#define TICK() do {} while (0)
+#endif
+    TICK();
+    if (threadIdx.x < 32) {
+        // one warp: the extent of every window row / interior row in `sorted` (4 loads per row), then their prefixes
         const int r = threadIdx.x;
-        int len = r < nrow ? S.cs[r][ncol - 1] - S.cs[r][0] : 0;
-        int lin = (r <= y1 - y0) ? S.cs[y0 - wy0 + r][x1 + 1 - wx0] - S.cs[y0 - wy0 + r][x0 - wx0] : 0;
-        int a = len, bI = lin;
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, a, o), t2 = __shfl_up_sync(0xffffffffu, bI, o); if (r >= o) { a += t; bI += t2; } }
-        if (r <= nrow) S.rowBase[r] = a - len;     // exclusive; entry nrow = total (len = 0 there)
-        if (r <= y1 - y0 + 1) S.inBase[r] = bI - lin;
+        int s0 = 0, s1 = 0, i0 = 0, i1 = 0;
+        if (r < nrow) {
+            const int *row = D.cellStart + (size_t)(rep * K.ncy + wy0 + r) * K.ncx;
+            s0 = __ldg(row + wx0); s1 = __ldg(row + wx1 + 1);
+            if (r >= y0 - wy0 && r < y0 - wy0 + nir) { i0 = __ldg(row + x0); i1 = __ldg(row + x1 + 1); }
+        }
+        const int len = s1 - s0, lin = i1 - i0;
+        const int a = warp_incl_scan(len), bI = warp_incl_scan(lin);
+        if (r <= nrow) { S.rowBase[r] = a - len; S.rowStart[r] = s0; }
+        // interior rows are window rows y0-wy0 .. : store their prefix indexed by interior row
+        const int ir = r - (y0 - wy0);
+        if (ir >= 0 && ir <= nir) S.inBase[ir] = bI - lin;
+        if (r == 0) nsurv = 0;
     }
     __syncthreads();
-    const int total = S.rowBase[nrow];
+    TICK();
+    const int total = S.rowBase[nrow], nst = min(total, TCAP);
+    const double tox = K.gx0 + (double)wx0 / K.cellInv, toy = K.gy0 + (double)wy0 / K.cellInv;    // window origin
     // stage the window (first TCAP entries; the rest, if a tile is that crowded, is read from global memory on demand)
-    for (int i = threadIdx.x; i < min(total, TCAP); i += TTHREADS) {
+    // and, in the same latency window, the cellStart values of the window (column ranges of the 3x3 walks)
+    for (int i = threadIdx.x; i < nst; i += TTHREADS) {
         int lo = 0, hi = nrow;                      // largest r with rowBase[r] <= i
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.rowBase[mid] <= i) lo = mid; else hi = mid; }
-        TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.cs[lo][0] + (i - S.rowBase[lo])]));
+        const TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.rowStart[lo] + (i - S.rowBase[lo])]));
         S.ox[i] = t.ox; S.oy[i] = t.oy; S.nx[i] = t.nx; S.ny[i] = t.ny; S.gid[i] = t.gid; S.unit[i] = t.unit; S.flg[i] = (unsigned char)t.flg;
+        const bool g = t.flg & F_GHOST;                                   // what this entry stands for, window-relative, fp32 (cut only)
+        S.sx[i] = (float)((g ? t.nx : t.ox) - tox); S.sy[i] = (float)((g ? t.ny : t.oy) - toy);
     }
+    for (int r = threadIdx.x / 32; r < nrow; r += TTHREADS / 32)
+        for (int c = threadIdx.x & 31; c < ncol; c += 32)
+            S.cs[r][c] = __ldg(&D.cellStart[(size_t)(rep * K.ncy + wy0 + r) * K.ncx + wx0 + c]);
     __syncthreads();
+    TICK();
     auto staged = [&](int i) -> TileRec { TileRec t; t.ox = S.ox[i]; t.oy = S.oy[i]; t.nx = S.nx[i]; t.ny = S.ny[i]; t.gid = S.gid[i]; t.unit = S.unit[i]; t.flg = S.flg[i]; return t; };
-    const int nin = S.inBase[y1 - y0 + 1];
+    const int nin = S.inBase[nir];
+    const bool fits = total <= TCAP;
+    // squared cut radii (fp32, with a safety margin): overlap reach + one skin (the neighbour's pose moves at most a skin from
+    // its entry), S3 pre-selection reach + two skins (the probe's own final centre may be its old one)
+    const float mg = 0.05f, sk = (float)K.skin;
+    const float cRR = fmaxf((float)K.ovAA + sk, (float)K.reachCis + 2 * sk) + mg, cRL = fmaxf((float)K.reachRL + sk, (float)K.reachOn + 2 * sk) + mg,
+                cLR = (float)K.reachRL + sk + mg, cLL = (float)K.reachLL + sk + mg;
     // phase 1: every interior entry scans its 3x3 cells with a cheap distance cut; survivors go to a shared list
     for (int q = threadIdx.x; q < nin; q += TTHREADS) {
-        int lo = 0, hi = y1 - y0 + 1;
+        int lo = 0, hi = nir;
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.inBase[mid] <= q) lo = mid; else hi = mid; }
         const int wr = y0 - wy0 + lo;
         const int eme = S.cs[wr][x0 - wx0] + (q - S.inBase[lo]);          // global entry index of this interior entry
-        const int ime = S.rowBase[wr] + (eme - S.cs[wr][0]);               // its staged index
-        const TileRec me = ime < TCAP ? staged(ime) : fetch_rec(K, D, __ldg(&D.sorted[eme]));
-        const ProbeCtx c = make_probe(K, me);
-        const double wxp = c.ghost ? me.nx : me.ox;                        // walk centre: what this entry stands for
-        const int cx = min(max((int)floor((wxp - K.gx0) * K.cellInv), 0), K.ncx - 1);
-        const int cxl = max(cx - 1, 0) - wx0, cxh = min(cx + 1, K.ncx - 1) + 1 - wx0;
-        const double cutR = (c.prec ? fmax(K.reachRL, K.reachOn) : K.reachLL) + 2 * K.skin;     // measured from P (O for a far old entry)
-        const double cut2 = cutR * cutR;
-        int res = 0, conf = -1, nconf = 0;
-        for (int dr = -1; dr <= 1; dr++) {
-            const int r = wr + dr;
-            if (r < 0 || r >= nrow) continue;
-            const int e0 = S.cs[r][cxl], e1 = S.cs[r][cxh], ib = S.rowBase[r] - S.cs[r][0];
-            for (int e = e0; e < e1; e++) {
-                const int i = ib + e;
-                if (i < TCAP && ime < TCAP) {
-                    if (S.gid[i] == c.m) continue;
-                    const bool g = S.flg[i] & F_GHOST;
-                    const double ex = (g ? S.nx[i] : S.ox[i]) - c.fax, ey = (g ? S.ny[i] : S.oy[i]) - c.fay;
-                    if (ex * ex + ey * ey > cut2) continue;
+        const int ime = S.rowBase[wr] + (eme - S.rowStart[wr]);            // its staged index
+        if (fits) {
+            const bool prec = S.gid[ime] < K.NAt;
+            const int f = S.flg[ime];
+            // centre the cut is measured from: P, or O for the old entry of a far mover (which is only a reaction partner)
+            const bool pOnly = (f & F_FAR) && !(f & F_GHOST);
+            const float fx = (float)((pOnly ? S.ox[ime] : S.nx[ime]) - tox), fy = (float)((pOnly ? S.oy[ime] : S.ny[ime]) - toy);
+            const int cxe = min(max((int)floor(((f & F_GHOST ? S.nx[ime] : S.ox[ime]) - K.gx0) * K.cellInv), 0), K.ncx - 1);
+            const int cxl = max(cxe - 1, 0) - wx0, cxh = min(cxe + 1, K.ncx - 1) + 1 - wx0;
+            const float cR = prec ? cRR : cLR, cL = prec ? cRL : cLL;
+            const float cR2 = cR * cR, cL2 = cL * cL;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++) {
+                const int r = wr + dr;
+                if (r < 0 || r >= nrow) continue;
+                const int ib = S.rowBase[r] - S.rowStart[r];
+                const int i0 = ib + S.cs[r][cxl], i1 = ib + S.cs[r][cxh];
+                for (int i = i0; i < i1; i++) {
+                    const float ex = S.sx[i] - fx, ey = S.sy[i] - fy;
+                    const float lim = (S.gid[i] < K.NAt) ? cR2 : cL2;
+                    if (ex * ex + ey * ey > lim || i == ime) continue;
                     const int slot = atomicAdd(&nsurv, 1);
-                    if (slot < NSURV) { surv[slot] = ((unsigned)ime << 16) | (unsigned)i; continue; }
+                    if (slot < NSURV) surv[slot] = ((unsigned)ime << 16) | (unsigned)i;
+                    else {                                                  // survivor list full: evaluate in place
+                        const ProbeCtx c = make_probe(K, staged(ime));
+                        int cf = -1; const int rr = pair_eval(K, D, c, staged(i), &cf);
+                        publish(D, c.u, rr, cf);
+                    }
                 }
-                // crowded tile (entry not staged or survivor list full): evaluate in place
-                const TileRec o = i < TCAP ? staged(i) : fetch_rec(K, D, __ldg(&D.sorted[e]));
-                if (o.gid == c.m) continue;
-                int cf = -1; const int rr = pair_eval(K, D, c, o, &cf);
-                res |= rr; if (rr == 2) { nconf += (cf != conf); conf = cf; }
+            }
+        } else {
+            // crowded tile: generic path, entries beyond the staged part are fetched from global memory
+            const TileRec me = ime < TCAP ? staged(ime) : fetch_rec(K, D, __ldg(&D.sorted[eme]));
+            const ProbeCtx c = make_probe(K, me);
+            const double wxp = c.ghost ? me.nx : me.ox;
+            const int cxe = min(max((int)floor((wxp - K.gx0) * K.cellInv), 0), K.ncx - 1);
+            const int cxl = max(cxe - 1, 0) - wx0, cxh = min(cxe + 1, K.ncx - 1) + 1 - wx0;
+            const double cutR = (c.prec ? fmax(K.reachRL, K.reachOn) : K.reachLL) + 2 * K.skin, cut2 = cutR * cutR;
+            for (int dr = -1; dr <= 1; dr++) {
+                const int r = wr + dr;
+                if (r < 0 || r >= nrow) continue;
+                const int e0 = S.cs[r][cxl], e1 = S.cs[r][cxh], ib = S.rowBase[r] - S.rowStart[r];
+                for (int e = e0; e < e1; e++) {
+                    const int i = ib + e;
+                    const TileRec o = i < TCAP ? staged(i) : fetch_rec(K, D, __ldg(&D.sorted[e]));
+                    const bool g = o.flg & F_GHOST;
+                    const double ex = (g ? o.nx : o.ox) - c.fax, ey = (g ? o.ny : o.oy) - c.fay;
+                    if (ex * ex + ey * ey > cut2) continue;
+                    int cf = -1; const int rr = pair_eval(K, D, c, o, &cf);
+                    publish(D, c.u, rr, cf);
+                }
             }
         }
-        if (res) publish(D, c.u, nconf > 1 ? (res | 4) : res, conf);
     }
     __syncthreads();
+    TICK();
     // phase 2: one thread per surviving (probe, neighbour) pair
     const int ns = min(nsurv, NSURV);
     for (int s = threadIdx.x; s < ns; s += TTHREADS) {
@@ -906,6 +964,11 @@ __global__ void __launch_bounds__(TTHREADS, 8) k_resolve_tiles(const __grid_cons
         const int rr = pair_eval(K, D, c, staged((int)(w & 0xffffu)), &cf);
         publish(D, c.u, rr, cf);
     }
+#ifdef KMC_TILE_TIMING
+    __syncthreads();
+    TICK();
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) atomicAdd(&D.events[10 + i], (unsigned long long)(tq[i + 1] - tq[i])); atomicAdd(&D.events[15], 1ULL); }
+#endif
 }
 // after the tile pass: settle every unit whose members found nothing or a definite overlap. A unit whose only finding is
 // one overlap with one pose of a single earlier unit is settled from that unit's own findings when those are conclusive;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libkmc_b200.so")
+LIB_PATH = os.environ.get("KMC_LIB") or os.path.join(PKG_DIR, "libkmc_b200.so")
 
 MODE_REPLAY, MODE_PRODUCTION = 0, 1
 
