@@ -130,6 +130,8 @@ int64_t kmc_get_complexes(kmc_handle *h, int32_t replica, int32_t *row_len, int3
 /* histogram of ligand-rooted complex sizes over replica (or all replicas if replica < 0): hist[s] = number of
  * complexes with s members, sizes >= nbins-1 are accumulated in the last bin */
 int kmc_get_oligomer_hist(kmc_handle *h, int32_t replica, int64_t *hist, int32_t nbins);
+/* geometry of the neighbour grid (cell = floor((x - x0) * inv_edge)); the checkerboard order of KMC_MODE_PRODUCTION colours these cells */
+int kmc_get_grid(kmc_handle *h, double *x0, double *y0, double *inv_edge, int32_t *ncx, int32_t *ncy);
 /* replay diagnostics: accepted[N+1] (1-based): 1 if the molecule's unit kept its move in the last step */
 int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
 /* ev[16] accumulated since creation: [0] R-L on, [1] mono-cis on, [2] cis on, [3] R-L off, [4] mono-cis off,

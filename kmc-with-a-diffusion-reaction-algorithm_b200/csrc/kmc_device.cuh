@@ -33,6 +33,7 @@ struct Dev {
     // complexes (S1, main.cpp:514-562)
     int *ufParent;                         // union-find over uid: ligands [0,NBt), receptors NBt + a
     int *unitOf;                           // [NT] gid of the head of the moving unit this molecule belongs to
+    int *ukey;                             // [NT] sweep-order key of that unit: (colour << 30) | head; aliases unitOf in replay mode
     int *cxSize, *cxOff, *cxRoots;         // per root ligand: members, offset into members[]; list of roots with size>1
     int *members, *rowWork;                // member gids in BFS order / working copy permuted by the shuffles
     int *bfsMark;

@@ -172,7 +172,7 @@ extern "C" const char *kmc_last_error(const kmc_handle *h) { return h ? h->err.c
 extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     if (!p || !out) { g_create_error = "null argument"; return KMC_ERR_INVALID; }
     *out = nullptr;
-    if (p->n_receptor < 0 || p->n_ligand < 1 || p->n_replicas < 1 || p->box[0] <= 0 || p->box[1] <= 0 || p->box[2] <= 0 ||
+    if ((p->mode != KMC_MODE_REPLAY && p->mode != KMC_MODE_PRODUCTION) || p->n_receptor < 0 || p->n_ligand < 1 || p->n_replicas < 1 || p->box[0] <= 0 || p->box[1] <= 0 || p->box[2] <= 0 ||
         p->rA <= 0 || p->rB <= 0 || p->dt <= 0) { g_create_error = "invalid parameters"; return KMC_ERR_INVALID; }
     if ((int64_t)(p->n_receptor + p->n_ligand) * p->n_replicas >= (1LL << 30)) { g_create_error = "too many molecules"; return KMC_ERR_INVALID; }
     kmc_handle *h = new kmc_handle;
@@ -197,7 +197,8 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(recC, K.NAt); A(recS2, K.NAt); A(recS3, K.NAt); A(recCn, K.NAt); A(recS2n, K.NAt); A(recS3n, K.NAt);
     A(lig, (size_t)K.NBt * 24); A(lign, (size_t)K.NBt * 24);
     A(recLig, K.NAt); A(recSite, K.NAt); A(recCis, K.NAt); A(ligRec, (size_t)K.NBt * 3);
-    A(ufParent, K.NT); A(unitOf, K.NT); A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
+    A(ufParent, K.NT); A(unitOf, K.NT);
+    if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
     A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT);
     A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -611,6 +612,13 @@ extern "C" int kmc_get_oligomer_hist(kmc_handle *h, int32_t rep, int64_t *hist, 
     int b0 = rep < 0 ? 0 : rep * h->NB, b1 = rep < 0 ? h->NBt : (rep + 1) * h->NB;
     for (int b = b0; b < b1; b++)
         if (hc.unitOf[h->NAt + b] == h->NAt + b) hist[std::min(hc.cxSize[b], nbins - 1)]++;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_grid(kmc_handle *h, double *x0, double *y0, double *inv_edge, int32_t *ncx, int32_t *ncy) {
+    if (!h) return KMC_ERR_INVALID;
+    if (x0) *x0 = h->K.gx0; if (y0) *y0 = h->K.gy0; if (inv_edge) *inv_edge = h->K.cellInv;
+    if (ncx) *ncx = h->K.ncx; if (ncy) *ncy = h->K.ncy;
     return KMC_OK;
 }
 

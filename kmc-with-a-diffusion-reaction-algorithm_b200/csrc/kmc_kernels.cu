@@ -109,6 +109,17 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     }
 }
 
+// Order of the sweep. Every molecule carries the key of its unit: (colour << 30) | head gid. In replay mode the colour is 0,
+// so units are swept in index order like the reference (main.cpp:577); in production mode the colour is the 2x2
+// checkerboard colour of the head's cell, so the sweep runs colour by colour and by index inside a colour.
+#define UNIT_MASK 0x3fffffff
+KD bool unit_before(int v, int u) { return (unsigned)v < (unsigned)u; }
+KD int unit_key(const Consts &K, int head, double hx, double hy) {
+    if (K.mode == 0) return head;
+    const int cx = (int)floor((hx - K.gx0) * K.cellInv), cy = (int)floor((hy - K.gy0) * K.cellInv);
+    return (int)((unsigned)head | ((unsigned)((cx & 1) | ((cy & 1) << 1)) << 30));
+}
+
 // ------------------------------------------------------------------------------------------------
 // S2 proposals
 // ------------------------------------------------------------------------------------------------
@@ -163,6 +174,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
             rotz(cs, ss, t.s3x, t.s3y, t.cx, t.cy, n.s3x, n.s3y);
             store_rec(D.recCn, D.recS2n, D.recS3n, a, n);
             mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy);
+            if (K.mode) D.ukey[a] = unit_key(K, a, ra.cx, ra.cy);
         } else {
             // ---- S2b: this receptor is the lower index of a ligand-free cis pair ----
             Rec rb = load_rec(D.recC, D.recS2, D.recS3, p);
@@ -194,6 +206,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
             store_rec(D.recCn, D.recS2n, D.recS3n, p, nb);
             mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy);
             mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy);
+            if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
         D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
     } else {
@@ -224,6 +237,7 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
         store_lig(D.lign, h, n);
         mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1]);
+        if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
         D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
     }
 }
@@ -443,8 +457,10 @@ __global__ void k_propose_complex(const __grid_constant__ Args A) {
             if (a < K.NAt && D.recLig[a] >= 0 && D.recCis[a] >= 0 && D.recLig[D.recCis[a]] < 0) resnap_cis_partner(C, a, D.recCis[a]);
         }
     }
+    const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
     for (int q = 0; q < size; q++) {
         int m = row[q];
+        if (K.mode) D.ukey[m] = ckey;
         if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
         else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
     }
@@ -580,8 +596,6 @@ KD bool probe_hits(const Consts &K, const Dev &D, const Probe &P, int v, bool nx
     return P.rec ? hit_rec_beads(K, P.cx, P.cy, ob) : hit_beads_beads(K, ob, P.b);
 }
 
-// order of the sweep: true if unit head `v` is processed before unit head `u`
-KD bool unit_before(int v, int u) { return v < u; }
 
 // S3 pre-selection: receptor a (walked as probe) and neighbour v can only react if their FINAL centres come within
 // `reach`; each final centre is the old or the proposed one, so the minimum over those combinations is a safe bound.
@@ -620,7 +634,7 @@ template <bool PAIRS> KD int test_member(const Consts &cK, const Dev &D, int u, 
         const bool ghost = (e & GHOST_BIT) != 0;
         const int v = e & ~GHOST_BIT;
         if (v == m) return;
-        const int uv = D.unitOf[v];
+        const int uv = D.ukey[v];
         const bool far = D.farFlag[v] != 0;
         if (wantPairs) maybe_pair(cK, D, m, aFreeRL, aFreeCis, P.cx, P.cy, oax, oay, v, ghost, far);
         if (res & 1) return;
@@ -630,7 +644,7 @@ template <bool PAIRS> KD int test_member(const Consts &cK, const Dev &D, int u, 
         } else if (!unit_before(uv, u)) {                // later unit: still at its old pose
             if (!ghost && probe_hits(cK, D, P, v, false)) res |= 1;
         } else {                                         // earlier unit: new pose if it was accepted
-            const unsigned char s = ((volatile unsigned char *)D.unitState)[uv];
+            const unsigned char s = ((volatile unsigned char *)D.unitState)[uv & UNIT_MASK];
             if (ghost) {
                 if (s != U_REJECT && probe_hits(cK, D, P, v, true)) res |= (s == U_ACCEPT) ? 1 : 2;
             } else {
@@ -664,19 +678,20 @@ KD void load_probe(const Consts &K, const Dev &D, int m, Probe &P) {
 // evaluates unit `gid` (a head, currently undecided); writes its state if decidable; returns true if still undecided
 template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) {
     const int rep = replica_of_gid(K, gid);
+    const int uk = D.ukey[gid];                          // order key of this unit
     int res = 0;
     Probe P;
     if (gid < K.NAt) {
         load_probe(K, D, gid, P);
-        res |= test_member<PAIRS>(K, D, gid, gid, P, rep);
+        res |= test_member<PAIRS>(K, D, uk, gid, P, rep);
         int p = D.recCis[gid];
-        if (p >= 0 && (PAIRS || !(res & 1))) { load_probe(K, D, p, P); res |= test_member<PAIRS>(K, D, gid, p, P, rep); }
+        if (p >= 0 && (PAIRS || !(res & 1))) { load_probe(K, D, p, P); res |= test_member<PAIRS>(K, D, uk, p, P, rep); }
     } else {
         const int h = gid - K.NAt, size = D.cxSize[h];
-        if (size <= 1) { load_probe(K, D, gid, P); res |= test_member<PAIRS>(K, D, gid, gid, P, rep); }
+        if (size <= 1) { load_probe(K, D, gid, P); res |= test_member<PAIRS>(K, D, uk, gid, P, rep); }
         else {
             const int *row = D.rowWork + D.cxOff[h];
-            for (int i = 0; i < size && (PAIRS || !(res & 1)); i++) { int m = row[i]; load_probe(K, D, m, P); res |= test_member<PAIRS>(K, D, gid, m, P, rep); }
+            for (int i = 0; i < size && (PAIRS || !(res & 1)); i++) { int m = row[i]; load_probe(K, D, m, P); res |= test_member<PAIRS>(K, D, uk, m, P, rep); }
         }
     }
     if (res & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); return false; }
@@ -715,7 +730,7 @@ struct TileRec { double ox, oy, nx, ny; int gid, unit; int flg; };
 KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
     TileRec r;
     const int v = entry & ~GHOST_BIT;
-    r.gid = v; r.unit = D.unitOf[v];
+    r.gid = v; r.unit = D.ukey[v];
     int f = (D.farFlag[v] ? F_FAR : 0) | ((entry & GHOST_BIT) ? F_GHOST : 0);
     if (v < K.NAt) {
         double2 o = D.recC[v], n = D.recCn[v];
@@ -807,18 +822,19 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
         return (!vghost && tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.ox, o.oy, false)) ? 1 : 0;
     if (vghost) {                                        // earlier unit (undecided in pass 1): both poses possible
         if (!tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.nx, o.ny, true)) return 0;
-        *conf = uv | 0x40000000; return 2;
+        *conf = (uv & UNIT_MASK) | 0x40000000; return 2;
     }
     const bool hitOld = tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.ox, o.oy, false);
     const bool hitNew = !vfar && tile_hits(K, D, c.prec, c.px, c.py, pb, v, o.nx, o.ny, true);
     if (hitOld && hitNew) return 1;
-    if (hitOld || hitNew) { *conf = uv | (hitNew ? 0x40000000 : 0); return 2; }
+    if (hitOld || hitNew) { *conf = (uv & UNIT_MASK) | (hitNew ? 0x40000000 : 0); return 2; }
     return 0;
 }
 // publishes a probe's result: definite overlaps and pending ones are OR-ed into the unit head's word; a single-molecule
 // unit with exactly one pending conflict also records WHICH earlier unit and pose, so k_decide can settle it directly
-KD void publish(const Dev &D, int u, int res, int conf) {
+KD void publish(const Dev &D, int ukey, int res, int conf) {
     if (!res) return;
+    const int u = ukey & UNIT_MASK;
     atomicOr(&D.unitRes[u], res);
     if (res == 2) { int old = atomicCAS(&D.pend[u], -1, conf); if (old != -1 && old != conf) atomicOr(&D.unitRes[u], 4); }
 }

@@ -38,7 +38,7 @@ class Series(C.Structure):
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
-           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log"]
+           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid"]
 
 
 class KmcError(RuntimeError):
@@ -82,6 +82,7 @@ def lib():
         L.kmc_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
         L.kmc_get_accept.argtypes = [vp, i32, vp]
         L.kmc_get_events.argtypes = [vp, vp]
+        L.kmc_get_grid.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
         L.kmc_run.argtypes = [vp, i64, i32, C.c_char_p]
@@ -239,6 +240,11 @@ class Kmc:
         a = np.zeros(self.n + 1, dtype=np.int32)
         self._ck(lib().kmc_get_accept(self.h, replica, a.ctypes.data))
         return a
+
+    def grid(self):
+        x0, y0, edge, ncx, ncy = C.c_double(), C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
+        self._ck(lib().kmc_get_grid(self.h, C.byref(x0), C.byref(y0), C.byref(edge), C.byref(ncx), C.byref(ncy)))
+        return dict(x0=x0.value, y0=y0.value, inv_edge=edge.value, ncx=ncx.value, ncy=ncy.value)
 
     def events(self):
         e = np.zeros(16, dtype=np.int64)

@@ -805,12 +805,22 @@ struct Oracle {
         find_complexes();                                         // S1
         if (P.use_grid) { if (bins.empty()) grid_setup(); grid_fill(); }
         std::fill(accepted.begin(), accepted.end(), 1);
-        // S2 (577-1872), Gauss-Seidel in index order
-        for (int m = 1; m <= N; m++) {
+        // S2 (577-1872), Gauss-Seidel in index order (or, order_mode 1, colour by colour of the head's cell)
+        std::vector<int> seq(N);
+        for (int m = 1; m <= N; m++) seq[m - 1] = m;
+        if (P.order_mode == 1) {
+            std::vector<unsigned> key(N + 1);
+            for (int m = 1; m <= N; m++) {
+                int cx = (int)floor((R[m].p[1][1].x - P.order_x0) * P.order_inv_edge), cy = (int)floor((R[m].p[1][1].y - P.order_y0) * P.order_inv_edge);
+                key[m] = ((unsigned)((cx & 1) | ((cy & 1) << 1)) << 30) | (unsigned)m;
+            }
+            std::sort(seq.begin(), seq.end(), [&](int a, int b) { return key[a] < key[b]; });
+        }
+        for (int m : seq) {
             if (m <= NA) {
                 if (S(stn, m, 2) == 0 && S(stn, m, 3) == 0) move_free_receptor(m);
                 int p = NBR(nb, m, 3);
-                if (visited[m] == 0 && NBR(nb, m, 2) == 0 && m == NBR(nb, p, 3) && NBR(nb, p, 2) == 0) {
+                if (visited[m] == 0 && NBR(nb, m, 2) == 0 && m == NBR(nb, p, 3) && NBR(nb, p, 2) == 0 && (P.order_mode == 0 || m < p)) {
                     visited[p] = 1;
                     move_cis_dimer(m, p);
                 }
@@ -839,6 +849,7 @@ void kmco_default_params(kmco_params *p) {
     p->bond_dist_cut = 18; p->thetapd_cut = 45; p->thetaot_cut = 90; p->cis_thetaot_cut = 10; p->cis_dist_cut = 15;
     p->n_receptor = 150; p->n_ligand = 50; p->stream_mode = 0; p->use_grid = 0; p->seed = 1;
     p->rand2_state = 88172645463325252ULL; p->rand_state = 0x9E3779B97F4A7C15ULL;
+    p->order_mode = 0; p->order_x0 = p->order_y0 = 0; p->order_inv_edge = 1.0 / 256;
 }
 void *kmco_create(const kmco_params *p) { return new Oracle(*p); }
 void kmco_destroy(void *h) { delete (Oracle *)h; }

@@ -22,6 +22,12 @@ typedef struct kmco_params {
     int32_t use_grid;              // 0 = all-pairs loops like the reference, 1 = O(N) cell grid (same results)
     uint64_t seed;                 // keyed mode
     uint64_t rand2_state, rand_state;  // sequential mode stream states
+    // sweep order of S2 (main.cpp:577). 0 = molecule index, the reference's order. 1 = checkerboard: units are visited colour by
+    // colour of the grid cell (2x2 colouring, cell = floor((x - order_x0)*order_inv_edge)) of their head molecule's committed centre,
+    // by index inside a colour; a cis dimer is moved by its lower index. NOT in the reference: it restates the product's
+    // production mode with the reference's own step functions, so that mode can be checked bit for bit as well.
+    int32_t order_mode, pad_;
+    double order_x0, order_y0, order_inv_edge;
 } kmco_params;
 
 void kmco_default_params(kmco_params *p);

@@ -22,7 +22,8 @@ class Params(C.Structure):
                 ("cis_thetaot_cut", C.c_double), ("cis_dist_cut", C.c_double),
                 ("n_receptor", C.c_int32), ("n_ligand", C.c_int32), ("stream_mode", C.c_int32),
                 ("use_grid", C.c_int32), ("seed", C.c_uint64), ("rand2_state", C.c_uint64),
-                ("rand_state", C.c_uint64)]
+                ("rand_state", C.c_uint64), ("order_mode", C.c_int32), ("pad_", C.c_int32),
+                ("order_x0", C.c_double), ("order_y0", C.c_double), ("order_inv_edge", C.c_double)]
 
 
 def build(force=False):
