@@ -14,6 +14,7 @@ enum Scalar {
     S_NCAND_RL, S_NCAND_CIS,
     S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
     S_OVERFLOW,           // a device buffer overflowed (bitmask)
+    S_NA_LIVE, S_NB_LIVE, // molecules actually present in the receptor / ligand blocks (<= NAt / NBt; strips change them)
     S_COUNT = 16
 };
 enum UnitState : unsigned char { U_UNKNOWN = 0, U_ACCEPT = 1, U_REJECT = 2 };
@@ -51,6 +52,7 @@ struct Dev {
     int *pend;                                // [NT] single pending conflict of a unit: earlier unit | pose bit, -1 none
     int *unitRes;                             // [NT] per unit head: bit0 definite overlap, bit1 overlap pending on an earlier unit
     unsigned long long *step64;               // [1] mc_time_step of the step being computed
+    unsigned *refA, *refB;                    // reference (global, 1-based) ids of local receptors / ligands; null = a%NA+1, NA+h%NB+1
     int *scal;
     int *maxComplex;                       // [R]
     unsigned long long *events;
@@ -86,13 +88,26 @@ KD void store_lig(double *base, int h, const Lig &l) {
     for (int q = 0; q < 12; q++) p[q] = make_double2(d[2 * q], d[2 * q + 1]);
 }
 
+// x in the frame the cells are hashed in: with strips, the periodic image nearest to the strip centre, so that the band of the
+// membrane on the far side of the periodic seam sits next to this strip in the grid (distances always use true coordinates:
+// the reference has no minimum image, main.cpp:642-646; a molecule starts to interact across the seam only once it is wrapped)
+KD double hash_x(const Consts &K, double x) {       // stripHalf = +inf on a single GPU: two compares, never shifts
+    const double t = x - K.stripXc;
+    return t > K.stripHalf ? x - K.Lx : (t < -K.stripHalf ? x + K.Lx : x);
+}   // real branch: the single-GPU path pays nothing
+KD int nA_live(const Dev &D) { return D.scal[S_NA_LIVE]; }
+KD int nB_live(const Dev &D) { return D.scal[S_NB_LIVE]; }
+KD bool gid_live(const Consts &K, const Dev &D, int gid) { return gid < K.NAt ? gid < nA_live(D) : (gid < K.NT && gid - K.NAt < nB_live(D)); }
 KD int cell_of(const Consts &K, int replica, double x, double y) {
-    int cx = (int)floor((x - K.gx0) * K.cellInv), cy = (int)floor((y - K.gy0) * K.cellInv);
+    int cx = (int)floor((hash_x(K, x) - K.gx0) * K.cellInv), cy = (int)floor((y - K.gy0) * K.cellInv);
     cx = min(max(cx, 0), K.ncx - 1); cy = min(max(cy, 0), K.ncy - 1);
     return (replica * K.ncy + cy) * K.ncx + cx;
 }
 KD int replica_of_gid(const Consts &K, int gid) { return gid < K.NAt ? gid / K.NA : (gid - K.NAt) / K.NB; }
 // reference molecule id (1-based) used to key the random stream
-KD uint32_t ref_id(const Consts &K, int gid) { return gid < K.NAt ? (uint32_t)(gid % K.NA + 1) : (uint32_t)(K.NA + (gid - K.NAt) % K.NB + 1); }
+KD uint32_t ref_id(const Consts &K, const Dev &D, int gid) {
+    if (D.refA) return gid < K.NAt ? D.refA[gid] : D.refB[gid - K.NAt];
+    return gid < K.NAt ? (uint32_t)(gid % K.NA + 1) : (uint32_t)(K.NA + (gid - K.NAt) % K.NB + 1);
+}
 
 }  // namespace kmc

@@ -148,6 +148,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     if (const char *sk = getenv("KMC_SKIN")) { double v = atof(sk); if (v > 0) K.skin = v; }
     K.NA = P.n_receptor; K.NB = P.n_ligand; K.R = P.n_replicas; K.mode = P.mode;
     K.NAt = K.NA * K.R; K.NBt = K.NB * K.R; K.NT = K.NAt + K.NBt; K.seed = P.seed;
+    K.strips = 1; K.stripRank = 0; K.stripXc = 0; K.stripHalf = INFINITY;
     double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + 2 * K.skin + 1.0;   // walk around the OLD centre: reach + 2 skins
     if (P.cell_edge > edge) edge = P.cell_edge;
     else if (P.cell_edge == 0) edge = std::max(edge, getenv("KMC_EDGE") ? atof(getenv("KMC_EDGE")) : 256.0);
@@ -218,6 +219,8 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
          cudaMemset(D.recCis, 0xff, sizeof(int) * K.NAt) == cudaSuccess && cudaMemset(D.ligRec, 0xff, sizeof(int) * 3 * (size_t)K.NBt) == cudaSuccess;
     int one = 1;
     ok = ok && cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(D.scal + S_NA_LIVE, &K.NAt, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(D.scal + S_NB_LIVE, &K.NBt, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) return fail(KMC_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
     *out = h;
     return KMC_OK;

@@ -45,8 +45,10 @@ struct Consts {
     double skin;                              // far-mover threshold
     double gx0, gy0, cellInv; int ncx, ncy;   // neighbour grid
     int NA, NB, R, mode;                      // per-replica sizes, replicas
-    int NAt, NBt, NT;                         // totals
+    int NAt, NBt, NT;                         // totals (capacities of the receptor / ligand blocks; live counts are device scalars)
     uint64_t seed;
+    int strips, stripRank;                    // strip decomposition along x (1 = whole membrane on this GPU)
+    double stripXc, stripHalf;                // centre of this rank's strip and Lx/2 (+inf without strips): cells are hashed in the periodic frame around the centre
 };
 
 struct Rec { double cx, cy, s2x, s2y, s3x, s3y; };

@@ -51,7 +51,7 @@ __global__ void k_uf_init(const __grid_constant__ Args A) {
     if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cK.NT) return;
-    D.ufParent[i] = i; D.bfsMark[i] = 0;
+    D.ufParent[i] = i; D.bfsMark[i] = 0;          // (dead slots of a strip are harmless singletons)
     if (i < cK.NBt) { D.cxSize[i] = 0; D.cxOff[i] = -1; }
 }
 // one thread per receptor: its ligand edge and (once per pair) its cis edge
@@ -59,7 +59,7 @@ __global__ void k_uf_hook(const __grid_constant__ Args A) {
     KARGS
     if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
     int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= cK.NAt) return;
+    if (a >= nA_live(D)) return;
     int ua = cK.NBt + a;
     int l = D.recLig[a];
     if (l >= 0) uf_union(D.ufParent, ua, l);
@@ -70,7 +70,7 @@ __global__ void k_uf_flatten(const __grid_constant__ Args A) {
     KARGS
     if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
     int i = blockIdx.x * blockDim.x + threadIdx.x;   // uid
-    if (i >= cK.NT) return;
+    if (i >= cK.NT || !(i < cK.NBt ? i < nB_live(D) : i - cK.NBt < nA_live(D))) return;
     int r = uf_find(D.ufParent, i);
     int gid = i < cK.NBt ? cK.NAt + i : i - cK.NBt;
     int head = r < cK.NBt ? cK.NAt + r : r - cK.NBt;
@@ -83,7 +83,7 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     KARGS
     if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
     int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= cK.NBt) return;
+    if (h >= nB_live(D)) return;
     if (D.unitOf[cK.NAt + h] != cK.NAt + h) return;
     int size = D.cxSize[h];
     if (size > D.maxComplex[h / cK.NB]) atomicMax(&D.maxComplex[h / cK.NB], size);      // main.cpp:896-898 (read first: one hot address)
@@ -116,7 +116,7 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
 KD bool unit_before(int v, int u) { return (unsigned)v < (unsigned)u; }
 KD int unit_key(const Consts &K, int head, double hx, double hy) {
     if (K.mode == 0) return head;
-    const int cx = (int)floor((hx - K.gx0) * K.cellInv), cy = (int)floor((hy - K.gy0) * K.cellInv);
+    const int cx = (int)floor((hash_x(K, hx) - K.gx0) * K.cellInv), cy = (int)floor((hy - K.gy0) * K.cellInv);
     return (int)((unsigned)head | ((unsigned)((cx & 1) | ((cy & 1) << 1)) << 30));
 }
 
@@ -145,13 +145,13 @@ __global__ void k_propose_simple(const __grid_constant__ Args A) {
     KARGS
     const uint64_t step = D.step64[0];
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= cK.NT) return;
     if (gid == 0) D.scal[S_TOPO_DIRTY] = 0;       // the gated rebuild kernels of this step are done; S3 sets it again
+    if (!gid_live(cK, D, gid)) return;
     if (D.unitOf[gid] != gid) return;             // not the head of a unit
     const Consts &K = cK;
     const int rep = replica_of_gid(K, gid);
     const uint64_t seed = seed_of(cK, rep);
-    const uint32_t me = ref_id(K, gid);
+    const uint32_t me = ref_id(K, D, gid);
     if (gid < K.NAt) {
         const int a = gid, p = D.recCis[a];
         Rec ra = load_rec(D.recC, D.recS2, D.recS3, a);
@@ -322,7 +322,7 @@ __global__ void k_propose_complex(const __grid_constant__ Args A) {
     int *row = D.rowWork + D.cxOff[h0];
     const int rep = h0 / K.NB;
     const uint64_t seed = seed_of(cK, rep);
-    const uint32_t me = ref_id(K, rootGid);
+    const uint32_t me = ref_id(K, D, rootGid);
     CxCtx C{D, K};
     int nA = 0, nB = 0;
     for (int i = 0; i < size; i++) { int m = rowIn[i]; row[i] = m; D.movedFlag[m] = 0; if (m < K.NAt) nA++; else nB++; }
@@ -479,7 +479,7 @@ KD void centre_of(const Consts &cK, const Dev &D, int gid, bool nxt, double &x, 
 __global__ void k_grid_scatter(const __grid_constant__ Args A) {
     KARGS
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid < cK.NT) {
+    if (gid_live(cK, D, gid)) {
         int rep = replica_of_gid(cK, gid);
         double x, y; centre_of(cK, D, gid, false, x, y);
         int c = cell_of(cK, rep, x, y);
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(256) k_scan_down(int4 *in, const int *blockSum
 struct Probe { bool rec; double cx, cy; double b[3][3]; };
 
 template <class F> KD void for_cells3x3(const Consts &cK, int rep, double x, double y, const Dev &D, F f) {
-    int cx = (int)floor((x - cK.gx0) * cK.cellInv), cy = (int)floor((y - cK.gy0) * cK.cellInv);
+    int cx = (int)floor((hash_x(cK, x) - cK.gx0) * cK.cellInv), cy = (int)floor((y - cK.gy0) * cK.cellInv);
     cx = min(max(cx, 0), cK.ncx - 1); cy = min(max(cy, 0), cK.ncy - 1);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, cK.ncx - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, cK.ncy - 1);
     int e0[3], e1[3];
@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
         const TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.rowStart[lo] + (i - S.rowBase[lo])]));
         S.ox[i] = t.ox; S.oy[i] = t.oy; S.nx[i] = t.nx; S.ny[i] = t.ny; S.gid[i] = t.gid; S.unit[i] = t.unit; S.flg[i] = (unsigned char)t.flg;
         const bool g = t.flg & F_GHOST;                                   // what this entry stands for, window-relative, fp32 (cut only)
-        S.sx[i] = (float)((g ? t.nx : t.ox) - tox); S.sy[i] = (float)((g ? t.ny : t.oy) - toy);
+        S.sx[i] = (float)(hash_x(K, g ? t.nx : t.ox) - tox); S.sy[i] = (float)((g ? t.ny : t.oy) - toy);
     }
     for (int r = threadIdx.x / 32; r < nrow; r += TTHREADS / 32)
         for (int c = threadIdx.x & 31; c < ncol; c += 32)
@@ -921,8 +921,8 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
             const int f = S.flg[ime];
             // centre the cut is measured from: P, or O for the old entry of a far mover (which is only a reaction partner)
             const bool pOnly = (f & F_FAR) && !(f & F_GHOST);
-            const float fx = (float)((pOnly ? S.ox[ime] : S.nx[ime]) - tox), fy = (float)((pOnly ? S.oy[ime] : S.ny[ime]) - toy);
-            const int cxe = min(max((int)floor(((f & F_GHOST ? S.nx[ime] : S.ox[ime]) - K.gx0) * K.cellInv), 0), K.ncx - 1);
+            const float fx = (float)(hash_x(K, pOnly ? S.ox[ime] : S.nx[ime]) - tox), fy = (float)((pOnly ? S.oy[ime] : S.ny[ime]) - toy);
+            const int cxe = min(max((int)floor((hash_x(K, f & F_GHOST ? S.nx[ime] : S.ox[ime]) - K.gx0) * K.cellInv), 0), K.ncx - 1);
             const int cxl = max(cxe - 1, 0) - wx0, cxh = min(cxe + 1, K.ncx - 1) + 1 - wx0;
             const float cR = prec ? cRR : cLR, cL = prec ? cRL : cLL;
             const float cR2 = cR * cR, cL2 = cL * cL;
@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
             const TileRec me = ime < TCAP ? staged(ime) : fetch_rec(K, D, __ldg(&D.sorted[eme]));
             const ProbeCtx c = make_probe(K, me);
             const double wxp = c.ghost ? me.nx : me.ox;
-            const int cxe = min(max((int)floor((wxp - K.gx0) * K.cellInv), 0), K.ncx - 1);
+            const int cxe = min(max((int)floor((hash_x(K, wxp) - K.gx0) * K.cellInv), 0), K.ncx - 1);
             const int cxl = max(cxe - 1, 0) - wx0, cxh = min(cxe + 1, K.ncx - 1) + 1 - wx0;
             const double cutR = (c.prec ? fmax(K.reachRL, K.reachOn) : K.reachLL) + 2 * K.skin, cut2 = cutR * cutR;
             for (int dr = -1; dr <= 1; dr++) {
@@ -992,7 +992,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
 __global__ void k_decide(const __grid_constant__ Args A) {
     KARGS
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= cK.NT || D.unitOf[gid] != gid) return;
+    if (!gid_live(cK, D, gid) || D.unitOf[gid] != gid) return;
     const int r = D.unitRes[gid];
     int st = U_UNKNOWN;
     if (r & 1) st = U_REJECT;
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(256) k_resolve_finish(const __grid_constant__ 
 __global__ void k_restore(const __grid_constant__ Args A) {
     KARGS
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= cK.NT) return;
+    if (!gid_live(cK, D, gid)) return;
     if (D.unitState[D.unitOf[gid]] != U_REJECT) return;
     if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
     else {
@@ -1071,7 +1071,7 @@ __global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Arg
         const int a = (int)(pr >> 32), v = (int)(pr & 0xffffffffu);
         const int rep = a / K.NA;
         const uint64_t seed = seed_of(K, rep);
-        const uint32_t me = ref_id(K, a), j = ref_id(K, v);
+        const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
         const Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
         if (v >= K.NAt) {
             if (D.recLig[a] >= 0) continue;
@@ -1155,13 +1155,13 @@ __global__ void k_dissociate(const __grid_constant__ Args A) {
     KARGS
     const uint64_t step = D.step64[0];
     int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= cK.NAt) return;
+    if (a >= nA_live(D)) return;
     const Consts &K = cK;
     const int rep = a / K.NA;
     const uint64_t seed = seed_of(cK, rep);
     const int h = D.recLig[a], p = D.recCis[a];
     if (h < 0 && p < 0) return;
-    const uint32_t me = ref_id(K, a);
+    const uint32_t me = ref_id(K, D, a);
     bool boundAfter = false;
     if (h >= 0) {
         if (keyed_uniform(seed, me, 0, step, SLOT_RL_OFF) < K.pOff) {
@@ -1171,7 +1171,7 @@ __global__ void k_dissociate(const __grid_constant__ Args A) {
         } else boundAfter = true;
     }
     if (p > a) {
-        const uint32_t pid = ref_id(K, p);
+        const uint32_t pid = ref_id(K, D, p);
         // partner's ligand state after ITS R-L dissociation trial: -1 already cleared, else apply its draw
         bool pBoundAfter = D.recLig[p] >= 0 && !(keyed_uniform(seed, pid, 0, step, SLOT_RL_OFF) < K.pOff);
         bool inComplex = boundAfter || pBoundAfter;
@@ -1191,7 +1191,7 @@ __global__ void k_dissociate(const __grid_constant__ Args A) {
 __global__ void k_series(const __grid_constant__ Args A, int *out /*[R][4]: rl, mono, cis, -*/) {
     KARGS
     int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= cK.NAt) return;
+    if (a >= nA_live(D)) return;
     int rep = a / cK.NA;
     if (D.recLig[a] >= 0) atomicAdd(&out[rep * 4 + 0], 1);
     int p = D.recCis[a];
