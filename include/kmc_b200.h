@@ -150,6 +150,22 @@ int kmc_write_cluster_log(kmc_handle *h, int32_t replica, const char *path);
 /* the reference's own main loop: n_steps steps with records every output_every steps into directory `dir` */
 int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, const char *dir);
 
+/* ---- strip decomposition of one membrane across GPUs (one handle per rank; see csrc/kmc_strips.cu) ------------------------
+ * The handle is created with n_receptor / n_ligand = local CAPACITIES (owned + halo molecules), then configured as rank
+ * `rank` of `nranks` strips along x with halo width `halo_width` (Angstrom). The caller steps all ranks by the same number of
+ * steps and, every k steps, refreshes: begin_refresh on every rank, message(0) -> rank-1 (received there as from_high),
+ * message(1) -> rank+1 (received as from_low), ranks 0 and nranks-1 being neighbours through the periodic seam; then rebuild.
+ * Exactness needs halo_width >= k * (interaction reach + 2 max displacement per step) + largest complex extent.
+ * message(2) after begin_refresh is the set this rank owns (gather of the global state). Message layout: int64 nRec, int64 nLig,
+ * nRec x {int32 ref, ligRef, site(0..2,-1), cisRef; double pose[6]}, nLig x {int32 ref, recRef[3]; double pose[24]}; refs are
+ * reference ids (1-based: receptors 1..NA, ligands NA+1..N), 0 = none; both lists sorted by ref. */
+int kmc_strip_configure(kmc_handle *h, int32_t rank, int32_t nranks, double halo_width);
+int kmc_strip_load_global(kmc_handle *h, int32_t n_rec, int32_t n_lig, const double *rec_pose, const double *lig_pose,
+                          const int32_t *rec_lig, const int32_t *rec_site, const int32_t *rec_cis, int64_t step_done);
+int kmc_strip_begin_refresh(kmc_handle *h);
+int64_t kmc_strip_message(kmc_handle *h, int32_t side, const void **data);
+int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_low, const void *from_high, int64_t n_high);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,18 @@ using namespace kmc;
 
 static thread_local std::string g_create_error;
 
+// ---- strip decomposition bookkeeping (csrc/kmc_strips.cu) ----
+#pragma pack(push, 1)
+struct RecMsg { int32_t ref, ligRef, site, cisRef; double pose[6]; };      // 64 bytes; refs are reference ids (1-based), 0 = none
+struct LigMsg { int32_t ref, recRef[3]; double pose[24]; };               // 208 bytes
+#pragma pack(pop)
+
+struct HostLocal {       // host mirror of the live local state
+    std::vector<double> rec, lig; std::vector<int> rl, rs, rc, lr; std::vector<unsigned> refA, refB;
+    int nA = 0, nB = 0;
+};
+
+
 struct kmc_handle {
     kmc_params P;
     Consts K;
@@ -32,6 +44,9 @@ struct kmc_handle {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int parity = 0, launches_per_step = 0;
     bool use_graph = true;
+    // strips
+    bool strip_on = false; double strip_W = 0, strip_lo = 0, strip_hi = 0; int64_t strip_refreshes = 0;
+    HostLocal strip_local; std::vector<char> strip_msg[3];
     int64_t launches = 0, passes = 0;
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py roofline)
     bool profiling = false;
@@ -816,3 +831,5 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
     CK(cudaMemcpy(h->D.maxComplex, zero.data(), sizeof(int) * h->R, cudaMemcpyHostToDevice));
     return KMC_OK;
 }
+
+#include "kmc_strips.cu"

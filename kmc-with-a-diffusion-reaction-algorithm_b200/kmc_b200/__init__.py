@@ -38,7 +38,8 @@ class Series(C.Structure):
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
-           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid"]
+           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
+           "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild"]
 
 
 class KmcError(RuntimeError):
@@ -82,6 +83,12 @@ def lib():
         L.kmc_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
         L.kmc_get_accept.argtypes = [vp, i32, vp]
         L.kmc_get_events.argtypes = [vp, vp]
+        L.kmc_strip_configure.argtypes = [vp, i32, i32, C.c_double]
+        L.kmc_strip_load_global.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64]
+        L.kmc_strip_begin_refresh.argtypes = [vp]
+        L.kmc_strip_message.restype = i64
+        L.kmc_strip_message.argtypes = [vp, i32, C.POINTER(vp)]
+        L.kmc_strip_rebuild.argtypes = [vp, vp, i64, vp, i64]
         L.kmc_get_grid.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
@@ -240,6 +247,28 @@ class Kmc:
         a = np.zeros(self.n + 1, dtype=np.int32)
         self._ck(lib().kmc_get_accept(self.h, replica, a.ctypes.data))
         return a
+
+    # ---- strip decomposition (csrc/kmc_strips.cu) ----
+    def strip_configure(self, rank, nranks, halo_width):
+        self._ck(lib().kmc_strip_configure(self.h, rank, nranks, float(halo_width)))
+
+    def strip_load_global(self, rec, lig, rl=None, rs=None, rc=None, step_done=0):
+        rec = np.ascontiguousarray(rec, dtype=np.float64); lig = np.ascontiguousarray(lig, dtype=np.float64)
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.int32) for a in (rl, rs, rc)]
+        ptr = [None if a is None else a.ctypes.data for a in arrs]
+        self._ck(lib().kmc_strip_load_global(self.h, rec.shape[0], lig.shape[0], rec.ctypes.data, lig.ctypes.data, ptr[0], ptr[1], ptr[2], step_done))
+
+    def strip_begin_refresh(self):
+        self._ck(lib().kmc_strip_begin_refresh(self.h))
+
+    def strip_message(self, side):
+        """bytes of message `side` (0: to lower-x neighbour, 1: to higher-x neighbour, 2: the owned set) after strip_begin_refresh"""
+        ptr = C.c_void_p()
+        n = self._ck(lib().kmc_strip_message(self.h, side, C.byref(ptr)))
+        return C.string_at(ptr, n) if n else b""
+
+    def strip_rebuild(self, from_low, from_high):
+        self._ck(lib().kmc_strip_rebuild(self.h, from_low, len(from_low), from_high, len(from_high)))
 
     def grid(self):
         x0, y0, edge, ncx, ncy = C.c_double(), C.c_double(), C.c_double(), C.c_int32(), C.c_int32()

@@ -1,0 +1,164 @@
+"""Strip decomposition driver: one membrane across several GPUs (one kmc handle per rank, csrc/kmc_strips.cu).
+
+StripRank wraps one rank's handle; the exchange of the boundary bands is done here, either between handles living in one
+process (LocalStrips: K logical ranks on one GPU, used to prove equality with the single-GPU run) or between processes with
+torch.distributed point-to-point operations (DistStrips: NCCL send/recv over NVLink when the backend is nccl; gloo on CPU for
+the message plumbing tests)."""
+import numpy as np
+
+from . import Kmc
+
+REC_DT = np.dtype([("ref", "<i4"), ("ligRef", "<i4"), ("site", "<i4"), ("cisRef", "<i4"), ("pose", "<f8", (6,))])
+LIG_DT = np.dtype([("ref", "<i4"), ("recRef", "<i4", (3,)), ("pose", "<f8", (24,))])
+assert REC_DT.itemsize == 64 and LIG_DT.itemsize == 208
+
+# per-step reach of information: largest overlap reach (ligand-ligand centres, 2 rB + 2*2rB/sqrt3 = 129.3 A at default radii) plus
+# twice the largest displacement of a molecule in one step (complex members swing up to ~31 A); rounded up generously
+D1 = 200.0
+
+
+def halo_for(refresh_every, complex_extent=400.0):
+    """halo width that keeps the owned strip exact for `refresh_every` steps between refreshes"""
+    return refresh_every * D1 + complex_extent
+
+
+def parse_message(buf):
+    if len(buf) < 16:
+        return np.zeros(0, REC_DT), np.zeros(0, LIG_DT)
+    n = np.frombuffer(buf, dtype="<i8", count=2)
+    rec = np.frombuffer(buf, dtype=REC_DT, count=int(n[0]), offset=16)
+    lig = np.frombuffer(buf, dtype=LIG_DT, count=int(n[1]), offset=16 + int(n[0]) * 64)
+    return rec, lig
+
+
+def assemble_global(messages, n_rec, n_lig):
+    """owned sets of all ranks -> global packed state (rec[n_rec,6], lig[n_lig,24], rec_lig, rec_site, rec_cis as 0-based
+    global indices / site 2..4, the kmc_get_packed conventions). Every molecule must be owned exactly once."""
+    rec = np.full((n_rec, 6), np.nan); lig = np.full((n_lig, 24), np.nan)
+    rl = np.full(n_rec, -1, np.int32); rs = np.zeros(n_rec, np.int32); rc = np.full(n_rec, -1, np.int32)
+    seen_r = np.zeros(n_rec, np.int32); seen_l = np.zeros(n_lig, np.int32)
+    for buf in messages:
+        r, l = parse_message(buf)
+        a = r["ref"] - 1
+        rec[a] = r["pose"]; seen_r[a] += 1
+        rl[a] = np.where(r["ligRef"] > 0, r["ligRef"] - n_rec - 1, -1); rs[a] = np.where(r["ligRef"] > 0, r["site"] + 2, 0)
+        rc[a] = np.where(r["cisRef"] > 0, r["cisRef"] - 1, -1)
+        b = l["ref"] - n_rec - 1
+        lig[b] = l["pose"]; seen_l[b] += 1
+    assert (seen_r == 1).all() and (seen_l == 1).all(), "ownership is not a partition: %d/%d receptors, %d/%d ligands owned once" % (
+        (seen_r == 1).sum(), n_rec, (seen_l == 1).sum(), n_lig)
+    return rec, lig, rl, rs, rc
+
+
+class StripRank:
+    def __init__(self, params, rank, nranks, halo_width):
+        self.k = Kmc(params)
+        self.rank, self.nranks = rank, nranks
+        self.k.strip_configure(rank, nranks, halo_width)
+
+    def load_global(self, rec, lig, rl=None, rs=None, rc=None, step_done=0):
+        self.k.strip_load_global(rec, lig, rl, rs, rc, step_done)
+
+
+class LocalStrips:
+    """K logical ranks in one process (all on one GPU): the in-process stand-in for the NCCL exchange."""
+
+    def __init__(self, make_params, nranks, refresh_every, halo_width=None):
+        self.n, self.every = nranks, refresh_every
+        self.halo = halo_width if halo_width is not None else halo_for(refresh_every)
+        self.ranks = [StripRank(make_params(r), r, nranks, self.halo) for r in range(nranks)]
+        self.since = 0
+
+    def load_global(self, *a, **kw):
+        for r in self.ranks:
+            r.load_global(*a, **kw)
+
+    def refresh(self):
+        for r in self.ranks:
+            r.k.strip_begin_refresh()
+        low = [r.k.strip_message(0) for r in self.ranks]; high = [r.k.strip_message(1) for r in self.ranks]
+        for i, r in enumerate(self.ranks):
+            if self.n == 1:
+                r.k.strip_rebuild(b"", b"")
+            else:   # what my lower neighbour sent upwards arrives as from_low; what my upper neighbour sent downwards as from_high
+                r.k.strip_rebuild(high[(i - 1) % self.n], low[(i + 1) % self.n])
+        self.since = 0
+
+    def step(self, n):
+        while n > 0:
+            m = min(n, self.every - self.since)
+            for r in self.ranks:
+                r.k.step(m)
+            self.since += m; n -= m
+            if self.since == self.every:
+                self.refresh()
+
+    def gather(self, n_rec, n_lig):
+        for r in self.ranks:
+            r.k.strip_begin_refresh()
+        return assemble_global([r.k.strip_message(2) for r in self.ranks], n_rec, n_lig)
+
+
+class DistStrips:
+    """one rank per process; boundary bands travel with torch.distributed send/recv (NCCL over NVLink with backend nccl)"""
+
+    def __init__(self, params, refresh_every, halo_width=None, dist=None, device=None):
+        import torch
+        self.torch, self.dist = torch, dist
+        self.rank, self.n = dist.get_rank(), dist.get_world_size()
+        self.every = refresh_every
+        self.halo = halo_width if halo_width is not None else halo_for(refresh_every)
+        self.device = device if device is not None else ("cuda:%d" % params.device if dist.get_backend() == "nccl" else "cpu")
+        self.sr = StripRank(params, self.rank, self.n, self.halo)
+        self.k = self.sr.k
+        self.since = 0
+        self.bytes_sent = 0
+
+    def load_global(self, *a, **kw):
+        self.sr.load_global(*a, **kw)
+
+    def _exchange(self, to_low, to_high):
+        torch, dist = self.torch, self.dist
+        lo, hi = (self.rank - 1) % self.n, (self.rank + 1) % self.n
+        def as_t(b):
+            return torch.frombuffer(bytearray(b) if b else bytearray(1), dtype=torch.uint8).to(self.device)
+        s_low, s_high = as_t(to_low), as_t(to_high)
+        sizes_out = torch.tensor([len(to_low), len(to_high)], dtype=torch.int64, device=self.device)
+        sz_from_low = torch.zeros(2, dtype=torch.int64, device=self.device); sz_from_high = torch.zeros(2, dtype=torch.int64, device=self.device)
+        ops = [dist.P2POp(dist.isend, sizes_out, lo), dist.P2POp(dist.isend, sizes_out.clone(), hi),
+               dist.P2POp(dist.irecv, sz_from_low, lo), dist.P2POp(dist.irecv, sz_from_high, hi)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        # the lower neighbour's message for me is its "to_high" (index 1); the upper neighbour's is its "to_low" (index 0)
+        n_low, n_high = int(sz_from_low[1].item()), int(sz_from_high[0].item())
+        r_low = torch.empty(max(n_low, 1), dtype=torch.uint8, device=self.device); r_high = torch.empty(max(n_high, 1), dtype=torch.uint8, device=self.device)
+        ops = [dist.P2POp(dist.isend, s_low, lo), dist.P2POp(dist.isend, s_high, hi), dist.P2POp(dist.irecv, r_low, lo), dist.P2POp(dist.irecv, r_high, hi)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.bytes_sent += len(to_low) + len(to_high)
+        return bytes(r_low[:n_low].cpu().numpy().tobytes()), bytes(r_high[:n_high].cpu().numpy().tobytes())
+
+    def refresh(self):
+        self.k.strip_begin_refresh()
+        if self.n == 1:
+            self.k.strip_rebuild(b"", b"")
+        else:
+            from_low, from_high = self._exchange(self.k.strip_message(0), self.k.strip_message(1))
+            self.k.strip_rebuild(from_low, from_high)
+        self.since = 0
+
+    def step(self, n):
+        while n > 0:
+            m = min(n, self.every - self.since)
+            self.k.step(m)
+            self.since += m; n -= m
+            if self.since == self.every:
+                self.refresh()
+
+    def gather(self, n_rec, n_lig):
+        """global state on every rank (all_gather of the owned sets)"""
+        self.k.strip_begin_refresh()
+        mine = self.k.strip_message(2)
+        out = [None] * self.n
+        self.dist.all_gather_object(out, mine)
+        return assemble_global(out, n_rec, n_lig)
