@@ -50,6 +50,30 @@ def assemble_global(messages, n_rec, n_lig):
     return rec, lig, rl, rs, rc
 
 
+def ring_exchange(torch, dist, device, to_low, to_high):
+    """Every rank sends `to_low` to rank-1 and `to_high` to rank+1 (periodic) and returns (what rank-1 sent upwards, what rank+1
+    sent downwards). Point-to-point operations (NCCL has no tags: operations between one pair of ranks are matched in posting
+    order, so sends are posted [to_low, to_high] and receives [from the upper neighbour, from the lower neighbour]; with two
+    ranks, where both neighbours are the same peer, that makes the peer's first receive meet my first send)."""
+    rank, n = dist.get_rank(), dist.get_world_size()
+    lo, hi = (rank - 1) % n, (rank + 1) % n
+
+    def as_t(b):
+        return torch.frombuffer(bytearray(b) if b else bytearray(1), dtype=torch.uint8).to(device)
+
+    def run(ops):
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    sizes = torch.tensor([len(to_low), len(to_high)], dtype=torch.int64, device=device)
+    sz_hi = torch.zeros(2, dtype=torch.int64, device=device); sz_lo = torch.zeros(2, dtype=torch.int64, device=device)
+    run([dist.P2POp(dist.isend, sizes, lo), dist.P2POp(dist.isend, sizes.clone(), hi), dist.P2POp(dist.irecv, sz_hi, hi), dist.P2POp(dist.irecv, sz_lo, lo)])
+    n_from_hi, n_from_lo = int(sz_hi[0].item()), int(sz_lo[1].item())      # the upper neighbour's to_low, the lower neighbour's to_high
+    r_hi = torch.empty(max(n_from_hi, 1), dtype=torch.uint8, device=device); r_lo = torch.empty(max(n_from_lo, 1), dtype=torch.uint8, device=device)
+    run([dist.P2POp(dist.isend, as_t(to_low), lo), dist.P2POp(dist.isend, as_t(to_high), hi), dist.P2POp(dist.irecv, r_hi, hi), dist.P2POp(dist.irecv, r_lo, lo)])
+    return r_lo[:n_from_lo].cpu().numpy().tobytes(), r_hi[:n_from_hi].cpu().numpy().tobytes()
+
+
 class StripRank:
     def __init__(self, params, rank, nranks, halo_width):
         self.k = Kmc(params)
@@ -118,25 +142,9 @@ class DistStrips:
         self.sr.load_global(*a, **kw)
 
     def _exchange(self, to_low, to_high):
-        torch, dist = self.torch, self.dist
-        lo, hi = (self.rank - 1) % self.n, (self.rank + 1) % self.n
-        def as_t(b):
-            return torch.frombuffer(bytearray(b) if b else bytearray(1), dtype=torch.uint8).to(self.device)
-        s_low, s_high = as_t(to_low), as_t(to_high)
-        sizes_out = torch.tensor([len(to_low), len(to_high)], dtype=torch.int64, device=self.device)
-        sz_from_low = torch.zeros(2, dtype=torch.int64, device=self.device); sz_from_high = torch.zeros(2, dtype=torch.int64, device=self.device)
-        ops = [dist.P2POp(dist.isend, sizes_out, lo), dist.P2POp(dist.isend, sizes_out.clone(), hi),
-               dist.P2POp(dist.irecv, sz_from_low, lo), dist.P2POp(dist.irecv, sz_from_high, hi)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        # the lower neighbour's message for me is its "to_high" (index 1); the upper neighbour's is its "to_low" (index 0)
-        n_low, n_high = int(sz_from_low[1].item()), int(sz_from_high[0].item())
-        r_low = torch.empty(max(n_low, 1), dtype=torch.uint8, device=self.device); r_high = torch.empty(max(n_high, 1), dtype=torch.uint8, device=self.device)
-        ops = [dist.P2POp(dist.isend, s_low, lo), dist.P2POp(dist.isend, s_high, hi), dist.P2POp(dist.irecv, r_low, lo), dist.P2POp(dist.irecv, r_high, hi)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+        out = ring_exchange(self.torch, self.dist, self.device, to_low, to_high)
         self.bytes_sent += len(to_low) + len(to_high)
-        return bytes(r_low[:n_low].cpu().numpy().tobytes()), bytes(r_high[:n_high].cpu().numpy().tobytes())
+        return out
 
     def refresh(self):
         self.k.strip_begin_refresh()

@@ -38,3 +38,46 @@ def test_two_ranks_gloo(tmp_path):
     assert out["world"] == 2 and out["ms"] == 15.0
     assert [r[0] for r in out["rows"]] == list(range(7))
     assert [r[1]["seed"] for r in out["rows"]] == [50 + r for r in range(7)]   # replica r keeps seed base + r for any GPU count
+
+
+RING = textwrap.dedent('''
+    import os, sys, json
+    sys.path.insert(0, os.path.join(%r, "kmc-with-a-diffusion-reaction-algorithm_b200"))
+    import torch, torch.distributed as dist
+    from kmc_b200.strips import ring_exchange
+    dist.init_process_group("gloo")
+    r, n = dist.get_rank(), dist.get_world_size()
+    ok = True
+    for trial in range(3):
+        to_low = bytes([r, 0, trial]) * (5 + r + trial); to_high = bytes([r, 1, trial]) * (2 + 3 * r)
+        if trial == 2: to_low = b""
+        from_low, from_high = ring_exchange(torch, dist, "cpu", to_low, to_high)
+        lo, hi = (r - 1) %% n, (r + 1) %% n
+        exp_low = bytes([lo, 1, trial]) * (2 + 3 * lo)                       # the lower neighbour's to_high
+        exp_high = b"" if trial == 2 else bytes([hi, 0, trial]) * (5 + hi + trial)   # the upper neighbour's to_low
+        ok = ok and from_low == exp_low and from_high == exp_high
+    res = [None] * n
+    dist.all_gather_object(res, ok)
+    if r == 0: print(json.dumps({"ok": all(res), "world": n}))
+    dist.destroy_process_group()
+''') % ROOT
+
+
+def _run_ring(tmp_path, nproc, port):
+    script = tmp_path / ("ring%d.py" % nproc)
+    script.write_text(RING)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    import json
+    return json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_strip_ring_exchange_two_ranks(tmp_path):
+    """halo messages between strips: with two ranks both neighbours are the same peer (through the middle boundary and through the
+    periodic seam) -- the pairing of untagged point-to-point operations must still be right"""
+    assert _run_ring(tmp_path, 2, 29741) == {"ok": True, "world": 2}
+
+
+def test_strip_ring_exchange_three_ranks(tmp_path):
+    assert _run_ring(tmp_path, 3, 29743) == {"ok": True, "world": 3}
