@@ -165,6 +165,12 @@ int kmc_strip_load_global(kmc_handle *h, int32_t n_rec, int32_t n_lig, const dou
 int kmc_strip_begin_refresh(kmc_handle *h);
 int64_t kmc_strip_message(kmc_handle *h, int32_t side, const void **data);
 int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_low, const void *from_high, int64_t n_high);
+/* the same refresh with all data staying in device memory: messages are [rec records][lig records] in device buffers (counts are
+ * returned separately), the caller moves them GPU to GPU (NCCL) into the buffers kmc_strip_recv_dev hands out */
+int kmc_strip_begin_refresh_dev(kmc_handle *h);
+int kmc_strip_message_dev(kmc_handle *h, int32_t side, void **dev_ptr, int64_t *n_rec, int64_t *n_lig);
+int kmc_strip_recv_dev(kmc_handle *h, int32_t side, int64_t n_rec, int64_t n_lig, void **dev_ptr);
+int kmc_strip_rebuild_dev(kmc_handle *h, int64_t rec_low, int64_t lig_low, int64_t rec_high, int64_t lig_high);
 
 #ifdef __cplusplus
 }

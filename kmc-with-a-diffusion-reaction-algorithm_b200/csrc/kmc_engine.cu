@@ -18,6 +18,7 @@ using namespace kmc;
 static thread_local std::string g_create_error;
 
 // ---- strip decomposition bookkeeping (csrc/kmc_strips.cu) ----
+struct StripDev;
 #pragma pack(push, 1)
 struct RecMsg { int32_t ref, ligRef, site, cisRef; double pose[6]; };      // 64 bytes; refs are reference ids (1-based), 0 = none
 struct LigMsg { int32_t ref, recRef[3]; double pose[24]; };               // 208 bytes
@@ -47,6 +48,7 @@ struct kmc_handle {
     // strips
     bool strip_on = false; double strip_W = 0, strip_lo = 0, strip_hi = 0; int64_t strip_refreshes = 0;
     HostLocal strip_local; std::vector<char> strip_msg[3];
+    struct StripDev *strip_dev = nullptr;
     int64_t launches = 0, passes = 0;
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py roofline)
     bool profiling = false;

@@ -291,3 +291,241 @@ extern "C" int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_
     h->strip_refreshes++;
     return strip_upload(h, s);
 }
+
+// ================================================================================================================
+// Device-side refresh: the same three phases (classify + pack, exchange by the caller, merge) without the host round trip.
+// Messages live in device buffers ([RecMsg x nRec][LigMsg x nLig], counts travel separately), so NCCL moves them GPU to GPU.
+// The host path above is kept as the reference implementation (tests compare the two).
+// ================================================================================================================
+struct StripDev {
+    unsigned char *flag = nullptr;            // [NT] bit0 owned, bit1 send to lower-x neighbour, bit2 send to higher-x neighbour
+    int *tmp = nullptr, *blk = nullptr;       // scan input (padded) and block sums
+    int *pos[6] = {nullptr};                  // exclusive prefixes: [list*2 + species] (list 0 low, 1 high, 2 keep; species 0 rec, 1 lig)
+    char *msg[3] = {nullptr}; size_t msgCap[3] = {0};     // packed messages (2 = the owned set)
+    char *rcv[2] = {nullptr}; size_t rcvCap[2] = {0};     // what the neighbours sent (0 from lower x, 1 from higher x)
+    int *bondRef = nullptr;                   // [NAt*3 + NBt*3] bonds of the merged molecules as reference ids, before translation
+    int cnt[6] = {0};                         // totals of pos[]
+    int padN = 0;
+};
+
+__device__ __forceinline__ int d_strip_owner(const Consts &K, double x) {
+    const double L = K.Lx, xw = x - L * round(x / L);
+    int r = (int)floor((xw + L / 2) / (L / K.strips));
+    return min(max(r, 0), K.strips - 1);
+}
+__global__ void k_strip_prebuild(const __grid_constant__ Args A) {
+    KARGS
+    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; }
+}
+// one thread per molecule, unit heads act: owner of the unit from the head's centre; bands from every member
+__global__ void k_strip_classify(const __grid_constant__ Args A, unsigned char *flag, double lo, double hi, double W) {
+    KARGS
+    const Consts &K = cK;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!gid_live(K, D, gid) || D.unitOf[gid] != gid) return;
+    double hx0, hy0; centre_of(K, D, gid, false, hx0, hy0);
+    const bool own = d_strip_owner(K, hx0) == K.stripRank;
+    int nmem = 1, m2 = -1; const int *row = nullptr;
+    if (gid < K.NAt) { m2 = D.recCis[gid]; if (m2 >= 0) nmem = 2; }
+    else if (D.cxSize[gid - K.NAt] > 1) { nmem = D.cxSize[gid - K.NAt]; row = D.members + D.cxOff[gid - K.NAt]; }
+    int f = own ? 1 : 0;
+    if (own)
+        for (int i = 0; i < nmem; i++) {
+            const int m = row ? row[i] : (i == 0 ? gid : m2);
+            double x, y; centre_of(K, D, m, false, x, y);
+            const double t = hash_x(K, x);
+            if (t < lo + W) f |= 2;
+            if (t >= hi - W) f |= 4;
+        }
+    for (int i = 0; i < nmem; i++) flag[row ? row[i] : (i == 0 ? gid : m2)] = (unsigned char)f;
+}
+__global__ void k_strip_flag_ints(const __grid_constant__ Args A, const unsigned char *flag, int species, int bit, int *out) {
+    KARGS
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = species == 0 ? nA_live(D) : nB_live(D);
+    if (i < n) out[i] = (flag[species == 0 ? i : cK.NAt + i] >> bit) & 1;
+}
+// writes the records of list `bit` (receptors then ligands) at their prefix positions
+__global__ void k_strip_pack(const __grid_constant__ Args A, const unsigned char *flag, int bit, const int *posA, const int *posB, int nRecOut, char *out) {
+    KARGS
+    const Consts &K = cK;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!gid_live(K, D, gid) || !((flag[gid] >> bit) & 1)) return;
+    if (gid < K.NAt) {
+        RecMsg m; m.ref = (int)D.refA[gid];
+        const int l = D.recLig[gid], c = D.recCis[gid];
+        m.ligRef = l >= 0 ? (int)D.refB[l] : 0; m.site = D.recSite[gid]; m.cisRef = c >= 0 ? (int)D.refA[c] : 0;
+        const double2 cc = D.recC[gid], s2 = D.recS2[gid], s3 = D.recS3[gid];
+        m.pose[0] = cc.x; m.pose[1] = cc.y; m.pose[2] = s2.x; m.pose[3] = s2.y; m.pose[4] = s3.x; m.pose[5] = s3.y;
+        reinterpret_cast<RecMsg *>(out)[posA[gid]] = m;
+    } else {
+        const int h = gid - K.NAt;
+        LigMsg *o = reinterpret_cast<LigMsg *>(out + (size_t)nRecOut * sizeof(RecMsg)) + posB[h];
+        o->ref = (int)D.refB[h];
+        for (int k = 0; k < 3; k++) { const int r = D.ligRec[h * 3 + k]; o->recRef[k] = r >= 0 ? (int)D.refA[r] : 0; }
+        const double *p = D.lig + (size_t)h * 24;
+        for (int q = 0; q < 24; q++) o->pose[q] = p[q];
+    }
+}
+template <class T> __device__ __forceinline__ int d_lower_bound(const T *a, int n, int ref) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid].ref < ref) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// merge of the three id-sorted lists (kept, from low, from high): every record knows its final index
+struct MergeSrc { const RecMsg *r[3]; const LigMsg *l[3]; int nr[3], nl[3]; };
+__global__ void k_strip_merge(const __grid_constant__ Args A, MergeSrc M, int *bondRef) {
+    KARGS
+    const Consts &K = cK;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int totR = M.nr[0] + M.nr[1] + M.nr[2], totL = M.nl[0] + M.nl[1] + M.nl[2];
+    if (i < totR) {
+        int k = 0; while (i >= M.nr[k]) { i -= M.nr[k]; k++; }
+        const RecMsg m = M.r[k][i];
+        int pos = i;
+        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(M.r[o], M.nr[o], m.ref);
+        D.recC[pos] = make_double2(m.pose[0], m.pose[1]); D.recS2[pos] = make_double2(m.pose[2], m.pose[3]); D.recS3[pos] = make_double2(m.pose[4], m.pose[5]);
+        D.refA[pos] = (unsigned)m.ref; D.recSite[pos] = m.site;
+        bondRef[pos * 2] = m.ligRef; bondRef[pos * 2 + 1] = m.cisRef;
+    } else if (i < totR + totL) {
+        i -= totR;
+        int k = 0; while (i >= M.nl[k]) { i -= M.nl[k]; k++; }
+        const LigMsg *src = &M.l[k][i];
+        int pos = i;
+        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(M.l[o], M.nl[o], src->ref);
+        D.refB[pos] = (unsigned)src->ref;
+        double *p = D.lig + (size_t)pos * 24;
+        for (int q = 0; q < 24; q++) p[q] = src->pose[q];
+        for (int q = 0; q < 3; q++) bondRef[2 * K.NAt + pos * 3 + q] = src->recRef[q];
+    }
+}
+__device__ __forceinline__ int d_find_ref(const unsigned *a, int n, int ref) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < (unsigned)ref) lo = mid + 1; else hi = mid; }
+    return (lo < n && a[lo] == (unsigned)ref) ? lo : -1;
+}
+__global__ void k_strip_fix_bonds(const __grid_constant__ Args A, const int *bondRef, int nA, int nB) {
+    KARGS
+    const Consts &K = cK;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nA) {
+        const int lr = bondRef[i * 2], cr = bondRef[i * 2 + 1];
+        const int l = lr ? d_find_ref(D.refB, nB, lr) : -1, c = cr ? d_find_ref(D.refA, nA, cr) : -1;
+        if ((lr && l < 0) || (cr && c < 0)) atomicOr(&D.scal[S_OVERFLOW], 16);        // a unit arrived incomplete
+        D.recLig[i] = l; D.recCis[i] = c; if (l < 0) D.recSite[i] = -1;
+    } else if (i < nA + nB) {
+        const int h = i - nA;
+        for (int q = 0; q < 3; q++) {
+            const int rr = bondRef[2 * K.NAt + h * 3 + q], r = rr ? d_find_ref(D.refA, nA, rr) : -1;
+            if (rr && r < 0) atomicOr(&D.scal[S_OVERFLOW], 16);
+            D.ligRec[h * 3 + q] = r;
+        }
+    }
+}
+
+static int strip_dev_alloc(kmc_handle *h) {
+    StripDev &S = *h->strip_dev;
+    if (S.flag) return KMC_OK;
+    const int NT = h->NT;
+    S.padN = ((std::max(h->NAt, h->NBt) + 1 + SCAN_TILE - 1) / SCAN_TILE) * SCAN_TILE;
+    bool ok = dalloc(h, &S.flag, NT) == cudaSuccess && dalloc(h, &S.tmp, S.padN) == cudaSuccess && dalloc(h, &S.blk, S.padN / SCAN_TILE + 1) == cudaSuccess &&
+              dalloc(h, &S.bondRef, (size_t)2 * h->NAt + (size_t)3 * h->NBt + 8) == cudaSuccess;
+    for (int k = 0; k < 6 && ok; k++) ok = dalloc(h, &S.pos[k], S.padN) == cudaSuccess;
+    const size_t full = (size_t)h->NAt * sizeof(RecMsg) + (size_t)h->NBt * sizeof(LigMsg) + 64, band = full / 3 + 4096;
+    for (int k = 0; k < 3 && ok; k++) { S.msgCap[k] = k == 2 ? full : band; ok = dalloc(h, &S.msg[k], S.msgCap[k]) == cudaSuccess; }
+    for (int k = 0; k < 2 && ok; k++) { S.rcvCap[k] = band; ok = dalloc(h, &S.rcv[k], S.rcvCap[k]) == cudaSuccess; }
+    if (!ok) { h->err = "strip: device buffer allocation failed"; return KMC_ERR_CUDA; }
+    return KMC_OK;
+}
+
+// Device refresh, part 1. Afterwards kmc_strip_message_dev(side) gives the device address and the record counts of each message.
+extern "C" int kmc_strip_begin_refresh_dev(kmc_handle *h) {
+    if (!h || !h->strip_on) { if (h) h->err = "kmc_strip_begin_refresh_dev: configure strips first"; return KMC_ERR_INVALID; }
+    CK(cudaSetDevice(h->P.device));
+    if (!h->strip_dev) h->strip_dev = new StripDev;
+    int rc = strip_dev_alloc(h); if (rc) return rc;
+    StripDev &S = *h->strip_dev;
+    cudaStream_t st = h->stream;
+    const Args A{h->D, h->K};
+    const int NT = h->NT, NAt = h->NAt, NBt = h->NBt, B = 128;
+    // complexes of the CURRENT bond table (the last step's reactions may have changed it)
+    LAUNCH(KID_STEP_BEGIN, (k_strip_prebuild<<<1, 1, 0, st>>>(A)));
+    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
+    CK(cudaMemsetAsync(S.flag, 0, NT, st));
+    k_strip_classify<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, h->strip_lo, h->strip_hi, h->strip_W);
+    const int sb = S.padN / SCAN_TILE;
+    for (int list = 0; list < 3; list++)
+        for (int sp = 0; sp < 2; sp++) {
+            const int bit = list == 2 ? 0 : list + 1;
+            CK(cudaMemsetAsync(S.tmp, 0, sizeof(int) * S.padN, st));
+            k_strip_flag_ints<<<nblk(std::max(sp == 0 ? NAt : NBt, 1), 256), 256, 0, st>>>(A, S.flag, sp, bit, S.tmp);
+            k_scan_reduce<<<sb, 256, 0, st>>>((const int4 *)S.tmp, S.blk);
+            k_scan_sums<<<1, 1024, 0, st>>>(S.blk, sb);
+            k_scan_down<<<sb, 256, 0, st>>>((int4 *)S.tmp, S.blk, (int4 *)S.pos[list * 2 + sp]);
+        }
+    int live[2];
+    CK(cudaMemcpyAsync(live, h->D.scal + S_NA_LIVE, sizeof live, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int list = 0; list < 3; list++)
+        for (int sp = 0; sp < 2; sp++)       // exclusive prefix one past the last live molecule = the total (flags beyond are zero)
+            CK(cudaMemcpyAsync(&S.cnt[list * 2 + sp], S.pos[list * 2 + sp] + live[sp], sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int list = 0; list < 3; list++) {
+        const size_t need = (size_t)S.cnt[list * 2] * sizeof(RecMsg) + (size_t)S.cnt[list * 2 + 1] * sizeof(LigMsg);
+        if (need > S.msgCap[list]) { h->err = "strip: message buffer too small (band holds more than a third of the local capacity)"; return KMC_ERR_CAPACITY; }
+        const int bit = list == 2 ? 0 : list + 1;
+        k_strip_pack<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, bit, S.pos[list * 2], S.pos[list * 2 + 1], S.cnt[list * 2], S.msg[list]);
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return KMC_OK;
+}
+extern "C" int kmc_strip_message_dev(kmc_handle *h, int32_t side, void **dev_ptr, int64_t *n_rec, int64_t *n_lig) {
+    if (!h || !h->strip_dev || side < 0 || side > 2) return KMC_ERR_INVALID;
+    StripDev &S = *h->strip_dev;
+    if (dev_ptr) *dev_ptr = S.msg[side];
+    if (n_rec) *n_rec = S.cnt[side * 2];
+    if (n_lig) *n_lig = S.cnt[side * 2 + 1];
+    return KMC_OK;
+}
+// device buffer the caller fills with the message coming from the lower-x (side 0) / higher-x (side 1) neighbour
+extern "C" int kmc_strip_recv_dev(kmc_handle *h, int32_t side, int64_t n_rec, int64_t n_lig, void **dev_ptr) {
+    if (!h || !h->strip_dev || side < 0 || side > 1 || !dev_ptr) return KMC_ERR_INVALID;
+    StripDev &S = *h->strip_dev;
+    const size_t need = (size_t)n_rec * sizeof(RecMsg) + (size_t)n_lig * sizeof(LigMsg);
+    if (need > S.rcvCap[side]) { h->err = "strip: incoming message larger than the receive buffer"; return KMC_ERR_CAPACITY; }
+    *dev_ptr = S.rcv[side];
+    return KMC_OK;
+}
+// Device refresh, part 2: merge kept + received (counts of the two incoming messages given), translate bonds, new live counts
+extern "C" int kmc_strip_rebuild_dev(kmc_handle *h, int64_t rec_low, int64_t lig_low, int64_t rec_high, int64_t lig_high) {
+    if (!h || !h->strip_dev) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    StripDev &S = *h->strip_dev;
+    cudaStream_t st = h->stream;
+    MergeSrc M;
+    const int nr[3] = {S.cnt[4], (int)rec_low, (int)rec_high}, nl[3] = {S.cnt[5], (int)lig_low, (int)lig_high};
+    const char *base[3] = {S.msg[2], S.rcv[0], S.rcv[1]};
+    for (int k = 0; k < 3; k++) {
+        M.nr[k] = nr[k]; M.nl[k] = nl[k];
+        M.r[k] = reinterpret_cast<const RecMsg *>(base[k]); M.l[k] = reinterpret_cast<const LigMsg *>(base[k] + (size_t)nr[k] * sizeof(RecMsg));
+    }
+    const int nA = nr[0] + nr[1] + nr[2], nB = nl[0] + nl[1] + nl[2];
+    if (nA > h->NAt || nB > h->NBt) {
+        h->err = "strip: local capacity exceeded (" + std::to_string(nA) + "/" + std::to_string(h->NAt) + " receptors, " + std::to_string(nB) + "/" +
+                 std::to_string(h->NBt) + " ligands)"; return KMC_ERR_CAPACITY;
+    }
+    const Args A{h->D, h->K};
+    k_strip_merge<<<nblk(std::max(nA + nB, 1), 128), 128, 0, st>>>(A, M, S.bondRef);
+    k_strip_fix_bonds<<<nblk(std::max(nA + nB, 1), 128), 128, 0, st>>>(A, S.bondRef, nA, nB);
+    int live[2] = {nA, nB}, one = 1;
+    CK(cudaMemcpyAsync(h->D.scal + S_NA_LIVE, live, sizeof live, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    h->stepped = false; h->strip_refreshes++;
+    return kmc_sync(h);
+}

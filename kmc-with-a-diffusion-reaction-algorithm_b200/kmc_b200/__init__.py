@@ -39,7 +39,8 @@ EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
-           "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild"]
+           "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_begin_refresh_dev", "kmc_strip_message_dev",
+           "kmc_strip_recv_dev", "kmc_strip_rebuild_dev"]
 
 
 class KmcError(RuntimeError):
@@ -89,6 +90,10 @@ def lib():
         L.kmc_strip_message.restype = i64
         L.kmc_strip_message.argtypes = [vp, i32, C.POINTER(vp)]
         L.kmc_strip_rebuild.argtypes = [vp, vp, i64, vp, i64]
+        L.kmc_strip_begin_refresh_dev.argtypes = [vp]
+        L.kmc_strip_message_dev.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
+        L.kmc_strip_recv_dev.argtypes = [vp, i32, i64, i64, C.POINTER(vp)]
+        L.kmc_strip_rebuild_dev.argtypes = [vp, i64, i64, i64, i64]
         L.kmc_get_grid.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
@@ -156,9 +161,9 @@ class Kmc:
             raise KmcError("kmc_create failed (%d): %s" % (rc, lib().kmc_last_error(None).decode()))
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().kmc_destroy(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.kmc_destroy(self.h)
+        self.h = None
 
     __del__ = close
 
@@ -269,6 +274,23 @@ class Kmc:
 
     def strip_rebuild(self, from_low, from_high):
         self._ck(lib().kmc_strip_rebuild(self.h, from_low, len(from_low), from_high, len(from_high)))
+
+    def strip_begin_refresh_dev(self):
+        self._ck(lib().kmc_strip_begin_refresh_dev(self.h))
+
+    def strip_message_dev(self, side):
+        """(device pointer, n_rec, n_lig) of message `side` after strip_begin_refresh_dev"""
+        ptr, nr, nl = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._ck(lib().kmc_strip_message_dev(self.h, side, C.byref(ptr), C.byref(nr), C.byref(nl)))
+        return ptr.value, nr.value, nl.value
+
+    def strip_recv_dev(self, side, n_rec, n_lig):
+        ptr = C.c_void_p()
+        self._ck(lib().kmc_strip_recv_dev(self.h, side, n_rec, n_lig, C.byref(ptr)))
+        return ptr.value
+
+    def strip_rebuild_dev(self, rec_low, lig_low, rec_high, lig_high):
+        self._ck(lib().kmc_strip_rebuild_dev(self.h, rec_low, lig_low, rec_high, lig_high))
 
     def grid(self):
         x0, y0, edge, ncx, ncy = C.c_double(), C.c_double(), C.c_double(), C.c_int32(), C.c_int32()

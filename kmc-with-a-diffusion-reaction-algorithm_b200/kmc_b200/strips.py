@@ -22,6 +22,21 @@ def halo_for(refresh_every, complex_extent=400.0):
     return refresh_every * D1 + complex_extent
 
 
+class _DevBuf:
+    """a raw device allocation of the library seen as a torch uint8 tensor (zero copy, __cuda_array_interface__)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+def dev_tensor(torch, ptr, nbytes, device):
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)[:nbytes]
+
+
+def msg_bytes(n_rec, n_lig):
+    return n_rec * 64 + n_lig * 208
+
+
 def parse_message(buf):
     if len(buf) < 16:
         return np.zeros(0, REC_DT), np.zeros(0, LIG_DT)
@@ -85,10 +100,11 @@ class StripRank:
 
 
 class LocalStrips:
-    """K logical ranks in one process (all on one GPU): the in-process stand-in for the NCCL exchange."""
+    """K logical ranks in one process (all on one GPU): the in-process stand-in for the NCCL exchange.
+    device_refresh=True keeps the refresh on the GPU (device-to-device copies instead of NCCL)."""
 
-    def __init__(self, make_params, nranks, refresh_every, halo_width=None):
-        self.n, self.every = nranks, refresh_every
+    def __init__(self, make_params, nranks, refresh_every, halo_width=None, device_refresh=False):
+        self.n, self.every, self.device_refresh = nranks, refresh_every, device_refresh
         self.halo = halo_width if halo_width is not None else halo_for(refresh_every)
         self.ranks = [StripRank(make_params(r), r, nranks, self.halo) for r in range(nranks)]
         self.since = 0
@@ -98,6 +114,8 @@ class LocalStrips:
             r.load_global(*a, **kw)
 
     def refresh(self):
+        if self.device_refresh:
+            return self._refresh_dev()
         for r in self.ranks:
             r.k.strip_begin_refresh()
         low = [r.k.strip_message(0) for r in self.ranks]; high = [r.k.strip_message(1) for r in self.ranks]
@@ -106,6 +124,25 @@ class LocalStrips:
                 r.k.strip_rebuild(b"", b"")
             else:   # what my lower neighbour sent upwards arrives as from_low; what my upper neighbour sent downwards as from_high
                 r.k.strip_rebuild(high[(i - 1) % self.n], low[(i + 1) % self.n])
+        self.since = 0
+
+    def _refresh_dev(self):
+        import torch
+        dev = "cuda:%d" % self.ranks[0].k.p.device
+        for r in self.ranks:
+            r.k.strip_begin_refresh_dev()
+        low = [r.k.strip_message_dev(0) for r in self.ranks]; high = [r.k.strip_message_dev(1) for r in self.ranks]
+        for i, r in enumerate(self.ranks):
+            if self.n == 1:
+                r.k.strip_rebuild_dev(0, 0, 0, 0); continue
+            src = (high[(i - 1) % self.n], low[(i + 1) % self.n])          # (from lower-x neighbour, from higher-x neighbour)
+            for side, (ptr, nr, nl) in enumerate(src):
+                dst = r.k.strip_recv_dev(side, nr, nl)
+                nb = msg_bytes(nr, nl)
+                if nb:
+                    dev_tensor(torch, dst, nb, dev).copy_(dev_tensor(torch, ptr, nb, dev))
+            torch.cuda.synchronize()
+            r.k.strip_rebuild_dev(src[0][1], src[0][2], src[1][1], src[1][2])
         self.since = 0
 
     def step(self, n):
@@ -126,8 +163,9 @@ class LocalStrips:
 class DistStrips:
     """one rank per process; boundary bands travel with torch.distributed send/recv (NCCL over NVLink with backend nccl)"""
 
-    def __init__(self, params, refresh_every, halo_width=None, dist=None, device=None):
+    def __init__(self, params, refresh_every, halo_width=None, dist=None, device=None, device_refresh=None):
         import torch
+        self.device_refresh = (dist.get_backend() == "nccl") if device_refresh is None else device_refresh
         self.torch, self.dist = torch, dist
         self.rank, self.n = dist.get_rank(), dist.get_world_size()
         self.every = refresh_every
@@ -146,7 +184,36 @@ class DistStrips:
         self.bytes_sent += len(to_low) + len(to_high)
         return out
 
+    def _refresh_dev(self):
+        """device messages, NCCL point-to-point GPU to GPU; same pairing rules as ring_exchange"""
+        torch, dist, dev = self.torch, self.dist, self.device
+        k = self.k
+        k.strip_begin_refresh_dev()
+        if self.n == 1:
+            k.strip_rebuild_dev(0, 0, 0, 0); self.since = 0; return
+        lo, hi = (self.rank - 1) % self.n, (self.rank + 1) % self.n
+        (pl, rl_, ll_), (ph, rh_, lh_) = k.strip_message_dev(0), k.strip_message_dev(1)
+
+        def run(ops):
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        counts = torch.tensor([rl_, ll_, rh_, lh_], dtype=torch.int64, device=dev)
+        c_hi = torch.zeros(4, dtype=torch.int64, device=dev); c_lo = torch.zeros(4, dtype=torch.int64, device=dev)
+        run([dist.P2POp(dist.isend, counts, lo), dist.P2POp(dist.isend, counts.clone(), hi), dist.P2POp(dist.irecv, c_hi, hi), dist.P2POp(dist.irecv, c_lo, lo)])
+        c_hi, c_lo = c_hi.tolist(), c_lo.tolist()
+        fl = (c_lo[2], c_lo[3])          # from the lower neighbour: its message towards higher x
+        fh = (c_hi[0], c_hi[1])          # from the higher neighbour: its message towards lower x
+        t_send_lo = dev_tensor(torch, pl, max(msg_bytes(rl_, ll_), 1), dev); t_send_hi = dev_tensor(torch, ph, max(msg_bytes(rh_, lh_), 1), dev)
+        t_recv_hi = dev_tensor(torch, k.strip_recv_dev(1, *fh), max(msg_bytes(*fh), 1), dev); t_recv_lo = dev_tensor(torch, k.strip_recv_dev(0, *fl), max(msg_bytes(*fl), 1), dev)
+        run([dist.P2POp(dist.isend, t_send_lo, lo), dist.P2POp(dist.isend, t_send_hi, hi), dist.P2POp(dist.irecv, t_recv_hi, hi), dist.P2POp(dist.irecv, t_recv_lo, lo)])
+        torch.cuda.synchronize()
+        self.bytes_sent += msg_bytes(rl_, ll_) + msg_bytes(rh_, lh_)
+        k.strip_rebuild_dev(fl[0], fl[1], fh[0], fh[1])
+        self.since = 0
+
     def refresh(self):
+        if self.device_refresh:
+            return self._refresh_dev()
         self.k.strip_begin_refresh()
         if self.n == 1:
             self.k.strip_rebuild(b"", b"")

@@ -19,12 +19,12 @@ def single_run(box, na, nb, regime, seed, steps):
     return start, k.get_packed(), k.series()
 
 
-@pytest.mark.parametrize("nranks,every", [(2, 3), (4, 2), (3, 5)])
-def test_strips_equal_single_gpu(nranks, every):
+@pytest.mark.parametrize("nranks,every,dev", [(2, 3, False), (4, 2, False), (3, 5, False), (2, 3, True), (4, 2, True), (3, 5, True)])
+def test_strips_equal_single_gpu(nranks, every, dev):
     na, nb, box, regime, seed, steps = 15000, 5000, (26000.0, 26000.0, 400.0), "hot", 5, 60
     start, end, series = single_run(box, na, nb, regime, seed, steps)
     cap = lambda r: apply_regime(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=seed), regime)   # capacity = whole system
-    ls = LocalStrips(cap, nranks, every, halo_width=halo_for(every))
+    ls = LocalStrips(cap, nranks, every, halo_width=halo_for(every), device_refresh=dev)
     ls.load_global(*start)
     ls.step(steps)
     rec, lig, rl, rs, rc = ls.gather(na, nb)
@@ -36,7 +36,8 @@ def test_strips_equal_single_gpu(nranks, every):
     assert sum(owned) == na and max(owned) < 0.8 * na
 
 
-def test_strips_with_complexes_across_boundaries():
+@pytest.mark.parametrize("dev", [False, True])
+def test_strips_with_complexes_across_boundaries(dev):
     """start from a state that already has complexes everywhere (evolved on one GPU), then continue on 4 strips"""
     na, nb, box, regime, seed = 6000, 2000, (12000.0, 12000.0, 400.0), "hot", 9
     k = kmc_b200.Kmc(apply_regime(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=seed), regime))
@@ -46,7 +47,7 @@ def test_strips_with_complexes_across_boundaries():
     assert k.series()["bond_num"] > 80
     k.step(40)
     end = k.get_packed()
-    ls = LocalStrips(lambda r: apply_regime(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=seed), regime), 4, 2, halo_width=1000.0)
+    ls = LocalStrips(lambda r: apply_regime(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=seed), regime), 4, 2, halo_width=1000.0, device_refresh=dev)
     ls.load_global(*mid, step_done=1500)
     ls.step(40)
     rec, lig, rl, rs, rc = ls.gather(na, nb)
