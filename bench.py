@@ -36,7 +36,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 B_ALG_STEP = 232.0      # whole step, fp64 pose read+written once (2*96) + bond words 24 + label 8 + cell key/index 8
 B_ALG_KERNEL = {
     "k_propose_simple": 96 + 96 + 4 + 4 + 2,          # old pose in, proposed pose out, unitOf, cis/size word, state+far flags
-    "k_resolve": 36 + 4 + 1 + 24 + 8,                 # proposed centre+beads (rec 16 B, lig 96 B), unitOf, state, 3 cell-row bounds, own entries
+    "k_resolve_tiles": 81,                            # per entry: id 4, unit 4, far 1, centres old+new 32, bond words 8-12 (+72 B beads for a ligand probe)
+                                                      # = 49 B receptor / 121 B ligand -> 67 B in the 3:1 mix, + cellStart window 2.56 cells x 1.34 x 4 B
     "k_react_pairs": 0.1 * (48 + 96 + 16),              # pre-selected pairs only (~0.1 per molecule): both poses + bond words
     "k_grid_count": 18 + 1 + 4 + 4,
     "k_grid_scatter": 18 + 4 + 4 + 4,
@@ -132,6 +133,10 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cell-edge", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomp", default="auto", choices=["auto", "strips", "patches"],
+                    help="N>1: 'strips' = ONE membrane of N*M molecules cut into N strips along x, halos refreshed over NCCL; "
+                         "'patches' = N independent membranes of M molecules (no communication); auto = strips, patches if that fails")
+    ap.add_argument("--refresh-every", type=int, default=32, help="strips: MC steps between halo refreshes")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -150,11 +155,46 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     M = args.molecules
     na, nb = (3 * M) // 4, M - (3 * M) // 4
-    p = kmc_b200.default_params(box=kmc_b200.scaled_box(M), n_receptor=na, n_ligand=nb, seed=args.seed + 1000 * rank,
-                                mode=kmc_b200.MODE_REPLAY, device=local, cell_edge=args.cell_edge)
-    k = kmc_b200.Kmc(p)
-    k.init_random(seed=args.seed + 7919 * rank, sort_cells=True)
     S = args.mc_steps
+    decomp = "patches" if world == 1 else args.decomp
+    strips_note, ds = None, None
+    if decomp in ("auto", "strips"):
+        try:
+            from kmc_b200.strips import DistStrips, halo_for
+            every = args.refresh_every
+            S = ((S + every - 1) // every) * every                      # whole refresh intervals per bench step
+            G = M * world
+            gna, gnb = (3 * G) // 4, G - (3 * G) // 4
+            gbox = kmc_b200.scaled_box(G)
+            pg = kmc_b200.default_params(box=gbox, n_receptor=gna, n_ligand=gnb, seed=args.seed)
+            grec, glig = kmc_b200.generate_packed(pg, seed=args.seed, sort_cells=True)      # every rank: the same global start state
+            halo = halo_for(every)
+            frac = (gbox[0] / world + 2 * halo) / (gbox[0] / world)
+            p = kmc_b200.default_params(box=gbox, n_receptor=int(gna / world * frac * 1.08) + 2000, n_ligand=int(gnb / world * frac * 1.08) + 2000,
+                                        seed=args.seed, mode=kmc_b200.MODE_REPLAY, device=local, cell_edge=args.cell_edge)
+            ds = DistStrips(p, every, halo_width=halo, dist=dist)
+            ds.load_global(grec, glig)
+            k = ds.k
+            decomp = "strips"
+            strips_note = "ONE %d-molecule membrane (L=%.0f A) cut into %d strips along x; halo %.0f A refreshed every %d steps, boundary bands over NCCL send/recv" % (
+                G, gbox[0], world, halo, every)
+        except Exception as ex:            # keep the run alive: fall back to independent patches and say why
+            if args.decomp == "strips":
+                raise
+            strips_note = "strips failed (%s): fell back to independent patches" % str(ex)[:200]
+            decomp, ds = "patches", None
+        # all ranks must take the same path (a rank falling back alone would leave the others waiting in NCCL)
+        okt = torch.tensor([1 if ds is not None else 0], dtype=torch.int64, device="cuda:%d" % local)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0 and ds is not None:
+            ds.k.close(); ds = None; decomp = "patches"
+            strips_note = "strips failed on another rank: fell back to independent patches"
+    if decomp == "patches":
+        p = kmc_b200.default_params(box=kmc_b200.scaled_box(M), n_receptor=na, n_ligand=nb, seed=args.seed + 1000 * rank,
+                                    mode=kmc_b200.MODE_REPLAY, device=local, cell_edge=args.cell_edge)
+        k = kmc_b200.Kmc(p)
+        k.init_random(seed=args.seed + 7919 * rank, sort_cells=True)
+    stepper = ds if ds is not None else k
 
     def barrier():
         if dist is not None:
@@ -162,17 +202,25 @@ def main():
         k.sync()
 
     for _ in range(args.warmup):
-        k.step(S)
-    # ---- timed region: EXACTLY K steps, device time on the library's stream, barrier + sync on both sides ----
+        stepper.step(S)
+    # ---- timed region: EXACTLY K steps, barrier + sync on both sides. Patches: device time from CUDA events on the library's
+    # stream. Strips: host wall clock between the barriers (the halo refresh is host-orchestrated: NCCL + rebuild kernels) ----
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     ev0 = k.events()
     barrier()
     ms = 0.0
+    t_wall = time.perf_counter()
     for _ in range(args.steps):
-        ms += k.step_timed(S)
+        if ds is None:
+            ms += k.step_timed(S)
+        else:
+            ds.step(S)
     barrier()
+    t_wall = time.perf_counter() - t_wall
+    if ds is not None:
+        ms = t_wall * 1e3
     ev1 = k.events()
     if sampler:
         sampler.stop_flag = True
@@ -186,7 +234,7 @@ def main():
     # ---- per-kernel CUDA-event timing (separate, untimed pass: events around every launch) ----
     k.profile(True)
     for _ in range(3):
-        k.step(S)
+        stepper.step(S)
     k.sync()
     prof = k.profile_get()
     k.profile(False)
@@ -198,20 +246,34 @@ def main():
     achieved = balg * M / (top_ms / top_n * 1e-3) / 1e9 if balg else None
 
     # ---- e2e through the C ABI with host buffers ----
-    rec, lig, rl, rs, rc = k.get_packed()
-    pin = [torch.from_numpy(a).pin_memory().numpy() for a in (rec, lig, rl, rs, rc)]
-    h2d = sum(a.nbytes for a in pin); d2h = h2d + 64
     e2e_t = []
-    for it in range(2 + max(3, args.steps // 2)):
-        barrier()
-        t0 = time.perf_counter()
-        k.set_packed(*pin, step_done=1000 + it * S)
-        k.step(S)
-        k.get_packed()
-        k.series()
-        dt = time.perf_counter() - t0
-        if it >= 2:
-            e2e_t.append(dt)
+    if ds is None:
+        rec, lig, rl, rs, rc = k.get_packed()
+        pin = [torch.from_numpy(a).pin_memory().numpy() for a in (rec, lig, rl, rs, rc)]
+        h2d = sum(a.nbytes for a in pin); d2h = h2d + 64
+        for it in range(2 + max(3, args.steps // 2)):
+            barrier()
+            t0 = time.perf_counter()
+            k.set_packed(*pin, step_done=1000 + it * S)
+            k.step(S)
+            k.get_packed()
+            k.series()
+            dt = time.perf_counter() - t0
+            if it >= 2:
+                e2e_t.append(dt)
+    else:       # strips: host arrays of the global state in, each rank's owned molecules out
+        h2d = d2h = 0
+        for it in range(2 + max(3, args.steps // 2)):
+            barrier()
+            t0 = time.perf_counter()
+            ds.load_global(grec, glig, step_done=1000 + it * S)
+            ds.step(S)
+            k.strip_begin_refresh()
+            owned = k.strip_message(2)
+            dt = time.perf_counter() - t0
+            h2d = d2h = len(owned)
+            if it >= 2:
+                e2e_t.append(dt)
     te = torch.tensor([sum(e2e_t) / len(e2e_t)], dtype=torch.float64, device="cuda:%d" % local)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -235,7 +297,8 @@ def main():
                                        "fresh random start); %s" % (M, na, nb, p.box[0],
                                                                   "per-GPU share of the 1e7-molecule membrane (configs[4])" if M == 1250000 else "custom size"),
                            "mc_steps_per_step": S, "mode": "replay (index-order sweep, keyed Philox)", "l2": "working set > L2 (no flush needed)",
-                           "decomposition": "independent patches per GPU, no data-path collective (strip halo exchange is a later row)",
+                           "decomposition": strips_note if decomp == "strips" else ("independent patches per GPU, no data-path collective" + ("; " + strips_note if strips_note else "")),
+                           "timing": "host wall clock between barriers (halo refresh is host-orchestrated)" if decomp == "strips" else "CUDA events on the library stream",
                            "ms_per_mc_step": ms_max / args.steps / S},
                 "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": achieved / peak if achieved else None, "traffic": None,

@@ -93,6 +93,8 @@ const char *kmc_last_error(const kmc_handle *h);     /* h may be NULL: error of 
  * orientation distributions; O(N) with a cell grid). Replica r is seeded with init_seed + r.
  * sort_cells != 0 numbers the molecules in cell-major order (memory locality for large membranes). */
 int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_cells);
+/* the same generator as pure host code (no handle, no device): rec_pose[n_replicas*n_receptor][6], lig_pose[n_replicas*n_ligand][24] */
+int kmc_generate_packed(const kmc_params *p, uint64_t init_seed, int32_t sort_cells, double *rec_pose, double *lig_pose);
 
 /* State in the reference's array shapes (main.cpp:102-118), one replica at a time:
  *   R_x, R_y, R_z  double[N+1][5][5]   (1-based; receptor uses [1..4][1..4], ligand [1..4][1..2])

@@ -19,10 +19,9 @@ static thread_local std::string g_create_error;
 
 // ---- strip decomposition bookkeeping (csrc/kmc_strips.cu) ----
 struct StripDev;
-#pragma pack(push, 1)
 struct RecMsg { int32_t ref, ligRef, site, cisRef; double pose[6]; };      // 64 bytes; refs are reference ids (1-based), 0 = none
 struct LigMsg { int32_t ref, recRef[3]; double pose[24]; };               // 208 bytes
-#pragma pack(pop)
+static_assert(sizeof(RecMsg) == 64 && sizeof(LigMsg) == 208, "message records have no padding");
 
 struct HostLocal {       // host mirror of the live local state
     std::vector<double> rec, lig; std::vector<int> rl, rs, rc, lr; std::vector<unsigned> refA, refB;
@@ -759,14 +758,12 @@ struct HostGrid {
 };
 }  // namespace
 
-extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_cells) {
-    if (!h) return KMC_ERR_INVALID;
-    const kmc_params &P = h->P;
-    const int NA = h->NA, NB = h->NB;
+// pure host code (no device): fills rec[R*NA][6], lig[R*NB][24]; returns an error text or nullptr
+static const char *generate_random(const kmc_params &P, const Consts &K, uint64_t init_seed, int32_t sort_cells, double *recOut, double *ligOut) {
+    const int NA = P.n_receptor, NB = P.n_ligand, R = P.n_replicas;
     const double rs = P.rB * 2 / sqrt(3.0);
     const double exRR = P.rA + P.rA, exRL = P.rA + rs + P.rB, exLL = rs + rs + 2 * P.rB;      // main.cpp:293, 368, 380
-    std::vector<double> rec((size_t)h->NAt * 6), lig((size_t)h->NBt * 24);
-    for (int rep = 0; rep < h->R; rep++) {
+    for (int rep = 0; rep < R; rep++) {
         const uint64_t seed = init_seed + (uint64_t)rep;
         uint32_t ctr = 0;
         auto U = [&](uint32_t mol) { return keyed_uniform(seed, mol, ctr++, 0, SLOT_INIT); };
@@ -774,7 +771,7 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
         HostGrid ga(P.box[0], P.box[1], exRR, NA), gb(P.box[0], P.box[1], exLL, NB), gab(P.box[0], P.box[1], exRL, NA);
         for (int a = 0; a < NA; a++) {
             for (int tries = 0;; tries++) {
-                if (tries > 100000) { h->err = "kmc_init_random: cannot place receptors (box too dense)"; return KMC_ERR_INVALID; }
+                if (tries > 100000) return "kmc_init_random: cannot place receptors (box too dense)";
                 double x = U(a + 1) * P.box[0] - P.box[0] / 2, y = U(a + 1) * P.box[1] - P.box[1] / 2;
                 bool clash = ga.any_near(x, y, [&](int j) { double dx = x - ax[j], dy = y - ay[j]; return sqrt(dx * dx + dy * dy) <= exRR; });
                 if (!clash) { ax[a] = x; ay[a] = y; ga.put(x, y, a); gab.put(x, y, a); break; }
@@ -782,7 +779,7 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
         }
         for (int b = 0; b < NB; b++) {
             for (int tries = 0;; tries++) {
-                if (tries > 100000) { h->err = "kmc_init_random: cannot place ligands (box too dense)"; return KMC_ERR_INVALID; }
+                if (tries > 100000) return "kmc_init_random: cannot place ligands (box too dense)";
                 double x = U(NA + b + 1) * P.box[0] - P.box[0] / 2, y = U(NA + b + 1) * P.box[1] - P.box[1] / 2, z = U(NA + b + 1) * P.box[2];
                 bool clash = gab.any_near(x, y, [&](int j) {
                     for (int k = 0; k < 4; k++) { double dx = x - ax[j], dy = y - ay[j], dz = z - 2 * k * P.rA; if (sqrt(dx * dx + dy * dy + dz * dz) <= exRL) return true; }
@@ -796,7 +793,6 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
         for (int i = 0; i < NA; i++) oa[i] = i;
         for (int i = 0; i < NB; i++) ob[i] = i;
         if (sort_cells) {
-            const Consts &K = h->K;
             auto key = [&](double x, double y) {
                 long cx = (long)floor((x - K.gx0) * K.cellInv), cy = (long)floor((y - K.gy0) * K.cellInv);
                 return cy * (long)K.ncx + cx; };
@@ -806,7 +802,7 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
         for (int a = 0; a < NA; a++) {
             const int src = oa[a];
             const double psai = (2 * U(a + 1) - 1) * P.pai, x = ax[src], y = ay[src];
-            double *o = rec.data() + ((size_t)rep * NA + a) * 6;
+            double *o = recOut + ((size_t)rep * NA + a) * 6;
             o[0] = x; o[1] = y;
             o[2] = cos(psai) * P.rA + x; o[3] = sin(psai) * P.rA + y;
             o[4] = cos(psai) * (-P.rA) + x; o[5] = sin(psai) * (-P.rA) + y;
@@ -821,17 +817,31 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
             const double tpl[8][3] = {{0, 0, 0}, {0, rB * 2 / sqrt(3), 0}, {-rB, -rB / sqrt(3), 0}, {rB, -rB / sqrt(3), 0}, {0, 0, rB},
                                       {0, rB * (2 / sqrt(3) + 1), 0}, {-rB * (sqrt(3) / 2 + 1), -rB / sqrt(3) - rB / 2, 0},
                                       {rB * (sqrt(3) / 2 + 1), -rB / sqrt(3) - rB / 2, 0}};
-            double *o = lig.data() + ((size_t)rep * NB + b) * 24;
+            double *o = ligOut + ((size_t)rep * NB + b) * 24;
             const double c[3] = {bx[src], by[src], bz[src]};
             for (int q = 0; q < 8; q++)
                 for (int d = 0; d < 3; d++) o[q * 3 + d] = t[d][0] * tpl[q][0] + t[d][1] * tpl[q][1] + t[d][2] * tpl[q][2] + c[d];
         }
     }
+    return nullptr;
+}
+
+extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_cells) {
+    if (!h) return KMC_ERR_INVALID;
+    std::vector<double> rec((size_t)h->NAt * 6), lig((size_t)h->NBt * 24);
+    if (const char *msg = generate_random(h->P, h->K, init_seed, sort_cells, rec.data(), lig.data())) { h->err = msg; return KMC_ERR_INVALID; }
     int rc = kmc_set_packed(h, rec.data(), lig.data(), nullptr, nullptr, nullptr, 0);
     if (rc) return rc;
     std::vector<int> zero(h->R, 0);
     CK(cudaMemcpy(h->D.maxComplex, zero.data(), sizeof(int) * h->R, cudaMemcpyHostToDevice));
     return KMC_OK;
+}
+
+// the same generator without a handle or a device: host arrays out (strips: every rank generates the global start state)
+extern "C" int kmc_generate_packed(const kmc_params *p, uint64_t init_seed, int32_t sort_cells, double *rec_pose, double *lig_pose) {
+    if (!p || !rec_pose || !lig_pose || p->n_replicas < 1) return KMC_ERR_INVALID;
+    Consts K; fill_consts(*p, K);
+    return generate_random(*p, K, init_seed, sort_cells, rec_pose, lig_pose) ? KMC_ERR_INVALID : KMC_OK;
 }
 
 #include "kmc_strips.cu"

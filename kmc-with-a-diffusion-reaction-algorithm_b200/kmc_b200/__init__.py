@@ -40,7 +40,7 @@ EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_begin_refresh_dev", "kmc_strip_message_dev",
-           "kmc_strip_recv_dev", "kmc_strip_rebuild_dev"]
+           "kmc_strip_recv_dev", "kmc_strip_rebuild_dev", "kmc_generate_packed"]
 
 
 class KmcError(RuntimeError):
@@ -94,6 +94,7 @@ def lib():
         L.kmc_strip_message_dev.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
         L.kmc_strip_recv_dev.argtypes = [vp, i32, i64, i64, C.POINTER(vp)]
         L.kmc_strip_rebuild_dev.argtypes = [vp, i64, i64, i64, i64]
+        L.kmc_generate_packed.argtypes = [C.POINTER(Params), u64, i32, vp, vp]
         L.kmc_get_grid.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_cluster_log.argtypes = [vp, i32, C.c_char_p]
@@ -117,6 +118,16 @@ def default_params(**kw):
         else:
             setattr(p, k, v)
     return p
+
+
+def generate_packed(params, seed=1, sort_cells=True):
+    """random non-overlapping start state (the generator of kmc_init_random) as host arrays; needs no GPU"""
+    r = params.n_replicas
+    rec = np.zeros((r * params.n_receptor, 6)); lig = np.zeros((r * params.n_ligand, 24))
+    rc = lib().kmc_generate_packed(C.byref(params), seed, int(sort_cells), rec.ctypes.data, lig.ctypes.data)
+    if rc != 0:
+        raise KmcError("kmc_generate_packed failed (%d): box too dense?" % rc)
+    return rec, lig
 
 
 def scaled_box(n_total, z=1000.0):
