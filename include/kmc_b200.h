@@ -149,6 +149,19 @@ int64_t kmc_format_cluster_log(double dt, int64_t step, int32_t n_ligand, const 
 /* Byte-compatible writers for the reference's output files (append one record, main.cpp:2247-2253, 2291-2305) */
 int kmc_write_bond_dat(kmc_handle *h, int32_t replica, const char *path);
 int kmc_write_cluster_log(kmc_handle *h, int32_t replica, const char *path);
+/* The reference's other text files. Array-level functions are pure host code on reference-shaped arrays (no device):
+ * test.gro frame (main.cpp:2258-2287), position.cpt writer/reader (main.cpp:2206-2244 / 226-268; counters[6] = bond_num,
+ * bond_num_rl, bond_num_cis, bond_num_mono_cis, protein_num_in_Max_Complex, mc_time_step), parameter.log (main.cpp:179-205). */
+int kmc_gro_append_arrays(const char *path, int32_t NA, int32_t NB, const double *R_x, const double *R_y, const double *R_z,
+                          double dt, int64_t step, const double *box);
+int kmc_checkpoint_write_arrays(const char *path, int32_t NA, int32_t NB, const double *R_x, const double *R_y, const double *R_z,
+                                const int32_t *protein_status, const int32_t *res_nei, const int64_t *counters);
+int kmc_checkpoint_read_arrays(const char *path, int32_t NA, int32_t NB, double *R_x, double *R_y, double *R_z,
+                               int32_t *protein_status, int32_t *res_nei, int64_t *counters);
+int kmc_parameter_log_write(const kmc_params *p, const char *path);
+int kmc_write_gro(kmc_handle *h, int32_t replica, const char *path);
+int kmc_write_checkpoint(kmc_handle *h, int32_t replica, const char *path);
+int kmc_read_checkpoint(kmc_handle *h, int32_t replica, const char *path);      /* restart: main.cpp:226-268 */
 /* the reference's own main loop: n_steps steps with records every output_every steps into directory `dir` */
 int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, const char *dir);
 

@@ -727,6 +727,8 @@ extern "C" int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, con
                 std::string suf = h->R > 1 ? "." + std::to_string(r) : "";
                 rc = kmc_write_bond_dat(h, r, (d + "/bond.dat" + suf).c_str()); if (rc) return rc;
                 rc = kmc_write_cluster_log(h, r, (d + "/cluster.log" + suf).c_str()); if (rc) return rc;
+                rc = kmc_write_gro(h, r, (d + "/test.gro" + suf).c_str()); if (rc) return rc;                 // main.cpp:2258
+                rc = kmc_write_checkpoint(h, r, (d + "/position.cpt" + suf).c_str()); if (rc) return rc;      // main.cpp:2206
             }
     }
     return KMC_OK;
@@ -835,6 +837,119 @@ extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_c
     std::vector<int> zero(h->R, 0);
     CK(cudaMemcpy(h->D.maxComplex, zero.data(), sizeof(int) * h->R, cudaMemcpyHostToDevice));
     return KMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the reference's remaining text files: pure host formatting on reference-shaped arrays
+// ------------------------------------------------------------------------------------------------
+// test.gro frame, main.cpp:2258-2287 (fixed, precision 3; coordinates in nm)
+extern "C" int kmc_gro_append_arrays(const char *path, int32_t NA, int32_t NB, const double *Rx, const double *Ry, const double *Rz,
+                                     double dt, int64_t step, const double *box) {
+    if (!path || !Rx || !Ry || !Rz || !box) return KMC_ERR_INVALID;
+    FILE *f = fopen(path, "a");
+    if (!f) return KMC_ERR_IO;
+    fprintf(f, "Hello Gro!, t=%.3f\n%d\n", (double)step * dt, NA * 4 + NB * 3);
+    for (int i = 1; i <= NA; i++)
+        for (int j = 1; j <= 4; j++)
+            fprintf(f, "%5dALA%7s%5d%8.3f%8.3f%8.3f\n", i, "CA", i, Rx[RI(i, j, 1)] / 10, Ry[RI(i, j, 1)] / 10, Rz[RI(i, j, 1)] / 10);
+    for (int i = NA + 1; i <= NA + NB; i++)
+        for (int j = 2; j <= 4; j++)
+            fprintf(f, "%5dLEU%7s%5d%8.3f%8.3f%8.3f\n", i, "CA", i, Rx[RI(i, j, 1)] / 10, Ry[RI(i, j, 1)] / 10, Rz[RI(i, j, 1)] / 10);
+    fprintf(f, "%8.3f%12.3f%12.3f\n", box[0] / 10, box[1] / 10, box[2] / 10);
+    fclose(f);
+    return KMC_OK;
+}
+// position.cpt, main.cpp:2206-2244 (truncates; fixed, precision 3: a restart from it is lossy by design)
+// counters[6] = bond_num, bond_num_rl, bond_num_cis, bond_num_mono_cis, protein_num_in_Max_Complex, mc_time_step
+extern "C" int kmc_checkpoint_write_arrays(const char *path, int32_t NA, int32_t NB, const double *Rx, const double *Ry, const double *Rz,
+                                           const int32_t *status, const int32_t *res_nei, const int64_t *counters) {
+    if (!path || !Rx || !Ry || !Rz || !status || !res_nei || !counters) return KMC_ERR_INVALID;
+    FILE *f = fopen(path, "w");
+    if (!f) return KMC_ERR_IO;
+    for (int i = 1; i <= NA; i++) {
+        for (int j = 1; j <= 4; j++)
+            for (int k = 1; k <= 4; k++) fprintf(f, "%10.3f%10.3f%10.3f\n", Rx[RI(i, j, k)], Ry[RI(i, j, k)], Rz[RI(i, j, k)]);
+        fprintf(f, "%8d%8d%8d%8d%8d\n", status[i * 5 + 2], status[i * 5 + 3], res_nei[i * 7 + 2], res_nei[i * 7 + 4], res_nei[i * 7 + 3]);
+    }
+    for (int i = NA + 1; i <= NA + NB; i++)
+        for (int j = 1; j <= 4; j++) {
+            for (int k = 1; k <= 2; k++) fprintf(f, "%10.3f%10.3f%10.3f\n", Rx[RI(i, j, k)], Ry[RI(i, j, k)], Rz[RI(i, j, k)]);
+            fprintf(f, "%8d%8d\n", status[i * 5 + j], res_nei[i * 7 + j]);
+        }
+    for (int q = 0; q < 6; q++) fprintf(f, "%lld\n", (long long)counters[q]);
+    fclose(f);
+    return KMC_OK;
+}
+// reader of the same token stream, main.cpp:231-266 (any precision is parsed exactly)
+extern "C" int kmc_checkpoint_read_arrays(const char *path, int32_t NA, int32_t NB, double *Rx, double *Ry, double *Rz, int32_t *status,
+                                          int32_t *res_nei, int64_t *counters) {
+    if (!path || !Rx || !Ry || !Rz || !status || !res_nei || !counters) return KMC_ERR_INVALID;
+    FILE *f = fopen(path, "r");
+    if (!f) return KMC_ERR_IO;
+    const int N = NA + NB;
+    memset(Rx, 0, sizeof(double) * 25 * (N + 1)); memset(Ry, 0, sizeof(double) * 25 * (N + 1)); memset(Rz, 0, sizeof(double) * 25 * (N + 1));
+    memset(status, 0, sizeof(int32_t) * 5 * (N + 1)); memset(res_nei, 0, sizeof(int32_t) * 7 * (N + 1));
+    bool ok = true;
+    auto D = [&](double &v) { char tok[128]; if (fscanf(f, "%127s", tok) != 1) { ok = false; v = 0; return; } v = strtod(tok, nullptr); };
+    auto I = [&](int32_t &v) { long long t = 0; if (fscanf(f, "%lld", &t) != 1) ok = false; v = (int32_t)t; };
+    for (int i = 1; i <= NA; i++) {
+        for (int j = 1; j <= 4; j++)
+            for (int k = 1; k <= 4; k++) { D(Rx[RI(i, j, k)]); D(Ry[RI(i, j, k)]); D(Rz[RI(i, j, k)]); }
+        I(status[i * 5 + 2]); I(status[i * 5 + 3]); I(res_nei[i * 7 + 2]); I(res_nei[i * 7 + 4]); I(res_nei[i * 7 + 3]);
+    }
+    for (int i = NA + 1; i <= N; i++)
+        for (int j = 1; j <= 4; j++) {
+            for (int k = 1; k <= 2; k++) { D(Rx[RI(i, j, k)]); D(Ry[RI(i, j, k)]); D(Rz[RI(i, j, k)]); }
+            I(status[i * 5 + j]); I(res_nei[i * 7 + j]);
+        }
+    for (int q = 0; q < 6; q++) { long long t = 0; if (fscanf(f, "%lld", &t) != 1) ok = false; counters[q] = t; }
+    fclose(f);
+    return ok ? KMC_OK : KMC_ERR_IO;
+}
+// parameter.log, main.cpp:179-205 (default ostream float format = %g, widths 25/15)
+extern "C" int kmc_parameter_log_write(const kmc_params *p, const char *path) {
+    if (!p || !path) return KMC_ERR_INVALID;
+    FILE *f = fopen(path, "w");
+    if (!f) return KMC_ERR_IO;
+    fprintf(f, "%25s%15g%7g%7g\n\n", "box size: x y z", p->box[0], p->box[1], p->box[2]);
+    fprintf(f, "%25s%15d\n%25s%15d\n%25s%15d\n%25s%15d\n\n", "protein_A_tot_num", p->n_receptor, "RB_A_tot_num", p->n_receptor * 4,
+            "protein_B_tot_num", p->n_ligand, "RB_B_tot_num", p->n_ligand * 4);
+    fprintf(f, "%25s%15g\n%25s%15g\n%25s%15g\n%25s%15g\n\n", "RB_A_D", p->DA, "RB_A_rot_D", p->DrotA, "RB_B_D", p->DB, "RB_B_rot_D", p->DrotB);
+    fprintf(f, "%25s\n%25s%15g\n%25s%15g\n%25s%15g\n%25s%15g\n\n", "R-L interaction:", "bond_D", p->bond_D, "bond_rot_D", p->bond_Drot, "Ass_Rate", p->on,
+            "Diss_Rate", p->off);
+    fprintf(f, "%25s\n%25s%15g\n%25s%15g\n%25s%15g\n%25s%15g\n\n%25s%15g\n%25s%15g\n\n", "Cis interaction:", "cis_D", p->cis_D, "cis_rot_D", p->cis_Drot,
+            "mono_cis_Ass_Rate", p->mono_cis_on, "mono_cis_Diss_Rate", p->mono_cis_off, "cis_Ass_Rate", p->cis_on, "cis_Diss_Rate", p->cis_off);
+    fclose(f);
+    return KMC_OK;
+}
+// handle-level conveniences: state of one replica -> the reference's files, and restart from a position.cpt
+extern "C" int kmc_write_gro(kmc_handle *h, int32_t rep, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    const size_t n = (size_t)(h->N + 1);
+    std::vector<double> X(n * 25), Y(n * 25), Z(n * 25); std::vector<int32_t> st(n * 5), rn(n * 7);
+    int rc = kmc_get_state(h, rep, X.data(), Y.data(), Z.data(), st.data(), rn.data()); if (rc) return rc;
+    rc = kmc_gro_append_arrays(path, h->NA, h->NB, X.data(), Y.data(), Z.data(), h->P.dt, h->step_done, h->P.box);
+    if (rc) h->err = std::string("cannot write ") + path;
+    return rc;
+}
+extern "C" int kmc_write_checkpoint(kmc_handle *h, int32_t rep, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    const size_t n = (size_t)(h->N + 1);
+    std::vector<double> X(n * 25), Y(n * 25), Z(n * 25); std::vector<int32_t> st(n * 5), rn(n * 7);
+    int rc = kmc_get_state(h, rep, X.data(), Y.data(), Z.data(), st.data(), rn.data()); if (rc) return rc;
+    kmc_series s; rc = kmc_get_series(h, rep, &s); if (rc) return rc;
+    const int64_t c[6] = {s.bond_num, s.bond_num_rl, s.bond_num_cis, s.bond_num_mono_cis, s.max_complex, s.step};
+    rc = kmc_checkpoint_write_arrays(path, h->NA, h->NB, X.data(), Y.data(), Z.data(), st.data(), rn.data(), c);
+    if (rc) h->err = std::string("cannot write ") + path;
+    return rc;
+}
+extern "C" int kmc_read_checkpoint(kmc_handle *h, int32_t rep, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    const size_t n = (size_t)(h->N + 1);
+    std::vector<double> X(n * 25), Y(n * 25), Z(n * 25); std::vector<int32_t> st(n * 5), rn(n * 7); int64_t c[6];
+    int rc = kmc_checkpoint_read_arrays(path, h->NA, h->NB, X.data(), Y.data(), Z.data(), st.data(), rn.data(), c);
+    if (rc) { h->err = std::string("cannot read ") + path; return rc; }
+    return kmc_set_state(h, rep, X.data(), Y.data(), Z.data(), st.data(), rn.data(), c[5], (int32_t)c[4]);    // main.cpp:261-267
 }
 
 // the same generator without a handle or a device: host arrays out (strips: every rank generates the global start state)

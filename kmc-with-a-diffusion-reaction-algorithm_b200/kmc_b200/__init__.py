@@ -40,7 +40,8 @@ EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy",
            "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_begin_refresh_dev", "kmc_strip_message_dev",
-           "kmc_strip_recv_dev", "kmc_strip_rebuild_dev", "kmc_generate_packed"]
+           "kmc_strip_recv_dev", "kmc_strip_rebuild_dev", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
+           "kmc_checkpoint_read_arrays", "kmc_parameter_log_write", "kmc_write_gro", "kmc_write_checkpoint", "kmc_read_checkpoint"]
 
 
 class KmcError(RuntimeError):
@@ -94,6 +95,13 @@ def lib():
         L.kmc_strip_message_dev.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
         L.kmc_strip_recv_dev.argtypes = [vp, i32, i64, i64, C.POINTER(vp)]
         L.kmc_strip_rebuild_dev.argtypes = [vp, i64, i64, i64, i64]
+        L.kmc_gro_append_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, C.c_double, i64, vp]
+        L.kmc_checkpoint_write_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.kmc_checkpoint_read_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.kmc_parameter_log_write.argtypes = [C.POINTER(Params), C.c_char_p]
+        L.kmc_write_gro.argtypes = [vp, i32, C.c_char_p]
+        L.kmc_write_checkpoint.argtypes = [vp, i32, C.c_char_p]
+        L.kmc_read_checkpoint.argtypes = [vp, i32, C.c_char_p]
         L.kmc_generate_packed.argtypes = [C.POINTER(Params), u64, i32, vp, vp]
         L.kmc_get_grid.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
@@ -134,6 +142,44 @@ def scaled_box(n_total, z=1000.0):
     """Box edge that keeps the reference's default densities (main.cpp:43-57): L = 5773*sqrt(N/200)."""
     L = 5773.0 * (n_total / 200.0) ** 0.5
     return (L, L, z)
+
+
+def _xyz(R):
+    return [np.ascontiguousarray(R[..., c], dtype=np.float64) for c in range(3)]
+
+
+def gro_append(path, na, nb, R, dt, step, box):
+    """append one test.gro frame (main.cpp:2258-2287) for reference-shaped coordinates R[N+1,5,5,3]; host only"""
+    X, Y, Z = _xyz(R); bx = np.array(box, dtype=np.float64)
+    rc = lib().kmc_gro_append_arrays(os.fsencode(path), na, nb, X.ctypes.data, Y.ctypes.data, Z.ctypes.data, dt, step, bx.ctypes.data)
+    if rc:
+        raise KmcError("kmc_gro_append_arrays failed: %d" % rc)
+
+
+def checkpoint_write(path, na, nb, R, status, res_nei, counters):
+    """position.cpt in the reference's format (main.cpp:2206-2244); counters = (bond_num, rl, cis, mono_cis, max_complex, step)"""
+    X, Y, Z = _xyz(R); st = np.ascontiguousarray(status, dtype=np.int32); rn = np.ascontiguousarray(res_nei, dtype=np.int32)
+    c = np.array(counters, dtype=np.int64)
+    rc = lib().kmc_checkpoint_write_arrays(os.fsencode(path), na, nb, X.ctypes.data, Y.ctypes.data, Z.ctypes.data, st.ctypes.data, rn.ctypes.data, c.ctypes.data)
+    if rc:
+        raise KmcError("kmc_checkpoint_write_arrays failed: %d" % rc)
+
+
+def checkpoint_read(path, na, nb):
+    """-> R[N+1,5,5,3], status, res_nei, counters[6]   (main.cpp:226-268)"""
+    n = na + nb
+    X = np.zeros((n + 1, 5, 5)); Y = np.zeros_like(X); Z = np.zeros_like(X)
+    st = np.zeros((n + 1, 5), dtype=np.int32); rn = np.zeros((n + 1, 7), dtype=np.int32); c = np.zeros(6, dtype=np.int64)
+    rc = lib().kmc_checkpoint_read_arrays(os.fsencode(path), na, nb, X.ctypes.data, Y.ctypes.data, Z.ctypes.data, st.ctypes.data, rn.ctypes.data, c.ctypes.data)
+    if rc:
+        raise KmcError("kmc_checkpoint_read_arrays failed: %d" % rc)
+    return np.stack([X, Y, Z], axis=-1), st, rn, c
+
+
+def parameter_log_write(params, path):
+    rc = lib().kmc_parameter_log_write(C.byref(params), os.fsencode(path))
+    if rc:
+        raise KmcError("kmc_parameter_log_write failed: %d" % rc)
 
 
 def format_bond_dat(dt, step, bond_num_rl, bond_num_mono_cis, bond_num_cis, bond_num, cluster_size, max_complex):
@@ -320,6 +366,15 @@ class Kmc:
 
     def write_cluster_log(self, path, replica=0):
         self._ck(lib().kmc_write_cluster_log(self.h, replica, os.fsencode(path)))
+
+    def write_gro(self, path, replica=0):
+        self._ck(lib().kmc_write_gro(self.h, replica, os.fsencode(path)))
+
+    def write_checkpoint(self, path, replica=0):
+        self._ck(lib().kmc_write_checkpoint(self.h, replica, os.fsencode(path)))
+
+    def read_checkpoint(self, path, replica=0):
+        self._ck(lib().kmc_read_checkpoint(self.h, replica, os.fsencode(path)))
 
     def run(self, n_steps, output_every, directory):
         self._ck(lib().kmc_run(self.h, n_steps, output_every, os.fsencode(directory)))

@@ -64,6 +64,21 @@ def main():
         subprocess.run(cmd, cwd=td, check=True, capture_output=True)
         kat["ref_records"] = dict(bond_dat=open(os.path.join(wd, "bond.dat")).read(), cluster_log=open(os.path.join(wd, "cluster.log")).read(),
                                   note="dense system, steps 5000 and 10000, written by the unmodified reference")
+    # the reference's own position.cpt / test.gro / parameter.log of a 5000-step N=40 hot run, with the state they describe
+    with tempfile.TemporaryDirectory() as td:
+        wd = os.path.join(td, "wd"); out = os.path.join(td, "f.bin")
+        sets40 = dict(cell_range_x=1000, cell_range_y=1000, cell_range_z=300); sets40.update(HOT)
+        cmd = [os.path.join(refio.REF_DIR, "kmcref_n40"), "--steps", "5000", "--workdir", wd, "--out", out]
+        for k2, v2 in sets40.items():
+            cmd += ["--set", "%s=%r" % (k2, float(v2))]
+        for k2, v2 in DENSE["scales"].items():
+            cmd += ["--scale", "%s=%r" % (k2, float(v2))]
+        subprocess.run(cmd, cwd=td, check=True, capture_output=True)
+        fr = refio.read_frames(out, 40)[-1]
+        kat["ref_files40"] = dict(position_cpt=open(os.path.join(wd, "position.cpt")).read(), test_gro=open(os.path.join(wd, "test.gro")).read(),
+                                  parameter_log=open(os.path.join(wd, "parameter.log")).read(), sets=sets40, scales=DENSE["scales"])
+        save_state("hot40_step5000.npz", fr, dict(box=[1000, 1000, 300], cis_on_scale=20, mono_cis_on_scale=20, bond_num=fr["bond_num"], bond_num_rl=fr["bond_num_rl"],
+                                                  bond_num_cis=fr["bond_num_cis"], bond_num_mono_cis=fr["bond_num_mono_cis"], **HOT))
     json.dump(kat, open(os.path.join(HERE, "ref_kat.json"), "w"), indent=1)
     print(json.dumps({k: v["frames"][-1] for k, v in kat.items()}, indent=1))
 
