@@ -89,3 +89,21 @@ def test_ensemble_statistics_match_reference(mode):
         a = np.array([row["series"][ti]["rl"] for row in ref["seeds"]], float); b = np.array([series[r][ti]["bond_num_rl"] for r in range(nseeds)], float)
         se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
         assert abs(a.mean() - b.mean()) < 3.5 * se + 0.5, (ti, a.mean(), b.mean(), se)
+
+
+def test_affinity_sweep_driver(tmp_path):
+    """configs[4] driver: stronger on-rate -> more R-L bonds, wider angle window -> more bonds; histograms are consistent"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "affinity_sweep.py"), "--molecules", "40000", "--steps", "1500", "--on", "0.005,0.09",
+                        "--thetaot", "30,90", "--density-scale", "8"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    rows = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{") and "\"grid_point\"" in l]
+    assert len(rows) == 4
+    by = {(r["on"], r["thetaot_cut"]): r for r in rows}
+    assert by[(0.09, 90.0)]["series"]["bond_num_rl"] > 1.5 * by[(0.005, 90.0)]["series"]["bond_num_rl"] > 0
+    assert by[(0.09, 90.0)]["series"]["bond_num_rl"] > by[(0.09, 30.0)]["series"]["bond_num_rl"]
+    for r in rows:
+        h = {int(k): v for k, v in r["oligomer_hist"].items()}
+        assert sum(h.values()) > 0 and sum(k * v for k, v in h.items() if k >= 2) == r["series"]["n_in_complexes"]
