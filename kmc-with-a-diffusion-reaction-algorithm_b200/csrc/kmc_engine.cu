@@ -173,8 +173,10 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     K.cellInv = 1.0 / edge;
 }
 
+static void strip_dev_free(kmc_handle *h);
 extern "C" void kmc_destroy(kmc_handle *h) {
     if (!h) return;
+    strip_dev_free(h);
     cudaSetDevice(h->P.device);
     for (void *p : h->allocs) cudaFree(p);
     for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }

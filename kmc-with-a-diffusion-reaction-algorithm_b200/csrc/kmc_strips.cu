@@ -423,6 +423,8 @@ __global__ void k_strip_fix_bonds(const __grid_constant__ Args A, const int *bon
     }
 }
 
+static void strip_dev_free(kmc_handle *h) { delete h->strip_dev; h->strip_dev = nullptr; }    // device buffers are in h->allocs
+
 static int strip_dev_alloc(kmc_handle *h) {
     StripDev &S = *h->strip_dev;
     if (S.flag) return KMC_OK;

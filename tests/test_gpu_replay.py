@@ -112,3 +112,15 @@ def test_config2_1e5_molecules_replay():
         lockstep(o, k, steps, 20, "1e5-" + regime)
         assert np.array_equal(o.accepted()[1:], k.accepted()[1:])
         k.close()
+
+
+def test_crowded_tiles_generic_path():
+    """2000 molecules at 6x the default density: more entries per tile window than the shared-memory staging holds, so the tile
+    kernel's overflow path (entries read from global memory, in-place evaluation) is what is being checked against the oracle"""
+    na, nb = 1500, 500
+    o, k = make_pair(na, nb, (7500.0, 7500.0, 400.0), "hot", seed=21)
+    k.init_random(seed=8)
+    o.set_state(*k.get_state())
+    lockstep(o, k, 60, 1, "crowded", per_step_accept=True)
+    lockstep(o, k, 540, 60, "crowded")
+    assert k.series()["bond_num"] >= 1
