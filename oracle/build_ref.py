@@ -48,8 +48,20 @@ def build(tag):
     sh("g++", *flags, "-c", src, "-o", obj)
     inj, ship = obj.replace(".o", "_inj.o"), obj.replace(".o", "_ship.o")
     sh("objcopy", "--redefine-sym", "main=ref_main", "--weaken-symbol=_Z5rand2v", obj, inj)
+    # call sites of rand2() inside ref_main -> source lines (DWARF), so that the injected rand2 can key its draw by call site:
+    # return address - &ref_main  ->  main.cpp line
+    dis = subprocess.run(["objdump", "-dr", "--no-show-raw-insn", inj], capture_output=True, text=True, check=True).stdout.splitlines()
+    sites = []
+    for n, line in enumerate(dis):
+        if "R_X86_64_PLT32" in line and "_Z5rand2v" in line:
+            addr = int(dis[n - 1].split(":")[0].strip(), 16)
+            src_line = subprocess.run(["addr2line", "-e", inj, "-j", ".text.startup", hex(addr)], capture_output=True, text=True, check=True).stdout
+            sites.append((addr + 5, int(re.search(r":(\d+)", src_line).group(1))))
+    assert len(sites) == 30, len(sites)
+    with open(os.path.join(TMP, "callsites_%s.h" % tag), "w") as f:
+        f.write("static const struct { long ret; int line; } g_sites[] = {%s};\n" % ", ".join("{%d, %d}" % s for s in sites))
     sh("objcopy", "--redefine-sym", "main=ref_main", obj, ship)
-    hflags = ["-O2", "-DKMC_NA=%d" % na, "-DKMC_NB=%d" % nb] + (["-mcmodel=medium"] if na + nb >= 10000 else [])
+    hflags = ["-O2", "-DKMC_NA=%d" % na, "-DKMC_NB=%d" % nb, "-I", TMP, "-I", HERE, "-DKMC_CALLSITES=\"callsites_%s.h\"" % tag] + (["-mcmodel=medium"] if na + nb >= 10000 else [])
     harness = os.path.join(HERE, "ref_harness.cpp")
     sh("g++", *hflags, harness, inj, "-o", os.path.join(HERE, "_ref", "kmcref_" + tag))
     sh("g++", *hflags, "-DKMC_SHIPPED_RAND2", harness, ship, "-o", os.path.join(HERE, "_ref", "kmcref_%s_shipped" % tag))

@@ -70,7 +70,7 @@ def ref_available(tag="n200"):
 
 
 def run_ref(tag, n, steps, sets=None, scales=None, rand2_state=None, rand_state=None, frames_every=0,
-            in_frame=None, shipped=False, timeout=3600):
+            in_frame=None, shipped=False, timeout=3600, keyed_seed=None):
     """Runs oracle/_ref/kmcref_<tag>; returns (summary dict, list of frames)."""
     exe = os.path.join(REF_DIR, "kmcref_" + tag + ("_shipped" if shipped else ""))
     with tempfile.TemporaryDirectory() as td:
@@ -86,6 +86,8 @@ def run_ref(tag, n, steps, sets=None, scales=None, rand2_state=None, rand_state=
             cmd += ["--rand-state", str(rand_state)]
         if frames_every:
             cmd += ["--frames-every", str(frames_every)]
+        if keyed_seed is not None:
+            cmd += ["--keyed", str(keyed_seed)]
         if in_frame is not None:
             inp = os.path.join(td, "in.bin")
             write_frame(inp, in_frame)

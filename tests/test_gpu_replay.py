@@ -124,3 +124,21 @@ def test_crowded_tiles_generic_path():
     lockstep(o, k, 60, 1, "crowded", per_step_accept=True)
     lockstep(o, k, 540, 60, "crowded")
     assert k.series()["bond_num"] >= 1
+
+
+def test_gpu_against_keyed_reference_directly(golden_dir):
+    """No oracle in between: the bond table after 1000/2000/3000 steps must hash to what the UNMODIFIED reference produced when driven
+    by the same keyed Philox stream (tests/golden/ref_kat.json: keyed_hot200, written by oracle/ref_harness.cpp --keyed)."""
+    import json
+    import refio
+    kk = json.load(open(os.path.join(golden_dir, "ref_kat.json")))["keyed_hot200"]
+    g = load_golden_state(os.path.join(golden_dir, kk["start"]))
+    k = kmc_b200.Kmc(apply_regime(kmc_b200.default_params(box=tuple(g["params"]["box"]), seed=kk["seed"], mode=kmc_b200.MODE_REPLAY), "hot"))
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    done = g["step"]
+    for fr in kk["frames"]:
+        k.step(fr["step"] - done); done = fr["step"]
+        R, st, rn = k.get_state()
+        assert "%016x" % refio.fnv1a64(rn, st) == fr["hash_bonds"], "bond table differs from the keyed reference at step %d" % done
+        s = k.series()
+        assert (s["bond_num"], s["bond_num_rl"], s["bond_num_cis"], s["bond_num_mono_cis"]) == (fr["bond_num"], fr["bond_num_rl"], fr["bond_num_cis"], fr["bond_num_mono_cis"])

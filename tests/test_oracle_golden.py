@@ -144,3 +144,36 @@ def test_compact_pose_invariants(golden_dir):
             assert np.array_equal(A[:, j, 1:4, :2], A[:, 1, 1:4, :2])
             assert np.array_equal(A[:, j, 4, :2], A[:, 1, 1, :2])
             assert np.all(A[:, j, 1:4, 2] == (2 * j - 2) * 20.0) and np.all(A[:, j, 4, 2] == (2 * j - 1) * 20.0)
+
+
+def test_keyed_oracle_against_keyed_reference_golden(golden_dir):
+    """The keyed (Philox) stream: golden frames written by the UNMODIFIED reference when ref_harness.cpp keys every draw by its call
+    site (return address -> main.cpp line -> slot), molecule, partner and step. The oracle in stream_mode=1 must reproduce them bit for
+    bit -- this is the stream the GPU replay tests use."""
+    from common import load_golden_state
+    kk = KAT["keyed_hot200"]
+    g = load_golden_state(os.path.join(golden_dir, kk["start"]))
+    p = apply_regime(pyoracle.default_params(box=tuple(g["params"]["box"]), use_grid=1, stream_mode=1, seed=kk["seed"]), "hot")
+    o = pyoracle.Oracle(p)
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    done = g["step"]
+    for fr in kk["frames"]:
+        o.step(fr["step"] - done); done = fr["step"]
+        hr, hb = hashes(o)
+        assert (hb, hr) == (fr["hash_bonds"], fr["hash_R"]), "keyed oracle differs from the keyed reference at step %d" % done
+    assert o.counts()["rand_draws"] == kk["summary"]["rand_draws"]
+
+
+@pytest.mark.skipif(not refio.ref_available("n40"), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_keyed_reference_live_n40(golden_dir):
+    from common import load_golden_state
+    g = load_golden_state(os.path.join(golden_dir, "hot40_step200000.npz"))
+    sets = dict(cell_range_x=1000, cell_range_y=1000, cell_range_z=300, Diss_Rate=2e-5, cis_Diss_Rate=2e-5, mono_cis_Diss_Rate=1e-4)
+    fr = dict(step=g["step"], bond_num=0, bond_num_rl=0, bond_num_cis=0, bond_num_mono_cis=0, max_complex=g["max_complex"], R=g["R"], status=g["status"], res_nei=g["res_nei"])
+    s, frames = refio.run_ref("n40", 40, 20000, sets=sets, scales=dict(cis_Ass_Rate=20, mono_cis_Ass_Rate=20), in_frame=fr, keyed_seed=77)
+    p = apply_regime(pyoracle.default_params(box=(1000, 1000, 300), n_receptor=30, n_ligand=10, use_grid=1, stream_mode=1, seed=77), "hot")
+    o = pyoracle.Oracle(p)
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    o.step(20000)
+    R, st, rn = o.get_state()
+    assert np.array_equal(R, frames[-1]["R"]) and np.array_equal(rn, frames[-1]["res_nei"]) and np.array_equal(st, frames[-1]["status"])
