@@ -174,6 +174,19 @@ static void fill_consts(const kmc_params &P, Consts &K) {
 }
 
 static void strip_dev_free(kmc_handle *h);
+// tile edge of k_resolve_tiles: the largest of 16/12/8/6/4/2 cells whose window ((edge+2)^2 cells) is expected to hold at most
+// ~300 entries (the staging buffers take TCAP = 384; a fuller window still works through the slower overflow path)
+static void choose_tiles(kmc_handle *h) {
+    Consts &K = h->K;
+    const double perCell = (double)K.NT / std::max(1.0, (double)K.R * K.ncx * K.ncy);
+    const int cand[6] = {16, 12, 8, 6, 4, 2};
+    int ts = 2;
+    for (int c : cand) if ((c + 2.0) * (c + 2.0) * perCell <= 300.0) { ts = c; break; }
+    if (const char *o = getenv("KMC_TILE_EDGE")) { int v = atoi(o); if (v >= 1 && v <= TS) ts = v; }
+    K.tileEdge = std::min(ts, TS);
+    h->nTiles = K.R * ((K.ncx + K.tileEdge - 1) / K.tileEdge) * ((K.ncy + K.tileEdge - 1) / K.tileEdge);
+}
+
 extern "C" void kmc_destroy(kmc_handle *h) {
     if (!h) return;
     strip_dev_free(h);
@@ -222,7 +235,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
     A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
-    h->nTiles = K.R * ((K.ncx + TS - 1) / TS) * ((K.ncy + TS - 1) / TS);
+    choose_tiles(h);
     A(scanTmp, (size_t)h->scanBlocks + 1);
     A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);

@@ -44,6 +44,7 @@ struct Consts {
     double reachRR, reachRL, reachLL, reachOn, reachCis;   // centre-centre search bounds (with margin)
     double skin;                              // far-mover threshold
     double gx0, gy0, cellInv; int ncx, ncy;   // neighbour grid
+    int tileEdge;                             // k_resolve_tiles: cells per tile edge
     int NA, NB, R, mode;                      // per-replica sizes, replicas
     int NAt, NBt, NT;                         // totals (capacities of the receptor / ligand blocks; live counts are device scalars)
     uint64_t seed;

@@ -854,11 +854,12 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
     __shared__ TileSmem S;
     __shared__ unsigned int surv[NSURV];          // (staged index of probe << 16) | staged index of neighbour
     __shared__ int nsurv;
-    const int ntx = (K.ncx + TS - 1) / TS, nty = (K.ncy + TS - 1) / TS;
+    const int ts = K.tileEdge;        // tile edge in cells (<= TS), chosen from the mean cell occupancy so that a window fits the staging buffers
+    const int ntx = (K.ncx + ts - 1) / ts, nty = (K.ncy + ts - 1) / ts;
     int b = blockIdx.x;
     const int tx = b % ntx; b /= ntx;
     const int ty = b % nty; const int rep = b / nty;
-    const int x0 = tx * TS, x1 = min(x0 + TS - 1, K.ncx - 1), y0 = ty * TS, y1 = min(y0 + TS - 1, K.ncy - 1);
+    const int x0 = tx * ts, x1 = min(x0 + ts - 1, K.ncx - 1), y0 = ty * ts, y1 = min(y0 + ts - 1, K.ncy - 1);
     const int wx0 = max(x0 - 1, 0), wx1 = min(x1 + 1, K.ncx - 1), wy0 = max(y0 - 1, 0), wy1 = min(y1 + 1, K.ncy - 1);
     const int nrow = wy1 - wy0 + 1, ncol = wx1 - wx0 + 2, nir = y1 - y0 + 1;
 #ifdef KMC_TILE_TIMING

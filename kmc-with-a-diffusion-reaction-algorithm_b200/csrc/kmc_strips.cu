@@ -149,7 +149,7 @@ extern "C" int kmc_strip_configure(kmc_handle *h, int32_t rank, int32_t nranks, 
             if (!ok) { h->err = "kmc_strip_configure: grid allocation failed"; return KMC_ERR_CUDA; }
         }
         D.ncell = ncell;
-        h->nTiles = ((K.ncx + TS - 1) / TS) * ((K.ncy + TS - 1) / TS);
+        choose_tiles(h);
     }
     if (!D.refA) {
         if (dalloc(h, &D.refA, std::max(h->NAt, 1)) != cudaSuccess || dalloc(h, &D.refB, std::max(h->NBt, 1)) != cudaSuccess) { h->err = "kmc_strip_configure: allocation failed"; return KMC_ERR_CUDA; }
