@@ -38,6 +38,7 @@ struct Dev {
     int *cxSize, *cxOff, *cxRoots;         // per root ligand: members, offset into members[]; list of roots with size>1
     int *members, *rowWork;                // member gids in BFS order / working copy permuted by the shuffles
     int *bfsMark;
+    int *rowPos;                           // [NT] position of a complex member in its breadth-first member list
     unsigned char *unitState, *farFlag, *movedFlag;
     // neighbour grid
     int *cellCount, *cellStart, *scanTmp;  // [ncell+1]

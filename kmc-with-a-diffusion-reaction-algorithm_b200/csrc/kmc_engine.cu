@@ -231,7 +231,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(recLig, K.NAt); A(recSite, K.NAt); A(recCis, K.NAt); A(ligRec, (size_t)K.NBt * 3);
     A(ufParent, K.NT); A(unitOf, K.NT);
     if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
-    A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT);
+    A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT); A(rowPos, K.NT);
     A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
     A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
@@ -465,7 +465,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     // S2 proposals
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
-    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, 64), 148 * 4), 64, 0, st>>>(A)));
+    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, st>>>(A)));
     // neighbour grid: the histogram was accumulated by the propose kernels (cellCount is zero at step start: k_scan_down clears it)
     LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>((const int4 *)D.cellCount, D.scanTmp)));
     LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks)));
@@ -475,7 +475,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const int gl = std::min(nblk(NT, B), 148 * 8);
     LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<std::min(gl, 148), B, 0, st>>>(A, 0)));
+    LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<std::min(gl, 148 * 4), B, 0, st>>>(A, 0)));
     LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));
     LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
     // S3

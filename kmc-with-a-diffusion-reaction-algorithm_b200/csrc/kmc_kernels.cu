@@ -93,7 +93,7 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     D.cxRoots[atomicAdd(&D.scal[S_NCX], 1)] = h;
     int *row = D.members + off;
     int head = 0, tail = 0;
-    row[tail++] = cK.NAt + h; D.bfsMark[cK.NAt + h] = 1;
+    row[tail++] = cK.NAt + h; D.bfsMark[cK.NAt + h] = 1; D.rowPos[cK.NAt + h] = 0;
     while (head < tail) {
         int m = row[head++];
         int cand[3], nc = 0;
@@ -105,7 +105,7 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
             for (int s = 0; s < 3; s++) if (D.ligRec[hh * 3 + s] >= 0) cand[nc++] = D.ligRec[hh * 3 + s];
         }
         for (int c = 0; c < nc; c++)
-            if (!D.bfsMark[cand[c]]) { D.bfsMark[cand[c]] = 1; if (tail < size) row[tail++] = cand[c]; }
+            if (!D.bfsMark[cand[c]]) { D.bfsMark[cand[c]] = 1; if (tail < size) { D.rowPos[cand[c]] = tail; row[tail++] = cand[c]; } }
     }
 }
 
@@ -245,19 +245,59 @@ __global__ void __launch_bounds__(128, PSMINB) k_propose_simple(const __grid_con
     }
 }
 
-// ---- complexes: one thread per ligand-rooted complex with more than one member -------------------
-struct CxCtx {
-    const Dev &D; const Consts &K;
-    KD Rec rec(int a) const { return load_rec(D.recCn, D.recS2n, D.recS3n, a); }
-    KD void put(int a, const Rec &r) const { store_rec(D.recCn, D.recS2n, D.recS3n, a, r); }
-    KD void lig(int h, Lig &l) const { load_lig(D.lign, h, l); }
-    KD void put(int h, const Lig &l) const { store_lig(D.lign, h, l); }
+// ---- complexes: one WARP per ligand-rooted complex with more than one member ------------------------------------------
+// The alignment code (S2e/S2f) is sequential by nature (order-dependent snaps, shuffles, the goto state machine) and runs on
+// lane 0, but against a copy of the complex held in shared memory: member poses, the bonds inside the complex as member slots,
+// the moved[] flags and the working row. All lanes load/translate/rotate/store the members in parallel; sums whose operand
+// order matters (wrap centre, rotation centre: main.cpp:1007-1008, 1049-1067) are accumulated by lane 0 in row order.
+// A member handle `m` is a slot of the cache (canonical breadth-first order); complexes with more members than the cache holds
+// take the same code through accessors that go to global memory (handle = gid).
+#define CX_CAP 40          // members cached per complex
+#define CX_WARPS 4         // complexes per CTA
+
+struct CxShared {          // per warp
+    double pose[CX_CAP][24];             // receptor: cx,cy,s2x,s2y,s3x,s3y ; ligand: 8 points x 3
+    int gid[CX_CAP];
+    short lig[CX_CAP], cis[CX_CAP], site[CX_CAP];   // receptor: slot of its ligand / cis partner (-1 none), ligand site 0..2
+    short rec3[CX_CAP][3];               // ligand: slot of the receptor on site s (-1 none)
+    unsigned char moved[CX_CAP];
+    int row[CX_CAP];                     // working order (handles), permuted by the shuffles
+    int draw[CX_CAP];                    // the rand() values of one shuffle, drawn by all lanes at once
+};
+
+struct CxLocal {           // accessors on the shared-memory copy; handle = slot
+    CxShared &S; const Consts &K; int NAt;
+    KD bool is_rec(int m) const { return S.gid[m] < NAt; }
+    KD int recLig(int m) const { return S.lig[m]; }
+    KD int recSite(int m) const { return S.site[m]; }
+    KD int recCis(int m) const { return S.cis[m]; }
+    KD int ligRec(int m, int s) const { return S.rec3[m][s]; }
+    KD bool moved(int m) const { return S.moved[m] != 0; }
+    KD void set_moved(int m) const { S.moved[m] = 1; }
+    KD Rec rec(int m) const { const double *p = S.pose[m]; Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]}; return r; }
+    KD void put(int m, const Rec &r) const { double *p = S.pose[m]; p[0] = r.cx; p[1] = r.cy; p[2] = r.s2x; p[3] = r.s2y; p[4] = r.s3x; p[5] = r.s3y; }
+    KD void lig(int m, Lig &l) const { const double *p = S.pose[m]; for (int q = 0; q < 24; q++) (&l.p[0][0])[q] = p[q]; }
+    KD void put(int m, const Lig &l) const { double *p = S.pose[m]; for (int q = 0; q < 24; q++) p[q] = (&l.p[0][0])[q]; }
+};
+struct CxGlobal {          // accessors straight on the nxt arrays; handle = gid
+    const Dev &D; const Consts &K; int NAt;
+    KD bool is_rec(int m) const { return m < NAt; }
+    KD int recLig(int m) const { int h = D.recLig[m]; return h < 0 ? -1 : NAt + h; }
+    KD int recSite(int m) const { return D.recSite[m]; }
+    KD int recCis(int m) const { return D.recCis[m]; }
+    KD int ligRec(int m, int s) const { return D.ligRec[(m - NAt) * 3 + s]; }
+    KD bool moved(int m) const { return D.movedFlag[m] != 0; }
+    KD void set_moved(int m) const { D.movedFlag[m] = 1; }
+    KD Rec rec(int m) const { return load_rec(D.recCn, D.recS2n, D.recS3n, m); }
+    KD void put(int m, const Rec &r) const { store_rec(D.recCn, D.recS2n, D.recS3n, m, r); }
+    KD void lig(int m, Lig &l) const { load_lig(D.lign, m - NAt, l); }
+    KD void put(int m, const Lig &l) const { store_lig(D.lign, m - NAt, l); }
 };
 
 // main.cpp:1296-1328 (also 1511-1545, 1651-1683): re-snap receptor a onto its ligand if misaligned
-KD bool resnap_rec_to_its_ligand(const CxCtx &C, int a) {
-    int h = C.D.recLig[a]; if (h < 0) return false;
-    int s = C.D.recSite[a];
+template <class Cx> KD bool resnap_rec_to_its_ligand(const Cx &C, int a) {
+    const int h = C.recLig(a); if (h < 0) return false;
+    const int s = C.recSite(a);
     Lig b; C.lig(h, b);
     Rec r = C.rec(a);
     if (!rl_misaligned(C.K, b, s, r)) return false;
@@ -265,18 +305,18 @@ KD bool resnap_rec_to_its_ligand(const CxCtx &C, int a) {
     return true;
 }
 // main.cpp:1548-1578, 1699-1728: re-snap the cis partner of a from a's axis if misaligned
-KD bool resnap_cis_partner(const CxCtx &C, int a, int a2) {
+template <class Cx> KD bool resnap_cis_partner(const Cx &C, int a, int a2) {
     Rec r1 = C.rec(a), r2 = C.rec(a2);
     if (!cis_misaligned(C.K, r1, r2)) return false;
     snap_cis(C.K, r2, r1); C.put(a2, r2);
     return true;
 }
 // body at `lable4`, main.cpp:1439-1585
-KD void reseat_ligand(const CxCtx &C, int h, int s, int a1) {
-    const Consts &K = C.K; const Dev &D = C.D;
-    D.movedFlag[K.NAt + h] = 1;
+template <class Cx> KD void reseat_ligand(const Cx &C, int h, int s, int a1) {
+    const Consts &K = C.K;
+    C.set_moved(h);
     Lig b; C.lig(h, b);
-    Rec r = C.rec(a1);
+    const Rec r = C.rec(a1);
     const double zA = rec_bead_z(K, 3);
     for (int q = 0; q < 8; q++) b.p[q][2] = zA;
     b.p[4][2] = add(zA, K.rB);
@@ -288,20 +328,20 @@ KD void reseat_ligand(const CxCtx &C, int h, int s, int a1) {
     seat_ligand(K, b, angle, cx, cy);
     C.put(h, b);
     for (int m = 0; m < 3; m++) {
-        int am = D.ligRec[h * 3 + m];
+        const int am = C.ligRec(h, m);
         if (am < 0) continue;
-        if (resnap_rec_to_its_ligand(C, am)) D.movedFlag[am] = 1;
-        int a2 = D.recCis[am];
-        if (a2 >= 0 && resnap_cis_partner(C, am, a2)) D.movedFlag[a2] = 1;
+        if (resnap_rec_to_its_ligand(C, am)) C.set_moved(am);
+        const int a2 = C.recCis(am);
+        if (a2 >= 0 && resnap_cis_partner(C, am, a2)) C.set_moved(a2);
     }
 }
-KD bool bridge_candidate(const CxCtx &C, int h, int s) {        // main.cpp:1420-1423
-    int a1 = C.D.ligRec[h * 3 + s]; if (a1 < 0) return false;
-    int a2 = C.D.recCis[a1]; if (a2 < 0) return false;
-    return C.D.recLig[a2] >= 0 && C.D.movedFlag[C.K.NAt + h] == 0;
+template <class Cx> KD bool bridge_candidate(const Cx &C, int h, int s) {        // main.cpp:1420-1423
+    const int a1 = C.ligRec(h, s); if (a1 < 0) return false;
+    const int a2 = C.recCis(a1); if (a2 < 0) return false;
+    return C.recLig(a2) >= 0 && !C.moved(h);
 }
-KD bool lig_site_misaligned(const CxCtx &C, int h, int s, int a1) {
-    Lig b; C.lig(h, b); Rec r = C.rec(a1);
+template <class Cx> KD bool lig_site_misaligned(const Cx &C, int h, int s, int a1) {
+    Lig b; C.lig(h, b); const Rec r = C.rec(a1);
     return rl_misaligned(C.K, b, s, r);
 }
 // std::random_shuffle(&row[1], &row[size]) with rand() (libstdc++): the last member never moves (main.cpp:1285)
@@ -312,162 +352,302 @@ KD void shuffle_row(int *row, int size, uint64_t seed, uint32_t root, uint32_t &
         if (i != j) { int t = row[i]; row[i] = row[j]; row[j] = t; }
     }
 }
-
-__global__ void k_propose_complex(const __grid_constant__ Args A) {
-    KARGS
-    const uint64_t step = D.step64[0];
-    const Consts &K = cK;
-    const int ncx = D.scal[S_NCX];
-    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < ncx; ci += gridDim.x * blockDim.x) {
-    const int h0 = D.cxRoots[ci], rootGid = K.NAt + h0;
-    const int size = D.cxSize[h0];
-    const int *rowIn = D.members + D.cxOff[h0];
-    int *row = D.rowWork + D.cxOff[h0];
-    const int rep = h0 / K.NB;
-    const uint64_t seed = seed_of(cK, rep);
-    const uint32_t me = ref_id(K, D, rootGid);
-    CxCtx C{D, K};
-    int nA = 0, nB = 0;
-    for (int i = 0; i < size; i++) { int m = rowIn[i]; row[i] = m; D.movedFlag[m] = 0; if (m < K.NAt) nA++; else nB++; }
-    const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
-                 u2 = keyed_uniform(seed, me, 0, step, 2);
-    // ---- S2d rigid move (main.cpp:974-1131); complexes with >= 2 ligands have D = 0 but still draw ----
-    const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
-    const double phai = mul(mul(u1, 2.0), K.pai);
-    double sp, cp; sincos(phai, &sp, &cp);
-    const double shx = mul(amp, cp), shy = mul(amp, sp);
-    double PBx = 0, PBy = 0;
-    for (int i = 0; i < size; i++) {
-        int m = row[i];
-        if (m < K.NAt) {
-            Rec r = load_rec(D.recC, D.recS2, D.recS3, m);
-            r.cx = add(r.cx, shx); r.s2x = add(r.s2x, shx); r.s3x = add(r.s3x, shx);
-            r.cy = add(r.cy, shy); r.s2y = add(r.s2y, shy); r.s3y = add(r.s3y, shy);
-            C.put(m, r); PBx = add(PBx, r.cx); PBy = add(PBy, r.cy);
-        } else {
-            Lig l; load_lig(D.lig, m - K.NAt, l);
-            for (int q = 0; q < 8; q++) { l.p[q][0] = add(l.p[q][0], shx); l.p[q][1] = add(l.p[q][1], shy); }
-            C.put(m - K.NAt, l); PBx = add(PBx, l.p[0][0]); PBy = add(PBy, l.p[0][1]);
-        }
-    }
-    PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
-    PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
-    double cmx = 0, cmy = 0, cmz = 0;
-    for (int i = 0; i < size; i++) {
-        int m = row[i];
-        if (m < K.NAt) {
-            Rec r = C.rec(m);
-            r.cx = sub(r.cx, PBx); r.s2x = sub(r.s2x, PBx); r.s3x = sub(r.s3x, PBx);
-            r.cy = sub(r.cy, PBy); r.s2y = sub(r.s2y, PBy); r.s3y = sub(r.s3y, PBy);
-            C.put(m, r);
-            for (int j = 1; j <= 4; j++) { cmx = add(cmx, r.cx); cmy = add(cmy, r.cy); cmz = add(cmz, rec_bead_z(K, j)); }
-        } else {
-            Lig l; C.lig(m - K.NAt, l);
-            for (int q = 0; q < 8; q++) { l.p[q][0] = sub(l.p[q][0], PBx); l.p[q][1] = sub(l.p[q][1], PBy); }
-            C.put(m - K.NAt, l);
-            for (int q = 0; q < 4; q++) { cmx = add(cmx, l.p[q][0]); cmy = add(cmy, l.p[q][1]); cmz = add(cmz, l.p[q][2]); }
-        }
-    }
-    const double nbeads = (double)(4 * nA + 4 * nB);
-    cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
-    const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
-    double ss, cs; sincos(psai, &ss, &cs);
-    int lastA = -1;
-    for (int i = 0; i < size; i++) {
-        int m = row[i];
-        if (m < K.NAt) {
-            Rec t = C.rec(m), n;
-            rotz(cs, ss, t.cx, t.cy, cmx, cmy, n.cx, n.cy);
-            rotz(cs, ss, t.s2x, t.s2y, cmx, cmy, n.s2x, n.s2y);
-            rotz(cs, ss, t.s3x, t.s3y, cmx, cmy, n.s3x, n.s3y);
-            C.put(m, n); lastA = m;
-        } else {
-            Lig l; C.lig(m - K.NAt, l);
-            for (int q = 0; q < 8; q++) {
-                double nx, ny; rotz(cs, ss, l.p[q][0], l.p[q][1], cmx, cmy, nx, ny);
-                l.p[q][0] = nx; l.p[q][1] = ny;
-                l.p[q][2] = add(sub(l.p[q][2], cmz), cmz);        // 1*(z-c)+c, main.cpp:1123
-            }
-            C.put(m - K.NAt, l);
-        }
-    }
+// S2e (one ligand, handle hl) / S2f (several ligands): the sequential alignment of a complex after its rigid move
+template <class Cx> KD void align_complex(const Cx &C, int *row, int size, int nB, int hl, uint64_t seed, uint32_t me, uint64_t step) {
+    const Consts &K = C.K;
     if (nB == 1) {
         // ---- S2e (main.cpp:1138-1274) ----
-        const int h = h0;
-        Lig b; C.lig(h, b);
+        Lig b; C.lig(hl, b);
         if (b.p[4][2] != add(b.p[0][2], K.rB)) {                  // exact compare: first time only
-            const double zA = rec_bead_z(K, 3);                   // R_z_new[lastA][3][1]
+            const double zA = rec_bead_z(K, 3);                   // R_z_new[last receptor][3][1]: the template value
             for (int q = 0; q < 8; q++) b.p[q][2] = zA;
             b.p[4][2] = add(zA, K.rB);
             const double angle = add(atan2(sub(b.p[1][0], b.p[0][0]), sub(b.p[1][1], b.p[0][1])), K.pai);
             seat_ligand(K, b, angle, b.p[0][0], b.p[0][1]);
-            C.put(h, b);
+            C.put(hl, b);
         }
-        (void)lastA;
-        for (int s = 0; s < 3; s++) { int a1 = D.ligRec[h * 3 + s]; if (a1 >= 0) resnap_rec_to_its_ligand(C, a1); }
+        for (int s = 0; s < 3; s++) { const int a1 = C.ligRec(hl, s); if (a1 >= 0) resnap_rec_to_its_ligand(C, a1); }
         for (int s = 0; s < 3; s++) {
-            int a1 = D.ligRec[h * 3 + s];
-            if (a1 >= 0 && D.recCis[a1] >= 0) resnap_cis_partner(C, a1, D.recCis[a1]);
+            const int a1 = C.ligRec(hl, s);
+            if (a1 >= 0 && C.recCis(a1) >= 0) resnap_cis_partner(C, a1, C.recCis(a1));
         }
-    } else {
-        // ---- S2f (main.cpp:1284-1732) ----
-        uint32_t cnt = 0;
-        shuffle_row(row, size, seed, me, cnt, step);                       // pass 0
-        for (int i = 0; i < size; i++) { int a = row[i]; if (a < K.NAt && resnap_rec_to_its_ligand(C, a)) D.movedFlag[a] = 1; }
-        shuffle_row(row, size, seed, me, cnt, step);                       // pass 1
-        for (int i = 0; i < size; i++) {
-            int a = row[i];
-            if (a < K.NAt && D.recLig[a] >= 0 && D.recCis[a] >= 0 && D.recLig[D.recCis[a]] >= 0 && D.movedFlag[a] == 0) {
-                int a2 = D.recCis[a];
-                D.movedFlag[a] = 1; D.movedFlag[a2] = 1;
-                Rec r1 = C.rec(a), r2 = C.rec(a2);
-                if (cis_misaligned(K, r1, r2)) { snap_cis(K, r1, r2); C.put(a, r1); }   // a rebuilt FROM a2, 1390-1400
+        return;
+    }
+    // ---- S2f (main.cpp:1284-1732) ----
+    uint32_t cnt = 0;
+    shuffle_row(row, size, seed, me, cnt, step);                           // pass 0
+    for (int i = 0; i < size; i++) { const int a = row[i]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }
+    shuffle_row(row, size, seed, me, cnt, step);                           // pass 1
+    for (int i = 0; i < size; i++) {
+        const int a = row[i];
+        if (C.is_rec(a) && C.recLig(a) >= 0 && C.recCis(a) >= 0 && C.recLig(C.recCis(a)) >= 0 && !C.moved(a)) {
+            const int a2 = C.recCis(a);
+            C.set_moved(a); C.set_moved(a2);
+            Rec r1 = C.rec(a), r2 = C.rec(a2);
+            if (cis_misaligned(K, r1, r2)) { snap_cis(K, r1, r2); C.put(a, r1); }   // a rebuilt FROM a2, 1390-1400
+        }
+    }
+    // passes 2 and 3; pass 3 re-enters pass 2's innermost block (goto lable4, main.cpp:1628 -> 1438)
+    bool resume = false; int i = 0, s = 0, h = 0, a1 = 0;
+    for (;;) {
+        if (!resume) { shuffle_row(row, size, seed, me, cnt, step); i = 0; }
+        for (; i < size; i++) {
+            if (C.is_rec(row[i])) continue;
+            if (!resume) { h = row[i]; s = 0; }
+            for (; s < 3; s++) {
+                bool run;
+                if (resume) { run = true; resume = false; }
+                else {
+                    run = false;
+                    if (bridge_candidate(C, h, s)) { a1 = C.ligRec(h, s); run = lig_site_misaligned(C, h, s, a1); }
+                }
+                if (run) reseat_ligand(C, h, s, a1);
             }
         }
-        // passes 2 and 3; pass 3 re-enters pass 2's innermost block (goto lable4, main.cpp:1628 -> 1438)
-        bool resume = false; int i = 0, s = 0, h = 0, a1 = 0;
-        for (;;) {
-            if (!resume) { shuffle_row(row, size, seed, me, cnt, step); i = 0; }
+        shuffle_row(row, size, seed, me, cnt, step);                       // pass 3
+        for (i = 0; i < size; i++) {
+            if (C.is_rec(row[i])) continue;
+            h = row[i];
+            for (s = 0; s < 3; s++)
+                if (bridge_candidate(C, h, s)) {
+                    a1 = C.ligRec(h, s);
+                    if (lig_site_misaligned(C, h, s, a1)) { resume = true; break; }
+                }
+            if (resume) break;
+        }
+        if (!resume) break;
+    }
+    for (int q = 0; q < size; q++) { const int a = row[q]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }   // pass 4
+    for (int q = 0; q < size; q++) {                                                                                            // pass 5
+        const int a = row[q];
+        if (C.is_rec(a) && C.recLig(a) >= 0 && C.recCis(a) >= 0 && C.recLig(C.recCis(a)) < 0) resnap_cis_partner(C, a, C.recCis(a));
+    }
+}
+
+// The same alignment for a cached complex, executed by the whole warp: the passes whose iterations cannot influence each other
+// run one member per lane -- pass 0 and pass 4 (every receptor is re-snapped onto ITS ligand, ligands are not touched),
+// pass 5 (every ligand-free cis partner is rebuilt from ITS one partner) -- and the Philox draws of a shuffle are made by all
+// lanes; the order-dependent parts (the swaps of a shuffle, passes 1-3 with their moved[] flags and the goto) stay on lane 0.
+KD void shuffle_row_warp(CxShared &S, int size, uint64_t seed, uint32_t root, uint32_t &cnt, uint64_t step, int lane) {
+    const int n = size - 1;
+    for (int i = 1 + lane; i < n; i += 32) S.draw[i] = keyed_rand31(seed, root, cnt + (uint32_t)(i - 1), step) % (i + 1);
+    if (n > 1) cnt += (uint32_t)(n - 1);
+    __syncwarp();
+    if (lane == 0)
+        for (int i = 1; i < n; i++) { const int j = S.draw[i]; if (i != j) { const int t = S.row[i]; S.row[i] = S.row[j]; S.row[j] = t; } }
+    __syncwarp();
+}
+KD void align_complex_warp(const CxLocal &C, CxShared &S, int size, int nB, uint64_t seed, uint32_t me, uint64_t step, int lane) {
+    const Consts &K = C.K;
+    if (nB == 1) { if (lane == 0) align_complex(C, S.row, size, nB, 0, seed, me, step); __syncwarp(); return; }
+    uint32_t cnt = 0;
+    shuffle_row_warp(S, size, seed, me, cnt, step, lane);                   // pass 0 (order free: see above)
+    for (int i = lane; i < size; i += 32) { const int a = S.row[i]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }
+    __syncwarp();
+    shuffle_row_warp(S, size, seed, me, cnt, step, lane);                   // pass 1
+    if (lane == 0)
+        for (int i = 0; i < size; i++) {
+            const int a = S.row[i];
+            if (C.is_rec(a) && C.recLig(a) >= 0 && C.recCis(a) >= 0 && C.recLig(C.recCis(a)) >= 0 && !C.moved(a)) {
+                const int a2 = C.recCis(a);
+                C.set_moved(a); C.set_moved(a2);
+                Rec r1 = C.rec(a), r2 = C.rec(a2);
+                if (cis_misaligned(K, r1, r2)) { snap_cis(K, r1, r2); C.put(a, r1); }
+            }
+        }
+    __syncwarp();
+    // passes 2 and 3 (goto lable4, main.cpp:1628 -> 1438): lane 0 runs the state machine, every lane takes part in the shuffles
+    int resume = 0; int i = 0, s = 0, h = 0, a1 = 0;
+    for (;;) {
+        if (!resume) { shuffle_row_warp(S, size, seed, me, cnt, step, lane); i = 0; }
+        if (lane == 0) {
+            bool rs = resume != 0;
             for (; i < size; i++) {
-                if (row[i] < K.NAt) continue;
-                if (!resume) { h = row[i] - K.NAt; s = 0; }
+                if (C.is_rec(S.row[i])) continue;
+                if (!rs) { h = S.row[i]; s = 0; }
                 for (; s < 3; s++) {
                     bool run;
-                    if (resume) { run = true; resume = false; }
+                    if (rs) { run = true; rs = false; }
                     else {
                         run = false;
-                        if (bridge_candidate(C, h, s)) { a1 = D.ligRec[h * 3 + s]; run = lig_site_misaligned(C, h, s, a1); }
+                        if (bridge_candidate(C, h, s)) { a1 = C.ligRec(h, s); run = lig_site_misaligned(C, h, s, a1); }
                     }
                     if (run) reseat_ligand(C, h, s, a1);
                 }
             }
-            shuffle_row(row, size, seed, me, cnt, step);                   // pass 3
+        }
+        __syncwarp();
+        shuffle_row_warp(S, size, seed, me, cnt, step, lane);               // pass 3
+        resume = 0;
+        if (lane == 0) {
             for (i = 0; i < size; i++) {
-                if (row[i] < K.NAt) continue;
-                h = row[i] - K.NAt;
+                if (C.is_rec(S.row[i])) continue;
+                h = S.row[i];
                 for (s = 0; s < 3; s++)
                     if (bridge_candidate(C, h, s)) {
-                        a1 = D.ligRec[h * 3 + s];
-                        if (lig_site_misaligned(C, h, s, a1)) { resume = true; break; }
+                        a1 = C.ligRec(h, s);
+                        if (lig_site_misaligned(C, h, s, a1)) { resume = 1; break; }
                     }
                 if (resume) break;
             }
-            if (!resume) break;
         }
-        for (int q = 0; q < size; q++) { int a = row[q]; if (a < K.NAt && resnap_rec_to_its_ligand(C, a)) D.movedFlag[a] = 1; }   // pass 4
-        for (int q = 0; q < size; q++) {                                                                                        // pass 5
-            int a = row[q];
-            if (a < K.NAt && D.recLig[a] >= 0 && D.recCis[a] >= 0 && D.recLig[D.recCis[a]] < 0) resnap_cis_partner(C, a, D.recCis[a]);
+        resume = __shfl_sync(0xffffffffu, resume, 0);
+        if (!resume) break;
+    }
+    __syncwarp();
+    for (int q = lane; q < size; q += 32) { const int a = S.row[q]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }   // pass 4
+    __syncwarp();
+    for (int q = lane; q < size; q += 32) {                                                                                              // pass 5
+        const int a = S.row[q];
+        if (C.is_rec(a) && C.recLig(a) >= 0 && C.recCis(a) >= 0 && C.recLig(C.recCis(a)) < 0) resnap_cis_partner(C, a, C.recCis(a));
+    }
+    __syncwarp();
+}
+
+// rigid move of one member given the unit's shift / wrap / rotation (main.cpp:993-1026, 1035-1070, 1103-1128 for one molecule)
+KD void shift_pose(double *p, bool isRec, double dx, double dy, bool subtract) {
+    const int n = isRec ? 3 : 8, st = isRec ? 2 : 3;
+    for (int q = 0; q < n; q++) {
+        p[q * st] = subtract ? sub(p[q * st], dx) : add(p[q * st], dx);
+        p[q * st + 1] = subtract ? sub(p[q * st + 1], dy) : add(p[q * st + 1], dy);
+    }
+}
+KD void rotate_pose(double *p, bool isRec, double cs, double ss, double cmx, double cmy, double cmz) {
+    const int n = isRec ? 3 : 8, st = isRec ? 2 : 3;
+    for (int q = 0; q < n; q++) {
+        double nx, ny; rotz(cs, ss, p[q * st], p[q * st + 1], cmx, cmy, nx, ny);
+        p[q * st] = nx; p[q * st + 1] = ny;
+        if (!isRec) p[q * st + 2] = add(sub(p[q * st + 2], cmz), cmz);        // 1*(z-c)+c, main.cpp:1123
+    }
+}
+
+__global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __grid_constant__ Args A) {
+    KARGS
+    __shared__ CxShared SH[CX_WARPS];
+    const uint64_t step = D.step64[0];
+    const Consts &K = cK;
+    const int ncx = D.scal[S_NCX];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * CX_WARPS + wib, nwarps = gridDim.x * CX_WARPS;
+    CxShared &S = SH[wib];
+    for (int ci = warp; ci < ncx; ci += nwarps) {
+        const int h0 = D.cxRoots[ci], rootGid = K.NAt + h0;
+        const int size = D.cxSize[h0];
+        const int *rowIn = D.members + D.cxOff[h0];
+        int *rowOut = D.rowWork + D.cxOff[h0];
+        const uint64_t seed = seed_of(cK, h0 / K.NB);
+        const uint32_t me = ref_id(K, D, rootGid);
+        const bool cached = size <= CX_CAP;
+        int nB = 0;
+        for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;          // (uniform across the warp, tiny)
+        const int nA = size - nB;
+        const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1), u2 = keyed_uniform(seed, me, 0, step, 2);
+        // ---- S2d rigid move (main.cpp:974-1131); complexes with >= 2 ligands have D = 0 but still draw ----
+        const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
+        const double phai = mul(mul(u1, 2.0), K.pai);
+        double sp, cp; sincos(phai, &sp, &cp);
+        const double shx = mul(amp, cp), shy = mul(amp, sp);
+        const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
+        double ss, cs; sincos(psai, &ss, &cs);
+        __syncwarp();
+        if (cached) {
+            // load: every lane its members (old pose + the bonds inside the complex as slots), translated by the shift
+            for (int i = lane; i < size; i += 32) {
+                const int m = rowIn[i];
+                S.gid[i] = m; S.row[i] = i; S.moved[i] = 0;
+                double *p = S.pose[i];
+                if (m < K.NAt) {
+                    const Rec r = load_rec(D.recC, D.recS2, D.recS3, m);
+                    p[0] = r.cx; p[1] = r.cy; p[2] = r.s2x; p[3] = r.s2y; p[4] = r.s3x; p[5] = r.s3y;
+                    const int l = D.recLig[m], c = D.recCis[m];
+                    S.lig[i] = l >= 0 ? (short)D.rowPos[K.NAt + l] : (short)-1; S.site[i] = (short)D.recSite[m]; S.cis[i] = c >= 0 ? (short)D.rowPos[c] : (short)-1;
+                } else {
+                    const double *q = D.lig + (size_t)(m - K.NAt) * 24;
+                    for (int t = 0; t < 24; t++) p[t] = q[t];
+                    for (int s = 0; s < 3; s++) { const int r = D.ligRec[(m - K.NAt) * 3 + s]; S.rec3[i][s] = r >= 0 ? (short)D.rowPos[r] : (short)-1; }
+                }
+                shift_pose(p, m < K.NAt, shx, shy, false);
+            }
+            __syncwarp();
+            double PBx = 0, PBy = 0;
+            if (lane == 0) {                                             // wrap centre: sum in row order (main.cpp:1007-1008, 1022-1023)
+                for (int i = 0; i < size; i++) { PBx = add(PBx, S.pose[i][0]); PBy = add(PBy, S.pose[i][1]); }
+                PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
+                PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
+            }
+            PBx = __shfl_sync(0xffffffffu, PBx, 0); PBy = __shfl_sync(0xffffffffu, PBy, 0);
+            for (int i = lane; i < size; i += 32) shift_pose(S.pose[i], S.gid[i] < K.NAt, PBx, PBy, true);
+            __syncwarp();
+            double cmx = 0, cmy = 0, cmz = 0;
+            if (lane == 0) {                                             // rotation centre: bead by bead in row order (main.cpp:1048-1068)
+                for (int i = 0; i < size; i++) {
+                    const double *p = S.pose[i];
+                    if (S.gid[i] < K.NAt) for (int j = 1; j <= 4; j++) { cmx = add(cmx, p[0]); cmy = add(cmy, p[1]); cmz = add(cmz, rec_bead_z(K, j)); }
+                    else for (int q = 0; q < 4; q++) { cmx = add(cmx, p[q * 3]); cmy = add(cmy, p[q * 3 + 1]); cmz = add(cmz, p[q * 3 + 2]); }
+                }
+                const double nbeads = (double)(4 * nA + 4 * nB);
+                cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
+            }
+            cmx = __shfl_sync(0xffffffffu, cmx, 0); cmy = __shfl_sync(0xffffffffu, cmy, 0); cmz = __shfl_sync(0xffffffffu, cmz, 0);
+            for (int i = lane; i < size; i += 32) rotate_pose(S.pose[i], S.gid[i] < K.NAt, cs, ss, cmx, cmy, cmz);
+            __syncwarp();
+            { CxLocal C{S, K, K.NAt}; align_complex_warp(C, S, size, nB, seed, me, step, lane); }     // the root ligand is slot 0
+            // store: new poses, the working row (cluster.log order), far flags + grid histogram, order keys
+            const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
+            for (int i = lane; i < size; i += 32) {
+                const int m = S.gid[i]; const double *p = S.pose[i];
+                rowOut[i] = S.gid[S.row[i]];
+                if (K.mode) D.ukey[m] = ckey;
+                if (m < K.NAt) {
+                    const Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]};
+                    store_rec(D.recCn, D.recS2n, D.recS3n, m, r);
+                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy);
+                } else {
+                    double *q = D.lign + (size_t)(m - K.NAt) * 24;
+                    for (int t = 0; t < 24; t++) q[t] = p[t];
+                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1]);
+                }
+            }
+        } else if (lane == 0) {
+            // complex larger than the cache: the same steps by one lane on global memory (handles = gids)
+            CxGlobal C{D, K, K.NAt};
+            double PBx = 0, PBy = 0;
+            for (int i = 0; i < size; i++) {
+                const int m = rowIn[i]; rowOut[i] = m; D.movedFlag[m] = 0;
+                if (m < K.NAt) { Rec r = load_rec(D.recC, D.recS2, D.recS3, m); shift_pose(&r.cx, true, shx, shy, false); C.put(m, r); PBx = add(PBx, r.cx); PBy = add(PBy, r.cy); }
+                else { Lig l; load_lig(D.lig, m - K.NAt, l); shift_pose(&l.p[0][0], false, shx, shy, false); C.put(m, l); PBx = add(PBx, l.p[0][0]); PBy = add(PBy, l.p[0][1]); }
+            }
+            PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
+            PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
+            double cmx = 0, cmy = 0, cmz = 0;
+            for (int i = 0; i < size; i++) {
+                const int m = rowOut[i];
+                if (m < K.NAt) {
+                    Rec r = C.rec(m); shift_pose(&r.cx, true, PBx, PBy, true); C.put(m, r);
+                    for (int j = 1; j <= 4; j++) { cmx = add(cmx, r.cx); cmy = add(cmy, r.cy); cmz = add(cmz, rec_bead_z(K, j)); }
+                } else {
+                    Lig l; C.lig(m, l); shift_pose(&l.p[0][0], false, PBx, PBy, true); C.put(m, l);
+                    for (int q = 0; q < 4; q++) { cmx = add(cmx, l.p[q][0]); cmy = add(cmy, l.p[q][1]); cmz = add(cmz, l.p[q][2]); }
+                }
+            }
+            const double nbeads = (double)(4 * nA + 4 * nB);
+            cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
+            for (int i = 0; i < size; i++) {
+                const int m = rowOut[i];
+                if (m < K.NAt) { Rec r = C.rec(m); rotate_pose(&r.cx, true, cs, ss, cmx, cmy, cmz); C.put(m, r); }
+                else { Lig l; C.lig(m, l); rotate_pose(&l.p[0][0], false, cs, ss, cmx, cmy, cmz); C.put(m, l); }
+            }
+            align_complex(C, rowOut, size, nB, rootGid, seed, me, step);
+            const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
+            for (int q = 0; q < size; q++) {
+                const int m = rowOut[q];
+                if (K.mode) D.ukey[m] = ckey;
+                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
+                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
+            }
         }
-    }
-    const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
-    for (int q = 0; q < size; q++) {
-        int m = row[q];
-        if (K.mode) D.ukey[m] = ckey;
-        if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
-        else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
-    }
-    D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0; D.pend[rootGid] = -1;
+        if (lane == 0) { D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0; D.pend[rootGid] = -1; }
+        __syncwarp();
     }
 }
 
@@ -1012,14 +1192,35 @@ __global__ void k_decide(const __grid_constant__ Args A) {
     else D.unk[atomicAdd(&D.scal[S_NUNK0], 1)] = gid;
 }
 
-// pass 2: the undecided units of list `from` in parallel; what is still undecided goes to the other list
+// evaluates unit `gid` with one WARP (lanes = members); returns (to every lane) true if still undecided, writes its state otherwise
+KD bool eval_unit_warp(const Consts &K, const Dev &D, int gid) {
+    const int lane = threadIdx.x & 31;
+    const int rep = replica_of_gid(K, gid);
+    const int uk = D.ukey[gid];
+    int nmem = 1, m2 = -1; const int *row = nullptr;
+    if (gid < K.NAt) { m2 = D.recCis[gid]; if (m2 >= 0) nmem = 2; }
+    else if (D.cxSize[gid - K.NAt] > 1) { nmem = D.cxSize[gid - K.NAt]; row = D.rowWork + D.cxOff[gid - K.NAt]; }
+    int res = 0;
+    for (int i = lane; i < nmem; i += 32) {
+        const int m = row ? row[i] : (i == 0 ? gid : m2);
+        Probe P; load_probe(K, D, m, P);
+        res |= test_member<false>(K, D, uk, m, P, rep);
+    }
+    res = __reduce_or_sync(0xffffffffu, res);
+    if (res & 1) { if (lane == 0) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); } return false; }
+    if (res & 2) return true;
+    if (lane == 0) D.unitState[gid] = U_ACCEPT;
+    return false;
+}
+// pass 2: the undecided units of list `from`, one warp each; what is still undecided goes to the other list
 __global__ void __launch_bounds__(128) k_resolve_list(const __grid_constant__ Args A, int from) {
     KARGS
     const int n = D.scal[S_NUNK0 + from];
     const int *in = D.unk + (size_t)from * cK.NT; int *out = D.unk + (size_t)(1 - from) * cK.NT;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int gid = in[i];
-        if (eval_unit<false>(cK, D, gid)) out[atomicAdd(&D.scal[S_NUNK0 + 1 - from], 1)] = gid;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        const int gid = in[i];
+        if (eval_unit_warp(cK, D, gid) && (threadIdx.x & 31) == 0) out[atomicAdd(&D.scal[S_NUNK0 + 1 - from], 1)] = gid;
     }
 }
 // final pass, one CTA: iterate over list `from` until everything is decided (the lowest undecided unit is always
@@ -1029,12 +1230,13 @@ __global__ void __launch_bounds__(256) k_resolve_finish(const __grid_constant__ 
     __shared__ int remaining;
     const int n = D.scal[S_NUNK0 + from];
     const int *in = D.unk + (size_t)from * cK.NT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int sweep = 0; sweep <= n; sweep++) {
         if (threadIdx.x == 0) remaining = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            int gid = in[i];
-            if (((volatile unsigned char *)D.unitState)[gid] == U_UNKNOWN && eval_unit<false>(cK, D, gid)) atomicAdd(&remaining, 1);
+        for (int i = warp; i < n; i += 8) {
+            const int gid = in[i];
+            if (((volatile unsigned char *)D.unitState)[gid] == U_UNKNOWN && eval_unit_warp(cK, D, gid) && lane == 0) atomicAdd(&remaining, 1);
         }
         __threadfence();
         __syncthreads();
