@@ -301,7 +301,10 @@ def main():
                            "timing": "host wall clock between barriers (halo refresh is host-orchestrated)" if decomp == "strips" else "CUDA events on the library stream",
                            "ms_per_mc_step": ms_max / args.steps / S},
                 "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                             "frac": achieved / peak if achieved else None, "traffic": None,
+                             "frac": achieved / peak if achieved else None,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one k_resolve_tiles launch on this workload, ncu --set full
+                             # (profiles/r01b_ncu_full_raw.csv): 154.8 + 5.7 MB
+                             "traffic": 160.4e6 if (top_name == "k_resolve_tiles" and M == 1250000) else None,
                              "alg_bytes_per_molecule": balg, "kernel_ms": top_ms / top_n, "kernel_share_of_step": top_ms / tot_prof,
                              "step_frac": value / world * B_ALG_STEP / 1e9 / peak,
                              "kernels_ms_per_mc_step": {n: round(v[0] / (3 * S), 4) for n, v in sorted(prof.items(), key=lambda kv: -kv[1][0]) if v[1]}},

@@ -141,10 +141,7 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
 }
 
 // free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
-#ifndef PSMINB
-#define PSMINB 1
-#endif
-__global__ void __launch_bounds__(128, PSMINB) k_propose_simple(const __grid_constant__ Args A) {
+__global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant__ Args A) {
     KARGS
     const uint64_t step = D.step64[0];
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
