@@ -249,14 +249,15 @@ def main():
     e2e_t = []
     if ds is None:
         rec, lig, rl, rs, rc = k.get_packed()
-        pin = [torch.from_numpy(a).pin_memory().numpy() for a in (rec, lig, rl, rs, rc)]
+        pin = [torch.from_numpy(a).pin_memory().numpy() for a in (rec, lig, rl, rs, rc)]          # inputs, pinned host memory
+        pout = [torch.from_numpy(a.copy()).pin_memory().numpy() for a in (rec, lig, rl, rs, rc)]  # results, pinned host memory
         h2d = sum(a.nbytes for a in pin); d2h = h2d + 64
         for it in range(2 + max(3, args.steps // 2)):
             barrier()
             t0 = time.perf_counter()
             k.set_packed(*pin, step_done=1000 + it * S)
             k.step(S)
-            k.get_packed()
+            k.get_packed(out=pout)
             k.series()
             dt = time.perf_counter() - t0
             if it >= 2:

@@ -44,6 +44,7 @@ struct kmc_handle {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int parity = 0, launches_per_step = 0;
     bool use_graph = true;
+    double *stageRec = nullptr; int *stageInt = nullptr;      // device staging of kmc_set_packed / kmc_get_packed
     // strips
     bool strip_on = false; double strip_W = 0, strip_lo = 0, strip_hi = 0; int64_t strip_refreshes = 0;
     HostLocal strip_local; std::vector<char> strip_msg[3];
@@ -243,7 +244,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(pairs, D.pairCap); A(unk, (size_t)2 * K.NT); A(unitRes, K.NT); A(pend, K.NT); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
 #undef A
-    ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 4) == cudaSuccess;
+    ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 6) == cudaSuccess;
     if (!ok) return fail(KMC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     // empty bond table
     ok = cudaMemset(D.recLig, 0xff, sizeof(int) * K.NAt) == cudaSuccess && cudaMemset(D.recSite, 0xff, sizeof(int) * K.NAt) == cudaSuccess &&
@@ -376,73 +377,93 @@ extern "C" int kmc_get_state(kmc_handle *h, int32_t rep, double *Rx, double *Ry,
     return KMC_OK;
 }
 
+static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+// ---- compact state exchange: the caller's buffers cross PCIe as they are (one copy per array, full speed from pinned memory);
+// (de)interleaving, bond-table construction and validation run on the device ----
+__global__ void k_pack_get(const __grid_constant__ Args A, double *recPose, int *site) {
+    KARGS
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cK.NAt) return;
+    if (recPose) {
+        const double2 c = D.recC[a], s2 = D.recS2[a], s3 = D.recS3[a];
+        double *o = recPose + (size_t)a * 6;
+        o[0] = c.x; o[1] = c.y; o[2] = s2.x; o[3] = s2.y; o[4] = s3.x; o[5] = s3.y;
+    }
+    if (site) { const int s = D.recSite[a]; site[a] = s >= 0 ? s + 2 : 0; }
+}
+// recPose: device copy of the caller's [n][6]; rl/rs/rc: device copies of the caller's bond words (or null = no bonds);
+// builds recC/S2/S3, recLig/recSite/recCis and ligRec (pre-set to -1); flags[0] |= 1 R-L bond invalid, |= 2 cis bond invalid
+__global__ void k_pack_set(const __grid_constant__ Args A, const double *recPose, const int *rl, const int *rs, const int *rc, int *flags) {
+    KARGS
+    const Consts &K = cK;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= K.NAt) return;
+    const double *o = recPose + (size_t)a * 6;
+    D.recC[a] = make_double2(o[0], o[1]); D.recS2[a] = make_double2(o[2], o[3]); D.recS3[a] = make_double2(o[4], o[5]);
+    int l = rl ? rl[a] : -1, st = rs ? rs[a] : 0, cp = rc ? rc[a] : -1;
+    if (l >= 0) {
+        if (l >= K.NBt || l / K.NB != a / K.NA || st < 2 || st > 4 || atomicCAS(&D.ligRec[l * 3 + st - 2], -1, a) != -1) { atomicOr(flags, 1); l = -1; }
+    } else l = -1;
+    if (cp >= 0) { if (cp >= K.NAt || cp == a || cp / K.NA != a / K.NA || rc[cp] != a) { atomicOr(flags, 2); cp = -1; } } else cp = -1;
+    D.recLig[a] = l; D.recSite[a] = l >= 0 ? st - 2 : -1; D.recCis[a] = cp;
+}
+
+static int stage_alloc(kmc_handle *h) {
+    if (h->stageRec) return KMC_OK;
+    bool ok = dalloc(h, &h->stageRec, (size_t)std::max(h->NAt, 1) * 6) == cudaSuccess && dalloc(h, &h->stageInt, (size_t)std::max(h->NAt, 1) * 3 + 4) == cudaSuccess;
+    if (!ok) { h->err = "staging allocation failed"; return KMC_ERR_CUDA; }
+    return KMC_OK;
+}
+
 extern "C" int kmc_get_packed(kmc_handle *h, double *rec_pose, double *lig_pose, int32_t *rec_lig, int32_t *rec_site, int32_t *rec_cis) {
     if (!h) return KMC_ERR_INVALID;
     int rc = select_device(h); if (rc) return rc;
-    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt;
-    CK(cudaStreamSynchronize(h->stream));
-    if (rec_pose) {
-        std::vector<double2> c(NAt), s2(NAt), s3(NAt);
-        CK(cudaMemcpy(c.data(), D.recC, sizeof(double2) * NAt, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(s2.data(), D.recS2, sizeof(double2) * NAt, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(s3.data(), D.recS3, sizeof(double2) * NAt, cudaMemcpyDeviceToHost));
-        for (int a = 0; a < NAt; a++) {
-            double *o = rec_pose + (size_t)a * 6;
-            o[0] = c[a].x; o[1] = c[a].y; o[2] = s2[a].x; o[3] = s2[a].y; o[4] = s3[a].x; o[5] = s3[a].y;
-        }
+    rc = stage_alloc(h); if (rc) return rc;
+    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt; cudaStream_t st = h->stream;
+    const Args A{D, h->K};
+    if (rec_pose || rec_site) {
+        LAUNCH(KID_SERIES, (k_pack_get<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, rec_pose ? h->stageRec : nullptr, rec_site ? h->stageInt : nullptr)));
+        if (rec_pose) CK(cudaMemcpyAsync(rec_pose, h->stageRec, sizeof(double) * 6 * (size_t)NAt, cudaMemcpyDeviceToHost, st));
+        if (rec_site) CK(cudaMemcpyAsync(rec_site, h->stageInt, sizeof(int) * NAt, cudaMemcpyDeviceToHost, st));
     }
-    if (lig_pose) CK(cudaMemcpy(lig_pose, D.lig, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyDeviceToHost));
-    if (rec_lig) CK(cudaMemcpy(rec_lig, D.recLig, sizeof(int) * NAt, cudaMemcpyDeviceToHost));
-    if (rec_site) {
-        CK(cudaMemcpy(rec_site, D.recSite, sizeof(int) * NAt, cudaMemcpyDeviceToHost));
-        for (int a = 0; a < NAt; a++) rec_site[a] = rec_site[a] >= 0 ? rec_site[a] + 2 : 0;
-    }
-    if (rec_cis) CK(cudaMemcpy(rec_cis, D.recCis, sizeof(int) * NAt, cudaMemcpyDeviceToHost));
+    if (lig_pose) CK(cudaMemcpyAsync(lig_pose, D.lig, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyDeviceToHost, st));
+    if (rec_lig) CK(cudaMemcpyAsync(rec_lig, D.recLig, sizeof(int) * NAt, cudaMemcpyDeviceToHost, st));
+    if (rec_cis) CK(cudaMemcpyAsync(rec_cis, D.recCis, sizeof(int) * NAt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return KMC_OK;
 }
 
 extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const double *lig_pose, const int32_t *rec_lig,
                               const int32_t *rec_site, const int32_t *rec_cis, int64_t step_done) {
     if (!h || !rec_pose || !lig_pose) { if (h) h->err = "kmc_set_packed: null pose"; return KMC_ERR_INVALID; }
+    if ((rec_lig != nullptr) != (rec_site != nullptr)) { h->err = "kmc_set_packed: rec_lig and rec_site go together"; return KMC_ERR_INVALID; }
     int rc = select_device(h); if (rc) return rc;
-    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt, NA = h->NA, NB = h->NB;
-    std::vector<double2> c(NAt), s2(NAt), s3(NAt);
-    for (int a = 0; a < NAt; a++) {
-        const double *o = rec_pose + (size_t)a * 6;
-        c[a] = make_double2(o[0], o[1]); s2[a] = make_double2(o[2], o[3]); s3[a] = make_double2(o[4], o[5]);
-    }
-    std::vector<int> rl(NAt, -1), rs(NAt, -1), rcis(NAt, -1), lr((size_t)NBt * 3, -1);
-    for (int a = 0; a < NAt; a++) {
-        int l = rec_lig ? rec_lig[a] : -1, st = rec_site ? rec_site[a] : 0, cp = rec_cis ? rec_cis[a] : -1;
-        if (l >= 0) {
-            if (l >= NBt || l / NB != a / NA || st < 2 || st > 4 || lr[(size_t)l * 3 + st - 2] >= 0) { h->err = "kmc_set_packed: bad R-L bond at receptor " + std::to_string(a); return KMC_ERR_STATE; }
-            rl[a] = l; rs[a] = st - 2; lr[(size_t)l * 3 + st - 2] = a;
-        }
-        if (cp >= 0) {
-            if (cp >= NAt || cp == a || cp / NA != a / NA || !rec_cis || rec_cis[cp] != a) { h->err = "kmc_set_packed: bad cis bond at receptor " + std::to_string(a); return KMC_ERR_STATE; }
-            rcis[a] = cp;
-        }
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(D.recC, c.data(), sizeof(double2) * NAt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.recS2, s2.data(), sizeof(double2) * NAt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.recS3, s3.data(), sizeof(double2) * NAt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.lig, lig_pose, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.recLig, rl.data(), sizeof(int) * NAt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.recSite, rs.data(), sizeof(int) * NAt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.recCis, rcis.data(), sizeof(int) * NAt, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(D.ligRec, lr.data(), sizeof(int) * 3 * (size_t)NBt, cudaMemcpyHostToDevice));
-    int one = 1;
-    CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
+    rc = stage_alloc(h); if (rc) return rc;
+    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt; cudaStream_t st = h->stream;
+    int *dl = h->stageInt, *ds = h->stageInt + NAt, *dc = h->stageInt + 2 * (size_t)NAt, *dflag = h->stageInt + 3 * (size_t)NAt;
+    CK(cudaMemcpyAsync(h->stageRec, rec_pose, sizeof(double) * 6 * (size_t)NAt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.lig, lig_pose, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyHostToDevice, st));
+    if (rec_lig) { CK(cudaMemcpyAsync(dl, rec_lig, sizeof(int) * NAt, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(ds, rec_site, sizeof(int) * NAt, cudaMemcpyHostToDevice, st)); }
+    if (rec_cis) CK(cudaMemcpyAsync(dc, rec_cis, sizeof(int) * NAt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(D.ligRec, 0xff, sizeof(int) * 3 * (size_t)NBt, st));
+    CK(cudaMemsetAsync(dflag, 0, sizeof(int), st));
+    const Args A{D, h->K};
+    LAUNCH(KID_SERIES, (k_pack_set<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, h->stageRec, rec_lig ? dl : nullptr, rec_lig ? ds : nullptr, rec_cis ? dc : nullptr, dflag)));
+    int one = 1, flags = 0;
+    unsigned long long s64 = (unsigned long long)step_done;
+    CK(cudaMemcpyAsync(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.step64, &s64, sizeof s64, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(&flags, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     h->step_done = step_done; h->stepped = false;
-    { unsigned long long s64 = (unsigned long long)step_done; CK(cudaMemcpy(D.step64, &s64, sizeof s64, cudaMemcpyHostToDevice)); }
+    if (flags) { h->err = std::string("kmc_set_packed: inconsistent bond table (") + ((flags & 1) ? "R-L bond " : "") + ((flags & 2) ? "cis bond " : "") + "invalid or asymmetric)"; return KMC_ERR_STATE; }
     return KMC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the sweep
 // ------------------------------------------------------------------------------------------------
-static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
 // first kernel of a step: advances the device-side step counter, resets the per-step scalars; complexes are rebuilt by
 // the gated kernels that follow only if the bond table changed (S_TOPO_DIRTY, cleared by k_propose_simple)
@@ -595,10 +616,11 @@ extern "C" int kmc_get_series(kmc_handle *h, int32_t rep, kmc_series *out) {
     if (rep < 0 || rep >= h->R) { h->err = "kmc_get_series: bad replica"; return KMC_ERR_INVALID; }
     int rc = select_device(h); if (rc) return rc;
     Dev &D = h->D;
-    CK(cudaMemsetAsync(h->d_series, 0, sizeof(int) * 4 * h->R, h->stream));
+    CK(cudaMemsetAsync(h->d_series, 0, sizeof(int) * 6 * h->R, h->stream));
     const Args A{D, h->K};
     cudaStream_t st = h->stream;
     LAUNCH(KID_SERIES, (k_series<<<nblk(std::max(h->NAt, 1), 256), 256, 0, st>>>(A, h->d_series)));
+    if (h->stepped) LAUNCH(KID_SERIES, (k_cx_stats<<<nblk(std::max(h->NBt, 1), 256), 256, 0, st>>>(A, h->d_series + 4 * h->R)));
     int s4[4], mx = 0;
     CK(cudaMemcpyAsync(s4, h->d_series + 4 * rep, sizeof s4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&mx, D.maxComplex + rep, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -607,9 +629,9 @@ extern "C" int kmc_get_series(kmc_handle *h, int32_t rep, kmc_series *out) {
     out->step = h->step_done; out->bond_num_rl = s4[0]; out->bond_num_mono_cis = s4[1]; out->bond_num_cis = s4[2];
     out->bond_num = s4[0] + s4[1] + s4[2]; out->max_complex = mx;
     if (h->stepped) {
-        HostComplexes hc; rc = fetch_complexes(h, hc); if (rc) return rc;
-        for (int b = rep * h->NB; b < (rep + 1) * h->NB; b++)
-            if (hc.unitOf[h->NAt + b] == h->NAt + b && hc.cxSize[b] > 1) { out->n_complexes++; out->n_in_complexes += hc.cxSize[b]; }
+        int cx[2] = {0, 0};
+        CK(cudaMemcpy(cx, h->d_series + 4 * h->R + 2 * rep, sizeof cx, cudaMemcpyDeviceToHost));
+        out->n_complexes = cx[0]; out->n_in_complexes = cx[1];
         if (out->n_complexes) out->cluster_size = (double)out->n_in_complexes / out->n_complexes;     // main.cpp:2200-2202
     }
     return KMC_OK;

@@ -1401,4 +1401,13 @@ __global__ void k_series(const __grid_constant__ Args A, int *out /*[R][4]: rl, 
     if (p > a) atomicAdd(&out[rep * 4 + ((D.recLig[a] >= 0 || D.recLig[p] >= 0) ? 2 : 1)], 1);
 }
 
+// tot_cluster_num / tot_proteins_in_cluster (main.cpp:976-977) from the complex table of the last step: out[rep*2 + {0,1}]
+__global__ void k_cx_stats(const __grid_constant__ Args A, int *out) {
+    KARGS
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nB_live(D) || D.unitOf[cK.NAt + h] != cK.NAt + h) return;
+    const int size = D.cxSize[h];
+    if (size > 1) { atomicAdd(&out[(h / cK.NB) * 2], 1); atomicAdd(&out[(h / cK.NB) * 2 + 1], size); }
+}
+
 }  // namespace kmc

@@ -247,10 +247,14 @@ class Kmc:
         self._ck(lib().kmc_get_state(self.h, replica, X.ctypes.data, Y.ctypes.data, Z.ctypes.data, st.ctypes.data, rn.ctypes.data))
         return np.stack([X, Y, Z], axis=-1), st, rn
 
-    def get_packed(self):
+    def get_packed(self, out=None):
+        """-> rec[n,6], lig[n,24], rec_lig, rec_site, rec_cis. `out` = the same five arrays preallocated (e.g. pinned host memory)."""
         r = self.p.n_replicas
-        rec = np.zeros((r * self.na, 6)); lig = np.zeros((r * self.nb, 24))
-        rl = np.zeros(r * self.na, dtype=np.int32); rs = np.zeros_like(rl); rc = np.zeros_like(rl)
+        if out is not None:
+            rec, lig, rl, rs, rc = out
+        else:
+            rec = np.zeros((r * self.na, 6)); lig = np.zeros((r * self.nb, 24))
+            rl = np.zeros(r * self.na, dtype=np.int32); rs = np.zeros_like(rl); rc = np.zeros_like(rl)
         self._ck(lib().kmc_get_packed(self.h, rec.ctypes.data, lig.ctypes.data, rl.ctypes.data, rs.ctypes.data, rc.ctypes.data))
         return rec, lig, rl, rs, rc
 
