@@ -142,3 +142,32 @@ def test_gpu_against_keyed_reference_directly(golden_dir):
         assert "%016x" % refio.fnv1a64(rn, st) == fr["hash_bonds"], "bond table differs from the keyed reference at step %d" % done
         s = k.series()
         assert (s["bond_num"], s["bond_num_rl"], s["bond_num_cis"], s["bond_num_mono_cis"]) == (fr["bond_num"], fr["bond_num_rl"], fr["bond_num_cis"], fr["bond_num_mono_cis"])
+
+
+def test_errors_are_reported_not_swallowed():
+    """bad input must come back as an error code with a message (the reference checks nothing)"""
+    k = kmc_b200.Kmc(kmc_b200.default_params())
+    k.init_random(seed=1)
+    rec, lig, rl, rs, rc = k.get_packed()
+    bad_rl, bad_rs = rl.copy(), rs.copy()
+    bad_rl[0], bad_rs[0] = 3, 2
+    bad_rl[1], bad_rs[1] = 3, 2                      # two receptors on the same ligand site
+    with pytest.raises(kmc_b200.KmcError, match="R-L bond"):
+        k.set_packed(rec, lig, bad_rl, bad_rs, rc)
+    bad_rc = rc.copy(); bad_rc[5] = 7                # cis partner that does not point back
+    with pytest.raises(kmc_b200.KmcError, match="cis bond"):
+        k.set_packed(rec, lig, rl, rs, bad_rc)
+    R, st, rn = k.get_state()
+    R2 = R.copy(); R2[3, 2, 1, 0] += 1.0             # receptor beads no longer stacked
+    with pytest.raises(kmc_b200.KmcError, match="stack"):
+        k.set_state(R2, st, rn)
+    rn2 = rn.copy(); rn2[1, 2] = 151                 # half a bond
+    with pytest.raises(kmc_b200.KmcError, match="bond"):
+        k.set_state(R, st, rn2)
+    with pytest.raises(kmc_b200.KmcError):
+        kmc_b200.Kmc(kmc_b200.default_params(n_replicas=0))
+    with pytest.raises(kmc_b200.KmcError):
+        kmc_b200.Kmc(kmc_b200.default_params(mode=7))
+    k.set_packed(rec, lig, rl, rs, rc)               # and the handle is still usable afterwards
+    k.step(3)
+    assert k.series()["step"] == 3

@@ -21,7 +21,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 na, nb, regime, seed, steps, every = 60000, 20000, "hot", 5, int(os.environ.get("STEPS", "96")), 4
-L = 52000.0
+na, nb = (90000, 30000) if int(os.environ.get("WORLD_SIZE", "1")) > 2 else (na, nb)
+L = 52000.0 if na == 60000 else 78000.0
 box = (L, L, 400.0)
 mk = lambda cap_a, cap_b: apply_regime(kmc_b200.default_params(box=box, n_receptor=cap_a, n_ligand=cap_b, seed=seed, device=local), regime)
 # every rank builds the same global start state (deterministic initialiser) and, for the check, the single-GPU answer
