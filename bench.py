@@ -4,7 +4,8 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--molecules M] [--mc-steps S] [--impl reference]
 
 metric   molecule-moves/s = molecules x MC steps / seconds, whole job (all GPUs)
-"step"   one batch of S MC steps of the sweep over the membrane patch resident on each GPU
+"step"   one batch of S (default 100) MC steps of the sweep over the membrane resident on the GPUs: state in, S steps, state and
+         records out (the reference's own batch is 5000 steps between two output records)
 workload per GPU a membrane patch of M molecules (3:1 receptors:ligands, default densities and parameters,
          fresh non-overlapping random start), default M = 1.25e6 = the per-GPU share of the 1e7-molecule
          membrane of BASELINE.json configs[4] on 8 GPUs; working set (> 400 MB incl. neighbour grid) exceeds
@@ -127,7 +128,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--molecules", type=int, default=1250000, help="molecules per GPU (3:1 receptors:ligands)")
-    ap.add_argument("--mc-steps", type=int, default=20, help="MC steps per bench step")
+    ap.add_argument("--mc-steps", type=int, default=100, help="MC steps per bench step (the reference writes its records every 5000 steps: main.cpp:2206)")
     ap.add_argument("--ref-mc-steps", type=int, default=100)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--seed", type=int, default=1)

@@ -40,6 +40,7 @@ struct Dev {
     int *bfsMark;
     int *rowPos;                           // [NT] position of a complex member in its breadth-first member list
     unsigned char *unitState, *farFlag, *movedFlag;
+    double *nrec;                          // [NT][6] neighbour record per molecule: centre old xy, new xy, {gid, unit key, flags, -}
     // neighbour grid
     int *cellCount, *cellStart, *scanTmp;  // [ncell+1]
     int *sorted;                           // [2*NT] entries gid | ghost bit

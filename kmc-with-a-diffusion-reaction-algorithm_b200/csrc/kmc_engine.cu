@@ -233,7 +233,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(ufParent, K.NT); A(unitOf, K.NT);
     if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
     A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT); A(rowPos, K.NT);
-    A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT);
+    A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT); A(nrec, (size_t)6 * K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
     A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
     choose_tiles(h);

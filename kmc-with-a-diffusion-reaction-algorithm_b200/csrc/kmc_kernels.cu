@@ -125,12 +125,20 @@ KD int unit_key(const Consts &K, int head, double hx, double hy) {
 // ------------------------------------------------------------------------------------------------
 KD uint64_t seed_of(const Consts &cK, int replica) { return cK.seed + (uint64_t)replica; }
 
+#define F_FAR 1
+#define F_GHOST 2
+#define F_FREE_RL 4      // receptor: no ligand bound / ligand: at least one free site
+#define F_FREE_CIS 8
 // called once per molecule per step by whoever computed its proposal: far-mover flag + the counting-sort histogram of the
 // neighbour grid (entry in the cell of the OLD centre; a far mover gets a second, ghost entry in the cell of its proposal)
-KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny) {
+// also the 48-byte neighbour record of the molecule (centre old/new, unit key, far/free flags): what the tile kernel stages
+KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, int ukey, int freeFlags) {
     const double dx = nx - ox, dy = ny - oy;
     const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
     D.farFlag[gid] = far ? 1 : 0;
+    double2 *nr = reinterpret_cast<double2 *>(D.nrec) + (size_t)gid * 3;
+    nr[0] = make_double2(ox, oy); nr[1] = make_double2(nx, ny);
+    reinterpret_cast<int4 *>(nr)[2] = make_int4(gid, ukey, freeFlags | (far ? F_FAR : 0), 0);
     const int rep = replica_of_gid(cK, gid);
     D.molSlot[gid] = atomicAdd(&D.cellCount[cell_of(cK, rep, ox, oy)], 1);
     if (far) {
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             rotz(cs, ss, t.s2x, t.s2y, t.cx, t.cy, n.s2x, n.s2y);
             rotz(cs, ss, t.s3x, t.s3y, t.cx, t.cy, n.s3x, n.s3y);
             store_rec(D.recCn, D.recS2n, D.recS3n, a, n);
-            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy);
+            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL | F_FREE_CIS);
             if (K.mode) D.ukey[a] = unit_key(K, a, ra.cx, ra.cy);
         } else {
             // ---- S2b: this receptor is the lower index of a ligand-free cis pair ----
@@ -204,8 +212,8 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             if (cis_misaligned(K, na, nb)) snap_cis(K, nb, na);          // "relax", main.cpp:770-799
             store_rec(D.recCn, D.recS2n, D.recS3n, a, na);
             store_rec(D.recCn, D.recS2n, D.recS3n, p, nb);
-            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy);
-            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy);
+            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL);
+            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL);
             if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
         D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
         for (int q = 0; q < 8; q++) rot3_about(R3, l.p[q], c, n.p[q]);
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
         store_lig(D.lign, h, n);
-        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1]);
+        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], unit_key(K, gid, ox, oy), F_FREE_RL);
         if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
         D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
     }
@@ -598,11 +606,11 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 if (m < K.NAt) {
                     const Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]};
                     store_rec(D.recCn, D.recS2n, D.recS3n, m, r);
-                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy);
+                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0));
                 } else {
                     double *q = D.lign + (size_t)(m - K.NAt) * 24;
                     for (int t = 0; t < 24; t++) q[t] = p[t];
-                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1]);
+                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0);
                 }
             }
         } else if (lane == 0) {
@@ -639,8 +647,8 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
             for (int q = 0; q < size; q++) {
                 const int m = rowOut[q];
                 if (K.mode) D.ukey[m] = ckey;
-                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y); }
-                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], n[0], n[1]); }
+                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0)); }
+                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0); }
             }
         }
         if (lane == 0) { D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0; D.pend[rootGid] = -1; }
@@ -900,31 +908,16 @@ template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) 
 #ifndef TCAP
 #define TCAP 384
 #endif
-#define F_FAR 1
-#define F_GHOST 2
-#define F_FREE_RL 4      // receptor: no ligand bound / ligand: at least one free site
-#define F_FREE_CIS 8
 
 struct TileRec { double ox, oy, nx, ny; int gid, unit; int flg; };
 
 KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
-    TileRec r;
     const int v = entry & ~GHOST_BIT;
-    r.gid = v; r.unit = D.ukey[v];
-    int f = (D.farFlag[v] ? F_FAR : 0) | ((entry & GHOST_BIT) ? F_GHOST : 0);
-    if (v < K.NAt) {
-        double2 o = D.recC[v], n = D.recCn[v];
-        r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y;
-        if (D.recLig[v] < 0) f |= F_FREE_RL;
-        if (D.recCis[v] < 0) f |= F_FREE_CIS;
-    } else {
-        const int h = v - K.NAt;
-        const double *o = D.lig + (size_t)h * 24, *n = D.lign + (size_t)h * 24;
-        r.ox = o[0]; r.oy = o[1]; r.nx = n[0]; r.ny = n[1];
-        const int *occ = D.ligRec + (size_t)h * 3;
-        if (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) f |= F_FREE_RL;
-    }
-    r.flg = f;
+    const double2 *nr = reinterpret_cast<const double2 *>(D.nrec) + (size_t)v * 3;
+    const double2 o = nr[0], n = nr[1];
+    const int4 w = reinterpret_cast<const int4 *>(nr)[2];
+    TileRec r;
+    r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y; r.gid = v; r.unit = w.y; r.flg = w.z | ((entry & GHOST_BIT) ? F_GHOST : 0);
     return r;
 }
 
