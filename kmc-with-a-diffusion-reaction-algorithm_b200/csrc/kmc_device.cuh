@@ -14,6 +14,7 @@ enum Scalar {
     S_NCAND_RL, S_NCAND_CIS,
     S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
     S_OVERFLOW,           // a device buffer overflowed (bitmask)
+    S_NSURV,              // pairs in surv[] this step
     S_NA_LIVE, S_NB_LIVE, // molecules actually present in the receptor / ligand blocks (<= NAt / NBt; strips change them)
     S_COUNT = 16
 };
@@ -44,6 +45,9 @@ struct Dev {
     // neighbour grid
     int *cellCount, *cellStart, *scanTmp;  // [ncell+1]
     int *sorted;                           // [2*NT] entries gid | ghost bit
+    float2 *scen;                          // [2*NT] fp32 centre each entry stands for (old centre; proposed centre for a ghost), cell-sorted like `sorted`
+    int *scell;                            // [2*NT] cell of each entry
+    int2 *surv; int survCap;               // pairs that passed the distance cut of k_cells_cut (probe entry, neighbour entry)
     int *molSlot;                          // [NT]
     int4 *farList;                         // [NT] (gid, cell, slot, -)
     // reaction candidates (successful draws only)

@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 20
+#define KMC_NKERNELS 21
 
 #include <algorithm>
 #include <cmath>
@@ -41,6 +41,7 @@ struct kmc_handle {
     std::vector<void *> allocs;
     int *d_series = nullptr;
     int scanBlocks = 0, nTiles = 0;
+    bool useCells = false;      // pass 1 of the resolve: thread-per-entry kernel (sparse cells) instead of the tile kernel
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int parity = 0, launches_per_step = 0;
     bool use_graph = true;
@@ -62,10 +63,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_simple",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_decide", "k_resolve_list", "k_resolve_finish", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series"};
+    "k_resolve_tiles", "k_decide", "k_resolve_list", "k_resolve_finish", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series", "k_pairs_eval"};
 enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_DECIDE, KID_RESOLVE_LIST, KID_RESOLVE_FINISH,
-       KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES };
+       KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES, KID_PAIRS_EVAL };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -172,6 +173,8 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
     K.ncx = (int)ceil((P.box[0] + 2 * edge) / edge); K.ncy = (int)ceil((P.box[1] + 2 * edge) / edge);
     K.cellInv = 1.0 / edge;
+    const float maxc = (float)(std::max(P.box[0], P.box[1]) + 2 * edge);
+    K.cutMargin = 0.05f + 2 * (nextafterf(maxc, INFINITY) - maxc);
 }
 
 static void strip_dev_free(kmc_handle *h);
@@ -186,6 +189,9 @@ static void choose_tiles(kmc_handle *h) {
     if (const char *o = getenv("KMC_TILE_EDGE")) { int v = atoi(o); if (v >= 1 && v <= TS) ts = v; }
     K.tileEdge = std::min(ts, TS);
     h->nTiles = K.R * ((K.ncx + K.tileEdge - 1) / K.tileEdge) * ((K.ncy + K.tileEdge - 1) / K.tileEdge);
+    // sparse cells (the reference's own density: ~0.4 molecules per cell): no staging, one thread per grid entry
+    h->useCells = perCell <= 2.0;
+    if (const char *o = getenv("KMC_RESOLVE")) h->useCells = !strcmp(o, "cells");
 }
 
 extern "C" void kmc_destroy(kmc_handle *h) {
@@ -238,7 +244,8 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
     choose_tiles(h);
     A(scanTmp, (size_t)h->scanBlocks + 1);
-    A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT); A(farList, K.NT);
+    A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT);
+    if (h->useCells) { D.survCap = 4 * K.NT + 4096; A(scen, (size_t)2 * K.NT); A(scell, (size_t)2 * K.NT); A(surv, (size_t)D.survCap); } A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
     A(pairs, D.pairCap); A(unk, (size_t)2 * K.NT); A(unitRes, K.NT); A(pend, K.NT); A(step64, 1);
@@ -470,7 +477,7 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 __global__ void k_step_begin(const __grid_constant__ Args A) {
     KARGS
     D.step64[0] += 1;
-    D.scal[S_NFAR] = 0; D.scal[S_NUNK0] = 0; D.scal[S_NUNK1] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+    D.scal[S_NFAR] = 0; D.scal[S_NUNK0] = 0; D.scal[S_NUNK1] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSURV] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
 }
 
@@ -494,7 +501,10 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
     // S2g: tile pass over all molecules (+ reaction-pair pre-selection), settle, then the (rare) dependency chains in order
     const int gl = std::min(nblk(NT, B), 148 * 8);
-    LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
+    if (h->useCells) {
+        LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
+        LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PTHREADS), 148 * 8 * 8), PTHREADS, 0, st>>>(A)));
+    } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<std::min(gl, 148 * 4), B, 0, st>>>(A, 0)));
     LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));
@@ -590,7 +600,7 @@ extern "C" int kmc_profile_get(kmc_handle *h, int32_t idx, const char **name, do
     if (idx >= KMC_NKERNELS) return 1;
     CK(cudaSetDevice(h->P.device));
     harvest(h, true);
-    if (name) *name = g_kernel_names[idx];
+    if (name) *name = (idx == KID_RESOLVE && h->useCells) ? "k_cells_cut" : g_kernel_names[idx];
     if (total_ms) *total_ms = h->kms[idx];
     if (launches) *launches = h->kcount[idx];
     return KMC_OK;

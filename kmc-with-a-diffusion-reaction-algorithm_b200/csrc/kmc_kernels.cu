@@ -667,13 +667,21 @@ KD void centre_of(const Consts &cK, const Dev &D, int gid, bool nxt, double &x, 
 __global__ void k_grid_scatter(const __grid_constant__ Args A) {
     KARGS
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool cells = D.scen != nullptr;         // the thread-per-entry resolve wants the centre and the cell next to each entry
     if (gid_live(cK, D, gid)) {
         int rep = replica_of_gid(cK, gid);
         double x, y; centre_of(cK, D, gid, false, x, y);
         int c = cell_of(cK, rep, x, y);
-        D.sorted[D.cellStart[c] + D.molSlot[gid]] = gid;
+        const int e = D.cellStart[c] + D.molSlot[gid];
+        D.sorted[e] = gid;
+        if (cells) { D.scen[e] = make_float2((float)x, (float)y); D.scell[e] = c; }
     }
-    if (gid < D.scal[S_NFAR]) { int4 f = D.farList[gid]; D.sorted[D.cellStart[f.y] + f.z] = f.x | GHOST_BIT; }
+    if (gid < D.scal[S_NFAR]) {
+        int4 f = D.farList[gid];
+        const int e = D.cellStart[f.y] + f.z;
+        D.sorted[e] = f.x | GHOST_BIT;
+        if (cells) { double x, y; centre_of(cK, D, f.x, true, x, y); D.scen[e] = make_float2((float)x, (float)y); D.scell[e] = f.y; }
+    }
 }
 // exclusive scan of cellCount into cellStart in three phases (tile sums, scan of the sums, per-tile scan). Arrays are padded
 // to a multiple of SCAN_TILE; 8 consecutive ints per thread (two int4), warp shuffles, one shared word per warp. The last
@@ -964,7 +972,32 @@ KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
 // probe against one neighbour entry that survived the distance cut: S3 pre-selection + overlap classification.
 // returns bit0 definite overlap, bit1 overlap with exactly one pose of an earlier (still undecided) unit; in that case
 // *conf = that unit (bit 30 set if the overlapping pose is its NEW one)
-KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf) {
+// S3 candidate pairs found by a CTA are collected in shared memory and appended to D.pairs with ONE atomicAdd per CTA
+// (a per-pair atomicAdd on the single global counter serialises ~1e5 atomics per step at the L2)
+struct PairSink { unsigned long long *buf; int *cnt; int cap; };
+KD void append_pair_global(const Dev &D, unsigned long long pr) {
+    int p = atomicAdd(&D.scal[S_NPAIR], 1);
+    if (p < D.pairCap) D.pairs[p] = pr;
+    else atomicOr(&D.scal[S_OVERFLOW], 4);
+}
+KD void sink_pair(const Dev &D, const PairSink &ps, unsigned long long pr) {
+    const int i = atomicAdd(ps.cnt, 1);
+    if (i < ps.cap) ps.buf[i] = pr; else append_pair_global(D, pr);
+}
+// all threads of the CTA, after a __syncthreads() that follows the last sink_pair; `base` is a shared scratch word
+KD void flush_pairs(const Dev &D, const PairSink &ps, int *base) {
+    const int n = min(*ps.cnt, ps.cap);
+    if (threadIdx.x == 0 && n > 0) *base = atomicAdd(&D.scal[S_NPAIR], n);
+    __syncthreads();
+    if (n > 0) {
+        const int b = *base;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (b + i < D.pairCap) D.pairs[b + i] = ps.buf[i];
+            else atomicOr(&D.scal[S_OVERFLOW], 4);
+        }
+    }
+}
+KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf, const PairSink &ps) {
     const int v = o.gid;
     if (v == c.m) return 0;                              // the other (old/ghost) entry of the probe itself
     const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
@@ -976,11 +1009,7 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
             double d2 = fmin((vx - c.fax) * (vx - c.fax) + (vy - c.fay) * (vy - c.fay), (vx - c.fbx) * (vx - c.fbx) + (vy - c.fby) * (vy - c.fby));
             if (!vghost && !vfar)
                 d2 = fmin(d2, fmin((o.nx - c.fax) * (o.nx - c.fax) + (o.ny - c.fay) * (o.ny - c.fay), (o.nx - c.fbx) * (o.nx - c.fbx) + (o.ny - c.fby) * (o.ny - c.fby)));
-            if (d2 <= reach * reach) {
-                int p = atomicAdd(&D.scal[S_NPAIR], 1);
-                if (p < D.pairCap) D.pairs[p] = ((unsigned long long)c.m << 32) | (unsigned)v;
-                else atomicOr(&D.scal[S_OVERFLOW], 4);
-            }
+            if (d2 <= reach * reach) sink_pair(D, ps, ((unsigned long long)c.m << 32) | (unsigned)v);
         }
     }
     if (c.pairsOnly) return 0;
@@ -1018,12 +1047,16 @@ KD void publish(const Dev &D, int ukey, int res, int conf) {
 #ifndef TMINB
 #define TMINB 8
 #endif
+#define TPAIRS 128
 __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
     __shared__ TileSmem S;
     __shared__ unsigned int surv[NSURV];          // (staged index of probe << 16) | staged index of neighbour
     __shared__ int nsurv;
+    __shared__ unsigned long long pbuf[TPAIRS];
+    __shared__ int pcnt, pbase;
+    const PairSink ps = {pbuf, &pcnt, TPAIRS};
     const int ts = K.tileEdge;        // tile edge in cells (<= TS), chosen from the mean cell occupancy so that a window fits the staging buffers
     const int ntx = (K.ncx + ts - 1) / ts, nty = (K.ncy + ts - 1) / ts;
     int b = blockIdx.x;
@@ -1054,7 +1087,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
         // interior rows are window rows y0-wy0 .. : store their prefix indexed by interior row
         const int ir = r - (y0 - wy0);
         if (ir >= 0 && ir <= nir) S.inBase[ir] = bI - lin;
-        if (r == 0) nsurv = 0;
+        if (r == 0) { nsurv = 0; pcnt = 0; }
     }
     __syncthreads();
     TICK();
@@ -1114,7 +1147,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
                     if (slot < NSURV) surv[slot] = ((unsigned)ime << 16) | (unsigned)i;
                     else {                                                  // survivor list full: evaluate in place
                         const ProbeCtx c = make_probe(K, staged(ime));
-                        int cf = -1; const int rr = pair_eval(K, D, c, staged(i), &cf);
+                        int cf = -1; const int rr = pair_eval(K, D, c, staged(i), &cf, ps);
                         publish(D, c.u, rr, cf);
                     }
                 }
@@ -1137,7 +1170,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
                     const bool g = o.flg & F_GHOST;
                     const double ex = (g ? o.nx : o.ox) - c.fax, ey = (g ? o.ny : o.oy) - c.fay;
                     if (ex * ex + ey * ey > cut2) continue;
-                    int cf = -1; const int rr = pair_eval(K, D, c, o, &cf);
+                    int cf = -1; const int rr = pair_eval(K, D, c, o, &cf, ps);
                     publish(D, c.u, rr, cf);
                 }
             }
@@ -1151,14 +1184,130 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
         const unsigned w = surv[s];
         const ProbeCtx c = make_probe(K, staged((int)(w >> 16)));
         int cf = -1;
-        const int rr = pair_eval(K, D, c, staged((int)(w & 0xffffu)), &cf);
+        const int rr = pair_eval(K, D, c, staged((int)(w & 0xffffu)), &cf, ps);
         publish(D, c.u, rr, cf);
     }
+    __syncthreads();
+    flush_pairs(D, ps, &pbase);
 #ifdef KMC_TILE_TIMING
     __syncthreads();
     TICK();
     if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) atomicAdd(&D.events[10 + i], (unsigned long long)(tq[i + 1] - tq[i])); atomicAdd(&D.events[15], 1ULL); }
 #endif
+}
+// S2g pass 1 for SPARSE membranes (a fraction of a molecule per cell, the reference's own density), two kernels, no staging.
+//
+// k_cells_cut: one thread per grid entry in cell-sorted order. The scatter leaves, next to `sorted`, an fp32 copy of the
+// centre every entry stands for (`scen`), so the distance cut touches only cell-sorted, contiguous data: the entry's own 12
+// bytes, the six row extents of its 3x3 cells (shared with the neighbouring threads through L1) and 12 bytes per candidate.
+// It is a light kernel (no fp64, few registers, full occupancy); pairs that survive the cut are collected per CTA and appended
+// to a global list with one atomicAdd per CTA.
+// k_pairs_eval: one thread per surviving (probe entry, neighbour entry) pair: the same pair_eval as the tile kernel, from the
+// per-molecule records -- full warps instead of the few survivor lanes of a fused kernel.
+// The tile kernel remains the path for crowded cells, where staging a window once pays for the many candidates per probe.
+#ifndef CTHREADS
+#define CTHREADS 256
+#endif
+#ifndef CSURV
+#define CSURV 1024
+#endif
+#ifndef CMINB
+#define CMINB 8
+#endif
+// classification of one surviving pair straight from the records (also the overflow path of k_cells_cut: not inlined there,
+// so the cut keeps its small register footprint)
+KD void eval_entry_pair(const Consts &K, const Dev &D, int entry, int en, const PairSink &ps) {
+    const ProbeCtx pc = make_probe(K, fetch_rec(K, D, entry));
+    int cf = -1;
+    const int rr = pair_eval(K, D, pc, fetch_rec(K, D, en), &cf, ps);
+    publish(D, pc.u, rr, cf);
+}
+__device__ __noinline__ void eval_entry_pair_slow(const Args &A, int entry, int en) {
+    const PairSink none = {nullptr, nullptr, 0};
+    eval_entry_pair(A.K, A.D, entry, en, none);
+}
+__global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    __shared__ int2 surv[CSURV];                  // (entry of the probe, entry of the neighbour), ghost bits included
+    __shared__ int nsurv, gbase;
+    const int total = __ldg(&D.cellStart[D.ncell]);
+    // cut radii, measured between the centres the two ENTRIES stand for: every pose of either molecule that matters here lies
+    // within one skin of its entry (proposal of a near mover around its old entry; a far mover has one entry per pose), so
+    // overlap reach + 2 skins and S3 reach + 2 skins bound every test pair_eval can make. fp32 with a margin that covers the
+    // rounding of the stored coordinates (K.cutMargin, from the box size).
+    const float mg = K.cutMargin, sk2 = 2 * (float)K.skin;
+    const float cRR = fmaxf((float)K.ovAA, (float)K.reachCis) + sk2 + mg, cRL = fmaxf((float)K.reachRL, (float)K.reachOn) + sk2 + mg,
+                cLR = (float)K.reachRL + sk2 + mg, cLL = (float)K.reachLL + sk2 + mg;
+    const float gx0 = (float)K.gx0, gy0 = (float)K.gy0, cinv = (float)K.cellInv;
+    const int *__restrict__ sorted = D.sorted;
+    const float2 *__restrict__ scen = D.scen;
+    for (int base = blockIdx.x * CTHREADS; base < total; base += gridDim.x * CTHREADS) {
+        if (threadIdx.x == 0) nsurv = 0;
+        __syncthreads();
+        const int e = base + threadIdx.x;
+        if (e < total) {
+            const int entry = __ldg(&sorted[e]);
+            const float2 w = __ldg(&scen[e]);                                   // centre this entry stands for (grid frame): cut centre
+            const int cell = __ldg(&D.scell[e]);                                // its cell (exact, from the scatter)
+            const bool prec = (entry & ~GHOST_BIT) < K.NAt;
+            const int crow = cell / K.ncx, cx = cell - crow * K.ncx;            // crow = replica * ncy + cy
+            const int cy = crow % K.ncy;
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, K.ncx - 1);
+            const int r0 = crow - (cy > 0 ? 1 : 0), r1 = crow + (cy < K.ncy - 1 ? 1 : 0);
+            int e0[3], e1[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int rr = min(r0 + r, r1);
+                const int *row = D.cellStart + (size_t)rr * K.ncx;
+                e0[r] = __ldg(row + x0); e1[r] = (r0 + r <= r1) ? __ldg(row + x1 + 1) : e0[r];
+            }
+            const float cR2 = prec ? cRR * cRR : cLR * cLR, cL2 = prec ? cRL * cRL : cLL * cLL;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                for (int i = e0[r]; i < e1[r]; i++) {
+                    const int en = __ldg(&sorted[i]);
+                    const float2 c = __ldg(&scen[i]);
+                    const float ex = c.x - w.x, ey = c.y - w.y;
+                    if (ex * ex + ey * ey > ((en & ~GHOST_BIT) < K.NAt ? cR2 : cL2) || i == e) continue;
+                    const int slot = atomicAdd(&nsurv, 1);
+                    if (slot < CSURV) surv[slot] = make_int2(entry, en);
+                    else eval_entry_pair_slow(A, entry, en);                    // CTA list full (crowded spot)
+                }
+        }
+        __syncthreads();
+        const int ns = min(nsurv, CSURV);
+        if (threadIdx.x == 0 && ns > 0) gbase = atomicAdd(&D.scal[S_NSURV], ns);
+        __syncthreads();
+        if (ns > 0) {
+            const int gb = gbase;
+            for (int s = threadIdx.x; s < ns; s += CTHREADS) {
+                if (gb + s < D.survCap) D.surv[gb + s] = surv[s];
+                else eval_entry_pair_slow(A, surv[s].x, surv[s].y);             // global list full
+            }
+        }
+        __syncthreads();
+    }
+}
+#ifndef PTHREADS
+#define PTHREADS 128
+#endif
+__global__ void __launch_bounds__(PTHREADS, 8) k_pairs_eval(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    __shared__ unsigned long long pbuf[PTHREADS];
+    __shared__ int pcnt, pbase;
+    const PairSink ps = {pbuf, &pcnt, PTHREADS};
+    const int ns = min(D.scal[S_NSURV], D.survCap);
+    for (int base = blockIdx.x * PTHREADS; base < ns; base += gridDim.x * PTHREADS) {
+        if (threadIdx.x == 0) pcnt = 0;
+        __syncthreads();
+        const int s = base + threadIdx.x;
+        if (s < ns) { const int2 w = D.surv[s]; eval_entry_pair(K, D, w.x, w.y, ps); }
+        __syncthreads();
+        flush_pairs(D, ps, &pbase);
+        __syncthreads();
+    }
 }
 // after the tile pass: settle every unit whose members found nothing or a definite overlap. A unit whose only finding is
 // one overlap with one pose of a single earlier unit is settled from that unit's own findings when those are conclusive;
