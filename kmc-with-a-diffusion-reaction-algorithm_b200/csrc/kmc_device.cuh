@@ -9,7 +9,7 @@ enum Scalar {
     S_MEMBER_CURSOR = 0,  // next free slot in members[]
     S_NCX,                // number of complexes (size > 1) in cxRoots[]
     S_NFAR,               // far movers this step
-    S_NUNK0, S_NUNK1,     // undecided units in list 0 / list 1 (ping-pong between resolve passes)
+    S_NPEND, S_SPARE1,    // pending findings of this step (pendList)
     S_NPAIR,              // pre-selected reaction pairs of this step
     S_NCAND_RL, S_NCAND_CIS,
     S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
@@ -40,7 +40,7 @@ struct Dev {
     int *members, *rowWork;                // member gids in BFS order / working copy permuted by the shuffles
     int *bfsMark;
     int *rowPos;                           // [NT] position of a complex member in its breadth-first member list
-    unsigned char *unitState, *farFlag, *movedFlag;
+    unsigned char *movedFlag;
     double *nrec;                          // [NT][6] neighbour record per molecule: centre old xy, new xy, {gid, unit key, flags, -}
     // neighbour grid
     int *cellCount, *cellStart, *scanTmp;  // [ncell+1]
@@ -54,9 +54,9 @@ struct Dev {
     unsigned long long *candRL, *candCis;
     int candCap;
     unsigned long long *pairs; int pairCap;   // (receptor, neighbour) pairs that may react this step
-    int *unk;                                 // [2][NT] undecided unit heads
-    int *pend;                                // [NT] single pending conflict of a unit: earlier unit | pose bit, -1 none
-    int *unitRes;                             // [NT] per unit head: bit0 definite overlap, bit1 overlap pending on an earlier unit
+    int *unitRes;                             // [NT] per unit head: 0 accepted, bit0 rejected (definite overlap), 2 = waits on pending findings
+    int *pendCnt;                             // [NT] per unit head: pending findings not yet settled
+    int2 *pendList; int pendCap;              // (unit head, earlier unit | bit30: overlap is with its NEW pose)
     unsigned long long *step64;               // [1] mc_time_step of the step being computed
     unsigned *refA, *refB;                    // reference (global, 1-based) ids of local receptors / ligands; null = a%NA+1, NA+h%NB+1
     int *scal;

@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 21
+#define KMC_NKERNELS 19
 
 #include <algorithm>
 #include <cmath>
@@ -63,9 +63,9 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_simple",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_decide", "k_resolve_list", "k_resolve_finish", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series", "k_pairs_eval"};
+    "k_resolve_tiles", "k_pend_resolve", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series", "k_pairs_eval"};
 enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
-       KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_DECIDE, KID_RESOLVE_LIST, KID_RESOLVE_FINISH,
+       KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
        KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES, KID_PAIRS_EVAL };
 
 static cudaEvent_t take_event(kmc_handle *h) {
@@ -239,7 +239,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(ufParent, K.NT); A(unitOf, K.NT);
     if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
     A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT); A(rowPos, K.NT);
-    A(unitState, K.NT); A(farFlag, K.NT); A(movedFlag, K.NT); A(nrec, (size_t)6 * K.NT);
+    A(movedFlag, K.NT); A(nrec, (size_t)6 * K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
     A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
     choose_tiles(h);
@@ -248,7 +248,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     if (h->useCells) { D.survCap = 4 * K.NT + 4096; A(scen, (size_t)2 * K.NT); A(scell, (size_t)2 * K.NT); A(surv, (size_t)D.survCap); } A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
-    A(pairs, D.pairCap); A(unk, (size_t)2 * K.NT); A(unitRes, K.NT); A(pend, K.NT); A(step64, 1);
+    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); D.pendCap = 2 * K.NT + 4096; A(pendList, D.pendCap); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
 #undef A
     ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 6) == cudaSuccess;
@@ -477,7 +477,7 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 __global__ void k_step_begin(const __grid_constant__ Args A) {
     KARGS
     D.step64[0] += 1;
-    D.scal[S_NFAR] = 0; D.scal[S_NUNK0] = 0; D.scal[S_NUNK1] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSURV] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+    D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSURV] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
 }
 
@@ -505,9 +505,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
         LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
         LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PTHREADS), 148 * 8 * 8), PTHREADS, 0, st>>>(A)));
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
-    LAUNCH(KID_DECIDE, (k_decide<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_RESOLVE_LIST, (k_resolve_list<<<std::min(gl, 148 * 4), B, 0, st>>>(A, 0)));
-    LAUNCH(KID_RESOLVE_FINISH, (k_resolve_finish<<<1, 256, 0, st>>>(A, 1)));
+    LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
     LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
     // S3
     LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<gl, B, 0, st>>>(A)));
@@ -553,7 +551,7 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
         }
         // S4: the new buffers become the committed state
         swap_buffers(h->D); h->parity ^= 1;
-        h->passes += 3; h->step_done++; h->stepped = true;
+        h->passes += 1; h->step_done++; h->stepped = true;
     }
     CK(cudaGetLastError());
     return KMC_OK;
@@ -692,13 +690,13 @@ extern "C" int kmc_get_accept(kmc_handle *h, int32_t rep, int32_t *accepted) {
     if (!h || !accepted) return KMC_ERR_INVALID;
     if (rep < 0 || rep >= h->R) { h->err = "kmc_get_accept: bad replica"; return KMC_ERR_INVALID; }
     int rc = select_device(h); if (rc) return rc;
-    std::vector<int> unitOf(h->NT); std::vector<unsigned char> st(h->NT);
+    std::vector<int> unitOf(h->NT), st(h->NT);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(unitOf.data(), h->D.unitOf, sizeof(int) * h->NT, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(st.data(), h->D.unitState, h->NT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st.data(), h->D.unitRes, sizeof(int) * h->NT, cudaMemcpyDeviceToHost));      // 0 = accepted, bit0 = reverted
     accepted[0] = 1;
-    for (int a = 0; a < h->NA; a++) accepted[a + 1] = st[unitOf[rep * h->NA + a]] == U_ACCEPT;
-    for (int b = 0; b < h->NB; b++) accepted[h->NA + 1 + b] = st[unitOf[h->NAt + rep * h->NB + b]] == U_ACCEPT;
+    for (int a = 0; a < h->NA; a++) accepted[a + 1] = st[unitOf[rep * h->NA + a]] == 0;
+    for (int b = 0; b < h->NB; b++) accepted[h->NA + 1 + b] = st[unitOf[h->NAt + rep * h->NB + b]] == 0;
     return KMC_OK;
 }
 

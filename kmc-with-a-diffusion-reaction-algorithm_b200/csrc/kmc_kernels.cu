@@ -5,7 +5,7 @@
 //                                                                                           the bond table changed)
 //            [propose]    k_propose_simple, k_propose_complex                              (S2a-S2f, 577-1732)
 //            [grid]       k_grid_count -> scan -> k_grid_scatter                           (cell list, new)
-//            [resolve]    k_resolve (repeated until no unit is undecided) -> k_restore     (S2g, 1759-1860 + ordering)
+//            [resolve]    k_cells_cut + k_pairs_eval | k_resolve_tiles -> k_pend_resolve -> k_restore   (S2g, 1759-1860 + ordering)
 //            [reactions]  k_react_candidates -> k_react_resolve -> k_dissociate            (S3, 1876-2141)
 //            pointer swap                                                                  (S4, 2164-2202)
 //
@@ -135,7 +135,6 @@ KD uint64_t seed_of(const Consts &cK, int replica) { return cK.seed + (uint64_t)
 KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, int ukey, int freeFlags) {
     const double dx = nx - ox, dy = ny - oy;
     const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
-    D.farFlag[gid] = far ? 1 : 0;
     double2 *nr = reinterpret_cast<double2 *>(D.nrec) + (size_t)gid * 3;
     nr[0] = make_double2(ox, oy); nr[1] = make_double2(nx, ny);
     reinterpret_cast<int4 *>(nr)[2] = make_int4(gid, ukey, freeFlags | (far ? F_FAR : 0), 0);
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL);
             if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
-        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
+        D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
     } else {
         const int h = gid - K.NAt;
         if (D.cxSize[h] > 1) return;             // complexes: k_propose_complex
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
         store_lig(D.lign, h, n);
         mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], unit_key(K, gid, ox, oy), F_FREE_RL);
         if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
-        D.unitState[gid] = U_UNKNOWN; D.unitRes[gid] = 0; D.pend[gid] = -1;
+        D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
     }
 }
 
@@ -651,7 +650,7 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0); }
             }
         }
-        if (lane == 0) { D.unitState[rootGid] = U_UNKNOWN; D.unitRes[rootGid] = 0; D.pend[rootGid] = -1; }
+        if (lane == 0) { D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0; }
         __syncwarp();
     }
 }
@@ -739,23 +738,6 @@ __global__ void __launch_bounds__(256) k_scan_down(int4 *in, const int *blockSum
 // S2g with ordering: decide accept/reject of every unit. The same neighbour walk also collects the (few) molecule
 // pairs that can possibly react in S3, so the reaction stage never walks the grid again.
 // ------------------------------------------------------------------------------------------------
-// a member of the unit under test at its PROPOSED pose: receptor = centre only, ligand = centre + three beads
-struct Probe { bool rec; double cx, cy; double b[3][3]; };
-
-template <class F> KD void for_cells3x3(const Consts &cK, int rep, double x, double y, const Dev &D, F f) {
-    int cx = (int)floor((hash_x(cK, x) - cK.gx0) * cK.cellInv), cy = (int)floor((y - cK.gy0) * cK.cellInv);
-    cx = min(max(cx, 0), cK.ncx - 1); cy = min(max(cy, 0), cK.ncy - 1);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, cK.ncx - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, cK.ncy - 1);
-    int e0[3], e1[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {                         // the three cells of a row are contiguous in `sorted`
-        int yy = min(y0 + r, y1), base = (rep * cK.ncy + yy) * cK.ncx;
-        e0[r] = __ldg(&D.cellStart[base + x0]); e1[r] = (y0 + r <= y1) ? __ldg(&D.cellStart[base + x1 + 1]) : e0[r];
-    }
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-        for (int e = e0[r]; e < e1[r]; e++) f(__ldg(&D.sorted[e]));
-}
 KD bool hit_rec_beads(const Consts &K, double ax, double ay, const double b[3][3]) {
     for (int j = 0; j < 3; j++) {
         double d2 = add(sq(sub(b[j][0], ax)), sq(sub(b[j][1], ay)));
@@ -775,127 +757,6 @@ KD void load_beads(const double *base, int h, double b[3][3]) {
 #pragma unroll
     for (int i = 0; i < 9; i++) (&b[0][0])[i] = q[i];
 }
-// does probe (proposed pose of member m) overlap molecule v taken at its old (nxt=false) or proposed pose?
-KD bool probe_hits(const Consts &K, const Dev &D, const Probe &P, int v, bool nxt) {
-    if (v < K.NAt) {
-        double2 c = nxt ? D.recCn[v] : D.recC[v];
-        if (P.rec) return hit_rec_rec(K, P.cx, P.cy, c.x, c.y);
-        double dx = c.x - P.cx, dy = c.y - P.cy;
-        if (dx * dx + dy * dy > K.reachRL * K.reachRL) return false;
-        return hit_rec_beads(K, c.x, c.y, P.b);
-    }
-    const double *base = nxt ? D.lign : D.lig;
-    const double *pc = base + (size_t)(v - K.NAt) * 24;
-    double dx = pc[0] - P.cx, dy = pc[1] - P.cy, r = P.rec ? K.reachRL : K.reachLL;
-    if (dx * dx + dy * dy > r * r) return false;
-    double ob[3][3]; load_beads(base, v - K.NAt, ob);
-    return P.rec ? hit_rec_beads(K, P.cx, P.cy, ob) : hit_beads_beads(K, ob, P.b);
-}
-
-
-// S3 pre-selection: receptor a (walked as probe) and neighbour v can only react if their FINAL centres come within
-// `reach`; each final centre is the old or the proposed one, so the minimum over those combinations is a safe bound.
-KD void maybe_pair(const Consts &K, const Dev &D, int a, bool aFreeRL, bool aFreeCis, double pax, double pay, double oax, double oay,
-                   int v, bool ghost, bool vfar) {
-    const bool lig = v >= K.NAt;
-    if (lig ? !aFreeRL : (!aFreeCis || v == a)) return;
-    const double reach = lig ? K.reachOn : K.reachCis;
-    double ovx, ovy, pvx, pvy;
-    centre_of(K, D, v, ghost, ovx, ovy);                          // the position this entry stands for
-    const double lim = reach + 2 * K.skin;
-    double d2 = min((ovx - pax) * (ovx - pax) + (ovy - pay) * (ovy - pay), (ovx - oax) * (ovx - oax) + (ovy - oay) * (ovy - oay));
-    if (d2 > lim * lim) return;                                   // cheap cut with the displacement skins
-    if (!ghost && !vfar) {
-        centre_of(K, D, v, true, pvx, pvy);
-        d2 = min(d2, min((pvx - pax) * (pvx - pax) + (pvy - pay) * (pvy - pay), (pvx - oax) * (pvx - oax) + (pvy - oay) * (pvy - oay)));
-    }
-    if (d2 > reach * reach) return;
-    if (lig) { const int *o = D.ligRec + (size_t)(v - K.NAt) * 3; if (o[0] >= 0 && o[1] >= 0 && o[2] >= 0) return; }
-    else if (D.recCis[v] >= 0) return;
-    int q = atomicAdd(&D.scal[S_NPAIR], 1);
-    if (q < D.pairCap) D.pairs[q] = ((unsigned long long)a << 32) | (unsigned)v;
-    else atomicOr(&D.scal[S_OVERFLOW], 4);
-}
-
-// one member against everything around it; returns flags: bit0 definite overlap, bit1 overlap depends on an undecided earlier unit
-template <bool PAIRS> KD int test_member(const Consts &cK, const Dev &D, int u, int m, const Probe &P, int rep) {
-    int res = 0;
-    bool aFreeRL = false, aFreeCis = false; double oax = 0, oay = 0;
-    if (PAIRS && P.rec) {
-        aFreeRL = D.recLig[m] < 0; aFreeCis = D.recCis[m] < 0;
-        double2 o = D.recC[m]; oax = o.x; oay = o.y;
-    }
-    const bool wantPairs = PAIRS && P.rec && (aFreeRL || aFreeCis);
-    for_cells3x3(cK, rep, P.cx, P.cy, D, [&](int e) {
-        const bool ghost = (e & GHOST_BIT) != 0;
-        const int v = e & ~GHOST_BIT;
-        if (v == m) return;
-        const int uv = D.ukey[v];
-        const bool far = D.farFlag[v] != 0;
-        if (wantPairs) maybe_pair(cK, D, m, aFreeRL, aFreeCis, P.cx, P.cy, oax, oay, v, ghost, far);
-        if (res & 1) return;
-        if (uv == u) {                                   // co-moving member: proposed pose, once (Q20)
-            if (ghost != far) return;
-            if (probe_hits(cK, D, P, v, true)) res |= 1;
-        } else if (!unit_before(uv, u)) {                // later unit: still at its old pose
-            if (!ghost && probe_hits(cK, D, P, v, false)) res |= 1;
-        } else {                                         // earlier unit: new pose if it was accepted
-            const unsigned char s = ((volatile unsigned char *)D.unitState)[uv & UNIT_MASK];
-            if (ghost) {
-                if (s != U_REJECT && probe_hits(cK, D, P, v, true)) res |= (s == U_ACCEPT) ? 1 : 2;
-            } else {
-                const bool hitOld = (s != U_ACCEPT) && probe_hits(cK, D, P, v, false);
-                const bool hitNew = (s != U_REJECT) && !far && probe_hits(cK, D, P, v, true);
-                if (s == U_ACCEPT) { if (hitNew) res |= 1; }
-                else if (s == U_REJECT) { if (hitOld) res |= 1; }
-                else if (hitOld && hitNew) res |= 1;
-                else if (hitOld || hitNew) res |= 2;
-            }
-        }
-    });
-    // a far mover that ends up rejected stays at its old place: its possible partners there are collected as well
-    if (wantPairs && D.farFlag[m])
-        for_cells3x3(cK, rep, oax, oay, D, [&](int e) {
-            const int v = e & ~GHOST_BIT;
-            if (v != m) maybe_pair(cK, D, m, aFreeRL, aFreeCis, P.cx, P.cy, oax, oay, v, (e & GHOST_BIT) != 0, D.farFlag[v] != 0);
-        });
-    return res;
-}
-
-KD void load_probe(const Consts &K, const Dev &D, int m, Probe &P) {
-    if (m < K.NAt) { double2 c = D.recCn[m]; P.rec = true; P.cx = c.x; P.cy = c.y; }
-    else {
-        const double *q = D.lign + (size_t)(m - K.NAt) * 24;
-        P.rec = false; P.cx = q[0]; P.cy = q[1];
-#pragma unroll
-        for (int i = 0; i < 9; i++) (&P.b[0][0])[i] = q[3 + i];
-    }
-}
-// evaluates unit `gid` (a head, currently undecided); writes its state if decidable; returns true if still undecided
-template <bool PAIRS> KD bool eval_unit(const Consts &K, const Dev &D, int gid) {
-    const int rep = replica_of_gid(K, gid);
-    const int uk = D.ukey[gid];                          // order key of this unit
-    int res = 0;
-    Probe P;
-    if (gid < K.NAt) {
-        load_probe(K, D, gid, P);
-        res |= test_member<PAIRS>(K, D, uk, gid, P, rep);
-        int p = D.recCis[gid];
-        if (p >= 0 && (PAIRS || !(res & 1))) { load_probe(K, D, p, P); res |= test_member<PAIRS>(K, D, uk, p, P, rep); }
-    } else {
-        const int h = gid - K.NAt, size = D.cxSize[h];
-        if (size <= 1) { load_probe(K, D, gid, P); res |= test_member<PAIRS>(K, D, uk, gid, P, rep); }
-        else {
-            const int *row = D.rowWork + D.cxOff[h];
-            for (int i = 0; i < size && (PAIRS || !(res & 1)); i++) { int m = row[i]; load_probe(K, D, m, P); res |= test_member<PAIRS>(K, D, uk, m, P, rep); }
-        }
-    }
-    if (res & 1) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); return false; }
-    if (res & 2) return true;
-    D.unitState[gid] = U_ACCEPT;
-    return false;
-}
-
 // ------------------------------------------------------------------------------------------------
 // S2g pass 1, tile kernel: one CTA owns a TS x TS block of grid cells. The cell-sorted entries of the block and of
 // the ring of cells around it are staged in shared memory once (cooperative gather: centre old/new, unit, flags),
@@ -1032,13 +893,19 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
     if (hitOld || hitNew) { *conf = (uv & UNIT_MASK) | (hitNew ? 0x40000000 : 0); return 2; }
     return 0;
 }
-// publishes a probe's result: definite overlaps and pending ones are OR-ed into the unit head's word; a single-molecule
-// unit with exactly one pending conflict also records WHICH earlier unit and pose, so k_decide can settle it directly
+// publishes a probe's result into the unit head's word unitRes: 0 = nothing found (accept), bit0 = definite overlap (reject),
+// bit1 = undecided. A finding that depends on ONE pose of an earlier unit (res == 2) is appended to the pending list as
+// (unit, earlier unit | pose bit); after the pass the pending findings alone decide what is left (k_pend_resolve): no geometry
+// is ever evaluated twice and nothing after the pass needs the neighbour grid.
 KD void publish(const Dev &D, int ukey, int res, int conf) {
     if (!res) return;
     const int u = ukey & UNIT_MASK;
-    atomicOr(&D.unitRes[u], res);
-    if (res == 2) { int old = atomicCAS(&D.pend[u], -1, conf); if (old != -1 && old != conf) atomicOr(&D.unitRes[u], 4); }
+    if (res & 1) { atomicOr(&D.unitRes[u], 1); return; }
+    atomicOr(&D.unitRes[u], 2);
+    atomicAdd(&D.pendCnt[u], 1);
+    const int i = atomicAdd(&D.scal[S_NPEND], 1);
+    if (i < D.pendCap) D.pendList[i] = make_int2(u, conf);
+    else atomicOr(&D.scal[S_OVERFLOW], 16);
 }
 
 #ifndef NSURV
@@ -1309,95 +1176,66 @@ __global__ void __launch_bounds__(PTHREADS, 8) k_pairs_eval(const __grid_constan
         __syncthreads();
     }
 }
-// after the tile pass: settle every unit whose members found nothing or a definite overlap. A unit whose only finding is
-// one overlap with one pose of a single earlier unit is settled from that unit's own findings when those are conclusive;
-// whatever remains (chains of such dependencies) goes to the undecided list for k_resolve_list/_finish (in order).
-__global__ void k_decide(const __grid_constant__ Args A) {
-    KARGS
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!gid_live(cK, D, gid) || D.unitOf[gid] != gid) return;
-    const int r = D.unitRes[gid];
-    int st = U_UNKNOWN;
-    if (r & 1) st = U_REJECT;
-    else if (r == 0) st = U_ACCEPT;
-    else if (r == 2) {                                   // exactly one pending conflict (bit 2 = several)
-        const int cf = D.pend[gid], v = cf & 0x3fffffff; const bool onNew = cf & 0x40000000;
-        const int rv = D.unitRes[v];
-        if (rv & 1) st = onNew ? U_ACCEPT : U_REJECT;    // v is rejected: it stays at its old pose
-        else if (rv == 0) st = onNew ? U_REJECT : U_ACCEPT;   // v is accepted: it sits at its new pose
-    }
-    if (st == U_REJECT) atomicAdd(&D.events[EV_REVERTED], 1ULL);
-    if (st != U_UNKNOWN) D.unitState[gid] = (unsigned char)st;
-    else D.unk[atomicAdd(&D.scal[S_NUNK0], 1)] = gid;
+// Order dependence of the sweep (main.cpp:642: an overlap test sees the NEW pose of an earlier molecule that was accepted and
+// the OLD pose of one that was reverted). After the pass every unit is accepted (unitRes 0), rejected (bit0) or waits on
+// pending findings "overlaps earlier unit v at exactly one of v's two poses". Such a finding is a hit iff v ends up at that
+// pose; a unit with a hit is rejected, a unit whose findings all turn out to be misses is accepted. One CTA sweeps the (short)
+// list until nothing changes: the lowest undecided unit only waits on decided ones, so every sweep makes progress.
+KD int unit_state(const Dev &D, int u) {                 // U_ACCEPT / U_REJECT / U_UNKNOWN from the unit's word
+    const int r = ((volatile int *)D.unitRes)[u];
+    return (r & 1) ? U_REJECT : (r == 0 ? U_ACCEPT : U_UNKNOWN);
 }
-
-// evaluates unit `gid` with one WARP (lanes = members); returns (to every lane) true if still undecided, writes its state otherwise
-KD bool eval_unit_warp(const Consts &K, const Dev &D, int gid) {
-    const int lane = threadIdx.x & 31;
-    const int rep = replica_of_gid(K, gid);
-    const int uk = D.ukey[gid];
-    int nmem = 1, m2 = -1; const int *row = nullptr;
-    if (gid < K.NAt) { m2 = D.recCis[gid]; if (m2 >= 0) nmem = 2; }
-    else if (D.cxSize[gid - K.NAt] > 1) { nmem = D.cxSize[gid - K.NAt]; row = D.rowWork + D.cxOff[gid - K.NAt]; }
-    int res = 0;
-    for (int i = lane; i < nmem; i += 32) {
-        const int m = row ? row[i] : (i == 0 ? gid : m2);
-        Probe P; load_probe(K, D, m, P);
-        res |= test_member<false>(K, D, uk, m, P, rep);
-    }
-    res = __reduce_or_sync(0xffffffffu, res);
-    if (res & 1) { if (lane == 0) { D.unitState[gid] = U_REJECT; atomicAdd(&D.events[EV_REVERTED], 1ULL); } return false; }
-    if (res & 2) return true;
-    if (lane == 0) D.unitState[gid] = U_ACCEPT;
-    return false;
-}
-// pass 2: the undecided units of list `from`, one warp each; what is still undecided goes to the other list
-__global__ void __launch_bounds__(128) k_resolve_list(const __grid_constant__ Args A, int from) {
+__global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ Args A) {
     KARGS
-    const int n = D.scal[S_NUNK0 + from];
-    const int *in = D.unk + (size_t)from * cK.NT; int *out = D.unk + (size_t)(1 - from) * cK.NT;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp; i < n; i += nwarps) {
-        const int gid = in[i];
-        if (eval_unit_warp(cK, D, gid) && (threadIdx.x & 31) == 0) out[atomicAdd(&D.scal[S_NUNK0 + 1 - from], 1)] = gid;
-    }
-}
-// final pass, one CTA: iterate over list `from` until everything is decided (the lowest undecided unit is always
-// decidable, so every sweep makes progress); normally the list is empty or a handful of units
-__global__ void __launch_bounds__(256) k_resolve_finish(const __grid_constant__ Args A, int from) {
-    KARGS
-    __shared__ int remaining;
-    const int n = D.scal[S_NUNK0 + from];
-    const int *in = D.unk + (size_t)from * cK.NT;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int changed;
+    const int n = min(D.scal[S_NPEND], D.pendCap);
     for (int sweep = 0; sweep <= n; sweep++) {
-        if (threadIdx.x == 0) remaining = 0;
+        if (threadIdx.x == 0) changed = 0;
         __syncthreads();
-        for (int i = warp; i < n; i += 8) {
-            const int gid = in[i];
-            if (((volatile unsigned char *)D.unitState)[gid] == U_UNKNOWN && eval_unit_warp(cK, D, gid) && lane == 0) atomicAdd(&remaining, 1);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int2 rec = D.pendList[i];                              // (only this thread ever rewrites entry i)
+            if (rec.x < 0) continue;                                        // settled in an earlier sweep
+            const int u = rec.x, v = rec.y & UNIT_MASK; const bool onNew = rec.y & 0x40000000;
+            bool done = false;
+            if (unit_state(D, u) != U_UNKNOWN) done = true;                 // u already rejected through another finding
+            else {
+                const int sv = unit_state(D, v);
+                if (sv != U_UNKNOWN) {
+                    done = true;
+                    if ((sv == U_ACCEPT) == onNew) { atomicOr(&D.unitRes[u], 1); changed = 1; }          // v sits at the pose u overlaps
+                    else if (atomicSub(&D.pendCnt[u], 1) == 1) { atomicCAS(&D.unitRes[u], 2, 0); changed = 1; }   // last finding, all misses
+                }
+            }
+            if (done) D.pendList[i].x = -1;
         }
         __threadfence();
         __syncthreads();
-        if (remaining == 0) break;
+        const bool again = changed != 0;
         __syncthreads();
+        if (!again) break;
     }
-    if (threadIdx.x == 0 && remaining != 0) atomicOr(&D.scal[S_OVERFLOW], 8);   // cannot happen: progress is guaranteed
 }
 
 // revert the members of rejected units (main.cpp:666-674, 851-863, 1831-1860)
 __global__ void k_restore(const __grid_constant__ Args A) {
     KARGS
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!gid_live(cK, D, gid)) return;
-    if (D.unitState[D.unitOf[gid]] != U_REJECT) return;
+    bool rejHead = false, rej = false;
+    if (gid_live(cK, D, gid)) {
+        const int u = D.unitOf[gid];
+        const int r = D.unitRes[u];
+        rej = r & 1; rejHead = rej && u == gid;
+        if (r == 2) atomicOr(&D.scal[S_OVERFLOW], 8);          // cannot happen: the pending findings always settle
+    }
+    const unsigned nrej = __popc(__ballot_sync(0xffffffffu, rejHead));
+    if (nrej && (threadIdx.x & 31) == 0) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
+    if (!rej) return;
     if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
     else {
         const double2 *s = reinterpret_cast<const double2 *>(D.lig + (size_t)(gid - cK.NAt) * 24);
         double2 *d = reinterpret_cast<double2 *>(D.lign + (size_t)(gid - cK.NAt) * 24);
         for (int q = 0; q < 12; q++) d[q] = s[q];
     }
-    D.farFlag[gid] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
