@@ -9,7 +9,9 @@ enum Scalar {
     S_MEMBER_CURSOR = 0,  // next free slot in members[]
     S_NCX,                // number of complexes (size > 1) in cxRoots[]
     S_NFAR,               // far movers this step
-    S_NPEND, S_SPARE1,    // pending findings of this step (pendList)
+    S_NPEND,              // pending findings of this step (pendList)
+    S_EPOCH,              // steps taken by this handle (never reset): stamps the per-cell chains of special entries
+    S_NSPEC,              // special entries of this step (specList): far movers and displaced molecules of a list-reuse step
     S_NPAIR,              // pre-selected reaction pairs of this step
     S_NCAND_RL, S_NCAND_CIS,
     S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
@@ -50,6 +52,11 @@ struct Dev {
     int2 *surv; int survCap;               // pairs that passed the distance cut of k_cells_cut (probe entry, neighbour entry)
     int *molSlot;                          // [NT]
     int4 *farList;                         // [NT] (gid, cell, slot, -)
+    // list reuse (sparse path): the grid and the pair list of a build step serve the following steps as well
+    float2 *bcen;                          // [NT] centre of the molecule's grid entry (fp32, what k_cells_cut measured from)
+    int *specList;                         // [2*NT] entries (gid | ghost bit) that the stale grid/list do not cover this step
+    unsigned long long *specNext;          // [2*NT] next special entry of the same cell: (stamp << 32) | (index + 1)
+    unsigned long long *cellHead;          // [ncell] head of the per-cell chain of special entries, stamped with the step
     // reaction candidates (successful draws only)
     unsigned long long *candRL, *candCis;
     int candCap;

@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 19
+#define KMC_NKERNELS 20
 
 #include <algorithm>
 #include <cmath>
@@ -42,8 +42,12 @@ struct kmc_handle {
     int *d_series = nullptr;
     int scanBlocks = 0, nTiles = 0;
     bool useCells = false;      // pass 1 of the resolve: thread-per-entry kernel (sparse cells) instead of the tile kernel
-    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
-    int parity = 0, launches_per_step = 0;
+    // list reuse (sparse path): every listEvery-th step rebuilds the neighbour grid and the pair list (phase 0), the steps in
+    // between reuse them (phase 1); sinceBuild = steps taken since the last rebuild, 0 = the next step must rebuild
+    int listEvery = 1, sinceBuild = 0, cellHeadCap = 0;
+    unsigned epoch = 0;
+    cudaGraphExec_t gexec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [phase][buffer parity]
+    int parity = 0, launches_per_step[2] = {0, 0};
     bool use_graph = true;
     double *stageRec = nullptr; int *stageInt = nullptr;      // device staging of kmc_set_packed / kmc_get_packed
     // strips
@@ -63,10 +67,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_simple",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_pend_resolve", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series", "k_pairs_eval"};
+    "k_resolve_tiles", "k_pend_resolve", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series", "k_pairs_eval", "k_special_pairs"};
 enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
-       KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES, KID_PAIRS_EVAL };
+       KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -162,12 +166,20 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     const double rs = rB * 2 / sqrt(3.0);
     K.reachRR = 2 * P.rA + 1e-3; K.reachRL = P.rA + P.rB + rs + 1e-3; K.reachLL = 2 * P.rB + 2 * rs + 1e-3;
     K.reachOn = P.rA + P.bond_dist_cut + rs + P.rB + 1e-3; K.reachCis = 2 * P.rA + P.cis_dist_cut + 1e-3;
-    K.skin = 24.0;                               // far-mover threshold; KMC_SKIN overrides (tuning knob, any value is exact)
+    // list reuse: the pair list of a build step serves the following (reuse - 1) steps; the cut and the cells grow by the
+    // drift a molecule may accumulate meanwhile (free units move at most max(amp) per step; whatever moves further is handled
+    // as a special entry). KMC_REUSE / KMC_SKIN / KMC_DRIFT override (tuning knobs, every setting is exact).
+    int reuse = 4;
+    if (const char *o = getenv("KMC_REUSE")) reuse = std::max(1, atoi(o));
+    K.skin = reuse > 1 ? 12.0 : 24.0;            // far-mover threshold
     if (const char *sk = getenv("KMC_SKIN")) { double v = atof(sk); if (v > 0) K.skin = v; }
+    K.drift = reuse > 1 ? (reuse - 1) * std::max({K.ampA, K.ampB, K.ampCis, K.ampBond}) + 0.25 : 0.0;
+    if (const char *o = getenv("KMC_DRIFT")) { double v = atof(o); if (v >= 0 && reuse > 1) K.drift = v; }
+    K.phase = 0;
     K.NA = P.n_receptor; K.NB = P.n_ligand; K.R = P.n_replicas; K.mode = P.mode;
     K.NAt = K.NA * K.R; K.NBt = K.NB * K.R; K.NT = K.NAt + K.NBt; K.seed = P.seed;
     K.strips = 1; K.stripRank = 0; K.stripXc = 0; K.stripHalf = INFINITY;
-    double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + 2 * K.skin + 1.0;   // walk around the OLD centre: reach + 2 skins
+    double edge = std::max({K.reachLL, K.reachOn, K.reachCis}) + 2 * K.skin + 2 * K.drift + 1.0;   // walk around the entry: reach + 2 skins (+ 2 drifts)
     if (P.cell_edge > edge) edge = P.cell_edge;
     else if (P.cell_edge == 0) edge = std::max(edge, getenv("KMC_EDGE") ? atof(getenv("KMC_EDGE")) : 256.0);
     K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
@@ -192,6 +204,23 @@ static void choose_tiles(kmc_handle *h) {
     // sparse cells (the reference's own density: ~0.4 molecules per cell): no staging, one thread per grid entry
     h->useCells = perCell <= 2.0;
     if (const char *o = getenv("KMC_RESOLVE")) h->useCells = !strcmp(o, "cells");
+    h->listEvery = 1;
+    if (!h->useCells) { K.drift = 0; if (!getenv("KMC_SKIN")) K.skin = 24.0; }      // tile path: rebuilt every step (the cells are at least as large as this needs)
+    if (h->useCells && K.drift > 0) { h->listEvery = 4; if (const char *o = getenv("KMC_REUSE")) h->listEvery = std::max(1, atoi(o)); }
+    h->sinceBuild = 0;
+}
+// arrays of the sparse path (allocated on first need: strips can re-derive the grid and with it the choice of path)
+static bool ensure_cells_arrays(kmc_handle *h) {
+    Dev &D = h->D; const Consts &K = h->K;
+    if (!h->useCells) return true;
+    bool ok = true;
+    if (!D.scen) {
+        D.survCap = 8 * K.NT + 4096;
+        ok = dalloc(h, &D.scen, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.scell, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.surv, (size_t)D.survCap) == cudaSuccess &&
+             dalloc(h, &D.bcen, (size_t)K.NT) == cudaSuccess && dalloc(h, &D.specList, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.specNext, (size_t)2 * K.NT) == cudaSuccess;
+    }
+    if (ok && h->cellHeadCap < D.ncell) { ok = dalloc(h, &D.cellHead, (size_t)D.ncell) == cudaSuccess; h->cellHeadCap = D.ncell; }
+    return ok;
 }
 
 extern "C" void kmc_destroy(kmc_handle *h) {
@@ -201,7 +230,7 @@ extern "C" void kmc_destroy(kmc_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto ev : h->evpool) cudaEventDestroy(ev);
-    for (int p = 0; p < 2; p++) if (h->gexec[p]) cudaGraphExecDestroy(h->gexec[p]);
+    for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -245,7 +274,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     choose_tiles(h);
     A(scanTmp, (size_t)h->scanBlocks + 1);
     A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT);
-    if (h->useCells) { D.survCap = 4 * K.NT + 4096; A(scen, (size_t)2 * K.NT); A(scell, (size_t)2 * K.NT); A(surv, (size_t)D.survCap); } A(farList, K.NT);
+    ok = ok && ensure_cells_arrays(h); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
     A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); D.pendCap = 2 * K.NT + 4096; A(pendList, D.pendCap); A(step64, 1);
@@ -333,7 +362,7 @@ extern "C" int kmc_set_state(kmc_handle *h, int32_t rep, const double *Rx, const
     int one = 1;
     CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D.maxComplex + rep, &max_complex, sizeof(int), cudaMemcpyHostToDevice));
-    h->step_done = step_done; h->stepped = false;
+    h->step_done = step_done; h->stepped = false; h->sinceBuild = 0;
     { unsigned long long s64 = (unsigned long long)step_done; CK(cudaMemcpy(D.step64, &s64, sizeof s64, cudaMemcpyHostToDevice)); }
     return KMC_OK;
 }
@@ -463,7 +492,7 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
     CK(cudaMemcpyAsync(D.step64, &s64, sizeof s64, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(&flags, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    h->step_done = step_done; h->stepped = false;
+    h->step_done = step_done; h->stepped = false; h->sinceBuild = 0;
     if (flags) { h->err = std::string("kmc_set_packed: inconsistent bond table (") + ((flags & 1) ? "R-L bond " : "") + ((flags & 2) ? "cis bond " : "") + "invalid or asymmetric)"; return KMC_ERR_STATE; }
     return KMC_OK;
 }
@@ -476,15 +505,18 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 // the gated kernels that follow only if the bond table changed (S_TOPO_DIRTY, cleared by k_propose_simple)
 __global__ void k_step_begin(const __grid_constant__ Args A) {
     KARGS
-    D.step64[0] += 1;
-    D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSURV] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+    D.step64[0] += 1; D.scal[S_EPOCH] += 1;
+    D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+    if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
 }
 
-// all launches of one time step (main.cpp:461-2202) on stream st; no host synchronisation anywhere
+// all launches of one time step (main.cpp:461-2202) on stream st; no host synchronisation anywhere.
+// A.K.phase: 0 = the step rebuilds the neighbour grid (and, on the sparse path, the pair list), 1 = it reuses them.
 static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const Dev &D = A.D;
     const int B = 128, NT = h->NT, NAt = h->NAt, NBt = h->NBt;
+    const bool build = A.K.phase == 0;
     LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A)));
     // S1 (gated on a device flag)
     LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
@@ -494,16 +526,20 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     // S2 proposals
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, st>>>(A)));
-    // neighbour grid: the histogram was accumulated by the propose kernels (cellCount is zero at step start: k_scan_down clears it)
-    LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>((const int4 *)D.cellCount, D.scanTmp)));
-    LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks)));
-    LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>((int4 *)D.cellCount, D.scanTmp, (int4 *)D.cellStart)));
-    LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    // S2g: tile pass over all molecules (+ reaction-pair pre-selection), settle, then the (rare) dependency chains in order
+    if (build) {
+        // neighbour grid: the histogram was accumulated by the propose kernels (cellCount is zero at step start: k_scan_down clears it)
+        LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>((const int4 *)D.cellCount, D.scanTmp)));
+        LAUNCH(KID_SCAN_SUMS, (k_scan_sums<<<1, 1024, 0, st>>>(D.scanTmp, h->scanBlocks)));
+        LAUNCH(KID_SCAN_DOWN, (k_scan_down<<<h->scanBlocks, 256, 0, st>>>((int4 *)D.cellCount, D.scanTmp, (int4 *)D.cellStart)));
+        LAUNCH(KID_GRID_SCATTER, (k_grid_scatter<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    }
+    // S2g: every (probe, neighbour) pair within reach is classified once (+ reaction-pair pre-selection), then the order
+    // dependence is settled from the pending findings
     const int gl = std::min(nblk(NT, B), 148 * 8);
     if (h->useCells) {
-        LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
+        if (build) LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
         LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PTHREADS), 148 * 8 * 8), PTHREADS, 0, st>>>(A)));
+        if (!build) LAUNCH(KID_SPECIAL, (k_special_pairs<<<148 * 2, 32 * SP_WARPS, 0, st>>>(A)));
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
     LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
@@ -514,22 +550,26 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
 }
 static void swap_buffers(Dev &D) { std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign); }
 
-// the step as a CUDA graph, one per buffer parity (the committed/new buffers alternate, S4 is a pointer swap)
+// the step as a CUDA graph, one per phase and buffer parity (the committed/new buffers alternate, S4 is a pointer swap)
 static int ensure_graphs(kmc_handle *h) {
-    if (h->gexec[0]) return KMC_OK;
+    if (h->gexec[0][0]) return KMC_OK;
     const int64_t saved = h->launches;
-    for (int p = 0; p < 2; p++) {
-        Dev Dp = h->D;
-        if (p != h->parity) swap_buffers(Dp);
-        const Args A{Dp, h->K};
-        cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        issue_step(h, A, h->stream);
-        CK(cudaStreamEndCapture(h->stream, &g));
-        CK(cudaGraphInstantiate(&h->gexec[p], g, 0));
-        cudaGraphDestroy(g);
+    for (int ph = 0; ph < (h->listEvery > 1 ? 2 : 1); ph++) {
+        const int64_t before = h->launches;
+        for (int p = 0; p < 2; p++) {
+            Dev Dp = h->D;
+            if (p != h->parity) swap_buffers(Dp);
+            Args A{Dp, h->K};
+            A.K.phase = ph;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            issue_step(h, A, h->stream);
+            CK(cudaStreamEndCapture(h->stream, &g));
+            CK(cudaGraphInstantiate(&h->gexec[ph][p], g, 0));
+            cudaGraphDestroy(g);
+        }
+        h->launches_per_step[ph] = (int)((h->launches - before) / 2);
     }
-    h->launches_per_step = (int)((h->launches - saved) / 2);
     h->launches = saved;
     return KMC_OK;
 }
@@ -541,16 +581,25 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     cudaStream_t st = h->stream;
     if (!h->profiling && h->use_graph && n > 0) { rc = ensure_graphs(h); if (rc) return rc; }
     for (int64_t it = 0; it < n; it++) {
+        const int phase = (h->sinceBuild == 0 || h->sinceBuild >= h->listEvery) ? 0 : 1;
+        if (phase == 0) h->sinceBuild = 0;
+        if (++h->epoch >= 0xfffffff0u) {         // the stamp of the per-cell chains is about to wrap: start a new era
+            if (h->D.cellHead) CK(cudaMemsetAsync(h->D.cellHead, 0, sizeof(unsigned long long) * (size_t)h->cellHeadCap, st));
+            CK(cudaMemsetAsync(h->D.scal + S_EPOCH, 0, sizeof(int), st));
+            h->epoch = 1;
+        }
         if (h->profiling || !h->use_graph) {
-            const Args A{h->D, h->K};
+            Args A{h->D, h->K};
+            A.K.phase = phase;
             issue_step(h, A, st);
             if (h->profiling && (it & 15) == 15) harvest(h, false);
         } else {
-            CK(cudaGraphLaunch(h->gexec[h->parity], st));
-            h->launches += h->launches_per_step;
+            CK(cudaGraphLaunch(h->gexec[phase][h->parity], st));
+            h->launches += h->launches_per_step[phase];
         }
         // S4: the new buffers become the committed state
         swap_buffers(h->D); h->parity ^= 1;
+        h->sinceBuild++;
         h->passes += 1; h->step_done++; h->stepped = true;
     }
     CK(cudaGetLastError());
@@ -563,7 +612,9 @@ extern "C" int kmc_sync(kmc_handle *h) {
     CK(cudaStreamSynchronize(h->stream));
     int scal[S_COUNT];
     CK(cudaMemcpy(scal, h->D.scal, sizeof scal, cudaMemcpyDeviceToHost));
-    if (scal[S_OVERFLOW]) { h->err = "device buffer overflow (mask " + std::to_string(scal[S_OVERFLOW]) + ")"; return KMC_ERR_CAPACITY; }
+    int ovf = scal[S_OVERFLOW];
+    if (h->listEvery <= 1) ovf &= ~32;          // a pair list that is rebuilt every step may overflow into in-place evaluation
+    if (ovf) { h->err = "device buffer overflow (mask " + std::to_string(ovf) + ((ovf & 32) ? "; pair list too small for list reuse: set KMC_REUSE=1" : "") + ")"; return KMC_ERR_CAPACITY; }
     return KMC_OK;
 }
 

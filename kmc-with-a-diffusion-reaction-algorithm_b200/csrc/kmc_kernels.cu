@@ -129,28 +129,52 @@ KD uint64_t seed_of(const Consts &cK, int replica) { return cK.seed + (uint64_t)
 #define F_GHOST 2
 #define F_FREE_RL 4      // receptor: no ligand bound / ligand: at least one free site
 #define F_FREE_CIS 8
-// called once per molecule per step by whoever computed its proposal: far-mover flag + the counting-sort histogram of the
-// neighbour grid (entry in the cell of the OLD centre; a far mover gets a second, ghost entry in the cell of its proposal)
-// also the 48-byte neighbour record of the molecule (centre old/new, unit key, far/free flags): what the tile kernel stages
-KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, int ukey, int freeFlags) {
+#define F_DISP 16        // list-reuse step: the molecule has drifted away from its grid entry (or jumped since the grid was built)
+// a special entry of a list-reuse step: appended to specList and chained to the cell of the centre it stands for
+KD void register_special(const Consts &cK, const Dev &D, int entry, int cell, unsigned stamp) {
+    const int idx = atomicAdd(&D.scal[S_NSPEC], 1);
+    D.specList[idx] = entry;
+    D.specNext[idx] = atomicExch(&D.cellHead[cell], ((unsigned long long)stamp << 32) | (unsigned)(idx + 1));
+}
+// called once per molecule per step by whoever computed its proposal: the 48-byte neighbour record of the molecule (centre
+// old/new, unit key, far/free flags: what the resolve kernels read) and its place in the neighbour search.
+//  build step (phase 0): counting-sort histogram of the grid -- entry in the cell of the OLD centre; a far mover gets a second,
+//    ghost entry in the cell of its proposal -- and the fp32 centre of the entry (bcen), which later steps measure drift from;
+//  reuse step (phase 1): the grid and the pair list of the last build step stand; a far mover, or a molecule whose old centre
+//    has drifted more than K.drift from its entry, is SPECIAL: the stale structures do not cover it, k_special_pairs does.
+KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, int ukey, int freeFlags, unsigned stamp) {
     const double dx = nx - ox, dy = ny - oy;
     const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
+    const int rep = replica_of_gid(cK, gid);
+    int flags = freeFlags | (far ? F_FAR : 0);
+    if (cK.phase == 0) {
+        if (D.bcen) D.bcen[gid] = make_float2((float)ox, (float)oy);
+        D.molSlot[gid] = atomicAdd(&D.cellCount[cell_of(cK, rep, ox, oy)], 1);
+        if (far) {
+            const int c2 = cell_of(cK, rep, nx, ny);
+            const int slot = atomicAdd(&D.cellCount[c2], 1);
+            D.farList[atomicAdd(&D.scal[S_NFAR], 1)] = make_int4(gid, c2, slot, 0);
+        }
+    } else {
+        const float2 bc = D.bcen[gid];
+        const double ex = ox - (double)bc.x, ey = oy - (double)bc.y;
+        const bool disp = ex * ex + ey * ey > cK.drift * cK.drift;
+        if (disp) flags |= F_DISP;
+        if (far || disp) {
+            register_special(cK, D, gid, cell_of(cK, rep, ox, oy), stamp);
+            if (far) register_special(cK, D, gid | GHOST_BIT, cell_of(cK, rep, nx, ny), stamp);
+        }
+    }
     double2 *nr = reinterpret_cast<double2 *>(D.nrec) + (size_t)gid * 3;
     nr[0] = make_double2(ox, oy); nr[1] = make_double2(nx, ny);
-    reinterpret_cast<int4 *>(nr)[2] = make_int4(gid, ukey, freeFlags | (far ? F_FAR : 0), 0);
-    const int rep = replica_of_gid(cK, gid);
-    D.molSlot[gid] = atomicAdd(&D.cellCount[cell_of(cK, rep, ox, oy)], 1);
-    if (far) {
-        const int c2 = cell_of(cK, rep, nx, ny);
-        const int slot = atomicAdd(&D.cellCount[c2], 1);
-        D.farList[atomicAdd(&D.scal[S_NFAR], 1)] = make_int4(gid, c2, slot, 0);
-    }
+    reinterpret_cast<int4 *>(nr)[2] = make_int4(gid, ukey, flags, 0);
 }
 
 // free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
 __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant__ Args A) {
     KARGS
     const uint64_t step = D.step64[0];
+    const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid == 0) D.scal[S_TOPO_DIRTY] = 0;       // the gated rebuild kernels of this step are done; S3 sets it again
     if (!gid_live(cK, D, gid)) return;
@@ -180,7 +204,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             rotz(cs, ss, t.s2x, t.s2y, t.cx, t.cy, n.s2x, n.s2y);
             rotz(cs, ss, t.s3x, t.s3y, t.cx, t.cy, n.s3x, n.s3y);
             store_rec(D.recCn, D.recS2n, D.recS3n, a, n);
-            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL | F_FREE_CIS);
+            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL | F_FREE_CIS, stamp);
             if (K.mode) D.ukey[a] = unit_key(K, a, ra.cx, ra.cy);
         } else {
             // ---- S2b: this receptor is the lower index of a ligand-free cis pair ----
@@ -211,8 +235,8 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             if (cis_misaligned(K, na, nb)) snap_cis(K, nb, na);          // "relax", main.cpp:770-799
             store_rec(D.recCn, D.recS2n, D.recS3n, a, na);
             store_rec(D.recCn, D.recS2n, D.recS3n, p, nb);
-            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL);
-            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL);
+            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp);
+            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp);
             if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
@@ -243,7 +267,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
         for (int q = 0; q < 8; q++) rot3_about(R3, l.p[q], c, n.p[q]);
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
         store_lig(D.lign, h, n);
-        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], unit_key(K, gid, ox, oy), F_FREE_RL);
+        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], unit_key(K, gid, ox, oy), F_FREE_RL, stamp);
         if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
     }
@@ -529,6 +553,7 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
     KARGS
     __shared__ CxShared SH[CX_WARPS];
     const uint64_t step = D.step64[0];
+    const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const Consts &K = cK;
     const int ncx = D.scal[S_NCX];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -605,11 +630,11 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 if (m < K.NAt) {
                     const Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]};
                     store_rec(D.recCn, D.recS2n, D.recS3n, m, r);
-                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0));
+                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0), stamp);
                 } else {
                     double *q = D.lign + (size_t)(m - K.NAt) * 24;
                     for (int t = 0; t < 24; t++) q[t] = p[t];
-                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0);
+                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0, stamp);
                 }
             }
         } else if (lane == 0) {
@@ -646,8 +671,8 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
             for (int q = 0; q < size; q++) {
                 const int m = rowOut[q];
                 if (K.mode) D.ukey[m] = ckey;
-                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0)); }
-                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0); }
+                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp); }
+                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp); }
             }
         }
         if (lane == 0) { D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0; }
@@ -1103,7 +1128,7 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
     // within one skin of its entry (proposal of a near mover around its old entry; a far mover has one entry per pose), so
     // overlap reach + 2 skins and S3 reach + 2 skins bound every test pair_eval can make. fp32 with a margin that covers the
     // rounding of the stored coordinates (K.cutMargin, from the box size).
-    const float mg = K.cutMargin, sk2 = 2 * (float)K.skin;
+    const float mg = K.cutMargin, sk2 = 2 * (float)K.skin + 2 * (float)K.drift;     // (+ the drift allowed while the list is reused)
     const float cRR = fmaxf((float)K.ovAA, (float)K.reachCis) + sk2 + mg, cRL = fmaxf((float)K.reachRL, (float)K.reachOn) + sk2 + mg,
                 cLR = (float)K.reachRL + sk2 + mg, cLL = (float)K.reachLL + sk2 + mg;
     const float gx0 = (float)K.gx0, gy0 = (float)K.gy0, cinv = (float)K.cellInv;
@@ -1139,7 +1164,11 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
                     if (ex * ex + ey * ey > ((en & ~GHOST_BIT) < K.NAt ? cR2 : cL2) || i == e) continue;
                     const int slot = atomicAdd(&nsurv, 1);
                     if (slot < CSURV) surv[slot] = make_int2(entry, en);
-                    else eval_entry_pair_slow(A, entry, en);                    // CTA list full (crowded spot)
+                    else {                                                      // CTA list full (crowded spot): append one by one
+                        const int g = atomicAdd(&D.scal[S_NSURV], 1);
+                        if (g < D.survCap) D.surv[g] = make_int2(entry, en);
+                        else { eval_entry_pair_slow(A, entry, en); atomicOr(&D.scal[S_OVERFLOW], 32); }
+                    }
                 }
         }
         __syncthreads();
@@ -1150,7 +1179,7 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
             const int gb = gbase;
             for (int s = threadIdx.x; s < ns; s += CTHREADS) {
                 if (gb + s < D.survCap) D.surv[gb + s] = surv[s];
-                else eval_entry_pair_slow(A, surv[s].x, surv[s].y);             // global list full
+                else { eval_entry_pair_slow(A, surv[s].x, surv[s].y); atomicOr(&D.scal[S_OVERFLOW], 32); }   // global list full: exact for this step, but the list cannot be reused (the host reports it unless it rebuilds every step)
             }
         }
         __syncthreads();
@@ -1170,12 +1199,96 @@ __global__ void __launch_bounds__(PTHREADS, 8) k_pairs_eval(const __grid_constan
         if (threadIdx.x == 0) pcnt = 0;
         __syncthreads();
         const int s = base + threadIdx.x;
-        if (s < ns) { const int2 w = D.surv[s]; eval_entry_pair(K, D, w.x, w.y, ps); }
+        if (s < ns) {
+            const int2 w = D.surv[s];
+            if (K.phase == 0) eval_entry_pair(K, D, w.x, w.y, ps);
+            else if (!((w.x | w.y) & GHOST_BIT)) {
+                // reuse step: ghost entries belong to the build step only; a molecule that is special this step (far mover or
+                // displaced) is not where the list believes it to be and is handled by k_special_pairs instead
+                const TileRec a = fetch_rec(K, D, w.x), b = fetch_rec(K, D, w.y);
+                if (!((a.flg | b.flg) & (F_FAR | F_DISP))) {
+                    int cf = -1;
+                    const ProbeCtx pc = make_probe(K, a);
+                    const int rr = pair_eval(K, D, pc, b, &cf, ps);
+                    publish(D, pc.u, rr, cf);
+                }
+            }
+        }
         __syncthreads();
         flush_pairs(D, ps, &pbase);
         __syncthreads();
     }
 }
+// List-reuse steps: the molecules the stale grid / pair list do not cover. A special entry stands for one centre X of its
+// molecule f (a far mover has two: old centre, and proposal with the ghost bit; a displaced molecule one: its old centre,
+// the proposal is within a skin of it). One warp per special entry walks the 3x3 cells around X in the STALE grid:
+//   * every ordinary molecule n entered there is still within drift + skin of its entry, so the walk finds everything f can
+//     touch from X (cell edge >= reach + 2 skins + 2 drifts); both directions are classified here, (f, n) and (n, f),
+//     because the list pairs of f are skipped by k_pairs_eval;
+//   * other special entries are found through the per-cell chains built by mark_far (direction (f, g); g's warp does (g, f)).
+// pair_eval is exact for any two entries, so duplicates (a molecule with a leftover ghost entry in the stale grid) only repeat
+// idempotent findings.
+#define SP_WARPS 4
+__global__ void __launch_bounds__(32 * SP_WARPS) k_special_pairs(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    __shared__ unsigned long long pbuf[128];
+    __shared__ int pcnt, pbase;
+    const PairSink ps = {pbuf, &pcnt, 128};
+    const int ns = min(D.scal[S_NSPEC], 2 * K.NT);
+    const unsigned stamp = (unsigned)D.scal[S_EPOCH];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int base = blockIdx.x * SP_WARPS; base < ns; base += gridDim.x * SP_WARPS) {
+        if (threadIdx.x == 0) pcnt = 0;
+        __syncthreads();
+        const int si = base + wib;
+        if (si < ns) {
+            const int ef = D.specList[si], f = ef & ~GHOST_BIT;
+            const TileRec rf = fetch_rec(K, D, ef);
+            const ProbeCtx pf = make_probe(K, rf);
+            const double X = (ef & GHOST_BIT) ? rf.nx : rf.ox, Y = (ef & GHOST_BIT) ? rf.ny : rf.oy;
+            const int rep = replica_of_gid(K, f);
+            int cx = (int)floor((hash_x(K, X) - K.gx0) * K.cellInv), cy = (int)floor((Y - K.gy0) * K.cellInv);
+            cx = min(max(cx, 0), K.ncx - 1); cy = min(max(cy, 0), K.ncy - 1);
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, K.ncx - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, K.ncy - 1);
+            for (int yy = y0; yy <= y1; yy++) {
+                const int rowc = (rep * K.ncy + yy) * K.ncx;
+                const int e0 = D.cellStart[rowc + x0], e1 = D.cellStart[rowc + x1 + 1];
+                for (int i = e0 + lane; i < e1; i += 32) {
+                    const int n = D.sorted[i] & ~GHOST_BIT;
+                    if (n == f) continue;
+                    const TileRec rn = fetch_rec(K, D, n);
+                    if (rn.flg & (F_FAR | F_DISP)) continue;              // special as well: met through the chains below
+                    int cf = -1;
+                    int rr = pair_eval(K, D, pf, rn, &cf, ps);
+                    publish(D, pf.u, rr, cf);
+                    const ProbeCtx pn = make_probe(K, rn);
+                    cf = -1; rr = pair_eval(K, D, pn, rf, &cf, ps);
+                    publish(D, pn.u, rr, cf);
+                }
+            }
+            // the chains of special entries of the same 3x3 cells, one cell per lane
+            const int ncolw = x1 - x0 + 1, ncw = ncolw * (y1 - y0 + 1);
+            if (lane < ncw) {
+                const int cell = (rep * K.ncy + y0 + lane / ncolw) * K.ncx + x0 + lane % ncolw;
+                unsigned long long link = D.cellHead[cell];
+                for (int guard = 0; guard < ns && (unsigned)(link >> 32) == stamp && (unsigned)link != 0; guard++) {
+                    const int gi = (int)(unsigned)link - 1;
+                    const int eg = D.specList[gi];
+                    link = D.specNext[gi];
+                    if ((eg & ~GHOST_BIT) == f) continue;
+                    int cf = -1;
+                    const int rr = pair_eval(K, D, pf, fetch_rec(K, D, eg), &cf, ps);
+                    publish(D, pf.u, rr, cf);
+                }
+            }
+        }
+        __syncthreads();
+        flush_pairs(D, ps, &pbase);
+        __syncthreads();
+    }
+}
+
 // Order dependence of the sweep (main.cpp:642: an overlap test sees the NEW pose of an earlier molecule that was accepted and
 // the OLD pose of one that was reverted). After the pass every unit is accepted (unitRes 0), rejected (bit0) or waits on
 // pending findings "overlaps earlier unit v at exactly one of v's two poses". Such a finding is a hit iff v ends up at that

@@ -84,7 +84,7 @@ static int strip_upload(kmc_handle *h, const HostLocal &s) {
     int live[2] = {s.nA, s.nB}, one = 1;
     CK(cudaMemcpy(D.scal + S_NA_LIVE, live, sizeof live, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
-    h->stepped = false;
+    h->stepped = false; h->sinceBuild = 0;
     return KMC_OK;
 }
 
@@ -150,13 +150,14 @@ extern "C" int kmc_strip_configure(kmc_handle *h, int32_t rank, int32_t nranks, 
         }
         D.ncell = ncell;
         choose_tiles(h);
+        if (!ensure_cells_arrays(h)) { h->err = "kmc_strip_configure: allocation failed"; return KMC_ERR_CUDA; }
     }
     if (!D.refA) {
         if (dalloc(h, &D.refA, std::max(h->NAt, 1)) != cudaSuccess || dalloc(h, &D.refB, std::max(h->NBt, 1)) != cudaSuccess) { h->err = "kmc_strip_configure: allocation failed"; return KMC_ERR_CUDA; }
     }
     int zero[2] = {0, 0};
     CK(cudaMemcpy(D.scal + S_NA_LIVE, zero, sizeof zero, cudaMemcpyHostToDevice));
-    for (int p = 0; p < 2; p++) if (h->gexec[p]) { cudaGraphExecDestroy(h->gexec[p]); h->gexec[p] = nullptr; }
+    for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) { cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]); h->gexec[p >> 1][p & 1] = nullptr; }
     return KMC_OK;
 }
 
@@ -528,6 +529,6 @@ extern "C" int kmc_strip_rebuild_dev(kmc_handle *h, int64_t rec_low, int64_t lig
     CK(cudaMemcpyAsync(h->D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    h->stepped = false; h->strip_refreshes++;
+    h->stepped = false; h->sinceBuild = 0; h->strip_refreshes++;
     return kmc_sync(h);
 }

@@ -171,3 +171,25 @@ def test_errors_are_reported_not_swallowed():
     k.set_packed(rec, lig, rl, rs, rc)               # and the handle is still usable afterwards
     k.step(3)
     assert k.series()["step"] == 3
+
+
+@pytest.mark.parametrize("reuse,skin,drift", [("1", None, None), ("4", None, None), ("7", "3", "2.5"), ("3", "30", "0.5"), ("5", "1.5", "40")])
+def test_list_reuse_settings_are_all_exact(golden_dir, monkeypatch, reuse, skin, drift):
+    """The sparse path rebuilds the neighbour grid / pair list every KMC_REUSE-th step and reuses them in between; far movers
+    (beyond KMC_SKIN) and molecules that drifted more than KMC_DRIFT from their grid entry are handled as special entries. Every
+    setting must reproduce the oracle: tiny skins / drifts make most molecules special, large ones stretch the stale list."""
+    monkeypatch.setenv("KMC_RESOLVE", "cells")
+    monkeypatch.setenv("KMC_REUSE", reuse)
+    if skin: monkeypatch.setenv("KMC_SKIN", skin)
+    if drift: monkeypatch.setenv("KMC_DRIFT", drift)
+    g = load_golden_state(os.path.join(golden_dir, "hot200_step40000.npz"))
+    o, k = make_pair(150, 50, tuple(g["params"]["box"]), "hot", seed=77)
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    lockstep(o, k, 150, 1, "reuse-%s" % reuse, per_step_accept=True)
+    lockstep(o, k, 850, 50, "reuse-%s" % reuse)
+    # a state pushed in from outside in the middle of a reuse window must force a rebuild
+    R, st, rn = o.get_state()
+    k.set_state(R, st, rn, step_done=o.counts()["step"], max_complex=o.counts()["max_complex"])
+    lockstep(o, k, 60, 1, "reuse-%s after set_state" % reuse, per_step_accept=True)
+    k.close()
