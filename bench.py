@@ -35,16 +35,17 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 # algorithmic bytes per molecule and launch of each kernel (DESIGN.md "Kernels"), 3:1 receptor:ligand mix
 B_ALG_STEP = 232.0      # whole step, fp64 pose read+written once (2*96) + bond words 24 + label 8 + cell key/index 8
+# algorithmic bytes per launch of a kernel, per molecule of the system (3:1 receptors:ligands) unless the kernel works on a list
 B_ALG_KERNEL = {
-    "k_propose_simple": 96 + 96 + 4 + 4 + 2,          # old pose in, proposed pose out, unitOf, cis/size word, state+far flags
+    "k_propose_rec": 0.75 * (48 + 48 + 4 + 4),        # receptors: old pose in, proposed pose out, unit word, cis word
+    "k_propose_lig": 0.25 * (192 + 192 + 4 + 4),      # ligands: old pose in, proposed pose out, unit word, complex-size word
     "k_resolve_tiles": 81,                            # per entry: id 4, unit 4, far 1, centres old+new 32, bond words 8-12 (+72 B beads for a ligand probe)
                                                       # = 49 B receptor / 121 B ligand -> 67 B in the 3:1 mix, + cellStart window 2.56 cells x 1.34 x 4 B
-    "k_react_pairs": 0.1 * (48 + 96 + 16),              # pre-selected pairs only (~0.1 per molecule): both poses + bond words
-    "k_grid_count": 18 + 1 + 4 + 4,
+    "k_cells_cut": 12 + 6 * 4 * 0.5 + 3.6 * 12,       # per entry: own id/centre/cell, row extents (shared between neighbours), ~3.6 candidates x 12 B
     "k_grid_scatter": 18 + 4 + 4 + 4,
-    "k_restore": 4 + 1,
-    "k_dissociate": 0.75 * 8,
+    "k_finish": 4 + 4 + 0.75 * 8,                     # unit word + unit result, bond words of the receptors
 }
+B_ALG_PER_LIST_PAIR = 8 + 2 * 40                      # k_pairs_eval: the pair + two records (centres old/new 32, unit key 4, flags 4)
 
 
 def read_peaks():
@@ -243,7 +244,10 @@ def main():
     top = max(prof.items(), key=lambda kv: kv[1][0])
     peak, peak_src = read_peaks()
     top_name, (top_ms, top_n) = top
+    evp = k.events()
     balg = B_ALG_KERNEL.get(top_name)
+    if top_name == "k_pairs_eval":
+        balg = B_ALG_PER_LIST_PAIR * evp["list_pairs"] / M
     achieved = balg * M / (top_ms / top_n * 1e-3) / 1e9 if balg else None
 
     # ---- e2e through the C ABI with host buffers ----
@@ -313,7 +317,8 @@ def main():
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "molecule-moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": ev1["launches"] - ev0["launches"],
-                "resolve_passes_per_mc_step": (ev1["passes"] - ev0["passes"]) / (args.steps * S),
+                "work_lists_last_step": {q: evp[q] for q in ("list_pairs", "special_entries", "pending_findings", "reaction_pairs")},
+                "events_in_timed_region": {q: ev1[q] - ev0[q] for q in ("rl_on", "mono_cis_on", "cis_on", "rl_off", "reverted", "rebuilds")},
                 "clocks": sampler.result() if sampler else None}
         print(json.dumps(line))
     if dist is not None:

@@ -138,7 +138,9 @@ int kmc_get_grid(kmc_handle *h, double *x0, double *y0, double *inv_edge, int32_
 int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
 /* ev[16] accumulated since creation: [0] R-L on, [1] mono-cis on, [2] cis on, [3] R-L off, [4] mono-cis off,
  * [5] cis off, [6] unit moves reverted, [7] unit moves tried, [8] far movers, [9] conflict-resolution passes,
- * [10] complex-table rebuilds, [11] kernels launched */
+ * [10] complex-table rebuilds, [11] kernels launched; sizes of the last step's work lists: [12] entry pairs in the neighbour
+ * list, [13] special entries (far movers / drifted molecules of a list-reuse step), [14] pending findings, [15] pre-selected
+ * reaction pairs */
 int kmc_get_events(kmc_handle *h, int64_t *ev);
 
 /* Pure host formatting of the reference's records (no device needed): one bond.dat line (main.cpp:2249-2251) and one

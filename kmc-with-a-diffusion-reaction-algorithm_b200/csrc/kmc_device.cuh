@@ -43,7 +43,7 @@ struct Dev {
     int *bfsMark;
     int *rowPos;                           // [NT] position of a complex member in its breadth-first member list
     unsigned char *movedFlag;
-    double *nrec;                          // [NT][6] neighbour record per molecule: centre old xy, new xy, {gid, unit key, flags, -}
+    double *nrec;                          // [NT][6] neighbour record per molecule: centre old xy, new xy, {old z (fp32), unit key, flags, new z (fp32)}
     // neighbour grid
     int *cellCount, *cellStart, *scanTmp;  // [ncell+1]
     int *sorted;                           // [2*NT] entries gid | ghost bit
@@ -116,10 +116,11 @@ KD int cell_of(const Consts &K, int replica, double x, double y) {
     cx = min(max(cx, 0), K.ncx - 1); cy = min(max(cy, 0), K.ncy - 1);
     return (replica * K.ncy + cy) * K.ncx + cx;
 }
-KD int replica_of_gid(const Consts &K, int gid) { return gid < K.NAt ? gid / K.NA : (gid - K.NAt) / K.NB; }
+KD int replica_of_gid(const Consts &K, int gid) { return K.R == 1 ? 0 : (gid < K.NAt ? gid / K.NA : (gid - K.NAt) / K.NB); }
 // reference molecule id (1-based) used to key the random stream
 KD uint32_t ref_id(const Consts &K, const Dev &D, int gid) {
     if (D.refA) return gid < K.NAt ? D.refA[gid] : D.refB[gid - K.NAt];
+    if (K.R == 1) return (uint32_t)(gid + 1);          // one replica: no integer division on the hot path
     return gid < K.NAt ? (uint32_t)(gid % K.NA + 1) : (uint32_t)(K.NA + (gid - K.NAt) % K.NB + 1);
 }
 

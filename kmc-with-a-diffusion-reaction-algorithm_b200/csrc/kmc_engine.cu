@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 20
+#define KMC_NKERNELS 19
 
 #include <algorithm>
 #include <cmath>
@@ -33,7 +33,8 @@ struct kmc_handle {
     kmc_params P;
     Consts K;
     Dev D;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, side[2] = {nullptr, nullptr};      // side streams: forked branches of the step (graph)
+    cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int R = 1, NA = 0, NB = 0, N = 0, NAt = 0, NBt = 0, NT = 0;
     int64_t step_done = 0;
@@ -65,12 +66,12 @@ struct kmc_handle {
 };
 
 static const char *const g_kernel_names[KMC_NKERNELS] = {
-    "k_step_begin", "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_simple",
+    "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_pend_resolve", "k_restore", "k_react_pairs", "k_react_resolve", "k_dissociate", "k_series", "k_pairs_eval", "k_special_pairs"};
-enum { KID_STEP_BEGIN = 0, KID_UF_INIT, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
+    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig"};
+enum { KID_UF_INIT = 0, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
-       KID_RESTORE, KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_DISSOCIATE, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL };
+       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -231,6 +232,9 @@ extern "C" void kmc_destroy(kmc_handle *h) {
     for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto ev : h->evpool) cudaEventDestroy(ev);
     for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]);
+    for (auto e : h->evFork) if (e) cudaEventDestroy(e);
+    for (auto e : h->evJoin) if (e) cudaEventDestroy(e);
+    for (auto q : h->side) if (q) cudaStreamDestroy(q);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -261,6 +265,9 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     D.ncell = K.R * K.ncx * K.ncy;
     D.candCap = std::max(1 << 14, K.NAt / 8);
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &q : h->side) ok = ok && cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &e : h->evFork) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    for (auto &e : h->evJoin) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
 #define A(ptr, n) ok = ok && dalloc(h, &D.ptr, (size_t)(n)) == cudaSuccess
     A(recC, K.NAt); A(recS2, K.NAt); A(recS3, K.NAt); A(recCn, K.NAt); A(recS2n, K.NAt); A(recS3n, K.NAt);
     A(lig, (size_t)K.NBt * 24); A(lign, (size_t)K.NBt * 24);
@@ -501,31 +508,28 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 // the sweep
 // ------------------------------------------------------------------------------------------------
 
-// first kernel of a step: advances the device-side step counter, resets the per-step scalars; complexes are rebuilt by
-// the gated kernels that follow only if the bond table changed (S_TOPO_DIRTY, cleared by k_propose_simple)
-__global__ void k_step_begin(const __grid_constant__ Args A) {
-    KARGS
-    D.step64[0] += 1; D.scal[S_EPOCH] += 1;
-    D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
-    if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
-    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
-}
-
 // all launches of one time step (main.cpp:461-2202) on stream st; no host synchronisation anywhere.
 // A.K.phase: 0 = the step rebuilds the neighbour grid (and, on the sparse path, the pair list), 1 = it reuses them.
 static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const Dev &D = A.D;
     const int B = 128, NT = h->NT, NAt = h->NAt, NBt = h->NBt;
     const bool build = A.K.phase == 0;
-    LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 1, 0, st>>>(A)));
-    // S1 (gated on a device flag)
-    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    // step begin (one thread) + S1 (gated on a device flag)
+    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A, 1)));
     LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
     LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
-    // S2 proposals
-    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_simple<<<nblk(NT, B), B, 0, st>>>(A)));
-    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, st>>>(A)));
+    // S2 proposals: free receptors / cis dimers, free ligands and complexes are disjoint sets of molecules -- three kernels side
+    // by side (forked branches of the graph; on one stream when per-kernel timing is on)
+    cudaStream_t s1 = h->profiling ? st : h->side[0], s2 = h->profiling ? st : h->side[1];
+    if (!h->profiling) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
+    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
+    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, s2>>>(A)));
+    if (!h->profiling) {
+        cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);
+        cudaStreamWaitEvent(st, h->evJoin[0], 0); cudaStreamWaitEvent(st, h->evJoin[1], 0);
+    }
     if (build) {
         // neighbour grid: the histogram was accumulated by the propose kernels (cellCount is zero at step start: k_scan_down clears it)
         LAUNCH(KID_SCAN_REDUCE, (k_scan_reduce<<<h->scanBlocks, 256, 0, st>>>((const int4 *)D.cellCount, D.scanTmp)));
@@ -538,15 +542,18 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const int gl = std::min(nblk(NT, B), 148 * 8);
     if (h->useCells) {
         if (build) LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
+        if (!build && !h->profiling) { cudaEventRecord(h->evFork[1], st); cudaStreamWaitEvent(s1, h->evFork[1], 0); }
         LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PTHREADS), 148 * 8 * 8), PTHREADS, 0, st>>>(A)));
-        if (!build) LAUNCH(KID_SPECIAL, (k_special_pairs<<<148 * 2, 32 * SP_WARPS, 0, st>>>(A)));
+        if (!build) {           // the special entries next to the list pairs (both only publish findings)
+            LAUNCH(KID_SPECIAL, (k_special_pairs<<<148, 32 * SP_WARPS, 0, s1>>>(A)));
+            if (!h->profiling) { cudaEventRecord(h->evJoin[2], s1); cudaStreamWaitEvent(st, h->evJoin[2], 0); }
+        }
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
-    LAUNCH(KID_RESTORE, (k_restore<<<nblk(NT, 256), 256, 0, st>>>(A)));
     // S3
     LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<gl, B, 0, st>>>(A)));
     LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
-    LAUNCH(KID_DISSOCIATE, (k_dissociate<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_FINISH, (k_finish<<<nblk(NT, 256), 256, 0, st>>>(A)));
 }
 static void swap_buffers(Dev &D) { std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign); }
 
@@ -759,6 +766,9 @@ extern "C" int kmc_get_events(kmc_handle *h, int64_t *ev) {
     CK(cudaMemcpy(d, h->D.events, sizeof d, cudaMemcpyDeviceToHost));
     for (int i = 0; i < EV_COUNT; i++) ev[i] = (int64_t)d[i];
     ev[EV_PASSES] = h->passes; ev[EV_LAUNCHES] = h->launches;
+    int scal[S_COUNT];
+    CK(cudaMemcpy(scal, h->D.scal, sizeof scal, cudaMemcpyDeviceToHost));
+    ev[12] = scal[S_NSURV]; ev[13] = scal[S_NSPEC]; ev[14] = scal[S_NPEND]; ev[15] = scal[S_NPAIR];      // sizes of the last step's work lists
     return KMC_OK;
 }
 

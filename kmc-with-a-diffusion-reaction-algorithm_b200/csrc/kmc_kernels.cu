@@ -5,8 +5,8 @@
 //                                                                                           the bond table changed)
 //            [propose]    k_propose_simple, k_propose_complex                              (S2a-S2f, 577-1732)
 //            [grid]       k_grid_count -> scan -> k_grid_scatter                           (cell list, new)
-//            [resolve]    k_cells_cut + k_pairs_eval | k_resolve_tiles -> k_pend_resolve -> k_restore   (S2g, 1759-1860 + ordering)
-//            [reactions]  k_react_candidates -> k_react_resolve -> k_dissociate            (S3, 1876-2141)
+//            [resolve]    k_cells_cut + k_pairs_eval | k_resolve_tiles -> k_pend_resolve                (S2g, 1759-1860 + ordering)
+//            [reactions]  k_react_pairs -> k_react_resolve -> k_finish (revert + dissociation)   (S3, 1876-2141)
 //            pointer swap                                                                  (S4, 2164-2202)
 //
 // Sequential semantics in parallel: the reference sweeps molecules in index order and every overlap test
@@ -46,8 +46,16 @@ KD void uf_union(int *parent, int a, int b) {
     }
 }
 
-__global__ void k_uf_init(const __grid_constant__ Args A) {
+// first kernel of a step when `begin` is set: one thread also advances the device-side step counter and resets the per-step
+// scalars (none of them is read by this kernel's other threads)
+__global__ void k_uf_init(const __grid_constant__ Args A, int begin) {
     KARGS
+    if (begin && blockIdx.x == 0 && threadIdx.x == 0) {
+        D.step64[0] += 1; D.scal[S_EPOCH] += 1;
+        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+        if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
+        if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
+    }
     if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cK.NT) return;
@@ -142,7 +150,10 @@ KD void register_special(const Consts &cK, const Dev &D, int entry, int cell, un
 //    ghost entry in the cell of its proposal -- and the fp32 centre of the entry (bcen), which later steps measure drift from;
 //  reuse step (phase 1): the grid and the pair list of the last build step stand; a far mover, or a molecule whose old centre
 //    has drifted more than K.drift from its entry, is SPECIAL: the stale structures do not cover it, k_special_pairs does.
-KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, int ukey, int freeFlags, unsigned stamp) {
+// oz / nz: height of a ligand's centre (0 for a receptor), kept as fp32 in the record: the resolve kernels use it to discard
+// pairs that are close in the membrane plane but far apart in z before any bead is fetched. bc = D.bcen[gid], loaded by the caller.
+KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, double oz, double nz, int ukey, int freeFlags,
+                 unsigned stamp, float2 bc) {
     const double dx = nx - ox, dy = ny - oy;
     const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
     const int rep = replica_of_gid(cK, gid);
@@ -156,7 +167,6 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
             D.farList[atomicAdd(&D.scal[S_NFAR], 1)] = make_int4(gid, c2, slot, 0);
         }
     } else {
-        const float2 bc = D.bcen[gid];
         const double ex = ox - (double)bc.x, ey = oy - (double)bc.y;
         const bool disp = ex * ex + ey * ey > cK.drift * cK.drift;
         if (disp) flags |= F_DISP;
@@ -167,25 +177,33 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
     }
     double2 *nr = reinterpret_cast<double2 *>(D.nrec) + (size_t)gid * 3;
     nr[0] = make_double2(ox, oy); nr[1] = make_double2(nx, ny);
-    reinterpret_cast<int4 *>(nr)[2] = make_int4(gid, ukey, flags, 0);
+    reinterpret_cast<int4 *>(nr)[2] = make_int4(__float_as_int((float)oz), ukey, flags, __float_as_int((float)nz));
 }
 
 // free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
-__global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant__ Args A) {
+// (two kernels, receptors and ligands: the receptor path needs a third of the registers of the ligand path, and the two run
+// side by side on forked streams of the step graph)
+template <bool REC> KD void propose_simple_body(const Args &A) {
     KARGS
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid == 0) D.scal[S_TOPO_DIRTY] = 0;       // the gated rebuild kernels of this step are done; S3 sets it again
-    if (!gid_live(cK, D, gid)) return;
-    if (D.unitOf[gid] != gid) return;             // not the head of a unit
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = REC ? idx : cK.NAt + idx;
+    if (!REC && idx == 0) D.scal[S_TOPO_DIRTY] = 0;       // the gated rebuild kernels of this step are done; S3 sets it again
+    if (REC ? idx >= nA_live(D) : idx >= nB_live(D)) return;
     const Consts &K = cK;
+    // every load this thread can need is issued before the first decision (one memory latency instead of a chain of them)
+    const int head = D.unitOf[gid];
+    const float2 bc = K.phase ? D.bcen[gid] : make_float2(0.f, 0.f);
+    int p = -1, csize = 0; Rec ra; Lig l;
+    if (REC) { p = D.recCis[gid]; ra = load_rec(D.recC, D.recS2, D.recS3, gid); }
+    else { csize = D.cxSize[idx]; load_lig(D.lig, idx, l); }
+    if (head != gid) return;                      // not the head of a unit
     const int rep = replica_of_gid(K, gid);
     const uint64_t seed = seed_of(cK, rep);
     const uint32_t me = ref_id(K, D, gid);
-    if (gid < K.NAt) {
-        const int a = gid, p = D.recCis[a];
-        Rec ra = load_rec(D.recC, D.recS2, D.recS3, a);
+    if (REC) {
+        const int a = gid;
         const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
                      u2 = keyed_uniform(seed, me, 0, step, 2);
         const double phai = mul(mul(u1, 2.0), K.pai);
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             rotz(cs, ss, t.s2x, t.s2y, t.cx, t.cy, n.s2x, n.s2y);
             rotz(cs, ss, t.s3x, t.s3y, t.cx, t.cy, n.s3x, n.s3y);
             store_rec(D.recCn, D.recS2n, D.recS3n, a, n);
-            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL | F_FREE_CIS, stamp);
+            mark_far(cK, D, a, ra.cx, ra.cy, n.cx, n.cy, 0.0, 0.0, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL | F_FREE_CIS, stamp, bc);
             if (K.mode) D.ukey[a] = unit_key(K, a, ra.cx, ra.cy);
         } else {
             // ---- S2b: this receptor is the lower index of a ligand-free cis pair ----
@@ -235,17 +253,16 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
             if (cis_misaligned(K, na, nb)) snap_cis(K, nb, na);          // "relax", main.cpp:770-799
             store_rec(D.recCn, D.recS2n, D.recS3n, a, na);
             store_rec(D.recCn, D.recS2n, D.recS3n, p, nb);
-            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp);
-            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp);
+            mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy, 0.0, 0.0, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp, bc);
+            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, 0.0, 0.0, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp, K.phase ? D.bcen[p] : bc);
             if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
     } else {
-        const int h = gid - K.NAt;
-        if (D.cxSize[h] > 1) return;             // complexes: k_propose_complex
+        const int h = idx;
+        if (csize > 1) return;                   // complexes: k_propose_complex
         // ---- S2c ----
-        Lig l; load_lig(D.lig, h, l);
-        const double ox = l.p[0][0], oy = l.p[0][1];
+        const double ox = l.p[0][0], oy = l.p[0][1], oz = l.p[0][2];
         const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
                      u2 = keyed_uniform(seed, me, 0, step, 2), u3 = keyed_uniform(seed, me, 0, step, 3),
                      u4 = keyed_uniform(seed, me, 0, step, 4), u5 = keyed_uniform(seed, me, 0, step, 5);
@@ -267,11 +284,13 @@ __global__ void __launch_bounds__(128, 5) k_propose_simple(const __grid_constant
         for (int q = 0; q < 8; q++) rot3_about(R3, l.p[q], c, n.p[q]);
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
         store_lig(D.lign, h, n);
-        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], unit_key(K, gid, ox, oy), F_FREE_RL, stamp);
+        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], oz, n.p[0][2], unit_key(K, gid, ox, oy), F_FREE_RL, stamp, bc);
         if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
     }
 }
+__global__ void __launch_bounds__(256, 4) k_propose_rec(const __grid_constant__ Args A) { propose_simple_body<true>(A); }
+__global__ void __launch_bounds__(128, 5) k_propose_lig(const __grid_constant__ Args A) { propose_simple_body<false>(A); }
 
 // ---- complexes: one WARP per ligand-rooted complex with more than one member ------------------------------------------
 // The alignment code (S2e/S2f) is sequential by nature (order-dependent snaps, shuffles, the goto state machine) and runs on
@@ -630,11 +649,11 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 if (m < K.NAt) {
                     const Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]};
                     store_rec(D.recCn, D.recS2n, D.recS3n, m, r);
-                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0), stamp);
+                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, 0.0, 0.0, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0), stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f));
                 } else {
                     double *q = D.lign + (size_t)(m - K.NAt) * 24;
                     for (int t = 0; t < 24; t++) q[t] = p[t];
-                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0, stamp);
+                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], o[2], p[2], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f));
                 }
             }
         } else if (lane == 0) {
@@ -671,8 +690,8 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
             for (int q = 0; q < size; q++) {
                 const int m = rowOut[q];
                 if (K.mode) D.ukey[m] = ckey;
-                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp); }
-                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp); }
+                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, 0.0, 0.0, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
+                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], o[2], n[2], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
             }
         }
         if (lane == 0) { D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0; }
@@ -803,7 +822,7 @@ KD void load_beads(const double *base, int h, double b[3][3]) {
 #define TCAP 384
 #endif
 
-struct TileRec { double ox, oy, nx, ny; int gid, unit; int flg; };
+struct TileRec { double ox, oy, nx, ny; float oz, nz; int gid, unit; int flg; };
 
 KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
     const int v = entry & ~GHOST_BIT;
@@ -811,7 +830,7 @@ KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
     const double2 o = nr[0], n = nr[1];
     const int4 w = reinterpret_cast<const int4 *>(nr)[2];
     TileRec r;
-    r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y; r.gid = v; r.unit = w.y; r.flg = w.z | ((entry & GHOST_BIT) ? F_GHOST : 0);
+    r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y; r.oz = __int_as_float(w.x); r.nz = __int_as_float(w.w); r.gid = v; r.unit = w.y; r.flg = w.z | ((entry & GHOST_BIT) ? F_GHOST : 0);
     return r;
 }
 
@@ -821,6 +840,7 @@ struct TileSmem {
     int inBase[TS + 1];           // prefix of interior entries per interior row
     int rowStart[TS + 3];         // index in `sorted` of the first entry of each window row
     double ox[TCAP], oy[TCAP], nx[TCAP], ny[TCAP];
+    float oz[TCAP], nz[TCAP];     // height of a ligand's centre, old / proposed
     float sx[TCAP], sy[TCAP];     // window-relative fp32 copy of the centre the entry stands for (distance cut only)
     int gid[TCAP], unit[TCAP];
     unsigned char flg[TCAP];
@@ -842,6 +862,7 @@ KD bool tile_hits(const Consts &K, const Dev &D, bool prec, double px, double py
 struct ProbeCtx {
     int m, u, flg; bool ghost, far, prec, pairsOnly, wantPairs;
     double px, py;            // proposed centre P
+    float pz;                 // its height (ligand)
     double fax, fay, fbx, fby; // the two candidate FINAL centres for S3 pre-selection (normal entry: P and O)
 };
 KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
@@ -849,7 +870,7 @@ KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
     c.m = me.gid; c.u = me.unit; c.flg = me.flg;
     c.ghost = me.flg & F_GHOST; c.far = me.flg & F_FAR; c.prec = me.gid < K.NAt;
     c.pairsOnly = !c.ghost && c.far;                 // old entry of a far mover: it is only a reaction partner here
-    c.px = me.nx; c.py = me.ny;
+    c.px = me.nx; c.py = me.ny; c.pz = me.nz;
     c.fax = c.pairsOnly ? me.ox : c.px; c.fay = c.pairsOnly ? me.oy : c.py;
     c.fbx = c.ghost ? c.px : me.ox;     c.fby = c.ghost ? c.py : me.oy;
     c.wantPairs = c.prec && (me.flg & (F_FREE_RL | F_FREE_CIS));
@@ -867,6 +888,7 @@ KD void append_pair_global(const Dev &D, unsigned long long pr) {
     else atomicOr(&D.scal[S_OVERFLOW], 4);
 }
 KD void sink_pair(const Dev &D, const PairSink &ps, unsigned long long pr) {
+    if (!ps.cnt) { append_pair_global(D, pr); return; }
     const int i = atomicAdd(ps.cnt, 1);
     if (i < ps.cap) ps.buf[i] = pr; else append_pair_global(D, pr);
 }
@@ -883,6 +905,11 @@ KD void flush_pairs(const Dev &D, const PairSink &ps, int *base) {
         }
     }
 }
+// lower bounds on a separation in z from the fp32 heights kept in the records (0.01 covers their rounding)
+KD double z_excess(double dz) { return fmax(0.0, dz - 0.01); }
+KD double z_above_stack(const Consts &K, float z) {          // from a ligand centre at height z to the receptor's bead stack [0, 6 rA]
+    return z_excess(fmax((double)z - rec_bead_z(K, 4), -(double)z));
+}
 KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf, const PairSink &ps) {
     const int v = o.gid;
     if (v == c.m) return 0;                              // the other (old/ghost) entry of the probe itself
@@ -892,13 +919,27 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
         if (vlig ? ((c.flg & F_FREE_RL) && (o.flg & F_FREE_RL)) : ((c.flg & F_FREE_CIS) && (o.flg & F_FREE_CIS))) {
             const double reach = vlig ? K.reachOn : K.reachCis;
             const double vx = vghost ? o.nx : o.ox, vy = vghost ? o.ny : o.oy;
-            double d2 = fmin((vx - c.fax) * (vx - c.fax) + (vy - c.fay) * (vy - c.fay), (vx - c.fbx) * (vx - c.fbx) + (vy - c.fby) * (vy - c.fby));
+            // a ligand binds at the receptor's bead 3 (z = 2*rA*2): its centre must also be within reach of that height
+            const double zs = rec_bead_z(K, 3);
+            const double z1 = vlig ? z_excess(fabs((double)(vghost ? o.nz : o.oz) - zs)) : 0.0, z2 = vlig ? z_excess(fabs((double)o.nz - zs)) : 0.0;
+            double d2 = fmin((vx - c.fax) * (vx - c.fax) + (vy - c.fay) * (vy - c.fay), (vx - c.fbx) * (vx - c.fbx) + (vy - c.fby) * (vy - c.fby)) + z1 * z1;
             if (!vghost && !vfar)
-                d2 = fmin(d2, fmin((o.nx - c.fax) * (o.nx - c.fax) + (o.ny - c.fay) * (o.ny - c.fay), (o.nx - c.fbx) * (o.nx - c.fbx) + (o.ny - c.fby) * (o.ny - c.fby)));
+                d2 = fmin(d2, fmin((o.nx - c.fax) * (o.nx - c.fax) + (o.ny - c.fay) * (o.ny - c.fay), (o.nx - c.fbx) * (o.nx - c.fbx) + (o.ny - c.fby) * (o.ny - c.fby)) + z2 * z2);
             if (d2 <= reach * reach) sink_pair(D, ps, ((unsigned long long)c.m << 32) | (unsigned)v);
         }
     }
     if (c.pairsOnly) return 0;
+    {   // nothing of v within reach of the probe at either of v's poses: done before any bead is fetched (most list pairs end here)
+        // (3-D: a ligand high above the membrane is out of every receptor's reach, two ligands at different heights miss each other)
+        const bool vrec = v < K.NAt;
+        double r, zo = 0.0, zn = 0.0;
+        if (c.prec && vrec) r = K.reachRR;
+        else if (c.prec) { r = K.reachRL; zo = z_above_stack(K, o.oz); zn = z_above_stack(K, o.nz); }
+        else if (vrec) { r = K.reachRL; zo = zn = z_above_stack(K, c.pz); }
+        else { r = K.reachLL; zo = z_excess(fabs((double)o.oz - (double)c.pz)); zn = z_excess(fabs((double)o.nz - (double)c.pz)); }
+        const double ax = o.ox - c.px, ay = o.oy - c.py, bx = o.nx - c.px, by = o.ny - c.py;
+        if (fmin(ax * ax + ay * ay + zo * zo, bx * bx + by * by + zn * zn) > r * r) return 0;
+    }
     double pb[3][3];
     if (!c.prec) load_beads(D.lign, c.m - K.NAt, pb);
     const int uv = o.unit;
@@ -991,7 +1032,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
         int lo = 0, hi = nrow;                      // largest r with rowBase[r] <= i
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.rowBase[mid] <= i) lo = mid; else hi = mid; }
         const TileRec t = fetch_rec(K, D, __ldg(&D.sorted[S.rowStart[lo] + (i - S.rowBase[lo])]));
-        S.ox[i] = t.ox; S.oy[i] = t.oy; S.nx[i] = t.nx; S.ny[i] = t.ny; S.gid[i] = t.gid; S.unit[i] = t.unit; S.flg[i] = (unsigned char)t.flg;
+        S.ox[i] = t.ox; S.oy[i] = t.oy; S.nx[i] = t.nx; S.ny[i] = t.ny; S.oz[i] = t.oz; S.nz[i] = t.nz; S.gid[i] = t.gid; S.unit[i] = t.unit; S.flg[i] = (unsigned char)t.flg;
         const bool g = t.flg & F_GHOST;                                   // what this entry stands for, window-relative, fp32 (cut only)
         S.sx[i] = (float)(hash_x(K, g ? t.nx : t.ox) - tox); S.sy[i] = (float)((g ? t.ny : t.oy) - toy);
     }
@@ -1000,7 +1041,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
             S.cs[r][c] = __ldg(&D.cellStart[(size_t)(rep * K.ncy + wy0 + r) * K.ncx + wx0 + c]);
     __syncthreads();
     TICK();
-    auto staged = [&](int i) -> TileRec { TileRec t; t.ox = S.ox[i]; t.oy = S.oy[i]; t.nx = S.nx[i]; t.ny = S.ny[i]; t.gid = S.gid[i]; t.unit = S.unit[i]; t.flg = S.flg[i]; return t; };
+    auto staged = [&](int i) -> TileRec { TileRec t; t.ox = S.ox[i]; t.oy = S.oy[i]; t.nx = S.nx[i]; t.ny = S.ny[i]; t.oz = S.oz[i]; t.nz = S.nz[i]; t.gid = S.gid[i]; t.unit = S.unit[i]; t.flg = S.flg[i]; return t; };
     const int nin = S.inBase[nir];
     const bool fits = total <= TCAP;
     // squared cut radii (fp32, with a safety margin): overlap reach + one skin (the neighbour's pose moves at most a skin from
@@ -1108,11 +1149,18 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
 #endif
 // classification of one surviving pair straight from the records (also the overflow path of k_cells_cut: not inlined there,
 // so the cut keeps its small register footprint)
+KD void eval_rec_pair(const Consts &K, const Dev &D, const TileRec &a, const TileRec &b, const PairSink &ps) {
+#pragma unroll 1
+    for (int dir = 0; dir < 2; dir++) {
+        int cf = -1;
+        const ProbeCtx pc = make_probe(K, dir ? b : a);
+        const int rr = pair_eval(K, D, pc, dir ? a : b, &cf, ps);
+        publish(D, pc.u, rr, cf);
+    }
+}
+// an unordered pair of grid entries: each entry is the probe once
 KD void eval_entry_pair(const Consts &K, const Dev &D, int entry, int en, const PairSink &ps) {
-    const ProbeCtx pc = make_probe(K, fetch_rec(K, D, entry));
-    int cf = -1;
-    const int rr = pair_eval(K, D, pc, fetch_rec(K, D, en), &cf, ps);
-    publish(D, pc.u, rr, cf);
+    eval_rec_pair(K, D, fetch_rec(K, D, entry), fetch_rec(K, D, en), ps);
 }
 __device__ __noinline__ void eval_entry_pair_slow(const Args &A, int entry, int en) {
     const PairSink none = {nullptr, nullptr, 0};
@@ -1129,9 +1177,10 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
     // overlap reach + 2 skins and S3 reach + 2 skins bound every test pair_eval can make. fp32 with a margin that covers the
     // rounding of the stored coordinates (K.cutMargin, from the box size).
     const float mg = K.cutMargin, sk2 = 2 * (float)K.skin + 2 * (float)K.drift;     // (+ the drift allowed while the list is reused)
+    // every UNORDERED pair of entries is listed once (by its lower entry index) and classified in both directions, so the
+    // receptor-ligand radius is the larger of the two directions' needs
     const float cRR = fmaxf((float)K.ovAA, (float)K.reachCis) + sk2 + mg, cRL = fmaxf((float)K.reachRL, (float)K.reachOn) + sk2 + mg,
-                cLR = (float)K.reachRL + sk2 + mg, cLL = (float)K.reachLL + sk2 + mg;
-    const float gx0 = (float)K.gx0, gy0 = (float)K.gy0, cinv = (float)K.cellInv;
+                cLR = cRL, cLL = (float)K.reachLL + sk2 + mg;
     const int *__restrict__ sorted = D.sorted;
     const float2 *__restrict__ scen = D.scen;
     for (int base = blockIdx.x * CTHREADS; base < total; base += gridDim.x * CTHREADS) {
@@ -1161,7 +1210,7 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
                     const int en = __ldg(&sorted[i]);
                     const float2 c = __ldg(&scen[i]);
                     const float ex = c.x - w.x, ey = c.y - w.y;
-                    if (ex * ex + ey * ey > ((en & ~GHOST_BIT) < K.NAt ? cR2 : cL2) || i == e) continue;
+                    if (ex * ex + ey * ey > ((en & ~GHOST_BIT) < K.NAt ? cR2 : cL2) || i <= e) continue;
                     const int slot = atomicAdd(&nsurv, 1);
                     if (slot < CSURV) surv[slot] = make_int2(entry, en);
                     else {                                                      // CTA list full (crowded spot): append one by one
@@ -1188,7 +1237,10 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
 #ifndef PTHREADS
 #define PTHREADS 128
 #endif
-__global__ void __launch_bounds__(PTHREADS, 8) k_pairs_eval(const __grid_constant__ Args A) {
+#ifndef PMINB
+#define PMINB 5
+#endif
+__global__ void __launch_bounds__(PTHREADS, PMINB) k_pairs_eval(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
     __shared__ unsigned long long pbuf[PTHREADS];
@@ -1206,12 +1258,7 @@ __global__ void __launch_bounds__(PTHREADS, 8) k_pairs_eval(const __grid_constan
                 // reuse step: ghost entries belong to the build step only; a molecule that is special this step (far mover or
                 // displaced) is not where the list believes it to be and is handled by k_special_pairs instead
                 const TileRec a = fetch_rec(K, D, w.x), b = fetch_rec(K, D, w.y);
-                if (!((a.flg | b.flg) & (F_FAR | F_DISP))) {
-                    int cf = -1;
-                    const ProbeCtx pc = make_probe(K, a);
-                    const int rr = pair_eval(K, D, pc, b, &cf, ps);
-                    publish(D, pc.u, rr, cf);
-                }
+                if (!((a.flg | b.flg) & (F_FAR | F_DISP))) eval_rec_pair(K, D, a, b, ps);
             }
         }
         __syncthreads();
@@ -1259,12 +1306,7 @@ __global__ void __launch_bounds__(32 * SP_WARPS) k_special_pairs(const __grid_co
                     if (n == f) continue;
                     const TileRec rn = fetch_rec(K, D, n);
                     if (rn.flg & (F_FAR | F_DISP)) continue;              // special as well: met through the chains below
-                    int cf = -1;
-                    int rr = pair_eval(K, D, pf, rn, &cf, ps);
-                    publish(D, pf.u, rr, cf);
-                    const ProbeCtx pn = make_probe(K, rn);
-                    cf = -1; rr = pair_eval(K, D, pn, rf, &cf, ps);
-                    publish(D, pn.u, rr, cf);
+                    eval_rec_pair(K, D, rf, rn, ps);
                 }
             }
             // the chains of special entries of the same 3x3 cells, one cell per lane
@@ -1329,28 +1371,6 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
     }
 }
 
-// revert the members of rejected units (main.cpp:666-674, 851-863, 1831-1860)
-__global__ void k_restore(const __grid_constant__ Args A) {
-    KARGS
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    bool rejHead = false, rej = false;
-    if (gid_live(cK, D, gid)) {
-        const int u = D.unitOf[gid];
-        const int r = D.unitRes[u];
-        rej = r & 1; rejHead = rej && u == gid;
-        if (r == 2) atomicOr(&D.scal[S_OVERFLOW], 8);          // cannot happen: the pending findings always settle
-    }
-    const unsigned nrej = __popc(__ballot_sync(0xffffffffu, rejHead));
-    if (nrej && (threadIdx.x & 31) == 0) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
-    if (!rej) return;
-    if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
-    else {
-        const double2 *s = reinterpret_cast<const double2 *>(D.lig + (size_t)(gid - cK.NAt) * 24);
-        double2 *d = reinterpret_cast<double2 *>(D.lign + (size_t)(gid - cK.NAt) * 24);
-        for (int q = 0; q < 12; q++) d[q] = s[q];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // S3 reactions
 // ------------------------------------------------------------------------------------------------
@@ -1368,12 +1388,14 @@ __global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Arg
         const int rep = a / K.NA;
         const uint64_t seed = seed_of(K, rep);
         const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
-        const Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
+        // final pose of a molecule: its proposal, or its old pose if its unit was reverted (the copy-back happens in k_finish)
+        const bool rejA = D.unitRes[D.unitOf[a]] & 1, rejV = D.unitRes[D.unitOf[v]] & 1;
+        const Rec ra = rejA ? load_rec(D.recC, D.recS2, D.recS3, a) : load_rec(D.recCn, D.recS2n, D.recS3n, a);
         if (v >= K.NAt) {
             if (D.recLig[a] >= 0) continue;
             const int h = v - K.NAt;
             int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
-            Lig b; load_lig(D.lign, h, b);
+            Lig b; load_lig(rejV ? D.lig : D.lign, h, b);
             for (int s = 0; s < 3; s++) {
                 if (occ[s] >= 0 || !rl_geometry_ok(K, ra, b, s)) continue;
                 if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
@@ -1384,7 +1406,7 @@ __global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Arg
             }
         } else {
             if (D.recCis[a] >= 0 || D.recCis[v] >= 0) continue;
-            const Rec rb = load_rec(D.recCn, D.recS2n, D.recS3n, v);
+            const Rec rb = rejV ? load_rec(D.recC, D.recS2, D.recS3, v) : load_rec(D.recCn, D.recS2n, D.recS3n, v);
             if (!cis_geometry_ok(K, ra, rb)) continue;
             const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
             const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
@@ -1444,14 +1466,35 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
     }
 }
 
-// S3c, main.cpp:2062-2141. Keyed draws make the three sequential loops order free: a thread owns the R-L bond of
-// its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L outcome from the
-// partner's own keyed draw instead of waiting for it.
-__global__ void k_dissociate(const __grid_constant__ Args A) {
+// Last kernel of a step, one thread per molecule:
+//  (1) revert the members of rejected units (main.cpp:666-674, 851-863, 1831-1860): copy the old pose over the proposal;
+//  (2) S3c, main.cpp:2062-2141, for receptors. Keyed draws make the three sequential loops order free: a thread owns the R-L
+//      bond of its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L outcome from the
+//      partner's own keyed draw instead of waiting for it.
+__global__ void k_finish(const __grid_constant__ Args A) {
     KARGS
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gid_live(cK, D, gid);
+    bool rejHead = false, rej = false;
+    if (live) {
+        const int u = D.unitOf[gid];
+        const int r = D.unitRes[u];
+        rej = r & 1; rejHead = rej && u == gid;
+        if (r == 2) atomicOr(&D.scal[S_OVERFLOW], 8);          // cannot happen: the pending findings always settle
+    }
+    const unsigned nrej = __popc(__ballot_sync(0xffffffffu, rejHead));
+    if (nrej && (threadIdx.x & 31) == 0) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
+    if (rej) {
+        if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
+        else {
+            const double2 *s = reinterpret_cast<const double2 *>(D.lig + (size_t)(gid - cK.NAt) * 24);
+            double2 *d = reinterpret_cast<double2 *>(D.lign + (size_t)(gid - cK.NAt) * 24);
+            for (int q = 0; q < 12; q++) d[q] = s[q];
+        }
+    }
+    if (!live || gid >= cK.NAt) return;
     const uint64_t step = D.step64[0];
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= nA_live(D)) return;
+    const int a = gid;
     const Consts &K = cK;
     const int rep = a / K.NA;
     const uint64_t seed = seed_of(cK, rep);

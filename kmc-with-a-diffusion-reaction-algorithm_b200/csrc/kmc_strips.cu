@@ -452,8 +452,8 @@ extern "C" int kmc_strip_begin_refresh_dev(kmc_handle *h) {
     const Args A{h->D, h->K};
     const int NT = h->NT, NAt = h->NAt, NBt = h->NBt, B = 128;
     // complexes of the CURRENT bond table (the last step's reactions may have changed it)
-    LAUNCH(KID_STEP_BEGIN, (k_strip_prebuild<<<1, 1, 0, st>>>(A)));
-    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_UF_INIT, (k_strip_prebuild<<<1, 1, 0, st>>>(A)));
+    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A, 0)));
     LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
     LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));

@@ -363,7 +363,8 @@ class Kmc:
         self._ck(lib().kmc_get_events(self.h, e.ctypes.data))
         return dict(rl_on=int(e[0]), mono_cis_on=int(e[1]), cis_on=int(e[2]), rl_off=int(e[3]), mono_cis_off=int(e[4]),
                     cis_off=int(e[5]), reverted=int(e[6]), tried=int(e[7]), far=int(e[8]), passes=int(e[9]),
-                    rebuilds=int(e[10]), launches=int(e[11]))
+                    rebuilds=int(e[10]), launches=int(e[11]), list_pairs=int(e[12]), special_entries=int(e[13]),
+                    pending_findings=int(e[14]), reaction_pairs=int(e[15]))
 
     def write_bond_dat(self, path, replica=0):
         self._ck(lib().kmc_write_bond_dat(self.h, replica, os.fsencode(path)))
