@@ -17,6 +17,7 @@ enum Scalar {
     S_TOPO_DIRTY,         // bond table changed: complexes must be rebuilt before the next sweep
     S_OVERFLOW,           // a device buffer overflowed (bitmask)
     S_NSURV,              // pairs in surv[] this step
+    S_NREJ,               // rejected units of this step (rejList)
     S_NA_LIVE, S_NB_LIVE, // molecules actually present in the receptor / ligand blocks (<= NAt / NBt; strips change them)
     S_COUNT = 16
 };
@@ -49,7 +50,8 @@ struct Dev {
     int *sorted;                           // [2*NT] entries gid | ghost bit
     float2 *scen;                          // [2*NT] fp32 centre each entry stands for (old centre; proposed centre for a ghost), cell-sorted like `sorted`
     int *scell;                            // [2*NT] cell of each entry
-    int2 *surv; int survCap;               // pairs that passed the distance cut of k_cells_cut (probe entry, neighbour entry)
+    int2 *surv; int survCap;               // unordered entry pairs that passed the distance cut of k_cells_cut
+    unsigned char *survFlag;               // [survCap] per list pair: directions that may react in S3 (bit0 first->second, bit1 second->first)
     int *molSlot;                          // [NT]
     int4 *farList;                         // [NT] (gid, cell, slot, -)
     // list reuse (sparse path): the grid and the pair list of a build step serve the following steps as well
@@ -63,6 +65,7 @@ struct Dev {
     unsigned long long *pairs; int pairCap;   // (receptor, neighbour) pairs that may react this step
     int *unitRes;                             // [NT] per unit head: 0 accepted, bit0 rejected (definite overlap), 2 = waits on pending findings
     int *pendCnt;                             // [NT] per unit head: pending findings not yet settled
+    int *rejList;                             // [NT] heads of the units rejected this step (each once): their members are copied back
     int2 *pendList; int pendCap;              // (unit head, earlier unit | bit30: overlap is with its NEW pose)
     unsigned long long *step64;               // [1] mc_time_step of the step being computed
     unsigned *refA, *refB;                    // reference (global, 1-based) ids of local receptors / ligands; null = a%NA+1, NA+h%NB+1

@@ -217,7 +217,7 @@ static bool ensure_cells_arrays(kmc_handle *h) {
     bool ok = true;
     if (!D.scen) {
         D.survCap = 8 * K.NT + 4096;
-        ok = dalloc(h, &D.scen, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.scell, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.surv, (size_t)D.survCap) == cudaSuccess &&
+        ok = dalloc(h, &D.scen, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.scell, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.surv, (size_t)D.survCap) == cudaSuccess && dalloc(h, &D.survFlag, (size_t)D.survCap) == cudaSuccess &&
              dalloc(h, &D.bcen, (size_t)K.NT) == cudaSuccess && dalloc(h, &D.specList, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.specNext, (size_t)2 * K.NT) == cudaSuccess;
     }
     if (ok && h->cellHeadCap < D.ncell) { ok = dalloc(h, &D.cellHead, (size_t)D.ncell) == cudaSuccess; h->cellHeadCap = D.ncell; }
@@ -284,7 +284,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     ok = ok && ensure_cells_arrays(h); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
-    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); D.pendCap = 2 * K.NT + 4096; A(pendList, D.pendCap); A(step64, 1);
+    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); A(rejList, K.NT); D.pendCap = 2 * K.NT + 4096; A(pendList, D.pendCap); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
 #undef A
     ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 6) == cudaSuccess;
@@ -521,12 +521,14 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     // S2 proposals: free receptors / cis dimers, free ligands and complexes are disjoint sets of molecules -- three kernels side
     // by side (forked branches of the graph; on one stream when per-kernel timing is on)
-    cudaStream_t s1 = h->profiling ? st : h->side[0], s2 = h->profiling ? st : h->side[1];
-    if (!h->profiling) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
+    const int forkMask = h->profiling ? 0 : (getenv("KMC_FORK") ? atoi(getenv("KMC_FORK")) : 2);     // bit0: proposals (measured slower than back to back), bit1: special entries
+    const bool fork = forkMask & 1, fork2 = forkMask & 2;
+    cudaStream_t s1 = fork ? h->side[0] : st, s2 = fork ? h->side[1] : st;
+    if (fork) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, s2>>>(A)));
-    if (!h->profiling) {
+    if (fork) {
         cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);
         cudaStreamWaitEvent(st, h->evJoin[0], 0); cudaStreamWaitEvent(st, h->evJoin[1], 0);
     }
@@ -542,18 +544,19 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const int gl = std::min(nblk(NT, B), 148 * 8);
     if (h->useCells) {
         if (build) LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
-        if (!build && !h->profiling) { cudaEventRecord(h->evFork[1], st); cudaStreamWaitEvent(s1, h->evFork[1], 0); }
+        cudaStream_t s3 = fork2 ? h->side[0] : st;
+        if (!build && fork2) { cudaEventRecord(h->evFork[1], st); cudaStreamWaitEvent(s3, h->evFork[1], 0); }
         LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PTHREADS), 148 * 8 * 8), PTHREADS, 0, st>>>(A)));
         if (!build) {           // the special entries next to the list pairs (both only publish findings)
-            LAUNCH(KID_SPECIAL, (k_special_pairs<<<148, 32 * SP_WARPS, 0, s1>>>(A)));
-            if (!h->profiling) { cudaEventRecord(h->evJoin[2], s1); cudaStreamWaitEvent(st, h->evJoin[2], 0); }
+            LAUNCH(KID_SPECIAL, (k_special_pairs<<<148, 32 * SP_WARPS, 0, s3>>>(A)));
+            if (fork2) { cudaEventRecord(h->evJoin[2], s3); cudaStreamWaitEvent(st, h->evJoin[2], 0); }
         }
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
     // S3
-    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<gl, B, 0, st>>>(A)));
+    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 4 + 1, RP_CHUNK) + 148, 148 * 16), B, 0, st>>>(A)));
     LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
-    LAUNCH(KID_FINISH, (k_finish<<<nblk(NT, 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
 }
 static void swap_buffers(Dev &D) { std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign); }
 

@@ -5,8 +5,8 @@
 //                                                                                           the bond table changed)
 //            [propose]    k_propose_simple, k_propose_complex                              (S2a-S2f, 577-1732)
 //            [grid]       k_grid_count -> scan -> k_grid_scatter                           (cell list, new)
-//            [resolve]    k_cells_cut + k_pairs_eval | k_resolve_tiles -> k_pend_resolve                (S2g, 1759-1860 + ordering)
-//            [reactions]  k_react_pairs -> k_react_resolve -> k_finish (revert + dissociation)   (S3, 1876-2141)
+//            [resolve]    k_cells_cut + k_pairs_eval | k_resolve_tiles -> k_pend_resolve (+ revert)     (S2g, 1759-1860 + ordering)
+//            [reactions]  k_react_pairs -> k_react_resolve -> k_finish (dissociation)            (S3, 1876-2141)
 //            pointer swap                                                                  (S4, 2164-2202)
 //
 // Sequential semantics in parallel: the reference sweeps molecules in index order and every overlap test
@@ -52,7 +52,7 @@ __global__ void k_uf_init(const __grid_constant__ Args A, int begin) {
     KARGS
     if (begin && blockIdx.x == 0 && threadIdx.x == 0) {
         D.step64[0] += 1; D.scal[S_EPOCH] += 1;
-        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0;
+        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0;
         if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
         if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
     }
@@ -180,29 +180,25 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
     reinterpret_cast<int4 *>(nr)[2] = make_int4(__float_as_int((float)oz), ukey, flags, __float_as_int((float)nz));
 }
 
-// free receptor (main.cpp:584-636), ligand-free cis dimer (682-799), free ligand (905-969): one thread per molecule
-// (two kernels, receptors and ligands: the receptor path needs a third of the registers of the ligand path, and the two run
-// side by side on forked streams of the step graph)
-template <bool REC> KD void propose_simple_body(const Args &A) {
+// free receptor (main.cpp:584-636), ligand-free cis dimer (682-799): one thread per receptor. (Receptors and ligands are
+// separate kernels: the receptor path needs far fewer registers, and the two run side by side on forked branches of the step graph.)
+KD void propose_rec_body(const Args &A) {
     KARGS
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gid = REC ? idx : cK.NAt + idx;
-    if (!REC && idx == 0) D.scal[S_TOPO_DIRTY] = 0;       // the gated rebuild kernels of this step are done; S3 sets it again
-    if (REC ? idx >= nA_live(D) : idx >= nB_live(D)) return;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nA_live(D)) return;
     const Consts &K = cK;
     // every load this thread can need is issued before the first decision (one memory latency instead of a chain of them)
     const int head = D.unitOf[gid];
     const float2 bc = K.phase ? D.bcen[gid] : make_float2(0.f, 0.f);
-    int p = -1, csize = 0; Rec ra; Lig l;
-    if (REC) { p = D.recCis[gid]; ra = load_rec(D.recC, D.recS2, D.recS3, gid); }
-    else { csize = D.cxSize[idx]; load_lig(D.lig, idx, l); }
+    const int p = D.recCis[gid];
+    Rec ra = load_rec(D.recC, D.recS2, D.recS3, gid);
     if (head != gid) return;                      // not the head of a unit
     const int rep = replica_of_gid(K, gid);
     const uint64_t seed = seed_of(cK, rep);
     const uint32_t me = ref_id(K, D, gid);
-    if (REC) {
+    {
         const int a = gid;
         const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
                      u2 = keyed_uniform(seed, me, 0, step, 2);
@@ -213,7 +209,7 @@ template <bool REC> KD void propose_simple_body(const Args &A) {
             const double amp = mul(K.ampA, u0);
             const double shx = mul(amp, cp), shy = mul(amp, sp);
             Rec t = {add(ra.cx, shx), add(ra.cy, shy), add(ra.s2x, shx), add(ra.s2y, shy), add(ra.s3x, shx), add(ra.s3y, shy)};
-            const double PBx = mul(K.Lx, round(dvd(t.cx, K.Lx))), PBy = mul(K.Ly, round(dvd(t.cy, K.Ly)));
+            const double PBx = wrap_offset(t.cx, K.Lx), PBy = wrap_offset(t.cy, K.Ly);
             t.cx = sub(t.cx, PBx); t.s2x = sub(t.s2x, PBx); t.s3x = sub(t.s3x, PBx);
             t.cy = sub(t.cy, PBy); t.s2y = sub(t.s2y, PBy); t.s3y = sub(t.s3y, PBy);
             const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotA);
@@ -258,10 +254,53 @@ template <bool REC> KD void propose_simple_body(const Args &A) {
             if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
-    } else {
-        const int h = idx;
-        if (csize > 1) return;                   // complexes: k_propose_complex
-        // ---- S2c ----
+    }
+}
+#ifndef RECMINB
+#define RECMINB 4
+#endif
+#ifndef LIGMINB
+#define LIGMINB 5
+#endif
+__global__ void __launch_bounds__(256, RECMINB) k_propose_rec(const __grid_constant__ Args A) { propose_rec_body(A); }
+
+// ---- free ligands (S2c, main.cpp:905-969): one thread per ligand, poses staged through shared memory -------------------------
+// A ligand pose is 192 contiguous bytes (AoS). Thread-per-ligand global access would touch 32 half-used sectors per warp
+// instruction; instead the CTA copies its 128 poses (24 KB, contiguous) with fully coalesced 16-byte accesses into a padded
+// tile (row stride 13 x 16 B: conflict-free 128-bit row reads), every thread works on its own row, and the proposals go
+// back the same way. Rows of ligands that do not move here (members of complexes: k_propose_complex writes those) are not stored.
+#define LIG_TILE 128
+__global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    __shared__ double2 tile[LIG_TILE][13];
+    __shared__ unsigned char moved[LIG_TILE];
+    const uint64_t step = D.step64[0];
+    const unsigned stamp = (unsigned)D.scal[S_EPOCH];
+    const int h0 = blockIdx.x * LIG_TILE, h = h0 + threadIdx.x, gid = K.NAt + h;
+    if (h == 0) D.scal[S_TOPO_DIRTY] = 0;         // the gated rebuild kernels of this step are done; S3 sets it again
+    const int nrows = min(LIG_TILE, nB_live(D) - h0);
+    if (nrows <= 0) return;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(D.lig) + (size_t)h0 * 12;
+        for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; tile[r][i - r * 12] = src[i]; }
+    }
+    const bool live = threadIdx.x < nrows;
+    // the scalar words of this thread's ligand travel in the same latency window as the tile
+    int head = -1, csize = 0; float2 bc = make_float2(0.f, 0.f);
+    if (live) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; }
+    __syncthreads();
+    const bool act = live && head == gid && csize <= 1;          // a free ligand (complexes: k_propose_complex)
+    moved[threadIdx.x] = act ? 1 : 0;
+    if (act) {
+        Lig l;
+        {
+            double *d = &l.p[0][0];
+#pragma unroll
+            for (int q = 0; q < 12; q++) { const double2 v = tile[threadIdx.x][q]; d[2 * q] = v.x; d[2 * q + 1] = v.y; }
+        }
+        const uint64_t seed = seed_of(cK, replica_of_gid(K, gid));
+        const uint32_t me = ref_id(K, D, gid);
         const double ox = l.p[0][0], oy = l.p[0][1], oz = l.p[0][2];
         const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
                      u2 = keyed_uniform(seed, me, 0, step, 2), u3 = keyed_uniform(seed, me, 0, step, 3),
@@ -271,10 +310,11 @@ template <bool REC> KD void propose_simple_body(const Args &A) {
         double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
         const double shx = mul(mul(amp, st), cp), shy = mul(mul(amp, st), sp), shz = mul(amp, ct);
         for (int q = 0; q < 8; q++) { l.p[q][0] = add(l.p[q][0], shx); l.p[q][1] = add(l.p[q][1], shy); l.p[q][2] = add(l.p[q][2], shz); }
-        const double PBx = mul(K.Lx, round(dvd(l.p[0][0], K.Lx))), PBy = mul(K.Ly, round(dvd(l.p[0][1], K.Ly))),
-                     PBz = mul(K.Lz, round(dvd(l.p[0][2], K.Lz)));
-        if (l.p[0][2] > K.Lz || l.p[0][2] < 0)
+        const double PBx = wrap_offset(l.p[0][0], K.Lx), PBy = wrap_offset(l.p[0][1], K.Ly);
+        if (l.p[0][2] > K.Lz || l.p[0][2] < 0) {
+            const double PBz = mul(K.Lz, round(dvd(l.p[0][2], K.Lz)));
             for (int q = 0; q < 8; q++) l.p[q][2] = add(-l.p[q][2], mul(2.0, PBz));     // reflect, main.cpp:925-931
+        }
         for (int q = 0; q < 8; q++) { l.p[q][0] = sub(l.p[q][0], PBx); l.p[q][1] = sub(l.p[q][1], PBy); }
         const double rt = mul(sub(mul(2.0, u3), 1.0), K.rotB), rp = mul(sub(mul(2.0, u4), 1.0), K.rotB),
                      rs = mul(sub(mul(2.0, u5), 1.0), K.rotB);
@@ -283,14 +323,22 @@ template <bool REC> KD void propose_simple_body(const Args &A) {
         const double c[3] = {l.p[0][0], l.p[0][1], l.p[0][2]};
         for (int q = 0; q < 8; q++) rot3_about(R3, l.p[q], c, n.p[q]);
         n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
-        store_lig(D.lign, h, n);
+        {
+            const double *d = &n.p[0][0];
+#pragma unroll
+            for (int q = 0; q < 12; q++) tile[threadIdx.x][q] = make_double2(d[2 * q], d[2 * q + 1]);
+        }
         mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], oz, n.p[0][2], unit_key(K, gid, ox, oy), F_FREE_RL, stamp, bc);
         if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
     }
+    __syncthreads();
+    {
+        double2 *dst = reinterpret_cast<double2 *>(D.lign) + (size_t)h0 * 12;
+        for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; if (moved[r]) dst[i] = tile[r][i - r * 12]; }
+    }
 }
-__global__ void __launch_bounds__(256, 4) k_propose_rec(const __grid_constant__ Args A) { propose_simple_body<true>(A); }
-__global__ void __launch_bounds__(128, 5) k_propose_lig(const __grid_constant__ Args A) { propose_simple_body<false>(A); }
+
 
 // ---- complexes: one WARP per ligand-rooted complex with more than one member ------------------------------------------
 // The alignment code (S2e/S2f) is sequential by nature (order-dependent snaps, shuffles, the goto state machine) and runs on
@@ -881,13 +929,16 @@ KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
 // *conf = that unit (bit 30 set if the overlapping pose is its NEW one)
 // S3 candidate pairs found by a CTA are collected in shared memory and appended to D.pairs with ONE atomicAdd per CTA
 // (a per-pair atomicAdd on the single global counter serialises ~1e5 atomics per step at the L2)
-struct PairSink { unsigned long long *buf; int *cnt; int cap; };
+// (k_pairs_eval does not collect at all: a list pair remembers in one byte which of its two directions is a candidate, and
+// k_react_pairs runs over the list again: flag != nullptr, bit = 1 for (first, second), 2 for (second, first))
+struct PairSink { unsigned long long *buf; int *cnt; int cap; int *flag; int bit; };
 KD void append_pair_global(const Dev &D, unsigned long long pr) {
     int p = atomicAdd(&D.scal[S_NPAIR], 1);
     if (p < D.pairCap) D.pairs[p] = pr;
     else atomicOr(&D.scal[S_OVERFLOW], 4);
 }
 KD void sink_pair(const Dev &D, const PairSink &ps, unsigned long long pr) {
+    if (ps.flag) { *ps.flag |= ps.bit; return; }
     if (!ps.cnt) { append_pair_global(D, pr); return; }
     const int i = atomicAdd(ps.cnt, 1);
     if (i < ps.cap) ps.buf[i] = pr; else append_pair_global(D, pr);
@@ -963,10 +1014,13 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
 // bit1 = undecided. A finding that depends on ONE pose of an earlier unit (res == 2) is appended to the pending list as
 // (unit, earlier unit | pose bit); after the pass the pending findings alone decide what is left (k_pend_resolve): no geometry
 // is ever evaluated twice and nothing after the pass needs the neighbour grid.
+KD void reject_unit(const Dev &D, int u) {              // whoever sets the bit first also lists the unit for the copy-back
+    if (!(atomicOr(&D.unitRes[u], 1) & 1)) D.rejList[atomicAdd(&D.scal[S_NREJ], 1)] = u;
+}
 KD void publish(const Dev &D, int ukey, int res, int conf) {
     if (!res) return;
     const int u = ukey & UNIT_MASK;
-    if (res & 1) { atomicOr(&D.unitRes[u], 1); return; }
+    if (res & 1) { reject_unit(D, u); return; }
     atomicOr(&D.unitRes[u], 2);
     atomicAdd(&D.pendCnt[u], 1);
     const int i = atomicAdd(&D.scal[S_NPEND], 1);
@@ -989,7 +1043,7 @@ __global__ void __launch_bounds__(TTHREADS, TMINB) k_resolve_tiles(const __grid_
     __shared__ int nsurv;
     __shared__ unsigned long long pbuf[TPAIRS];
     __shared__ int pcnt, pbase;
-    const PairSink ps = {pbuf, &pcnt, TPAIRS};
+    const PairSink ps = {pbuf, &pcnt, TPAIRS, nullptr, 0};
     const int ts = K.tileEdge;        // tile edge in cells (<= TS), chosen from the mean cell occupancy so that a window fits the staging buffers
     const int ntx = (K.ncx + ts - 1) / ts, nty = (K.ncy + ts - 1) / ts;
     int b = blockIdx.x;
@@ -1154,7 +1208,8 @@ KD void eval_rec_pair(const Consts &K, const Dev &D, const TileRec &a, const Til
     for (int dir = 0; dir < 2; dir++) {
         int cf = -1;
         const ProbeCtx pc = make_probe(K, dir ? b : a);
-        const int rr = pair_eval(K, D, pc, dir ? a : b, &cf, ps);
+        PairSink pd = ps; pd.bit = 1 << dir;
+        const int rr = pair_eval(K, D, pc, dir ? a : b, &cf, pd);
         publish(D, pc.u, rr, cf);
     }
 }
@@ -1163,7 +1218,7 @@ KD void eval_entry_pair(const Consts &K, const Dev &D, int entry, int en, const 
     eval_rec_pair(K, D, fetch_rec(K, D, entry), fetch_rec(K, D, en), ps);
 }
 __device__ __noinline__ void eval_entry_pair_slow(const Args &A, int entry, int en) {
-    const PairSink none = {nullptr, nullptr, 0};
+    const PairSink none = {nullptr, nullptr, 0, nullptr, 0};
     eval_entry_pair(A.K, A.D, entry, en, none);
 }
 __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_constant__ Args A) {
@@ -1195,22 +1250,20 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
             const int crow = cell / K.ncx, cx = cell - crow * K.ncx;            // crow = replica * ncy + cy
             const int cy = crow % K.ncy;
             const int x0 = max(cx - 1, 0), x1 = min(cx + 1, K.ncx - 1);
-            const int r0 = crow - (cy > 0 ? 1 : 0), r1 = crow + (cy < K.ncy - 1 ? 1 : 0);
-            int e0[3], e1[3];
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const int rr = min(r0 + r, r1);
-                const int *row = D.cellStart + (size_t)rr * K.ncx;
-                e0[r] = __ldg(row + x0); e1[r] = (r0 + r <= r1) ? __ldg(row + x1 + 1) : e0[r];
-            }
+            // only partners with a HIGHER entry index (the pair is listed once): the rest of this entry's own row of cells,
+            // then the row above; entries of the row below come earlier in the cell order and list this entry themselves
+            int e0[2], e1[2];
+            e0[0] = e + 1; e1[0] = __ldg(D.cellStart + (size_t)crow * K.ncx + x1 + 1);
+            e0[1] = e1[1] = 0;
+            if (cy < K.ncy - 1) { const int *row = D.cellStart + (size_t)(crow + 1) * K.ncx; e0[1] = __ldg(row + x0); e1[1] = __ldg(row + x1 + 1); }
             const float cR2 = prec ? cRR * cRR : cLR * cLR, cL2 = prec ? cRL * cRL : cLL * cLL;
 #pragma unroll
-            for (int r = 0; r < 3; r++)
+            for (int r = 0; r < 2; r++)
                 for (int i = e0[r]; i < e1[r]; i++) {
                     const int en = __ldg(&sorted[i]);
                     const float2 c = __ldg(&scen[i]);
                     const float ex = c.x - w.x, ey = c.y - w.y;
-                    if (ex * ex + ey * ey > ((en & ~GHOST_BIT) < K.NAt ? cR2 : cL2) || i <= e) continue;
+                    if (ex * ex + ey * ey > ((en & ~GHOST_BIT) < K.NAt ? cR2 : cL2)) continue;
                     const int slot = atomicAdd(&nsurv, 1);
                     if (slot < CSURV) surv[slot] = make_int2(entry, en);
                     else {                                                      // CTA list full (crowded spot): append one by one
@@ -1243,27 +1296,19 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
 __global__ void __launch_bounds__(PTHREADS, PMINB) k_pairs_eval(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
-    __shared__ unsigned long long pbuf[PTHREADS];
-    __shared__ int pcnt, pbase;
-    const PairSink ps = {pbuf, &pcnt, PTHREADS};
     const int ns = min(D.scal[S_NSURV], D.survCap);
-    for (int base = blockIdx.x * PTHREADS; base < ns; base += gridDim.x * PTHREADS) {
-        if (threadIdx.x == 0) pcnt = 0;
-        __syncthreads();
-        const int s = base + threadIdx.x;
-        if (s < ns) {
-            const int2 w = D.surv[s];
-            if (K.phase == 0) eval_entry_pair(K, D, w.x, w.y, ps);
-            else if (!((w.x | w.y) & GHOST_BIT)) {
-                // reuse step: ghost entries belong to the build step only; a molecule that is special this step (far mover or
-                // displaced) is not where the list believes it to be and is handled by k_special_pairs instead
-                const TileRec a = fetch_rec(K, D, w.x), b = fetch_rec(K, D, w.y);
-                if (!((a.flg | b.flg) & (F_FAR | F_DISP))) eval_rec_pair(K, D, a, b, ps);
-            }
+    for (int s = blockIdx.x * PTHREADS + threadIdx.x; s < ns; s += gridDim.x * PTHREADS) {
+        const int2 w = D.surv[s];
+        int flag = 0;
+        const PairSink ps = {nullptr, nullptr, 0, &flag, 0};
+        if (K.phase == 0) eval_entry_pair(K, D, w.x, w.y, ps);
+        else if (!((w.x | w.y) & GHOST_BIT)) {
+            // reuse step: ghost entries belong to the build step only; a molecule that is special this step (far mover or
+            // displaced) is not where the list believes it to be and is handled by k_special_pairs instead
+            const TileRec a = fetch_rec(K, D, w.x), b = fetch_rec(K, D, w.y);
+            if (!((a.flg | b.flg) & (F_FAR | F_DISP))) eval_rec_pair(K, D, a, b, ps);
         }
-        __syncthreads();
-        flush_pairs(D, ps, &pbase);
-        __syncthreads();
+        D.survFlag[s] = (unsigned char)flag;         // which directions of this pair may react in S3 (k_react_pairs)
     }
 }
 // List-reuse steps: the molecules the stale grid / pair list do not cover. A special entry stands for one centre X of its
@@ -1281,7 +1326,7 @@ __global__ void __launch_bounds__(32 * SP_WARPS) k_special_pairs(const __grid_co
     const Consts &K = cK;
     __shared__ unsigned long long pbuf[128];
     __shared__ int pcnt, pbase;
-    const PairSink ps = {pbuf, &pcnt, 128};
+    const PairSink ps = {pbuf, &pcnt, 128, nullptr, 0};
     const int ns = min(D.scal[S_NSPEC], 2 * K.NT);
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1340,6 +1385,14 @@ KD int unit_state(const Dev &D, int u) {                 // U_ACCEPT / U_REJECT 
     const int r = ((volatile int *)D.unitRes)[u];
     return (r & 1) ? U_REJECT : (r == 0 ? U_ACCEPT : U_UNKNOWN);
 }
+KD void restore_pose(const Consts &cK, const Dev &D, int gid) {
+    if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
+    else {
+        const double2 *s = reinterpret_cast<const double2 *>(D.lig + (size_t)(gid - cK.NAt) * 24);
+        double2 *d = reinterpret_cast<double2 *>(D.lign + (size_t)(gid - cK.NAt) * 24);
+        for (int q = 0; q < 12; q++) d[q] = s[q];
+    }
+}
 __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ Args A) {
     KARGS
     __shared__ int changed;
@@ -1357,7 +1410,7 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
                 const int sv = unit_state(D, v);
                 if (sv != U_UNKNOWN) {
                     done = true;
-                    if ((sv == U_ACCEPT) == onNew) { atomicOr(&D.unitRes[u], 1); changed = 1; }          // v sits at the pose u overlaps
+                    if ((sv == U_ACCEPT) == onNew) { reject_unit(D, u); changed = 1; }                   // v sits at the pose u overlaps
                     else if (atomicSub(&D.pendCnt[u], 1) == 1) { atomicCAS(&D.unitRes[u], 2, 0); changed = 1; }   // last finding, all misses
                 }
             }
@@ -1369,6 +1422,10 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
         __syncthreads();
         if (!again) break;
     }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {           // cannot happen: the pending findings always settle
+        const int u = D.pendList[i].x;
+        if (u >= 0 && unit_state(D, u) == U_UNKNOWN) atomicOr(&D.scal[S_OVERFLOW], 8);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1377,45 +1434,77 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
 // one thread per pre-selected pair (receptor a, neighbour v), final poses: geometric tests of main.cpp:1882-1915 /
 // 1960-1981 / 2014-2035; candidates whose keyed draw succeeds are appended (a failed draw never changes anything,
 // main.cpp:1921/1987/2041); the ordered, first-come-first-served application happens in k_react_resolve
+KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
+    const int rep = replica_of_gid(K, a);
+    const uint64_t seed = seed_of(K, rep);
+    const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
+    // final pose of a molecule: its proposal, or its old pose if its unit was reverted (the copy-back happens in k_finish)
+    const bool rejA = D.unitRes[D.unitOf[a]] & 1, rejV = D.unitRes[D.unitOf[v]] & 1;
+    const Rec ra = rejA ? load_rec(D.recC, D.recS2, D.recS3, a) : load_rec(D.recCn, D.recS2n, D.recS3n, a);
+    if (v >= K.NAt) {
+        if (D.recLig[a] >= 0) return;
+        const int h = v - K.NAt;
+        int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
+        Lig b; load_lig(rejV ? D.lig : D.lign, h, b);
+        for (int s = 0; s < 3; s++) {
+            if (occ[s] >= 0 || !rl_geometry_ok(K, ra, b, s)) continue;
+            if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
+                int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
+                if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
+                else atomicOr(&D.scal[S_OVERFLOW], 1);
+            }
+        }
+    } else {
+        if (D.recCis[a] >= 0 || D.recCis[v] >= 0) return;
+        const Rec rb = rejV ? load_rec(D.recC, D.recS2, D.recS3, v) : load_rec(D.recCn, D.recS2n, D.recS3n, v);
+        if (!cis_geometry_ok(K, ra, rb)) return;
+        const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
+        const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
+        if (okMono || okCis) {
+            int q = atomicAdd(&D.scal[S_NCAND_CIS], 1);
+            if (q < D.candCap) D.candCis[q] = ((unsigned long long)a << 32) | ((unsigned long long)v << 2) | (okMono ? 1u : 0u) | (okCis ? 2u : 0u);
+            else atomicOr(&D.scal[S_OVERFLOW], 2);
+        }
+    }
+}
+// work items: the list pairs flagged by k_pairs_eval (sparse path), then the pairs collected by the tile kernel / the special
+// entries. Flagged pairs are few (~1 in 10): each CTA compacts the flags of a chunk of the list in shared memory first, so the
+// expensive geometry + draw runs with full warps.
+#define RP_CHUNK 1024
 __global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
+    __shared__ int items[2 * RP_CHUNK];          // (list index << 1) | direction
+    __shared__ int nitems;
     const uint64_t step = D.step64[0];
-    const int n = min(D.scal[S_NPAIR], D.pairCap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long pr = D.pairs[i];
-        const int a = (int)(pr >> 32), v = (int)(pr & 0xffffffffu);
-        const int rep = a / K.NA;
-        const uint64_t seed = seed_of(K, rep);
-        const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
-        // final pose of a molecule: its proposal, or its old pose if its unit was reverted (the copy-back happens in k_finish)
-        const bool rejA = D.unitRes[D.unitOf[a]] & 1, rejV = D.unitRes[D.unitOf[v]] & 1;
-        const Rec ra = rejA ? load_rec(D.recC, D.recS2, D.recS3, a) : load_rec(D.recCn, D.recS2n, D.recS3n, a);
-        if (v >= K.NAt) {
-            if (D.recLig[a] >= 0) continue;
-            const int h = v - K.NAt;
-            int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
-            Lig b; load_lig(rejV ? D.lig : D.lign, h, b);
-            for (int s = 0; s < 3; s++) {
-                if (occ[s] >= 0 || !rl_geometry_ok(K, ra, b, s)) continue;
-                if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
-                    int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
-                    if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
-                    else atomicOr(&D.scal[S_OVERFLOW], 1);
-                }
-            }
-        } else {
-            if (D.recCis[a] >= 0 || D.recCis[v] >= 0) continue;
-            const Rec rb = rejV ? load_rec(D.recC, D.recS2, D.recS3, v) : load_rec(D.recCn, D.recS2n, D.recS3n, v);
-            if (!cis_geometry_ok(K, ra, rb)) continue;
-            const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
-            const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
-            if (okMono || okCis) {
-                int q = atomicAdd(&D.scal[S_NCAND_CIS], 1);
-                if (q < D.candCap) D.candCis[q] = ((unsigned long long)a << 32) | ((unsigned long long)v << 2) | (okMono ? 1u : 0u) | (okCis ? 2u : 0u);
-                else atomicOr(&D.scal[S_OVERFLOW], 2);
+    const int nl = D.survFlag ? min(D.scal[S_NSURV], D.survCap) : 0;
+    for (int base = blockIdx.x * RP_CHUNK; base < nl; base += gridDim.x * RP_CHUNK) {
+        if (threadIdx.x == 0) nitems = 0;
+        __syncthreads();
+        const unsigned *fw = reinterpret_cast<const unsigned *>(D.survFlag + base);         // base is a multiple of 4
+        for (int k = threadIdx.x; k < RP_CHUNK / 4 && base + 4 * k < nl; k += blockDim.x) {
+            unsigned w = fw[k];                                                             // four flags (bytes past nl are stale: masked below)
+            for (int b = 0; b < 4 && w; b++, w >>= 8) {
+                const int i = base + 4 * k + b, f = w & 3;
+                if (!f || i >= nl) continue;
+                if (f & 1) items[atomicAdd(&nitems, 1)] = i << 1;
+                if (f & 2) items[atomicAdd(&nitems, 1)] = (i << 1) | 1;
             }
         }
+        __syncthreads();
+        const int ni = nitems;
+        for (int q = threadIdx.x; q < ni; q += blockDim.x) {
+            const int it = items[q];
+            const int2 w = D.surv[it >> 1];
+            const int a = w.x & ~GHOST_BIT, b = w.y & ~GHOST_BIT;
+            if (it & 1) react_pair(K, D, step, b, a); else react_pair(K, D, step, a, b);
+        }
+        __syncthreads();
+    }
+    const int np = min(D.scal[S_NPAIR], D.pairCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const unsigned long long pr = D.pairs[i];
+        react_pair(K, D, step, (int)(pr >> 32), (int)(pr & 0xffffffffu));
     }
 }
 
@@ -1466,40 +1555,37 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
     }
 }
 
-// Last kernel of a step, one thread per molecule:
-//  (1) revert the members of rejected units (main.cpp:666-674, 851-863, 1831-1860): copy the old pose over the proposal;
-//  (2) S3c, main.cpp:2062-2141, for receptors. Keyed draws make the three sequential loops order free: a thread owns the R-L
-//      bond of its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L outcome from the
-//      partner's own keyed draw instead of waiting for it.
+// Last kernel of a step: the copy-back of rejected units, then S3c, main.cpp:2062-2141, one thread per receptor. Keyed draws make the three sequential loops order
+// free: a thread owns the R-L bond of its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L
+// outcome from the partner's own keyed draw instead of waiting for it.
 __global__ void k_finish(const __grid_constant__ Args A) {
     KARGS
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = gid_live(cK, D, gid);
-    bool rejHead = false, rej = false;
-    if (live) {
-        const int u = D.unitOf[gid];
-        const int r = D.unitRes[u];
-        rej = r & 1; rejHead = rej && u == gid;
-        if (r == 2) atomicOr(&D.scal[S_OVERFLOW], 8);          // cannot happen: the pending findings always settle
+    // (1) revert the members of the rejected units (main.cpp:666-674, 851-863, 1831-1860): the old pose over the proposal, one
+    // thread per listed unit. Membership is the one of THIS step's sweep (unitOf / the member table), whatever S3 did to the bonds.
+    const int nrej = min(D.scal[S_NREJ], cK.NT);
+    if (gid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
+    // Ligand-headed units (free ligands, complexes) are taken from the list; a receptor-headed unit (free receptor, ligand-free
+    // cis dimer) is reverted by the head's own thread, which reads its cis word before its own dissociation trial can clear it.
+    for (int i = gid; i < nrej; i += gridDim.x * blockDim.x) {
+        const int u = D.rejList[i];
+        if (u < cK.NAt) continue;
+        const int hh = u - cK.NAt, size = D.cxSize[hh];
+        if (size <= 1) restore_pose(cK, D, u);
+        else { const int *row = D.members + D.cxOff[hh]; for (int q = 0; q < size; q++) restore_pose(cK, D, row[q]); }
     }
-    const unsigned nrej = __popc(__ballot_sync(0xffffffffu, rejHead));
-    if (nrej && (threadIdx.x & 31) == 0) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
-    if (rej) {
-        if (gid < cK.NAt) { D.recCn[gid] = D.recC[gid]; D.recS2n[gid] = D.recS2[gid]; D.recS3n[gid] = D.recS3[gid]; }
-        else {
-            const double2 *s = reinterpret_cast<const double2 *>(D.lig + (size_t)(gid - cK.NAt) * 24);
-            double2 *d = reinterpret_cast<double2 *>(D.lign + (size_t)(gid - cK.NAt) * 24);
-            for (int q = 0; q < 12; q++) d[q] = s[q];
-        }
+    if (gid >= nA_live(D)) return;
+    const int h = D.recLig[gid], p = D.recCis[gid];
+    if (D.unitOf[gid] == gid && (D.unitRes[gid] & 1)) {
+        restore_pose(cK, D, gid);
+        if (p >= 0 && D.unitOf[p] == gid) restore_pose(cK, D, p);      // (a cis bond formed in this step's S3 is not part of the unit)
     }
-    if (!live || gid >= cK.NAt) return;
+    // (2) dissociation
     const uint64_t step = D.step64[0];
     const int a = gid;
     const Consts &K = cK;
-    const int rep = a / K.NA;
-    const uint64_t seed = seed_of(cK, rep);
-    const int h = D.recLig[a], p = D.recCis[a];
     if (h < 0 && p < 0) return;
+    const uint64_t seed = seed_of(cK, replica_of_gid(K, a));
     const uint32_t me = ref_id(K, D, a);
     bool boundAfter = false;
     if (h >= 0) {
