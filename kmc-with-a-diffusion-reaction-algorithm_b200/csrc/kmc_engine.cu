@@ -170,7 +170,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     // list reuse: the pair list of a build step serves the following (reuse - 1) steps; the cut and the cells grow by the
     // drift a molecule may accumulate meanwhile (free units move at most max(amp) per step; whatever moves further is handled
     // as a special entry). KMC_REUSE / KMC_SKIN / KMC_DRIFT override (tuning knobs, every setting is exact).
-    int reuse = 4;
+    int reuse = 6;
     if (const char *o = getenv("KMC_REUSE")) reuse = std::max(1, atoi(o));
     K.skin = reuse > 1 ? 12.0 : 24.0;            // far-mover threshold
     if (const char *sk = getenv("KMC_SKIN")) { double v = atof(sk); if (v > 0) K.skin = v; }
@@ -207,7 +207,7 @@ static void choose_tiles(kmc_handle *h) {
     if (const char *o = getenv("KMC_RESOLVE")) h->useCells = !strcmp(o, "cells");
     h->listEvery = 1;
     if (!h->useCells) { K.drift = 0; if (!getenv("KMC_SKIN")) K.skin = 24.0; }      // tile path: rebuilt every step (the cells are at least as large as this needs)
-    if (h->useCells && K.drift > 0) { h->listEvery = 4; if (const char *o = getenv("KMC_REUSE")) h->listEvery = std::max(1, atoi(o)); }
+    if (h->useCells && K.drift > 0) { h->listEvery = 6; if (const char *o = getenv("KMC_REUSE")) h->listEvery = std::max(1, atoi(o)); }
     h->sinceBuild = 0;
 }
 // arrays of the sparse path (allocated on first need: strips can re-derive the grid and with it the choice of path)
@@ -521,14 +521,14 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     // S2 proposals: free receptors / cis dimers, free ligands and complexes are disjoint sets of molecules -- three kernels side
     // by side (forked branches of the graph; on one stream when per-kernel timing is on)
-    const int forkMask = h->profiling ? 0 : (getenv("KMC_FORK") ? atoi(getenv("KMC_FORK")) : 2);     // bit0: proposals (measured slower than back to back), bit1: special entries
-    const bool fork = forkMask & 1, fork2 = forkMask & 2;
-    cudaStream_t s1 = fork ? h->side[0] : st, s2 = fork ? h->side[1] : st;
-    if (fork) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
+    const int forkMask = h->profiling ? 0 : (getenv("KMC_FORK") ? atoi(getenv("KMC_FORK")) : 6);     // bit0: receptor/ligand proposals side by side (measured slower than back to back), bit1: special entries, bit2: complexes
+    const bool fork = forkMask & 1, fork2 = forkMask & 2, forkC = forkMask & 5;                       // bit2: only the complexes on a side branch
+    cudaStream_t s1 = fork ? h->side[0] : st, s2 = forkC ? h->side[1] : st;
+    if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, s2>>>(A)));
-    if (fork) {
+    if (fork || forkC) {
         cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);
         cudaStreamWaitEvent(st, h->evJoin[0], 0); cudaStreamWaitEvent(st, h->evJoin[1], 0);
     }

@@ -173,7 +173,7 @@ def test_errors_are_reported_not_swallowed():
     assert k.series()["step"] == 3
 
 
-@pytest.mark.parametrize("reuse,skin,drift", [("1", None, None), ("4", None, None), ("7", "3", "2.5"), ("3", "30", "0.5"), ("5", "1.5", "40")])
+@pytest.mark.parametrize("reuse,skin,drift", [("1", None, None), ("4", None, None), ("6", None, None), ("7", "3", "2.5"), ("3", "30", "0.5"), ("5", "1.5", "40")])
 def test_list_reuse_settings_are_all_exact(golden_dir, monkeypatch, reuse, skin, drift):
     """The sparse path rebuilds the neighbour grid / pair list every KMC_REUSE-th step and reuses them in between; far movers
     (beyond KMC_SKIN) and molecules that drifted more than KMC_DRIFT from their grid entry are handled as special entries. Every
