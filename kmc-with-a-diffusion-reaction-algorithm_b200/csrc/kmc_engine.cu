@@ -546,7 +546,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
         if (build) LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
         cudaStream_t s3 = fork2 ? h->side[0] : st;
         if (!build && fork2) { cudaEventRecord(h->evFork[1], st); cudaStreamWaitEvent(s3, h->evFork[1], 0); }
-        LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PTHREADS), 148 * 8 * 8), PTHREADS, 0, st>>>(A)));
+        LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PE_CHUNK) + 148, 148 * 16), PTHREADS, 0, st>>>(A)));
         if (!build) {           // the special entries next to the list pairs (both only publish findings)
             LAUNCH(KID_SPECIAL, (k_special_pairs<<<148, 32 * SP_WARPS, 0, s3>>>(A)));
             if (fork2) { cudaEventRecord(h->evJoin[2], s3); cudaStreamWaitEvent(st, h->evJoin[2], 0); }

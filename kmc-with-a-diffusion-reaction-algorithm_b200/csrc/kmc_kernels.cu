@@ -961,9 +961,10 @@ KD double z_excess(double dz) { return fmax(0.0, dz - 0.01); }
 KD double z_above_stack(const Consts &K, float z) {          // from a ligand centre at height z to the receptor's bead stack [0, 6 rA]
     return z_excess(fmax((double)z - rec_bead_z(K, 4), -(double)z));
 }
-KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf, const PairSink &ps) {
+// cheap part, from the two records alone: S3 pre-selection; returns true if beads have to be looked at (pair_detail)
+KD bool pair_pre(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, const PairSink &ps) {
     const int v = o.gid;
-    if (v == c.m) return 0;                              // the other (old/ghost) entry of the probe itself
+    if (v == c.m) return false;                          // the other (old/ghost) entry of the probe itself
     const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
     if (c.wantPairs) {
         const bool vlig = v >= K.NAt;
@@ -979,7 +980,7 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
             if (d2 <= reach * reach) sink_pair(D, ps, ((unsigned long long)c.m << 32) | (unsigned)v);
         }
     }
-    if (c.pairsOnly) return 0;
+    if (c.pairsOnly) return false;
     {   // nothing of v within reach of the probe at either of v's poses: done before any bead is fetched (most list pairs end here)
         // (3-D: a ligand high above the membrane is out of every receptor's reach, two ligands at different heights miss each other)
         const bool vrec = v < K.NAt;
@@ -989,8 +990,14 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
         else if (vrec) { r = K.reachRL; zo = zn = z_above_stack(K, c.pz); }
         else { r = K.reachLL; zo = z_excess(fabs((double)o.oz - (double)c.pz)); zn = z_excess(fabs((double)o.nz - (double)c.pz)); }
         const double ax = o.ox - c.px, ay = o.oy - c.py, bx = o.nx - c.px, by = o.ny - c.py;
-        if (fmin(ax * ax + ay * ay + zo * zo, bx * bx + by * by + zn * zn) > r * r) return 0;
+        if (fmin(ax * ax + ay * ay + zo * zo, bx * bx + by * by + zn * zn) > r * r) return false;
     }
+    return true;
+}
+// exact classification of a pair that passed pair_pre
+KD int pair_detail(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf) {
+    const int v = o.gid;
+    const bool vghost = o.flg & F_GHOST, vfar = o.flg & F_FAR;
     double pb[3][3];
     if (!c.prec) load_beads(D.lign, c.m - K.NAt, pb);
     const int uv = o.unit;
@@ -1009,6 +1016,9 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
     if (hitOld && hitNew) return 1;
     if (hitOld || hitNew) { *conf = (uv & UNIT_MASK) | (hitNew ? 0x40000000 : 0); return 2; }
     return 0;
+}
+KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec &o, int *conf, const PairSink &ps) {
+    return pair_pre(K, D, c, o, ps) ? pair_detail(K, D, c, o, conf) : 0;
 }
 // publishes a probe's result into the unit head's word unitRes: 0 = nothing found (accept), bit0 = definite overlap (reject),
 // bit1 = undecided. A finding that depends on ONE pose of an earlier unit (res == 2) is appended to the pending list as
@@ -1293,22 +1303,50 @@ __global__ void __launch_bounds__(CTHREADS, CMINB) k_cells_cut(const __grid_cons
 #ifndef PMINB
 #define PMINB 5
 #endif
+// Two phases per chunk of the list. Phase A, one thread per list pair: the two records, S3 pre-selection and the 3-D early out
+// for both directions -- every lane busy, no bead touched; the (few) directions that need beads are queued in shared memory.
+// Phase B, one thread per queued direction: the exact classification, with full warps instead of the 2-3 lanes per warp
+// that reach it when it is done in place.
+#ifndef PE_CHUNK
+#define PE_CHUNK 512
+#endif
 __global__ void __launch_bounds__(PTHREADS, PMINB) k_pairs_eval(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
+    __shared__ int items[2 * PE_CHUNK];          // (list index << 1) | direction
+    __shared__ int nitems;
     const int ns = min(D.scal[S_NSURV], D.survCap);
-    for (int s = blockIdx.x * PTHREADS + threadIdx.x; s < ns; s += gridDim.x * PTHREADS) {
-        const int2 w = D.surv[s];
-        int flag = 0;
-        const PairSink ps = {nullptr, nullptr, 0, &flag, 0};
-        if (K.phase == 0) eval_entry_pair(K, D, w.x, w.y, ps);
-        else if (!((w.x | w.y) & GHOST_BIT)) {
+    for (int base = blockIdx.x * PE_CHUNK; base < ns; base += gridDim.x * PE_CHUNK) {
+        if (threadIdx.x == 0) nitems = 0;
+        __syncthreads();
+        for (int s = base + threadIdx.x; s < min(base + PE_CHUNK, ns); s += PTHREADS) {
+            const int2 w = D.surv[s];
+            int flag = 0;
             // reuse step: ghost entries belong to the build step only; a molecule that is special this step (far mover or
             // displaced) is not where the list believes it to be and is handled by k_special_pairs instead
-            const TileRec a = fetch_rec(K, D, w.x), b = fetch_rec(K, D, w.y);
-            if (!((a.flg | b.flg) & (F_FAR | F_DISP))) eval_rec_pair(K, D, a, b, ps);
+            if (K.phase == 0 || !((w.x | w.y) & GHOST_BIT)) {
+                const TileRec a = fetch_rec(K, D, w.x), b = fetch_rec(K, D, w.y);
+                if (K.phase == 0 || !((a.flg | b.flg) & (F_FAR | F_DISP))) {
+                    PairSink ps = {nullptr, nullptr, 0, &flag, 1};
+                    if (pair_pre(K, D, make_probe(K, a), b, ps)) items[atomicAdd(&nitems, 1)] = s << 1;
+                    ps.bit = 2;
+                    if (pair_pre(K, D, make_probe(K, b), a, ps)) items[atomicAdd(&nitems, 1)] = (s << 1) | 1;
+                }
+            }
+            D.survFlag[s] = (unsigned char)flag;         // which directions of this pair may react in S3 (k_react_pairs)
         }
-        D.survFlag[s] = (unsigned char)flag;         // which directions of this pair may react in S3 (k_react_pairs)
+        __syncthreads();
+        const int ni = nitems;
+        for (int q = threadIdx.x; q < ni; q += PTHREADS) {
+            const int it = items[q];
+            const int2 w = D.surv[it >> 1];
+            const TileRec a = fetch_rec(K, D, (it & 1) ? w.y : w.x), b = fetch_rec(K, D, (it & 1) ? w.x : w.y);
+            const ProbeCtx pc = make_probe(K, a);
+            int cf = -1;
+            const int rr = pair_detail(K, D, pc, b, &cf);
+            publish(D, pc.u, rr, cf);
+        }
+        __syncthreads();
     }
 }
 // List-reuse steps: the molecules the stale grid / pair list do not cover. A special entry stands for one centre X of its
@@ -1435,19 +1473,28 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
 // 1960-1981 / 2014-2035; candidates whose keyed draw succeeds are appended (a failed draw never changes anything,
 // main.cpp:1921/1987/2041); the ordered, first-come-first-served application happens in k_react_resolve
 KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
-    const int rep = replica_of_gid(K, a);
-    const uint64_t seed = seed_of(K, rep);
-    const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
-    // final pose of a molecule: its proposal, or its old pose if its unit was reverted (the copy-back happens in k_finish)
-    const bool rejA = D.unitRes[D.unitOf[a]] & 1, rejV = D.unitRes[D.unitOf[v]] & 1;
-    const Rec ra = rejA ? load_rec(D.recC, D.recS2, D.recS3, a) : load_rec(D.recCn, D.recS2n, D.recS3n, a);
+    // everything that depends only on (a, v) is requested at once: unit words, bond words and the PROPOSED poses (the final
+    // pose of a molecule is its proposal unless its unit was reverted -- the copy-back happens in k_finish --, which is rare:
+    // the old pose is fetched only then)
+    const int ua = D.unitOf[a], uv = D.unitOf[v];
+    Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
     if (v >= K.NAt) {
-        if (D.recLig[a] >= 0) return;
         const int h = v - K.NAt;
-        int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
-        Lig b; load_lig(rejV ? D.lig : D.lign, h, b);
+        const int la = D.recLig[a];
+        const int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
+        Lig b; load_lig(D.lign, h, b);
+        const bool rejA = D.unitRes[ua] & 1, rejV = D.unitRes[uv] & 1;
+        if (la >= 0) return;
+        if (rejA) ra = load_rec(D.recC, D.recS2, D.recS3, a);
+        if (rejV) load_lig(D.lig, h, b);
+        bool any = false;
+        bool ok[3];
+        for (int s = 0; s < 3; s++) { ok[s] = occ[s] < 0 && rl_geometry_ok(K, ra, b, s); any |= ok[s]; }
+        if (!any) return;
+        const uint64_t seed = seed_of(K, replica_of_gid(K, a));
+        const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
         for (int s = 0; s < 3; s++) {
-            if (occ[s] >= 0 || !rl_geometry_ok(K, ra, b, s)) continue;
+            if (!ok[s]) continue;
             if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
                 int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
                 if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
@@ -1455,9 +1502,15 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
             }
         }
     } else {
-        if (D.recCis[a] >= 0 || D.recCis[v] >= 0) return;
-        const Rec rb = rejV ? load_rec(D.recC, D.recS2, D.recS3, v) : load_rec(D.recCn, D.recS2n, D.recS3n, v);
+        const int ca = D.recCis[a], cv = D.recCis[v];
+        Rec rb = load_rec(D.recCn, D.recS2n, D.recS3n, v);
+        const bool rejA = D.unitRes[ua] & 1, rejV = D.unitRes[uv] & 1;
+        if (ca >= 0 || cv >= 0) return;
+        if (rejA) ra = load_rec(D.recC, D.recS2, D.recS3, a);
+        if (rejV) rb = load_rec(D.recC, D.recS2, D.recS3, v);
         if (!cis_geometry_ok(K, ra, rb)) return;
+        const uint64_t seed = seed_of(K, replica_of_gid(K, a));
+        const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
         const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
         const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
         if (okMono || okCis) {
@@ -1470,7 +1523,7 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
 // work items: the list pairs flagged by k_pairs_eval (sparse path), then the pairs collected by the tile kernel / the special
 // entries. Flagged pairs are few (~1 in 10): each CTA compacts the flags of a chunk of the list in shared memory first, so the
 // expensive geometry + draw runs with full warps.
-#define RP_CHUNK 1024
+#define RP_CHUNK 512
 __global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
