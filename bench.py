@@ -321,6 +321,10 @@ def main():
                 "events_in_timed_region": {q: ev1[q] - ev0[q] for q in ("rl_on", "mono_cis_on", "cis_on", "rl_off", "reverted", "rebuilds")},
                 "clocks": sampler.result() if sampler else None}
         print(json.dumps(line))
+    if ds is not None and getattr(ds, "timing", None) and rank == 0:
+        tt = ds.timing
+        print("strip refresh timing (ms per refresh): classify+pack %.3f, exchange %.3f, merge %.3f over %d refreshes" % (
+            1e3 * tt[0] / tt[3], 1e3 * tt[1] / tt[3], 1e3 * tt[2] / tt[3], tt[3]), file=sys.stderr)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -300,8 +300,9 @@ extern "C" int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_
 // ================================================================================================================
 struct StripDev {
     unsigned char *flag = nullptr;            // [NT] bit0 owned, bit1 send to lower-x neighbour, bit2 send to higher-x neighbour
-    int *tmp = nullptr, *blk = nullptr;       // scan input (padded) and block sums
-    int *pos[6] = {nullptr};                  // exclusive prefixes: [list*2 + species] (list 0 low, 1 high, 2 keep; species 0 rec, 1 lig)
+    int *tileCnt = nullptr, *tileOff = nullptr;   // per tile of ST_TILE molecules of one species: members of list 0 low, 1 high, 2 keep; their exclusive prefixes
+    int *dcnt = nullptr, *hcnt = nullptr;         // totals [list*2 + species] on the device / in pinned host memory (+ [6] = overflow flag)
+    int ntA = 0, ntB = 0;
     char *msg[3] = {nullptr}; size_t msgCap[3] = {0};     // packed messages (2 = the owned set)
     char *rcv[2] = {nullptr}; size_t rcvCap[2] = {0};     // what the neighbours sent (0 from lower x, 1 from higher x)
     int *bondRef = nullptr;                   // [NAt*3 + NBt*3] bonds of the merged molecules as reference ids, before translation
@@ -340,32 +341,108 @@ __global__ void k_strip_classify(const __grid_constant__ Args A, unsigned char *
         }
     for (int i = 0; i < nmem; i++) flag[row ? row[i] : (i == 0 ? gid : m2)] = (unsigned char)f;
 }
-__global__ void k_strip_flag_ints(const __grid_constant__ Args A, const unsigned char *flag, int species, int bit, int *out) {
-    KARGS
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = species == 0 ? nA_live(D) : nB_live(D);
-    if (i < n) out[i] = (flag[species == 0 ? i : cK.NAt + i] >> bit) & 1;
+// ---- the three messages in one pass ---------------------------------------------------------------------------------------
+// Records must be id-sorted, i.e. in index order. A tile = ST_TILE consecutive molecules of one species (receptor tiles first),
+// a thread 8 consecutive molecules: k_strip_count counts the members of the three lists per tile, k_strip_scan_tiles turns the
+// counts into tile offsets and totals, k_strip_pack_all recomputes the ranks inside its tile and writes the records.
+#define ST_TILE 2048
+__device__ __forceinline__ void strip_tile_counts(const Consts &K, const Dev &D, const unsigned char *flag, int ntA, int &first, int &n, bool &lig, int c[3]) {
+    const int t = blockIdx.x;
+    lig = t >= ntA;
+    first = (lig ? t - ntA : t) * ST_TILE + threadIdx.x * 8;          // index inside the species
+    n = lig ? nB_live(D) : nA_live(D);
+    c[0] = c[1] = c[2] = 0;
+    for (int q = 0; q < 8; q++) {
+        const int i = first + q;
+        if (i < n) { const int f = flag[lig ? K.NAt + i : i]; c[0] += (f >> 1) & 1; c[1] += (f >> 2) & 1; c[2] += f & 1; }
+    }
 }
-// writes the records of list `bit` (receptors then ligands) at their prefix positions
-__global__ void k_strip_pack(const __grid_constant__ Args A, const unsigned char *flag, int bit, const int *posA, const int *posB, int nRecOut, char *out) {
+__global__ void __launch_bounds__(256) k_strip_count(const __grid_constant__ Args A, const unsigned char *flag, int ntA, int *tileCnt) {
     KARGS
-    const Consts &K = cK;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!gid_live(K, D, gid) || !((flag[gid] >> bit) & 1)) return;
+    __shared__ int sh[3][8];
+    int first, n, c[3]; bool lig;
+    strip_tile_counts(cK, D, flag, ntA, first, n, lig, c);
+    for (int l = 0; l < 3; l++) {
+        int v = c[l];
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[l][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) { int v = 0; for (int w = 0; w < 8; w++) v += sh[threadIdx.x][w]; tileCnt[blockIdx.x * 3 + threadIdx.x] = v; }
+}
+// one CTA: exclusive prefix over the tiles of each species for each list; totals to cnt6[list*2 + species]; capacity check of the messages
+__global__ void __launch_bounds__(1024) k_strip_scan_tiles(const int *tileCnt, int *tileOff, int ntA, int ntB, int *cnt6, size_t cap0, size_t cap1, size_t cap2) {
+    __shared__ int sh[32]; __shared__ int carry;
+    for (int seq = 0; seq < 6; seq++) {
+        const int sp = seq & 1, list = seq >> 1, t0 = sp ? ntA : 0, nt = sp ? ntB : ntA;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < nt; base += 1024) {
+            const int i = base + threadIdx.x, v = i < nt ? tileCnt[(t0 + i) * 3 + list] : 0;
+            const int inc = warp_incl_scan(v);
+            if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
+            __syncthreads();
+            if (threadIdx.x < 32) sh[threadIdx.x] = warp_incl_scan(sh[threadIdx.x]);
+            __syncthreads();
+            const int wofs = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+            if (i < nt) tileOff[(t0 + i) * 3 + list] = carry + wofs + inc - v;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry += wofs + inc;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) cnt6[seq] = carry;         // seq == list*2 + species
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const size_t cap[3] = {cap0, cap1, cap2};
+        int bad = 0;
+        for (int l = 0; l < 3; l++) if ((size_t)cnt6[l * 2] * sizeof(RecMsg) + (size_t)cnt6[l * 2 + 1] * sizeof(LigMsg) > cap[l]) bad |= 1 << l;
+        cnt6[6] = bad;
+    }
+}
+__device__ __forceinline__ void strip_write_record(const Consts &K, const Dev &D, int gid, char *out, int nRecOut, int pos) {
     if (gid < K.NAt) {
         RecMsg m; m.ref = (int)D.refA[gid];
         const int l = D.recLig[gid], c = D.recCis[gid];
         m.ligRef = l >= 0 ? (int)D.refB[l] : 0; m.site = D.recSite[gid]; m.cisRef = c >= 0 ? (int)D.refA[c] : 0;
         const double2 cc = D.recC[gid], s2 = D.recS2[gid], s3 = D.recS3[gid];
         m.pose[0] = cc.x; m.pose[1] = cc.y; m.pose[2] = s2.x; m.pose[3] = s2.y; m.pose[4] = s3.x; m.pose[5] = s3.y;
-        reinterpret_cast<RecMsg *>(out)[posA[gid]] = m;
+        reinterpret_cast<RecMsg *>(out)[pos] = m;
     } else {
         const int h = gid - K.NAt;
-        LigMsg *o = reinterpret_cast<LigMsg *>(out + (size_t)nRecOut * sizeof(RecMsg)) + posB[h];
+        LigMsg *o = reinterpret_cast<LigMsg *>(out + (size_t)nRecOut * sizeof(RecMsg)) + pos;
         o->ref = (int)D.refB[h];
         for (int k = 0; k < 3; k++) { const int r = D.ligRec[h * 3 + k]; o->recRef[k] = r >= 0 ? (int)D.refA[r] : 0; }
         const double *p = D.lig + (size_t)h * 24;
         for (int q = 0; q < 24; q++) o->pose[q] = p[q];
+    }
+}
+__global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ Args A, const unsigned char *flag, int ntA, const int *tileOff, const int *cnt6,
+                                                        char *msg0, char *msg1, char *msg2) {
+    KARGS
+    const Consts &K = cK;
+    __shared__ int sh[3][8];
+    if (cnt6[6]) return;                                   // a message does not fit its buffer: the host reports it
+    int first, n, c[3]; bool lig;
+    strip_tile_counts(K, D, flag, ntA, first, n, lig, c);
+    int rank[3];
+    for (int l = 0; l < 3; l++) {                          // exclusive prefix of the thread counts inside the tile
+        const int inc = warp_incl_scan(c[l]);
+        if ((threadIdx.x & 31) == 31) sh[l][threadIdx.x >> 5] = inc;
+        rank[l] = inc - c[l];
+    }
+    __syncthreads();
+    for (int l = 0; l < 3; l++) {
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) rank[l] += sh[l][w];
+        rank[l] += tileOff[blockIdx.x * 3 + l];
+    }
+    char *msg[3] = {msg0, msg1, msg2};
+    for (int q = 0; q < 8; q++) {
+        const int i = first + q;
+        if (i >= n) break;
+        const int gid = lig ? K.NAt + i : i, f = flag[gid];
+        const int bits[3] = {(f >> 1) & 1, (f >> 2) & 1, f & 1};
+        for (int l = 0; l < 3; l++) if (bits[l]) strip_write_record(K, D, gid, msg[l], cnt6[l * 2], rank[l]++);
     }
 }
 template <class T> __device__ __forceinline__ int d_lower_bound(const T *a, int n, int ref) {
@@ -424,16 +501,17 @@ __global__ void k_strip_fix_bonds(const __grid_constant__ Args A, const int *bon
     }
 }
 
-static void strip_dev_free(kmc_handle *h) { delete h->strip_dev; h->strip_dev = nullptr; }    // device buffers are in h->allocs
+static void strip_dev_free(kmc_handle *h) { if (h->strip_dev && h->strip_dev->hcnt) cudaFreeHost(h->strip_dev->hcnt); delete h->strip_dev; h->strip_dev = nullptr; }    // device buffers are in h->allocs
 
 static int strip_dev_alloc(kmc_handle *h) {
     StripDev &S = *h->strip_dev;
     if (S.flag) return KMC_OK;
     const int NT = h->NT;
-    S.padN = ((std::max(h->NAt, h->NBt) + 1 + SCAN_TILE - 1) / SCAN_TILE) * SCAN_TILE;
-    bool ok = dalloc(h, &S.flag, NT) == cudaSuccess && dalloc(h, &S.tmp, S.padN) == cudaSuccess && dalloc(h, &S.blk, S.padN / SCAN_TILE + 1) == cudaSuccess &&
-              dalloc(h, &S.bondRef, (size_t)2 * h->NAt + (size_t)3 * h->NBt + 8) == cudaSuccess;
-    for (int k = 0; k < 6 && ok; k++) ok = dalloc(h, &S.pos[k], S.padN) == cudaSuccess;
+    S.ntA = (h->NAt + ST_TILE - 1) / ST_TILE; S.ntB = (h->NBt + ST_TILE - 1) / ST_TILE;
+    bool ok = dalloc(h, &S.flag, NT) == cudaSuccess && dalloc(h, &S.tileCnt, (size_t)3 * (S.ntA + S.ntB) + 3) == cudaSuccess &&
+              dalloc(h, &S.tileOff, (size_t)3 * (S.ntA + S.ntB) + 3) == cudaSuccess && dalloc(h, &S.dcnt, 8) == cudaSuccess &&
+              dalloc(h, &S.bondRef, (size_t)2 * h->NAt + (size_t)3 * h->NBt + 8) == cudaSuccess &&
+              cudaMallocHost((void **)&S.hcnt, 8 * sizeof(int)) == cudaSuccess;
     const size_t full = (size_t)h->NAt * sizeof(RecMsg) + (size_t)h->NBt * sizeof(LigMsg) + 64, band = full / 3 + 4096;
     for (int k = 0; k < 3 && ok; k++) { S.msgCap[k] = k == 2 ? full : band; ok = dalloc(h, &S.msg[k], S.msgCap[k]) == cudaSuccess; }
     for (int k = 0; k < 2 && ok; k++) { S.rcvCap[k] = band; ok = dalloc(h, &S.rcv[k], S.rcvCap[k]) == cudaSuccess; }
@@ -459,29 +537,14 @@ extern "C" int kmc_strip_begin_refresh_dev(kmc_handle *h) {
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     CK(cudaMemsetAsync(S.flag, 0, NT, st));
     k_strip_classify<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, h->strip_lo, h->strip_hi, h->strip_W);
-    const int sb = S.padN / SCAN_TILE;
-    for (int list = 0; list < 3; list++)
-        for (int sp = 0; sp < 2; sp++) {
-            const int bit = list == 2 ? 0 : list + 1;
-            CK(cudaMemsetAsync(S.tmp, 0, sizeof(int) * S.padN, st));
-            k_strip_flag_ints<<<nblk(std::max(sp == 0 ? NAt : NBt, 1), 256), 256, 0, st>>>(A, S.flag, sp, bit, S.tmp);
-            k_scan_reduce<<<sb, 256, 0, st>>>((const int4 *)S.tmp, S.blk);
-            k_scan_sums<<<1, 1024, 0, st>>>(S.blk, sb);
-            k_scan_down<<<sb, 256, 0, st>>>((int4 *)S.tmp, S.blk, (int4 *)S.pos[list * 2 + sp]);
-        }
-    int live[2];
-    CK(cudaMemcpyAsync(live, h->D.scal + S_NA_LIVE, sizeof live, cudaMemcpyDeviceToHost, st));
+    const int nt = S.ntA + S.ntB;
+    k_strip_count<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileCnt);
+    k_strip_scan_tiles<<<1, 1024, 0, st>>>(S.tileCnt, S.tileOff, S.ntA, S.ntB, S.dcnt, S.msgCap[0], S.msgCap[1], S.msgCap[2]);
+    k_strip_pack_all<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileOff, S.dcnt, S.msg[0], S.msg[1], S.msg[2]);
+    CK(cudaMemcpyAsync(S.hcnt, S.dcnt, 7 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int list = 0; list < 3; list++)
-        for (int sp = 0; sp < 2; sp++)       // exclusive prefix one past the last live molecule = the total (flags beyond are zero)
-            CK(cudaMemcpyAsync(&S.cnt[list * 2 + sp], S.pos[list * 2 + sp] + live[sp], sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int list = 0; list < 3; list++) {
-        const size_t need = (size_t)S.cnt[list * 2] * sizeof(RecMsg) + (size_t)S.cnt[list * 2 + 1] * sizeof(LigMsg);
-        if (need > S.msgCap[list]) { h->err = "strip: message buffer too small (band holds more than a third of the local capacity)"; return KMC_ERR_CAPACITY; }
-        const int bit = list == 2 ? 0 : list + 1;
-        k_strip_pack<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, bit, S.pos[list * 2], S.pos[list * 2 + 1], S.cnt[list * 2], S.msg[list]);
-    }
+    for (int q = 0; q < 6; q++) S.cnt[q] = S.hcnt[q];
+    if (S.hcnt[6]) { h->err = "strip: message buffer too small (band holds more than a third of the local capacity)"; return KMC_ERR_CAPACITY; }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return KMC_OK;

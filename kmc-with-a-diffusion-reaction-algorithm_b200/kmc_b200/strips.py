@@ -188,7 +188,13 @@ class DistStrips:
         """device messages, NCCL point-to-point GPU to GPU; same pairing rules as ring_exchange"""
         torch, dist, dev = self.torch, self.dist, self.device
         k = self.k
+        import os, time
+        timing = os.environ.get("KMC_STRIP_TIMING")
+        if timing:
+            k.sync(); t0 = time.perf_counter()
         k.strip_begin_refresh_dev()
+        if timing:
+            t1 = time.perf_counter()
         if self.n == 1:
             k.strip_rebuild_dev(0, 0, 0, 0); self.since = 0; return
         lo, hi = (self.rank - 1) % self.n, (self.rank + 1) % self.n
@@ -207,8 +213,14 @@ class DistStrips:
         t_recv_hi = dev_tensor(torch, k.strip_recv_dev(1, *fh), max(msg_bytes(*fh), 1), dev); t_recv_lo = dev_tensor(torch, k.strip_recv_dev(0, *fl), max(msg_bytes(*fl), 1), dev)
         run([dist.P2POp(dist.isend, t_send_lo, lo), dist.P2POp(dist.isend, t_send_hi, hi), dist.P2POp(dist.irecv, t_recv_hi, hi), dist.P2POp(dist.irecv, t_recv_lo, lo)])
         torch.cuda.synchronize()
+        if timing:
+            t2 = time.perf_counter()
         self.bytes_sent += msg_bytes(rl_, ll_) + msg_bytes(rh_, lh_)
         k.strip_rebuild_dev(fl[0], fl[1], fh[0], fh[1])
+        if timing:
+            t3 = time.perf_counter()
+            self.timing = getattr(self, "timing", [0.0, 0.0, 0.0, 0])
+            self.timing[0] += t1 - t0; self.timing[1] += t2 - t1; self.timing[2] += t3 - t2; self.timing[3] += 1
         self.since = 0
 
     def refresh(self):
