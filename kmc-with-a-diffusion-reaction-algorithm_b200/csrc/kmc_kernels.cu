@@ -187,14 +187,16 @@ KD void propose_rec_body(const Args &A) {
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nA_live(D)) return;
     const Consts &K = cK;
-    // every load this thread can need is issued before the first decision (one memory latency instead of a chain of them)
+    if (gid >= K.NAt) return;
+    // every load this thread can need is issued before the first decision (one memory latency instead of a chain of them);
+    // that includes the live count: slots past it are allocated, reading them is harmless
+    const int nLive = nA_live(D);
     const int head = D.unitOf[gid];
     const float2 bc = K.phase ? D.bcen[gid] : make_float2(0.f, 0.f);
     const int p = D.recCis[gid];
     Rec ra = load_rec(D.recC, D.recS2, D.recS3, gid);
-    if (head != gid) return;                      // not the head of a unit
+    if (gid >= nLive || head != gid) return;      // not the head of a unit
     const int rep = replica_of_gid(K, gid);
     const uint64_t seed = seed_of(cK, rep);
     const uint32_t me = ref_id(K, D, gid);
@@ -279,18 +281,18 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int h0 = blockIdx.x * LIG_TILE, h = h0 + threadIdx.x, gid = K.NAt + h;
     if (h == 0) D.scal[S_TOPO_DIRTY] = 0;         // the gated rebuild kernels of this step are done; S3 sets it again
-    const int nrows = min(LIG_TILE, nB_live(D) - h0);
+    const int nrows = min(LIG_TILE, K.NBt - h0);          // rows of the tile by CAPACITY: the live count travels with the data
     if (nrows <= 0) return;
+    const int nLive = nB_live(D);
     {
         const double2 *src = reinterpret_cast<const double2 *>(D.lig) + (size_t)h0 * 12;
         for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; tile[r][i - r * 12] = src[i]; }
     }
-    const bool live = threadIdx.x < nrows;
     // the scalar words of this thread's ligand travel in the same latency window as the tile
     int head = -1, csize = 0; float2 bc = make_float2(0.f, 0.f);
-    if (live) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; }
+    if (threadIdx.x < nrows) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; }
     __syncthreads();
-    const bool act = live && head == gid && csize <= 1;          // a free ligand (complexes: k_propose_complex)
+    const bool act = h < nLive && head == gid && csize <= 1;     // a free ligand (complexes: k_propose_complex)
     moved[threadIdx.x] = act ? 1 : 0;
     if (act) {
         Lig l;
@@ -1616,6 +1618,10 @@ __global__ void k_finish(const __grid_constant__ Args A) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     // (1) revert the members of the rejected units (main.cpp:666-674, 851-863, 1831-1860): the old pose over the proposal, one
     // thread per listed unit. Membership is the one of THIS step's sweep (unitOf / the member table), whatever S3 did to the bonds.
+    // (all words of this thread are requested before the first dependent use)
+    int h = -1, p = -1, myUnit = -1, myRes = 0;
+    if (gid < cK.NAt) { h = D.recLig[gid]; p = D.recCis[gid]; myUnit = D.unitOf[gid]; myRes = D.unitRes[gid]; }
+    const int nLiveA = nA_live(D);
     const int nrej = min(D.scal[S_NREJ], cK.NT);
     if (gid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
     // Ligand-headed units (free ligands, complexes) are taken from the list; a receptor-headed unit (free receptor, ligand-free
@@ -1627,9 +1633,8 @@ __global__ void k_finish(const __grid_constant__ Args A) {
         if (size <= 1) restore_pose(cK, D, u);
         else { const int *row = D.members + D.cxOff[hh]; for (int q = 0; q < size; q++) restore_pose(cK, D, row[q]); }
     }
-    if (gid >= nA_live(D)) return;
-    const int h = D.recLig[gid], p = D.recCis[gid];
-    if (D.unitOf[gid] == gid && (D.unitRes[gid] & 1)) {
+    if (gid >= nLiveA) return;
+    if (myUnit == gid && (myRes & 1)) {
         restore_pose(cK, D, gid);
         if (p >= 0 && D.unitOf[p] == gid) restore_pose(cK, D, p);      // (a cis bond formed in this step's S3 is not part of the unit)
     }
