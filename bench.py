@@ -45,6 +45,7 @@ B_ALG_KERNEL = {
     "k_grid_scatter": 18 + 4 + 4 + 4,
     "k_finish": 4 + 4 + 0.75 * 8,                     # unit word + unit result, bond words of the receptors
 }
+NCU_TRAFFIC = {"k_propose_lig": 65.0e6 + 28.5e6, "k_propose_rec": 60.0e6 + 42.5e6, "k_pairs_eval": 49.3e6 + 0.1e6, "k_resolve_tiles": 154.8e6 + 5.7e6}
 B_ALG_PER_LIST_PAIR = 8 + 2 * 40                      # k_pairs_eval: the pair + two records (centres old/new 32, unit key 4, flags 4)
 
 
@@ -308,9 +309,9 @@ def main():
                            "ms_per_mc_step": ms_max / args.steps / S},
                 "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": achieved / peak if achieved else None,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of one k_resolve_tiles launch on this workload, ncu --set full
-                             # (profiles/r01b_ncu_full_raw.csv): 154.8 + 5.7 MB
-                             "traffic": 160.4e6 if (top_name == "k_resolve_tiles" and M == 1250000) else None,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, ncu --set full
+                             # (profiles/r01e_ncu_full_raw.csv; k_resolve_tiles: profiles/r01b_ncu_full_raw.csv)
+                             "traffic": NCU_TRAFFIC.get(top_name) if M == 1250000 else None,
                              "alg_bytes_per_molecule": balg, "kernel_ms": top_ms / top_n, "kernel_share_of_step": top_ms / tot_prof,
                              "step_frac": value / world * B_ALG_STEP / 1e9 / peak,
                              "kernels_ms_per_mc_step": {n: round(v[0] / (3 * S), 4) for n, v in sorted(prof.items(), key=lambda kv: -kv[1][0]) if v[1]}},
