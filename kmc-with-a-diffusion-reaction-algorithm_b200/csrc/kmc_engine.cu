@@ -525,7 +525,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const bool fork = forkMask & 1, fork2 = forkMask & 2, forkC = forkMask & 5;                       // bit2: only the complexes on a side branch
     cudaStream_t s1 = fork ? h->side[0] : st, s2 = forkC ? h->side[1] : st;
     if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
-    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<std::min(nblk(std::max(NAt, 1), REC_TILE), 148 * RECMINB), REC_TILE, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, s2>>>(A)));
     if (fork || forkC) {

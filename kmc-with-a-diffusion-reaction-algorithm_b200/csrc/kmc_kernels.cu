@@ -15,6 +15,8 @@
 // its accept/reject decision depends on earlier units only through their (rare) rejections, and is
 // resolved by a monotone fixed point: a unit is decided as soon as every earlier unit it could touch is.
 #include "kmc_device.cuh"
+#include <cuda_pipeline.h>
+#define REC_TILE 256
 
 namespace kmc {
 
@@ -182,20 +184,49 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
 
 // free receptor (main.cpp:584-636), ligand-free cis dimer (682-799): one thread per receptor. (Receptors and ligands are
 // separate kernels: the receptor path needs far fewer registers, and the two run side by side on forked branches of the step graph.)
+// Persistent CTAs, software pipeline: while a thread transforms receptor gid of tile t out of shared memory, the 64 bytes it needs
+// for tile t + gridDim (centre, two sites, unit word, cis word, entry centre) are already in flight (cp.async, 16 B per request,
+// each thread copies and later reads only its own slot: no barrier, just the pipeline wait). The load latency that every warp
+// used to sit out at its start now overlaps the previous tile's arithmetic.
+struct RecStage { double2 c[REC_TILE], s2[REC_TILE], s3[REC_TILE]; float2 bc[REC_TILE]; int head[REC_TILE], cis[REC_TILE]; };
+KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile) {
+    const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
+    if (gid < K.NAt) {
+        __pipeline_memcpy_async(&S.c[t], &D.recC[gid], 16); __pipeline_memcpy_async(&S.s2[t], &D.recS2[gid], 16);
+        __pipeline_memcpy_async(&S.s3[t], &D.recS3[gid], 16);
+        __pipeline_memcpy_async(&S.head[t], &D.unitOf[gid], 4); __pipeline_memcpy_async(&S.cis[t], &D.recCis[gid], 4);
+        if (K.phase) __pipeline_memcpy_async(&S.bc[t], &D.bcen[gid], 8);
+    }
+}
+KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc);
 KD void propose_rec_body(const Args &A) {
     KARGS
+    const Consts &K = cK;
+    __shared__ RecStage ST[2];
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const Consts &K = cK;
-    if (gid >= K.NAt) return;
-    // every load this thread can need is issued before the first decision (one memory latency instead of a chain of them);
-    // that includes the live count: slots past it are allocated, reading them is harmless
     const int nLive = nA_live(D);
-    const int head = D.unitOf[gid];
-    const float2 bc = K.phase ? D.bcen[gid] : make_float2(0.f, 0.f);
-    const int p = D.recCis[gid];
-    Rec ra = load_rec(D.recC, D.recS2, D.recS3, gid);
+    const int ntiles = (K.NAt + REC_TILE - 1) / REC_TILE;
+    int tile = blockIdx.x;
+    if (tile < ntiles) rec_prefetch(K, D, ST[0], tile);
+    __pipeline_commit();
+    for (int it = 0; tile < ntiles; it++, tile += gridDim.x) {
+        const int next = tile + gridDim.x;
+        if (next < ntiles) rec_prefetch(K, D, ST[(it + 1) & 1], next);
+        __pipeline_commit();
+        __pipeline_wait_prior(1);                 // everything but the newest group has landed: this tile's slot is ready
+        const RecStage &S = ST[it & 1];
+        const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
+        if (gid < K.NAt) {
+            Rec ra; ra.cx = S.c[t].x; ra.cy = S.c[t].y; ra.s2x = S.s2[t].x; ra.s2y = S.s2[t].y; ra.s3x = S.s3[t].x; ra.s3y = S.s3[t].y;
+            propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase ? S.bc[t] : make_float2(0.f, 0.f));
+        }
+    }
+    __pipeline_wait_prior(0);
+}
+KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc) {
+    KARGS
+    const Consts &K = cK;
     if (gid >= nLive || head != gid) return;      // not the head of a unit
     const int rep = replica_of_gid(K, gid);
     const uint64_t seed = seed_of(cK, rep);
