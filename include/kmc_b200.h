@@ -164,6 +164,11 @@ int kmc_parameter_log_write(const kmc_params *p, const char *path);
 int kmc_write_gro(kmc_handle *h, int32_t replica, const char *path);
 int kmc_write_checkpoint(kmc_handle *h, int32_t replica, const char *path);
 int kmc_read_checkpoint(kmc_handle *h, int32_t replica, const char *path);      /* restart: main.cpp:226-268 */
+/* Lossless binary checkpoint of the whole handle (all replicas): position.cpt keeps three decimals (main.cpp:2213), so a restart
+ * from it cannot continue a run bit for bit; this one can (header "KMCB2001", sizes, step, running-max complex sizes, then the
+ * arrays of kmc_get_packed). The handle must have been created with the same n_receptor / n_ligand / n_replicas. */
+int kmc_write_checkpoint_bin(kmc_handle *h, const char *path);
+int kmc_read_checkpoint_bin(kmc_handle *h, const char *path);
 /* the reference's own main loop: n_steps steps with records every output_every steps into directory `dir` */
 int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, const char *dir);
 

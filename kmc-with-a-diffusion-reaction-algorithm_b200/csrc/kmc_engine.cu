@@ -1061,6 +1061,49 @@ extern "C" int kmc_read_checkpoint(kmc_handle *h, int32_t rep, const char *path)
     return kmc_set_state(h, rep, X.data(), Y.data(), Z.data(), st.data(), rn.data(), c[5], (int32_t)c[4]);    // main.cpp:261-267
 }
 
+// Lossless checkpoint: position.cpt keeps 3 decimals (main.cpp:2206-2244), so a restart from it is not
+// bit-continuable. This one stores the whole handle (all replicas) in binary: header, running-max complex sizes, then the
+// arrays of kmc_get_packed. A run restored from it continues bit for bit (the random stream is keyed, not stateful).
+namespace { struct BinHeader { char magic[8]; int32_t n_receptor, n_ligand, n_replicas, reserved; int64_t step_done; }; }
+extern "C" int kmc_write_checkpoint_bin(kmc_handle *h, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    std::vector<double> rec((size_t)h->NAt * 6), lig((size_t)h->NBt * 24);
+    std::vector<int32_t> rl(h->NAt), rs(h->NAt), rc_(h->NAt), mx(h->R);
+    int rc = kmc_get_packed(h, rec.data(), lig.data(), rl.data(), rs.data(), rc_.data()); if (rc) return rc;
+    CK(cudaMemcpy(mx.data(), h->D.maxComplex, sizeof(int) * h->R, cudaMemcpyDeviceToHost));
+    BinHeader H; memcpy(H.magic, "KMCB2001", 8); H.n_receptor = h->NA; H.n_ligand = h->NB; H.n_replicas = h->R; H.reserved = 0; H.step_done = h->step_done;
+    FILE *f = fopen(path, "wb");
+    bool ok = f != nullptr;
+    ok = ok && fwrite(&H, sizeof H, 1, f) == 1 && fwrite(mx.data(), sizeof(int32_t), mx.size(), f) == mx.size();
+    ok = ok && fwrite(rec.data(), sizeof(double), rec.size(), f) == rec.size() && fwrite(lig.data(), sizeof(double), lig.size(), f) == lig.size();
+    ok = ok && fwrite(rl.data(), 4, rl.size(), f) == rl.size() && fwrite(rs.data(), 4, rs.size(), f) == rs.size() && fwrite(rc_.data(), 4, rc_.size(), f) == rc_.size();
+    if (f) ok = (fclose(f) == 0) && ok;
+    if (!ok) { h->err = std::string("cannot write ") + path; return KMC_ERR_IO; }
+    return KMC_OK;
+}
+extern "C" int kmc_read_checkpoint_bin(kmc_handle *h, const char *path) {
+    if (!h || !path) return KMC_ERR_INVALID;
+    FILE *f = fopen(path, "rb");
+    if (!f) { h->err = std::string("cannot read ") + path; return KMC_ERR_IO; }
+    BinHeader H;
+    bool ok = fread(&H, sizeof H, 1, f) == 1 && memcmp(H.magic, "KMCB2001", 8) == 0;
+    if (ok && (H.n_receptor != h->NA || H.n_ligand != h->NB || H.n_replicas != h->R)) {
+        fclose(f); h->err = "kmc_read_checkpoint_bin: the file holds " + std::to_string(H.n_receptor) + "+" + std::to_string(H.n_ligand) + " molecules x " +
+                            std::to_string(H.n_replicas) + " replicas, the handle " + std::to_string(h->NA) + "+" + std::to_string(h->NB) + " x " + std::to_string(h->R);
+        return KMC_ERR_STATE;
+    }
+    std::vector<double> rec((size_t)h->NAt * 6), lig((size_t)h->NBt * 24);
+    std::vector<int32_t> rl(h->NAt), rs(h->NAt), rc_(h->NAt), mx(h->R);
+    ok = ok && fread(mx.data(), sizeof(int32_t), mx.size(), f) == mx.size();
+    ok = ok && fread(rec.data(), sizeof(double), rec.size(), f) == rec.size() && fread(lig.data(), sizeof(double), lig.size(), f) == lig.size();
+    ok = ok && fread(rl.data(), 4, rl.size(), f) == rl.size() && fread(rs.data(), 4, rs.size(), f) == rs.size() && fread(rc_.data(), 4, rc_.size(), f) == rc_.size();
+    fclose(f);
+    if (!ok) { h->err = std::string("not a complete KMCB2001 checkpoint: ") + path; return KMC_ERR_IO; }
+    int rc = kmc_set_packed(h, rec.data(), lig.data(), rl.data(), rs.data(), rc_.data(), H.step_done); if (rc) return rc;
+    CK(cudaMemcpy(h->D.maxComplex, mx.data(), sizeof(int) * h->R, cudaMemcpyHostToDevice));
+    return KMC_OK;
+}
+
 // the same generator without a handle or a device: host arrays out (strips: every rank generates the global start state)
 extern "C" int kmc_generate_packed(const kmc_params *p, uint64_t init_seed, int32_t sort_cells, double *rec_pose, double *lig_pose) {
     if (!p || !rec_pose || !lig_pose || p->n_replicas < 1) return KMC_ERR_INVALID;

@@ -41,7 +41,8 @@ EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_begin_refresh_dev", "kmc_strip_message_dev",
            "kmc_strip_recv_dev", "kmc_strip_rebuild_dev", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
-           "kmc_checkpoint_read_arrays", "kmc_parameter_log_write", "kmc_write_gro", "kmc_write_checkpoint", "kmc_read_checkpoint"]
+           "kmc_checkpoint_read_arrays", "kmc_parameter_log_write", "kmc_write_gro", "kmc_write_checkpoint", "kmc_read_checkpoint",
+           "kmc_write_checkpoint_bin", "kmc_read_checkpoint_bin"]
 
 
 class KmcError(RuntimeError):
@@ -102,6 +103,8 @@ def lib():
         L.kmc_write_gro.argtypes = [vp, i32, C.c_char_p]
         L.kmc_write_checkpoint.argtypes = [vp, i32, C.c_char_p]
         L.kmc_read_checkpoint.argtypes = [vp, i32, C.c_char_p]
+        L.kmc_write_checkpoint_bin.argtypes = [vp, C.c_char_p]
+        L.kmc_read_checkpoint_bin.argtypes = [vp, C.c_char_p]
         L.kmc_generate_packed.argtypes = [C.POINTER(Params), u64, i32, vp, vp]
         L.kmc_get_grid.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
         L.kmc_write_bond_dat.argtypes = [vp, i32, C.c_char_p]
@@ -380,6 +383,12 @@ class Kmc:
 
     def read_checkpoint(self, path, replica=0):
         self._ck(lib().kmc_read_checkpoint(self.h, replica, os.fsencode(path)))
+
+    def write_checkpoint_bin(self, path):
+        self._ck(lib().kmc_write_checkpoint_bin(self.h, os.fsencode(path)))
+
+    def read_checkpoint_bin(self, path):
+        self._ck(lib().kmc_read_checkpoint_bin(self.h, os.fsencode(path)))
 
     def run(self, n_steps, output_every, directory):
         self._ck(lib().kmc_run(self.h, n_steps, output_every, os.fsencode(directory)))

@@ -193,3 +193,34 @@ def test_list_reuse_settings_are_all_exact(golden_dir, monkeypatch, reuse, skin,
     k.set_state(R, st, rn, step_done=o.counts()["step"], max_complex=o.counts()["max_complex"])
     lockstep(o, k, 60, 1, "reuse-%s after set_state" % reuse, per_step_accept=True)
     k.close()
+
+
+def test_binary_checkpoint_continues_bit_for_bit(golden_dir, tmp_path):
+    """kmc_write_checkpoint_bin / kmc_read_checkpoint_bin: a run restored from the binary checkpoint continues exactly
+    like the uninterrupted one -- poses bit for bit, bonds, running-max complex, complex tables -- whereas the reference's own
+    position.cpt keeps three decimals. Two replicas, hot regime (complexes form and break in the window)."""
+    g = load_golden_state(os.path.join(golden_dir, "hot200_step40000.npz"))
+    def make():
+        k = kmc_b200.Kmc(apply_regime(kmc_b200.default_params(box=tuple(g["params"]["box"]), seed=31, n_replicas=2), "hot"))
+        for r in range(2):
+            k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"], replica=r)
+        return k
+    a = make()
+    a.step(333)
+    path = str(tmp_path / "state.kmcb")
+    a.write_checkpoint_bin(path)
+    a.step(400)
+    b = make()
+    b.read_checkpoint_bin(path)
+    assert b.series(0)["step"] == g["step"] + 333
+    b.step(400)
+    for x, y in zip(a.get_packed(), b.get_packed()):
+        assert np.array_equal(x, y)
+    for r in range(2):
+        assert a.series(r) == b.series(r)
+        assert a.complexes(r) == b.complexes(r)
+    other = kmc_b200.Kmc(kmc_b200.default_params(n_receptor=10, n_ligand=5))
+    with pytest.raises(kmc_b200.KmcError, match="molecules"):
+        other.read_checkpoint_bin(path)
+    with pytest.raises(kmc_b200.KmcError):
+        other.read_checkpoint_bin(str(tmp_path / "missing.kmcb"))
