@@ -46,6 +46,7 @@ struct kmc_handle {
     // list reuse (sparse path): every listEvery-th step rebuilds the neighbour grid and the pair list (phase 0), the steps in
     // between reuse them (phase 1); sinceBuild = steps taken since the last rebuild, 0 = the next step must rebuild
     int listEvery = 1, sinceBuild = 0, cellHeadCap = 0;
+    bool adapt = true, adapted = false;      // kmc_sync may fall back to a rebuild every step (see there)
     unsigned epoch = 0;
     cudaGraphExec_t gexec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [phase][buffer parity]
     int parity = 0, launches_per_step[2] = {0, 0};
@@ -209,6 +210,7 @@ static void choose_tiles(kmc_handle *h) {
     if (!h->useCells) { K.drift = 0; if (!getenv("KMC_SKIN")) K.skin = 24.0; }      // tile path: rebuilt every step (the cells are at least as large as this needs)
     if (h->useCells && K.drift > 0) { h->listEvery = 6; if (const char *o = getenv("KMC_REUSE")) h->listEvery = std::max(1, atoi(o)); }
     h->sinceBuild = 0;
+    h->adapt = !(getenv("KMC_ADAPT") && atoi(getenv("KMC_ADAPT")) == 0);
 }
 // arrays of the sparse path (allocated on first need: strips can re-derive the grid and with it the choice of path)
 static bool ensure_cells_arrays(kmc_handle *h) {
@@ -622,6 +624,15 @@ extern "C" int kmc_sync(kmc_handle *h) {
     CK(cudaStreamSynchronize(h->stream));
     int scal[S_COUNT];
     CK(cudaMemcpy(scal, h->D.scal, sizeof scal, cudaMemcpyDeviceToHost));
+    // List reuse pays while few molecules outrun their grid entries. A state in which many do (most ligands bound: the members
+    // of a rotating complex swing 10-30 A per step) makes every reuse step walk the stale grid once per such molecule; from
+    // NT/64 special entries per step on, rebuilding every step is the cheaper exact path. Decided here, where the host
+    // synchronises anyway; the graphs are captured again with the new constants. KMC_ADAPT=0 disables it.
+    if (h->listEvery > 1 && h->sinceBuild > 1 && h->adapt && scal[S_NSPEC] > std::max(h->NT / 64, 64)) {
+        h->listEvery = 1; h->sinceBuild = 0; h->adapted = true;
+        h->K.drift = 0; if (!getenv("KMC_SKIN")) h->K.skin = 24.0;
+        for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) { cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]); h->gexec[p >> 1][p & 1] = nullptr; }
+    }
     int ovf = scal[S_OVERFLOW];
     if (h->listEvery <= 1) ovf &= ~32;          // a pair list that is rebuilt every step may overflow into in-place evaluation
     if (ovf) { h->err = "device buffer overflow (mask " + std::to_string(ovf) + ((ovf & 32) ? "; pair list too small for list reuse: set KMC_REUSE=1" : "") + ")"; return KMC_ERR_CAPACITY; }

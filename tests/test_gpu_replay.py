@@ -179,6 +179,7 @@ def test_list_reuse_settings_are_all_exact(golden_dir, monkeypatch, reuse, skin,
     (beyond KMC_SKIN) and molecules that drifted more than KMC_DRIFT from their grid entry are handled as special entries. Every
     setting must reproduce the oracle: tiny skins / drifts make most molecules special, large ones stretch the stale list."""
     monkeypatch.setenv("KMC_RESOLVE", "cells")
+    monkeypatch.setenv("KMC_ADAPT", "0")           # stay on the requested setting however many special entries it makes
     monkeypatch.setenv("KMC_REUSE", reuse)
     if skin: monkeypatch.setenv("KMC_SKIN", skin)
     if drift: monkeypatch.setenv("KMC_DRIFT", drift)
@@ -224,3 +225,20 @@ def test_binary_checkpoint_continues_bit_for_bit(golden_dir, tmp_path):
         other.read_checkpoint_bin(path)
     with pytest.raises(kmc_b200.KmcError):
         other.read_checkpoint_bin(str(tmp_path / "missing.kmcb"))
+
+
+def test_list_reuse_backs_off_when_molecules_outrun_their_entries(golden_dir, monkeypatch):
+    """With a 1.5 A skin most molecules are 'special entries' of every reuse step; at the next host synchronisation the library
+    falls back to rebuilding the grid every step (with its default skin). The switch happens in the middle of a run and must not
+    change a bit."""
+    monkeypatch.setenv("KMC_RESOLVE", "cells"); monkeypatch.setenv("KMC_REUSE", "6"); monkeypatch.setenv("KMC_SKIN", "1.5")
+    g = load_golden_state(os.path.join(golden_dir, "hot200_step40000.npz"))
+    o, k = make_pair(150, 50, tuple(g["params"]["box"]), "hot", seed=12)
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    o.step(9); k.step(9)
+    assert k.events()["special_entries"] > 10
+    k.sync()                                       # the back-off is decided here
+    lockstep(o, k, 300, 1, "adapt", per_step_accept=True)
+    assert k.events()["special_entries"] == 0      # every step rebuilds now: no special entries any more
+    k.close()
