@@ -1,19 +1,20 @@
 // csrc/kmc_kernels.cu -- hand-written sm_100a kernels of the per-timestep KMC sweep
 // (replaces /root/reference/main.cpp:461-2202).
 //
-//  step s:   [complexes]  k_uf_init -> k_uf_hook -> k_uf_flatten -> k_cx_build            (S1, 514-562; only when
-//                                                                                           the bond table changed)
-//            [propose]    k_propose_simple, k_propose_complex                              (S2a-S2f, 577-1732)
-//            [grid]       k_grid_count -> scan -> k_grid_scatter                           (cell list, new)
-//            [resolve]    k_cells_cut + k_pairs_eval | k_resolve_tiles -> k_pend_resolve (+ revert)     (S2g, 1759-1860 + ordering)
-//            [reactions]  k_react_pairs -> k_react_resolve -> k_finish (dissociation)            (S3, 1876-2141)
+//  step s:   [complexes]  k_uf_init (+ step begin) -> k_uf_hook -> k_uf_flatten -> k_cx_build   (S1, 514-562; bodies run only
+//                                                                                           when the bond table changed)
+//            [propose]    k_propose_rec, k_propose_lig, k_propose_complex                  (S2a-S2f, 577-1732)
+//            [grid]       k_scan_* -> k_grid_scatter -> k_cells_cut                        (cell list + pair list; sparse path:
+//                                                                                           every 6th step, reused in between)
+//            [resolve]    k_pairs_eval (+ k_special_pairs) | k_resolve_tiles -> k_pend_resolve   (S2g, 1759-1860 + ordering)
+//            [reactions]  k_react_pairs -> k_react_resolve -> k_finish (copy-back of rejected units, dissociation)   (S3, 1876-2141)
 //            pointer swap                                                                  (S4, 2164-2202)
 //
 // Sequential semantics in parallel: the reference sweeps molecules in index order and every overlap test
 // sees the already-updated positions of earlier molecules (Gauss-Seidel, main.cpp:577/642). A unit's
 // PROPOSAL depends only on its own old pose and its keyed draws, so all proposals are computed at once;
 // its accept/reject decision depends on earlier units only through their (rare) rejections, and is
-// resolved by a monotone fixed point: a unit is decided as soon as every earlier unit it could touch is.
+// resolved by a monotone fixed point over the recorded findings: a unit is decided as soon as every earlier unit it touches is.
 #include "kmc_device.cuh"
 #include <cuda_pipeline.h>
 #define REC_TILE 256
