@@ -556,7 +556,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
     // S3
-    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 4 + 1, RP_CHUNK) + 148, 148 * 16), B, 0, st>>>(A)));
+    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 4 + 1, RP_CHUNK) + 148, 148 * 32), RPTHREADS, 0, st>>>(A)));
     LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
     LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
 }

@@ -1557,8 +1557,13 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
 // work items: the list pairs flagged by k_pairs_eval (sparse path), then the pairs collected by the tile kernel / the special
 // entries. Flagged pairs are few (~1 in 10): each CTA compacts the flags of a chunk of the list in shared memory first, so the
 // expensive geometry + draw runs with full warps.
+#ifndef RP_CHUNK
 #define RP_CHUNK 512
-__global__ void __launch_bounds__(128) k_react_pairs(const __grid_constant__ Args A) {
+#endif
+#ifndef RPTHREADS
+#define RPTHREADS 64
+#endif
+__global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
     __shared__ int items[2 * RP_CHUNK];          // (list index << 1) | direction
