@@ -242,3 +242,55 @@ def test_list_reuse_backs_off_when_molecules_outrun_their_entries(golden_dir, mo
     lockstep(o, k, 300, 1, "adapt", per_step_accept=True)
     assert k.events()["special_entries"] == 0      # every step rebuilds now: no special entries any more
     k.close()
+
+
+def test_full_size_membrane_properties(monkeypatch):
+    """BASELINE configs[3] size on one GPU (1e6 molecules, default density), where the oracle is too slow to follow: the
+    size-independent properties the domain offers. (a) Exactness of the list reuse at full size: a handle that rebuilds its
+    neighbour grid every step and one that reuses it for 6 steps end bit-identical. (b) What the sweep must conserve:
+    rigid bodies keep their edge lengths, no committed overlap (receptor centres >= 2 rA, receptor-ligand beads >= rA + rB,
+    ligand-ligand beads >= 2 rB; plain Euclidean distances, the reference has no minimum image), a symmetric bond table whose
+    counters add up, ligand centres inside the slab up to one reflection."""
+    from scipy.spatial import cKDTree
+    na, nb = 750000, 250000
+    box = kmc_b200.scaled_box(na + nb)
+    runs = []
+    for reuse in ("1", "6"):
+        monkeypatch.setenv("KMC_REUSE", reuse)
+        k = kmc_b200.Kmc(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=9))
+        k.init_random(seed=4, sort_cells=True)
+        k.step(26)
+        k.sync()
+        runs.append((k.get_packed(), k.series(), k.events()))
+        k.close()
+    (pa, sa, ea), (pb, sb, eb) = runs
+    for x, y in zip(pa, pb):
+        assert np.array_equal(x, y)
+    assert sa == sb and ea["reverted"] == eb["reverted"] and ea["reverted"] > 0
+    rec, lig, rl, rs, rc = pb
+    p = kmc_b200.default_params()
+    rA, rB = p.rA, p.rB
+    c, s2, s3 = rec[:, 0:2], rec[:, 2:4], rec[:, 4:6]
+    assert np.allclose(np.linalg.norm(s2 - c, axis=1), rA, rtol=0, atol=1e-9) and np.allclose(np.linalg.norm(s3 - c, axis=1), rA, rtol=0, atol=1e-9)
+    L = lig.reshape(nb, 8, 3)
+    rs_ = 2 * rB / np.sqrt(3.0)
+    for q in (1, 2, 3):
+        assert np.allclose(np.linalg.norm(L[:, q] - L[:, 0], axis=1), rs_, rtol=0, atol=1e-9)
+        assert np.allclose(np.linalg.norm(L[:, 4 + q] - L[:, 0], axis=1), rs_ + rB, rtol=0, atol=1e-9)
+    assert np.allclose(np.linalg.norm(L[:, 4] - L[:, 0], axis=1), rB, rtol=0, atol=1e-9)
+    assert L[:, 0, 2].min() > -8.0 and L[:, 0, 2].max() < box[2] + 8.0
+    # no committed overlap
+    assert len(cKDTree(c).query_pairs(2 * rA - 1e-9)) == 0
+    beads = L[:, 1:4].reshape(-1, 3)
+    owner = np.repeat(np.arange(nb), 3)
+    pairs = cKDTree(beads).query_pairs(2 * rB - 1e-9, output_type="ndarray")
+    assert not len(pairs) or (owner[pairs[:, 0]] == owner[pairs[:, 1]]).all()            # only beads of one ligand are that close
+    rec_beads = np.concatenate([np.column_stack([c, np.full(na, z)]) for z in (0.0, 2 * rA, 4 * rA, 6 * rA)])
+    low = beads[beads[:, 2] < 6 * rA + rA + rB]                      # only beads this close to the membrane can touch a receptor
+    assert len(low) > 1000
+    assert cKDTree(rec_beads).query_ball_point(low, rA + rB - 1e-9, return_length=True).sum() == 0
+    # bond table: symmetric, counters add up
+    bound = np.nonzero(rl >= 0)[0]
+    assert sb["bond_num_rl"] == len(bound) and sb["bond_num"] == sb["bond_num_rl"] + sb["bond_num_cis"] + sb["bond_num_mono_cis"]
+    cis = np.nonzero(rc >= 0)[0]
+    assert (rc[rc[cis]] == cis).all() and len(cis) == 2 * (sb["bond_num_cis"] + sb["bond_num_mono_cis"])
