@@ -303,7 +303,8 @@ def main():
                 "config": {"workload": "%d-molecule membrane patch per GPU (%d receptors + %d ligands, default density L=%.0f A, paper parameters, "
                                        "fresh random start); %s" % (M, na, nb, p.box[0],
                                                                   "per-GPU share of the 1e7-molecule membrane (configs[4])" if M == 1250000 else "custom size"),
-                           "mc_steps_per_step": S, "mode": "replay (index-order sweep, keyed Philox)", "l2": "working set > L2 (no flush needed)",
+                           "mc_steps_per_step": S, "mode": "replay (index-order sweep, keyed Philox)",
+                           "neighbour_list": "grid + pair list rebuilt every %s steps, reused in between (exact: far movers / drifted molecules are special entries)" % os.environ.get("KMC_REUSE", "6"), "l2": "working set > L2 (no flush needed)",
                            "decomposition": strips_note if decomp == "strips" else ("independent patches per GPU, no data-path collective" + ("; " + strips_note if strips_note else "")),
                            "timing": "host wall clock between barriers (halo refresh is host-orchestrated)" if decomp == "strips" else "CUDA events on the library stream",
                            "ms_per_mc_step": ms_max / args.steps / S},
