@@ -63,7 +63,8 @@ typedef struct kmc_params {
     uint64_t seed;                 /* Philox key; replica r uses seed + r */
     double cell_edge;              /* neighbour-grid cell edge in Angstrom; 0 = automatic */
     int32_t device;                /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t min_image;             /* 0 = plain Euclidean distances, the reference's behaviour (main.cpp:642-646: positions are wrapped,
+                                      distances never use the minimum image). 1 is refused with KMC_ERR_INVALID (not implemented). */
 } kmc_params;
 
 /* the bond.dat columns, main.cpp:2251 (plus the step they belong to) */
@@ -132,6 +133,10 @@ int64_t kmc_get_complexes(kmc_handle *h, int32_t replica, int32_t *row_len, int3
 /* histogram of ligand-rooted complex sizes over replica (or all replicas if replica < 0): hist[s] = number of
  * complexes with s members, sizes >= nbins-1 are accumulated in the last bin */
 int kmc_get_oligomer_hist(kmc_handle *h, int32_t replica, int64_t *hist, int32_t nbins);
+/* component label of every molecule after the last step: root[i] (1-based, i = 1..N; root[0] = 0) = reference id of the head of the
+ * unit molecule i moves with -- the BFS root ligand of its complex (main.cpp:525-560: the lowest-index ligand), or, for a ligand-free
+ * receptor, itself / the lower index of its cis pair (main.cpp:682-688) */
+int kmc_get_complex_labels(kmc_handle *h, int32_t replica, int32_t *root_of_molecule);
 /* geometry of the neighbour grid (cell = floor((x - x0) * inv_edge)); the checkerboard order of KMC_MODE_PRODUCTION colours these cells */
 int kmc_get_grid(kmc_handle *h, double *x0, double *y0, double *inv_edge, int32_t *ncx, int32_t *ncy);
 /* replay diagnostics: accepted[N+1] (1-based): 1 if the molecule's unit kept its move in the last step */

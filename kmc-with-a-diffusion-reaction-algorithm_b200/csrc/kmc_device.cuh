@@ -19,6 +19,7 @@ enum Scalar {
     S_NSURV,              // pairs in surv[] this step
     S_NREJ,               // rejected units of this step (rejList)
     S_NA_LIVE, S_NB_LIVE, // molecules actually present in the receptor / ligand blocks (<= NAt / NBt; strips change them)
+    S_NSPEC_MAX,          // largest S_NSPEC of any step so far (the host decides the list-reuse back-off from it)
     S_COUNT = 16
 };
 enum UnitState : unsigned char { U_UNKNOWN = 0, U_ACCEPT = 1, U_REJECT = 2 };

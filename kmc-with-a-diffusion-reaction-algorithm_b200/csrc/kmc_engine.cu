@@ -4,6 +4,7 @@
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
 #define KMC_NKERNELS 19
+#define MON_EVERY 256
 
 #include <algorithm>
 #include <cmath>
@@ -54,9 +55,16 @@ struct kmc_handle {
     double *stageRec = nullptr; int *stageInt = nullptr;      // device staging of kmc_set_packed / kmc_get_packed
     // strips
     bool strip_on = false; double strip_W = 0, strip_lo = 0, strip_hi = 0; int64_t strip_refreshes = 0;
+    int strip_every = 0, strip_since = 0;      // > 0: kmc_step refreshes the halos itself every strip_every steps (kmc_strip_comm_init)
     HostLocal strip_local; std::vector<char> strip_msg[3];
     struct StripDev *strip_dev = nullptr;
     int64_t launches = 0, passes = 0;
+    int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
+    int forkMask = 6;                // KMC_FORK, read once at kmc_create
+    // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
+    // (asynchronously) and the copy of the PREVIOUS interval is examined -- capacity overflows are reported and the list-reuse
+    // back-off is decided without ever stalling the stream
+    int *monHost = nullptr; cudaEvent_t monEvent = nullptr; bool monPending = false; int64_t sinceMon = 0;
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py roofline)
     bool profiling = false;
     struct Pending { int id; cudaEvent_t a, b; };
@@ -234,6 +242,8 @@ extern "C" void kmc_destroy(kmc_handle *h) {
     for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto ev : h->evpool) cudaEventDestroy(ev);
     for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]);
+    if (h->monHost) cudaFreeHost(h->monHost);
+    if (h->monEvent) cudaEventDestroy(h->monEvent);
     for (auto e : h->evFork) if (e) cudaEventDestroy(e);
     for (auto e : h->evJoin) if (e) cudaEventDestroy(e);
     for (auto q : h->side) if (q) cudaStreamDestroy(q);
@@ -259,6 +269,9 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || cudaSetDevice(p->device) != cudaSuccess) return fail(KMC_ERR_CUDA, "cannot select device");
     if (prop.major != 10) return fail(KMC_ERR_CUDA, "device is not compute capability 10.x: the kernels are built for sm_100a only");
+    if (p->min_image != 0) return fail(KMC_ERR_INVALID, "min_image = 1 is not implemented: the reference computes plain Euclidean distances (main.cpp:642-646), which is what 0 selects");
+    h->nSM = std::max(prop.multiProcessorCount, 1);
+    if (const char *o = getenv("KMC_FORK")) h->forkMask = atoi(o);
     fill_consts(*p, h->K);
     const Consts &K = h->K;
     h->R = K.R; h->NA = K.NA; h->NB = K.NB; h->N = K.NA + K.NB; h->NAt = K.NAt; h->NBt = K.NBt; h->NT = K.NT;
@@ -270,6 +283,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     for (auto &q : h->side) ok = ok && cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &e : h->evFork) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     for (auto &e : h->evJoin) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->monEvent, cudaEventDisableTiming) == cudaSuccess && cudaMallocHost((void **)&h->monHost, sizeof(int) * S_COUNT) == cudaSuccess;
 #define A(ptr, n) ok = ok && dalloc(h, &D.ptr, (size_t)(n)) == cudaSuccess
     A(recC, K.NAt); A(recS2, K.NAt); A(recS3, K.NAt); A(recCn, K.NAt); A(recS2n, K.NAt); A(recS3n, K.NAt);
     A(lig, (size_t)K.NBt * 24); A(lign, (size_t)K.NBt * 24);
@@ -523,13 +537,13 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     // S2 proposals: free receptors / cis dimers, free ligands and complexes are disjoint sets of molecules -- three kernels side
     // by side (forked branches of the graph; on one stream when per-kernel timing is on)
-    const int forkMask = h->profiling ? 0 : (getenv("KMC_FORK") ? atoi(getenv("KMC_FORK")) : 6);     // bit0: receptor/ligand proposals side by side (measured slower than back to back), bit1: special entries, bit2: complexes
+    const int forkMask = h->profiling ? 0 : h->forkMask;     // bit0: receptor/ligand proposals side by side (measured slower than back to back), bit1: special entries, bit2: complexes
     const bool fork = forkMask & 1, fork2 = forkMask & 2, forkC = forkMask & 5;                       // bit2: only the complexes on a side branch
     cudaStream_t s1 = fork ? h->side[0] : st, s2 = forkC ? h->side[1] : st;
     if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
-    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<std::min(nblk(std::max(NAt, 1), REC_TILE), 148 * RECMINB), REC_TILE, 0, st>>>(A)));
+    LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<std::min(nblk(std::max(NAt, 1), REC_TILE), h->nSM * RECMINB), REC_TILE, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
-    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), 148 * 12), 32 * CX_WARPS, 0, s2>>>(A)));
+    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), h->nSM * 12), 32 * CX_WARPS, 0, s2>>>(A)));
     if (fork || forkC) {
         cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);
         cudaStreamWaitEvent(st, h->evJoin[0], 0); cudaStreamWaitEvent(st, h->evJoin[1], 0);
@@ -543,20 +557,20 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     }
     // S2g: every (probe, neighbour) pair within reach is classified once (+ reaction-pair pre-selection), then the order
     // dependence is settled from the pending findings
-    const int gl = std::min(nblk(NT, B), 148 * 8);
+    const int gl = std::min(nblk(NT, B), h->nSM * 8);
     if (h->useCells) {
-        if (build) LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), 148 * CMINB * 16), CTHREADS, 0, st>>>(A)));
+        if (build) LAUNCH(KID_RESOLVE, (k_cells_cut<<<std::min(nblk(NT + NT / 16 + 1, CTHREADS), h->nSM * CMINB * 16), CTHREADS, 0, st>>>(A)));
         cudaStream_t s3 = fork2 ? h->side[0] : st;
         if (!build && fork2) { cudaEventRecord(h->evFork[1], st); cudaStreamWaitEvent(s3, h->evFork[1], 0); }
-        LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PE_CHUNK) + 148, 148 * 16), PTHREADS, 0, st>>>(A)));
+        LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PE_CHUNK) + h->nSM, h->nSM * 16), PTHREADS, 0, st>>>(A)));
         if (!build) {           // the special entries next to the list pairs (both only publish findings)
-            LAUNCH(KID_SPECIAL, (k_special_pairs<<<148, 32 * SP_WARPS, 0, s3>>>(A)));
+            LAUNCH(KID_SPECIAL, (k_special_pairs<<<h->nSM, 32 * SP_WARPS, 0, s3>>>(A)));
             if (fork2) { cudaEventRecord(h->evJoin[2], s3); cudaStreamWaitEvent(st, h->evJoin[2], 0); }
         }
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
     // S3
-    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 4 + 1, RP_CHUNK) + 148, 148 * 32), RPTHREADS, 0, st>>>(A)));
+    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 4 + 1, RP_CHUNK) + h->nSM, h->nSM * 32), RPTHREADS, 0, st>>>(A)));
     LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
     LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
 }
@@ -586,13 +600,52 @@ static int ensure_graphs(kmc_handle *h) {
     return KMC_OK;
 }
 
+// What the host does with a snapshot of the device scalars (taken at kmc_sync, or asynchronously every MON_EVERY steps of a
+// long kmc_step): report capacity overflows, and decide the list-reuse back-off.
+// List reuse pays while few molecules outrun their grid entries. A state in which many do (most ligands bound: the members
+// of a rotating complex swing 10-30 A per step) makes every reuse step walk the stale grid once per such molecule; from
+// NT/64 special entries per step on, rebuilding every step is the cheaper exact path; the graphs are captured again with
+// the new constants. KMC_ADAPT=0 disables it.
+static int examine_scalars(kmc_handle *h, const int *scal) {
+    const int nspec = std::max(scal[S_NSPEC], scal[S_NSPEC_MAX]);
+    if (h->listEvery > 1 && h->adapt && nspec > std::max(h->NT / 64, 64)) {
+        h->listEvery = 1; h->sinceBuild = 0; h->adapted = true;
+        h->K.drift = 0; if (!getenv("KMC_SKIN")) h->K.skin = 24.0;
+        for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) { cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]); h->gexec[p >> 1][p & 1] = nullptr; }
+    }
+    int ovf = scal[S_OVERFLOW];
+    if (h->listEvery <= 1) ovf &= ~32;          // a pair list that is rebuilt every step may overflow into in-place evaluation
+    if (ovf) {
+        h->err = "device buffer overflow (mask " + std::to_string(ovf) + ((ovf & 32) ? "; pair list too small for list reuse: set KMC_REUSE=1" : "") +
+                 ((ovf & 64) ? "; strips: a complex is wider than the halo budget (halo_width - refresh_every * reach)" : "") +
+                 ((ovf & 128) ? "; strips: a message or the local capacity is too small" : "") +
+                 ((ovf & 256) ? "; strips: a halo copy inside the exact zone differs from its owner's original" : "") + ")";
+        return KMC_ERR_CAPACITY;
+    }
+    return KMC_OK;
+}
+static int monitor_poll(kmc_handle *h) {
+    if (h->monPending) {
+        CK(cudaEventSynchronize(h->monEvent));          // recorded MON_EVERY steps ago: long complete unless the host runs far ahead
+        h->monPending = false;
+        int rc = examine_scalars(h, h->monHost); if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h->monHost, h->D.scal, sizeof(int) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->monEvent, h->stream));
+    h->monPending = true; h->sinceMon = 0;
+    return KMC_OK;
+}
+
+static int strip_auto_refresh(kmc_handle *h);
+
 extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     if (!h) return KMC_ERR_INVALID;
     if (n < 0) { h->err = "kmc_step: negative step count"; return KMC_ERR_INVALID; }
     int rc = select_device(h); if (rc) return rc;
     cudaStream_t st = h->stream;
-    if (!h->profiling && h->use_graph && n > 0) { rc = ensure_graphs(h); if (rc) return rc; }
     for (int64_t it = 0; it < n; it++) {
+        if (h->sinceMon >= MON_EVERY) { rc = monitor_poll(h); if (rc) return rc; }
+        if (!h->profiling && h->use_graph && !h->gexec[0][0]) { rc = ensure_graphs(h); if (rc) return rc; }
         const int phase = (h->sinceBuild == 0 || h->sinceBuild >= h->listEvery) ? 0 : 1;
         if (phase == 0) h->sinceBuild = 0;
         if (++h->epoch >= 0xfffffff0u) {         // the stamp of the per-cell chains is about to wrap: start a new era
@@ -611,8 +664,9 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
         }
         // S4: the new buffers become the committed state
         swap_buffers(h->D); h->parity ^= 1;
-        h->sinceBuild++;
+        h->sinceBuild++; h->sinceMon++;
         h->passes += 1; h->step_done++; h->stepped = true;
+        if (h->strip_every > 0 && ++h->strip_since >= h->strip_every) { rc = strip_auto_refresh(h); if (rc) return rc; }
     }
     CK(cudaGetLastError());
     return KMC_OK;
@@ -624,19 +678,8 @@ extern "C" int kmc_sync(kmc_handle *h) {
     CK(cudaStreamSynchronize(h->stream));
     int scal[S_COUNT];
     CK(cudaMemcpy(scal, h->D.scal, sizeof scal, cudaMemcpyDeviceToHost));
-    // List reuse pays while few molecules outrun their grid entries. A state in which many do (most ligands bound: the members
-    // of a rotating complex swing 10-30 A per step) makes every reuse step walk the stale grid once per such molecule; from
-    // NT/64 special entries per step on, rebuilding every step is the cheaper exact path. Decided here, where the host
-    // synchronises anyway; the graphs are captured again with the new constants. KMC_ADAPT=0 disables it.
-    if (h->listEvery > 1 && h->sinceBuild > 1 && h->adapt && scal[S_NSPEC] > std::max(h->NT / 64, 64)) {
-        h->listEvery = 1; h->sinceBuild = 0; h->adapted = true;
-        h->K.drift = 0; if (!getenv("KMC_SKIN")) h->K.skin = 24.0;
-        for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) { cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]); h->gexec[p >> 1][p & 1] = nullptr; }
-    }
-    int ovf = scal[S_OVERFLOW];
-    if (h->listEvery <= 1) ovf &= ~32;          // a pair list that is rebuilt every step may overflow into in-place evaluation
-    if (ovf) { h->err = "device buffer overflow (mask " + std::to_string(ovf) + ((ovf & 32) ? "; pair list too small for list reuse: set KMC_REUSE=1" : "") + ")"; return KMC_ERR_CAPACITY; }
-    return KMC_OK;
+    h->monPending = false; h->sinceMon = 0;
+    return examine_scalars(h, scal);
 }
 
 // n steps bracketed by CUDA events on the handle's stream (the stream the kernels are launched on)
@@ -736,6 +779,21 @@ extern "C" int64_t kmc_get_complexes(kmc_handle *h, int32_t rep, int32_t *row_le
         }
     }
     return tot;
+}
+
+extern "C" int kmc_get_complex_labels(kmc_handle *h, int32_t rep, int32_t *root) {
+    if (!h || !root) return KMC_ERR_INVALID;
+    if (rep < 0 || rep >= h->R) { h->err = "kmc_get_complex_labels: bad replica"; return KMC_ERR_INVALID; }
+    if (!h->stepped) { h->err = "kmc_get_complex_labels: no completed step yet (labels are those of the last step's sweep)"; return KMC_ERR_INVALID; }
+    int rc = select_device(h); if (rc) return rc;
+    std::vector<int> unitOf(h->NT);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(unitOf.data(), h->D.unitOf, sizeof(int) * h->NT, cudaMemcpyDeviceToHost));
+    auto ref_id_host = [&](int gid) { return gid < h->NAt ? gid % h->NA + 1 : h->NA + (gid - h->NAt) % h->NB + 1; };
+    root[0] = 0;
+    for (int a = 0; a < h->NA; a++) root[a + 1] = ref_id_host(unitOf[rep * h->NA + a]);
+    for (int b = 0; b < h->NB; b++) root[h->NA + 1 + b] = ref_id_host(unitOf[h->NAt + rep * h->NB + b]);
+    return KMC_OK;
 }
 
 extern "C" int kmc_get_oligomer_hist(kmc_handle *h, int32_t rep, int64_t *hist, int32_t nbins) {
@@ -842,6 +900,7 @@ extern "C" int kmc_run(kmc_handle *h, int64_t n_steps, int32_t output_every, con
     while (h->step_done < end) {
         int64_t next = std::min<int64_t>(end, (h->step_done / output_every + 1) * output_every);
         int rc = kmc_step(h, next - h->step_done); if (rc) return rc;
+        rc = kmc_sync(h); if (rc) return rc;                                    // capacity errors of the interval are reported here, never dropped
         if (h->step_done % output_every == 0)                                   // main.cpp:2247, 2291
             for (int r = 0; r < h->R; r++) {
                 std::string suf = h->R > 1 ? "." + std::to_string(r) : "";

@@ -55,6 +55,7 @@ __global__ void k_uf_init(const __grid_constant__ Args A, int begin) {
     KARGS
     if (begin && blockIdx.x == 0 && threadIdx.x == 0) {
         D.step64[0] += 1; D.scal[S_EPOCH] += 1;
+        if (D.scal[S_NSPEC] > D.scal[S_NSPEC_MAX]) D.scal[S_NSPEC_MAX] = D.scal[S_NSPEC];
         D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0;
         if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
         if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
@@ -234,8 +235,8 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
     const uint32_t me = ref_id(K, D, gid);
     {
         const int a = gid;
-        const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
-                     u2 = keyed_uniform(seed, me, 0, step, 2);
+        double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
+        const double u2 = keyed_uniform(seed, me, 0, step, 2);
         const double phai = mul(mul(u1, 2.0), K.pai);
         double sp, cp; sincos(phai, &sp, &cp);
         if (p < 0) {
@@ -336,9 +337,8 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
         const uint64_t seed = seed_of(cK, replica_of_gid(K, gid));
         const uint32_t me = ref_id(K, D, gid);
         const double ox = l.p[0][0], oy = l.p[0][1], oz = l.p[0][2];
-        const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1),
-                     u2 = keyed_uniform(seed, me, 0, step, 2), u3 = keyed_uniform(seed, me, 0, step, 3),
-                     u4 = keyed_uniform(seed, me, 0, step, 4), u5 = keyed_uniform(seed, me, 0, step, 5);
+        double u0, u1, u2, u3, u4, u5;
+        keyed_uniform2(seed, me, 0, step, 0, u0, u1); keyed_uniform2(seed, me, 0, step, 2, u2, u3); keyed_uniform2(seed, me, 0, step, 4, u4, u5);
         const double amp = mul(K.ampB, u0);
         const double theta = mul(u1, K.pai), phai = mul(mul(u2, 2.0), K.pai);
         double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
@@ -671,7 +671,8 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
         int nB = 0;
         for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;          // (uniform across the warp, tiny)
         const int nA = size - nB;
-        const double u0 = keyed_uniform(seed, me, 0, step, 0), u1 = keyed_uniform(seed, me, 0, step, 1), u2 = keyed_uniform(seed, me, 0, step, 2);
+        double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
+        const double u2 = keyed_uniform(seed, me, 0, step, 2);
         // ---- S2d rigid move (main.cpp:974-1131); complexes with >= 2 ligands have D = 0 but still draw ----
         const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
         const double phai = mul(mul(u1, 2.0), K.pai);

@@ -36,12 +36,22 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
     }
 }
 
-// U[0,1) with 53 random bits
-__host__ __device__ __forceinline__ double keyed_uniform(uint64_t seed, uint32_t mol, uint32_t partner, uint64_t step, uint32_t slot) {
-    uint32_t c[4] = {mol, partner, (uint32_t)step, slot | ((uint32_t)(step >> 32) << 8)};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    uint64_t bits = ((uint64_t)c[1] << 32) | c[0];
+// U[0,1) with 53 random bits. One Philox block serves TWO draws: slots 2b and 2b+1 share the block whose counter carries the even
+// slot number, slot 2b takes the words (x1:x0), slot 2b+1 the words (x3:x2). keyed_uniform2 returns both halves of a block
+// (the proposal kernels need slots 0..5 of one molecule: three blocks instead of six).
+__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    const uint64_t bits = ((uint64_t)hi << 32) | lo;
     return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+__host__ __device__ __forceinline__ void keyed_uniform2(uint64_t seed, uint32_t mol, uint32_t partner, uint64_t step, uint32_t evenSlot, double &ua, double &ub) {
+    uint32_t c[4] = {mol, partner, (uint32_t)step, evenSlot | ((uint32_t)(step >> 32) << 8)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    ua = u53(c[1], c[0]); ub = u53(c[3], c[2]);
+}
+__host__ __device__ __forceinline__ double keyed_uniform(uint64_t seed, uint32_t mol, uint32_t partner, uint64_t step, uint32_t slot) {
+    uint32_t c[4] = {mol, partner, (uint32_t)step, (slot & ~1u) | ((uint32_t)(step >> 32) << 8)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (slot & 1u) ? u53(c[3], c[2]) : u53(c[1], c[0]);
 }
 // 31-bit integer, the stand-in for libc rand() (RAND_MAX = 2^31-1)
 __host__ __device__ __forceinline__ int keyed_rand31(uint64_t seed, uint32_t mol, uint32_t count, uint64_t step) {

@@ -595,3 +595,4 @@ extern "C" int kmc_strip_rebuild_dev(kmc_handle *h, int64_t rec_low, int64_t lig
     h->stepped = false; h->sinceBuild = 0; h->strip_refreshes++;
     return kmc_sync(h);
 }
+static int strip_auto_refresh(kmc_handle *h) { h->strip_since = 0; return KMC_OK; }

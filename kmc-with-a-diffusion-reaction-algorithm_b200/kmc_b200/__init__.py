@@ -25,7 +25,7 @@ class Params(C.Structure):
                 ("bond_dist_cut", C.c_double), ("thetapd_cut", C.c_double), ("thetaot_cut", C.c_double),
                 ("cis_thetaot_cut", C.c_double), ("cis_dist_cut", C.c_double),
                 ("n_receptor", C.c_int32), ("n_ligand", C.c_int32), ("n_replicas", C.c_int32), ("mode", C.c_int32),
-                ("seed", C.c_uint64), ("cell_edge", C.c_double), ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("seed", C.c_uint64), ("cell_edge", C.c_double), ("device", C.c_int32), ("min_image", C.c_int32)]
 
 
 class Series(C.Structure):
@@ -37,7 +37,7 @@ class Series(C.Structure):
 
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
-           "kmc_get_complexes", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
+           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_begin_refresh_dev", "kmc_strip_message_dev",
            "kmc_strip_recv_dev", "kmc_strip_rebuild_dev", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
@@ -83,6 +83,7 @@ def lib():
         L.kmc_get_series.argtypes = [vp, i32, C.POINTER(Series)]
         L.kmc_get_complexes.restype = i64
         L.kmc_get_complexes.argtypes = [vp, i32, vp, vp, i64]
+        L.kmc_get_complex_labels.argtypes = [vp, i32, vp]
         L.kmc_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
         L.kmc_get_accept.argtypes = [vp, i32, vp]
         L.kmc_get_events.argtypes = [vp, vp]
@@ -306,6 +307,12 @@ class Kmc:
             rows.append(mem[o:o + rl[l]].tolist()); o += rl[l]
         assert o == tot
         return rows
+
+    def complex_labels(self, replica=0):
+        """root[i] (1-based): reference id of the head of the unit molecule i belongs to after the last step"""
+        a = np.zeros(self.n + 1, dtype=np.int32)
+        self._ck(lib().kmc_get_complex_labels(self.h, replica, a.ctypes.data))
+        return a
 
     def oligomer_hist(self, replica=-1, nbins=64):
         hist = np.zeros(nbins, dtype=np.int64)

@@ -6,7 +6,8 @@
 // Draw keying shared by oracle and product (DESIGN.md "Random streams"):
 //   key     = 64-bit seed (lo, hi)
 //   counter = (molecule id [1-based, reference numbering], partner code, step, slot)
-//   U[0,1)  = ((x1:x0) >> 11) * 2^-53            (53 random bits, like generate_canonical<double,53>)
+//   U[0,1)  = ((x1:x0) >> 11) * 2^-53 for an even slot, ((x3:x2) >> 11) * 2^-53 for the odd slot that shares its block
+//             (counter word 3 carries the even slot number; 53 random bits, like generate_canonical<double,53>)
 //   rand()  = x0 >> 1                             (31 bits, RAND_MAX = 2^31-1)
 #pragma once
 #include <cstdint>
@@ -40,10 +41,13 @@ enum Slot : uint32_t {
     SLOT_SHUFFLE = 16,        // main.cpp:1285/1345/1413/1597  molecule = root ligand, partner = running rand() count
 };
 
+// one Philox block serves two draws: slots 2b and 2b+1 share the block whose counter carries the even slot number;
+// slot 2b takes (x1:x0), slot 2b+1 takes (x3:x2)
 static inline double keyed_uniform(uint64_t seed, uint32_t mol, uint32_t partner, uint64_t step, uint32_t slot) {
-    Philox4 r = philox4x32_10(mol, partner, (uint32_t)step, slot | ((uint32_t)(step >> 32) << 8),
+    Philox4 r = philox4x32_10(mol, partner, (uint32_t)step, (slot & ~1u) | ((uint32_t)(step >> 32) << 8),
                               (uint32_t)seed, (uint32_t)(seed >> 32));
-    uint64_t bits = ((uint64_t)r.v[1] << 32) | r.v[0];
+    const int h = (slot & 1u) ? 2 : 0;
+    uint64_t bits = ((uint64_t)r.v[h + 1] << 32) | r.v[h];
     return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
 }
 

@@ -37,7 +37,26 @@ def save_state(name, fr, params):
                         max_complex=fr["max_complex"], params=json.dumps(params))
 
 
+def keyed_entry(kat):
+    """the UNMODIFIED reference driven by the keyed Philox stream (ref_harness.cpp --keyed: draw = f(seed; call site -> slot, molecule,
+    partner, step)), continued from the hot 40000-step state: pins the keyed mode of the oracle and, through the bond table, the GPU"""
+    g40 = np.load(os.path.join(HERE, "hot200_step40000.npz"))
+    last = kat["hot200_40000"]["frames"][-1]
+    fr_in = dict(step=int(g40["step"]), bond_num=last["bond_num"], bond_num_rl=last["bond_num_rl"], bond_num_cis=last["bond_num_cis"],
+                 bond_num_mono_cis=last["bond_num_mono_cis"], max_complex=int(g40["max_complex"]), R=g40["R"], status=g40["status"], res_nei=g40["res_nei"])
+    sets_k = dict(DENSE["sets"]); sets_k.update(HOT)
+    s, fr = refio.run_ref("n200", 200, 3000, frames_every=1000, sets=sets_k, scales=DENSE["scales"], in_frame=fr_in, keyed_seed=4242)
+    kat["keyed_hot200"] = dict(summary=s, frames=[summarize(f) for f in fr], seed=4242, start="hot200_step40000.npz", sets=sets_k, scales=DENSE["scales"])
+
+
 def main():
+    if "--only-keyed" in sys.argv:          # the key layout of the Philox stream changed: only this entry depends on it
+        path = os.path.join(HERE, "ref_kat.json")
+        kat = json.load(open(path))
+        keyed_entry(kat)
+        json.dump(kat, open(path, "w"), indent=1)
+        print(json.dumps(kat["keyed_hot200"]["frames"][-1]))
+        return
     kat = {}
     s, fr = refio.run_ref("n200", 200, 1000)
     kat["default_1000"] = dict(summary=s, frames=[summarize(f) for f in fr])
@@ -64,15 +83,7 @@ def main():
         subprocess.run(cmd, cwd=td, check=True, capture_output=True)
         kat["ref_records"] = dict(bond_dat=open(os.path.join(wd, "bond.dat")).read(), cluster_log=open(os.path.join(wd, "cluster.log")).read(),
                                   note="dense system, steps 5000 and 10000, written by the unmodified reference")
-    # the UNMODIFIED reference driven by the keyed Philox stream (ref_harness.cpp --keyed: draw = f(seed; call site -> slot, molecule,
-    # partner, step)), continued from the hot 40000-step state: pins the keyed mode of the oracle and, through the bond table, the GPU
-    g40 = np.load(os.path.join(HERE, "hot200_step40000.npz"))
-    fr_in = dict(step=int(g40["step"]), bond_num=kat["hot200_40000"]["frames"][-1]["bond_num"], bond_num_rl=kat["hot200_40000"]["frames"][-1]["bond_num_rl"],
-                 bond_num_cis=kat["hot200_40000"]["frames"][-1]["bond_num_cis"], bond_num_mono_cis=kat["hot200_40000"]["frames"][-1]["bond_num_mono_cis"],
-                 max_complex=int(g40["max_complex"]), R=g40["R"], status=g40["status"], res_nei=g40["res_nei"])
-    sets_k = dict(DENSE["sets"]); sets_k.update(HOT)
-    s, fr = refio.run_ref("n200", 200, 3000, frames_every=1000, sets=sets_k, scales=DENSE["scales"], in_frame=fr_in, keyed_seed=4242)
-    kat["keyed_hot200"] = dict(summary=s, frames=[summarize(f) for f in fr], seed=4242, start="hot200_step40000.npz", sets=sets_k, scales=DENSE["scales"])
+    keyed_entry(kat)
     # the reference's own position.cpt / test.gro / parameter.log of a 5000-step N=40 hot run, with the state they describe
     with tempfile.TemporaryDirectory() as td:
         wd = os.path.join(td, "wd"); out = os.path.join(td, "f.bin")
