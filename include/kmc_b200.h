@@ -192,12 +192,32 @@ int kmc_strip_load_global(kmc_handle *h, int32_t n_rec, int32_t n_lig, const dou
 int kmc_strip_begin_refresh(kmc_handle *h);
 int64_t kmc_strip_message(kmc_handle *h, int32_t side, const void **data);
 int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_low, const void *from_high, int64_t n_high);
-/* the same refresh with all data staying in device memory: messages are [rec records][lig records] in device buffers (counts are
- * returned separately), the caller moves them GPU to GPU (NCCL) into the buffers kmc_strip_recv_dev hands out */
-int kmc_strip_begin_refresh_dev(kmc_handle *h);
-int kmc_strip_message_dev(kmc_handle *h, int32_t side, void **dev_ptr, int64_t *n_rec, int64_t *n_lig);
-int kmc_strip_recv_dev(kmc_handle *h, int32_t side, int64_t n_rec, int64_t n_lig, void **dev_ptr);
-int kmc_strip_rebuild_dev(kmc_handle *h, int64_t rec_low, int64_t lig_low, int64_t rec_high, int64_t lig_high);
+/* ---- the product path of the refresh: device resident, one exchange round, no host synchronisation (csrc/kmc_strips.cu) ----
+ * Messages are fixed-capacity device buffers with the record counts in a 64-byte header; classify/pack kernels, the exchange and
+ * the merge kernels are all enqueued on the handle's stream. Guards (reported by kmc_sync / kmc_step as KMC_ERR_CAPACITY): a unit
+ * wider in x than halo_width - refresh_every * (reach per step), a band or the local capacity too small, a unit that arrives
+ * incomplete. */
+/* halo width that keeps the owned strip exact for refresh_every steps: refresh_every * (reach of information per step) + complex_extent */
+double kmc_strip_halo_width(const kmc_params *p, int32_t refresh_every, double complex_extent);
+/* NCCL communicator over the ranks of kmc_strip_configure: rank 0 fills id128 (128 bytes) with kmc_strip_unique_id, the caller
+ * distributes it (MPI, torch.distributed, a file ...), every rank calls kmc_strip_comm_init (collective). refresh_every > 0 makes
+ * kmc_step refresh the halos itself every refresh_every steps. All ranks must have been created with the same capacities. */
+int kmc_strip_unique_id(void *id128);
+int kmc_strip_comm_init(kmc_handle *h, const void *id128, int32_t refresh_every);
+/* one refresh over NCCL (grouped ncclSend/ncclRecv with the two x-neighbours); asynchronous; collective */
+int kmc_strip_refresh(kmc_handle *h);
+/* the same refresh between n handles of ONE process (logical ranks 0..n-1 on one GPU; device-to-device copies instead of NCCL) */
+int kmc_strip_refresh_local(kmc_handle **handles, int32_t n, int32_t refresh_every);
+/* outputs of the WHOLE membrane (main.cpp:2247-2253, 2291-2305): every complex counted by the owner of its root ligand, every bond
+ * by the owner of the receptor's unit. reduce != 0: ncclAllReduce over the communicator (collective, every rank gets the result);
+ * reduce == 0: this rank's part. Values are those of the last refresh; a communicator-backed handle refreshes first if it has stepped since. */
+int kmc_strip_get_series(kmc_handle *h, int32_t reduce, kmc_series *out);
+int kmc_strip_get_oligomer_hist(kmc_handle *h, int32_t reduce, int64_t *hist, int32_t nbins);
+/* per-rank state exchange with HOST buffers in the message record layout (64-byte receptor records, then 208-byte ligand records,
+ * id-sorted). which = 2: the units this rank owns (union over ranks = the membrane); 3: everything it holds (owned + halo copies),
+ * which is what kmc_strip_load_records takes to restore the rank. */
+int kmc_strip_get_records(kmc_handle *h, int32_t which, void *host_buf, int64_t cap_bytes, int64_t *n_rec, int64_t *n_lig);
+int kmc_strip_load_records(kmc_handle *h, const void *host_buf, int64_t n_rec, int64_t n_lig, int64_t step_done);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,12 @@ KD double hash_x(const Consts &K, double x) {       // stripHalf = +inf on a sin
     const double t = x - K.stripXc;
     return t > K.stripHalf ? x - K.Lx : (t < -K.stripHalf ? x + K.Lx : x);
 }   // real branch: the single-GPU path pays nothing
+// strip (rank) that owns a unit whose head molecule has its centre at x: strips of equal width along x, periodic
+KD int d_strip_owner(const Consts &K, double x) {
+    const double L = K.Lx, xw = x - L * round(x / L);
+    int r = (int)floor((xw + L / 2) / (L / K.strips));
+    return min(max(r, 0), K.strips - 1);
+}
 KD int nA_live(const Dev &D) { return D.scal[S_NA_LIVE]; }
 KD int nB_live(const Dev &D) { return D.scal[S_NB_LIVE]; }
 KD bool gid_live(const Consts &K, const Dev &D, int gid) { return gid < K.NAt ? gid < nA_live(D) : (gid < K.NT && gid - K.NAt < nB_live(D)); }

@@ -300,7 +300,9 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     ok = ok && ensure_cells_arrays(h); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
-    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); A(rejList, K.NT); D.pendCap = 2 * K.NT + 4096; A(pendList, D.pendCap); A(step64, 1);
+    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); A(rejList, K.NT); D.pendCap = 2 * K.NT + 4096;
+    if (const char *o = getenv("KMC_TEST_PENDCAP")) D.pendCap = std::max(1, atoi(o));      // tests: force the overflow report
+    A(pendList, D.pendCap); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
 #undef A
     ok = ok && dalloc(h, &h->d_series, (size_t)K.R * 6) == cudaSuccess;

@@ -98,7 +98,9 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     if (h >= nB_live(D)) return;
     if (D.unitOf[cK.NAt + h] != cK.NAt + h) return;
     int size = D.cxSize[h];
-    if (size > D.maxComplex[h / cK.NB]) atomicMax(&D.maxComplex[h / cK.NB], size);      // main.cpp:896-898 (read first: one hot address)
+    // main.cpp:896-898 (read first: one hot address). With strips only the rank that owns the root counts it: a halo copy in the
+    // outer (possibly stale) part of the halo may show a complex the true trajectory never had
+    if (size > D.maxComplex[h / cK.NB] && (cK.strips <= 1 || d_strip_owner(cK, D.lig[(size_t)h * 24]) == cK.stripRank)) atomicMax(&D.maxComplex[h / cK.NB], size);
     if (size <= 1) return;
     int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
     D.cxOff[h] = off;

@@ -294,33 +294,108 @@ extern "C" int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_
 }
 
 // ================================================================================================================
-// Device-side refresh: the same three phases (classify + pack, exchange by the caller, merge) without the host round trip.
-// Messages live in device buffers ([RecMsg x nRec][LigMsg x nLig], counts travel separately), so NCCL moves them GPU to GPU.
+// Device-side refresh: classify + pack, exchange, merge -- every phase enqueued on the handle's stream, NO host synchronisation.
+// Messages live in device buffers of FIXED capacity: a 64-byte header {nRec, nLig, overflow} followed by RecMsg[nRec] and
+// LigMsg[nLig] (both id-sorted). The counts travel inside the message, so one exchange round suffices and the host never
+// has to know them: it always moves the whole band buffer (a few MB over NVLink), the merge kernels read the headers.
+//   exchange = NCCL (kmc_strip_refresh: ncclSend/ncclRecv to the two x-neighbours in one group, on the handle's stream), or
+//              device-to-device copies between handles of one process (kmc_strip_refresh_local: K logical ranks on one GPU,
+//              how the tests prove equality with the single-GPU run).
+// By-products of every refresh: the owned-only bond counts, complex statistics and oligomer-size histogram of this rank
+// (kmc_strip_get_series / kmc_strip_get_oligomer_hist all-reduce them: the bond.dat row of the WHOLE membrane).
 // The host path above is kept as the reference implementation (tests compare the two).
 // ================================================================================================================
+#include <dlfcn.h>
+#include <nccl.h>
+
+#define MSG_HDR 64
+#define STRIP_HIST_BINS 256
+
+// NCCL is bound at run time (dlopen): the library stays loadable on a machine without NCCL, and inside a process that already
+// carries a libnccl.so.2 (torch) the same copy is used.
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static const char *nccl_load() {
+    if (g_nccl.lib) return nullptr;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return "libnccl.so.2 not found (strips over several GPUs need NCCL)";
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) return "libnccl: missing symbol " name
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return nullptr;
+}
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) { h->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return KMC_ERR_CUDA; }   \
+    } while (0)
+
 struct StripDev {
     unsigned char *flag = nullptr;            // [NT] bit0 owned, bit1 send to lower-x neighbour, bit2 send to higher-x neighbour
     int *tileCnt = nullptr, *tileOff = nullptr;   // per tile of ST_TILE molecules of one species: members of list 0 low, 1 high, 2 keep; their exclusive prefixes
-    int *dcnt = nullptr, *hcnt = nullptr;         // totals [list*2 + species] on the device / in pinned host memory (+ [6] = overflow flag)
+    int *dcnt = nullptr;                      // [8] totals [list*2 + species], [6] = lists that do not fit their buffer (bit mask)
     int ntA = 0, ntB = 0;
-    char *msg[3] = {nullptr}; size_t msgCap[3] = {0};     // packed messages (2 = the owned set)
-    char *rcv[2] = {nullptr}; size_t rcvCap[2] = {0};     // what the neighbours sent (0 from lower x, 1 from higher x)
-    int *bondRef = nullptr;                   // [NAt*3 + NBt*3] bonds of the merged molecules as reference ids, before translation
-    int cnt[6] = {0};                         // totals of pos[]
-    int padN = 0;
+    char *msg[3] = {nullptr}; size_t msgCap[3] = {0};     // packed messages: 0 to lower x, 1 to higher x (band capacity), 2 = the owned set (full capacity)
+    char *rcv[2] = {nullptr};                 // what the neighbours sent (0 from lower x, 1 from higher x), band capacity
+    size_t bandCap = 0;                       // bytes of a band message (header + records): the same on every rank
+    int *bondRef = nullptr;                   // [NAt*2 + NBt*3] bonds of the merged molecules as reference ids, before translation
+    int *series = nullptr;                    // [8] device, owned only: R-L, mono-cis, cis bonds, complexes, molecules in complexes, -, -, running-max complex
+    unsigned long long *hist = nullptr;       // [STRIP_HIST_BINS] sizes of the owned ligand-rooted complexes (last step's tables)
+    int *hostI = nullptr;                     // pinned: [0..15] header staging, [16..31] series read-back
+    unsigned long long *hostH = nullptr;      // pinned: histogram read-back
+    ncclComm_t comm = nullptr;
+    bool fresh = false;                       // no step since the last refresh: by-products and msg[2] describe the current state
+    double budget = INFINITY;                 // largest x-extent of a unit the halo width covers (halo - refresh_every * reach per step)
 };
 
-__device__ __forceinline__ int d_strip_owner(const Consts &K, double x) {
-    const double L = K.Lx, xw = x - L * round(x / L);
-    int r = (int)floor((xw + L / 2) / (L / K.strips));
-    return min(max(r, 0), K.strips - 1);
-}
 __global__ void k_strip_prebuild(const __grid_constant__ Args A) {
     KARGS
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; }
 }
-// one thread per molecule, unit heads act: owner of the unit from the head's centre; bands from every member
-__global__ void k_strip_classify(const __grid_constant__ Args A, unsigned char *flag, double lo, double hi, double W) {
+// by-product 1 (before the complexes are rebuilt: the tables are those of the last step's sweep, like kmc_get_series /
+// kmc_get_oligomer_hist on one GPU): complexes rooted at a ligand this rank owns -- owner = strip of the root's centre
+__global__ void k_strip_cx_owned(const __grid_constant__ Args A, int stepped, int *series, unsigned long long *hist) {
+    KARGS
+    const Consts &K = cK;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    int size = 0;
+    if (stepped && h < nB_live(D) && D.unitOf[K.NAt + h] == K.NAt + h && d_strip_owner(K, D.lig[(size_t)h * 24]) == K.stripRank) size = D.cxSize[h];
+    const unsigned ones = __ballot_sync(0xffffffffu, size == 1);
+    if ((threadIdx.x & 31) == 0 && ones) atomicAdd(&hist[1], (unsigned long long)__popc(ones));
+    if (size > 1) { atomicAdd(&hist[min(size, STRIP_HIST_BINS - 1)], 1ULL); atomicAdd(&series[3], 1); atomicAdd(&series[4], size); }
+}
+// by-product 2 (after k_strip_classify): bonds of the receptors whose unit this rank owns (the bond.dat columns, main.cpp:2251)
+__global__ void k_strip_bonds_owned(const __grid_constant__ Args A, const unsigned char *flag, int *series) {
+    KARGS
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    int rl = 0, mono = 0, cis = 0;
+    if (a < nA_live(D) && (flag[a] & 1)) {
+        rl = D.recLig[a] >= 0;
+        const int p = D.recCis[a];
+        if (p > a) { if (rl || D.recLig[p] >= 0) cis = 1; else mono = 1; }
+    }
+    for (int o = 16; o; o >>= 1) { rl += __shfl_down_sync(0xffffffffu, rl, o); mono += __shfl_down_sync(0xffffffffu, mono, o); cis += __shfl_down_sync(0xffffffffu, cis, o); }
+    if ((threadIdx.x & 31) == 0) { if (rl) atomicAdd(&series[0], rl); if (mono) atomicAdd(&series[1], mono); if (cis) atomicAdd(&series[2], cis); }
+    if (a == 0) series[7] = D.maxComplex[0];
+}
+// one thread per molecule, unit heads act: owner of the unit from the head's centre; bands from every member.
+// Guard of the exactness precondition: a unit wider (in x) than the halo budget could reach beyond what the neighbours sent.
+__global__ void k_strip_classify(const __grid_constant__ Args A, unsigned char *flag, double lo, double hi, double W, double budget) {
     KARGS
     const Consts &K = cK;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -331,20 +406,31 @@ __global__ void k_strip_classify(const __grid_constant__ Args A, unsigned char *
     if (gid < K.NAt) { m2 = D.recCis[gid]; if (m2 >= 0) nmem = 2; }
     else if (D.cxSize[gid - K.NAt] > 1) { nmem = D.cxSize[gid - K.NAt]; row = D.members + D.cxOff[gid - K.NAt]; }
     int f = own ? 1 : 0;
-    if (own)
+    if (own) {
+        double xmin = INFINITY, xmax = -INFINITY;
         for (int i = 0; i < nmem; i++) {
             const int m = row ? row[i] : (i == 0 ? gid : m2);
             double x, y; centre_of(K, D, m, false, x, y);
             const double t = hash_x(K, x);
+            xmin = fmin(xmin, t); xmax = fmax(xmax, t);
             if (t < lo + W) f |= 2;
             if (t >= hi - W) f |= 4;
         }
+        if (K.strips > 1 && xmax - xmin > budget) atomicOr(&D.scal[S_OVERFLOW], 64);
+        if (K.strips == 2 && (f & 2)) f &= ~4;          // two ranks: both neighbours are the same peer -- a unit inside both bands travels once
+    }
     for (int i = 0; i < nmem; i++) flag[row ? row[i] : (i == 0 ? gid : m2)] = (unsigned char)f;
+}
+__global__ void k_strip_flag_all(const __grid_constant__ Args A, unsigned char *flag) {       // every live molecule into list 2
+    KARGS
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < cK.NT) flag[gid] = gid_live(cK, D, gid) ? 1 : 0;
 }
 // ---- the three messages in one pass ---------------------------------------------------------------------------------------
 // Records must be id-sorted, i.e. in index order. A tile = ST_TILE consecutive molecules of one species (receptor tiles first),
 // a thread 8 consecutive molecules: k_strip_count counts the members of the three lists per tile, k_strip_scan_tiles turns the
-// counts into tile offsets and totals, k_strip_pack_all recomputes the ranks inside its tile and writes the records.
+// counts into tile offsets and totals and writes the message headers, k_strip_pack_all recomputes the ranks inside its tile and
+// writes the records.
 #define ST_TILE 2048
 __device__ __forceinline__ void strip_tile_counts(const Consts &K, const Dev &D, const unsigned char *flag, int ntA, int &first, int &n, bool &lig, int c[3]) {
     const int t = blockIdx.x;
@@ -370,8 +456,10 @@ __global__ void __launch_bounds__(256) k_strip_count(const __grid_constant__ Arg
     __syncthreads();
     if (threadIdx.x < 3) { int v = 0; for (int w = 0; w < 8; w++) v += sh[threadIdx.x][w]; tileCnt[blockIdx.x * 3 + threadIdx.x] = v; }
 }
-// one CTA: exclusive prefix over the tiles of each species for each list; totals to cnt6[list*2 + species]; capacity check of the messages
-__global__ void __launch_bounds__(1024) k_strip_scan_tiles(const int *tileCnt, int *tileOff, int ntA, int ntB, int *cnt6, size_t cap0, size_t cap1, size_t cap2) {
+// one CTA: exclusive prefix over the tiles of each species for each list; totals to cnt6[list*2 + species]; capacity check and
+// header of each message (a list that does not fit travels empty with its overflow word set: sender and receiver both report it)
+struct MsgBufs { char *p[3]; size_t cap[3]; };
+__global__ void __launch_bounds__(1024) k_strip_scan_tiles(const int *tileCnt, int *tileOff, int ntA, int ntB, int *cnt6, MsgBufs M, int *scal) {
     __shared__ int sh[32]; __shared__ int carry;
     for (int seq = 0; seq < 6; seq++) {
         const int sp = seq & 1, list = seq >> 1, t0 = sp ? ntA : 0, nt = sp ? ntB : ntA;
@@ -394,10 +482,15 @@ __global__ void __launch_bounds__(1024) k_strip_scan_tiles(const int *tileCnt, i
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const size_t cap[3] = {cap0, cap1, cap2};
         int bad = 0;
-        for (int l = 0; l < 3; l++) if ((size_t)cnt6[l * 2] * sizeof(RecMsg) + (size_t)cnt6[l * 2 + 1] * sizeof(LigMsg) > cap[l]) bad |= 1 << l;
+        for (int l = 0; l < 3; l++) {
+            const bool fits = MSG_HDR + (size_t)cnt6[l * 2] * sizeof(RecMsg) + (size_t)cnt6[l * 2 + 1] * sizeof(LigMsg) <= M.cap[l];
+            if (!fits) bad |= 1 << l;
+            int *hdr = reinterpret_cast<int *>(M.p[l]);
+            hdr[0] = fits ? cnt6[l * 2] : 0; hdr[1] = fits ? cnt6[l * 2 + 1] : 0; hdr[2] = fits ? 0 : 1;
+        }
         cnt6[6] = bad;
+        if (bad) atomicOr(&scal[S_OVERFLOW], 128);
     }
 }
 __device__ __forceinline__ void strip_write_record(const Consts &K, const Dev &D, int gid, char *out, int nRecOut, int pos) {
@@ -417,12 +510,11 @@ __device__ __forceinline__ void strip_write_record(const Consts &K, const Dev &D
         for (int q = 0; q < 24; q++) o->pose[q] = p[q];
     }
 }
-__global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ Args A, const unsigned char *flag, int ntA, const int *tileOff, const int *cnt6,
-                                                        char *msg0, char *msg1, char *msg2) {
+__global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ Args A, const unsigned char *flag, int ntA, const int *tileOff, const int *cnt6, MsgBufs M) {
     KARGS
     const Consts &K = cK;
     __shared__ int sh[3][8];
-    if (cnt6[6]) return;                                   // a message does not fit its buffer: the host reports it
+    const int bad = cnt6[6];
     int first, n, c[3]; bool lig;
     strip_tile_counts(K, D, flag, ntA, first, n, lig, c);
     int rank[3];
@@ -436,13 +528,12 @@ __global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ 
         for (int w = 0; w < (int)(threadIdx.x >> 5); w++) rank[l] += sh[l][w];
         rank[l] += tileOff[blockIdx.x * 3 + l];
     }
-    char *msg[3] = {msg0, msg1, msg2};
     for (int q = 0; q < 8; q++) {
         const int i = first + q;
         if (i >= n) break;
         const int gid = lig ? K.NAt + i : i, f = flag[gid];
         const int bits[3] = {(f >> 1) & 1, (f >> 2) & 1, f & 1};
-        for (int l = 0; l < 3; l++) if (bits[l]) strip_write_record(K, D, gid, msg[l], cnt6[l * 2], rank[l]++);
+        for (int l = 0; l < 3; l++) if (bits[l] && !((bad >> l) & 1)) strip_write_record(K, D, gid, M.p[l] + MSG_HDR, cnt6[l * 2], rank[l]++);
     }
 }
 template <class T> __device__ __forceinline__ int d_lower_bound(const T *a, int n, int ref) {
@@ -450,27 +541,37 @@ template <class T> __device__ __forceinline__ int d_lower_bound(const T *a, int 
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid].ref < ref) lo = mid + 1; else hi = mid; }
     return lo;
 }
-// merge of the three id-sorted lists (kept, from low, from high): every record knows its final index
-struct MergeSrc { const RecMsg *r[3]; const LigMsg *l[3]; int nr[3], nl[3]; };
+// merge of the three id-sorted lists (kept, from low, from high): every record knows its final index. The lists are disjoint:
+// a molecule has one owner, and with two ranks (both bands from the same peer) the sender lists a unit once (k_strip_classify).
+struct MergeSrc { const char *base[3]; };
+__device__ __forceinline__ bool merge_counts(const Consts &K, const Dev &D, const MergeSrc &M, int nr[3], int nl[3]) {
+    bool bad = false;
+    for (int k = 0; k < 3; k++) { const int *hdr = reinterpret_cast<const int *>(M.base[k]); nr[k] = hdr[0]; nl[k] = hdr[1]; bad |= hdr[2] != 0; }
+    return !bad && nr[0] + nr[1] + nr[2] <= K.NAt && nl[0] + nl[1] + nl[2] <= K.NBt;
+}
 __global__ void k_strip_merge(const __grid_constant__ Args A, MergeSrc M, int *bondRef) {
     KARGS
     const Consts &K = cK;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int totR = M.nr[0] + M.nr[1] + M.nr[2], totL = M.nl[0] + M.nl[1] + M.nl[2];
+    int nr[3], nl[3];
+    if (!merge_counts(K, D, M, nr, nl)) { if (i == 0) atomicOr(&D.scal[S_OVERFLOW], 128); return; }      // a message or the local capacity is too small
+    const int totR = nr[0] + nr[1] + nr[2], totL = nl[0] + nl[1] + nl[2];
+    const RecMsg *R[3]; const LigMsg *L[3];
+    for (int k = 0; k < 3; k++) { R[k] = reinterpret_cast<const RecMsg *>(M.base[k] + MSG_HDR); L[k] = reinterpret_cast<const LigMsg *>(M.base[k] + MSG_HDR + (size_t)nr[k] * sizeof(RecMsg)); }
     if (i < totR) {
-        int k = 0; while (i >= M.nr[k]) { i -= M.nr[k]; k++; }
-        const RecMsg m = M.r[k][i];
+        int k = 0; while (i >= nr[k]) { i -= nr[k]; k++; }
+        const RecMsg m = R[k][i];
         int pos = i;
-        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(M.r[o], M.nr[o], m.ref);
+        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(R[o], nr[o], m.ref);
         D.recC[pos] = make_double2(m.pose[0], m.pose[1]); D.recS2[pos] = make_double2(m.pose[2], m.pose[3]); D.recS3[pos] = make_double2(m.pose[4], m.pose[5]);
         D.refA[pos] = (unsigned)m.ref; D.recSite[pos] = m.site;
         bondRef[pos * 2] = m.ligRef; bondRef[pos * 2 + 1] = m.cisRef;
     } else if (i < totR + totL) {
         i -= totR;
-        int k = 0; while (i >= M.nl[k]) { i -= M.nl[k]; k++; }
-        const LigMsg *src = &M.l[k][i];
+        int k = 0; while (i >= nl[k]) { i -= nl[k]; k++; }
+        const LigMsg *src = &L[k][i];
         int pos = i;
-        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(M.l[o], M.nl[o], src->ref);
+        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(L[o], nl[o], src->ref);
         D.refB[pos] = (unsigned)src->ref;
         double *p = D.lig + (size_t)pos * 24;
         for (int q = 0; q < 24; q++) p[q] = src->pose[q];
@@ -482,10 +583,15 @@ __device__ __forceinline__ int d_find_ref(const unsigned *a, int n, int ref) {
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < (unsigned)ref) lo = mid + 1; else hi = mid; }
     return (lo < n && a[lo] == (unsigned)ref) ? lo : -1;
 }
-__global__ void k_strip_fix_bonds(const __grid_constant__ Args A, const int *bondRef, int nA, int nB) {
+// bonds back from reference ids to local indices; thread 0 publishes the new live counts (nobody in this kernel reads them)
+__global__ void k_strip_fix_bonds(const __grid_constant__ Args A, MergeSrc M, const int *bondRef) {
     KARGS
     const Consts &K = cK;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int nr[3], nl[3];
+    if (!merge_counts(K, D, M, nr, nl)) return;
+    const int nA = nr[0] + nr[1] + nr[2], nB = nl[0] + nl[1] + nl[2];
+    if (i == 0) { D.scal[S_NA_LIVE] = nA; D.scal[S_NB_LIVE] = nB; D.scal[S_TOPO_DIRTY] = 1; }
     if (i < nA) {
         const int lr = bondRef[i * 2], cr = bondRef[i * 2 + 1];
         const int l = lr ? d_find_ref(D.refB, nB, lr) : -1, c = cr ? d_find_ref(D.refA, nA, cr) : -1;
@@ -501,9 +607,30 @@ __global__ void k_strip_fix_bonds(const __grid_constant__ Args A, const int *bon
     }
 }
 
-static void strip_dev_free(kmc_handle *h) { if (h->strip_dev && h->strip_dev->hcnt) cudaFreeHost(h->strip_dev->hcnt); delete h->strip_dev; h->strip_dev = nullptr; }    // device buffers are in h->allocs
+static void strip_dev_free(kmc_handle *h) {       // device buffers are in h->allocs
+    if (!h->strip_dev) return;
+    StripDev &S = *h->strip_dev;
+    if (S.comm && g_nccl.CommDestroy) { cudaSetDevice(h->P.device); cudaStreamSynchronize(h->stream); g_nccl.CommDestroy(S.comm); }
+    if (S.hostI) cudaFreeHost(S.hostI);
+    if (S.hostH) cudaFreeHost(S.hostH);
+    delete h->strip_dev; h->strip_dev = nullptr;
+}
+
+// reach of information per step (A): the largest overlap reach (ligand-ligand centres) plus twice the largest displacement of a
+// molecule in one step (translation + the swing of a ligand site / complex member under the rotation)
+static double strip_reach_per_step(const Consts &K) {
+    const double rs = K.rB * 2 / sqrt(3.0);
+    const double disp = std::max({K.ampA, K.ampB, K.ampCis, K.ampBond}) + 0.45 * (rs + K.rB);
+    return K.reachLL + 2 * disp;
+}
+extern "C" double kmc_strip_halo_width(const kmc_params *p, int32_t refresh_every, double complex_extent) {
+    if (!p || refresh_every < 1) return -1.0;
+    Consts K; fill_consts(*p, K);
+    return refresh_every * strip_reach_per_step(K) + complex_extent;
+}
 
 static int strip_dev_alloc(kmc_handle *h) {
+    if (!h->strip_dev) h->strip_dev = new StripDev;
     StripDev &S = *h->strip_dev;
     if (S.flag) return KMC_OK;
     const int NT = h->NT;
@@ -511,24 +638,40 @@ static int strip_dev_alloc(kmc_handle *h) {
     bool ok = dalloc(h, &S.flag, NT) == cudaSuccess && dalloc(h, &S.tileCnt, (size_t)3 * (S.ntA + S.ntB) + 3) == cudaSuccess &&
               dalloc(h, &S.tileOff, (size_t)3 * (S.ntA + S.ntB) + 3) == cudaSuccess && dalloc(h, &S.dcnt, 8) == cudaSuccess &&
               dalloc(h, &S.bondRef, (size_t)2 * h->NAt + (size_t)3 * h->NBt + 8) == cudaSuccess &&
-              cudaMallocHost((void **)&S.hcnt, 8 * sizeof(int)) == cudaSuccess;
-    const size_t full = (size_t)h->NAt * sizeof(RecMsg) + (size_t)h->NBt * sizeof(LigMsg) + 64, band = full / 3 + 4096;
-    for (int k = 0; k < 3 && ok; k++) { S.msgCap[k] = k == 2 ? full : band; ok = dalloc(h, &S.msg[k], S.msgCap[k]) == cudaSuccess; }
-    for (int k = 0; k < 2 && ok; k++) { S.rcvCap[k] = band; ok = dalloc(h, &S.rcv[k], S.rcvCap[k]) == cudaSuccess; }
+              dalloc(h, &S.series, 8) == cudaSuccess && dalloc(h, &S.hist, STRIP_HIST_BINS) == cudaSuccess &&
+              cudaMallocHost((void **)&S.hostI, 32 * sizeof(int)) == cudaSuccess && cudaMallocHost((void **)&S.hostH, STRIP_HIST_BINS * sizeof(unsigned long long)) == cudaSuccess;
+    // band capacity: 1.5 x the share of the local capacity a band of width W is expected to hold (+ slack for small systems);
+    // derived from the handle's capacities and the strip geometry only, so that every rank computes the same number
+    const double width = h->K.Lx / h->K.strips, f = std::min(1.0, 1.5 * h->strip_W / (width + 2 * h->strip_W));
+    const size_t bandRec = std::min<size_t>(h->NAt, (size_t)(h->NAt * f) + 2048), bandLig = std::min<size_t>(h->NBt, (size_t)(h->NBt * f) + 2048);
+    S.bandCap = MSG_HDR + bandRec * sizeof(RecMsg) + bandLig * sizeof(LigMsg);
+    const size_t full = MSG_HDR + (size_t)h->NAt * sizeof(RecMsg) + (size_t)h->NBt * sizeof(LigMsg);
+    for (int k = 0; k < 3 && ok; k++) { S.msgCap[k] = k == 2 ? full : S.bandCap; ok = dalloc(h, &S.msg[k], S.msgCap[k]) == cudaSuccess; }
+    for (int k = 0; k < 2 && ok; k++) ok = dalloc(h, &S.rcv[k], S.bandCap) == cudaSuccess;
     if (!ok) { h->err = "strip: device buffer allocation failed"; return KMC_ERR_CUDA; }
     return KMC_OK;
 }
 
-// Device refresh, part 1. Afterwards kmc_strip_message_dev(side) gives the device address and the record counts of each message.
-extern "C" int kmc_strip_begin_refresh_dev(kmc_handle *h) {
-    if (!h || !h->strip_on) { if (h) h->err = "kmc_strip_begin_refresh_dev: configure strips first"; return KMC_ERR_INVALID; }
-    CK(cudaSetDevice(h->P.device));
-    if (!h->strip_dev) h->strip_dev = new StripDev;
+// classify -> count -> scan -> pack of the flagged lists into msg[0..2] (flags already set)
+static void strip_pack_lists(kmc_handle *h, cudaStream_t st) {
+    StripDev &S = *h->strip_dev;
+    const Args A{h->D, h->K};
+    const int nt = S.ntA + S.ntB;
+    MsgBufs M; for (int k = 0; k < 3; k++) { M.p[k] = S.msg[k]; M.cap[k] = S.msgCap[k]; }
+    k_strip_count<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileCnt);
+    k_strip_scan_tiles<<<1, 1024, 0, st>>>(S.tileCnt, S.tileOff, S.ntA, S.ntB, S.dcnt, M, h->D.scal);
+    k_strip_pack_all<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileOff, S.dcnt, M);
+}
+// Refresh, phase 1 (asynchronous): by-products, complexes of the CURRENT bond table, ownership + bands, the three messages
+static int strip_pack(kmc_handle *h) {
     int rc = strip_dev_alloc(h); if (rc) return rc;
     StripDev &S = *h->strip_dev;
     cudaStream_t st = h->stream;
     const Args A{h->D, h->K};
     const int NT = h->NT, NAt = h->NAt, NBt = h->NBt, B = 128;
+    CK(cudaMemsetAsync(S.series, 0, 8 * sizeof(int), st));
+    CK(cudaMemsetAsync(S.hist, 0, STRIP_HIST_BINS * sizeof(unsigned long long), st));
+    k_strip_cx_owned<<<nblk(std::max(NBt, 1), 256), 256, 0, st>>>(A, h->stepped ? 1 : 0, S.series, S.hist);
     // complexes of the CURRENT bond table (the last step's reactions may have changed it)
     LAUNCH(KID_UF_INIT, (k_strip_prebuild<<<1, 1, 0, st>>>(A)));
     LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A, 0)));
@@ -536,63 +679,205 @@ extern "C" int kmc_strip_begin_refresh_dev(kmc_handle *h) {
     LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
     CK(cudaMemsetAsync(S.flag, 0, NT, st));
-    k_strip_classify<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, h->strip_lo, h->strip_hi, h->strip_W);
-    const int nt = S.ntA + S.ntB;
-    k_strip_count<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileCnt);
-    k_strip_scan_tiles<<<1, 1024, 0, st>>>(S.tileCnt, S.tileOff, S.ntA, S.ntB, S.dcnt, S.msgCap[0], S.msgCap[1], S.msgCap[2]);
-    k_strip_pack_all<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileOff, S.dcnt, S.msg[0], S.msg[1], S.msg[2]);
-    CK(cudaMemcpyAsync(S.hcnt, S.dcnt, 7 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int q = 0; q < 6; q++) S.cnt[q] = S.hcnt[q];
-    if (S.hcnt[6]) { h->err = "strip: message buffer too small (band holds more than a third of the local capacity)"; return KMC_ERR_CAPACITY; }
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
+    k_strip_classify<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, h->strip_lo, h->strip_hi, h->strip_W, S.budget);
+    k_strip_bonds_owned<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, S.flag, S.series);
+    strip_pack_lists(h, st);
     return KMC_OK;
 }
-extern "C" int kmc_strip_message_dev(kmc_handle *h, int32_t side, void **dev_ptr, int64_t *n_rec, int64_t *n_lig) {
-    if (!h || !h->strip_dev || side < 0 || side > 2) return KMC_ERR_INVALID;
-    StripDev &S = *h->strip_dev;
-    if (dev_ptr) *dev_ptr = S.msg[side];
-    if (n_rec) *n_rec = S.cnt[side * 2];
-    if (n_lig) *n_lig = S.cnt[side * 2 + 1];
-    return KMC_OK;
-}
-// device buffer the caller fills with the message coming from the lower-x (side 0) / higher-x (side 1) neighbour
-extern "C" int kmc_strip_recv_dev(kmc_handle *h, int32_t side, int64_t n_rec, int64_t n_lig, void **dev_ptr) {
-    if (!h || !h->strip_dev || side < 0 || side > 1 || !dev_ptr) return KMC_ERR_INVALID;
-    StripDev &S = *h->strip_dev;
-    const size_t need = (size_t)n_rec * sizeof(RecMsg) + (size_t)n_lig * sizeof(LigMsg);
-    if (need > S.rcvCap[side]) { h->err = "strip: incoming message larger than the receive buffer"; return KMC_ERR_CAPACITY; }
-    *dev_ptr = S.rcv[side];
-    return KMC_OK;
-}
-// Device refresh, part 2: merge kept + received (counts of the two incoming messages given), translate bonds, new live counts
-extern "C" int kmc_strip_rebuild_dev(kmc_handle *h, int64_t rec_low, int64_t lig_low, int64_t rec_high, int64_t lig_high) {
-    if (!h || !h->strip_dev) return KMC_ERR_INVALID;
-    CK(cudaSetDevice(h->P.device));
+// Refresh, phase 2 (asynchronous): the new local set = the units this rank owns + what the two neighbours sent
+static int strip_merge(kmc_handle *h) {
     StripDev &S = *h->strip_dev;
     cudaStream_t st = h->stream;
-    MergeSrc M;
-    const int nr[3] = {S.cnt[4], (int)rec_low, (int)rec_high}, nl[3] = {S.cnt[5], (int)lig_low, (int)lig_high};
-    const char *base[3] = {S.msg[2], S.rcv[0], S.rcv[1]};
-    for (int k = 0; k < 3; k++) {
-        M.nr[k] = nr[k]; M.nl[k] = nl[k];
-        M.r[k] = reinterpret_cast<const RecMsg *>(base[k]); M.l[k] = reinterpret_cast<const LigMsg *>(base[k] + (size_t)nr[k] * sizeof(RecMsg));
-    }
-    const int nA = nr[0] + nr[1] + nr[2], nB = nl[0] + nl[1] + nl[2];
-    if (nA > h->NAt || nB > h->NBt) {
-        h->err = "strip: local capacity exceeded (" + std::to_string(nA) + "/" + std::to_string(h->NAt) + " receptors, " + std::to_string(nB) + "/" +
-                 std::to_string(h->NBt) + " ligands)"; return KMC_ERR_CAPACITY;
-    }
     const Args A{h->D, h->K};
-    k_strip_merge<<<nblk(std::max(nA + nB, 1), 128), 128, 0, st>>>(A, M, S.bondRef);
-    k_strip_fix_bonds<<<nblk(std::max(nA + nB, 1), 128), 128, 0, st>>>(A, S.bondRef, nA, nB);
-    int live[2] = {nA, nB}, one = 1;
-    CK(cudaMemcpyAsync(h->D.scal + S_NA_LIVE, live, sizeof live, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
+    MergeSrc M; M.base[0] = S.msg[2]; M.base[1] = S.rcv[0]; M.base[2] = S.rcv[1];
+    k_strip_merge<<<nblk(std::max(h->NT, 1), 128), 128, 0, st>>>(A, M, S.bondRef);
+    k_strip_fix_bonds<<<nblk(std::max(h->NT, 1), 128), 128, 0, st>>>(A, M, S.bondRef);
     CK(cudaGetLastError());
-    h->stepped = false; h->sinceBuild = 0; h->strip_refreshes++;
-    return kmc_sync(h);
+    h->stepped = false; h->sinceBuild = 0; h->strip_since = 0; h->strip_refreshes++;
+    S.fresh = true;
+    return KMC_OK;
 }
-static int strip_auto_refresh(kmc_handle *h) { h->strip_since = 0; return KMC_OK; }
+
+extern "C" int kmc_strip_unique_id(void *id128) {
+    if (!id128) return KMC_ERR_INVALID;
+    if (const char *e = nccl_load()) { g_create_error = e; return KMC_ERR_CUDA; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return KMC_ERR_CUDA; }
+    memcpy(id128, &id, sizeof id);
+    return KMC_OK;
+}
+// One NCCL communicator over the ranks given to kmc_strip_configure (rank 0 creates the id with kmc_strip_unique_id, the caller
+// hands the 128 bytes to every rank by whatever means it has). refresh_every > 0: kmc_step refreshes the halos itself every
+// refresh_every steps. Collective: every rank must call it.
+extern "C" int kmc_strip_comm_init(kmc_handle *h, const void *id128, int32_t refresh_every) {
+    if (!h || !h->strip_on || !id128 || refresh_every < 0) { if (h) h->err = "kmc_strip_comm_init: configure strips first"; return KMC_ERR_INVALID; }
+    CK(cudaSetDevice(h->P.device));
+    if (const char *e = nccl_load()) { h->err = e; return KMC_ERR_CUDA; }
+    int rc = strip_dev_alloc(h); if (rc) return rc;
+    StripDev &S = *h->strip_dev;
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&S.comm, h->K.strips, id, h->K.stripRank));
+    // every rank must move band messages of the same size
+    long long *d = reinterpret_cast<long long *>(S.hist);
+    long long v[2] = {(long long)S.bandCap, -(long long)S.bandCap};
+    CK(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllReduce(d, d, 2, ncclInt64, ncclMax, S.comm, h->stream));
+    CK(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (v[0] != -v[1]) { h->err = "kmc_strip_comm_init: ranks were created with different capacities (band messages must have one size)"; return KMC_ERR_INVALID; }
+    h->strip_every = refresh_every; h->strip_since = 0;
+    if (refresh_every > 0) S.budget = h->strip_W - refresh_every * strip_reach_per_step(h->K);
+    return KMC_OK;
+}
+// The refresh over NCCL: pack -> one grouped send/recv round with the two x-neighbours -> merge, all on the handle's stream.
+extern "C" int kmc_strip_refresh(kmc_handle *h) {
+    if (!h || !h->strip_on) { if (h) h->err = "kmc_strip_refresh: configure strips first"; return KMC_ERR_INVALID; }
+    CK(cudaSetDevice(h->P.device));
+    int rc = strip_pack(h); if (rc) return rc;
+    StripDev &S = *h->strip_dev;
+    const int n = h->K.strips, r = h->K.stripRank;
+    if (n > 1) {
+        if (!S.comm) { h->err = "kmc_strip_refresh: no communicator (kmc_strip_comm_init)"; return KMC_ERR_INVALID; }
+        const int lo = (r + n - 1) % n, hi = (r + 1) % n;
+        // untagged point-to-point operations between one pair of ranks are matched in posting order: sends [to low, to high],
+        // receives [from high, from low] -- with two ranks (both neighbours the same peer) my first send meets its first receive
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.Send(S.msg[0], S.bandCap, ncclChar, lo, S.comm, h->stream));
+        NC(g_nccl.Send(S.msg[1], S.bandCap, ncclChar, hi, S.comm, h->stream));
+        NC(g_nccl.Recv(S.rcv[1], S.bandCap, ncclChar, hi, S.comm, h->stream));
+        NC(g_nccl.Recv(S.rcv[0], S.bandCap, ncclChar, lo, S.comm, h->stream));
+        NC(g_nccl.GroupEnd());
+    } else { CK(cudaMemsetAsync(S.rcv[0], 0, MSG_HDR, h->stream)); CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, h->stream)); }
+    return strip_merge(h);
+}
+static int strip_auto_refresh(kmc_handle *h) { return kmc_strip_refresh(h); }
+// The same refresh between K handles of ONE process (logical ranks 0..K-1, all configured with nranks = K): device-to-device
+// copies stand in for NCCL. refresh_every only sets the extent guard (0 = no guard).
+extern "C" int kmc_strip_refresh_local(kmc_handle **hs, int32_t n, int32_t refresh_every) {
+    if (!hs || n < 1) return KMC_ERR_INVALID;
+    for (int i = 0; i < n; i++) {
+        kmc_handle *h = hs[i];
+        if (!h || !h->strip_on || h->K.strips != n || h->K.stripRank != i) { if (h) h->err = "kmc_strip_refresh_local: handle i must be rank i of n"; return KMC_ERR_INVALID; }
+        CK(cudaSetDevice(h->P.device));
+        int rc = strip_dev_alloc(h); if (rc) return rc;
+        h->strip_dev->budget = refresh_every > 0 ? h->strip_W - refresh_every * strip_reach_per_step(h->K) : INFINITY;
+        rc = strip_pack(h); if (rc) return rc;
+    }
+    for (int i = 0; i < n; i++) { kmc_handle *h = hs[i]; CK(cudaStreamSynchronize(h->stream)); }
+    for (int i = 0; i < n; i++) {
+        kmc_handle *h = hs[i]; StripDev &S = *h->strip_dev;
+        if (n > 1) {
+            StripDev &L = *hs[(i + n - 1) % n]->strip_dev, &H = *hs[(i + 1) % n]->strip_dev;
+            if (L.bandCap != S.bandCap || H.bandCap != S.bandCap) { h->err = "kmc_strip_refresh_local: handles have different capacities"; return KMC_ERR_INVALID; }
+            CK(cudaMemcpyAsync(S.rcv[0], L.msg[1], S.bandCap, cudaMemcpyDeviceToDevice, h->stream));      // what my lower neighbour sent upwards
+            CK(cudaMemcpyAsync(S.rcv[1], H.msg[0], S.bandCap, cudaMemcpyDeviceToDevice, h->stream));      // what my upper neighbour sent downwards
+        } else { CK(cudaMemsetAsync(S.rcv[0], 0, MSG_HDR, h->stream)); CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, h->stream)); }
+        int rc = strip_merge(h); if (rc) return rc;
+    }
+    for (int i = 0; i < n; i++) { kmc_handle *h = hs[i]; CK(cudaStreamSynchronize(h->stream)); }
+    return KMC_OK;
+}
+
+// ---- global outputs of a strip-decomposed membrane (main.cpp:2247-2253, 2291-2305) ------------------------------------------
+// Every complex is counted once, by the rank that owns its root ligand; every bond by the rank that owns the receptor's unit.
+// reduce != 0: all-reduced over the communicator (every rank calls, every rank gets the row of the WHOLE membrane);
+// reduce == 0: this rank's owned-only part (in-process ranks: the caller adds them up).
+static int strip_fresh(kmc_handle *h, const char *who) {
+    if (!h || !h->strip_on) { if (h) h->err = std::string(who) + ": configure strips first"; return KMC_ERR_INVALID; }
+    CK(cudaSetDevice(h->P.device));
+    if (h->strip_dev && h->strip_dev->fresh) return KMC_OK;
+    if (h->K.strips > 1 && !(h->strip_dev && h->strip_dev->comm)) { h->err = std::string(who) + ": the values are those of the last refresh; refresh first"; return KMC_ERR_INVALID; }
+    return kmc_strip_refresh(h);            // refreshing more often than scheduled is always exact
+}
+extern "C" int kmc_strip_get_series(kmc_handle *h, int32_t reduce, kmc_series *out) {
+    if (!out) return KMC_ERR_INVALID;
+    const bool hadStep = h && h->stepped;
+    int rc = strip_fresh(h, "kmc_strip_get_series"); if (rc) return rc;
+    (void)hadStep;
+    StripDev &S = *h->strip_dev; cudaStream_t st = h->stream;
+    int *d = S.series;
+    if (reduce && h->K.strips > 1) {
+        if (!S.comm) { h->err = "kmc_strip_get_series: no communicator"; return KMC_ERR_INVALID; }
+        int *tmp = reinterpret_cast<int *>(S.tileCnt);          // scratch (free between refreshes)
+        CK(cudaMemcpyAsync(tmp, S.series, 8 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        NC(g_nccl.AllReduce(tmp, tmp, 5, ncclInt32, ncclSum, S.comm, st));
+        NC(g_nccl.AllReduce(tmp + 7, tmp + 7, 1, ncclInt32, ncclMax, S.comm, st));
+        d = tmp;
+    }
+    CK(cudaMemcpyAsync(S.hostI + 16, d, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int *v = S.hostI + 16;
+    memset(out, 0, sizeof *out);
+    out->step = h->step_done; out->bond_num_rl = v[0]; out->bond_num_mono_cis = v[1]; out->bond_num_cis = v[2]; out->bond_num = v[0] + v[1] + v[2];
+    out->n_complexes = v[3]; out->n_in_complexes = v[4]; out->max_complex = v[7];
+    if (out->n_complexes) out->cluster_size = (double)out->n_in_complexes / out->n_complexes;     // main.cpp:2200-2202
+    return KMC_OK;
+}
+extern "C" int kmc_strip_get_oligomer_hist(kmc_handle *h, int32_t reduce, int64_t *hist, int32_t nbins) {
+    if (!hist || nbins < 2) return KMC_ERR_INVALID;
+    int rc = strip_fresh(h, "kmc_strip_get_oligomer_hist"); if (rc) return rc;
+    StripDev &S = *h->strip_dev; cudaStream_t st = h->stream;
+    unsigned long long *d = S.hist;
+    if (reduce && h->K.strips > 1) {
+        if (!S.comm) { h->err = "kmc_strip_get_oligomer_hist: no communicator"; return KMC_ERR_INVALID; }
+        unsigned long long *tmp = reinterpret_cast<unsigned long long *>(S.tileOff);      // scratch; 3*(tiles)+3 ints >= 512 ints? checked below
+        if ((size_t)3 * (S.ntA + S.ntB) + 3 < 2 * STRIP_HIST_BINS) tmp = reinterpret_cast<unsigned long long *>(S.bondRef);
+        CK(cudaMemcpyAsync(tmp, S.hist, STRIP_HIST_BINS * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        NC(g_nccl.AllReduce(tmp, tmp, STRIP_HIST_BINS, ncclUint64, ncclSum, S.comm, st));
+        d = tmp;
+    }
+    CK(cudaMemcpyAsync(S.hostH, d, STRIP_HIST_BINS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < nbins; i++) hist[i] = 0;
+    for (int i = 0; i < STRIP_HIST_BINS; i++) hist[std::min(i, nbins - 1)] += (int64_t)S.hostH[i];
+    return KMC_OK;
+}
+
+// ---- per-rank state exchange with HOST buffers (the e2e path of a strip run: every rank moves only its own slab) ------------
+// which = 2: the units this rank owns (the union over ranks is the membrane, every molecule once);
+// which = 3: everything this rank holds (owned + halo copies): what kmc_strip_load_records takes to restore the rank.
+// host_buf receives RecMsg[n_rec] then LigMsg[n_lig] (id-sorted), pinned memory recommended.
+extern "C" int kmc_strip_get_records(kmc_handle *h, int32_t which, void *host_buf, int64_t cap_bytes, int64_t *n_rec, int64_t *n_lig) {
+    if (!h || !h->strip_on || !host_buf || (which != 2 && which != 3)) { if (h) h->err = "kmc_strip_get_records: bad argument"; return KMC_ERR_INVALID; }
+    int rc;
+    if (which == 2) { rc = strip_fresh(h, "kmc_strip_get_records"); if (rc) return rc; }
+    else {
+        CK(cudaSetDevice(h->P.device));
+        rc = strip_dev_alloc(h); if (rc) return rc;
+        const Args A{h->D, h->K};
+        k_strip_flag_all<<<nblk(std::max(h->NT, 1), 256), 256, 0, h->stream>>>(A, h->strip_dev->flag);
+        strip_pack_lists(h, h->stream);
+        h->strip_dev->fresh = false;            // msg[2] no longer holds the owned set
+    }
+    StripDev &S = *h->strip_dev; cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(S.hostI, S.msg[2], MSG_HDR, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t nr = S.hostI[0], nl = S.hostI[1], bytes = nr * (int64_t)sizeof(RecMsg) + nl * (int64_t)sizeof(LigMsg);
+    if (S.hostI[2]) { h->err = "kmc_strip_get_records: message buffer overflow"; return KMC_ERR_CAPACITY; }
+    if (bytes > cap_bytes) { h->err = "kmc_strip_get_records: host buffer too small (" + std::to_string(bytes) + " bytes needed)"; return KMC_ERR_CAPACITY; }
+    if (bytes) CK(cudaMemcpyAsync(host_buf, S.msg[2] + MSG_HDR, (size_t)bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_rec) *n_rec = nr; if (n_lig) *n_lig = nl;
+    return KMC_OK;
+}
+extern "C" int kmc_strip_load_records(kmc_handle *h, const void *host_buf, int64_t n_rec, int64_t n_lig, int64_t step_done) {
+    if (!h || !h->strip_on || !host_buf || n_rec < 0 || n_lig < 0) { if (h) h->err = "kmc_strip_load_records: bad argument"; return KMC_ERR_INVALID; }
+    CK(cudaSetDevice(h->P.device));
+    int rc = strip_dev_alloc(h); if (rc) return rc;
+    if (n_rec > h->NAt || n_lig > h->NBt) { h->err = "kmc_strip_load_records: more molecules than the handle's capacity"; return KMC_ERR_CAPACITY; }
+    StripDev &S = *h->strip_dev; cudaStream_t st = h->stream;
+    CK(cudaStreamSynchronize(st));
+    memset(S.hostI, 0, MSG_HDR); S.hostI[0] = (int)n_rec; S.hostI[1] = (int)n_lig;
+    unsigned long long *s64 = reinterpret_cast<unsigned long long *>(S.hostI + 24); *s64 = (unsigned long long)step_done;
+    CK(cudaMemcpyAsync(S.msg[2], S.hostI, MSG_HDR, cudaMemcpyHostToDevice, st));
+    const size_t bytes = (size_t)n_rec * sizeof(RecMsg) + (size_t)n_lig * sizeof(LigMsg);
+    if (bytes) CK(cudaMemcpyAsync(S.msg[2] + MSG_HDR, host_buf, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(S.rcv[0], 0, MSG_HDR, st)); CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, st));
+    CK(cudaMemcpyAsync(h->D.step64, s64, sizeof *s64, cudaMemcpyHostToDevice, st));
+    rc = strip_merge(h); if (rc) return rc;
+    S.fresh = false;                          // by-products describe nothing yet
+    h->step_done = step_done; h->strip_refreshes--;
+    CK(cudaStreamSynchronize(st));
+    return KMC_OK;
+}

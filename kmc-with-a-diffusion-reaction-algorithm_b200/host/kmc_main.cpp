@@ -1,6 +1,8 @@
 // host/kmc_main.cpp -- the reference's program shape on top of the C ABI: same parameter set (shipped defaults of
-// main.cpp:39-99, overridable on the command line since the reference needs a recompile for that), same outputs
-// (bond.dat, cluster.log every `output_every` steps, main.cpp:2247-2253 / 2291-2305) written into the working directory.
+// main.cpp:39-99, overridable on the command line since the reference needs a recompile for that), same start / restart
+// behaviour (main.cpp:226-278: continue from position.cpt if there is one, else a fresh random start that truncates the
+// output files), same outputs (parameter.log, and bond.dat, cluster.log, test.gro, position.cpt every `output_every` steps,
+// main.cpp:179-205, 2206-2305) written into the working directory.
 //
 //   kmc_main [--steps N] [--output-every M] [--seed S] [--receptors NA --ligands NB --box LX LY LZ] [--replicas R]
 //            [--set name=value ...]     names: dt DA DrotA DB DrotB on off cis_on cis_off mono_cis_on mono_cis_off ...
@@ -42,10 +44,24 @@ int main(int argc, char **argv) {
     }
     kmc_handle *h = nullptr;
     if (kmc_create(&P, &h)) { fprintf(stderr, "kmc_create: %s\n", kmc_last_error(nullptr)); return 1; }
-    if (kmc_init_random(h, init_seed, P.n_receptor + P.n_ligand > 20000)) { fprintf(stderr, "%s\n", kmc_last_error(h)); return 1; }
-    remove("bond.dat"); remove("cluster.log");                      // fresh start truncates, main.cpp:275-277
-    if (kmc_run(h, steps, every, ".")) { fprintf(stderr, "%s\n", kmc_last_error(h)); return 1; }
+    kmc_parameter_log_write(&P, "parameter.log");                    // main.cpp:169, 179-205 (truncated at every start, Q17)
+    // main.cpp:226-278: a position.cpt in the working directory means restart (outputs are appended), none means a fresh start
+    // (outputs truncated). An EMPTY position.cpt -- what a reference run killed before its first output leaves behind, Q21 --
+    // is treated as none instead of being read as zeros.
+    bool restart = false;
+    if (FILE *f = fopen("position.cpt", "r")) { restart = fgetc(f) != EOF; fclose(f); }
+    if (restart && P.n_replicas == 1) {
+        if (kmc_read_checkpoint(h, 0, "position.cpt")) { fprintf(stderr, "%s\n", kmc_last_error(h)); return 1; }
+        printf("CPT file exist\n");                                   // main.cpp:229
+    } else {
+        if (kmc_init_random(h, init_seed, P.n_receptor + P.n_ligand > 20000)) { fprintf(stderr, "%s\n", kmc_last_error(h)); return 1; }
+        remove("bond.dat"); remove("cluster.log"); remove("test.gro"); remove("position.cpt");      // main.cpp:275-278
+        printf("CPT file not exist\n");                               // main.cpp:274
+    }
     kmc_series s; kmc_get_series(h, 0, &s);
+    const long left = steps - (long)s.step;                           // the loop runs to simu_step in total (main.cpp:461)
+    if (left > 0 && kmc_run(h, left, every, ".")) { fprintf(stderr, "%s\n", kmc_last_error(h)); return 1; }
+    kmc_get_series(h, 0, &s);
     printf("step %lld  R-L %d  mono-cis %d  cis %d  bonds %d  mean complex %.3f  max complex %d\n", (long long)s.step, s.bond_num_rl,
            s.bond_num_mono_cis, s.bond_num_cis, s.bond_num, s.cluster_size, s.max_complex);
     kmc_destroy(h);

@@ -39,8 +39,9 @@ EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
-           "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_begin_refresh_dev", "kmc_strip_message_dev",
-           "kmc_strip_recv_dev", "kmc_strip_rebuild_dev", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
+           "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_halo_width", "kmc_strip_unique_id",
+           "kmc_strip_comm_init", "kmc_strip_refresh", "kmc_strip_refresh_local", "kmc_strip_get_series", "kmc_strip_get_oligomer_hist",
+           "kmc_strip_get_records", "kmc_strip_load_records", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
            "kmc_checkpoint_read_arrays", "kmc_parameter_log_write", "kmc_write_gro", "kmc_write_checkpoint", "kmc_read_checkpoint",
            "kmc_write_checkpoint_bin", "kmc_read_checkpoint_bin"]
 
@@ -93,10 +94,16 @@ def lib():
         L.kmc_strip_message.restype = i64
         L.kmc_strip_message.argtypes = [vp, i32, C.POINTER(vp)]
         L.kmc_strip_rebuild.argtypes = [vp, vp, i64, vp, i64]
-        L.kmc_strip_begin_refresh_dev.argtypes = [vp]
-        L.kmc_strip_message_dev.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
-        L.kmc_strip_recv_dev.argtypes = [vp, i32, i64, i64, C.POINTER(vp)]
-        L.kmc_strip_rebuild_dev.argtypes = [vp, i64, i64, i64, i64]
+        L.kmc_strip_halo_width.restype = C.c_double
+        L.kmc_strip_halo_width.argtypes = [C.POINTER(Params), i32, C.c_double]
+        L.kmc_strip_unique_id.argtypes = [vp]
+        L.kmc_strip_comm_init.argtypes = [vp, vp, i32]
+        L.kmc_strip_refresh.argtypes = [vp]
+        L.kmc_strip_refresh_local.argtypes = [C.POINTER(vp), i32, i32]
+        L.kmc_strip_get_series.argtypes = [vp, i32, C.POINTER(Series)]
+        L.kmc_strip_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
+        L.kmc_strip_get_records.argtypes = [vp, i32, vp, i64, C.POINTER(i64), C.POINTER(i64)]
+        L.kmc_strip_load_records.argtypes = [vp, vp, i64, i64, i64]
         L.kmc_gro_append_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, C.c_double, i64, vp]
         L.kmc_checkpoint_write_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp]
         L.kmc_checkpoint_read_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -140,6 +147,27 @@ def generate_packed(params, seed=1, sort_cells=True):
     if rc != 0:
         raise KmcError("kmc_generate_packed failed (%d): box too dense?" % rc)
     return rec, lig
+
+
+def strip_unique_id():
+    """128 bytes identifying a new NCCL communicator (rank 0 calls it and hands the bytes to the other ranks)"""
+    buf = C.create_string_buffer(128)
+    rc = lib().kmc_strip_unique_id(buf)
+    if rc != 0:
+        raise KmcError("kmc_strip_unique_id failed (%d): %s" % (rc, lib().kmc_last_error(None).decode()))
+    return buf.raw
+
+
+def strip_halo_width(params, refresh_every, complex_extent=400.0):
+    return lib().kmc_strip_halo_width(C.byref(params), refresh_every, complex_extent)
+
+
+def strip_refresh_local(handles, refresh_every=0):
+    """one refresh between K handles of this process (logical ranks 0..K-1 on one GPU)"""
+    arr = (C.c_void_p * len(handles))(*[k.h for k in handles])
+    rc = lib().kmc_strip_refresh_local(arr, len(handles), refresh_every)
+    if rc < 0:
+        raise KmcError("kmc_strip_refresh_local failed (%d): %s" % (rc, "; ".join(lib().kmc_last_error(k.h).decode() for k in handles)))
 
 
 def scaled_box(n_total, z=1000.0):
@@ -346,22 +374,32 @@ class Kmc:
     def strip_rebuild(self, from_low, from_high):
         self._ck(lib().kmc_strip_rebuild(self.h, from_low, len(from_low), from_high, len(from_high)))
 
-    def strip_begin_refresh_dev(self):
-        self._ck(lib().kmc_strip_begin_refresh_dev(self.h))
+    def strip_comm_init(self, id128, refresh_every):
+        """collective: NCCL communicator over the configured ranks; refresh_every > 0 = kmc_step refreshes the halos itself"""
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._ck(lib().kmc_strip_comm_init(self.h, buf, refresh_every))
 
-    def strip_message_dev(self, side):
-        """(device pointer, n_rec, n_lig) of message `side` after strip_begin_refresh_dev"""
-        ptr, nr, nl = C.c_void_p(), C.c_int64(), C.c_int64()
-        self._ck(lib().kmc_strip_message_dev(self.h, side, C.byref(ptr), C.byref(nr), C.byref(nl)))
-        return ptr.value, nr.value, nl.value
+    def strip_refresh(self):
+        self._ck(lib().kmc_strip_refresh(self.h))
 
-    def strip_recv_dev(self, side, n_rec, n_lig):
-        ptr = C.c_void_p()
-        self._ck(lib().kmc_strip_recv_dev(self.h, side, n_rec, n_lig, C.byref(ptr)))
-        return ptr.value
+    def strip_series(self, reduce=True):
+        s = Series()
+        self._ck(lib().kmc_strip_get_series(self.h, int(reduce), C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Series._fields_ if k != "reserved"}
 
-    def strip_rebuild_dev(self, rec_low, lig_low, rec_high, lig_high):
-        self._ck(lib().kmc_strip_rebuild_dev(self.h, rec_low, lig_low, rec_high, lig_high))
+    def strip_oligomer_hist(self, reduce=True, nbins=64):
+        hist = np.zeros(nbins, dtype=np.int64)
+        self._ck(lib().kmc_strip_get_oligomer_hist(self.h, int(reduce), hist.ctypes.data, nbins))
+        return hist
+
+    def strip_get_records(self, which, out):
+        """which 2 = owned units, 3 = everything local; out = uint8 host array (pinned recommended) -> (n_rec, n_lig)"""
+        nr, nl = C.c_int64(), C.c_int64()
+        self._ck(lib().kmc_strip_get_records(self.h, which, out.ctypes.data, out.nbytes, C.byref(nr), C.byref(nl)))
+        return nr.value, nl.value
+
+    def strip_load_records(self, buf, n_rec, n_lig, step_done=0):
+        self._ck(lib().kmc_strip_load_records(self.h, buf.ctypes.data, n_rec, n_lig, step_done))
 
     def grid(self):
         x0, y0, edge, ncx, ncy = C.c_double(), C.c_double(), C.c_double(), C.c_int32(), C.c_int32()

@@ -1,9 +1,11 @@
-"""Strip decomposition driver: one membrane across several GPUs (one kmc handle per rank, csrc/kmc_strips.cu).
+"""Strip decomposition: thin callers of the C ABI (one kmc handle per rank, csrc/kmc_strips.cu).
 
-StripRank wraps one rank's handle; the exchange of the boundary bands is done here, either between handles living in one
-process (LocalStrips: K logical ranks on one GPU, used to prove equality with the single-GPU run) or between processes with
-torch.distributed point-to-point operations (DistStrips: NCCL send/recv over NVLink when the backend is nccl; gloo on CPU for
-the message plumbing tests)."""
+The refresh itself -- classify, pack, NCCL send/recv with the two x-neighbours, merge -- lives in the library
+(kmc_strip_refresh, on the handle's stream, no host synchronisation; kmc_step calls it every refresh_every steps once
+kmc_strip_comm_init has run). What is left here: DistStrips hands the NCCL unique id from rank 0 to the other ranks through
+torch.distributed (any transport would do) and LocalStrips drives K logical ranks inside one process (one GPU: how the tests
+prove equality with the single-GPU run). The host-path refresh (strip_begin_refresh / strip_message / strip_rebuild and the
+ring_exchange of byte strings below) is the slow reference implementation the device path is tested against."""
 import numpy as np
 
 from . import Kmc
@@ -17,20 +19,13 @@ assert REC_DT.itemsize == 64 and LIG_DT.itemsize == 208
 D1 = 200.0
 
 
-def halo_for(refresh_every, complex_extent=400.0):
-    """halo width that keeps the owned strip exact for `refresh_every` steps between refreshes"""
+def halo_for(refresh_every, complex_extent=400.0, params=None):
+    """halo width that keeps the owned strip exact for `refresh_every` steps between refreshes (kmc_strip_halo_width when the
+    parameters are given; the constant D1 covers the default radii)"""
+    if params is not None:
+        from . import strip_halo_width
+        return strip_halo_width(params, refresh_every, complex_extent)
     return refresh_every * D1 + complex_extent
-
-
-class _DevBuf:
-    """a raw device allocation of the library seen as a torch uint8 tensor (zero copy, __cuda_array_interface__)"""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
-
-
-def dev_tensor(torch, ptr, nbytes, device):
-    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)[:nbytes]
 
 
 def msg_bytes(n_rec, n_lig):
@@ -103,8 +98,8 @@ class LocalStrips:
     """K logical ranks in one process (all on one GPU): the in-process stand-in for the NCCL exchange.
     device_refresh=True keeps the refresh on the GPU (device-to-device copies instead of NCCL)."""
 
-    def __init__(self, make_params, nranks, refresh_every, halo_width=None, device_refresh=False):
-        self.n, self.every, self.device_refresh = nranks, refresh_every, device_refresh
+    def __init__(self, make_params, nranks, refresh_every, halo_width=None, device_refresh=False, guard=False):
+        self.n, self.every, self.device_refresh, self.guard = nranks, refresh_every, device_refresh, guard
         self.halo = halo_width if halo_width is not None else halo_for(refresh_every)
         self.ranks = [StripRank(make_params(r), r, nranks, self.halo) for r in range(nranks)]
         self.since = 0
@@ -127,23 +122,22 @@ class LocalStrips:
         self.since = 0
 
     def _refresh_dev(self):
-        import torch
-        dev = "cuda:%d" % self.ranks[0].k.p.device
-        for r in self.ranks:
-            r.k.strip_begin_refresh_dev()
-        low = [r.k.strip_message_dev(0) for r in self.ranks]; high = [r.k.strip_message_dev(1) for r in self.ranks]
-        for i, r in enumerate(self.ranks):
-            if self.n == 1:
-                r.k.strip_rebuild_dev(0, 0, 0, 0); continue
-            src = (high[(i - 1) % self.n], low[(i + 1) % self.n])          # (from lower-x neighbour, from higher-x neighbour)
-            for side, (ptr, nr, nl) in enumerate(src):
-                dst = r.k.strip_recv_dev(side, nr, nl)
-                nb = msg_bytes(nr, nl)
-                if nb:
-                    dev_tensor(torch, dst, nb, dev).copy_(dev_tensor(torch, ptr, nb, dev))
-            torch.cuda.synchronize()
-            r.k.strip_rebuild_dev(src[0][1], src[0][2], src[1][1], src[1][2])
+        from . import strip_refresh_local
+        strip_refresh_local([r.k for r in self.ranks], self.every if self.guard else 0)
         self.since = 0
+
+    def series(self):
+        """bond.dat row of the whole membrane: the ranks' owned-only parts added up (values of the last refresh)"""
+        parts = [r.k.strip_series(reduce=False) for r in self.ranks]
+        out = dict(parts[0])
+        for k in ("bond_num_rl", "bond_num_mono_cis", "bond_num_cis", "bond_num", "n_complexes", "n_in_complexes"):
+            out[k] = sum(p[k] for p in parts)
+        out["max_complex"] = max(p["max_complex"] for p in parts)
+        out["cluster_size"] = out["n_in_complexes"] / out["n_complexes"] if out["n_complexes"] else 0.0
+        return out
+
+    def oligomer_hist(self, nbins=64):
+        return sum(r.k.strip_oligomer_hist(reduce=False, nbins=nbins) for r in self.ranks)
 
     def step(self, n):
         while n > 0:
@@ -161,7 +155,8 @@ class LocalStrips:
 
 
 class DistStrips:
-    """one rank per process; boundary bands travel with torch.distributed send/recv (NCCL over NVLink with backend nccl)"""
+    """one rank per process. Backend nccl: the library's own refresh (C++ + NCCL on the handle's stream, kmc_step refreshes by
+    itself). Any other backend (gloo, CPU plumbing tests): the host-path refresh with the byte strings sent through torch."""
 
     def __init__(self, params, refresh_every, halo_width=None, dist=None, device=None, device_refresh=None):
         import torch
@@ -175,6 +170,11 @@ class DistStrips:
         self.k = self.sr.k
         self.since = 0
         self.bytes_sent = 0
+        if self.device_refresh:
+            from . import strip_unique_id
+            box = [strip_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.k.strip_comm_init(box[0], refresh_every)
 
     def load_global(self, *a, **kw):
         self.sr.load_global(*a, **kw)
@@ -184,48 +184,10 @@ class DistStrips:
         self.bytes_sent += len(to_low) + len(to_high)
         return out
 
-    def _refresh_dev(self):
-        """device messages, NCCL point-to-point GPU to GPU; same pairing rules as ring_exchange"""
-        torch, dist, dev = self.torch, self.dist, self.device
-        k = self.k
-        import os, time
-        timing = os.environ.get("KMC_STRIP_TIMING")
-        if timing:
-            k.sync(); t0 = time.perf_counter()
-        k.strip_begin_refresh_dev()
-        if timing:
-            t1 = time.perf_counter()
-        if self.n == 1:
-            k.strip_rebuild_dev(0, 0, 0, 0); self.since = 0; return
-        lo, hi = (self.rank - 1) % self.n, (self.rank + 1) % self.n
-        (pl, rl_, ll_), (ph, rh_, lh_) = k.strip_message_dev(0), k.strip_message_dev(1)
-
-        def run(ops):
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        counts = torch.tensor([rl_, ll_, rh_, lh_], dtype=torch.int64, device=dev)
-        c_hi = torch.zeros(4, dtype=torch.int64, device=dev); c_lo = torch.zeros(4, dtype=torch.int64, device=dev)
-        run([dist.P2POp(dist.isend, counts, lo), dist.P2POp(dist.isend, counts.clone(), hi), dist.P2POp(dist.irecv, c_hi, hi), dist.P2POp(dist.irecv, c_lo, lo)])
-        c_hi, c_lo = c_hi.tolist(), c_lo.tolist()
-        fl = (c_lo[2], c_lo[3])          # from the lower neighbour: its message towards higher x
-        fh = (c_hi[0], c_hi[1])          # from the higher neighbour: its message towards lower x
-        t_send_lo = dev_tensor(torch, pl, max(msg_bytes(rl_, ll_), 1), dev); t_send_hi = dev_tensor(torch, ph, max(msg_bytes(rh_, lh_), 1), dev)
-        t_recv_hi = dev_tensor(torch, k.strip_recv_dev(1, *fh), max(msg_bytes(*fh), 1), dev); t_recv_lo = dev_tensor(torch, k.strip_recv_dev(0, *fl), max(msg_bytes(*fl), 1), dev)
-        run([dist.P2POp(dist.isend, t_send_lo, lo), dist.P2POp(dist.isend, t_send_hi, hi), dist.P2POp(dist.irecv, t_recv_hi, hi), dist.P2POp(dist.irecv, t_recv_lo, lo)])
-        torch.cuda.synchronize()
-        if timing:
-            t2 = time.perf_counter()
-        self.bytes_sent += msg_bytes(rl_, ll_) + msg_bytes(rh_, lh_)
-        k.strip_rebuild_dev(fl[0], fl[1], fh[0], fh[1])
-        if timing:
-            t3 = time.perf_counter()
-            self.timing = getattr(self, "timing", [0.0, 0.0, 0.0, 0])
-            self.timing[0] += t1 - t0; self.timing[1] += t2 - t1; self.timing[2] += t3 - t2; self.timing[3] += 1
-        self.since = 0
-
     def refresh(self):
         if self.device_refresh:
-            return self._refresh_dev()
+            self.k.strip_refresh(); self.since = 0
+            return
         self.k.strip_begin_refresh()
         if self.n == 1:
             self.k.strip_rebuild(b"", b"")
@@ -235,6 +197,9 @@ class DistStrips:
         self.since = 0
 
     def step(self, n):
+        if self.device_refresh:             # the library refreshes every `every` steps on its own
+            self.k.step(n)
+            return
         while n > 0:
             m = min(n, self.every - self.since)
             self.k.step(m)
@@ -242,10 +207,65 @@ class DistStrips:
             if self.since == self.every:
                 self.refresh()
 
+    def series(self):
+        return self.k.strip_series(reduce=True)
+
+    def oligomer_hist(self, nbins=64):
+        return self.k.strip_oligomer_hist(reduce=True, nbins=nbins)
+
     def gather(self, n_rec, n_lig):
-        """global state on every rank (all_gather of the owned sets)"""
+        """global state on every rank (all_gather of the owned sets; host path, for checks)"""
         self.k.strip_begin_refresh()
         mine = self.k.strip_message(2)
         out = [None] * self.n
         self.dist.all_gather_object(out, mine)
         return assemble_global(out, n_rec, n_lig)
+
+
+def nccl_check(dist, local, molecules=100000, steps=64, every=8, regime_scale=20.0, seed=5):
+    """ONE membrane on the live NCCL ranks == the same membrane on one GPU, bit for bit (collective; returns a dict on every rank).
+    Hot, dense regime (on-rates x20, fast dissociation, 6.6x the default density) so that bonds form and break, complexes
+    straddle boundaries and units migrate within the window. Every rank runs the single-GPU trajectory itself and compares the
+    records of the units it owns after the strip run with it; the bond.dat row of the whole membrane (kmc_strip_get_series,
+    all-reduced in the library) must equal the single-GPU row, the oligomer histogram likewise."""
+    import torch
+    from . import Kmc, default_params, strip_halo_width
+    na, nb = (3 * molecules) // 4, molecules - (3 * molecules) // 4
+    L = 26000.0 * (molecules / 20000.0) ** 0.5
+    box = (L, L, 400.0)
+
+    def mk():
+        p = default_params(box=box, n_receptor=na, n_ligand=nb, seed=seed, device=local)
+        p.cis_on *= regime_scale; p.mono_cis_on *= regime_scale
+        p.off, p.cis_off, p.mono_cis_off = 2e-5, 2e-5, 1e-4
+        return p
+    k = Kmc(mk()); k.init_random(seed=17, sort_cells=True)
+    start = k.get_packed()
+    k.step(steps)
+    end = k.get_packed(); want = k.series(); want_hist = k.oligomer_hist(); k.close()
+    halo = strip_halo_width(mk(), every, 400.0)
+    ds = DistStrips(mk(), every, halo_width=halo, dist=dist)
+    ds.load_global(*start)
+    ds.step(steps)
+    buf = np.zeros(64 * na + 208 * nb, dtype=np.uint8)
+    nr, nl = ds.k.strip_get_records(2, buf)
+    rec = np.frombuffer(buf, dtype=REC_DT, count=nr); lig = np.frombuffer(buf, dtype=LIG_DT, count=nl, offset=64 * nr)
+    a, b = rec["ref"] - 1, lig["ref"] - na - 1
+    ok = bool(np.array_equal(rec["pose"], end[0][a]) and np.array_equal(lig["pose"], end[1][b]) and
+              np.array_equal(np.where(rec["ligRef"] > 0, rec["ligRef"] - na - 1, -1), end[2][a]) and
+              np.array_equal(np.where(rec["ligRef"] > 0, rec["site"] + 2, 0), end[3][a]) and
+              np.array_equal(np.where(rec["cisRef"] > 0, rec["cisRef"] - 1, -1), end[4][a]))
+    got = ds.series(); got_hist = ds.oligomer_hist()
+    keys = ("bond_num", "bond_num_rl", "bond_num_cis", "bond_num_mono_cis", "max_complex", "n_complexes", "n_in_complexes", "cluster_size")
+    series_ok = all(got[q] == want[q] for q in keys) and bool(np.array_equal(got_hist, want_hist))
+    ds.k.sync()
+    t = torch.tensor([1 if ok else 0, 1 if series_ok else 0, nr + nl, -(nr + nl)], dtype=torch.int64, device="cuda:%d" % local)
+    tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    refreshes = steps // every
+    ds.k.close()
+    return {"equal_single_gpu": bool(tmin[0].item() == 1 and tsum[2].item() == na + nb), "series_equal": bool(tmin[1].item() == 1),
+            "ranks": dist.get_world_size(), "molecules": molecules, "steps": steps, "refreshes": refreshes, "refresh_every": every, "halo": halo,
+            "bonds": want["bond_num"], "complexes": want["n_complexes"], "max_complex": want["max_complex"],
+            "owned_min": int(-tmin[3].item()), "owned_total": int(tsum[2].item()), "backend": dist.get_backend(),
+            "exchange": "kmc_strip_refresh: C++ ncclSend/ncclRecv on the handle's stream"}

@@ -30,6 +30,27 @@ def load_golden_state(path):
                 params=json.loads(str(z["params"])))
 
 
+def strict_errors(ref, got):
+    """(max |x_ref - x| in Angstrom, max |x_ref - x| / |x_ref| over coordinates with |x_ref| > 1e-6 A): the strict figures next to the
+    floored one that compare_states asserts"""
+    Rr, Rg = ref[0], got[0]
+    d = np.abs(Rr - Rg)
+    big = np.abs(Rr) > 1e-6
+    return float(d.max()), float((d[big] / np.abs(Rr[big])).max()) if big.any() else 0.0
+
+
+def log_errors(label, floored, ref, got):
+    """one line per comparison into gpurun_out/position_errors.jsonl (brought back from the GPU box; summarised under profiles/)"""
+    a, r = strict_errors(ref, got)
+    line = json.dumps({"test": label, "rel_floored_100A": floored, "abs_A": a, "rel_strict": r})
+    print("position error", line)
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "position_errors.jsonl"), "a") as f:
+            f.write(line + "\n")
+    return a, r
+
+
 def compare_states(ref, got, label=""):
     """ref/got = (R, status, res_nei). Bond table must be identical; positions within POS_RTOL relative
     (relative to max(|x_ref|, POS_FLOOR)). Returns max relative position error."""

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 import kmc_b200
 import pyoracle
-from common import apply_regime, compare_states, load_golden_state
+from common import apply_regime, compare_states, load_golden_state, log_errors
 
 
 def make_pair(na, nb, box, regime, seed, grid=1, **kw):
@@ -38,6 +38,9 @@ def lockstep(o, k, nsteps, check_every, label, per_step_accept=False):
         assert c["tot_cluster_num"] == s["n_complexes"] and c["tot_proteins_in_cluster"] == s["n_in_complexes"]
         assert c["cluster_size"] == s["cluster_size"]
         assert o.results() == k.complexes(), "%s: complex member lists differ at step %d" % (label, done)
+    # strict figures (absolute in Angstrom, relative to |x| itself) next to the floored one the assertion uses; absolute error bounded too
+    a, r = log_errors(label, worst, o.get_state(), k.get_state())
+    assert a <= 1e-9, "%s: absolute position error %.3e A" % (label, a)
     return worst
 
 
@@ -62,6 +65,21 @@ def test_from_reference_state_with_complexes(golden_dir, name, regime):
     lockstep(o, k, 1300, 100, name)
     ev_o, ev_k = o.events(), k.events()
     assert (ev_k["rl_on"], ev_k["mono_cis_on"], ev_k["cis_on"], ev_k["rl_off"], ev_k["mono_cis_off"], ev_k["cis_off"]) == tuple(int(x) for x in ev_o[:6])
+
+
+def test_laydown_and_goto_back_edge_fire_inside_the_window(golden_dir):
+    """S2e lay-down (main.cpp:1141-1189) and the `goto lable4` back edge of the multi-ligand alignment (main.cpp:1628 -> 1438) are
+    rare events; this start state (tests/golden/make_goto_state.py) sits right before both. The oracle's own counters must advance
+    inside the per-step lockstep window, so the GPU's S2e/S2f code is known to have executed them, decisions and member order equal."""
+    g = load_golden_state(os.path.join(golden_dir, "hot200_step180900_goto.npz"))
+    o, k = make_pair(150, 50, tuple(g["params"]["box"]), "hot", seed=g["params"]["keyed_seed"])
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    ev0 = o.events().copy()
+    lockstep(o, k, 600, 1, "goto-window", per_step_accept=True)
+    ev1 = o.events()
+    assert ev1[8] - ev0[8] >= 1, "no lay-down inside the window"
+    assert ev1[9] - ev0[9] >= 2, "goto lable4 not taken inside the window"
 
 
 def test_hot_from_scratch_long():
@@ -101,17 +119,21 @@ def test_replicas_are_independent_systems():
         assert o.results() == k.complexes(r)
 
 
-def test_config2_1e5_molecules_replay():
-    """configs[1]: 1e5-molecule membrane (75 000 receptors + 25 000 ligands, default density), replay check vs the oracle."""
+@pytest.mark.parametrize("regime,steps,every", [("default", 1000, 250), ("hot", 200, 50)])
+def test_config2_1e5_molecules_replay(regime, steps, every):
+    """configs[1]: 1e5-molecule membrane (75 000 receptors + 25 000 ligands, default density), replay check vs the oracle:
+    10^3 steps with the paper's parameters, 200 steps of the hot variant (association, dissociation, complexes fire)."""
     na, nb = 75000, 25000
     box = kmc_b200.scaled_box(na + nb)
-    for regime, steps in (("default", 40), ("hot", 40)):
-        o, k = make_pair(na, nb, box, regime, seed=1)
-        k.init_random(seed=1, sort_cells=True)
-        o.set_state(*k.get_state())
-        lockstep(o, k, steps, 20, "1e5-" + regime)
-        assert np.array_equal(o.accepted()[1:], k.accepted()[1:])
-        k.close()
+    o, k = make_pair(na, nb, box, regime, seed=1)
+    k.init_random(seed=1, sort_cells=True)
+    o.set_state(*k.get_state())
+    lockstep(o, k, steps, every, "1e5-" + regime)
+    assert np.array_equal(o.accepted()[1:], k.accepted()[1:])
+    ev_o, ev_k = o.events(), k.events()
+    assert (ev_k["rl_on"], ev_k["mono_cis_on"], ev_k["cis_on"], ev_k["rl_off"], ev_k["mono_cis_off"], ev_k["cis_off"]) == tuple(int(x) for x in ev_o[:6])
+    assert ev_k["rl_on"] > 0 and ev_k["reverted"] == int(ev_o[6])
+    k.close()
 
 
 def test_crowded_tiles_generic_path():
