@@ -147,6 +147,8 @@ int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
  * list, [13] special entries (far movers / drifted molecules of a list-reuse step), [14] pending findings, [15] pre-selected
  * reaction pairs */
 int kmc_get_events(kmc_handle *h, int64_t *ev);
+/* molecules currently held by the handle (all of n_receptor / n_ligand x replicas unless strips made them capacities) */
+int kmc_get_live_counts(kmc_handle *h, int32_t *n_rec, int32_t *n_lig);
 
 /* Pure host formatting of the reference's records (no device needed): one bond.dat line (main.cpp:2249-2251) and one
  * cluster.log frame (main.cpp:2293-2301). Return the number of characters written (excluding the NUL) or a negative status. */
@@ -197,6 +199,10 @@ int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_low, const 
  * the merge kernels are all enqueued on the handle's stream. Guards (reported by kmc_sync / kmc_step as KMC_ERR_CAPACITY): a unit
  * wider in x than halo_width - refresh_every * (reach per step), a band or the local capacity too small, a unit that arrives
  * incomplete. */
+/* start state of a strip run generated on the GPU: every rank generates the same global configuration of n_rec + n_lig molecules (the
+ * generator of kmc_init_random, a few ms for 1e7 molecules) and keeps what lies within reach of its strip; reference ids are the
+ * global indices (receptor a -> a + 1, ligand b -> n_rec + b + 1) */
+int kmc_strip_init_random(kmc_handle *h, int32_t n_rec, int32_t n_lig, uint64_t seed, int32_t sort_cells);
 /* halo width that keeps the owned strip exact for refresh_every steps: refresh_every * (reach of information per step) + complex_extent */
 double kmc_strip_halo_width(const kmc_params *p, int32_t refresh_every, double complex_extent);
 /* NCCL communicator over the ranks of kmc_strip_configure: rank 0 fills id128 (128 bytes) with kmc_strip_unique_id, the caller

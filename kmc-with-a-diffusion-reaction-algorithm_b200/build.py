@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.environ.get("KMC_LIB_OUT") or os.path.join(HERE, "libkmc_b200.so")
 SRC = [os.path.join(HERE, "csrc", "kmc_engine.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("kmc_engine.cu", "kmc_kernels.cu", "kmc_device.cuh", "kmc_geom.cuh", "kmc_philox.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("kmc_engine.cu", "kmc_kernels.cu", "kmc_strips.cu", "kmc_init.cu", "kmc_device.cuh", "kmc_geom.cuh", "kmc_philox.cuh")] + \
        [os.path.join(HERE, "..", "include", "kmc_b200.h")]
 
 

@@ -59,6 +59,7 @@ struct kmc_handle {
     HostLocal strip_local; std::vector<char> strip_msg[3];
     struct StripDev *strip_dev = nullptr;
     int64_t launches = 0, passes = 0;
+    int init_rounds = 0;             // rounds the GPU generator needed (diagnostics)
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
@@ -832,6 +833,16 @@ extern "C" int kmc_get_accept(kmc_handle *h, int32_t rep, int32_t *accepted) {
     return KMC_OK;
 }
 
+extern "C" int kmc_get_live_counts(kmc_handle *h, int32_t *n_rec, int32_t *n_lig) {
+    if (!h) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaStreamSynchronize(h->stream));
+    int live[2];
+    CK(cudaMemcpy(live, h->D.scal + S_NA_LIVE, sizeof live, cudaMemcpyDeviceToHost));
+    if (n_rec) *n_rec = live[0]; if (n_lig) *n_lig = live[1];
+    return KMC_OK;
+}
+
 extern "C" int kmc_get_events(kmc_handle *h, int64_t *ev) {
     if (!h || !ev) return KMC_ERR_INVALID;
     CK(cudaSetDevice(h->P.device));
@@ -1009,14 +1020,28 @@ static const char *generate_random(const kmc_params &P, const Consts &K, uint64_
     return nullptr;
 }
 
+#include "kmc_init.cu"
+
+// the configuration is generated ON THE DEVICE (csrc/kmc_init.cu: the reference's sequential insertion as a parallel fixed point)
+// straight into the handle's arrays; nothing crosses PCIe
 extern "C" int kmc_init_random(kmc_handle *h, uint64_t init_seed, int32_t sort_cells) {
     if (!h) return KMC_ERR_INVALID;
-    std::vector<double> rec((size_t)h->NAt * 6), lig((size_t)h->NBt * 24);
-    if (const char *msg = generate_random(h->P, h->K, init_seed, sort_cells, rec.data(), lig.data())) { h->err = msg; return KMC_ERR_INVALID; }
-    int rc = kmc_set_packed(h, rec.data(), lig.data(), nullptr, nullptr, nullptr, 0);
-    if (rc) return rc;
-    std::vector<int> zero(h->R, 0);
-    CK(cudaMemcpy(h->D.maxComplex, zero.data(), sizeof(int) * h->R, cudaMemcpyHostToDevice));
+    int rc = select_device(h); if (rc) return rc;
+    rc = stage_alloc(h); if (rc) return rc;
+    Dev &D = h->D; cudaStream_t st = h->stream;
+    CK(cudaStreamSynchronize(st));
+    if (const char *msg = generate_random_device(h->P, h->NA, h->NB, h->R, init_seed, sort_cells, h->stageRec, D.lig, st, &h->init_rounds)) { h->err = msg; return KMC_ERR_INVALID; }
+    int *dflag = h->stageInt + 3 * (size_t)h->NAt;
+    CK(cudaMemsetAsync(D.ligRec, 0xff, sizeof(int) * 3 * (size_t)h->NBt, st));
+    CK(cudaMemsetAsync(dflag, 0, sizeof(int), st));
+    const Args A{D, h->K};
+    LAUNCH(KID_SERIES, (k_pack_set<<<nblk(std::max(h->NAt, 1), 256), 256, 0, st>>>(A, h->stageRec, nullptr, nullptr, nullptr, dflag)));
+    CK(cudaMemsetAsync(D.step64, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(D.maxComplex, 0, sizeof(int) * h->R, st));
+    int one = 1;
+    CK(cudaMemcpyAsync(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->step_done = 0; h->stepped = false; h->sinceBuild = 0;
     return KMC_OK;
 }
 

@@ -881,3 +881,83 @@ extern "C" int kmc_strip_load_records(kmc_handle *h, const void *host_buf, int64
     CK(cudaStreamSynchronize(st));
     return KMC_OK;
 }
+
+// ---- start state of a strip run, generated on the GPU: every rank generates the SAME global configuration (n_rec + n_lig
+// molecules in the handle's box, csrc/kmc_init.cu -- a few ms even for 1e7 molecules) in scratch device memory and keeps the
+// molecules within reach of its strip (owned + halo). Nothing crosses PCIe, nothing is exchanged.
+__global__ void k_strip_select_flags(const __grid_constant__ Args A, const double *rec, const double *lig, int nR, int nL, double lo, double hi, double W, int *flagA, int *flagB) {
+    KARGS
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nR) { const double t = hash_x(cK, rec[(size_t)i * 6]); flagA[i] = (t >= lo - W && t < hi + W) ? 1 : 0; }
+    else if (i < nR + nL) { const int b = i - nR; const double t = hash_x(cK, lig[(size_t)b * 24]); flagB[b] = (t >= lo - W && t < hi + W) ? 1 : 0; }
+}
+__global__ void k_strip_select_scatter(const __grid_constant__ Args A, const double *rec, const double *lig, int nR, int nL, double lo, double hi, double W, const int *offA, const int *offB) {
+    KARGS
+    const Consts &K = cK;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nR) {
+        const double *o = rec + (size_t)i * 6;
+        const double t = hash_x(K, o[0]);
+        if (!(t >= lo - W && t < hi + W)) return;
+        const int d = offA[i];
+        if (d >= K.NAt) return;
+        D.recC[d] = make_double2(o[0], o[1]); D.recS2[d] = make_double2(o[2], o[3]); D.recS3[d] = make_double2(o[4], o[5]);
+        D.refA[d] = (unsigned)(i + 1); D.recLig[d] = -1; D.recSite[d] = -1; D.recCis[d] = -1;
+    } else if (i < nR + nL) {
+        const int b = i - nR;
+        const double *o = lig + (size_t)b * 24;
+        const double t = hash_x(K, o[0]);
+        if (!(t >= lo - W && t < hi + W)) return;
+        const int d = offB[b];
+        if (d >= K.NBt) return;
+        double *p = D.lig + (size_t)d * 24;
+        for (int q = 0; q < 24; q++) p[q] = o[q];
+        D.refB[d] = (unsigned)(nR + b + 1);
+        for (int q = 0; q < 3; q++) D.ligRec[d * 3 + q] = -1;
+    }
+}
+extern "C" int kmc_strip_init_random(kmc_handle *h, int32_t n_rec, int32_t n_lig, uint64_t seed, int32_t sort_cells) {
+    if (!h || !h->strip_on || n_rec < 0 || n_lig < 1) { if (h) h->err = "kmc_strip_init_random: configure strips first"; return KMC_ERR_INVALID; }
+    CK(cudaSetDevice(h->P.device));
+    cudaStream_t st = h->stream;
+    CK(cudaStreamSynchronize(st));
+    double *rec = nullptr, *lig = nullptr; int *fl[2] = {nullptr, nullptr}, *off[2] = {nullptr, nullptr}, *tmp = nullptr;
+    const size_t sbA = ((size_t)n_rec + 1 + SCAN_TILE - 1) / SCAN_TILE, sbB = ((size_t)n_lig + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    bool ok = cudaMalloc(&rec, sizeof(double) * 6 * (size_t)std::max(n_rec, 1)) == cudaSuccess && cudaMalloc(&lig, sizeof(double) * 24 * (size_t)n_lig) == cudaSuccess &&
+              cudaMalloc(&fl[0], sizeof(int) * sbA * SCAN_TILE) == cudaSuccess && cudaMalloc(&off[0], sizeof(int) * sbA * SCAN_TILE) == cudaSuccess &&
+              cudaMalloc(&fl[1], sizeof(int) * sbB * SCAN_TILE) == cudaSuccess && cudaMalloc(&off[1], sizeof(int) * sbB * SCAN_TILE) == cudaSuccess &&
+              cudaMalloc(&tmp, sizeof(int) * (std::max(sbA, sbB) + 1)) == cudaSuccess;
+    int rc = KMC_OK, tot[2] = {0, 0};
+    if (!ok) { h->err = "kmc_strip_init_random: scratch allocation failed"; rc = KMC_ERR_CUDA; }
+    if (!rc) if (const char *msg = generate_random_device(h->P, n_rec, n_lig, 1, seed, sort_cells, rec, lig, st, &h->init_rounds)) { h->err = msg; rc = KMC_ERR_INVALID; }
+    if (!rc) {
+        const Args A{h->D, h->K};
+        const int n = n_rec + n_lig;
+        cudaMemsetAsync(fl[0], 0, sizeof(int) * sbA * SCAN_TILE, st); cudaMemsetAsync(fl[1], 0, sizeof(int) * sbB * SCAN_TILE, st);
+        k_strip_select_flags<<<nblk(n, 256), 256, 0, st>>>(A, rec, lig, n_rec, n_lig, h->strip_lo, h->strip_hi, h->strip_W, fl[0], fl[1]);
+        const size_t sb[2] = {sbA, sbB};
+        for (int s = 0; s < 2; s++) {
+            k_scan_reduce<<<(unsigned)sb[s], 256, 0, st>>>((const int4 *)fl[s], tmp);
+            k_scan_sums<<<1, 1024, 0, st>>>(tmp, (int)sb[s]);
+            k_scan_down<<<(unsigned)sb[s], 256, 0, st>>>((int4 *)fl[s], tmp, (int4 *)off[s]);
+        }
+        k_strip_select_scatter<<<nblk(n, 256), 256, 0, st>>>(A, rec, lig, n_rec, n_lig, h->strip_lo, h->strip_hi, h->strip_W, off[0], off[1]);
+        cudaMemcpyAsync(&tot[0], off[0] + n_rec, sizeof(int), cudaMemcpyDeviceToHost, st);        // exclusive prefix at index n = the total
+        cudaMemcpyAsync(&tot[1], off[1] + n_lig, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { h->err = "kmc_strip_init_random: CUDA error"; rc = KMC_ERR_CUDA; }
+    }
+    cudaFree(rec); cudaFree(lig); cudaFree(fl[0]); cudaFree(fl[1]); cudaFree(off[0]); cudaFree(off[1]); cudaFree(tmp);
+    if (rc) return rc;
+    if (tot[0] > h->NAt || tot[1] > h->NBt) {
+        h->err = "strip: local capacity exceeded (" + std::to_string(tot[0]) + "/" + std::to_string(h->NAt) + " receptors, " + std::to_string(tot[1]) + "/" +
+                 std::to_string(h->NBt) + " ligands): create the handle with larger n_receptor/n_ligand"; return KMC_ERR_CAPACITY;
+    }
+    int one = 1;
+    CK(cudaMemcpy(h->D.scal + S_NA_LIVE, tot, sizeof tot, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->D.step64, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(h->D.maxComplex, 0, sizeof(int)));
+    h->step_done = 0; h->stepped = false; h->sinceBuild = 0; h->strip_since = 0;
+    if (h->strip_dev) h->strip_dev->fresh = false;
+    return KMC_OK;
+}

