@@ -55,6 +55,7 @@ struct kmc_handle {
     double *stageRec = nullptr; int *stageInt = nullptr;      // device staging of kmc_set_packed / kmc_get_packed
     // strips
     bool strip_on = false; double strip_W = 0, strip_lo = 0, strip_hi = 0; int64_t strip_refreshes = 0;
+    double strip_t[3] = {0, 0, 0};             // KMC_STRIP_TIMING: accumulated wall-clock of the refresh phases (us)
     int strip_every = 0, strip_since = 0;      // > 0: kmc_step refreshes the halos itself every strip_every steps (kmc_strip_comm_init)
     HostLocal strip_local; std::vector<char> strip_msg[3];
     struct StripDev *strip_dev = nullptr;

@@ -193,9 +193,9 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
 // each thread copies and later reads only its own slot: no barrier, just the pipeline wait). The load latency that every warp
 // used to sit out at its start now overlaps the previous tile's arithmetic.
 struct RecStage { double2 c[REC_TILE], s2[REC_TILE], s3[REC_TILE]; float2 bc[REC_TILE]; int head[REC_TILE], cis[REC_TILE]; };
-KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile) {
+KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile, int nLive) {
     const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
-    if (gid < K.NAt) {
+    if (gid < nLive) {
         __pipeline_memcpy_async(&S.c[t], &D.recC[gid], 16); __pipeline_memcpy_async(&S.s2[t], &D.recS2[gid], 16);
         __pipeline_memcpy_async(&S.s3[t], &D.recS3[gid], 16);
         __pipeline_memcpy_async(&S.head[t], &D.unitOf[gid], 4); __pipeline_memcpy_async(&S.cis[t], &D.recCis[gid], 4);
@@ -210,18 +210,18 @@ KD void propose_rec_body(const Args &A) {
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int nLive = nA_live(D);
-    const int ntiles = (K.NAt + REC_TILE - 1) / REC_TILE;
+    const int ntiles = (nLive + REC_TILE - 1) / REC_TILE;          // (live receptors only: a strip's capacity padding costs nothing)
     int tile = blockIdx.x;
-    if (tile < ntiles) rec_prefetch(K, D, ST[0], tile);
+    if (tile < ntiles) rec_prefetch(K, D, ST[0], tile, nLive);
     __pipeline_commit();
     for (int it = 0; tile < ntiles; it++, tile += gridDim.x) {
         const int next = tile + gridDim.x;
-        if (next < ntiles) rec_prefetch(K, D, ST[(it + 1) & 1], next);
+        if (next < ntiles) rec_prefetch(K, D, ST[(it + 1) & 1], next, nLive);
         __pipeline_commit();
         __pipeline_wait_prior(1);                 // everything but the newest group has landed: this tile's slot is ready
         const RecStage &S = ST[it & 1];
         const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
-        if (gid < K.NAt) {
+        if (gid < nLive) {
             Rec ra; ra.cx = S.c[t].x; ra.cy = S.c[t].y; ra.s2x = S.s2[t].x; ra.s2y = S.s2[t].y; ra.s3x = S.s3[t].x; ra.s3y = S.s3[t].y;
             propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase ? S.bc[t] : make_float2(0.f, 0.f));
         }
@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int h0 = blockIdx.x * LIG_TILE, h = h0 + threadIdx.x, gid = K.NAt + h;
     if (h == 0) D.scal[S_TOPO_DIRTY] = 0;         // the gated rebuild kernels of this step are done; S3 sets it again
-    const int nrows = min(LIG_TILE, K.NBt - h0);          // rows of the tile by CAPACITY: the live count travels with the data
-    if (nrows <= 0) return;
     const int nLive = nB_live(D);
+    const int nrows = min(LIG_TILE, nLive - h0);          // live rows only (the capacity padding of a strip costs nothing)
+    if (nrows <= 0) return;
     {
         const double2 *src = reinterpret_cast<const double2 *>(D.lig) + (size_t)h0 * 12;
         for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; tile[r][i - r * 12] = src[i]; }

@@ -305,6 +305,7 @@ extern "C" int kmc_strip_rebuild(kmc_handle *h, const void *from_low, int64_t n_
 // (kmc_strip_get_series / kmc_strip_get_oligomer_hist all-reduce them: the bond.dat row of the WHOLE membrane).
 // The host path above is kept as the reference implementation (tests compare the two).
 // ================================================================================================================
+#include <chrono>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -353,7 +354,11 @@ struct StripDev {
     char *msg[3] = {nullptr}; size_t msgCap[3] = {0};     // packed messages: 0 to lower x, 1 to higher x (band capacity), 2 = the owned set (full capacity)
     char *rcv[2] = {nullptr};                 // what the neighbours sent (0 from lower x, 1 from higher x), band capacity
     size_t bandCap = 0;                       // bytes of a band message (header + records): the same on every rank
-    int *bondRef = nullptr;                   // [NAt*2 + NBt*3] bonds of the merged molecules as reference ids, before translation
+    int *bondRef = nullptr;                   // [NAt*3 + NBt*3] bonds of the merged molecules as reference ids, before translation
+    int *keptRank = nullptr;                  // [NT] owned molecules of the same species with a lower index
+    unsigned char *ownFlag = nullptr;         // [NT] after a merge: molecule of a unit this rank owns
+    unsigned *refA2 = nullptr, *refB2 = nullptr;   // reference ids of the merged set (copied over refA / refB by k_strip_fix_bonds)
+    int *cref = nullptr;                      // [2 NAt + 2 NBt] compact reference ids of the incoming lists
     int *series = nullptr;                    // [8] device, owned only: R-L, mono-cis, cis bonds, complexes, molecules in complexes, -, -, running-max complex
     unsigned long long *hist = nullptr;       // [STRIP_HIST_BINS] sizes of the owned ligand-rooted complexes (last step's tables)
     int *hostI = nullptr;                     // pinned: [0..15] header staging, [16..31] series read-back
@@ -510,11 +515,11 @@ __device__ __forceinline__ void strip_write_record(const Consts &K, const Dev &D
         for (int q = 0; q < 24; q++) o->pose[q] = p[q];
     }
 }
-__global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ Args A, const unsigned char *flag, int ntA, const int *tileOff, const int *cnt6, MsgBufs M) {
+__global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ Args A, const unsigned char *flag, int ntA, const int *tileOff, const int *cnt6, MsgBufs M, int lists, int *keptRank) {
     KARGS
     const Consts &K = cK;
     __shared__ int sh[3][8];
-    const int bad = cnt6[6];
+    const int bad = cnt6[6] | ~lists;          // lists: bit mask of the messages this launch writes
     int first, n, c[3]; bool lig;
     strip_tile_counts(K, D, flag, ntA, first, n, lig, c);
     int rank[3];
@@ -533,78 +538,135 @@ __global__ void __launch_bounds__(256) k_strip_pack_all(const __grid_constant__ 
         if (i >= n) break;
         const int gid = lig ? K.NAt + i : i, f = flag[gid];
         const int bits[3] = {(f >> 1) & 1, (f >> 2) & 1, f & 1};
-        for (int l = 0; l < 3; l++) if (bits[l] && !((bad >> l) & 1)) strip_write_record(K, D, gid, M.p[l] + MSG_HDR, cnt6[l * 2], rank[l]++);
+        if (keptRank) keptRank[gid] = rank[2];             // owned molecules of this species with a lower index
+        for (int l = 0; l < 3; l++) if (bits[l]) { if (!((bad >> l) & 1)) strip_write_record(K, D, gid, M.p[l] + MSG_HDR, cnt6[l * 2], rank[l]); rank[l]++; }
     }
 }
-template <class T> __device__ __forceinline__ int d_lower_bound(const T *a, int n, int ref) {
+__device__ __forceinline__ int d_lower_bound_i(const int *a, int n, int ref) {
     int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid].ref < ref) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < ref) lo = mid + 1; else hi = mid; }
     return lo;
-}
-// merge of the three id-sorted lists (kept, from low, from high): every record knows its final index. The lists are disjoint:
-// a molecule has one owner, and with two ranks (both bands from the same peer) the sender lists a unit once (k_strip_classify).
-struct MergeSrc { const char *base[3]; };
-__device__ __forceinline__ bool merge_counts(const Consts &K, const Dev &D, const MergeSrc &M, int nr[3], int nl[3]) {
-    bool bad = false;
-    for (int k = 0; k < 3; k++) { const int *hdr = reinterpret_cast<const int *>(M.base[k]); nr[k] = hdr[0]; nl[k] = hdr[1]; bad |= hdr[2] != 0; }
-    return !bad && nr[0] + nr[1] + nr[2] <= K.NAt && nl[0] + nl[1] + nl[2] <= K.NBt;
-}
-__global__ void k_strip_merge(const __grid_constant__ Args A, MergeSrc M, int *bondRef) {
-    KARGS
-    const Consts &K = cK;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int nr[3], nl[3];
-    if (!merge_counts(K, D, M, nr, nl)) { if (i == 0) atomicOr(&D.scal[S_OVERFLOW], 128); return; }      // a message or the local capacity is too small
-    const int totR = nr[0] + nr[1] + nr[2], totL = nl[0] + nl[1] + nl[2];
-    const RecMsg *R[3]; const LigMsg *L[3];
-    for (int k = 0; k < 3; k++) { R[k] = reinterpret_cast<const RecMsg *>(M.base[k] + MSG_HDR); L[k] = reinterpret_cast<const LigMsg *>(M.base[k] + MSG_HDR + (size_t)nr[k] * sizeof(RecMsg)); }
-    if (i < totR) {
-        int k = 0; while (i >= nr[k]) { i -= nr[k]; k++; }
-        const RecMsg m = R[k][i];
-        int pos = i;
-        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(R[o], nr[o], m.ref);
-        D.recC[pos] = make_double2(m.pose[0], m.pose[1]); D.recS2[pos] = make_double2(m.pose[2], m.pose[3]); D.recS3[pos] = make_double2(m.pose[4], m.pose[5]);
-        D.refA[pos] = (unsigned)m.ref; D.recSite[pos] = m.site;
-        bondRef[pos * 2] = m.ligRef; bondRef[pos * 2 + 1] = m.cisRef;
-    } else if (i < totR + totL) {
-        i -= totR;
-        int k = 0; while (i >= nl[k]) { i -= nl[k]; k++; }
-        const LigMsg *src = &L[k][i];
-        int pos = i;
-        for (int o = 0; o < 3; o++) if (o != k) pos += d_lower_bound(L[o], nl[o], src->ref);
-        D.refB[pos] = (unsigned)src->ref;
-        double *p = D.lig + (size_t)pos * 24;
-        for (int q = 0; q < 24; q++) p[q] = src->pose[q];
-        for (int q = 0; q < 3; q++) bondRef[2 * K.NAt + pos * 3 + q] = src->recRef[q];
-    }
 }
 __device__ __forceinline__ int d_find_ref(const unsigned *a, int n, int ref) {
     int lo = 0, hi = n;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < (unsigned)ref) lo = mid + 1; else hi = mid; }
     return (lo < n && a[lo] == (unsigned)ref) ? lo : -1;
 }
-// bonds back from reference ids to local indices; thread 0 publishes the new live counts (nobody in this kernel reads them)
-__global__ void k_strip_fix_bonds(const __grid_constant__ Args A, MergeSrc M, const int *bondRef) {
+// ---- merge: new local set = the molecules this rank keeps (owned units, still in the arrays) + the two incoming lists, id-sorted.
+// The kept molecules never leave the arrays: they are copied from the committed pose buffers straight to their new index in the
+// other ("next") pose buffers, which are scratch between two steps; the host then swaps the buffers like a step does. The lists
+// are disjoint: a molecule has one owner, and with two ranks (both bands from the same peer) the sender lists a unit once.
+struct MergeIn {
+    const char *base[2];          // incoming lists: [from lower x, from higher x] (header + records)
+    int *cref;                    // compact copies of their reference ids: rec list 0 at 0, rec list 1 at NAt, lig list 0 at 2 NAt, lig list 1 at 2 NAt + NBt
+    const int *dcnt;              // [4] kept receptors, [5] kept ligands
+    const int *keptRank;          // per old molecule: kept molecules of its species with a lower index
+    const unsigned char *flag;    // bit0: kept
+    unsigned *refA2, *refB2;      // new reference ids
+    unsigned char *ownFlag;       // new: 1 = molecule of a unit this rank owns
+    int *bond;                    // new bonds as reference ids: receptor [pos*3 + {lig, cis, site}], ligand [3 NAt + pos*3 + site]
+};
+__device__ __forceinline__ bool merge_counts(const Consts &K, const MergeIn &M, int nr[2], int nl[2], int &keptR, int &keptL) {
+    bool bad = false;
+    for (int k = 0; k < 2; k++) { const int *hdr = reinterpret_cast<const int *>(M.base[k]); nr[k] = hdr[0]; nl[k] = hdr[1]; bad |= hdr[2] != 0; }
+    keptR = M.dcnt[4]; keptL = M.dcnt[5];
+    return !bad && keptR + nr[0] + nr[1] <= K.NAt && keptL + nl[0] + nl[1] <= K.NBt;
+}
+__global__ void k_strip_refs(const __grid_constant__ Args A, MergeIn M) {
+    KARGS
+    const Consts &K = cK;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < 2; k++) {
+        const int *hdr = reinterpret_cast<const int *>(M.base[k]);
+        const int nr = min(hdr[0], K.NAt), nl = min(hdr[1], K.NBt);
+        if (i < nr) { M.cref[k * K.NAt + i] = reinterpret_cast<const RecMsg *>(M.base[k] + MSG_HDR)[i].ref; return; }
+        i -= nr;
+        if (i < nl) { M.cref[2 * K.NAt + k * K.NBt + i] = reinterpret_cast<const LigMsg *>(M.base[k] + MSG_HDR + (size_t)nr * sizeof(RecMsg))[i].ref; return; }
+        i -= nl;
+    }
+}
+__global__ void k_strip_merge(const __grid_constant__ Args A, MergeIn M) {
+    KARGS
+    const Consts &K = cK;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int nr[2], nl[2], keptR, keptL;
+    if (!merge_counts(K, M, nr, nl, keptR, keptL)) { if (i == 0) atomicOr(&D.scal[S_OVERFLOW], 128); return; }      // a message or the local capacity is too small
+    const int nAold = nA_live(D), nBold = nB_live(D);
+    const int *cR[2] = {M.cref, M.cref + K.NAt}, *cL[2] = {M.cref + 2 * K.NAt, M.cref + 2 * K.NAt + K.NBt};
+    if (i < K.NT) {                                               // a molecule that stays
+        if (!(i < K.NAt ? i < nAold : i - K.NAt < nBold) || !(M.flag[i] & 1)) return;
+        if (i < K.NAt) {
+            const int ref = (int)D.refA[i];
+            const int pos = M.keptRank[i] + d_lower_bound_i(cR[0], nr[0], ref) + d_lower_bound_i(cR[1], nr[1], ref);
+            D.recCn[pos] = D.recC[i]; D.recS2n[pos] = D.recS2[i]; D.recS3n[pos] = D.recS3[i];
+            M.refA2[pos] = (unsigned)ref; M.ownFlag[pos] = 1;
+            const int l = D.recLig[i], c = D.recCis[i];
+            M.bond[pos * 3] = l >= 0 ? (int)D.refB[l] : 0; M.bond[pos * 3 + 1] = c >= 0 ? (int)D.refA[c] : 0; M.bond[pos * 3 + 2] = D.recSite[i];
+        } else {
+            const int b = i - K.NAt, ref = (int)D.refB[b];
+            const int pos = M.keptRank[i] + d_lower_bound_i(cL[0], nl[0], ref) + d_lower_bound_i(cL[1], nl[1], ref);
+            const double2 *src = reinterpret_cast<const double2 *>(D.lig + (size_t)b * 24);
+            double2 *dst = reinterpret_cast<double2 *>(D.lign + (size_t)pos * 24);
+#pragma unroll
+            for (int q = 0; q < 12; q++) dst[q] = src[q];
+            M.refB2[pos] = (unsigned)ref; M.ownFlag[K.NAt + pos] = 1;
+            for (int q = 0; q < 3; q++) { const int r = D.ligRec[b * 3 + q]; M.bond[3 * K.NAt + pos * 3 + q] = r >= 0 ? (int)D.refA[r] : 0; }
+        }
+        return;
+    }
+    i -= K.NT;                                                    // an incoming record
+    if (i < nr[0] + nr[1]) {
+        const int k = i < nr[0] ? 0 : 1; if (k) i -= nr[0];
+        const RecMsg m = reinterpret_cast<const RecMsg *>(M.base[k] + MSG_HDR)[i];
+        int q = 0; { int lo = 0, hi = nAold; while (lo < hi) { const int mid = (lo + hi) >> 1; if (D.refA[mid] < (unsigned)m.ref) lo = mid + 1; else hi = mid; } q = lo; }
+        const int pos = i + (q < nAold ? M.keptRank[q] : keptR) + d_lower_bound_i(cR[1 - k], nr[1 - k], m.ref);
+        D.recCn[pos] = make_double2(m.pose[0], m.pose[1]); D.recS2n[pos] = make_double2(m.pose[2], m.pose[3]); D.recS3n[pos] = make_double2(m.pose[4], m.pose[5]);
+        M.refA2[pos] = (unsigned)m.ref; M.ownFlag[pos] = 0;
+        M.bond[pos * 3] = m.ligRef; M.bond[pos * 3 + 1] = m.cisRef; M.bond[pos * 3 + 2] = m.site;
+        return;
+    }
+    i -= nr[0] + nr[1];
+    if (i < nl[0] + nl[1]) {
+        const int k = i < nl[0] ? 0 : 1; if (k) i -= nl[0];
+        const LigMsg *src = reinterpret_cast<const LigMsg *>(M.base[k] + MSG_HDR + (size_t)nr[k] * sizeof(RecMsg)) + i;
+        const int ref = src->ref;
+        int q = 0; { int lo = 0, hi = nBold; while (lo < hi) { const int mid = (lo + hi) >> 1; if (D.refB[mid] < (unsigned)ref) lo = mid + 1; else hi = mid; } q = lo; }
+        const int pos = i + (q < nBold ? M.keptRank[K.NAt + q] : keptL) + d_lower_bound_i(cL[1 - k], nl[1 - k], ref);
+        double *p = D.lign + (size_t)pos * 24;
+        for (int t = 0; t < 24; t++) p[t] = src->pose[t];
+        M.refB2[pos] = (unsigned)ref; M.ownFlag[K.NAt + pos] = 0;
+        for (int t = 0; t < 3; t++) M.bond[3 * K.NAt + pos * 3 + t] = src->recRef[t];
+    }
+}
+// bonds back from reference ids to local indices (new numbering); thread 0 publishes the new live counts (nobody in this kernel reads them)
+__global__ void k_strip_fix_bonds(const __grid_constant__ Args A, MergeIn M) {
     KARGS
     const Consts &K = cK;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int nr[3], nl[3];
-    if (!merge_counts(K, D, M, nr, nl)) return;
-    const int nA = nr[0] + nr[1] + nr[2], nB = nl[0] + nl[1] + nl[2];
+    int nr[2], nl[2], keptR, keptL;
+    if (!merge_counts(K, M, nr, nl, keptR, keptL)) return;
+    const int nA = keptR + nr[0] + nr[1], nB = keptL + nl[0] + nl[1];
     if (i == 0) { D.scal[S_NA_LIVE] = nA; D.scal[S_NB_LIVE] = nB; D.scal[S_TOPO_DIRTY] = 1; }
     if (i < nA) {
-        const int lr = bondRef[i * 2], cr = bondRef[i * 2 + 1];
-        const int l = lr ? d_find_ref(D.refB, nB, lr) : -1, c = cr ? d_find_ref(D.refA, nA, cr) : -1;
+        const int lr = M.bond[i * 3], cr = M.bond[i * 3 + 1];
+        const int l = lr ? d_find_ref(M.refB2, nB, lr) : -1, c = cr ? d_find_ref(M.refA2, nA, cr) : -1;
         if ((lr && l < 0) || (cr && c < 0)) atomicOr(&D.scal[S_OVERFLOW], 16);        // a unit arrived incomplete
-        D.recLig[i] = l; D.recCis[i] = c; if (l < 0) D.recSite[i] = -1;
-    } else if (i < nA + nB) {
-        const int h = i - nA;
+        D.recLig[i] = l; D.recCis[i] = c; D.recSite[i] = l < 0 ? -1 : M.bond[i * 3 + 2];
+        D.refA[i] = M.refA2[i];
+    } else if (i >= K.NAt && i - K.NAt < nB) {
+        const int h = i - K.NAt;
         for (int q = 0; q < 3; q++) {
-            const int rr = bondRef[2 * K.NAt + h * 3 + q], r = rr ? d_find_ref(D.refA, nA, rr) : -1;
+            const int rr = M.bond[3 * K.NAt + h * 3 + q], r = rr ? d_find_ref(M.refA2, nA, rr) : -1;
             if (rr && r < 0) atomicOr(&D.scal[S_OVERFLOW], 16);
             D.ligRec[h * 3 + q] = r;
         }
+        D.refB[h] = M.refB2[h];
     }
+}
+__global__ void k_strip_flag_owned(const __grid_constant__ Args A, const unsigned char *ownFlag, unsigned char *flag) {       // the owned set into list 2
+    KARGS
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < cK.NT) flag[gid] = (gid_live(cK, D, gid) && ownFlag[gid]) ? 1 : 0;
 }
 
 static void strip_dev_free(kmc_handle *h) {       // device buffers are in h->allocs
@@ -637,7 +699,9 @@ static int strip_dev_alloc(kmc_handle *h) {
     S.ntA = (h->NAt + ST_TILE - 1) / ST_TILE; S.ntB = (h->NBt + ST_TILE - 1) / ST_TILE;
     bool ok = dalloc(h, &S.flag, NT) == cudaSuccess && dalloc(h, &S.tileCnt, (size_t)3 * (S.ntA + S.ntB) + 3) == cudaSuccess &&
               dalloc(h, &S.tileOff, (size_t)3 * (S.ntA + S.ntB) + 3) == cudaSuccess && dalloc(h, &S.dcnt, 8) == cudaSuccess &&
-              dalloc(h, &S.bondRef, (size_t)2 * h->NAt + (size_t)3 * h->NBt + 8) == cudaSuccess &&
+              dalloc(h, &S.bondRef, (size_t)3 * h->NAt + (size_t)3 * h->NBt + 8) == cudaSuccess &&
+              dalloc(h, &S.keptRank, NT) == cudaSuccess && dalloc(h, &S.ownFlag, NT) == cudaSuccess && dalloc(h, &S.refA2, std::max(h->NAt, 1)) == cudaSuccess &&
+              dalloc(h, &S.refB2, std::max(h->NBt, 1)) == cudaSuccess && dalloc(h, &S.cref, (size_t)2 * h->NAt + (size_t)2 * h->NBt + 8) == cudaSuccess &&
               dalloc(h, &S.series, 8) == cudaSuccess && dalloc(h, &S.hist, STRIP_HIST_BINS) == cudaSuccess &&
               cudaMallocHost((void **)&S.hostI, 32 * sizeof(int)) == cudaSuccess && cudaMallocHost((void **)&S.hostH, STRIP_HIST_BINS * sizeof(unsigned long long)) == cudaSuccess;
     // band capacity: 1.5 x the share of the local capacity a band of width W is expected to hold (+ slack for small systems);
@@ -652,15 +716,18 @@ static int strip_dev_alloc(kmc_handle *h) {
     return KMC_OK;
 }
 
-// classify -> count -> scan -> pack of the flagged lists into msg[0..2] (flags already set)
-static void strip_pack_lists(kmc_handle *h, cudaStream_t st) {
+// count -> scan -> pack of the flagged lists (bit mask `lists`: 1 to lower x, 2 to higher x, 4 the owned set) into msg[0..2];
+// the flags are already set. Counting and headers cover all three lists, whichever are written.
+static void strip_pack_lists(kmc_handle *h, cudaStream_t st, int lists, bool count) {
     StripDev &S = *h->strip_dev;
     const Args A{h->D, h->K};
     const int nt = S.ntA + S.ntB;
     MsgBufs M; for (int k = 0; k < 3; k++) { M.p[k] = S.msg[k]; M.cap[k] = S.msgCap[k]; }
-    k_strip_count<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileCnt);
-    k_strip_scan_tiles<<<1, 1024, 0, st>>>(S.tileCnt, S.tileOff, S.ntA, S.ntB, S.dcnt, M, h->D.scal);
-    k_strip_pack_all<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileOff, S.dcnt, M);
+    if (count) {
+        k_strip_count<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileCnt);
+        k_strip_scan_tiles<<<1, 1024, 0, st>>>(S.tileCnt, S.tileOff, S.ntA, S.ntB, S.dcnt, M, h->D.scal);
+    }
+    k_strip_pack_all<<<nt, 256, 0, st>>>(A, S.flag, S.ntA, S.tileOff, S.dcnt, M, lists, count ? S.keptRank : nullptr);
 }
 // Refresh, phase 1 (asynchronous): by-products, complexes of the CURRENT bond table, ownership + bands, the three messages
 static int strip_pack(kmc_handle *h) {
@@ -681,18 +748,21 @@ static int strip_pack(kmc_handle *h) {
     CK(cudaMemsetAsync(S.flag, 0, NT, st));
     k_strip_classify<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, h->strip_lo, h->strip_hi, h->strip_W, S.budget);
     k_strip_bonds_owned<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, S.flag, S.series);
-    strip_pack_lists(h, st);
+    strip_pack_lists(h, st, 3, true);           // the two band messages (the owned molecules stay in the arrays: only their ranks are computed)
     return KMC_OK;
 }
-// Refresh, phase 2 (asynchronous): the new local set = the units this rank owns + what the two neighbours sent
-static int strip_merge(kmc_handle *h) {
+// Refresh, phase 2 (asynchronous): the new local set = the units this rank owns + the two incoming lists
+static int strip_merge(kmc_handle *h, const char *fromLow, const char *fromHigh) {
     StripDev &S = *h->strip_dev;
     cudaStream_t st = h->stream;
     const Args A{h->D, h->K};
-    MergeSrc M; M.base[0] = S.msg[2]; M.base[1] = S.rcv[0]; M.base[2] = S.rcv[1];
-    k_strip_merge<<<nblk(std::max(h->NT, 1), 128), 128, 0, st>>>(A, M, S.bondRef);
-    k_strip_fix_bonds<<<nblk(std::max(h->NT, 1), 128), 128, 0, st>>>(A, M, S.bondRef);
+    MergeIn M; M.base[0] = fromLow; M.base[1] = fromHigh; M.cref = S.cref; M.dcnt = S.dcnt; M.keptRank = S.keptRank; M.flag = S.flag;
+    M.refA2 = S.refA2; M.refB2 = S.refB2; M.ownFlag = S.ownFlag; M.bond = S.bondRef;
+    k_strip_refs<<<nblk(std::max(h->NT, 1), 256), 256, 0, st>>>(A, M);
+    k_strip_merge<<<nblk(std::max(2 * h->NT, 1), 128), 128, 0, st>>>(A, M);
+    k_strip_fix_bonds<<<nblk(std::max(h->NT, 1), 128), 128, 0, st>>>(A, M);
     CK(cudaGetLastError());
+    swap_buffers(h->D); h->parity ^= 1;          // the merged poses were written into the "next" buffers
     h->stepped = false; h->sinceBuild = 0; h->strip_since = 0; h->strip_refreshes++;
     S.fresh = true;
     return KMC_OK;
@@ -734,22 +804,39 @@ extern "C" int kmc_strip_comm_init(kmc_handle *h, const void *id128, int32_t ref
 extern "C" int kmc_strip_refresh(kmc_handle *h) {
     if (!h || !h->strip_on) { if (h) h->err = "kmc_strip_refresh: configure strips first"; return KMC_ERR_INVALID; }
     CK(cudaSetDevice(h->P.device));
+    // KMC_STRIP_TIMING=1 (diagnostics only): synchronise between the phases and accumulate their wall-clock times
+    static const bool timing = getenv("KMC_STRIP_TIMING") != nullptr;
+    auto now = [&]() { cudaStreamSynchronize(h->stream); return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = timing ? now() : 0;
     int rc = strip_pack(h); if (rc) return rc;
     StripDev &S = *h->strip_dev;
+    double t1 = timing ? now() : 0;
     const int n = h->K.strips, r = h->K.stripRank;
     if (n > 1) {
         if (!S.comm) { h->err = "kmc_strip_refresh: no communicator (kmc_strip_comm_init)"; return KMC_ERR_INVALID; }
         const int lo = (r + n - 1) % n, hi = (r + 1) % n;
+        cudaStream_t xs = h->stream;
+        if (xs != h->stream) { CK(cudaEventRecord(h->evFork[1], h->stream)); CK(cudaStreamWaitEvent(xs, h->evFork[1], 0)); }
         // untagged point-to-point operations between one pair of ranks are matched in posting order: sends [to low, to high],
         // receives [from high, from low] -- with two ranks (both neighbours the same peer) my first send meets its first receive
         NC(g_nccl.GroupStart());
-        NC(g_nccl.Send(S.msg[0], S.bandCap, ncclChar, lo, S.comm, h->stream));
-        NC(g_nccl.Send(S.msg[1], S.bandCap, ncclChar, hi, S.comm, h->stream));
-        NC(g_nccl.Recv(S.rcv[1], S.bandCap, ncclChar, hi, S.comm, h->stream));
-        NC(g_nccl.Recv(S.rcv[0], S.bandCap, ncclChar, lo, S.comm, h->stream));
+        NC(g_nccl.Send(S.msg[0], S.bandCap, ncclChar, lo, S.comm, xs));
+        NC(g_nccl.Send(S.msg[1], S.bandCap, ncclChar, hi, S.comm, xs));
+        NC(g_nccl.Recv(S.rcv[1], S.bandCap, ncclChar, hi, S.comm, xs));
+        NC(g_nccl.Recv(S.rcv[0], S.bandCap, ncclChar, lo, S.comm, xs));
         NC(g_nccl.GroupEnd());
+        if (xs != h->stream) { CK(cudaEventRecord(h->evJoin[3], xs)); CK(cudaStreamWaitEvent(h->stream, h->evJoin[3], 0)); }
     } else { CK(cudaMemsetAsync(S.rcv[0], 0, MSG_HDR, h->stream)); CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, h->stream)); }
-    return strip_merge(h);
+    double t2 = timing ? now() : 0;
+    rc = strip_merge(h, S.rcv[0], S.rcv[1]);
+    if (timing) {
+        const double t3 = now();
+        h->strip_t[0] += t1 - t0; h->strip_t[1] += t2 - t1; h->strip_t[2] += t3 - t2;
+        if (h->strip_refreshes % 20 == 0 && r == 0)
+            fprintf(stderr, "strip refresh timing over %lld refreshes (us each): classify+pack %.1f, exchange %.1f (%zu bytes per band), merge %.1f\n",
+                    (long long)h->strip_refreshes, h->strip_t[0] / h->strip_refreshes, h->strip_t[1] / h->strip_refreshes, S.bandCap, h->strip_t[2] / h->strip_refreshes);
+    }
+    return rc;
 }
 static int strip_auto_refresh(kmc_handle *h) { return kmc_strip_refresh(h); }
 // The same refresh between K handles of ONE process (logical ranks 0..K-1, all configured with nranks = K): device-to-device
@@ -773,7 +860,7 @@ extern "C" int kmc_strip_refresh_local(kmc_handle **hs, int32_t n, int32_t refre
             CK(cudaMemcpyAsync(S.rcv[0], L.msg[1], S.bandCap, cudaMemcpyDeviceToDevice, h->stream));      // what my lower neighbour sent upwards
             CK(cudaMemcpyAsync(S.rcv[1], H.msg[0], S.bandCap, cudaMemcpyDeviceToDevice, h->stream));      // what my upper neighbour sent downwards
         } else { CK(cudaMemsetAsync(S.rcv[0], 0, MSG_HDR, h->stream)); CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, h->stream)); }
-        int rc = strip_merge(h); if (rc) return rc;
+        int rc = strip_merge(h, S.rcv[0], S.rcv[1]); if (rc) return rc;
     }
     for (int i = 0; i < n; i++) { kmc_handle *h = hs[i]; CK(cudaStreamSynchronize(h->stream)); }
     return KMC_OK;
@@ -841,14 +928,17 @@ extern "C" int kmc_strip_get_oligomer_hist(kmc_handle *h, int32_t reduce, int64_
 extern "C" int kmc_strip_get_records(kmc_handle *h, int32_t which, void *host_buf, int64_t cap_bytes, int64_t *n_rec, int64_t *n_lig) {
     if (!h || !h->strip_on || !host_buf || (which != 2 && which != 3)) { if (h) h->err = "kmc_strip_get_records: bad argument"; return KMC_ERR_INVALID; }
     int rc;
-    if (which == 2) { rc = strip_fresh(h, "kmc_strip_get_records"); if (rc) return rc; }
-    else {
+    if (which == 2) {
+        rc = strip_fresh(h, "kmc_strip_get_records"); if (rc) return rc;
+        const Args A{h->D, h->K};
+        k_strip_flag_owned<<<nblk(std::max(h->NT, 1), 256), 256, 0, h->stream>>>(A, h->strip_dev->ownFlag, h->strip_dev->flag);
+        strip_pack_lists(h, h->stream, 4, true);
+    } else {
         CK(cudaSetDevice(h->P.device));
         rc = strip_dev_alloc(h); if (rc) return rc;
         const Args A{h->D, h->K};
         k_strip_flag_all<<<nblk(std::max(h->NT, 1), 256), 256, 0, h->stream>>>(A, h->strip_dev->flag);
-        strip_pack_lists(h, h->stream);
-        h->strip_dev->fresh = false;            // msg[2] no longer holds the owned set
+        strip_pack_lists(h, h->stream, 4, true);
     }
     StripDev &S = *h->strip_dev; cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(S.hostI, S.msg[2], MSG_HDR, cudaMemcpyDeviceToHost, st));
@@ -873,9 +963,11 @@ extern "C" int kmc_strip_load_records(kmc_handle *h, const void *host_buf, int64
     CK(cudaMemcpyAsync(S.msg[2], S.hostI, MSG_HDR, cudaMemcpyHostToDevice, st));
     const size_t bytes = (size_t)n_rec * sizeof(RecMsg) + (size_t)n_lig * sizeof(LigMsg);
     if (bytes) CK(cudaMemcpyAsync(S.msg[2] + MSG_HDR, host_buf, bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(S.rcv[0], 0, MSG_HDR, st)); CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, st));
+    CK(cudaMemsetAsync(S.rcv[1], 0, MSG_HDR, st));
+    CK(cudaMemsetAsync(S.dcnt, 0, 8 * sizeof(int), st));                       // nothing is kept: the records are the whole new set
+    CK(cudaMemsetAsync(h->D.scal + S_NA_LIVE, 0, 2 * sizeof(int), st));
     CK(cudaMemcpyAsync(h->D.step64, s64, sizeof *s64, cudaMemcpyHostToDevice, st));
-    rc = strip_merge(h); if (rc) return rc;
+    rc = strip_merge(h, S.msg[2], S.rcv[1]); if (rc) return rc;
     S.fresh = false;                          // by-products describe nothing yet
     h->step_done = step_done; h->strip_refreshes--;
     CK(cudaStreamSynchronize(st));
