@@ -7,7 +7,7 @@ namespace kmc {
 
 enum Scalar {
     S_MEMBER_CURSOR = 0,  // next free slot in members[]
-    S_NCX,                // number of complexes (size > 1) in cxRoots[]
+    S_NCX,                // number of small complexes (1 < size <= CX_SMALL) at the front of cxRoots[] (one thread each)
     S_NFAR,               // far movers this step
     S_NPEND,              // pending findings of this step (pendList)
     S_EPOCH,              // steps taken by this handle (never reset): stamps the per-cell chains of special entries
@@ -20,7 +20,9 @@ enum Scalar {
     S_NREJ,               // rejected units of this step (rejList)
     S_NA_LIVE, S_NB_LIVE, // molecules actually present in the receptor / ligand blocks (<= NAt / NBt; strips change them)
     S_NSPEC_MAX,          // largest S_NSPEC of any step so far (the host decides the list-reuse back-off from it)
-    S_COUNT = 16
+    S_NCX_BIG,            // complexes with more than CX_SMALL members: listed from the END of the first half of cxRoots[] (one warp each)
+    S_NCX_MULTI,          // small complexes with several ligands: listed in the second half of cxRoots[] (S_NCX counts the single-ligand ones)
+    S_COUNT = 24
 };
 enum UnitState : unsigned char { U_UNKNOWN = 0, U_ACCEPT = 1, U_REJECT = 2 };
 enum Event { EV_RL_ON = 0, EV_MONO_ON, EV_CIS_ON, EV_RL_OFF, EV_MONO_OFF, EV_CIS_OFF, EV_REVERTED, EV_TRIED, EV_FAR,

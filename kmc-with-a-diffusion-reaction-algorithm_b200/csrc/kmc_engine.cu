@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 19
+#define KMC_NKERNELS 20
 #define MON_EVERY 256
 
 #include <algorithm>
@@ -79,10 +79,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig"};
+    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small"};
 enum { KID_UF_INIT = 0, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
-       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG };
+       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -291,7 +291,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(lig, (size_t)K.NBt * 24); A(lign, (size_t)K.NBt * 24);
     A(recLig, K.NAt); A(recSite, K.NAt); A(recCis, K.NAt); A(ligRec, (size_t)K.NBt * 3);
     A(ufParent, K.NT); A(unitOf, K.NT);
-    if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, K.NBt);
+    if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, (size_t)2 * K.NBt);
     A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT); A(rowPos, K.NT);
     A(movedFlag, K.NT); A(nrec, (size_t)6 * K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -547,6 +547,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<std::min(nblk(std::max(NAt, 1), REC_TILE), h->nSM * RECMINB), REC_TILE, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
+    LAUNCH(KID_PROPOSE_COMPLEX_SMALL, (k_propose_complex_small<<<std::min(nblk(NBt, 128), h->nSM * 16), 128, 0, s2>>>(A)));
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), h->nSM * 12), 32 * CX_WARPS, 0, s2>>>(A)));
     if (fork || forkC) {
         cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);

@@ -18,6 +18,9 @@
 #include "kmc_device.cuh"
 #include <cuda_pipeline.h>
 #define REC_TILE 256
+#ifndef CX_SMALL
+#define CX_SMALL 12        // complexes up to this size: one thread each; larger: one warp each
+#endif
 
 namespace kmc {
 
@@ -58,7 +61,7 @@ __global__ void k_uf_init(const __grid_constant__ Args A, int begin) {
         if (D.scal[S_NSPEC] > D.scal[S_NSPEC_MAX]) D.scal[S_NSPEC_MAX] = D.scal[S_NSPEC];
         D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0;
         if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
-        if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.events[EV_REBUILDS] += 1; }
+        if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.scal[S_NCX_BIG] = 0; D.scal[S_NCX_MULTI] = 0; D.events[EV_REBUILDS] += 1; }
     }
     if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,7 +107,7 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     if (size <= 1) return;
     int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
     D.cxOff[h] = off;
-    D.cxRoots[atomicAdd(&D.scal[S_NCX], 1)] = h;
+    // (listed below, once the member row is known: the lists are sorted by kind)
     int *row = D.members + off;
     int head = 0, tail = 0;
     row[tail++] = cK.NAt + h; D.bfsMark[cK.NAt + h] = 1; D.rowPos[cK.NAt + h] = 0;
@@ -121,6 +124,14 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
         for (int c = 0; c < nc; c++)
             if (!D.bfsMark[cand[c]]) { D.bfsMark[cand[c]] = 1; if (tail < size) { D.rowPos[cand[c]] = tail; row[tail++] = cand[c]; } }
     }
+    // Work lists of the proposal kernels, by kind, so that the threads of a warp run the same code path: small complexes
+    // (one THREAD each, k_propose_complex_small) with ONE ligand (S2e) from the front of cxRoots, small ones with several ligands
+    // (S2f: shuffles, passes) in its second half; large complexes (one warp each, k_propose_complex) from the back of the first half
+    int nlig = 0;
+    for (int i = 0; i < size; i++) nlig += row[i] >= cK.NAt;
+    if (size > CX_SMALL) D.cxRoots[cK.NBt - 1 - atomicAdd(&D.scal[S_NCX_BIG], 1)] = h;
+    else if (nlig == 1) D.cxRoots[atomicAdd(&D.scal[S_NCX], 1)] = h;
+    else D.cxRoots[cK.NBt + atomicAdd(&D.scal[S_NCX_MULTI], 1)] = h;
 }
 
 // Order of the sweep. Every molecule carries the key of its unit: (colour << 30) | head gid. In replay mode the colour is 0,
@@ -192,7 +203,7 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
 // for tile t + gridDim (centre, two sites, unit word, cis word, entry centre) are already in flight (cp.async, 16 B per request,
 // each thread copies and later reads only its own slot: no barrier, just the pipeline wait). The load latency that every warp
 // used to sit out at its start now overlaps the previous tile's arithmetic.
-struct RecStage { double2 c[REC_TILE], s2[REC_TILE], s3[REC_TILE]; float2 bc[REC_TILE]; int head[REC_TILE], cis[REC_TILE]; };
+struct RecStage { double2 c[REC_TILE], s2[REC_TILE], s3[REC_TILE]; float2 bc[REC_TILE]; int head[REC_TILE], cis[REC_TILE]; unsigned ref[REC_TILE]; };
 KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile, int nLive) {
     const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
     if (gid < nLive) {
@@ -200,9 +211,10 @@ KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile, int n
         __pipeline_memcpy_async(&S.s3[t], &D.recS3[gid], 16);
         __pipeline_memcpy_async(&S.head[t], &D.unitOf[gid], 4); __pipeline_memcpy_async(&S.cis[t], &D.recCis[gid], 4);
         if (K.phase) __pipeline_memcpy_async(&S.bc[t], &D.bcen[gid], 8);
+        if (D.refA) __pipeline_memcpy_async(&S.ref[t], &D.refA[gid], 4);          // strips: the reference id keys the random stream
     }
 }
-KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc);
+KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc, uint32_t me);
 KD void propose_rec_body(const Args &A) {
     KARGS
     const Consts &K = cK;
@@ -223,18 +235,17 @@ KD void propose_rec_body(const Args &A) {
         const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
         if (gid < nLive) {
             Rec ra; ra.cx = S.c[t].x; ra.cy = S.c[t].y; ra.s2x = S.s2[t].x; ra.s2y = S.s2[t].y; ra.s3x = S.s3[t].x; ra.s3y = S.s3[t].y;
-            propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase ? S.bc[t] : make_float2(0.f, 0.f));
+            propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase ? S.bc[t] : make_float2(0.f, 0.f), D.refA ? S.ref[t] : ref_id(K, D, gid));
         }
     }
     __pipeline_wait_prior(0);
 }
-KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc) {
+KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc, uint32_t me) {
     KARGS
     const Consts &K = cK;
     if (gid >= nLive || head != gid) return;      // not the head of a unit
     const int rep = replica_of_gid(K, gid);
     const uint64_t seed = seed_of(cK, rep);
-    const uint32_t me = ref_id(K, D, gid);
     {
         const int a = gid;
         double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
@@ -324,8 +335,8 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
         for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; tile[r][i - r * 12] = src[i]; }
     }
     // the scalar words of this thread's ligand travel in the same latency window as the tile
-    int head = -1, csize = 0; float2 bc = make_float2(0.f, 0.f);
-    if (threadIdx.x < nrows) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; }
+    int head = -1, csize = 0; float2 bc = make_float2(0.f, 0.f); uint32_t me = 0;
+    if (threadIdx.x < nrows) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; me = ref_id(K, D, gid); }
     __syncthreads();
     const bool act = h < nLive && head == gid && csize <= 1;     // a free ligand (complexes: k_propose_complex)
     moved[threadIdx.x] = act ? 1 : 0;
@@ -337,7 +348,6 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
             for (int q = 0; q < 12; q++) { const double2 v = tile[threadIdx.x][q]; d[2 * q] = v.x; d[2 * q + 1] = v.y; }
         }
         const uint64_t seed = seed_of(cK, replica_of_gid(K, gid));
-        const uint32_t me = ref_id(K, D, gid);
         const double ox = l.p[0][0], oy = l.p[0][1], oz = l.p[0][2];
         double u0, u1, u2, u3, u4, u5;
         keyed_uniform2(seed, me, 0, step, 0, u0, u1); keyed_uniform2(seed, me, 0, step, 2, u2, u3); keyed_uniform2(seed, me, 0, step, 4, u4, u5);
@@ -497,10 +507,23 @@ template <class Cx> KD void align_complex(const Cx &C, int *row, int size, int n
             seat_ligand(K, b, angle, b.p[0][0], b.p[0][1]);
             C.put(hl, b);
         }
-        for (int s = 0; s < 3; s++) { const int a1 = C.ligRec(hl, s); if (a1 >= 0) resnap_rec_to_its_ligand(C, a1); }
+        // (the ligand is not touched any more: one copy serves all its receptors; the receptors stay in registers for the cis pass)
+        Rec rr[3]; int aa[3];
         for (int s = 0; s < 3; s++) {
-            const int a1 = C.ligRec(hl, s);
-            if (a1 >= 0 && C.recCis(a1) >= 0) resnap_cis_partner(C, a1, C.recCis(a1));
+            const int a1 = aa[s] = C.ligRec(hl, s);
+            if (a1 < 0) continue;
+            rr[s] = C.rec(a1);
+            if (rl_misaligned(K, b, s, rr[s])) { snap_rec_to_lig(K, rr[s], b, s); C.put(a1, rr[s]); }      // main.cpp:1196-1233
+        }
+        for (int s = 0; s < 3; s++) {
+            if (aa[s] < 0) continue;
+            const int a2 = C.recCis(aa[s]);
+            if (a2 < 0) continue;
+            Rec r2 = C.rec(a2);
+            if (cis_misaligned(K, rr[s], r2)) {                                                              // main.cpp:1237-1274
+                snap_cis(K, r2, rr[s]); C.put(a2, r2);
+                for (int t = 0; t < 3; t++) if (aa[t] == a2) rr[t] = r2;          // (a partner that sits on the same ligand: keep the register copy current)
+            }
         }
         return;
     }
@@ -652,18 +675,106 @@ KD void rotate_pose(double *p, bool isRec, double cs, double ss, double cmx, dou
     }
 }
 
+// One complex moved by ONE thread on global memory (handles = gids): S2d rigid move + S2e/S2f alignment. Used by
+// k_propose_complex_small (a thread per small complex) and, for complexes beyond the shared-memory cache, by lane 0 of a warp.
+__device__ __noinline__ void complex_move_serial(const Args &A, int h0, int size, int nB, uint64_t step, unsigned stamp, double u0, double u1, double u2) {
+    KARGS
+    const Consts &K = cK;
+    const int rootGid = K.NAt + h0, nA = size - nB;
+    const int *rowIn = D.members + D.cxOff[h0];
+    int *rowOut = D.rowWork + D.cxOff[h0];
+    const uint64_t seed = seed_of(cK, h0 / K.NB);
+    const uint32_t me = ref_id(K, D, rootGid);
+    const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
+    const double phai = mul(mul(u1, 2.0), K.pai);
+    double sp, cp; sincos(phai, &sp, &cp);
+    const double shx = mul(amp, cp), shy = mul(amp, sp);
+    const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
+    double ss, cs; sincos(psai, &ss, &cs);
+    CxGlobal C{D, K, K.NAt};
+    // wrap centre (main.cpp:1007-1008, 1022-1023) and rotation centre (1048-1068) are sums over the members in row order: two
+    // read-only passes over centres / beads; then ONE pass that shifts, wraps and rotates every member and writes it once
+    double PBx = 0, PBy = 0;
+    for (int i = 0; i < size; i++) {
+        const int m = rowIn[i]; rowOut[i] = m; D.movedFlag[m] = 0;
+        double x, y;
+        if (m < K.NAt) { const double2 c = D.recC[m]; x = c.x; y = c.y; } else { const double *p = D.lig + (size_t)(m - K.NAt) * 24; x = p[0]; y = p[1]; }
+        PBx = add(PBx, add(x, shx)); PBy = add(PBy, add(y, shy));
+    }
+    PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
+    PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
+    double cmx = 0, cmy = 0, cmz = 0;
+    for (int i = 0; i < size; i++) {
+        const int m = rowOut[i];
+        if (m < K.NAt) {
+            const double2 c = D.recC[m];
+            const double x = sub(add(c.x, shx), PBx), y = sub(add(c.y, shy), PBy);
+            for (int j = 1; j <= 4; j++) { cmx = add(cmx, x); cmy = add(cmy, y); cmz = add(cmz, rec_bead_z(K, j)); }
+        } else {
+            const double *p = D.lig + (size_t)(m - K.NAt) * 24;
+            for (int q = 0; q < 4; q++) { cmx = add(cmx, sub(add(p[q * 3], shx), PBx)); cmy = add(cmy, sub(add(p[q * 3 + 1], shy), PBy)); cmz = add(cmz, p[q * 3 + 2]); }
+        }
+    }
+    const double nbeads = (double)(4 * nA + 4 * nB);
+    cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
+    for (int i = 0; i < size; i++) {
+        const int m = rowOut[i];
+        if (m < K.NAt) {
+            Rec r = load_rec(D.recC, D.recS2, D.recS3, m);
+            shift_pose(&r.cx, true, shx, shy, false); shift_pose(&r.cx, true, PBx, PBy, true); rotate_pose(&r.cx, true, cs, ss, cmx, cmy, cmz);
+            C.put(m, r);
+        } else {
+            Lig l; load_lig(D.lig, m - K.NAt, l);
+            shift_pose(&l.p[0][0], false, shx, shy, false); shift_pose(&l.p[0][0], false, PBx, PBy, true); rotate_pose(&l.p[0][0], false, cs, ss, cmx, cmy, cmz);
+            C.put(m, l);
+        }
+    }
+    align_complex(C, rowOut, size, nB, rootGid, seed, me, step);
+    const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
+    for (int q = 0; q < size; q++) {
+        const int m = rowOut[q];
+        if (K.mode) D.ukey[m] = ckey;
+        if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, 0.0, 0.0, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
+        else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], o[2], n[2], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
+    }
+}
+// small complexes (the bulk of an oligomerised membrane: 2-12 members): one THREAD per complex. The alignment is a serial,
+// branchy algorithm; a warp per complex leaves 31 of 32 lanes idle in it, a thread per complex runs 32 of them per warp.
+__global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    // two lists back to back: single-ligand complexes, padded to a whole number of warps, then the multi-ligand ones
+    const int n1 = D.scal[S_NCX], n1pad = (n1 + 31) & ~31, ncx = n1pad + D.scal[S_NCX_MULTI];
+    const uint64_t step = D.step64[0];
+    const unsigned stamp = (unsigned)D.scal[S_EPOCH];
+    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < ncx; ci += gridDim.x * blockDim.x) {
+        if (ci >= n1 && ci < n1pad) continue;
+        const int h0 = ci < n1 ? D.cxRoots[ci] : D.cxRoots[K.NBt + ci - n1pad], rootGid = K.NAt + h0;
+        const int size = D.cxSize[h0];
+        const int *rowIn = D.members + D.cxOff[h0];
+        int nB = 0;
+        for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;
+        const uint64_t seed = seed_of(cK, h0 / K.NB);
+        const uint32_t me = ref_id(K, D, rootGid);
+        double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
+        const double u2 = keyed_uniform(seed, me, 0, step, 2);
+        complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);
+        D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __grid_constant__ Args A) {
     KARGS
     __shared__ CxShared SH[CX_WARPS];
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const Consts &K = cK;
-    const int ncx = D.scal[S_NCX];
+    const int ncx = D.scal[S_NCX_BIG];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * CX_WARPS + wib, nwarps = gridDim.x * CX_WARPS;
     CxShared &S = SH[wib];
     for (int ci = warp; ci < ncx; ci += nwarps) {
-        const int h0 = D.cxRoots[ci], rootGid = K.NAt + h0;
+        const int h0 = D.cxRoots[K.NBt - 1 - ci], rootGid = K.NAt + h0;
         const int size = D.cxSize[h0];
         const int *rowIn = D.members + D.cxOff[h0];
         int *rowOut = D.rowWork + D.cxOff[h0];
@@ -741,44 +852,7 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                     const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], o[2], p[2], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f));
                 }
             }
-        } else if (lane == 0) {
-            // complex larger than the cache: the same steps by one lane on global memory (handles = gids)
-            CxGlobal C{D, K, K.NAt};
-            double PBx = 0, PBy = 0;
-            for (int i = 0; i < size; i++) {
-                const int m = rowIn[i]; rowOut[i] = m; D.movedFlag[m] = 0;
-                if (m < K.NAt) { Rec r = load_rec(D.recC, D.recS2, D.recS3, m); shift_pose(&r.cx, true, shx, shy, false); C.put(m, r); PBx = add(PBx, r.cx); PBy = add(PBy, r.cy); }
-                else { Lig l; load_lig(D.lig, m - K.NAt, l); shift_pose(&l.p[0][0], false, shx, shy, false); C.put(m, l); PBx = add(PBx, l.p[0][0]); PBy = add(PBy, l.p[0][1]); }
-            }
-            PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
-            PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
-            double cmx = 0, cmy = 0, cmz = 0;
-            for (int i = 0; i < size; i++) {
-                const int m = rowOut[i];
-                if (m < K.NAt) {
-                    Rec r = C.rec(m); shift_pose(&r.cx, true, PBx, PBy, true); C.put(m, r);
-                    for (int j = 1; j <= 4; j++) { cmx = add(cmx, r.cx); cmy = add(cmy, r.cy); cmz = add(cmz, rec_bead_z(K, j)); }
-                } else {
-                    Lig l; C.lig(m, l); shift_pose(&l.p[0][0], false, PBx, PBy, true); C.put(m, l);
-                    for (int q = 0; q < 4; q++) { cmx = add(cmx, l.p[q][0]); cmy = add(cmy, l.p[q][1]); cmz = add(cmz, l.p[q][2]); }
-                }
-            }
-            const double nbeads = (double)(4 * nA + 4 * nB);
-            cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
-            for (int i = 0; i < size; i++) {
-                const int m = rowOut[i];
-                if (m < K.NAt) { Rec r = C.rec(m); rotate_pose(&r.cx, true, cs, ss, cmx, cmy, cmz); C.put(m, r); }
-                else { Lig l; C.lig(m, l); rotate_pose(&l.p[0][0], false, cs, ss, cmx, cmy, cmz); C.put(m, l); }
-            }
-            align_complex(C, rowOut, size, nB, rootGid, seed, me, step);
-            const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
-            for (int q = 0; q < size; q++) {
-                const int m = rowOut[q];
-                if (K.mode) D.ukey[m] = ckey;
-                if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, 0.0, 0.0, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
-                else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], o[2], n[2], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
-            }
-        }
+        } else if (lane == 0) complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);      // larger than the cache
         if (lane == 0) { D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0; }
         __syncwarp();
     }

@@ -370,7 +370,7 @@ struct StripDev {
 
 __global__ void k_strip_prebuild(const __grid_constant__ Args A) {
     KARGS
-    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; }
+    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.scal[S_NCX_BIG] = 0; D.scal[S_NCX_MULTI] = 0; }
 }
 // by-product 1 (before the complexes are rebuilt: the tables are those of the last step's sweep, like kmc_get_series /
 // kmc_get_oligomer_hist on one GPU): complexes rooted at a ligand this rank owns -- owner = strip of the root's centre
@@ -585,36 +585,64 @@ __global__ void k_strip_refs(const __grid_constant__ Args A, MergeIn M) {
         i -= nl;
     }
 }
-__global__ void k_strip_merge(const __grid_constant__ Args A, MergeIn M) {
+// lower bound of `ref` in the sorted array c[0..n) for all lanes of a warp whose refs ascend with the lane (sorted molecules):
+// the bounds of the first and the last live lane are found by two warp-uniform binary searches (every lane probes the same
+// address: one broadcast load per step), each lane then searches only the few entries between them
+__device__ __forceinline__ int warp_lower_bound(const int *c, int n, int ref, unsigned live) {
+    if (!live) return 0;
+    const int first = __ffs(live) - 1, last = 31 - __clz(live);
+    const int lo0 = d_lower_bound_i(c, n, __shfl_sync(0xffffffffu, ref, first));
+    int hi = d_lower_bound_i(c, n, __shfl_sync(0xffffffffu, ref, last));
+    int lo = lo0;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c[mid] < ref) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+#define MERGE_B 128
+__global__ void __launch_bounds__(MERGE_B) k_strip_merge(const __grid_constant__ Args A, MergeIn M, int nbA, int nbB) {
     KARGS
     const Consts &K = cK;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     int nr[2], nl[2], keptR, keptL;
-    if (!merge_counts(K, M, nr, nl, keptR, keptL)) { if (i == 0) atomicOr(&D.scal[S_OVERFLOW], 128); return; }      // a message or the local capacity is too small
+    if (!merge_counts(K, M, nr, nl, keptR, keptL)) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&D.scal[S_OVERFLOW], 128); return; }      // a message or the local capacity is too small
     const int nAold = nA_live(D), nBold = nB_live(D);
     const int *cR[2] = {M.cref, M.cref + K.NAt}, *cL[2] = {M.cref + 2 * K.NAt, M.cref + 2 * K.NAt + K.NBt};
-    if (i < K.NT) {                                               // a molecule that stays
-        if (!(i < K.NAt ? i < nAold : i - K.NAt < nBold) || !(M.flag[i] & 1)) return;
-        if (i < K.NAt) {
-            const int ref = (int)D.refA[i];
-            const int pos = M.keptRank[i] + d_lower_bound_i(cR[0], nr[0], ref) + d_lower_bound_i(cR[1], nr[1], ref);
-            D.recCn[pos] = D.recC[i]; D.recS2n[pos] = D.recS2[i]; D.recS3n[pos] = D.recS3[i];
-            M.refA2[pos] = (unsigned)ref; M.ownFlag[pos] = 1;
-            const int l = D.recLig[i], c = D.recCis[i];
-            M.bond[pos * 3] = l >= 0 ? (int)D.refB[l] : 0; M.bond[pos * 3 + 1] = c >= 0 ? (int)D.refA[c] : 0; M.bond[pos * 3 + 2] = D.recSite[i];
-        } else {
-            const int b = i - K.NAt, ref = (int)D.refB[b];
-            const int pos = M.keptRank[i] + d_lower_bound_i(cL[0], nl[0], ref) + d_lower_bound_i(cL[1], nl[1], ref);
-            const double2 *src = reinterpret_cast<const double2 *>(D.lig + (size_t)b * 24);
-            double2 *dst = reinterpret_cast<double2 *>(D.lign + (size_t)pos * 24);
-#pragma unroll
-            for (int q = 0; q < 12; q++) dst[q] = src[q];
-            M.refB2[pos] = (unsigned)ref; M.ownFlag[K.NAt + pos] = 1;
-            for (int q = 0; q < 3; q++) { const int r = D.ligRec[b * 3 + q]; M.bond[3 * K.NAt + pos * 3 + q] = r >= 0 ? (int)D.refA[r] : 0; }
-        }
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x < nbA) {                                  // receptors that stay
+        const int a = blockIdx.x * MERGE_B + threadIdx.x;
+        const bool live = a < nAold;
+        const int ref = live ? (int)D.refA[a] : 0x7fffffff;
+        const unsigned lm = __ballot_sync(0xffffffffu, live);
+        const int o0 = warp_lower_bound(cR[0], nr[0], ref, lm), o1 = warp_lower_bound(cR[1], nr[1], ref, lm);
+        if (!live || !(M.flag[a] & 1)) return;
+        const int pos = M.keptRank[a] + o0 + o1;
+        D.recCn[pos] = D.recC[a]; D.recS2n[pos] = D.recS2[a]; D.recS3n[pos] = D.recS3[a];
+        M.refA2[pos] = (unsigned)ref; M.ownFlag[pos] = 1;
+        const int l = D.recLig[a], c = D.recCis[a];
+        M.bond[pos * 3] = l >= 0 ? (int)D.refB[l] : 0; M.bond[pos * 3 + 1] = c >= 0 ? (int)D.refA[c] : 0; M.bond[pos * 3 + 2] = D.recSite[a];
         return;
     }
-    i -= K.NT;                                                    // an incoming record
+    if ((int)blockIdx.x < nbA + nbB) {                            // ligands that stay: the 192-byte poses are copied by the whole warp, 16 bytes per lane
+        const int b = (blockIdx.x - nbA) * MERGE_B + threadIdx.x;
+        const bool live = b < nBold;
+        const int ref = live ? (int)D.refB[b] : 0x7fffffff;
+        const unsigned lm = __ballot_sync(0xffffffffu, live);
+        const int o0 = warp_lower_bound(cL[0], nl[0], ref, lm), o1 = warp_lower_bound(cL[1], nl[1], ref, lm);
+        const bool keep = live && (M.flag[K.NAt + b] & 1);
+        const int pos = keep ? M.keptRank[K.NAt + b] + o0 + o1 : -1;
+        const int b0 = b - lane;
+        const double2 *src = reinterpret_cast<const double2 *>(D.lig) + (size_t)b0 * 12;
+        double2 *dst = reinterpret_cast<double2 *>(D.lign);
+#pragma unroll
+        for (int it = 0; it < 12; it++) {
+            const int ch = it * 32 + lane, l = ch / 12, q = ch - l * 12;
+            const int dp = __shfl_sync(0xffffffffu, pos, l);
+            if (dp >= 0) dst[(size_t)dp * 12 + q] = src[ch];
+        }
+        if (!keep) return;
+        M.refB2[pos] = (unsigned)ref; M.ownFlag[K.NAt + pos] = 1;
+        for (int q = 0; q < 3; q++) { const int r = D.ligRec[b * 3 + q]; M.bond[3 * K.NAt + pos * 3 + q] = r >= 0 ? (int)D.refA[r] : 0; }
+        return;
+    }
+    int i = (blockIdx.x - nbA - nbB) * MERGE_B + threadIdx.x;     // an incoming record
     if (i < nr[0] + nr[1]) {
         const int k = i < nr[0] ? 0 : 1; if (k) i -= nr[0];
         const RecMsg m = reinterpret_cast<const RecMsg *>(M.base[k] + MSG_HDR)[i];
@@ -759,7 +787,8 @@ static int strip_merge(kmc_handle *h, const char *fromLow, const char *fromHigh)
     MergeIn M; M.base[0] = fromLow; M.base[1] = fromHigh; M.cref = S.cref; M.dcnt = S.dcnt; M.keptRank = S.keptRank; M.flag = S.flag;
     M.refA2 = S.refA2; M.refB2 = S.refB2; M.ownFlag = S.ownFlag; M.bond = S.bondRef;
     k_strip_refs<<<nblk(std::max(h->NT, 1), 256), 256, 0, st>>>(A, M);
-    k_strip_merge<<<nblk(std::max(2 * h->NT, 1), 128), 128, 0, st>>>(A, M);
+    const int nbA = nblk(std::max(h->NAt, 1), MERGE_B), nbB = nblk(std::max(h->NBt, 1), MERGE_B);
+    k_strip_merge<<<nbA + nbB + nblk(std::max(h->NT, 1), MERGE_B), MERGE_B, 0, st>>>(A, M, nbA, nbB);
     k_strip_fix_bonds<<<nblk(std::max(h->NT, 1), 128), 128, 0, st>>>(A, M);
     CK(cudaGetLastError());
     swap_buffers(h->D); h->parity ^= 1;          // the merged poses were written into the "next" buffers
@@ -798,6 +827,21 @@ extern "C" int kmc_strip_comm_init(kmc_handle *h, const void *id128, int32_t ref
     if (v[0] != -v[1]) { h->err = "kmc_strip_comm_init: ranks were created with different capacities (band messages must have one size)"; return KMC_ERR_INVALID; }
     h->strip_every = refresh_every; h->strip_since = 0;
     if (refresh_every > 0) S.budget = h->strip_W - refresh_every * strip_reach_per_step(h->K);
+    if (getenv("KMC_STRIP_TIMING") && h->K.strips > 1) {          // diagnostics: the band exchange alone, CUDA events
+        const int n = h->K.strips, r = h->K.stripRank, lo = (r + n - 1) % n, hi = (r + 1) % n;
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        for (int it = 0; it < 12; it++) {
+            if (it == 2) cudaEventRecord(a, h->stream);
+            NC(g_nccl.GroupStart());
+            NC(g_nccl.Send(S.msg[0], S.bandCap, ncclChar, lo, S.comm, h->stream)); NC(g_nccl.Send(S.msg[1], S.bandCap, ncclChar, hi, S.comm, h->stream));
+            NC(g_nccl.Recv(S.rcv[1], S.bandCap, ncclChar, hi, S.comm, h->stream)); NC(g_nccl.Recv(S.rcv[0], S.bandCap, ncclChar, lo, S.comm, h->stream));
+            NC(g_nccl.GroupEnd());
+        }
+        cudaEventRecord(b, h->stream); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (r == 0) fprintf(stderr, "band exchange alone: %.1f us per round (2 x %zu bytes each way)\n", 1e3 * ms / 10, S.bandCap);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
     return KMC_OK;
 }
 // The refresh over NCCL: pack -> one grouped send/recv round with the two x-neighbours -> merge, all on the handle's stream.
