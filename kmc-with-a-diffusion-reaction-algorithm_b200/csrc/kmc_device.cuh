@@ -22,6 +22,7 @@ enum Scalar {
     S_NSPEC_MAX,          // largest S_NSPEC of any step so far (the host decides the list-reuse back-off from it)
     S_NCX_BIG,            // complexes with more than CX_SMALL members: listed from the END of the first half of cxRoots[] (one warp each)
     S_NCX_MULTI,          // small complexes with several ligands: listed in the second half of cxRoots[] (S_NCX counts the single-ligand ones)
+    S_NTOUCH,             // endpoints of the bonds formed / broken in the last step's S3 (touchList): their complexes are updated incrementally
     S_COUNT = 24
 };
 enum UnitState : unsigned char { U_UNKNOWN = 0, U_ACCEPT = 1, U_REJECT = 2 };
@@ -45,6 +46,10 @@ struct Dev {
     int *cxSize, *cxOff, *cxRoots;         // per root ligand: members, offset into members[]; list of roots with size>1
     int *members, *rowWork;                // member gids in BFS order / working copy permuted by the shuffles
     int *bfsMark;
+    int *cxStamp;                          // [NT] incremental update: visited stamp (step epoch)
+    int *rootSlot;                         // [NBt] where a root ligand sits in the work lists of cxRoots: (list << 28) | position, -1 = not listed
+    int *touchList;                        // [TOUCH_CAP] molecules whose bonds changed in the last S3
+    int *bfsQueue;                         // [NT] scratch of the (single-threaded) incremental update
     int *rowPos;                           // [NT] position of a complex member in its breadth-first member list
     unsigned char *movedFlag;
     double *nrec;                          // [NT][6] neighbour record per molecule: centre old xy, new xy, {old z (fp32), unit key, flags, new z (fp32)}
@@ -79,6 +84,13 @@ struct Dev {
 };
 
 #define GHOST_BIT 0x40000000
+#define TOUCH_CAP 256
+// a bond of molecule gid changed: its complex is re-derived at the start of the next step (k_step_begin); beyond TOUCH_CAP
+// changes per step the whole table is rebuilt instead
+KD void touch_molecule(const Dev &D, int gid) {
+    const int i = atomicAdd(&D.scal[S_NTOUCH], 1);
+    if (i < TOUCH_CAP) D.touchList[i] = gid; else D.scal[S_TOPO_DIRTY] = 1;
+}
 
 KD Rec load_rec(const double2 *C, const double2 *S2, const double2 *S3, int a) {
     double2 c = C[a], s2 = S2[a], s3 = S3[a];

@@ -3,7 +3,7 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 20
+#define KMC_NKERNELS 21
 #define MON_EVERY 256
 
 #include <algorithm>
@@ -79,10 +79,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small"};
+    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small", "k_step_begin"};
 enum { KID_UF_INIT = 0, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
-       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL };
+       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL, KID_STEP_BEGIN };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -293,6 +293,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(ufParent, K.NT); A(unitOf, K.NT);
     if (K.mode == KMC_MODE_PRODUCTION) { A(ukey, K.NT); } else D.ukey = D.unitOf; A(cxSize, K.NBt); A(cxOff, K.NBt); A(cxRoots, (size_t)2 * K.NBt);
     A(members, K.NT); A(rowWork, K.NT); A(bfsMark, K.NT); A(rowPos, K.NT);
+    A(cxStamp, K.NT); A(rootSlot, K.NBt); A(touchList, TOUCH_CAP); A(bfsQueue, K.NT);
     A(movedFlag, K.NT); A(nrec, (size_t)6 * K.NT);
     h->scanBlocks = (D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
     A(cellCount, (size_t)h->scanBlocks * SCAN_TILE); A(cellStart, (size_t)h->scanBlocks * SCAN_TILE);
@@ -313,6 +314,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     ok = cudaMemset(D.recLig, 0xff, sizeof(int) * K.NAt) == cudaSuccess && cudaMemset(D.recSite, 0xff, sizeof(int) * K.NAt) == cudaSuccess &&
          cudaMemset(D.recCis, 0xff, sizeof(int) * K.NAt) == cudaSuccess && cudaMemset(D.ligRec, 0xff, sizeof(int) * 3 * (size_t)K.NBt) == cudaSuccess;
     int one = 1;
+    ok = ok && cudaMemset(D.rootSlot, 0xff, sizeof(int) * (size_t)K.NBt) == cudaSuccess;
     ok = ok && cudaMemcpy(D.scal + S_TOPO_DIRTY, &one, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(D.scal + S_NA_LIVE, &K.NAt, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(D.scal + S_NB_LIVE, &K.NBt, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -534,8 +536,10 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const Dev &D = A.D;
     const int B = 128, NT = h->NT, NAt = h->NAt, NBt = h->NBt;
     const bool build = A.K.phase == 0;
-    // step begin (one thread) + S1 (gated on a device flag)
-    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A, 1)));
+    // step begin + S1: incremental update of the complexes the last step's reactions touched (one thread); the parallel rebuild of
+    // the whole table is gated on a device flag (state loaded, strip refresh, too many changes at once)
+    LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 32, 0, st>>>(A, 1)));
+    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
     LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
@@ -656,6 +660,8 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
         if (++h->epoch >= 0xfffffff0u) {         // the stamp of the per-cell chains is about to wrap: start a new era
             if (h->D.cellHead) CK(cudaMemsetAsync(h->D.cellHead, 0, sizeof(unsigned long long) * (size_t)h->cellHeadCap, st));
             CK(cudaMemsetAsync(h->D.scal + S_EPOCH, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(h->D.cxStamp, 0, sizeof(int) * (size_t)h->NT, st));          // (the stamps of the incremental complex update restart too:
+            CK(cudaMemsetAsync(h->D.scal + S_TOPO_DIRTY, 1, 1, st));                         //  one full rebuild clears the marks)
             h->epoch = 1;
         }
         if (h->profiling || !h->use_graph) {

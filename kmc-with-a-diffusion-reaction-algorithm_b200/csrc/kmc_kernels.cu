@@ -52,22 +52,125 @@ KD void uf_union(int *parent, int a, int b) {
     }
 }
 
-// first kernel of a step when `begin` is set: one thread also advances the device-side step counter and resets the per-step
-// scalars (none of them is read by this kernel's other threads)
-__global__ void k_uf_init(const __grid_constant__ Args A, int begin) {
+// ---- work lists of the complex proposal kernels (cxRoots), by kind so that the threads of a warp run the same code path:
+// list 0: small complexes (<= CX_SMALL members, one THREAD each) with ONE ligand (S2e), front of cxRoots;
+// list 1: small complexes with several ligands (S2f: shuffles, passes), second half of cxRoots;
+// list 2: large complexes (one warp each), from the back of the first half. rootSlot[h] remembers where root h is listed.
+KD int *root_list_entry(const Consts &K, const Dev &D, int list, int pos) {
+    return list == 0 ? &D.cxRoots[pos] : (list == 1 ? &D.cxRoots[K.NBt + pos] : &D.cxRoots[K.NBt - 1 - pos]);
+}
+KD int root_list_counter(int list) { return list == 0 ? S_NCX : (list == 1 ? S_NCX_MULTI : S_NCX_BIG); }
+KD void root_list_add(const Consts &K, const Dev &D, int h, int size, int nlig) {        // (atomic: the parallel rebuild appends concurrently)
+    const int list = size > CX_SMALL ? 2 : (nlig == 1 ? 0 : 1);
+    const int pos = atomicAdd(&D.scal[root_list_counter(list)], 1);
+    *root_list_entry(K, D, list, pos) = h;
+    D.rootSlot[h] = (list << 28) | pos;
+}
+KD void root_list_remove(const Consts &K, const Dev &D, int h) {                         // single-threaded (incremental update)
+    const int slot = D.rootSlot[h];
+    if (slot < 0) return;
+    const int list = slot >> 28, pos = slot & 0x0fffffff;
+    const int last = --D.scal[root_list_counter(list)];
+    if (pos != last) { const int h2 = *root_list_entry(K, D, list, last); *root_list_entry(K, D, list, pos) = h2; D.rootSlot[h2] = (list << 28) | pos; }
+    D.rootSlot[h] = -1;
+}
+// neighbours in the bond graph in the reference's order (main.cpp:543-551): receptor -> its ligand, its cis partner; ligand -> sites 2,3,4
+KD int bond_neighbours(const Consts &K, const Dev &D, int m, int cand[3]) {
+    int nc = 0;
+    if (m < K.NAt) {
+        if (D.recLig[m] >= 0) cand[nc++] = K.NAt + D.recLig[m];
+        if (D.recCis[m] >= 0) cand[nc++] = D.recCis[m];
+    } else {
+        const int hh = m - K.NAt;
+        for (int s = 0; s < 3; s++) if (D.ligRec[hh * 3 + s] >= 0) cand[nc++] = D.ligRec[hh * 3 + s];
+    }
+    return nc;
+}
+// breadth-first member row of the complex rooted at ligand h (main.cpp:528-560), `mark` = value that flags a visited molecule
+KD void build_member_row(const Consts &K, const Dev &D, int h, int size, int *row, int mark, int &nlig) {
+    int head = 0, tail = 0;
+    row[tail++] = K.NAt + h; D.bfsMark[K.NAt + h] = mark; D.rowPos[K.NAt + h] = 0;
+    nlig = 0;
+    while (head < tail) {
+        const int m = row[head++];
+        nlig += m >= K.NAt;
+        int cand[3]; const int nc = bond_neighbours(K, D, m, cand);
+        for (int c = 0; c < nc; c++)
+            if (D.bfsMark[cand[c]] != mark) { D.bfsMark[cand[c]] = mark; if (tail < size) { D.rowPos[cand[c]] = tail; row[tail++] = cand[c]; } }
+    }
+}
+KD void note_max_complex(const Consts &K, const Dev &D, int h, int size) {
+    // main.cpp:896-898 (read first: one hot address). With strips only the rank that owns the root counts it: a halo copy in the
+    // outer (possibly stale) part of the halo may show a complex the true trajectory never had
+    if (size > D.maxComplex[h / K.NB] && (K.strips <= 1 || d_strip_owner(K, D.lig[(size_t)h * 24]) == K.stripRank)) atomicMax(&D.maxComplex[h / K.NB], size);
+}
+
+// First kernel of a step (one warp; begin = 0: only the complex tables, for the strip refresh). Lane 0
+//  (1) advances the device-side step counter and resets the per-step scalars;
+//  (2) S1, incrementally: the bond table changed only at the few molecules S3 of the last step touched (touchList). Their
+//      connected components are re-derived here -- unit heads, sizes, breadth-first member rows (main.cpp:514-562), work lists --
+//      and everything else stands. Only when the table changed wholesale (state loaded, strip refresh, more than TOUCH_CAP changes
+//      in one step, member storage exhausted) S_TOPO_DIRTY is set and the parallel rebuild kernels below run their bodies.
+__global__ void k_step_begin(const __grid_constant__ Args A, int begin) {
     KARGS
-    if (begin && blockIdx.x == 0 && threadIdx.x == 0) {
+    const Consts &K = cK;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (begin) {
         D.step64[0] += 1; D.scal[S_EPOCH] += 1;
         if (D.scal[S_NSPEC] > D.scal[S_NSPEC_MAX]) D.scal[S_NSPEC_MAX] = D.scal[S_NSPEC];
         D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0;
         if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
-        if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.scal[S_NCX_BIG] = 0; D.scal[S_NCX_MULTI] = 0; D.events[EV_REBUILDS] += 1; }
     }
-    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
+    const int nt = D.scal[S_NTOUCH];
+    D.scal[S_NTOUCH] = 0;
+    if (!D.scal[S_TOPO_DIRTY] && nt > 0) {
+        const int stamp = 2 + (D.scal[S_EPOCH] & 0x3fffffff) * 2 + (begin ? 0 : 1);          // never 0 / 1 (the parallel rebuild's marks), unique per pass
+        int *Q = D.bfsQueue;
+        for (int ti = 0; ti < min(nt, TOUCH_CAP) && !D.scal[S_TOPO_DIRTY]; ti++) {
+            const int t = D.touchList[ti];
+            if (D.cxStamp[t] == stamp) continue;
+            // the connected component of t (any order) and its lowest-index ligand
+            int qn = 0, minLig = 0x7fffffff, minRec = 0x7fffffff;
+            Q[qn++] = t; D.cxStamp[t] = stamp;
+            for (int qi = 0; qi < qn; qi++) {
+                const int m = Q[qi];
+                if (m >= K.NAt) minLig = min(minLig, m); else minRec = min(minRec, m);
+                int cand[3]; const int nc = bond_neighbours(K, D, m, cand);
+                for (int c = 0; c < nc; c++) if (D.cxStamp[cand[c]] != stamp) { D.cxStamp[cand[c]] = stamp; Q[qn++] = cand[c]; }
+            }
+            // the ligands of the component lose their old table entries and listings. (The root a member belonged to before is a
+            // ligand of this component or of a sibling piece of a split; every piece holds an end of a changed bond, so it is
+            // re-derived in this same pass -- and must not be unlisted again once a sibling has listed it afresh.)
+            for (int qi = 0; qi < qn; qi++) {
+                const int m = Q[qi];
+                if (m >= K.NAt) { root_list_remove(K, D, m - K.NAt); D.cxSize[m - K.NAt] = 0; D.cxOff[m - K.NAt] = -1; }
+            }
+            if (minLig == 0x7fffffff) { for (int qi = 0; qi < qn; qi++) D.unitOf[Q[qi]] = minRec; continue; }      // ligand-free unit: receptor / cis pair
+            const int h = minLig - K.NAt, size = qn;
+            for (int qi = 0; qi < qn; qi++) D.unitOf[Q[qi]] = minLig;
+            D.cxSize[h] = size;
+            note_max_complex(K, D, h, size);
+            if (size <= 1) continue;
+            const int off = D.scal[S_MEMBER_CURSOR];
+            if (off + size > K.NT) { D.scal[S_TOPO_DIRTY] = 1; break; }          // member storage exhausted (old rows are not reclaimed): compact by a full rebuild
+            D.scal[S_MEMBER_CURSOR] = off + size;
+            D.cxOff[h] = off;
+            int nlig; build_member_row(K, D, h, size, D.members + off, stamp, nlig);
+            for (int i = 0; i < size; i++) D.rowWork[off + i] = D.members[off + i];
+            root_list_add(K, D, h, size, nlig);
+        }
+        if (!D.scal[S_TOPO_DIRTY]) D.events[EV_REBUILDS] += 1;
+    }
+    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.scal[S_NCX_BIG] = 0; D.scal[S_NCX_MULTI] = 0; D.events[EV_REBUILDS] += 1; }
+}
+// the parallel rebuild of the whole table (bodies run only when S_TOPO_DIRTY is set)
+__global__ void k_uf_init(const __grid_constant__ Args A) {
+    KARGS
+    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged / updated incrementally: the complexes stand
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cK.NT) return;
     D.ufParent[i] = i; D.bfsMark[i] = 0;          // (dead slots of a strip are harmless singletons)
-    if (i < cK.NBt) { D.cxSize[i] = 0; D.cxOff[i] = -1; }
+    if (i < cK.NBt) { D.cxSize[i] = 0; D.cxOff[i] = -1; D.rootSlot[i] = -1; }
 }
 // one thread per receptor: its ligand edge and (once per pair) its cis edge
 __global__ void k_uf_hook(const __grid_constant__ Args A) {
@@ -101,37 +204,12 @@ __global__ void k_cx_build(const __grid_constant__ Args A) {
     if (h >= nB_live(D)) return;
     if (D.unitOf[cK.NAt + h] != cK.NAt + h) return;
     int size = D.cxSize[h];
-    // main.cpp:896-898 (read first: one hot address). With strips only the rank that owns the root counts it: a halo copy in the
-    // outer (possibly stale) part of the halo may show a complex the true trajectory never had
-    if (size > D.maxComplex[h / cK.NB] && (cK.strips <= 1 || d_strip_owner(cK, D.lig[(size_t)h * 24]) == cK.stripRank)) atomicMax(&D.maxComplex[h / cK.NB], size);
+    note_max_complex(cK, D, h, size);
     if (size <= 1) return;
     int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
     D.cxOff[h] = off;
-    // (listed below, once the member row is known: the lists are sorted by kind)
-    int *row = D.members + off;
-    int head = 0, tail = 0;
-    row[tail++] = cK.NAt + h; D.bfsMark[cK.NAt + h] = 1; D.rowPos[cK.NAt + h] = 0;
-    while (head < tail) {
-        int m = row[head++];
-        int cand[3], nc = 0;
-        if (m < cK.NAt) {
-            if (D.recLig[m] >= 0) cand[nc++] = cK.NAt + D.recLig[m];
-            if (D.recCis[m] >= 0) cand[nc++] = D.recCis[m];
-        } else {
-            int hh = m - cK.NAt;
-            for (int s = 0; s < 3; s++) if (D.ligRec[hh * 3 + s] >= 0) cand[nc++] = D.ligRec[hh * 3 + s];
-        }
-        for (int c = 0; c < nc; c++)
-            if (!D.bfsMark[cand[c]]) { D.bfsMark[cand[c]] = 1; if (tail < size) { D.rowPos[cand[c]] = tail; row[tail++] = cand[c]; } }
-    }
-    // Work lists of the proposal kernels, by kind, so that the threads of a warp run the same code path: small complexes
-    // (one THREAD each, k_propose_complex_small) with ONE ligand (S2e) from the front of cxRoots, small ones with several ligands
-    // (S2f: shuffles, passes) in its second half; large complexes (one warp each, k_propose_complex) from the back of the first half
-    int nlig = 0;
-    for (int i = 0; i < size; i++) nlig += row[i] >= cK.NAt;
-    if (size > CX_SMALL) D.cxRoots[cK.NBt - 1 - atomicAdd(&D.scal[S_NCX_BIG], 1)] = h;
-    else if (nlig == 1) D.cxRoots[atomicAdd(&D.scal[S_NCX], 1)] = h;
-    else D.cxRoots[cK.NBt + atomicAdd(&D.scal[S_NCX_MULTI], 1)] = h;
+    int nlig; build_member_row(cK, D, h, size, D.members + off, 1, nlig);
+    root_list_add(cK, D, h, size, nlig);
 }
 
 // Order of the sweep. Every molecule carries the key of its unit: (colour << 30) | head gid. In replay mode the colour is 0,
@@ -1705,6 +1783,7 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
         int a = (int)(key >> 32), h = (int)((key & 0xffffffffULL) >> 2), s = (int)(key & 3);
         if (D.recLig[a] < 0 && D.ligRec[h * 3 + s] < 0) {
             D.recLig[a] = h; D.recSite[a] = s; D.ligRec[h * 3 + s] = a; ev_rl++;
+            touch_molecule(D, a);
         }
     }
     for (int variant = 1; variant <= 2; variant++)
@@ -1716,10 +1795,10 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
             bool anyLig = D.recLig[a] >= 0 || D.recLig[b] >= 0;
             if ((variant == 1) == anyLig) continue;      // variant 1: both ligand-free; variant 2: at least one bound
             D.recCis[a] = b; D.recCis[b] = a;
+            touch_molecule(D, a);
             if (variant == 1) ev_mono++; else ev_cis++;
         }
     if (ev_rl | ev_mono | ev_cis) {
-        D.scal[S_TOPO_DIRTY] = 1;
         D.events[EV_RL_ON] += ev_rl; D.events[EV_MONO_ON] += ev_mono; D.events[EV_CIS_ON] += ev_cis;
     }
 }
@@ -1764,7 +1843,7 @@ __global__ void k_finish(const __grid_constant__ Args A) {
         if (keyed_uniform(seed, me, 0, step, SLOT_RL_OFF) < K.pOff) {
             int s = D.recSite[a];
             D.recLig[a] = -1; D.recSite[a] = -1; D.ligRec[h * 3 + s] = -1;
-            atomicAdd(&D.events[EV_RL_OFF], 1ULL); D.scal[S_TOPO_DIRTY] = 1;
+            atomicAdd(&D.events[EV_RL_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, cK.NAt + h);
         } else boundAfter = true;
     }
     if (p > a) {
@@ -1777,7 +1856,7 @@ __global__ void k_finish(const __grid_constant__ Args A) {
         // drawn from both ends: the lower index first, the partner only if the bond survived
         if (keyed_uniform(seed, me, 0, step, slot) < P || keyed_uniform(seed, pid, 0, step, slot) < P) {
             D.recCis[a] = -1; D.recCis[p] = -1;
-            atomicAdd(&D.events[inComplex ? EV_CIS_OFF : EV_MONO_OFF], 1ULL); D.scal[S_TOPO_DIRTY] = 1;
+            atomicAdd(&D.events[inComplex ? EV_CIS_OFF : EV_MONO_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, p);
         }
     }
 }

@@ -368,10 +368,6 @@ struct StripDev {
     double budget = INFINITY;                 // largest x-extent of a unit the halo width covers (halo - refresh_every * reach per step)
 };
 
-__global__ void k_strip_prebuild(const __grid_constant__ Args A) {
-    KARGS
-    if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.scal[S_NCX_BIG] = 0; D.scal[S_NCX_MULTI] = 0; }
-}
 // by-product 1 (before the complexes are rebuilt: the tables are those of the last step's sweep, like kmc_get_series /
 // kmc_get_oligomer_hist on one GPU): complexes rooted at a ligand this rank owns -- owner = strip of the root's centre
 __global__ void k_strip_cx_owned(const __grid_constant__ Args A, int stepped, int *series, unsigned long long *hist) {
@@ -768,8 +764,8 @@ static int strip_pack(kmc_handle *h) {
     CK(cudaMemsetAsync(S.hist, 0, STRIP_HIST_BINS * sizeof(unsigned long long), st));
     k_strip_cx_owned<<<nblk(std::max(NBt, 1), 256), 256, 0, st>>>(A, h->stepped ? 1 : 0, S.series, S.hist);
     // complexes of the CURRENT bond table (the last step's reactions may have changed it)
-    LAUNCH(KID_UF_INIT, (k_strip_prebuild<<<1, 1, 0, st>>>(A)));
-    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A, 0)));
+    LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 32, 0, st>>>(A, 0)));
+    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
     LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
     LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
