@@ -61,6 +61,7 @@ struct kmc_handle {
     struct StripDev *strip_dev = nullptr;
     int64_t launches = 0, passes = 0;
     int init_rounds = 0;             // rounds the GPU generator needed (diagnostics)
+    int cxBlocks = 0;                // grid of the cooperative rebuild kernel
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
@@ -77,7 +78,7 @@ struct kmc_handle {
 };
 
 static const char *const g_kernel_names[KMC_NKERNELS] = {
-    "k_uf_init", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
+    "k_cx_rebuild", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
     "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small", "k_step_begin"};
 enum { KID_UF_INIT = 0, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
@@ -530,6 +531,16 @@ extern "C" int kmc_set_packed(kmc_handle *h, const double *rec_pose, const doubl
 // the sweep
 // ------------------------------------------------------------------------------------------------
 
+// the gated parallel rebuild of the complex tables: one cooperative launch (grid = what fits on the device at once)
+static void launch_cx_rebuild(kmc_handle *h, const Args &A, cudaStream_t st) {
+    if (h->cxBlocks == 0) {
+        int per = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_cx_rebuild, 256, 0);
+        h->cxBlocks = std::max(1, std::min(per, 4)) * h->nSM;
+    }
+    void *args[] = {(void *)&A};
+    LAUNCH(KID_UF_INIT, (cudaLaunchCooperativeKernel((const void *)k_cx_rebuild, dim3(h->cxBlocks), dim3(256), args, 0, st)));
+}
 // all launches of one time step (main.cpp:461-2202) on stream st; no host synchronisation anywhere.
 // A.K.phase: 0 = the step rebuilds the neighbour grid (and, on the sparse path, the pair list), 1 = it reuses them.
 static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
@@ -539,10 +550,7 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     // step begin + S1: incremental update of the complexes the last step's reactions touched (one thread); the parallel rebuild of
     // the whole table is gated on a device flag (state loaded, strip refresh, too many changes at once)
     LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 32, 0, st>>>(A, 1)));
-    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
+    launch_cx_rebuild(h, A, st);
     // S2 proposals: free receptors / cis dimers, free ligands and complexes are disjoint sets of molecules -- three kernels side
     // by side (forked branches of the graph; on one stream when per-kernel timing is on)
     const int forkMask = h->profiling ? 0 : h->forkMask;     // bit0: receptor/ligand proposals side by side (measured slower than back to back), bit1: special entries, bit2: complexes

@@ -16,6 +16,7 @@
 // its accept/reject decision depends on earlier units only through their (rare) rejections, and is
 // resolved by a monotone fixed point over the recorded findings: a unit is decided as soon as every earlier unit it touches is.
 #include "kmc_device.cuh"
+#include <cooperative_groups.h>
 #include <cuda_pipeline.h>
 #define REC_TILE 256
 #ifndef CX_SMALL
@@ -163,53 +164,50 @@ __global__ void k_step_begin(const __grid_constant__ Args A, int begin) {
     }
     if (D.scal[S_TOPO_DIRTY]) { D.scal[S_MEMBER_CURSOR] = 0; D.scal[S_NCX] = 0; D.scal[S_NCX_BIG] = 0; D.scal[S_NCX_MULTI] = 0; D.events[EV_REBUILDS] += 1; }
 }
-// the parallel rebuild of the whole table (bodies run only when S_TOPO_DIRTY is set)
-__global__ void k_uf_init(const __grid_constant__ Args A) {
+// The parallel rebuild of the whole table: ONE cooperative kernel (grid-wide barriers between its four phases), a single graph
+// node that returns at once unless S_TOPO_DIRTY is set (a state was loaded, a strip refresh renumbered the molecules, more than
+// TOUCH_CAP bonds changed in one step, the member storage needs compacting).
+//   init: every molecule its own set; hook: one thread per receptor, its ligand edge and (once per pair) its cis edge; flatten:
+//   unit heads and component sizes; build: one thread per root ligand, breadth-first member order exactly as main.cpp:528-560
+__global__ void __launch_bounds__(256) k_cx_rebuild(const __grid_constant__ Args A) {
     KARGS
-    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged / updated incrementally: the complexes stand
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cK.NT) return;
-    D.ufParent[i] = i; D.bfsMark[i] = 0;          // (dead slots of a strip are harmless singletons)
-    if (i < cK.NBt) { D.cxSize[i] = 0; D.cxOff[i] = -1; D.rootSlot[i] = -1; }
-}
-// one thread per receptor: its ligand edge and (once per pair) its cis edge
-__global__ void k_uf_hook(const __grid_constant__ Args A) {
-    KARGS
-    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= nA_live(D)) return;
-    int ua = cK.NBt + a;
-    int l = D.recLig[a];
-    if (l >= 0) uf_union(D.ufParent, ua, l);
-    int c = D.recCis[a];
-    if (c > a) uf_union(D.ufParent, ua, cK.NBt + c);
-}
-__global__ void k_uf_flatten(const __grid_constant__ Args A) {
-    KARGS
-    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
-    int i = blockIdx.x * blockDim.x + threadIdx.x;   // uid
-    if (i >= cK.NT || !(i < cK.NBt ? i < nB_live(D) : i - cK.NBt < nA_live(D))) return;
-    int r = uf_find(D.ufParent, i);
-    int gid = i < cK.NBt ? cK.NAt + i : i - cK.NBt;
-    int head = r < cK.NBt ? cK.NAt + r : r - cK.NBt;
-    D.unitOf[gid] = head;
-    if (r < cK.NBt) atomicAdd(&D.cxSize[r], 1);
-}
-// one thread per root ligand: breadth-first member order exactly as main.cpp:528-560
-// (receptor neighbours: its ligand then its cis partner; ligand neighbours: sites 2,3,4)
-__global__ void k_cx_build(const __grid_constant__ Args A) {
-    KARGS
-    if (!D.scal[S_TOPO_DIRTY]) return;          // bond table unchanged: complexes of the previous step stand
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nB_live(D)) return;
-    if (D.unitOf[cK.NAt + h] != cK.NAt + h) return;
-    int size = D.cxSize[h];
-    note_max_complex(cK, D, h, size);
-    if (size <= 1) return;
-    int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
-    D.cxOff[h] = off;
-    int nlig; build_member_row(cK, D, h, size, D.members + off, 1, nlig);
-    root_list_add(cK, D, h, size, nlig);
+    if (!D.scal[S_TOPO_DIRTY]) return;          // (uniform over the grid: nobody reaches a barrier)
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int nA = nA_live(D), nB = nB_live(D);
+    for (int i = tid; i < cK.NT; i += nth) {
+        D.ufParent[i] = i; D.bfsMark[i] = 0;          // (dead slots of a strip are harmless singletons)
+        if (i < cK.NBt) { D.cxSize[i] = 0; D.cxOff[i] = -1; D.rootSlot[i] = -1; }
+    }
+    grid.sync();
+    for (int a = tid; a < nA; a += nth) {
+        const int ua = cK.NBt + a;
+        const int l = D.recLig[a];
+        if (l >= 0) uf_union(D.ufParent, ua, l);
+        const int c = D.recCis[a];
+        if (c > a) uf_union(D.ufParent, ua, cK.NBt + c);
+    }
+    grid.sync();
+    for (int i = tid; i < cK.NT; i += nth) {          // uid
+        if (!(i < cK.NBt ? i < nB : i - cK.NBt < nA)) continue;
+        const int r = uf_find(D.ufParent, i);
+        const int gid = i < cK.NBt ? cK.NAt + i : i - cK.NBt;
+        const int head = r < cK.NBt ? cK.NAt + r : r - cK.NBt;
+        D.unitOf[gid] = head;
+        if (r < cK.NBt) atomicAdd(&D.cxSize[r], 1);
+    }
+    grid.sync();
+    for (int h = tid; h < nB; h += nth) {
+        if (D.unitOf[cK.NAt + h] != cK.NAt + h) continue;
+        const int size = D.cxSize[h];
+        note_max_complex(cK, D, h, size);
+        if (size <= 1) continue;
+        const int off = atomicAdd(&D.scal[S_MEMBER_CURSOR], size);
+        D.cxOff[h] = off;
+        int nlig; build_member_row(cK, D, h, size, D.members + off, 1, nlig);
+        for (int i = 0; i < size; i++) D.rowWork[off + i] = D.members[off + i];       // (single-ligand complexes never permute their row)
+        root_list_add(cK, D, h, size, nlig);
+    }
 }
 
 // Order of the sweep. Every molecule carries the key of its unit: (colour << 30) | head gid. In replay mode the colour is 0,
@@ -816,6 +814,85 @@ __device__ __noinline__ void complex_move_serial(const Args &A, int h0, int size
         else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], o[2], n[2], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
     }
 }
+// Single-ligand complex (S2d + S2e), the commonest kind: ligand h0, the receptors on its sites and their ligand-free cis partners
+// (a cis partner with a ligand of its own would make it a multi-ligand complex). The topology fixes the breadth-first member row --
+// [ligand, receptors in site order, their partners in the same order] (main.cpp:528-560) -- so nothing has to be walked: the ligand
+// and the bond words are requested at once, then the receptors, then the partners: three dependent rounds of loads instead of one
+// per member and pass. Arithmetic and its order are those of complex_move_serial / align_complex. Returns false (nothing written)
+// if the complex is not of this shape.
+KD bool single_ligand_move(const Args &A, int h0, int size, uint64_t step, unsigned stamp, double u0, double u1, double u2) {
+    KARGS
+    const Consts &K = cK;
+    const int rootGid = K.NAt + h0;
+    Lig L; load_lig(D.lig, h0, L);
+    int a[3], p[3];
+    for (int s = 0; s < 3; s++) a[s] = D.ligRec[h0 * 3 + s];
+    double2 ca[3], cp_[3];
+    for (int s = 0; s < 3; s++) { p[s] = -1; if (a[s] >= 0) { ca[s] = D.recC[a[s]]; p[s] = D.recCis[a[s]]; } }
+    int n = 1;
+    for (int s = 0; s < 3; s++) {
+        if (a[s] >= 0) n++;
+        if (p[s] >= 0) { n++; cp_[s] = D.recC[p[s]]; if (p[s] == a[0] || p[s] == a[1] || p[s] == a[2]) return false; }
+    }
+    if (n != size) return false;
+    const double ox = L.p[0][0], oy = L.p[0][1], oz = L.p[0][2];
+    const double amp = mul(K.ampBond, u0);
+    const double phai = mul(mul(u1, 2.0), K.pai);
+    double sp, cp; sincos(phai, &sp, &cp);
+    const double shx = mul(amp, cp), shy = mul(amp, sp);
+    const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotBond);
+    double ss, cs; sincos(psai, &ss, &cs);
+    // wrap centre and rotation centre: sums in row order (ligand, receptors, partners)
+    double PBx = add(0.0, add(ox, shx)), PBy = add(0.0, add(oy, shy));
+    for (int s = 0; s < 3; s++) if (a[s] >= 0) { PBx = add(PBx, add(ca[s].x, shx)); PBy = add(PBy, add(ca[s].y, shy)); }
+    for (int s = 0; s < 3; s++) if (p[s] >= 0) { PBx = add(PBx, add(cp_[s].x, shx)); PBy = add(PBy, add(cp_[s].y, shy)); }
+    PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)size), K.Lx)));
+    PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)size), K.Ly)));
+    double cmx = 0, cmy = 0, cmz = 0;
+    for (int q = 0; q < 4; q++) { cmx = add(cmx, sub(add(L.p[q][0], shx), PBx)); cmy = add(cmy, sub(add(L.p[q][1], shy), PBy)); cmz = add(cmz, L.p[q][2]); }
+    for (int pass = 0; pass < 2; pass++)
+        for (int s = 0; s < 3; s++) {
+            if ((pass ? p[s] : a[s]) < 0) continue;
+            const double2 c = pass ? cp_[s] : ca[s];
+            const double x = sub(add(c.x, shx), PBx), y = sub(add(c.y, shy), PBy);
+            for (int j = 1; j <= 4; j++) { cmx = add(cmx, x); cmy = add(cmy, y); cmz = add(cmz, rec_bead_z(K, j)); }
+        }
+    const double nbeads = (double)(4 * size);
+    cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
+    // the ligand: rigid move, then lay-down (main.cpp:1140-1189)
+    shift_pose(&L.p[0][0], false, shx, shy, false); shift_pose(&L.p[0][0], false, PBx, PBy, true); rotate_pose(&L.p[0][0], false, cs, ss, cmx, cmy, cmz);
+    if (L.p[4][2] != add(L.p[0][2], K.rB)) {
+        const double zA = rec_bead_z(K, 3);
+        for (int q = 0; q < 8; q++) L.p[q][2] = zA;
+        L.p[4][2] = add(zA, K.rB);
+        const double angle = add(atan2(sub(L.p[1][0], L.p[0][0]), sub(L.p[1][1], L.p[0][1])), K.pai);
+        seat_ligand(K, L, angle, L.p[0][0], L.p[0][1]);
+    }
+    store_lig(D.lign, h0, L);
+    const int ckey = unit_key(K, rootGid, ox, oy);
+    const bool freeSite = a[0] < 0 || a[1] < 0 || a[2] < 0;
+    mark_far(cK, D, rootGid, ox, oy, L.p[0][0], L.p[0][1], oz, L.p[0][2], ckey, freeSite ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[rootGid] : make_float2(0.f, 0.f));
+    if (K.mode) D.ukey[rootGid] = ckey;
+    // every receptor (rigid move, snap onto its site: 1196-1233), then its partner (rigid move, snap onto the receptor: 1237-1274)
+    for (int s = 0; s < 3; s++) {
+        if (a[s] < 0) continue;
+        Rec r = load_rec(D.recC, D.recS2, D.recS3, a[s]);
+        shift_pose(&r.cx, true, shx, shy, false); shift_pose(&r.cx, true, PBx, PBy, true); rotate_pose(&r.cx, true, cs, ss, cmx, cmy, cmz);
+        if (rl_misaligned(K, L, s, r)) snap_rec_to_lig(K, r, L, s);
+        store_rec(D.recCn, D.recS2n, D.recS3n, a[s], r);
+        mark_far(cK, D, a[s], ca[s].x, ca[s].y, r.cx, r.cy, 0.0, 0.0, ckey, p[s] < 0 ? F_FREE_CIS : 0, stamp, K.phase ? D.bcen[a[s]] : make_float2(0.f, 0.f));
+        if (K.mode) D.ukey[a[s]] = ckey;
+        if (p[s] < 0) continue;
+        Rec r2 = load_rec(D.recC, D.recS2, D.recS3, p[s]);
+        shift_pose(&r2.cx, true, shx, shy, false); shift_pose(&r2.cx, true, PBx, PBy, true); rotate_pose(&r2.cx, true, cs, ss, cmx, cmy, cmz);
+        if (cis_misaligned(K, r, r2)) snap_cis(K, r2, r);
+        store_rec(D.recCn, D.recS2n, D.recS3n, p[s], r2);
+        mark_far(cK, D, p[s], cp_[s].x, cp_[s].y, r2.cx, r2.cy, 0.0, 0.0, ckey, F_FREE_RL, stamp, K.phase ? D.bcen[p[s]] : make_float2(0.f, 0.f));
+        if (K.mode) D.ukey[p[s]] = ckey;
+    }
+    return true;
+}
+
 // small complexes (the bulk of an oligomerised membrane: 2-12 members): one THREAD per complex. The alignment is a serial,
 // branchy algorithm; a warp per complex leaves 31 of 32 lanes idle in it, a thread per complex runs 32 of them per warp.
 __global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_constant__ Args A) {
@@ -829,14 +906,16 @@ __global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_cons
         if (ci >= n1 && ci < n1pad) continue;
         const int h0 = ci < n1 ? D.cxRoots[ci] : D.cxRoots[K.NBt + ci - n1pad], rootGid = K.NAt + h0;
         const int size = D.cxSize[h0];
-        const int *rowIn = D.members + D.cxOff[h0];
-        int nB = 0;
-        for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;
         const uint64_t seed = seed_of(cK, h0 / K.NB);
         const uint32_t me = ref_id(K, D, rootGid);
         double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
         const double u2 = keyed_uniform(seed, me, 0, step, 2);
-        complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);
+        if (ci >= n1 || !single_ligand_move(A, h0, size, step, stamp, u0, u1, u2)) {
+            const int *rowIn = D.members + D.cxOff[h0];
+            int nB = 0;
+            for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;
+            complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);
+        }
         D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0;
     }
 }

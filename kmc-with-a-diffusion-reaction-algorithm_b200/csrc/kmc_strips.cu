@@ -765,10 +765,7 @@ static int strip_pack(kmc_handle *h) {
     k_strip_cx_owned<<<nblk(std::max(NBt, 1), 256), 256, 0, st>>>(A, h->stepped ? 1 : 0, S.series, S.hist);
     // complexes of the CURRENT bond table (the last step's reactions may have changed it)
     LAUNCH(KID_STEP_BEGIN, (k_step_begin<<<1, 32, 0, st>>>(A, 0)));
-    LAUNCH(KID_UF_INIT, (k_uf_init<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_UF_HOOK, (k_uf_hook<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_UF_FLATTEN, (k_uf_flatten<<<nblk(NT, 256), 256, 0, st>>>(A)));
-    LAUNCH(KID_CX_BUILD, (k_cx_build<<<nblk(NBt, B), B, 0, st>>>(A)));
+    launch_cx_rebuild(h, A, st);
     CK(cudaMemsetAsync(S.flag, 0, NT, st));
     k_strip_classify<<<nblk(NT, 128), 128, 0, st>>>(A, S.flag, h->strip_lo, h->strip_hi, h->strip_W, S.budget);
     k_strip_bonds_owned<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, S.flag, S.series);
