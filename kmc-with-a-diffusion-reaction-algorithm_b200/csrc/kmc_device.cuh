@@ -22,6 +22,7 @@ enum Scalar {
     S_NSPEC_MAX,          // largest S_NSPEC of any step so far (the host decides the list-reuse back-off from it)
     S_NCX_BIG,            // complexes with more than CX_SMALL members: listed from the END of the first half of cxRoots[] (one warp each)
     S_NCX_MULTI,          // small complexes with several ligands: listed in the second half of cxRoots[] (S_NCX counts the single-ligand ones)
+    S_NREACT,             // entries of reactList this step
     S_NTOUCH,             // endpoints of the bonds formed / broken in the last step's S3 (touchList): their complexes are updated incrementally
     S_COUNT = 24
 };
@@ -59,7 +60,7 @@ struct Dev {
     float2 *scen;                          // [2*NT] fp32 centre each entry stands for (old centre; proposed centre for a ghost), cell-sorted like `sorted`
     int *scell;                            // [2*NT] cell of each entry
     int2 *surv; int survCap;               // unordered entry pairs that passed the distance cut of k_cells_cut
-    unsigned char *survFlag;               // [survCap] per list pair: directions that may react in S3 (bit0 first->second, bit1 second->first)
+    int *reactList;                        // [2*survCap] list pairs that may react in S3 this step: (list index << 1) | direction, appended per CTA by k_pairs_eval
     int *molSlot;                          // [NT]
     int4 *farList;                         // [NT] (gid, cell, slot, -)
     // list reuse (sparse path): the grid and the pair list of a build step serve the following steps as well
@@ -74,6 +75,7 @@ struct Dev {
     int *unitRes;                             // [NT] per unit head: 0 accepted, bit0 rejected (definite overlap), 2 = waits on pending findings
     int *pendCnt;                             // [NT] per unit head: pending findings not yet settled
     int *rejList;                             // [NT] heads of the units rejected this step (each once): their members are copied back
+    int *rejPartner;                          // [NT] for a receptor-headed unit: its cis partner at rejection time (-1 none), i.e. the other member
     int2 *pendList; int pendCap;              // (unit head, earlier unit | bit30: overlap is with its NEW pose)
     unsigned long long *step64;               // [1] mc_time_step of the step being computed
     unsigned *refA, *refB;                    // reference (global, 1-based) ids of local receptors / ligands; null = a%NA+1, NA+h%NB+1
@@ -81,6 +83,7 @@ struct Dev {
     int *maxComplex;                       // [R]
     unsigned long long *events;
     int ncell;
+    int nAcap;                             // = Consts::NAt (receptor gids are below it): for helpers that only get the Dev
 };
 
 #define GHOST_BIT 0x40000000

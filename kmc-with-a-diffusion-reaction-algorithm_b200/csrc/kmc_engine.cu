@@ -230,7 +230,7 @@ static bool ensure_cells_arrays(kmc_handle *h) {
     bool ok = true;
     if (!D.scen) {
         D.survCap = 8 * K.NT + 4096;
-        ok = dalloc(h, &D.scen, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.scell, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.surv, (size_t)D.survCap) == cudaSuccess && dalloc(h, &D.survFlag, (size_t)D.survCap) == cudaSuccess &&
+        ok = dalloc(h, &D.scen, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.scell, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.surv, (size_t)D.survCap) == cudaSuccess && dalloc(h, &D.reactList, (size_t)2 * D.survCap) == cudaSuccess &&
              dalloc(h, &D.bcen, (size_t)K.NT) == cudaSuccess && dalloc(h, &D.specList, (size_t)2 * K.NT) == cudaSuccess && dalloc(h, &D.specNext, (size_t)2 * K.NT) == cudaSuccess;
     }
     if (ok && h->cellHeadCap < D.ncell) { ok = dalloc(h, &D.cellHead, (size_t)D.ncell) == cudaSuccess; h->cellHeadCap = D.ncell; }
@@ -280,7 +280,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     h->R = K.R; h->NA = K.NA; h->NB = K.NB; h->N = K.NA + K.NB; h->NAt = K.NAt; h->NBt = K.NBt; h->NT = K.NT;
     if ((int64_t)K.R * K.ncx * K.ncy >= (1LL << 31) - 2) return fail(KMC_ERR_INVALID, "neighbour grid too large: raise cell_edge");
     Dev &D = h->D; memset(&D, 0, sizeof D);
-    D.ncell = K.R * K.ncx * K.ncy;
+    D.ncell = K.R * K.ncx * K.ncy; D.nAcap = K.NAt;
     D.candCap = std::max(1 << 14, K.NAt / 8);
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &q : h->side) ok = ok && cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
@@ -304,7 +304,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     ok = ok && ensure_cells_arrays(h); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
     D.pairCap = std::max(1 << 16, 4 * K.NAt);
-    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); A(rejList, K.NT); D.pendCap = 2 * K.NT + 4096;
+    A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); A(rejList, K.NT); A(rejPartner, K.NT); D.pendCap = 2 * K.NT + 4096;
     if (const char *o = getenv("KMC_TEST_PENDCAP")) D.pendCap = std::max(1, atoi(o));      // tests: force the overflow report
     A(pendList, D.pendCap); A(step64, 1);
     A(scal, S_COUNT); A(maxComplex, K.R); A(events, EV_COUNT);
@@ -587,9 +587,9 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
     // S3
-    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 4 + 1, RP_CHUNK) + h->nSM, h->nSM * 32), RPTHREADS, 0, st>>>(A)));
+    LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 16 + 1, RPTHREADS) + h->nSM, h->nSM * 32), RPTHREADS, 0, st>>>(A)));
     LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
-    LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max((NAt + 3) / 4, 1), 256), 256, 0, st>>>(A)));
 }
 static void swap_buffers(Dev &D) { std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign); }
 

@@ -119,7 +119,7 @@ __global__ void k_step_begin(const __grid_constant__ Args A, int begin) {
     if (begin) {
         D.step64[0] += 1; D.scal[S_EPOCH] += 1;
         if (D.scal[S_NSPEC] > D.scal[S_NSPEC_MAX]) D.scal[S_NSPEC_MAX] = D.scal[S_NSPEC];
-        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0;
+        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0; D.scal[S_NREACT] = 0;
         if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
     }
     const int nt = D.scal[S_NTOUCH];
@@ -1293,7 +1293,11 @@ KD int pair_eval(const Consts &K, const Dev &D, const ProbeCtx &c, const TileRec
 // (unit, earlier unit | pose bit); after the pass the pending findings alone decide what is left (k_pend_resolve): no geometry
 // is ever evaluated twice and nothing after the pass needs the neighbour grid.
 KD void reject_unit(const Dev &D, int u) {              // whoever sets the bit first also lists the unit for the copy-back
-    if (!(atomicOr(&D.unitRes[u], 1) & 1)) D.rejList[atomicAdd(&D.scal[S_NREJ], 1)] = u;
+    if (!(atomicOr(&D.unitRes[u], 1) & 1)) {
+        const int i = atomicAdd(&D.scal[S_NREJ], 1);
+        D.rejList[i] = u;
+        D.rejPartner[i] = u < D.nAcap ? D.recCis[u] : -1;       // (S3 has not run yet: the cis word is the one the unit moved with)
+    }
 }
 KD void publish(const Dev &D, int ukey, int res, int conf) {
     if (!res) return;
@@ -1582,10 +1586,11 @@ __global__ void __launch_bounds__(PTHREADS, PMINB) k_pairs_eval(const __grid_con
     KARGS
     const Consts &K = cK;
     __shared__ int items[2 * PE_CHUNK];          // (list index << 1) | direction
-    __shared__ int nitems;
+    __shared__ int ritems[2 * PE_CHUNK];         // the same coding: directions that may react in S3 (appended to D.reactList per chunk)
+    __shared__ int nitems, nreact, rbase;
     const int ns = min(D.scal[S_NSURV], D.survCap);
     for (int base = blockIdx.x * PE_CHUNK; base < ns; base += gridDim.x * PE_CHUNK) {
-        if (threadIdx.x == 0) nitems = 0;
+        if (threadIdx.x == 0) { nitems = 0; nreact = 0; }
         __syncthreads();
         for (int s = base + threadIdx.x; s < min(base + PE_CHUNK, ns); s += PTHREADS) {
             const int2 w = D.surv[s];
@@ -1601,10 +1606,14 @@ __global__ void __launch_bounds__(PTHREADS, PMINB) k_pairs_eval(const __grid_con
                     if (pair_pre(K, D, make_probe(K, b), a, ps)) items[atomicAdd(&nitems, 1)] = (s << 1) | 1;
                 }
             }
-            D.survFlag[s] = (unsigned char)flag;         // which directions of this pair may react in S3 (k_react_pairs)
+            if (flag & 1) ritems[atomicAdd(&nreact, 1)] = s << 1;           // which directions of this pair may react in S3 (k_react_pairs)
+            if (flag & 2) ritems[atomicAdd(&nreact, 1)] = (s << 1) | 1;
         }
         __syncthreads();
-        const int ni = nitems;
+        const int ni = nitems, nr = nreact;
+        if (threadIdx.x == 0 && nr) rbase = atomicAdd(&D.scal[S_NREACT], nr);          // one global atomic per chunk
+        __syncthreads();
+        for (int q = threadIdx.x; q < nr; q += PTHREADS) D.reactList[rbase + q] = ritems[q];
         for (int q = threadIdx.x; q < ni; q += PTHREADS) {
             const int it = items[q];
             const int2 w = D.surv[it >> 1];
@@ -1788,9 +1797,8 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
         }
     }
 }
-// work items: the list pairs flagged by k_pairs_eval (sparse path), then the pairs collected by the tile kernel / the special
-// entries. Flagged pairs are few (~1 in 10): each CTA compacts the flags of a chunk of the list in shared memory first, so the
-// expensive geometry + draw runs with full warps.
+// work items: the list pairs k_pairs_eval found within reaction reach (sparse path: D.reactList, a dense list, one thread per
+// entry), then the pairs collected by the tile kernel / the special entries (D.pairs).
 #ifndef RP_CHUNK
 #define RP_CHUNK 512
 #endif
@@ -1800,32 +1808,13 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
 __global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
-    __shared__ int items[2 * RP_CHUNK];          // (list index << 1) | direction
-    __shared__ int nitems;
     const uint64_t step = D.step64[0];
-    const int nl = D.survFlag ? min(D.scal[S_NSURV], D.survCap) : 0;
-    for (int base = blockIdx.x * RP_CHUNK; base < nl; base += gridDim.x * RP_CHUNK) {
-        if (threadIdx.x == 0) nitems = 0;
-        __syncthreads();
-        const unsigned *fw = reinterpret_cast<const unsigned *>(D.survFlag + base);         // base is a multiple of 4
-        for (int k = threadIdx.x; k < RP_CHUNK / 4 && base + 4 * k < nl; k += blockDim.x) {
-            unsigned w = fw[k];                                                             // four flags (bytes past nl are stale: masked below)
-            for (int b = 0; b < 4 && w; b++, w >>= 8) {
-                const int i = base + 4 * k + b, f = w & 3;
-                if (!f || i >= nl) continue;
-                if (f & 1) items[atomicAdd(&nitems, 1)] = i << 1;
-                if (f & 2) items[atomicAdd(&nitems, 1)] = (i << 1) | 1;
-            }
-        }
-        __syncthreads();
-        const int ni = nitems;
-        for (int q = threadIdx.x; q < ni; q += blockDim.x) {
-            const int it = items[q];
-            const int2 w = D.surv[it >> 1];
-            const int a = w.x & ~GHOST_BIT, b = w.y & ~GHOST_BIT;
-            if (it & 1) react_pair(K, D, step, b, a); else react_pair(K, D, step, a, b);
-        }
-        __syncthreads();
+    const int nl = D.reactList ? min(D.scal[S_NREACT], 2 * D.survCap) : 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nl; q += gridDim.x * blockDim.x) {
+        const int it = D.reactList[q];
+        const int2 w = D.surv[it >> 1];
+        const int a = w.x & ~GHOST_BIT, b = w.y & ~GHOST_BIT;
+        if (it & 1) react_pair(K, D, step, b, a); else react_pair(K, D, step, a, b);
     }
     const int np = min(D.scal[S_NPAIR], D.pairCap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
@@ -1882,47 +1871,18 @@ __global__ void k_react_resolve(const __grid_constant__ Args A) {
     }
 }
 
-// Last kernel of a step: the copy-back of rejected units, then S3c, main.cpp:2062-2141, one thread per receptor. Keyed draws make the three sequential loops order
+// S3c, main.cpp:2062-2141, for receptor a with ligand h / cis partner p (-1 none). Keyed draws make the three sequential loops order
 // free: a thread owns the R-L bond of its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L
 // outcome from the partner's own keyed draw instead of waiting for it.
-__global__ void k_finish(const __grid_constant__ Args A) {
-    KARGS
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    // (1) revert the members of the rejected units (main.cpp:666-674, 851-863, 1831-1860): the old pose over the proposal, one
-    // thread per listed unit. Membership is the one of THIS step's sweep (unitOf / the member table), whatever S3 did to the bonds.
-    // (all words of this thread are requested before the first dependent use)
-    int h = -1, p = -1, myUnit = -1, myRes = 0;
-    if (gid < cK.NAt) { h = D.recLig[gid]; p = D.recCis[gid]; myUnit = D.unitOf[gid]; myRes = D.unitRes[gid]; }
-    const int nLiveA = nA_live(D);
-    const int nrej = min(D.scal[S_NREJ], cK.NT);
-    if (gid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
-    // Ligand-headed units (free ligands, complexes) are taken from the list; a receptor-headed unit (free receptor, ligand-free
-    // cis dimer) is reverted by the head's own thread, which reads its cis word before its own dissociation trial can clear it.
-    for (int i = gid; i < nrej; i += gridDim.x * blockDim.x) {
-        const int u = D.rejList[i];
-        if (u < cK.NAt) continue;
-        const int hh = u - cK.NAt, size = D.cxSize[hh];
-        if (size <= 1) restore_pose(cK, D, u);
-        else { const int *row = D.members + D.cxOff[hh]; for (int q = 0; q < size; q++) restore_pose(cK, D, row[q]); }
-    }
-    if (gid >= nLiveA) return;
-    if (myUnit == gid && (myRes & 1)) {
-        restore_pose(cK, D, gid);
-        if (p >= 0 && D.unitOf[p] == gid) restore_pose(cK, D, p);      // (a cis bond formed in this step's S3 is not part of the unit)
-    }
-    // (2) dissociation
-    const uint64_t step = D.step64[0];
-    const int a = gid;
-    const Consts &K = cK;
-    if (h < 0 && p < 0) return;
-    const uint64_t seed = seed_of(cK, replica_of_gid(K, a));
+KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, int p) {
+    const uint64_t seed = seed_of(K, replica_of_gid(K, a));
     const uint32_t me = ref_id(K, D, a);
     bool boundAfter = false;
     if (h >= 0) {
         if (keyed_uniform(seed, me, 0, step, SLOT_RL_OFF) < K.pOff) {
             int s = D.recSite[a];
             D.recLig[a] = -1; D.recSite[a] = -1; D.ligRec[h * 3 + s] = -1;
-            atomicAdd(&D.events[EV_RL_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, cK.NAt + h);
+            atomicAdd(&D.events[EV_RL_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, K.NAt + h);
         } else boundAfter = true;
     }
     if (p > a) {
@@ -1938,6 +1898,37 @@ __global__ void k_finish(const __grid_constant__ Args A) {
             atomicAdd(&D.events[inComplex ? EV_CIS_OFF : EV_MONO_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, p);
         }
     }
+}
+// Last kernel of a step.
+// (1) The members of the rejected units get their old pose back (main.cpp:666-674, 851-863, 1831-1860), one thread per listed
+//     unit. Membership is the one of THIS step's sweep: the member table for a ligand-headed unit, the cis partner recorded at
+//     rejection time for a receptor-headed one -- whatever S3 did to the bonds since.
+// (2) Dissociation: a thread takes four consecutive receptors; their bond words arrive as two 16-byte loads, and on a
+//     membrane with few bonds that is all the kernel reads (8 bytes per receptor).
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) {
+    KARGS
+    const Consts &K = cK;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a0 = tid * 4;
+    const int nLiveA = nA_live(D);
+    int hh[4] = {-1, -1, -1, -1}, pp[4] = {-1, -1, -1, -1};
+    if (a0 + 3 < K.NAt) {
+        const int4 hv = *reinterpret_cast<const int4 *>(D.recLig + a0), pv = *reinterpret_cast<const int4 *>(D.recCis + a0);
+        hh[0] = hv.x; hh[1] = hv.y; hh[2] = hv.z; hh[3] = hv.w; pp[0] = pv.x; pp[1] = pv.y; pp[2] = pv.z; pp[3] = pv.w;
+    } else for (int k = 0; k < 4; k++) if (a0 + k < K.NAt) { hh[k] = D.recLig[a0 + k]; pp[k] = D.recCis[a0 + k]; }
+    const int nrej = min(D.scal[S_NREJ], K.NT);
+    if (tid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
+    for (int i = tid; i < nrej; i += gridDim.x * blockDim.x) {
+        const int u = D.rejList[i];
+        if (u < K.NAt) { restore_pose(K, D, u); const int q = D.rejPartner[i]; if (q >= 0) restore_pose(K, D, q); continue; }
+        const int h = u - K.NAt, size = D.cxSize[h];
+        if (size <= 1) restore_pose(K, D, u);
+        else { const int *row = D.members + D.cxOff[h]; for (int q = 0; q < size; q++) restore_pose(K, D, row[q]); }
+    }
+    if ((hh[0] & hh[1] & hh[2] & hh[3] & pp[0] & pp[1] & pp[2] & pp[3]) < 0) return;      // all eight words negative: no bond on any of the four
+    const uint64_t step = D.step64[0];
+    for (int k = 0; k < 4; k++)
+        if (a0 + k < nLiveA && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
 }
 
 // ------------------------------------------------------------------------------------------------
