@@ -123,6 +123,8 @@ int kmc_step_timed(kmc_handle *h, int64_t n, double *elapsed_ms);
  * kmc_profile_get(idx) returns 1 past the last kernel. */
 int kmc_profile(kmc_handle *h, int32_t enable);
 int kmc_profile_get(kmc_handle *h, int32_t idx, const char **name, double *total_ms, int64_t *launches);
+/* diagnostics: with KMC_TIMELINE=1 in the environment at kmc_create, prints (stderr) where every kernel of the last step graph ran on the device clock */
+int kmc_timeline_print(kmc_handle *h);
 
 /* Outputs the reference writes at its output cadence */
 int kmc_get_series(kmc_handle *h, int32_t replica, kmc_series *out);

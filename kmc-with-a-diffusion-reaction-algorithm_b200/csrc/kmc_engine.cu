@@ -62,6 +62,7 @@ struct kmc_handle {
     int64_t launches = 0, passes = 0;
     int init_rounds = 0;             // rounds the GPU generator needed (diagnostics)
     int cxBlocks = 0;                // grid of the cooperative rebuild kernel
+    unsigned long long *timeline = nullptr; int tlCount = 0, tlId[64]; cudaStream_t tlStream = nullptr;      // KMC_TIMELINE
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
@@ -100,11 +101,18 @@ static void harvest(kmc_handle *h, bool all) {
     }
     h->pending.resize(keep);
 }
+// KMC_TIMELINE=1 (diagnostics): every kernel of the step graph is bracketed by two one-thread stamp kernels that write %globaltimer,
+// kmc_timeline_print shows where each kernel of the LAST step ran on the device clock (the stamps add ~2 us per node)
+__global__ void k_stamp(unsigned long long *buf, int slot) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); buf[slot] = t; }
 // every kernel launch of the sweep goes through this macro: counts it, and brackets it with events when profiling
 #define LAUNCH(id, ...)                                                                              \
     do {                                                                                             \
         h->launches++;                                                                               \
-        if (h->profiling) {                                                                          \
+        if (h->timeline && h->tlCount < 64) {                                                        \
+            cudaStream_t ts_ = h->tlStream ? h->tlStream : st;                                       \
+            const int sl_ = h->tlCount++; h->tlId[sl_] = id;                                         \
+            k_stamp<<<1, 1, 0, ts_>>>(h->timeline, 2 * sl_); __VA_ARGS__; k_stamp<<<1, 1, 0, ts_>>>(h->timeline, 2 * sl_ + 1); \
+        } else if (h->profiling) {                                                                          \
             kmc_handle::Pending p_{id, take_event(h), take_event(h)};                                \
             cudaEventRecord(p_.a, st); __VA_ARGS__; cudaEventRecord(p_.b, st);                       \
             h->pending.push_back(p_);                                                                \
@@ -275,6 +283,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     if (p->min_image != 0) return fail(KMC_ERR_INVALID, "min_image = 1 is not implemented: the reference computes plain Euclidean distances (main.cpp:642-646), which is what 0 selects");
     h->nSM = std::max(prop.multiProcessorCount, 1);
     if (const char *o = getenv("KMC_FORK")) h->forkMask = atoi(o);
+    if (getenv("KMC_TIMELINE")) { void *q = nullptr; if (cudaMalloc(&q, 128 * sizeof(unsigned long long)) == cudaSuccess) { h->allocs.push_back(q); h->timeline = (unsigned long long *)q; } }
     fill_consts(*p, h->K);
     const Consts &K = h->K;
     h->R = K.R; h->NA = K.NA; h->NB = K.NB; h->N = K.NA + K.NB; h->NAt = K.NAt; h->NBt = K.NBt; h->NT = K.NT;
@@ -283,7 +292,10 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     D.ncell = K.R * K.ncx * K.ncy; D.nAcap = K.NAt;
     D.candCap = std::max(1 << 14, K.NAt / 8);
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (auto &q : h->side) ok = ok && cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
+    // the side branches of the step graph carry the latency-bound kernels (complexes, special entries): few CTAs with long serial
+    // chains. Highest priority, so that their CTAs are dispatched ahead of the streaming kernels' remaining CTAs and run underneath them
+    int prLo = 0, prHi = 0; cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    for (auto &q : h->side) ok = ok && cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, getenv("KMC_NOPRIO") ? prLo : prHi) == cudaSuccess;
     for (auto &e : h->evFork) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     for (auto &e : h->evJoin) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->monEvent, cudaEventDisableTiming) == cudaSuccess && cudaMallocHost((void **)&h->monHost, sizeof(int) * S_COUNT) == cudaSuccess;
@@ -559,8 +571,10 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<std::min(nblk(std::max(NAt, 1), REC_TILE), h->nSM * RECMINB), REC_TILE, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
+    h->tlStream = s2;
+    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), h->nSM * 12), 32 * CX_WARPS, 0, s2>>>(A)));      // (large complexes: rare, first)
     LAUNCH(KID_PROPOSE_COMPLEX_SMALL, (k_propose_complex_small<<<std::min(nblk(NBt, 128), h->nSM * 16), 128, 0, s2>>>(A)));
-    LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), h->nSM * 12), 32 * CX_WARPS, 0, s2>>>(A)));
+    h->tlStream = nullptr;
     if (fork || forkC) {
         cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);
         cudaStreamWaitEvent(st, h->evJoin[0], 0); cudaStreamWaitEvent(st, h->evJoin[1], 0);
@@ -581,7 +595,9 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
         if (!build && fork2) { cudaEventRecord(h->evFork[1], st); cudaStreamWaitEvent(s3, h->evFork[1], 0); }
         LAUNCH(KID_PAIRS_EVAL, (k_pairs_eval<<<std::min(nblk(NT / 2 + 1, PE_CHUNK) + h->nSM, h->nSM * 16), PTHREADS, 0, st>>>(A)));
         if (!build) {           // the special entries next to the list pairs (both only publish findings)
+            h->tlStream = s3;
             LAUNCH(KID_SPECIAL, (k_special_pairs<<<h->nSM, 32 * SP_WARPS, 0, s3>>>(A)));
+            h->tlStream = nullptr;
             if (fork2) { cudaEventRecord(h->evJoin[2], s3); cudaStreamWaitEvent(st, h->evJoin[2], 0); }
         }
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
@@ -606,6 +622,7 @@ static int ensure_graphs(kmc_handle *h) {
             A.K.phase = ph;
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            h->tlCount = 0;
             issue_step(h, A, h->stream);
             CK(cudaStreamEndCapture(h->stream, &g));
             CK(cudaGraphInstantiate(&h->gexec[ph][p], g, 0));
@@ -718,6 +735,18 @@ extern "C" int kmc_step_timed(kmc_handle *h, int64_t n, double *elapsed_ms) {
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     return rc;
+}
+extern "C" int kmc_timeline_print(kmc_handle *h) {
+    if (!h || !h->timeline) return KMC_ERR_INVALID;
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long t[128];
+    CK(cudaMemcpy(t, h->timeline, sizeof t, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < h->tlCount; i++) t0 = std::min(t0, t[2 * i]);
+    for (int i = 0; i < h->tlCount; i++)
+        fprintf(stderr, "timeline %-26s start %8.2f us  end %8.2f us  (%.2f)\n", g_kernel_names[h->tlId[i]], (t[2 * i] - t0) * 1e-3, (t[2 * i + 1] - t0) * 1e-3, (t[2 * i + 1] - t[2 * i]) * 1e-3);
+    return KMC_OK;
 }
 extern "C" int kmc_profile(kmc_handle *h, int32_t enable) {
     if (!h) return KMC_ERR_INVALID;

@@ -384,80 +384,89 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
 #define RECMINB 4
 #endif
 #ifndef LIGMINB
-#define LIGMINB 5
+#define LIGMINB 8
 #endif
 __global__ void __launch_bounds__(256, RECMINB) k_propose_rec(const __grid_constant__ Args A) { propose_rec_body(A); }
 
-// ---- free ligands (S2c, main.cpp:905-969): one thread per ligand, poses staged through shared memory -------------------------
-// A ligand pose is 192 contiguous bytes (AoS). Thread-per-ligand global access would touch 32 half-used sectors per warp
-// instruction; instead the CTA copies its 128 poses (24 KB, contiguous) with fully coalesced 16-byte accesses into a padded
-// tile (row stride 13 x 16 B: conflict-free 128-bit row reads), every thread works on its own row, and the proposals go
-// back the same way. Rows of ligands that do not move here (members of complexes: k_propose_complex writes those) are not stored.
+// ---- free ligands (S2c, main.cpp:905-969): one thread per ligand, poses staged through shared memory by the bulk-copy engine ----
+// A ligand pose is 192 contiguous bytes (AoS). Every thread asks the copy engine for ITS row (cp.async.bulk, global -> shared, one
+// 192-byte bulk copy per ligand, completion counted in bytes on one mbarrier per CTA) into a padded tile (row stride 13 x 16 B),
+// so no load instruction and no register is spent on staging. The pose then STAYS in shared memory: the thread keeps only the
+// rotation matrix, the shift and the centre in registers and carries one point at a time through translation, wrap, reflection
+// and rotation (each point's arithmetic is exactly the reference's, the points are independent), which halves the register
+// footprint of holding all eight points and doubles the warps an SM can keep in flight. Moved rows go back with bulk stores
+// (shared -> global); rows of ligands that do not move here (members of complexes: the complex kernels write those) are not stored.
 #define LIG_TILE 128
+KD uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+KD void mbar_init(uint64_t *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+KD void mbar_arrive_tx(uint64_t *bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+KD void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+KD void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+KD void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
 __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_constant__ Args A) {
     KARGS
     const Consts &K = cK;
-    __shared__ double2 tile[LIG_TILE][13];
-    __shared__ unsigned char moved[LIG_TILE];
+    __shared__ __align__(16) double2 tile[LIG_TILE][13];
+    __shared__ __align__(8) uint64_t bar;
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int h0 = blockIdx.x * LIG_TILE, h = h0 + threadIdx.x, gid = K.NAt + h;
-    if (h == 0) D.scal[S_TOPO_DIRTY] = 0;         // the gated rebuild kernels of this step are done; S3 sets it again
+    if (h == 0) D.scal[S_TOPO_DIRTY] = 0;         // the gated rebuild kernel of this step is done
     const int nLive = nB_live(D);
-    const int nrows = min(LIG_TILE, nLive - h0);          // live rows only (the capacity padding of a strip costs nothing)
-    if (nrows <= 0) return;
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(D.lig) + (size_t)h0 * 12;
-        for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; tile[r][i - r * 12] = src[i]; }
-    }
+    if (h0 >= nLive) return;                      // (whole CTA: the capacity padding of a strip costs nothing)
+    const bool live = h < nLive;
+    if (threadIdx.x == 0) { mbar_init(&bar, LIG_TILE); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    double *row = reinterpret_cast<double *>(&tile[threadIdx.x][0]);
+    if (live) { mbar_arrive_tx(&bar, 192); bulk_g2s(row, D.lig + (size_t)h * 24, 192, &bar); }
+    else mbar_arrive_tx(&bar, 0);
     // the scalar words of this thread's ligand travel in the same latency window as the tile
     int head = -1, csize = 0; float2 bc = make_float2(0.f, 0.f); uint32_t me = 0;
-    if (threadIdx.x < nrows) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; me = ref_id(K, D, gid); }
-    __syncthreads();
-    const bool act = h < nLive && head == gid && csize <= 1;     // a free ligand (complexes: k_propose_complex)
-    moved[threadIdx.x] = act ? 1 : 0;
-    if (act) {
-        Lig l;
-        {
-            double *d = &l.p[0][0];
-#pragma unroll
-            for (int q = 0; q < 12; q++) { const double2 v = tile[threadIdx.x][q]; d[2 * q] = v.x; d[2 * q + 1] = v.y; }
-        }
+    if (live) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; me = ref_id(K, D, gid); }
+    const bool act = live && head == gid && csize <= 1;     // a free ligand (complexes: the complex kernels)
+    double u0, u1, u2, u3, u4, u5;
+    if (act) {          // the draws do not need the pose: they overlap the copy
         const uint64_t seed = seed_of(cK, replica_of_gid(K, gid));
-        const double ox = l.p[0][0], oy = l.p[0][1], oz = l.p[0][2];
-        double u0, u1, u2, u3, u4, u5;
         keyed_uniform2(seed, me, 0, step, 0, u0, u1); keyed_uniform2(seed, me, 0, step, 2, u2, u3); keyed_uniform2(seed, me, 0, step, 4, u4, u5);
+    }
+    mbar_wait(&bar, 0);
+    if (act) {
+        const double ox = row[0], oy = row[1], oz = row[2];
         const double amp = mul(K.ampB, u0);
         const double theta = mul(u1, K.pai), phai = mul(mul(u2, 2.0), K.pai);
         double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
         const double shx = mul(mul(amp, st), cp), shy = mul(mul(amp, st), sp), shz = mul(amp, ct);
-        for (int q = 0; q < 8; q++) { l.p[q][0] = add(l.p[q][0], shx); l.p[q][1] = add(l.p[q][1], shy); l.p[q][2] = add(l.p[q][2], shz); }
-        const double PBx = wrap_offset(l.p[0][0], K.Lx), PBy = wrap_offset(l.p[0][1], K.Ly);
-        if (l.p[0][2] > K.Lz || l.p[0][2] < 0) {
-            const double PBz = mul(K.Lz, round(dvd(l.p[0][2], K.Lz)));
-            for (int q = 0; q < 8; q++) l.p[q][2] = add(-l.p[q][2], mul(2.0, PBz));     // reflect, main.cpp:925-931
-        }
-        for (int q = 0; q < 8; q++) { l.p[q][0] = sub(l.p[q][0], PBx); l.p[q][1] = sub(l.p[q][1], PBy); }
+        // the centre first: it decides the wrap and the reflection of the whole body and is the pivot of the rotation
+        const double c0x = add(ox, shx), c0y = add(oy, shy), c0z = add(oz, shz);
+        const double PBx = wrap_offset(c0x, K.Lx), PBy = wrap_offset(c0y, K.Ly);
+        const bool reflect = c0z > K.Lz || c0z < 0;
+        const double twoPBz = reflect ? mul(2.0, mul(K.Lz, round(dvd(c0z, K.Lz)))) : 0.0;      // main.cpp:925-931
+        double c[3] = {sub(c0x, PBx), sub(c0y, PBy), reflect ? add(-c0z, twoPBz) : c0z};
         const double rt = mul(sub(mul(2.0, u3), 1.0), K.rotB), rp = mul(sub(mul(2.0, u4), 1.0), K.rotB),
                      rs = mul(sub(mul(2.0, u5), 1.0), K.rotB);
         const Rot3 R3 = euler(rt, rp, rs);
-        Lig n;
-        const double c[3] = {l.p[0][0], l.p[0][1], l.p[0][2]};
-        for (int q = 0; q < 8; q++) rot3_about(R3, l.p[q], c, n.p[q]);
-        n.p[0][0] = c[0]; n.p[0][1] = c[1]; n.p[0][2] = c[2];     // t*(0)+c = c exactly (main.cpp:958-966)
-        {
-            const double *d = &n.p[0][0];
-#pragma unroll
-            for (int q = 0; q < 12; q++) tile[threadIdx.x][q] = make_double2(d[2 * q], d[2 * q + 1]);
+#pragma unroll 1
+        for (int q = 1; q < 8; q++) {
+            double pt[3] = {add(row[3 * q], shx), add(row[3 * q + 1], shy), add(row[3 * q + 2], shz)};
+            if (reflect) pt[2] = add(-pt[2], twoPBz);
+            pt[0] = sub(pt[0], PBx); pt[1] = sub(pt[1], PBy);
+            double o[3]; rot3_about(R3, pt, c, o);
+            row[3 * q] = o[0]; row[3 * q + 1] = o[1]; row[3 * q + 2] = o[2];
         }
-        mark_far(cK, D, gid, ox, oy, n.p[0][0], n.p[0][1], oz, n.p[0][2], unit_key(K, gid, ox, oy), F_FREE_RL, stamp, bc);
+        row[0] = c[0]; row[1] = c[1]; row[2] = c[2];          // t*(0)+c = c exactly (main.cpp:958-966)
+        mark_far(cK, D, gid, ox, oy, c[0], c[1], oz, c[2], unit_key(K, gid, ox, oy), F_FREE_RL, stamp, bc);
         if (K.mode) D.ukey[gid] = unit_key(K, gid, ox, oy);
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
-    }
-    __syncthreads();
-    {
-        double2 *dst = reinterpret_cast<double2 *>(D.lign) + (size_t)h0 * 12;
-        for (int i = threadIdx.x; i < nrows * 12; i += LIG_TILE) { const int r = i / 12; if (moved[r]) dst[i] = tile[r][i - r * 12]; }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the row was written through the generic proxy
+        bulk_s2g(D.lign + (size_t)h * 24, row, 192);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the shared row must outlive the copy
     }
 }
 
@@ -1708,29 +1717,34 @@ KD void restore_pose(const Consts &cK, const Dev &D, int gid) {
         for (int q = 0; q < 12; q++) d[q] = s[q];
     }
 }
-__global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ Args A) {
-    KARGS
+// one sweep over entries first, first + stride, ...: returns true if anything was decided
+KD bool pend_sweep(const Dev &D, int n, int first, int stride) {
+    bool changed = false;
+    for (int i = first; i < n; i += stride) {
+        const int2 rec = D.pendList[i];                              // (only this thread ever rewrites entry i)
+        if (rec.x < 0) continue;                                        // settled in an earlier sweep
+        const int u = rec.x, v = rec.y & UNIT_MASK; const bool onNew = rec.y & 0x40000000;
+        bool done = false;
+        if (unit_state(D, u) != U_UNKNOWN) done = true;                 // u already rejected through another finding
+        else {
+            const int sv = unit_state(D, v);
+            if (sv != U_UNKNOWN) {
+                done = true;
+                if ((sv == U_ACCEPT) == onNew) { reject_unit(D, u); changed = true; }                   // v sits at the pose u overlaps
+                else if (atomicSub(&D.pendCnt[u], 1) == 1) { atomicCAS(&D.unitRes[u], 2, 0); changed = true; }   // last finding, all misses
+            }
+        }
+        if (done) D.pendList[i].x = -1;
+    }
+    return changed;
+}
+// the fixed point by ONE CTA (short lists: a few hundred findings per step on the 1.25e6-molecule membrane)
+KD void pend_resolve_block(const Dev &D, int n) {
     __shared__ int changed;
-    const int n = min(D.scal[S_NPEND], D.pendCap);
     for (int sweep = 0; sweep <= n; sweep++) {
         if (threadIdx.x == 0) changed = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int2 rec = D.pendList[i];                              // (only this thread ever rewrites entry i)
-            if (rec.x < 0) continue;                                        // settled in an earlier sweep
-            const int u = rec.x, v = rec.y & UNIT_MASK; const bool onNew = rec.y & 0x40000000;
-            bool done = false;
-            if (unit_state(D, u) != U_UNKNOWN) done = true;                 // u already rejected through another finding
-            else {
-                const int sv = unit_state(D, v);
-                if (sv != U_UNKNOWN) {
-                    done = true;
-                    if ((sv == U_ACCEPT) == onNew) { reject_unit(D, u); changed = 1; }                   // v sits at the pose u overlaps
-                    else if (atomicSub(&D.pendCnt[u], 1) == 1) { atomicCAS(&D.unitRes[u], 2, 0); changed = 1; }   // last finding, all misses
-                }
-            }
-            if (done) D.pendList[i].x = -1;
-        }
+        if (pend_sweep(D, n, threadIdx.x, blockDim.x)) changed = 1;
         __threadfence();
         __syncthreads();
         const bool again = changed != 0;
@@ -1799,25 +1813,17 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
 }
 // work items: the list pairs k_pairs_eval found within reaction reach (sparse path: D.reactList, a dense list, one thread per
 // entry), then the pairs collected by the tile kernel / the special entries (D.pairs).
-#ifndef RP_CHUNK
-#define RP_CHUNK 512
-#endif
-#ifndef RPTHREADS
-#define RPTHREADS 64
-#endif
-__global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) {
-    KARGS
-    const Consts &K = cK;
+KD void react_pairs_body(const Consts &K, const Dev &D, int tid, int nth) {
     const uint64_t step = D.step64[0];
     const int nl = D.reactList ? min(D.scal[S_NREACT], 2 * D.survCap) : 0;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nl; q += gridDim.x * blockDim.x) {
+    for (int q = tid; q < nl; q += nth) {
         const int it = D.reactList[q];
         const int2 w = D.surv[it >> 1];
         const int a = w.x & ~GHOST_BIT, b = w.y & ~GHOST_BIT;
         if (it & 1) react_pair(K, D, step, b, a); else react_pair(K, D, step, a, b);
     }
     const int np = min(D.scal[S_NPAIR], D.pairCap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+    for (int i = tid; i < np; i += nth) {
         const unsigned long long pr = D.pairs[i];
         react_pair(K, D, step, (int)(pr >> 32), (int)(pr & 0xffffffffu));
     }
@@ -1825,8 +1831,7 @@ __global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant
 
 // single CTA: order the successful candidates as the reference's loops would meet them, then apply them
 // first-come-first-served (main.cpp:1877-1949, 1952-2003, 2007-2058)
-__global__ void k_react_resolve(const __grid_constant__ Args A) {
-    KARGS
+KD void react_resolve_block(const Dev &D) {
     unsigned long long *rl = D.candRL, *cis = D.candCis;
     const int nRL = min(D.scal[S_NCAND_RL], D.candCap), nCis = min(D.scal[S_NCAND_CIS], D.candCap);
     // ---- rank sort (n = successful draws of one step, tiny in practice; O(n^2/threads)) ----
@@ -1905,31 +1910,44 @@ KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, i
 //     rejection time for a receptor-headed one -- whatever S3 did to the bonds since.
 // (2) Dissociation: a thread takes four consecutive receptors; their bond words arrive as two 16-byte loads, and on a
 //     membrane with few bonds that is all the kernel reads (8 bytes per receptor).
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) {
-    KARGS
-    const Consts &K = cK;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int a0 = tid * 4;
+KD void finish_body(const Consts &K, const Dev &D, int tid, int nth) {
     const int nLiveA = nA_live(D);
-    int hh[4] = {-1, -1, -1, -1}, pp[4] = {-1, -1, -1, -1};
-    if (a0 + 3 < K.NAt) {
-        const int4 hv = *reinterpret_cast<const int4 *>(D.recLig + a0), pv = *reinterpret_cast<const int4 *>(D.recCis + a0);
-        hh[0] = hv.x; hh[1] = hv.y; hh[2] = hv.z; hh[3] = hv.w; pp[0] = pv.x; pp[1] = pv.y; pp[2] = pv.z; pp[3] = pv.w;
-    } else for (int k = 0; k < 4; k++) if (a0 + k < K.NAt) { hh[k] = D.recLig[a0 + k]; pp[k] = D.recCis[a0 + k]; }
     const int nrej = min(D.scal[S_NREJ], K.NT);
     if (tid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
-    for (int i = tid; i < nrej; i += gridDim.x * blockDim.x) {
+    for (int i = tid; i < nrej; i += nth) {
         const int u = D.rejList[i];
         if (u < K.NAt) { restore_pose(K, D, u); const int q = D.rejPartner[i]; if (q >= 0) restore_pose(K, D, q); continue; }
         const int h = u - K.NAt, size = D.cxSize[h];
         if (size <= 1) restore_pose(K, D, u);
         else { const int *row = D.members + D.cxOff[h]; for (int q = 0; q < size; q++) restore_pose(K, D, row[q]); }
     }
-    if ((hh[0] & hh[1] & hh[2] & hh[3] & pp[0] & pp[1] & pp[2] & pp[3]) < 0) return;      // all eight words negative: no bond on any of the four
     const uint64_t step = D.step64[0];
-    for (int k = 0; k < 4; k++)
-        if (a0 + k < nLiveA && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
+    for (int a0 = tid * 4; a0 < nLiveA; a0 += nth * 4) {
+        int hh[4] = {-1, -1, -1, -1}, pp[4] = {-1, -1, -1, -1};
+        if (a0 + 3 < K.NAt) {
+            const int4 hv = *reinterpret_cast<const int4 *>(D.recLig + a0), pv = *reinterpret_cast<const int4 *>(D.recCis + a0);
+            hh[0] = hv.x; hh[1] = hv.y; hh[2] = hv.z; hh[3] = hv.w; pp[0] = pv.x; pp[1] = pv.y; pp[2] = pv.z; pp[3] = pv.w;
+        } else for (int k = 0; k < 4; k++) if (a0 + k < K.NAt) { hh[k] = D.recLig[a0 + k]; pp[k] = D.recCis[a0 + k]; }
+        if ((hh[0] & hh[1] & hh[2] & hh[3] & pp[0] & pp[1] & pp[2] & pp[3]) < 0) continue;      // all eight words negative: no bond on any of the four
+        for (int k = 0; k < 4; k++)
+            if (a0 + k < nLiveA && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
+    }
 }
+
+// The tail of a step: four dependent kernels on lists of a few hundred to a few ten thousand items. (Measured on the B200: the
+// same four phases as ONE cooperative kernel with grid-wide barriers take 53 us instead of 47 -- the lists want many short-lived
+// threads, not a persistent grid that spins at barriers while one block settles the pending findings.)
+//   k_pend_resolve   the order dependence of the sweep is settled from the pending findings (one CTA, fixed point)
+//   k_react_pairs    S3 candidates: geometric tests + keyed draws, one thread per pre-selected pair (main.cpp:1877-2058)
+//   k_react_resolve  the successful candidates are applied in the reference's loop order, first come first served (one CTA)
+//   k_finish         rejected units get their old pose back; dissociation trials (main.cpp:2062-2141)
+__global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ Args A) { KARGS pend_resolve_block(D, min(D.scal[S_NPEND], D.pendCap)); }
+#ifndef RPTHREADS
+#define RPTHREADS 64
+#endif
+__global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) { KARGS react_pairs_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void k_react_resolve(const __grid_constant__ Args A) { KARGS react_resolve_block(D); }
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 
 // ------------------------------------------------------------------------------------------------
 // outputs (bond.dat columns, main.cpp:2251)

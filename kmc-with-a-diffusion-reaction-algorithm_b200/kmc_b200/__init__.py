@@ -38,7 +38,7 @@ class Series(C.Structure):
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
            "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_write_bond_dat",
-           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
+           "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_timeline_print", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_halo_width", "kmc_strip_unique_id",
            "kmc_strip_comm_init", "kmc_strip_refresh", "kmc_strip_refresh_local", "kmc_strip_get_series", "kmc_strip_get_oligomer_hist",
            "kmc_strip_get_records", "kmc_strip_load_records", "kmc_strip_init_random", "kmc_generate_packed", "kmc_gro_append_arrays", "kmc_checkpoint_write_arrays",
@@ -125,6 +125,7 @@ def lib():
         L.kmc_format_cluster_log.argtypes = [C.c_double, i64, i32, vp, vp, C.c_char_p, i64]
         L.kmc_step_timed.argtypes = [vp, i64, C.POINTER(C.c_double)]
         L.kmc_profile.argtypes = [vp, i32]
+        L.kmc_timeline_print.argtypes = [vp]
         L.kmc_profile_get.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(i64)]
         _lib = L
     return _lib
