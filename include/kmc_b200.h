@@ -149,6 +149,10 @@ int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
  * list, [13] special entries (far movers / drifted molecules of a list-reuse step), [14] pending findings, [15] pre-selected
  * reaction pairs */
 int kmc_get_events(kmc_handle *h, int64_t *ev);
+/* which implementation of the step the handle uses: 0 = the general multi-kernel path (one CUDA graph per step), 1 = the fused
+ * small-system step (csrc/kmc_small.cu: replicas of at most 512 molecules, one CTA per replica, the whole step in one kernel,
+ * many steps per launch). Chosen at kmc_create; the two give bit-identical results. KMC_FUSED=0 in the environment forces 0. */
+int kmc_get_step_path(kmc_handle *h);
 /* molecules currently held by the handle (all of n_receptor / n_ligand x replicas unless strips made them capacities) */
 int kmc_get_live_counts(kmc_handle *h, int32_t *n_rec, int32_t *n_lig);
 

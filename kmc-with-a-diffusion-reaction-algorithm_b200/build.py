@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.environ.get("KMC_LIB_OUT") or os.path.join(HERE, "libkmc_b200.so")
 SRC = [os.path.join(HERE, "csrc", "kmc_engine.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("kmc_engine.cu", "kmc_kernels.cu", "kmc_strips.cu", "kmc_init.cu", "kmc_device.cuh", "kmc_geom.cuh", "kmc_philox.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("kmc_engine.cu", "kmc_kernels.cu", "kmc_small.cu", "kmc_strips.cu", "kmc_init.cu", "kmc_device.cuh", "kmc_geom.cuh", "kmc_philox.cuh")] + \
        [os.path.join(HERE, "..", "include", "kmc_b200.h")]
 
 
@@ -23,7 +23,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-o", LIB] + SRC
-    for k in ("TS", "TTHREADS", "TCAP", "NSURV", "TMINB", "KMC_TILE_TIMING", "CTHREADS", "CSURV", "CMINB", "PMINB", "PTHREADS", "RECMINB", "LIGMINB", "PE_CHUNK", "RP_CHUNK", "RPTHREADS"):          # tile-kernel tuning knobs (experiments only)
+    for k in ("TS", "TTHREADS", "TCAP", "NSURV", "TMINB", "KMC_TILE_TIMING", "CTHREADS", "CSURV", "CMINB", "PMINB", "PTHREADS", "RECMINB", "LIGMINB", "PE_CHUNK", "RP_CHUNK", "RPTHREADS", "SMALL_T", "SMALL_MINB"):          # tile-kernel tuning knobs (experiments only)
         if os.environ.get("KMC_" + k):
             cmd.insert(1, "-D%s=%s" % (k, os.environ["KMC_" + k]))
     if verbose:

@@ -84,6 +84,9 @@ struct Dev {
     unsigned long long *events;
     int ncell;
     int nAcap;                             // = Consts::NAt (receptor gids are below it): for helpers that only get the Dev
+    // fused small-system step (k_small_step, phase 2): the CTA of a replica keeps an fp32 search record per molecule in shared
+    // memory -- old centre xy, search radius of the molecule this step -- indexed by the molecule's number inside the replica
+    float4 *smallCen; int smallRecBase, smallLigBase;      // local index = gid - smallRecBase (receptor) / gid - smallLigBase (ligand)
 };
 
 #define GHOST_BIT 0x40000000

@@ -3,7 +3,8 @@
 // There is no CPU compute path in this file: every stage of the sweep is a kernel in kmc_kernels.cu.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
-#define KMC_NKERNELS 21
+#include "kmc_small.cu"
+#define KMC_NKERNELS 22
 #define MON_EVERY 256
 
 #include <algorithm>
@@ -65,6 +66,7 @@ struct kmc_handle {
     unsigned long long *timeline = nullptr; int tlCount = 0, tlId[64]; cudaStream_t tlStream = nullptr;      // KMC_TIMELINE
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
+    bool fused = false;              // small replicas: the whole step is ONE kernel, one CTA per replica, many steps per launch (csrc/kmc_small.cu)
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
     // (asynchronously) and the copy of the PREVIOUS interval is examined -- capacity overflows are reported and the list-reuse
     // back-off is decided without ever stalling the stream
@@ -81,10 +83,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_cx_rebuild", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small", "k_step_begin"};
+    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small", "k_step_begin", "k_small_step"};
 enum { KID_UF_INIT = 0, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
-       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL, KID_STEP_BEGIN };
+       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL, KID_STEP_BEGIN, KID_SMALL_STEP };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -290,7 +292,10 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     if ((int64_t)K.R * K.ncx * K.ncy >= (1LL << 31) - 2) return fail(KMC_ERR_INVALID, "neighbour grid too large: raise cell_edge");
     Dev &D = h->D; memset(&D, 0, sizeof D);
     D.ncell = K.R * K.ncx * K.ncy; D.nAcap = K.NAt;
-    D.candCap = std::max(1 << 14, K.NAt / 8);
+    // systems that fit a CTA's shared-memory records take the fused step (KMC_FUSED=0, or an explicit KMC_RESOLVE, keeps the general path)
+    h->fused = K.NA + K.NB <= SMALL_MAXN && K.NB <= SMALL_MAXNB && std::max(p->box[0], p->box[1]) <= 2.0e5 &&
+               !(getenv("KMC_FUSED") && atoi(getenv("KMC_FUSED")) == 0) && !getenv("KMC_RESOLVE");
+    D.candCap = std::max({1 << 14, K.NAt / 8, h->fused ? 64 * K.R : 0});
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     // the side branches of the step graph carry the latency-bound kernels (complexes, special entries): few CTAs with long serial
     // chains. Highest priority, so that their CTAs are dispatched ahead of the streaming kernels' remaining CTAs and run underneath them
@@ -315,7 +320,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     A(sorted, (size_t)2 * K.NT); A(molSlot, K.NT);
     ok = ok && ensure_cells_arrays(h); A(farList, K.NT);
     A(candRL, (size_t)2 * D.candCap); A(candCis, (size_t)2 * D.candCap);
-    D.pairCap = std::max(1 << 16, 4 * K.NAt);
+    D.pairCap = std::max({1 << 16, 4 * K.NAt, h->fused ? 8 * K.NAt + 64 * K.R : 0});      // (the fused step deals every replica an equal slice of the lists)
     A(pairs, D.pairCap); A(unitRes, K.NT); A(pendCnt, K.NT); A(rejList, K.NT); A(rejPartner, K.NT); D.pendCap = 2 * K.NT + 4096;
     if (const char *o = getenv("KMC_TEST_PENDCAP")) D.pendCap = std::max(1, atoi(o));      // tests: force the overflow report
     A(pendList, D.pendCap); A(step64, 1);
@@ -677,6 +682,22 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
     if (n < 0) { h->err = "kmc_step: negative step count"; return KMC_ERR_INVALID; }
     int rc = select_device(h); if (rc) return rc;
     cudaStream_t st = h->stream;
+    if (h->fused) {
+        // one launch advances every replica by up to 8192 steps; S4 is a pointer swap inside the kernel, so an odd count leaves
+        // the committed state in the other buffer set
+        for (int64_t left = n; left > 0;) {
+            if (h->sinceMon >= MON_EVERY) { rc = monitor_poll(h); if (rc) return rc; }
+            const int chunk = (int)std::min<int64_t>(left, 8192);
+            Args A{h->D, h->K};
+            A.K.phase = 2;
+            LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->R, SMALL_T, 0, st>>>(A, (unsigned long long)h->step_done, chunk)));
+            if (chunk & 1) { swap_buffers(h->D); h->parity ^= 1; }
+            h->step_done += chunk; h->passes += chunk; h->sinceMon += chunk; left -= chunk;
+            h->stepped = true;
+        }
+        CK(cudaGetLastError());
+        return KMC_OK;
+    }
     for (int64_t it = 0; it < n; it++) {
         if (h->sinceMon >= MON_EVERY) { rc = monitor_poll(h); if (rc) return rc; }
         if (!h->profiling && h->use_graph && !h->gexec[0][0]) { rc = ensure_graphs(h); if (rc) return rc; }
@@ -877,6 +898,8 @@ extern "C" int kmc_get_accept(kmc_handle *h, int32_t rep, int32_t *accepted) {
     for (int b = 0; b < h->NB; b++) accepted[h->NA + 1 + b] = st[unitOf[h->NAt + rep * h->NB + b]] == 0;
     return KMC_OK;
 }
+
+extern "C" int kmc_get_step_path(kmc_handle *h) { return h ? (h->fused ? 1 : 0) : KMC_ERR_INVALID; }
 
 extern "C" int kmc_get_live_counts(kmc_handle *h, int32_t *n_rec, int32_t *n_lig) {
     if (!h) return KMC_ERR_INVALID;

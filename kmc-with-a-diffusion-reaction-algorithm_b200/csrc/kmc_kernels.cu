@@ -245,9 +245,29 @@ KD void register_special(const Consts &cK, const Dev &D, int entry, int cell, un
 //    has drifted more than K.drift from its entry, is SPECIAL: the stale structures do not cover it, k_special_pairs does.
 // oz / nz: height of a ligand's centre (0 for a receptor), kept as fp32 in the record: the resolve kernels use it to discard
 // pairs that are close in the membrane plane but far apart in z before any bead is fetched. bc = D.bcen[gid], loaded by the caller.
+// fp32 centre of the molecule's grid entry: only list-reuse steps (phase 1) measure drift from it
+KD float2 entry_centre(const Consts &K, const Dev &D, int gid) { return K.phase == 1 ? D.bcen[gid] : make_float2(0.f, 0.f); }
+// half of the largest centre-centre distance at which two molecules can still matter to each other (overlap or S3), split per
+// molecule so that the pair radius is a sum: receptor-receptor max(2 rA, cis reach), ligand-ligand reachLL, receptor-ligand
+// max(reachRL, reachOn) all fit under w(a) + w(b) (the receptor's share is raised until the mixed pair is covered)
+KD float search_share(const Consts &K, bool rec) {
+    const float wl = 0.5f * (float)K.reachLL;
+    return rec ? fmaxf(0.5f * fmaxf((float)K.ovAA, (float)K.reachCis), fmaxf((float)K.reachRL, (float)K.reachOn) - wl) : wl;
+}
 KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, double nx, double ny, double oz, double nz, int ukey, int freeFlags,
                  unsigned stamp, float2 bc) {
     const double dx = nx - ox, dy = ny - oy;
+    if (cK.phase == 2) {
+        // fused small-system step: no grid, no far movers (the CTA cuts ALL pairs of its replica, so a record with both poses is
+        // complete whatever the displacement). Search record: old centre + (share of the reach + displacement of this step), so that
+        // any pose combination of a pair within reach implies |O_a - O_b| <= r(a) + r(b) (triangle inequality)
+        const bool rec = gid < cK.NAt;
+        D.smallCen[rec ? gid - D.smallRecBase : gid - D.smallLigBase] = make_float4((float)ox, (float)oy, search_share(cK, rec) + (float)sqrt(dx * dx + dy * dy) * 1.0001f + 0.125f, 0.f);
+        double2 *nr = reinterpret_cast<double2 *>(D.nrec) + (size_t)gid * 3;
+        nr[0] = make_double2(ox, oy); nr[1] = make_double2(nx, ny);
+        reinterpret_cast<int4 *>(nr)[2] = make_int4(__float_as_int((float)oz), ukey, freeFlags, __float_as_int((float)nz));
+        return;
+    }
     const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
     const int rep = replica_of_gid(cK, gid);
     int flags = freeFlags | (far ? F_FAR : 0);
@@ -286,7 +306,7 @@ KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile, int n
         __pipeline_memcpy_async(&S.c[t], &D.recC[gid], 16); __pipeline_memcpy_async(&S.s2[t], &D.recS2[gid], 16);
         __pipeline_memcpy_async(&S.s3[t], &D.recS3[gid], 16);
         __pipeline_memcpy_async(&S.head[t], &D.unitOf[gid], 4); __pipeline_memcpy_async(&S.cis[t], &D.recCis[gid], 4);
-        if (K.phase) __pipeline_memcpy_async(&S.bc[t], &D.bcen[gid], 8);
+        if (K.phase == 1) __pipeline_memcpy_async(&S.bc[t], &D.bcen[gid], 8);
         if (D.refA) __pipeline_memcpy_async(&S.ref[t], &D.refA[gid], 4);          // strips: the reference id keys the random stream
     }
 }
@@ -311,7 +331,7 @@ KD void propose_rec_body(const Args &A) {
         const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
         if (gid < nLive) {
             Rec ra; ra.cx = S.c[t].x; ra.cy = S.c[t].y; ra.s2x = S.s2[t].x; ra.s2y = S.s2[t].y; ra.s3x = S.s3[t].x; ra.s3y = S.s3[t].y;
-            propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase ? S.bc[t] : make_float2(0.f, 0.f), D.refA ? S.ref[t] : ref_id(K, D, gid));
+            propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase == 1 ? S.bc[t] : make_float2(0.f, 0.f), D.refA ? S.ref[t] : ref_id(K, D, gid));
         }
     }
     __pipeline_wait_prior(0);
@@ -374,7 +394,7 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
             store_rec(D.recCn, D.recS2n, D.recS3n, a, na);
             store_rec(D.recCn, D.recS2n, D.recS3n, p, nb);
             mark_far(cK, D, a, ra.cx, ra.cy, na.cx, na.cy, 0.0, 0.0, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp, bc);
-            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, 0.0, 0.0, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp, K.phase ? D.bcen[p] : bc);
+            mark_far(cK, D, p, rb.cx, rb.cy, nb.cx, nb.cy, 0.0, 0.0, unit_key(K, a, ra.cx, ra.cy), F_FREE_RL, stamp, K.phase == 1 ? D.bcen[p] : bc);
             if (K.mode) { const int key = unit_key(K, a, ra.cx, ra.cy); D.ukey[a] = key; D.ukey[p] = key; }
         }
         D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
@@ -396,6 +416,30 @@ __global__ void __launch_bounds__(256, RECMINB) k_propose_rec(const __grid_const
 // and rotation (each point's arithmetic is exactly the reference's, the points are independent), which halves the register
 // footprint of holding all eight points and doubles the warps an SM can keep in flight. Moved rows go back with bulk stores
 // (shared -> global); rows of ligands that do not move here (members of complexes: the complex kernels write those) are not stored.
+// S2c for one free ligand (main.cpp:905-969), split so that a caller can carry the eight points through it one at a time:
+// the centre decides the wrap and the reflection of the whole body and is the pivot of the rotation; every other point is
+// shifted, reflected, wrapped and rotated about the new centre (the points are independent; each one's arithmetic is the reference's)
+struct LigMove { double shx, shy, shz, PBx, PBy, twoPBz, c[3]; Rot3 R3; bool reflect; };
+KD void lig_move_setup(const Consts &K, LigMove &M, double ox, double oy, double oz, double u0, double u1, double u2, double u3, double u4, double u5) {
+    const double amp = mul(K.ampB, u0);
+    const double theta = mul(u1, K.pai), phai = mul(mul(u2, 2.0), K.pai);
+    double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
+    M.shx = mul(mul(amp, st), cp); M.shy = mul(mul(amp, st), sp); M.shz = mul(amp, ct);
+    const double c0x = add(ox, M.shx), c0y = add(oy, M.shy), c0z = add(oz, M.shz);
+    M.PBx = wrap_offset(c0x, K.Lx); M.PBy = wrap_offset(c0y, K.Ly);
+    M.reflect = c0z > K.Lz || c0z < 0;
+    M.twoPBz = M.reflect ? mul(2.0, mul(K.Lz, round(dvd(c0z, K.Lz)))) : 0.0;      // main.cpp:925-931
+    M.c[0] = sub(c0x, M.PBx); M.c[1] = sub(c0y, M.PBy); M.c[2] = M.reflect ? add(-c0z, M.twoPBz) : c0z;
+    const double rt = mul(sub(mul(2.0, u3), 1.0), K.rotB), rp = mul(sub(mul(2.0, u4), 1.0), K.rotB),
+                 rs = mul(sub(mul(2.0, u5), 1.0), K.rotB);
+    M.R3 = euler(rt, rp, rs);
+}
+KD void lig_move_point(const LigMove &M, double x, double y, double z, double o[3]) {
+    double pt[3] = {add(x, M.shx), add(y, M.shy), add(z, M.shz)};
+    if (M.reflect) pt[2] = add(-pt[2], M.twoPBz);
+    pt[0] = sub(pt[0], M.PBx); pt[1] = sub(pt[1], M.PBy);
+    rot3_about(M.R3, pt, M.c, o);
+}
 #define LIG_TILE 128
 KD uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 KD void mbar_init(uint64_t *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -428,7 +472,7 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
     else mbar_arrive_tx(&bar, 0);
     // the scalar words of this thread's ligand travel in the same latency window as the tile
     int head = -1, csize = 0; float2 bc = make_float2(0.f, 0.f); uint32_t me = 0;
-    if (live) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase) bc = D.bcen[gid]; me = ref_id(K, D, gid); }
+    if (live) { head = D.unitOf[gid]; csize = D.cxSize[h]; if (K.phase == 1) bc = D.bcen[gid]; me = ref_id(K, D, gid); }
     const bool act = live && head == gid && csize <= 1;     // a free ligand (complexes: the complex kernels)
     double u0, u1, u2, u3, u4, u5;
     if (act) {          // the draws do not need the pose: they overlap the copy
@@ -438,25 +482,11 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
     mbar_wait(&bar, 0);
     if (act) {
         const double ox = row[0], oy = row[1], oz = row[2];
-        const double amp = mul(K.ampB, u0);
-        const double theta = mul(u1, K.pai), phai = mul(mul(u2, 2.0), K.pai);
-        double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
-        const double shx = mul(mul(amp, st), cp), shy = mul(mul(amp, st), sp), shz = mul(amp, ct);
-        // the centre first: it decides the wrap and the reflection of the whole body and is the pivot of the rotation
-        const double c0x = add(ox, shx), c0y = add(oy, shy), c0z = add(oz, shz);
-        const double PBx = wrap_offset(c0x, K.Lx), PBy = wrap_offset(c0y, K.Ly);
-        const bool reflect = c0z > K.Lz || c0z < 0;
-        const double twoPBz = reflect ? mul(2.0, mul(K.Lz, round(dvd(c0z, K.Lz)))) : 0.0;      // main.cpp:925-931
-        double c[3] = {sub(c0x, PBx), sub(c0y, PBy), reflect ? add(-c0z, twoPBz) : c0z};
-        const double rt = mul(sub(mul(2.0, u3), 1.0), K.rotB), rp = mul(sub(mul(2.0, u4), 1.0), K.rotB),
-                     rs = mul(sub(mul(2.0, u5), 1.0), K.rotB);
-        const Rot3 R3 = euler(rt, rp, rs);
+        LigMove M; lig_move_setup(K, M, ox, oy, oz, u0, u1, u2, u3, u4, u5);
+        const double *c = M.c;
 #pragma unroll 1
         for (int q = 1; q < 8; q++) {
-            double pt[3] = {add(row[3 * q], shx), add(row[3 * q + 1], shy), add(row[3 * q + 2], shz)};
-            if (reflect) pt[2] = add(-pt[2], twoPBz);
-            pt[0] = sub(pt[0], PBx); pt[1] = sub(pt[1], PBy);
-            double o[3]; rot3_about(R3, pt, c, o);
+            double o[3]; lig_move_point(M, row[3 * q], row[3 * q + 1], row[3 * q + 2], o);
             row[3 * q] = o[0]; row[3 * q + 1] = o[1]; row[3 * q + 2] = o[2];
         }
         row[0] = c[0]; row[1] = c[1]; row[2] = c[2];          // t*(0)+c = c exactly (main.cpp:958-966)
@@ -819,8 +849,8 @@ __device__ __noinline__ void complex_move_serial(const Args &A, int h0, int size
     for (int q = 0; q < size; q++) {
         const int m = rowOut[q];
         if (K.mode) D.ukey[m] = ckey;
-        if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, 0.0, 0.0, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
-        else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], o[2], n[2], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f)); }
+        if (m < K.NAt) { double2 o = D.recC[m], n = D.recCn[m]; mark_far(cK, D, m, o.x, o.y, n.x, n.y, 0.0, 0.0, ckey, (D.recLig[m] < 0 ? F_FREE_RL : 0) | (D.recCis[m] < 0 ? F_FREE_CIS : 0), stamp, entry_centre(K, D, m)); }
+        else { const double *o = D.lig + (size_t)(m - K.NAt) * 24, *n = D.lign + (size_t)(m - K.NAt) * 24; const int *occ = D.ligRec + (size_t)(m - K.NAt) * 3; mark_far(cK, D, m, o[0], o[1], n[0], n[1], o[2], n[2], ckey, (occ[0] < 0 || occ[1] < 0 || occ[2] < 0) ? F_FREE_RL : 0, stamp, entry_centre(K, D, m)); }
     }
 }
 // Single-ligand complex (S2d + S2e), the commonest kind: ligand h0, the receptors on its sites and their ligand-free cis partners
@@ -880,7 +910,7 @@ KD bool single_ligand_move(const Args &A, int h0, int size, uint64_t step, unsig
     store_lig(D.lign, h0, L);
     const int ckey = unit_key(K, rootGid, ox, oy);
     const bool freeSite = a[0] < 0 || a[1] < 0 || a[2] < 0;
-    mark_far(cK, D, rootGid, ox, oy, L.p[0][0], L.p[0][1], oz, L.p[0][2], ckey, freeSite ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[rootGid] : make_float2(0.f, 0.f));
+    mark_far(cK, D, rootGid, ox, oy, L.p[0][0], L.p[0][1], oz, L.p[0][2], ckey, freeSite ? F_FREE_RL : 0, stamp, entry_centre(K, D, rootGid));
     if (K.mode) D.ukey[rootGid] = ckey;
     // every receptor (rigid move, snap onto its site: 1196-1233), then its partner (rigid move, snap onto the receptor: 1237-1274)
     for (int s = 0; s < 3; s++) {
@@ -889,19 +919,37 @@ KD bool single_ligand_move(const Args &A, int h0, int size, uint64_t step, unsig
         shift_pose(&r.cx, true, shx, shy, false); shift_pose(&r.cx, true, PBx, PBy, true); rotate_pose(&r.cx, true, cs, ss, cmx, cmy, cmz);
         if (rl_misaligned(K, L, s, r)) snap_rec_to_lig(K, r, L, s);
         store_rec(D.recCn, D.recS2n, D.recS3n, a[s], r);
-        mark_far(cK, D, a[s], ca[s].x, ca[s].y, r.cx, r.cy, 0.0, 0.0, ckey, p[s] < 0 ? F_FREE_CIS : 0, stamp, K.phase ? D.bcen[a[s]] : make_float2(0.f, 0.f));
+        mark_far(cK, D, a[s], ca[s].x, ca[s].y, r.cx, r.cy, 0.0, 0.0, ckey, p[s] < 0 ? F_FREE_CIS : 0, stamp, entry_centre(K, D, a[s]));
         if (K.mode) D.ukey[a[s]] = ckey;
         if (p[s] < 0) continue;
         Rec r2 = load_rec(D.recC, D.recS2, D.recS3, p[s]);
         shift_pose(&r2.cx, true, shx, shy, false); shift_pose(&r2.cx, true, PBx, PBy, true); rotate_pose(&r2.cx, true, cs, ss, cmx, cmy, cmz);
         if (cis_misaligned(K, r, r2)) snap_cis(K, r2, r);
         store_rec(D.recCn, D.recS2n, D.recS3n, p[s], r2);
-        mark_far(cK, D, p[s], cp_[s].x, cp_[s].y, r2.cx, r2.cy, 0.0, 0.0, ckey, F_FREE_RL, stamp, K.phase ? D.bcen[p[s]] : make_float2(0.f, 0.f));
+        mark_far(cK, D, p[s], cp_[s].x, cp_[s].y, r2.cx, r2.cy, 0.0, 0.0, ckey, F_FREE_RL, stamp, entry_centre(K, D, p[s]));
         if (K.mode) D.ukey[p[s]] = ckey;
     }
     return true;
 }
 
+// one complex moved by one thread (S2d + S2e/S2f): the three-round single-ligand path where the shape allows it, the generic serial code otherwise
+KD void complex_move_thread(const Args &A, int h0, bool maybeSingle, uint64_t step, unsigned stamp) {
+    KARGS
+    const Consts &K = cK;
+    const int rootGid = K.NAt + h0;
+    const int size = D.cxSize[h0];
+    const uint64_t seed = seed_of(cK, h0 / K.NB);
+    const uint32_t me = ref_id(K, D, rootGid);
+    double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
+    const double u2 = keyed_uniform(seed, me, 0, step, 2);
+    if (!maybeSingle || !single_ligand_move(A, h0, size, step, stamp, u0, u1, u2)) {
+        const int *rowIn = D.members + D.cxOff[h0];
+        int nB = 0;
+        for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;
+        complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);
+    }
+    D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0;
+}
 // small complexes (the bulk of an oligomerised membrane: 2-12 members): one THREAD per complex. The alignment is a serial,
 // branchy algorithm; a warp per complex leaves 31 of 32 lanes idle in it, a thread per complex runs 32 of them per warp.
 __global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_constant__ Args A) {
@@ -913,19 +961,7 @@ __global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_cons
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < ncx; ci += gridDim.x * blockDim.x) {
         if (ci >= n1 && ci < n1pad) continue;
-        const int h0 = ci < n1 ? D.cxRoots[ci] : D.cxRoots[K.NBt + ci - n1pad], rootGid = K.NAt + h0;
-        const int size = D.cxSize[h0];
-        const uint64_t seed = seed_of(cK, h0 / K.NB);
-        const uint32_t me = ref_id(K, D, rootGid);
-        double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
-        const double u2 = keyed_uniform(seed, me, 0, step, 2);
-        if (ci >= n1 || !single_ligand_move(A, h0, size, step, stamp, u0, u1, u2)) {
-            const int *rowIn = D.members + D.cxOff[h0];
-            int nB = 0;
-            for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;
-            complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);
-        }
-        D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0;
+        complex_move_thread(A, ci < n1 ? D.cxRoots[ci] : D.cxRoots[K.NBt + ci - n1pad], ci < n1, step, stamp);
     }
 }
 
@@ -1011,11 +1047,11 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 if (m < K.NAt) {
                     const Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]};
                     store_rec(D.recCn, D.recS2n, D.recS3n, m, r);
-                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, 0.0, 0.0, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0), stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f));
+                    const double2 o = D.recC[m]; mark_far(cK, D, m, o.x, o.y, r.cx, r.cy, 0.0, 0.0, ckey, (S.lig[i] < 0 ? F_FREE_RL : 0) | (S.cis[i] < 0 ? F_FREE_CIS : 0), stamp, entry_centre(K, D, m));
                 } else {
                     double *q = D.lign + (size_t)(m - K.NAt) * 24;
                     for (int t = 0; t < 24; t++) q[t] = p[t];
-                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], o[2], p[2], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0, stamp, K.phase ? D.bcen[m] : make_float2(0.f, 0.f));
+                    const double *o = D.lig + (size_t)(m - K.NAt) * 24; mark_far(cK, D, m, o[0], o[1], p[0], p[1], o[2], p[2], ckey, (S.rec3[i][0] < 0 || S.rec3[i][1] < 0 || S.rec3[i][2] < 0) ? F_FREE_RL : 0, stamp, entry_centre(K, D, m));
                 }
             }
         } else if (lane == 0) complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);      // larger than the cache
@@ -1871,9 +1907,10 @@ KD void react_resolve_block(const Dev &D) {
             touch_molecule(D, a);
             if (variant == 1) ev_mono++; else ev_cis++;
         }
-    if (ev_rl | ev_mono | ev_cis) {
-        D.events[EV_RL_ON] += ev_rl; D.events[EV_MONO_ON] += ev_mono; D.events[EV_CIS_ON] += ev_cis;
-    }
+    // (atomic: in the fused small-system step every replica's CTA applies its own candidates)
+    if (ev_rl) atomicAdd(&D.events[EV_RL_ON], (unsigned long long)ev_rl);
+    if (ev_mono) atomicAdd(&D.events[EV_MONO_ON], (unsigned long long)ev_mono);
+    if (ev_cis) atomicAdd(&D.events[EV_CIS_ON], (unsigned long long)ev_cis);
 }
 
 // S3c, main.cpp:2062-2141, for receptor a with ligand h / cis partner p (-1 none). Keyed draws make the three sequential loops order
@@ -1910,8 +1947,7 @@ KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, i
 //     rejection time for a receptor-headed one -- whatever S3 did to the bonds since.
 // (2) Dissociation: a thread takes four consecutive receptors; their bond words arrive as two 16-byte loads, and on a
 //     membrane with few bonds that is all the kernel reads (8 bytes per receptor).
-KD void finish_body(const Consts &K, const Dev &D, int tid, int nth) {
-    const int nLiveA = nA_live(D);
+KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, int aEnd) {      // receptors [aBeg, aEnd) take their dissociation trials here
     const int nrej = min(D.scal[S_NREJ], K.NT);
     if (tid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
     for (int i = tid; i < nrej; i += nth) {
@@ -1922,7 +1958,7 @@ KD void finish_body(const Consts &K, const Dev &D, int tid, int nth) {
         else { const int *row = D.members + D.cxOff[h]; for (int q = 0; q < size; q++) restore_pose(K, D, row[q]); }
     }
     const uint64_t step = D.step64[0];
-    for (int a0 = tid * 4; a0 < nLiveA; a0 += nth * 4) {
+    for (int a0 = (aBeg & ~3) + tid * 4; a0 < aEnd; a0 += nth * 4) {
         int hh[4] = {-1, -1, -1, -1}, pp[4] = {-1, -1, -1, -1};
         if (a0 + 3 < K.NAt) {
             const int4 hv = *reinterpret_cast<const int4 *>(D.recLig + a0), pv = *reinterpret_cast<const int4 *>(D.recCis + a0);
@@ -1930,7 +1966,7 @@ KD void finish_body(const Consts &K, const Dev &D, int tid, int nth) {
         } else for (int k = 0; k < 4; k++) if (a0 + k < K.NAt) { hh[k] = D.recLig[a0 + k]; pp[k] = D.recCis[a0 + k]; }
         if ((hh[0] & hh[1] & hh[2] & hh[3] & pp[0] & pp[1] & pp[2] & pp[3]) < 0) continue;      // all eight words negative: no bond on any of the four
         for (int k = 0; k < 4; k++)
-            if (a0 + k < nLiveA && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
+            if (a0 + k >= aBeg && a0 + k < aEnd && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
     }
 }
 
@@ -1947,7 +1983,7 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
 #endif
 __global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) { KARGS react_pairs_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void k_react_resolve(const __grid_constant__ Args A) { KARGS react_resolve_block(D); }
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, nA_live(D)); }
 
 // ------------------------------------------------------------------------------------------------
 // outputs (bond.dat columns, main.cpp:2251)

@@ -136,6 +136,7 @@ extern "C" int kmc_strip_configure(kmc_handle *h, int32_t rank, int32_t nranks, 
     CK(cudaSetDevice(h->P.device));
     Consts &K = h->K; Dev &D = h->D;
     K.strips = nranks; K.stripRank = rank; K.stripXc = -K.Lx / 2 + (rank + 0.5) * width; K.stripHalf = nranks > 1 ? K.Lx / 2 : INFINITY;
+    h->fused = false;          // (strips renumber and migrate molecules: the general path)
     h->strip_on = true; h->strip_W = halo_width; h->strip_lo = -K.Lx / 2 + rank * width; h->strip_hi = h->strip_lo + width;
     if (nranks > 1) {        // the grid only has to cover the strip and its halos (in the periodic frame of the strip)
         const double edge = 1.0 / K.cellInv;

@@ -37,7 +37,7 @@ class Series(C.Structure):
 
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
-           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_write_bond_dat",
+           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_get_step_path", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_timeline_print", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_halo_width", "kmc_strip_unique_id",
            "kmc_strip_comm_init", "kmc_strip_refresh", "kmc_strip_refresh_local", "kmc_strip_get_series", "kmc_strip_get_oligomer_hist",
@@ -89,6 +89,7 @@ def lib():
         L.kmc_get_accept.argtypes = [vp, i32, vp]
         L.kmc_get_events.argtypes = [vp, vp]
         L.kmc_get_live_counts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.kmc_get_step_path.argtypes = [vp]
         L.kmc_strip_configure.argtypes = [vp, i32, i32, C.c_double]
         L.kmc_strip_load_global.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64]
         L.kmc_strip_begin_refresh.argtypes = [vp]
@@ -417,6 +418,10 @@ class Kmc:
         a, b = C.c_int32(), C.c_int32()
         self._ck(lib().kmc_get_live_counts(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def path(self):
+        """'fused' (small replicas: one CTA per replica, the whole step in one kernel) or 'general' (one CUDA graph per step)"""
+        return "fused" if self._ck(lib().kmc_get_step_path(self.h)) == 1 else "general"
 
     def events(self):
         e = np.zeros(16, dtype=np.int64)
