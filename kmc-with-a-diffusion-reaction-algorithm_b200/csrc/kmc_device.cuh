@@ -84,10 +84,26 @@ struct Dev {
     unsigned long long *events;
     int ncell;
     int nAcap;                             // = Consts::NAt (receptor gids are below it): for helpers that only get the Dev
-    // fused small-system step (k_small_step, phase 2): the CTA of a replica keeps an fp32 search record per molecule in shared
-    // memory -- old centre xy, search radius of the molecule this step -- indexed by the molecule's number inside the replica
-    float4 *smallCen; int smallRecBase, smallLigBase;      // local index = gid - smallRecBase (receptor) / gid - smallLigBase (ligand)
+    // fused small-system step (k_small_step, phase 2): the search records of the replica, in the shared memory of its CTA
+    struct SmallSearch *small;
 };
+
+// Search records of one replica in the fused small-system step (csrc/kmc_small.cu), indexed by the molecule's number inside the
+// replica (receptors first). Written by mark_far (phase 2) for every molecule once per step, read by the CTA's pair search.
+#define SMALL_MAXN 256        // molecules per replica the records hold
+#define SMALL_SPEC 32
+struct SmallSearch {
+    float4 cen[SMALL_MAXN];            // old centre (x, y), search radius of the molecule this step (its share of the reach + its displacement), displacement
+    float2 ref[SMALL_MAXN];            // centre when the pair list was built
+    int2 meta[SMALL_MAXN];             // unit key, free-site flags: with the centres of the resident poses, the neighbour record the general path keeps in D.nrec
+    unsigned char isSpec[SMALL_MAXN];  // this step the molecule may be further than dmax from its list centre: the list does not cover it
+    int spec[SMALL_SPEC];              // those molecules
+    int nspec;
+    int recBase, ligBase, N;           // local index = gid - recBase (receptor) / gid - ligBase (ligand)
+    float dmax;                        // drift the pair list allows for
+    float share[2];                    // search_share of a ligand [0] / a receptor [1]
+};
+KD int small_index(const Consts &K, const Dev &D, int gid) { return gid < K.NAt ? gid - D.small->recBase : gid - D.small->ligBase; }
 
 #define GHOST_BIT 0x40000000
 #define TOUCH_CAP 256
@@ -146,9 +162,10 @@ KD int cell_of(const Consts &K, int replica, double x, double y) {
     cx = min(max(cx, 0), K.ncx - 1); cy = min(max(cy, 0), K.ncy - 1);
     return (replica * K.ncy + cy) * K.ncx + cx;
 }
-KD int replica_of_gid(const Consts &K, int gid) { return K.R == 1 ? 0 : (gid < K.NAt ? gid / K.NA : (gid - K.NAt) / K.NB); }
+KD int replica_of_gid(const Consts &K, int gid) { return K.phase == 2 ? K.smallRep : (K.R == 1 ? 0 : (gid < K.NAt ? gid / K.NA : (gid - K.NAt) / K.NB)); }
 // reference molecule id (1-based) used to key the random stream
 KD uint32_t ref_id(const Consts &K, const Dev &D, int gid) {
+    if (K.phase == 2) return gid < K.NAt ? (uint32_t)(gid - K.smallRep * K.NA + 1) : (uint32_t)(gid - K.NAt - K.smallRep * K.NB + K.NA + 1);
     if (D.refA) return gid < K.NAt ? D.refA[gid] : D.refB[gid - K.NAt];
     if (K.R == 1) return (uint32_t)(gid + 1);          // one replica: no integer division on the hot path
     return gid < K.NAt ? (uint32_t)(gid % K.NA + 1) : (uint32_t)(K.NA + (gid - K.NAt) % K.NB + 1);

@@ -295,6 +295,11 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     // systems that fit a CTA's shared-memory records take the fused step (KMC_FUSED=0, or an explicit KMC_RESOLVE, keeps the general path)
     h->fused = K.NA + K.NB <= SMALL_MAXN && K.NB <= SMALL_MAXNB && std::max(p->box[0], p->box[1]) <= 2.0e5 &&
                !(getenv("KMC_FUSED") && atoi(getenv("KMC_FUSED")) == 0) && !getenv("KMC_RESOLVE");
+    if (h->fused) {          // (poses and bond table of a replica live in the shared memory of its CTA)
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k_small_step) != cudaSuccess || fa.sharedSizeBytes + small_dyn_bytes(K.NA, K.NB) > (size_t)prop.sharedMemPerBlockOptin ||
+            cudaFuncSetAttribute(k_small_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_dyn_bytes(K.NA, K.NB)) != cudaSuccess) { h->fused = false; cudaGetLastError(); }
+    }
     D.candCap = std::max({1 << 14, K.NAt / 8, h->fused ? 64 * K.R : 0});
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     // the side branches of the step graph carry the latency-bound kernels (complexes, special entries): few CTAs with long serial
@@ -690,7 +695,7 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
             const int chunk = (int)std::min<int64_t>(left, 8192);
             Args A{h->D, h->K};
             A.K.phase = 2;
-            LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->R, SMALL_T, 0, st>>>(A, (unsigned long long)h->step_done, chunk)));
+            LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->R, SMALL_T, small_dyn_bytes(h->NA, h->NB), st>>>(A, (unsigned long long)h->step_done, chunk)));
             if (chunk & 1) { swap_buffers(h->D); h->parity ^= 1; }
             h->step_done += chunk; h->passes += chunk; h->sinceMon += chunk; left -= chunk;
             h->stepped = true;

@@ -44,7 +44,8 @@ struct Consts {
     double reachRR, reachRL, reachLL, reachOn, reachCis;   // centre-centre search bounds (with margin)
     double skin;                              // far-mover threshold
     double drift;                             // list reuse: a molecule further than this from its grid entry is 'displaced' (0 = grid rebuilt every step)
-    int phase;                                // 0 = this step rebuilds the neighbour grid and the pair list, 1 = it reuses them
+    int phase;                                // 0 = this step rebuilds the neighbour grid and the pair list, 1 = it reuses them, 2 = fused small-system step (csrc/kmc_small.cu)
+    int smallRep;                             // phase 2: the replica this CTA's view stands for (spares the hot path every division by NA / NB)
     float cutMargin;                          // slack of the fp32 distance cut of k_cells_cut (covers the rounding of coordinates to fp32)
     double gx0, gy0, cellInv; int ncx, ncy;   // neighbour grid
     int tileEdge;                             // k_resolve_tiles: cells per tile edge

@@ -103,7 +103,7 @@ KD void build_member_row(const Consts &K, const Dev &D, int h, int size, int *ro
 KD void note_max_complex(const Consts &K, const Dev &D, int h, int size) {
     // main.cpp:896-898 (read first: one hot address). With strips only the rank that owns the root counts it: a halo copy in the
     // outer (possibly stale) part of the halo may show a complex the true trajectory never had
-    if (size > D.maxComplex[h / K.NB] && (K.strips <= 1 || d_strip_owner(K, D.lig[(size_t)h * 24]) == K.stripRank)) atomicMax(&D.maxComplex[h / K.NB], size);
+    if (size > D.maxComplex[replica_of_gid(K, K.NAt + h)] && (K.strips <= 1 || d_strip_owner(K, D.lig[(size_t)h * 24]) == K.stripRank)) atomicMax(&D.maxComplex[replica_of_gid(K, K.NAt + h)], size);
 }
 
 // First kernel of a step (one warp; begin = 0: only the complex tables, for the strip refresh). Lane 0
@@ -258,14 +258,22 @@ KD void mark_far(const Consts &cK, const Dev &D, int gid, double ox, double oy, 
                  unsigned stamp, float2 bc) {
     const double dx = nx - ox, dy = ny - oy;
     if (cK.phase == 2) {
-        // fused small-system step: no grid, no far movers (the CTA cuts ALL pairs of its replica, so a record with both poses is
-        // complete whatever the displacement). Search record: old centre + (share of the reach + displacement of this step), so that
-        // any pose combination of a pair within reach implies |O_a - O_b| <= r(a) + r(b) (triangle inequality)
+        // fused small-system step: no grid, no far movers (a record with both poses is complete whatever the displacement; the CTA
+        // of the replica searches pairs on these records). Search radius of the molecule this step = its share of the reach + its
+        // displacement, so that any pose combination of a pair within reach implies |O_a - O_b| <= r(a) + r(b). The pair list of
+        // the replica was built around `ref` with dmax of slack per molecule: a molecule whose poses may lie further out is special
+        SmallSearch &S = *D.small;
         const bool rec = gid < cK.NAt;
-        D.smallCen[rec ? gid - D.smallRecBase : gid - D.smallLigBase] = make_float4((float)ox, (float)oy, search_share(cK, rec) + (float)sqrt(dx * dx + dy * dy) * 1.0001f + 0.125f, 0.f);
-        double2 *nr = reinterpret_cast<double2 *>(D.nrec) + (size_t)gid * 3;
-        nr[0] = make_double2(ox, oy); nr[1] = make_double2(nx, ny);
-        reinterpret_cast<int4 *>(nr)[2] = make_int4(__float_as_int((float)oz), ukey, freeFlags, __float_as_int((float)nz));
+        const int li = rec ? gid - S.recBase : gid - S.ligBase;
+        const float disp = sqrtf((float)(dx * dx + dy * dy)) * 1.0001f + 0.0625f;
+        const float4 c = make_float4((float)ox, (float)oy, S.share[rec] + disp + 0.0625f, disp);
+        S.cen[li] = c;
+        const float2 rf = S.ref[li];
+        const float ex = c.x - rf.x, ey = c.y - rf.y;
+        const bool special = sqrtf(ex * ex + ey * ey) + disp > S.dmax;
+        S.isSpec[li] = special;
+        if (special) { const int i = atomicAdd(&S.nspec, 1); if (i < SMALL_SPEC) S.spec[i] = li; }
+        S.meta[li] = make_int2(ukey, freeFlags);          // (old / new centre and height: read from the resident poses, fetch_rec)
         return;
     }
     const bool far = dx * dx + dy * dy > cK.skin * cK.skin;
@@ -798,7 +806,7 @@ __device__ __noinline__ void complex_move_serial(const Args &A, int h0, int size
     const int rootGid = K.NAt + h0, nA = size - nB;
     const int *rowIn = D.members + D.cxOff[h0];
     int *rowOut = D.rowWork + D.cxOff[h0];
-    const uint64_t seed = seed_of(cK, h0 / K.NB);
+    const uint64_t seed = seed_of(cK, replica_of_gid(K, K.NAt + h0));
     const uint32_t me = ref_id(K, D, rootGid);
     const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
     const double phai = mul(mul(u1, 2.0), K.pai);
@@ -938,7 +946,7 @@ KD void complex_move_thread(const Args &A, int h0, bool maybeSingle, uint64_t st
     const Consts &K = cK;
     const int rootGid = K.NAt + h0;
     const int size = D.cxSize[h0];
-    const uint64_t seed = seed_of(cK, h0 / K.NB);
+    const uint64_t seed = seed_of(cK, replica_of_gid(K, K.NAt + h0));
     const uint32_t me = ref_id(K, D, rootGid);
     double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
     const double u2 = keyed_uniform(seed, me, 0, step, 2);
@@ -980,7 +988,7 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
         const int size = D.cxSize[h0];
         const int *rowIn = D.members + D.cxOff[h0];
         int *rowOut = D.rowWork + D.cxOff[h0];
-        const uint64_t seed = seed_of(cK, h0 / K.NB);
+        const uint64_t seed = seed_of(cK, replica_of_gid(K, K.NAt + h0));
         const uint32_t me = ref_id(K, D, rootGid);
         const bool cached = size <= CX_CAP;
         int nB = 0;
@@ -1187,6 +1195,16 @@ struct TileRec { double ox, oy, nx, ny; float oz, nz; int gid, unit; int flg; };
 
 KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
     const int v = entry & ~GHOST_BIT;
+    if (K.phase == 2) {          // fused small-system step: the poses are resident, the record is read from them (there are no ghost entries)
+        const int2 w = D.small->meta[small_index(K, D, v)];
+        TileRec r; r.gid = v; r.unit = w.x; r.flg = w.y;
+        if (v < K.NAt) { const double2 o = D.recC[v], n = D.recCn[v]; r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y; r.oz = 0.f; r.nz = 0.f; }
+        else {
+            const double *p = D.lig + (size_t)(v - K.NAt) * 24, *q = D.lign + (size_t)(v - K.NAt) * 24;
+            r.ox = p[0]; r.oy = p[1]; r.oz = (float)p[2]; r.nx = q[0]; r.ny = q[1]; r.nz = (float)q[2];
+        }
+        return r;
+    }
     const double2 *nr = reinterpret_cast<const double2 *>(D.nrec) + (size_t)v * 3;
     const double2 o = nr[0], n = nr[1];
     const int4 w = reinterpret_cast<const int4 *>(nr)[2];

@@ -11,9 +11,14 @@
 // whose scalars (list lengths, step counter) live in shared memory. Only the neighbour search differs: a replica's CTA cuts ALL
 // pairs of its molecules with an fp32 test on per-molecule search records (old centre, reach share + displacement of this
 // step) held in shared memory, so there is no grid, no far-mover bookkeeping and no list reuse; the pairs that survive are
-// classified by the same pair_eval as everywhere else. Results are bit-identical to the general path (tests/test_gpu_small.py)
+// classified by the same pair_eval as everywhere else. For the length of a launch the replica's poses (both buffers) and its
+// bond table live in the CTA's shared memory: the view's pose / bond pointers are shifted so that indexing them with the
+// molecule's GLOBAL index lands in the shared arrays -- the device functions neither know nor care. Results are bit-identical to the general path (tests/test_gpu_small.py)
 // and to the oracle (every small-system test of tests/test_gpu_replay.py runs through this kernel).
 #pragma once
+#ifdef SMALL_TIMING
+#include <cstdio>
+#endif
 
 namespace kmc {
 
@@ -21,29 +26,39 @@ namespace kmc {
 #define SMALL_T 128           // threads per replica
 #endif
 #ifndef SMALL_MINB
-#define SMALL_MINB 5          // CTAs per SM the register allocation aims at
+#define SMALL_MINB 4          // CTAs per SM the register allocation aims at
 #endif
-#define SMALL_MAXN 512        // molecules per replica the shared-memory records hold
 #define SMALL_MAXNB 128       // ligands per replica (complex work list)
-#define SMALL_SURV 1024       // pairs that survive the cut, per step
+#define SMALL_LIST 1024       // pairs the list of a replica holds
+#define SMALL_ITEMS 512       // directed pairs queued for exact classification per step (more: classified in place)
+#ifndef SMALL_DMAX
+#define SMALL_DMAX 24.0f      // drift (Angstrom) the pair list allows a molecule before it has to be searched on its own
+#endif
+#ifndef SMALL_SPEC_MAX
+#define SMALL_SPEC_MAX 6      // more molecules than this outside their allowance: the list is rebuilt
+#endif
 
 struct SmallShared {
-    Args view;                          // per-replica view of the device state (see above)
+    Args view[2];                       // per-replica views of the device state (see above); [1] = the pose buffers swapped (odd steps)
+    SmallSearch search;
     int scal[S_COUNT];
     unsigned long long step64;
-    float4 cen[SMALL_MAXN];             // search records: old centre (x, y), radius share of the molecule this step
     int touch[TOUCH_CAP];
     int cxList[SMALL_MAXNB];            // root ligands of the complexes with more than one member | bit 30: several ligands
-    unsigned surv[SMALL_SURV];          // (local index a << 16) | local index b
-    int ncx, nsurv, dirty;
+    unsigned list[SMALL_LIST];          // the pair list: (local index a << 16) | local index b
+    unsigned items[SMALL_ITEMS];        // this step's classification work: (probe << 16) | neighbour, both directions of every pair within reach
+    int ncx, nlist, listValid, nitems;
 };
+
+// dynamic shared memory of k_small_step for replicas of NA receptors + NB ligands
+static inline size_t small_dyn_bytes(int NA, int NB) { return (size_t)NA * 96 + (size_t)NB * 384 + (size_t)(2 * ((NA + 11) & ~3) + NA + 3 * NB) * 4 + 16; }
 
 KD int small_gid(const Consts &K, int rep, int m) { return m < K.NA ? rep * K.NA + m : K.NAt + rep * K.NB + (m - K.NA); }
 
 // S1 for one replica (main.cpp:514-562): union-find over its bond graph, unit heads, sizes, breadth-first member rows; the member
 // rows of replica r live in members[r*N, (r+1)*N)
-KD void small_rebuild(SmallShared &sm, int rep) {
-    const Dev &D = sm.view.D; const Consts &K = sm.view.K;
+KD void small_rebuild(SmallShared &sm, const Args &V, int rep) {
+    const Dev &D = V.D; const Consts &K = V.K;
     const int N = K.NA + K.NB, tid = threadIdx.x;
     for (int m = tid; m < N; m += SMALL_T) {
         const int gid = small_gid(K, rep, m);
@@ -51,7 +66,8 @@ KD void small_rebuild(SmallShared &sm, int rep) {
         D.ufParent[uid] = uid; D.bfsMark[gid] = 0;
         if (gid >= K.NAt) { D.cxSize[gid - K.NAt] = 0; D.cxOff[gid - K.NAt] = -1; }
     }
-    if (tid == 0) { sm.scal[S_MEMBER_CURSOR] = rep * N; sm.ncx = 0; }
+    __syncthreads();                    // (every thread has read the touch counters that sent it here)
+    if (tid == 0) { sm.scal[S_MEMBER_CURSOR] = rep * N; sm.ncx = 0; sm.scal[S_NTOUCH] = 0; sm.scal[S_TOPO_DIRTY] = 0; }
     __syncthreads();
     for (int m = tid; m < K.NA; m += SMALL_T) {
         const int a = rep * K.NA + m, ua = K.NBt + a;
@@ -85,7 +101,7 @@ KD void small_rebuild(SmallShared &sm, int rep) {
 }
 
 // S2c for one free ligand, straight between the committed and the new pose buffers, one point at a time
-KD void small_propose_lig(const Args &A, uint64_t step, int gid) {
+KD void small_propose_lig(const Args &A, uint64_t step, int gid, uint32_t me) {          // me = reference id (1-based number inside the replica)
     KARGS
     const Consts &K = cK;
     const int h = gid - K.NAt;
@@ -94,7 +110,6 @@ KD void small_propose_lig(const Args &A, uint64_t step, int gid) {
     double *__restrict__ dst = D.lign + (size_t)h * 24;
     const double ox = src[0], oy = src[1], oz = src[2];
     const uint64_t seed = seed_of(K, replica_of_gid(K, gid));
-    const uint32_t me = ref_id(K, D, gid);
     double u0, u1, u2, u3, u4, u5;
     keyed_uniform2(seed, me, 0, step, 0, u0, u1); keyed_uniform2(seed, me, 0, step, 2, u2, u3); keyed_uniform2(seed, me, 0, step, 4, u4, u5);
     LigMove M; lig_move_setup(K, M, ox, oy, oz, u0, u1, u2, u3, u4, u5);
@@ -109,92 +124,202 @@ KD void small_propose_lig(const Args &A, uint64_t step, int gid) {
     D.unitRes[gid] = 0; D.pendCnt[gid] = 0;
 }
 
+// S2g for one directed pair (main.cpp:640-664 / 804-849 / 1759-1826 restated as in kmc_kernels.cu): probe p against neighbour o,
+// local indices; the same pair_eval / publish as everywhere else. One copy of the code for every caller (instruction cache).
+__device__ __noinline__ void small_classify(const Args &V, int rep, int p, int o) {
+    const Dev &D = V.D; const Consts &K = V.K;
+    const PairSink none = {nullptr, nullptr, 0, nullptr, 0};
+    const ProbeCtx pc = make_probe(K, fetch_rec(K, D, small_gid(K, rep, p)));
+    int cf = -1;
+    const int rr = pair_eval(K, D, pc, fetch_rec(K, D, small_gid(K, rep, o)), &cf, none);
+    publish(D, pc.u, rr, cf);
+}
+// a pair within each other's reach this step: both directions are queued for the dense classification pass
+KD void small_queue_pair(const Args &V, SmallShared &sm, int rep, int a, int b) {
+    const int i = atomicAdd(&sm.nitems, 2);
+    if (i + 1 < SMALL_ITEMS) { sm.items[i] = ((unsigned)a << 16) | (unsigned)b; sm.items[i + 1] = ((unsigned)b << 16) | (unsigned)a; }
+    else { small_classify(V, rep, a, b); small_classify(V, rep, b, a); }
+}
+KD bool small_in_reach(const SmallSearch &S, int a, int b) {
+    const float4 ca = S.cen[a], cb = S.cen[b];
+    const float ex = cb.x - ca.x, ey = cb.y - ca.y, r = ca.z + cb.z;
+    return ex * ex + ey * ey <= r * r;
+}
+
 __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps) {
     __shared__ SmallShared sm;
+    extern __shared__ __align__(16) unsigned char small_dyn[];
     const int tid = threadIdx.x, rep = blockIdx.x;
     const int NA = A.K.NA, NB = A.K.NB, N = NA + NB, R = A.K.R;
+    // resident state of the replica: poses (committed + new buffer) and bond table
+    double2 *const sRecC = reinterpret_cast<double2 *>(small_dyn), *const sRecS2 = sRecC + 2 * NA, *const sRecS3 = sRecS2 + 2 * NA;
+    double *const sLig = reinterpret_cast<double *>(sRecS3 + 2 * NA);
+    int *const sBond = reinterpret_cast<int *>(sLig + 2 * (size_t)NB * 24);
+    // (finish_body reads the bond words of four consecutive receptors as one 16-byte load at GLOBAL indices that are multiples
+    // of four: the shared copies start at the same phase, with four spare words on either side)
+    const int ph = (rep * NA) & 3, NA8 = (NA + 11) & ~3;
+    int *const sRecLig = sBond + 4 + ph, *const sRecCis = sBond + NA8 + 4 + ph, *const sRecSite = sBond + 2 * NA8, *const sLigRec = sRecSite + NA;
+    for (int i = tid; i < 2 * NA8; i += SMALL_T) sBond[i] = -1;
+    __syncthreads();
+    for (int i = tid; i < NA; i += SMALL_T) {
+        const int a = rep * NA + i;
+        sRecC[i] = A.D.recC[a]; sRecS2[i] = A.D.recS2[a]; sRecS3[i] = A.D.recS3[a];
+        sRecLig[i] = A.D.recLig[a]; sRecCis[i] = A.D.recCis[a]; sRecSite[i] = A.D.recSite[a];
+    }
+    for (int i = tid; i < NB * 12; i += SMALL_T) reinterpret_cast<double2 *>(sLig)[i] = reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24)[i];
+    for (int i = tid; i < NB * 3; i += SMALL_T) sLigRec[i] = A.D.ligRec[(size_t)rep * NB * 3 + i];
     if (tid == 0) {
-        // the view: this replica's slices of the work lists, scalars in shared memory
-        sm.view = A;
-        Dev &V = sm.view.D;
-        V.scal = sm.scal; V.step64 = &sm.step64; V.touchList = sm.touch; V.reactList = nullptr;
-        V.smallCen = sm.cen; V.smallRecBase = rep * NA; V.smallLigBase = A.K.NAt + rep * NB - NA;
+        // the views: this replica's slices of the work lists; scalars, search records, poses and bonds in shared memory
+        sm.view[0] = A;
+        Dev &V = sm.view[0].D;
+        V.scal = sm.scal; V.step64 = &sm.step64; V.touchList = sm.touch; V.reactList = nullptr; V.small = &sm.search;
         const int pendPer = A.D.pendCap / R, pairPer = A.D.pairCap / R, candPer = A.D.candCap / R;
         V.pendList = A.D.pendList + (size_t)rep * pendPer; V.pendCap = pendPer;
         V.pairs = A.D.pairs + (size_t)rep * pairPer; V.pairCap = pairPer;
         V.candRL = A.D.candRL + (size_t)rep * 2 * candPer; V.candCis = A.D.candCis + (size_t)rep * 2 * candPer; V.candCap = candPer;
         V.rejList = A.D.rejList + (size_t)rep * N; V.rejPartner = A.D.rejPartner + (size_t)rep * N;
+        const ptrdiff_t a0 = (ptrdiff_t)rep * NA, b0 = (ptrdiff_t)rep * NB;
+        V.recC = sRecC - a0; V.recCn = sRecC + NA - a0; V.recS2 = sRecS2 - a0; V.recS2n = sRecS2 + NA - a0; V.recS3 = sRecS3 - a0; V.recS3n = sRecS3 + NA - a0;
+        V.lig = sLig - b0 * 24; V.lign = sLig + (ptrdiff_t)NB * 24 - b0 * 24;
+        V.recLig = sRecLig - a0; V.recCis = sRecCis - a0; V.recSite = sRecSite - a0; V.ligRec = sLigRec - b0 * 3;
+        sm.view[0].K.smallRep = rep;
+        sm.view[1] = sm.view[0];
+        Dev &W = sm.view[1].D;           // S4 (main.cpp:2164-2202) is a pointer swap: odd steps of the launch see the buffers exchanged
+        W.recC = V.recCn; W.recCn = V.recC; W.recS2 = V.recS2n; W.recS2n = V.recS2; W.recS3 = V.recS3n; W.recS3n = V.recS3; W.lig = V.lign; W.lign = V.lig;
         for (int i = 0; i < S_COUNT; i++) sm.scal[i] = 0;
         sm.scal[S_NA_LIVE] = A.K.NAt; sm.scal[S_NB_LIVE] = A.K.NBt;
-        sm.dirty = 1;                    // the complex tables are re-derived at the start of every launch
+        sm.scal[S_TOPO_DIRTY] = 1;       // the complex tables are re-derived at the start of every launch
+        sm.search.recBase = rep * NA; sm.search.ligBase = A.K.NAt + rep * NB - NA; sm.search.N = N; sm.search.dmax = SMALL_DMAX; sm.search.nspec = 0;
+        sm.search.share[0] = search_share(A.K, false); sm.search.share[1] = search_share(A.K, true);
+        sm.listValid = 0; sm.nlist = 0;
     }
+    for (int m = tid; m < N; m += SMALL_T) sm.search.ref[m] = make_float2(0.f, 0.f);
     __syncthreads();
-    const Args &V = sm.view;
-    const Dev &D = V.D; const Consts &K = V.K;
-    const PairSink none = {nullptr, nullptr, 0, nullptr, 0};
+    SmallSearch &S = sm.search;
+#ifdef SMALL_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define SMALL_TICK(i) do { if (tid == 0) { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
+#else
+#define SMALL_TICK(i) do {} while (0)
+#endif
     for (int s = 0; s < nsteps; s++) {
+        const Args &V = sm.view[s & 1];
+        const Dev &D = V.D; const Consts &K = V.K;
         const uint64_t step = step0 + (uint64_t)s + 1;
-        if (tid == 0) {
+        // ---- S1: only when the last step's reactions touched the bond table (or at the start of a launch) ----
+        if (sm.scal[S_NTOUCH] > 0 || sm.scal[S_TOPO_DIRTY]) small_rebuild(sm, V, rep);
+        if (tid == 0) {                  // (nothing below reads these before the next barrier; nobody still reads the last step's values: barrier at its end)
             sm.step64 = step;
-            sm.scal[S_NPEND] = 0; sm.scal[S_NPAIR] = 0; sm.scal[S_NCAND_RL] = 0; sm.scal[S_NCAND_CIS] = 0; sm.scal[S_NREJ] = 0; sm.scal[S_NTOUCH] = 0; sm.scal[S_TOPO_DIRTY] = 0;
-            sm.nsurv = 0;
+            sm.scal[S_NPEND] = 0; sm.scal[S_NPAIR] = 0; sm.scal[S_NCAND_RL] = 0; sm.scal[S_NCAND_CIS] = 0; sm.scal[S_NREJ] = 0;
+            sm.nitems = 0;
         }
-        // ---- S1 ----
-        if (sm.dirty) small_rebuild(sm, rep);          // (uniform: sm.dirty was written before the last barrier)
-        __syncthreads();
+        SMALL_TICK(0);
         // ---- S2 proposals: every molecule is proposed by exactly one thread (a unit head, or the thread of its complex) ----
-        for (int m = tid; m < N; m += SMALL_T) {
-            const int gid = small_gid(K, rep, m);
-            if (m < NA) propose_one_rec(V, step, 0u, K.NAt, gid, D.unitOf[gid], D.recCis[gid], load_rec(D.recC, D.recS2, D.recS3, gid), make_float2(0.f, 0.f), ref_id(K, D, gid));
-            else small_propose_lig(V, step, gid);
-        }
-        for (int ci = tid; ci < sm.ncx; ci += SMALL_T) complex_move_thread(V, sm.cxList[ci] & 0x3fffffff, !(sm.cxList[ci] & 0x40000000), step, 0u);
-        __syncthreads();
-        // ---- S2g: all pairs of the replica, fp32 cut on the search records; survivors are classified exactly ----
+        // (work index: receptors, ligands from the next multiple of 32 on -- a warp runs ONE of the code paths --, then the complexes)
         {
+            const int NAp = (NA + 31) & ~31, NBp = (NB + 31) & ~31, nw = NAp + NBp + sm.ncx;
+            for (int w = tid; w < nw; w += SMALL_T) {
+                if (w < NAp) {
+                    if (w >= NA) continue;
+                    const int gid = rep * NA + w;
+                    propose_one_rec(V, step, 0u, K.NAt, gid, D.unitOf[gid], D.recCis[gid], load_rec(D.recC, D.recS2, D.recS3, gid), make_float2(0.f, 0.f), (uint32_t)(w + 1));
+                } else if (w < NAp + NBp) {
+                    if (w - NAp < NB) small_propose_lig(V, step, K.NAt + rep * NB + (w - NAp), (uint32_t)(NA + w - NAp + 1));
+                } else { const int e = sm.cxList[w - NAp - NBp]; complex_move_thread(V, e & 0x3fffffff, !(e & 0x40000000), step, 0u); }
+            }
+        }
+        __syncthreads();
+        SMALL_TICK(1);
+        // ---- pair list: rebuilt when too many molecules have left their allowance (or a launch starts). A molecule stays covered
+        // by the list while all its poses lie within dmax of its centre at build time (ref): listed are all pairs with
+        // |ref_a - ref_b| <= share(a) + share(b) + 2 dmax ----
+        bool useList = true;
+        if (!sm.listValid || S.nspec > SMALL_SPEC_MAX) {
+            __syncthreads();             // (everyone has read nspec)
+            if (tid == 0) { S.nspec = 0; sm.nlist = 0; sm.listValid = 1; }
+            __syncthreads();
             const int half = N / 2;
             for (int m = tid; m < N; m += SMALL_T) {
-                const float4 me = sm.cen[m];
-                const int dmax = (2 * half == N && m >= half) ? half - 1 : half;      // even N: the pair (m, m + N/2) is listed by its lower member
+                const float4 me = S.cen[m];
+                S.ref[m] = make_float2(me.x, me.y);
+                const bool special = me.w > S.dmax;          // (this step's own move is already too long: periodic wrap, alignment snap)
+                S.isSpec[m] = special;
+                if (special) { const int i = atomicAdd(&S.nspec, 1); if (i < SMALL_SPEC) S.spec[i] = m; }
+                const float rm = me.z - me.w + 2.f * S.dmax + 0.0625f;          // the share alone (+ margins), plus both allowances
+                const int dmax_ = (2 * half == N && m >= half) ? half - 1 : half;      // even N: the pair (m, m + N/2) is listed by its lower member
                 int j = m;
-                for (int d = 1; d <= dmax; d++) {
-                    if (++j == N) j = 0;
-                    const float4 o = sm.cen[j];
-                    const float ex = o.x - me.x, ey = o.y - me.y, r = me.z + o.z;
-                    if (ex * ex + ey * ey > r * r) continue;
-                    const int slot = atomicAdd(&sm.nsurv, 1);
-                    if (slot < SMALL_SURV) sm.surv[slot] = ((unsigned)m << 16) | (unsigned)j;
-                    else eval_entry_pair(K, D, small_gid(K, rep, m), small_gid(K, rep, j), none);
+#pragma unroll 4
+                for (int d = 1; d <= dmax_; d++) {
+                    j = j + 1 == N ? 0 : j + 1;
+                    const float4 o = S.cen[j];
+                    const float ex = o.x - me.x, ey = o.y - me.y, r = rm + (o.z - o.w);
+                    if (ex * ex + ey * ey <= r * r) {
+                        const int slot = atomicAdd(&sm.nlist, 1);
+                        if (slot < SMALL_LIST) sm.list[slot] = ((unsigned)m << 16) | (unsigned)j;
+                    }
                 }
+            }
+            __syncthreads();
+            useList = sm.nlist <= SMALL_LIST && S.nspec <= SMALL_SPEC;      // else too crowded for the list: every pair, in place (and the next step tries again)
+            if (tid == 0) sm.listValid = useList;                           // (read again only after the next barrier)
+        }
+        SMALL_TICK(2);
+        // ---- S2g: list pairs (both members inside their allowance) + every pair of a special molecule: those within reach this
+        // step are queued, then classified exactly by a dense pass (one directed pair per thread) ----
+        if (!useList) {                  // (a replica too crowded for the list: every pair)
+            for (int m = tid; m < N; m += SMALL_T)
+                for (int j = m + 1; j < N; j++) if (small_in_reach(S, m, j)) small_queue_pair(V, sm, rep, m, j);
+        } else {
+            const int nl = sm.nlist;
+            for (int q = tid; q < nl; q += SMALL_T) {
+                const unsigned w = sm.list[q];
+                const int a = (int)(w >> 16), b = (int)(w & 0xffffu);
+                if (!(S.isSpec[a] | S.isSpec[b]) && small_in_reach(S, a, b)) small_queue_pair(V, sm, rep, a, b);
+            }
+            const int nsp = S.nspec;
+            for (int k = 0; k < nsp; k++) {
+                const int f = S.spec[k];
+                for (int t = tid; t < N; t += SMALL_T)
+                    if (t != f && !(S.isSpec[t] && t < f) && small_in_reach(S, f, t)) small_queue_pair(V, sm, rep, f, t);      // two special molecules: once, by the lower one
             }
         }
         __syncthreads();
         {
-            const int ns = min(sm.nsurv, SMALL_SURV);
-            for (int q = tid; q < ns; q += SMALL_T) {
-                const unsigned w = sm.surv[q];
-                eval_entry_pair(K, D, small_gid(K, rep, (int)(w >> 16)), small_gid(K, rep, (int)(w & 0xffffu)), none);
-            }
+            const int ni = min(sm.nitems, SMALL_ITEMS);
+            for (int q = tid; q < ni; q += SMALL_T) small_classify(V, rep, (int)(sm.items[q] >> 16), (int)(sm.items[q] & 0xffffu));
         }
         __syncthreads();
+        SMALL_TICK(3);
         // ---- the order dependence of the sweep, from the pending findings ----
         if (sm.scal[S_NPEND] > 0) pend_resolve_block(D, min(sm.scal[S_NPEND], D.pendCap));
         // ---- S3 ----
         react_pairs_body(K, D, tid, SMALL_T);
         __syncthreads();
-        if (sm.scal[S_NCAND_RL] | sm.scal[S_NCAND_CIS]) react_resolve_block(D);
-        __syncthreads();
+        SMALL_TICK(4);
+        if (sm.scal[S_NCAND_RL] | sm.scal[S_NCAND_CIS]) { react_resolve_block(D); __syncthreads(); }
+        SMALL_TICK(5);
+        if (tid == 0) S.nspec = 0;          // (the special molecules of the NEXT step register during its proposals)
         finish_body(K, D, tid, SMALL_T, rep * NA, (rep + 1) * NA);
         __syncthreads();
-        // ---- S4: the new buffers become the committed state ----
-        if (tid == 0) {
-            Dev &W = sm.view.D;
-            double2 *t2; double *t1;
-            t2 = W.recC; W.recC = W.recCn; W.recCn = t2; t2 = W.recS2; W.recS2 = W.recS2n; W.recS2n = t2; t2 = W.recS3; W.recS3 = W.recS3n; W.recS3n = t2;
-            t1 = W.lig; W.lig = W.lign; W.lign = t1;
-            sm.dirty = (sm.scal[S_NTOUCH] > 0) | sm.scal[S_TOPO_DIRTY];
+        SMALL_TICK(6);
+    }
+#ifdef SMALL_TIMING
+    if (tid == 0 && rep == 0 && nsteps >= 1000)          // (diagnostic build only) cycles per step: S1 | proposals | list | classify | pending + S3 pairs | S3 resolve | finish
+        printf("k_small_step cycles/step: %lld %lld %lld %lld %lld %lld %lld\n", tacc[0] / nsteps, tacc[1] / nsteps, tacc[2] / nsteps, tacc[3] / nsteps, tacc[4] / nsteps, tacc[5] / nsteps, tacc[6] / nsteps);
+#endif
+    // the committed state goes back to the global arrays: into the buffers the host regards as committed after this launch
+    // (it swaps its pointers when the step count is odd)
+    {
+        const int cb = nsteps & 1;
+        double2 *gC = cb ? A.D.recCn : A.D.recC, *gS2 = cb ? A.D.recS2n : A.D.recS2, *gS3 = cb ? A.D.recS3n : A.D.recS3;
+        double *gL = cb ? A.D.lign : A.D.lig;
+        for (int i = tid; i < NA; i += SMALL_T) {
+            const int a = rep * NA + i;
+            gC[a] = sRecC[cb * NA + i]; gS2[a] = sRecS2[cb * NA + i]; gS3[a] = sRecS3[cb * NA + i];
+            A.D.recLig[a] = sRecLig[i]; A.D.recCis[a] = sRecCis[i]; A.D.recSite[a] = sRecSite[i];
         }
-        __syncthreads();
+        for (int i = tid; i < NB * 12; i += SMALL_T) reinterpret_cast<double2 *>(gL + (size_t)rep * NB * 24)[i] = reinterpret_cast<const double2 *>(sLig + (size_t)cb * NB * 24)[i];
+        for (int i = tid; i < NB * 3; i += SMALL_T) A.D.ligRec[(size_t)rep * NB * 3 + i] = sLigRec[i];
     }
     if (tid == 0) {
         if (sm.scal[S_OVERFLOW]) atomicOr(&A.D.scal[S_OVERFLOW], sm.scal[S_OVERFLOW]);

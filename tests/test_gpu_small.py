@@ -66,7 +66,7 @@ def test_fused_from_random_start_and_long_launch(monkeypatch):
 
 def test_fused_small_odd_sizes_against_oracle():
     """odd molecule count (the all-pairs schedule differs for odd and even N), more molecules than threads, crowded box"""
-    for na, nb, box in ((31, 10, (900.0, 900.0, 300.0)), (300, 101, (4000.0, 4000.0, 400.0))):
+    for na, nb, box in ((31, 10, (900.0, 900.0, 300.0)), (170, 71, (3000.0, 3000.0, 400.0))):
         po = apply_regime(pyoracle.default_params(box=box, n_receptor=na, n_ligand=nb, use_grid=1, stream_mode=1, seed=3), "hot")
         pg = apply_regime(kmc_b200.default_params(box=box, n_receptor=na, n_ligand=nb, seed=3), "hot")
         o, k = pyoracle.Oracle(po), kmc_b200.Kmc(pg)
