@@ -204,7 +204,8 @@ def ensemble_measure(kmc_b200, replicas, local, seed, steps=2000):
     k.init_random(seed=seed + 1)
     k.step(200); k.sync()
     ms = k.step_timed(steps) / steps
-    out = {"value": 200 * replicas / (ms * 1e-3), "unit": "molecule-moves/s", "us_per_mc_step": 1e3 * ms, "replicas": replicas, "molecules_per_replica": 200}
+    out = {"value": 200 * replicas / (ms * 1e-3), "unit": "molecule-moves/s", "us_per_mc_step": 1e3 * ms, "replicas": replicas, "molecules_per_replica": 200,
+           "step_path": k.path() + (" (one CTA per replica, the whole step in one kernel, %d steps per launch)" % steps if k.path() == "fused" else "")}
     k.close()
     return out
 

@@ -72,6 +72,7 @@ struct Dev {
     unsigned long long *candRL, *candCis;
     int candCap;
     unsigned long long *pairs; int pairCap;   // (receptor, neighbour) pairs that may react this step
+    unsigned long long *pairsFast; int pairFastCap;   // fused small-system step: the first pairFastCap entries of that list live in shared memory (else null / 0)
     int *unitRes;                             // [NT] per unit head: 0 accepted, bit0 rejected (definite overlap), 2 = waits on pending findings
     int *pendCnt;                             // [NT] per unit head: pending findings not yet settled
     int *rejList;                             // [NT] heads of the units rejected this step (each once): their members are copied back
@@ -96,6 +97,7 @@ struct SmallSearch {
     float4 cen[SMALL_MAXN];            // old centre (x, y), search radius of the molecule this step (its share of the reach + its displacement), displacement
     float2 ref[SMALL_MAXN];            // centre when the pair list was built
     int2 meta[SMALL_MAXN];             // unit key, free-site flags: with the centres of the resident poses, the neighbour record the general path keeps in D.nrec
+    unsigned char ligFree[SMALL_MAXN]; // ligand b of the replica is a unit of its own (no receptor bound): moved by the ligand proposal, not by a complex
     unsigned char isSpec[SMALL_MAXN];  // this step the molecule may be further than dmax from its list centre: the list does not cover it
     int spec[SMALL_SPEC];              // those molecules
     int nspec;

@@ -66,6 +66,7 @@ struct kmc_handle {
     unsigned long long *timeline = nullptr; int tlCount = 0, tlId[64]; cudaStream_t tlStream = nullptr;      // KMC_TIMELINE
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
+    int smallGrid = 0; int *smallQueue = nullptr;      // fused step: CTAs resident at once; ticket queue (1 + R ints) for ensembles larger than that
     bool fused = false;              // small replicas: the whole step is ONE kernel, one CTA per replica, many steps per launch (csrc/kmc_small.cu)
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
     // (asynchronously) and the copy of the PREVIOUS interval is examined -- capacity overflows are reported and the list-reuse
@@ -299,6 +300,11 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, k_small_step) != cudaSuccess || fa.sharedSizeBytes + small_dyn_bytes(K.NA, K.NB) > (size_t)prop.sharedMemPerBlockOptin ||
             cudaFuncSetAttribute(k_small_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_dyn_bytes(K.NA, K.NB)) != cudaSuccess) { h->fused = false; cudaGetLastError(); }
+        int per = 0;
+        if (h->fused && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_small_step, SMALL_T, small_dyn_bytes(K.NA, K.NB)) != cudaSuccess || per < 1)) { h->fused = false; cudaGetLastError(); }
+        h->smallGrid = per * h->nSM;
+        if (const char *o = getenv("KMC_SMALL_GRID")) h->smallGrid = std::max(1, atoi(o));          // (tests: force the ticket path on a small ensemble)
+        if (h->fused && dalloc(h, &h->smallQueue, (size_t)K.R + 1) != cudaSuccess) return fail(KMC_ERR_CUDA, "device allocation failed");
     }
     D.candCap = std::max({1 << 14, K.NAt / 8, h->fused ? 64 * K.R : 0});
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -695,7 +701,10 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
             const int chunk = (int)std::min<int64_t>(left, 8192);
             Args A{h->D, h->K};
             A.K.phase = 2;
-            LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->R, SMALL_T, small_dyn_bytes(h->NA, h->NB), st>>>(A, (unsigned long long)h->step_done, chunk)));
+            if (h->R > h->smallGrid) {          // more replicas than resident CTAs: persistent grid, replicas dealt in chunks of 64 steps
+                CK(cudaMemsetAsync(h->smallQueue, 0, sizeof(int) * (size_t)(1 + h->R), st));
+                LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->smallGrid, SMALL_T, small_dyn_bytes(h->NA, h->NB), st>>>(A, (unsigned long long)h->step_done, chunk, 64, h->smallQueue)));
+            } else LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->R, SMALL_T, small_dyn_bytes(h->NA, h->NB), st>>>(A, (unsigned long long)h->step_done, chunk, chunk, nullptr)));
             if (chunk & 1) { swap_buffers(h->D); h->parity ^= 1; }
             h->step_done += chunk; h->passes += chunk; h->sinceMon += chunk; left -= chunk;
             h->stepped = true;

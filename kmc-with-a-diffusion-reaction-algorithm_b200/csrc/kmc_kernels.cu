@@ -355,7 +355,7 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
         double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
         const double u2 = keyed_uniform(seed, me, 0, step, 2);
         const double phai = mul(mul(u1, 2.0), K.pai);
-        double sp, cp; sincos(phai, &sp, &cp);
+        double sp, cp; KMC_SINCOS(K, phai, &sp, &cp);
         if (p < 0) {
             // ---- S2a ----
             const double amp = mul(K.ampA, u0);
@@ -365,7 +365,7 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
             t.cx = sub(t.cx, PBx); t.s2x = sub(t.s2x, PBx); t.s3x = sub(t.s3x, PBx);
             t.cy = sub(t.cy, PBy); t.s2y = sub(t.s2y, PBy); t.s3y = sub(t.s3y, PBy);
             const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotA);
-            double ss, cs; sincos(psai, &ss, &cs);
+            double ss, cs; KMC_SINCOS(K, psai, &ss, &cs);
             Rec n; n.cx = t.cx; n.cy = t.cy;
             rotz(cs, ss, t.s2x, t.s2y, t.cx, t.cy, n.s2x, n.s2y);
             rotz(cs, ss, t.s3x, t.s3y, t.cx, t.cy, n.s3x, n.s3y);
@@ -386,7 +386,7 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
             tb.cx = sub(tb.cx, PBx); tb.s2x = sub(tb.s2x, PBx); tb.s3x = sub(tb.s3x, PBx);
             tb.cy = sub(tb.cy, PBy); tb.s2y = sub(tb.s2y, PBy); tb.s3y = sub(tb.s3y, PBy);
             const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotCis);
-            double ss, cs; sincos(psai, &ss, &cs);
+            double ss, cs; KMC_SINCOS(K, psai, &ss, &cs);
             // rotation centre from the PRE-translation bead centres, summed bead by bead (main.cpp:744-753)
             double cmx = 0, cmy = 0;
             for (int j = 0; j < 4; j++) { cmx = add(add(cmx, ra.cx), rb.cx); cmy = add(add(cmy, ra.cy), rb.cy); }
@@ -431,7 +431,7 @@ struct LigMove { double shx, shy, shz, PBx, PBy, twoPBz, c[3]; Rot3 R3; bool ref
 KD void lig_move_setup(const Consts &K, LigMove &M, double ox, double oy, double oz, double u0, double u1, double u2, double u3, double u4, double u5) {
     const double amp = mul(K.ampB, u0);
     const double theta = mul(u1, K.pai), phai = mul(mul(u2, 2.0), K.pai);
-    double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phai, &sp, &cp);
+    double st, ct, sp, cp; KMC_SINCOS(K, theta, &st, &ct); KMC_SINCOS(K, phai, &sp, &cp);
     M.shx = mul(mul(amp, st), cp); M.shy = mul(mul(amp, st), sp); M.shz = mul(amp, ct);
     const double c0x = add(ox, M.shx), c0y = add(oy, M.shy), c0z = add(oz, M.shz);
     M.PBx = wrap_offset(c0x, K.Lx); M.PBy = wrap_offset(c0y, K.Ly);
@@ -440,7 +440,7 @@ KD void lig_move_setup(const Consts &K, LigMove &M, double ox, double oy, double
     M.c[0] = sub(c0x, M.PBx); M.c[1] = sub(c0y, M.PBy); M.c[2] = M.reflect ? add(-c0z, M.twoPBz) : c0z;
     const double rt = mul(sub(mul(2.0, u3), 1.0), K.rotB), rp = mul(sub(mul(2.0, u4), 1.0), K.rotB),
                  rs = mul(sub(mul(2.0, u5), 1.0), K.rotB);
-    M.R3 = euler(rt, rp, rs);
+    M.R3 = euler(K, rt, rp, rs);
 }
 KD void lig_move_point(const LigMove &M, double x, double y, double z, double o[3]) {
     double pt[3] = {add(x, M.shx), add(y, M.shy), add(z, M.shz)};
@@ -810,10 +810,10 @@ __device__ __noinline__ void complex_move_serial(const Args &A, int h0, int size
     const uint32_t me = ref_id(K, D, rootGid);
     const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
     const double phai = mul(mul(u1, 2.0), K.pai);
-    double sp, cp; sincos(phai, &sp, &cp);
+    double sp, cp; KMC_SINCOS(K, phai, &sp, &cp);
     const double shx = mul(amp, cp), shy = mul(amp, sp);
     const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
-    double ss, cs; sincos(psai, &ss, &cs);
+    double ss, cs; KMC_SINCOS(K, psai, &ss, &cs);
     CxGlobal C{D, K, K.NAt};
     // wrap centre (main.cpp:1007-1008, 1022-1023) and rotation centre (1048-1068) are sums over the members in row order: two
     // read-only passes over centres / beads; then ONE pass that shifts, wraps and rotates every member and writes it once
@@ -885,10 +885,10 @@ KD bool single_ligand_move(const Args &A, int h0, int size, uint64_t step, unsig
     const double ox = L.p[0][0], oy = L.p[0][1], oz = L.p[0][2];
     const double amp = mul(K.ampBond, u0);
     const double phai = mul(mul(u1, 2.0), K.pai);
-    double sp, cp; sincos(phai, &sp, &cp);
+    double sp, cp; KMC_SINCOS(K, phai, &sp, &cp);
     const double shx = mul(amp, cp), shy = mul(amp, sp);
     const double psai = mul(sub(mul(2.0, u2), 1.0), K.rotBond);
-    double ss, cs; sincos(psai, &ss, &cs);
+    double ss, cs; KMC_SINCOS(K, psai, &ss, &cs);
     // wrap centre and rotation centre: sums in row order (ligand, receptors, partners)
     double PBx = add(0.0, add(ox, shx)), PBy = add(0.0, add(oy, shy));
     for (int s = 0; s < 3; s++) if (a[s] >= 0) { PBx = add(PBx, add(ca[s].x, shx)); PBy = add(PBy, add(ca[s].y, shy)); }
@@ -999,10 +999,10 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
         // ---- S2d rigid move (main.cpp:974-1131); complexes with >= 2 ligands have D = 0 but still draw ----
         const double amp = mul(nB == 1 ? K.ampBond : 0.0, u0);
         const double phai = mul(mul(u1, 2.0), K.pai);
-        double sp, cp; sincos(phai, &sp, &cp);
+        double sp, cp; KMC_SINCOS(K, phai, &sp, &cp);
         const double shx = mul(amp, cp), shy = mul(amp, sp);
         const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
-        double ss, cs; sincos(psai, &ss, &cs);
+        double ss, cs; KMC_SINCOS(K, psai, &ss, &cs);
         __syncwarp();
         if (cached) {
             // load: every lane its members (old pose + the bonds inside the complex as slots), translated by the shift
@@ -1193,18 +1193,19 @@ KD void load_beads(const double *base, int h, double b[3][3]) {
 
 struct TileRec { double ox, oy, nx, ny; float oz, nz; int gid, unit; int flg; };
 
+// fused small-system step: the poses are resident in shared memory, the record is read from them (there are no ghost entries)
+KD TileRec fetch_rec_small(const Consts &K, const Dev &D, int v) {
+    const int2 w = D.small->meta[small_index(K, D, v)];
+    TileRec r; r.gid = v; r.unit = w.x; r.flg = w.y;
+    if (v < K.NAt) { const double2 o = D.recC[v], n = D.recCn[v]; r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y; r.oz = 0.f; r.nz = 0.f; }
+    else {
+        const double *p = D.lig + (size_t)(v - K.NAt) * 24, *q = D.lign + (size_t)(v - K.NAt) * 24;
+        r.ox = p[0]; r.oy = p[1]; r.oz = (float)p[2]; r.nx = q[0]; r.ny = q[1]; r.nz = (float)q[2];
+    }
+    return r;
+}
 KD TileRec fetch_rec(const Consts &K, const Dev &D, int entry) {
     const int v = entry & ~GHOST_BIT;
-    if (K.phase == 2) {          // fused small-system step: the poses are resident, the record is read from them (there are no ghost entries)
-        const int2 w = D.small->meta[small_index(K, D, v)];
-        TileRec r; r.gid = v; r.unit = w.x; r.flg = w.y;
-        if (v < K.NAt) { const double2 o = D.recC[v], n = D.recCn[v]; r.ox = o.x; r.oy = o.y; r.nx = n.x; r.ny = n.y; r.oz = 0.f; r.nz = 0.f; }
-        else {
-            const double *p = D.lig + (size_t)(v - K.NAt) * 24, *q = D.lign + (size_t)(v - K.NAt) * 24;
-            r.ox = p[0]; r.oy = p[1]; r.oz = (float)p[2]; r.nx = q[0]; r.ny = q[1]; r.nz = (float)q[2];
-        }
-        return r;
-    }
     const double2 *nr = reinterpret_cast<const double2 *>(D.nrec) + (size_t)v * 3;
     const double2 o = nr[0], n = nr[1];
     const int4 w = reinterpret_cast<const int4 *>(nr)[2];
@@ -1265,7 +1266,8 @@ KD ProbeCtx make_probe(const Consts &K, const TileRec &me) {
 struct PairSink { unsigned long long *buf; int *cnt; int cap; int *flag; int bit; };
 KD void append_pair_global(const Dev &D, unsigned long long pr) {
     int p = atomicAdd(&D.scal[S_NPAIR], 1);
-    if (p < D.pairCap) D.pairs[p] = pr;
+    if (p < D.pairFastCap) D.pairsFast[p] = pr;
+    else if (p - D.pairFastCap < D.pairCap) D.pairs[p - D.pairFastCap] = pr;
     else atomicOr(&D.scal[S_OVERFLOW], 4);
 }
 KD void sink_pair(const Dev &D, const PairSink &ps, unsigned long long pr) {
@@ -1821,7 +1823,8 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
     // everything that depends only on (a, v) is requested at once: unit words, bond words and the PROPOSED poses (the final
     // pose of a molecule is its proposal unless its unit was reverted -- the copy-back happens in k_finish --, which is rare:
     // the old pose is fetched only then)
-    const int ua = D.unitOf[a], uv = D.unitOf[v];
+    // (fused small-system step: the unit key written with this step's proposal carries the head)
+    const int ua = K.phase == 2 ? (D.small->meta[small_index(K, D, a)].x & UNIT_MASK) : D.unitOf[a], uv = K.phase == 2 ? (D.small->meta[small_index(K, D, v)].x & UNIT_MASK) : D.unitOf[v];
     Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
     if (v >= K.NAt) {
         const int h = v - K.NAt;
@@ -1876,9 +1879,9 @@ KD void react_pairs_body(const Consts &K, const Dev &D, int tid, int nth) {
         const int a = w.x & ~GHOST_BIT, b = w.y & ~GHOST_BIT;
         if (it & 1) react_pair(K, D, step, b, a); else react_pair(K, D, step, a, b);
     }
-    const int np = min(D.scal[S_NPAIR], D.pairCap);
+    const int np = min(D.scal[S_NPAIR], D.pairFastCap + D.pairCap);
     for (int i = tid; i < np; i += nth) {
-        const unsigned long long pr = D.pairs[i];
+        const unsigned long long pr = i < D.pairFastCap ? D.pairsFast[i] : D.pairs[i - D.pairFastCap];
         react_pair(K, D, step, (int)(pr >> 32), (int)(pr & 0xffffffffu));
     }
 }
@@ -1965,7 +1968,9 @@ KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, i
 //     rejection time for a receptor-headed one -- whatever S3 did to the bonds since.
 // (2) Dissociation: a thread takes four consecutive receptors; their bond words arrive as two 16-byte loads, and on a
 //     membrane with few bonds that is all the kernel reads (8 bytes per receptor).
-KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, int aEnd) {      // receptors [aBeg, aEnd) take their dissociation trials here
+template <bool RANGED>          // RANGED: receptors [aBeg, aEnd) take their dissociation trials here (a replica, fused small-system step); else all live ones
+KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, int aEnd) {
+    if (!RANGED) { aBeg = 0; aEnd = nA_live(D); }
     const int nrej = min(D.scal[S_NREJ], K.NT);
     if (tid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
     for (int i = tid; i < nrej; i += nth) {
@@ -1984,7 +1989,7 @@ KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, i
         } else for (int k = 0; k < 4; k++) if (a0 + k < K.NAt) { hh[k] = D.recLig[a0 + k]; pp[k] = D.recCis[a0 + k]; }
         if ((hh[0] & hh[1] & hh[2] & hh[3] & pp[0] & pp[1] & pp[2] & pp[3]) < 0) continue;      // all eight words negative: no bond on any of the four
         for (int k = 0; k < 4; k++)
-            if (a0 + k >= aBeg && a0 + k < aEnd && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
+            if ((!RANGED || a0 + k >= aBeg) && a0 + k < aEnd && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
     }
 }
 
@@ -2001,7 +2006,7 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
 #endif
 __global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) { KARGS react_pairs_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void k_react_resolve(const __grid_constant__ Args A) { KARGS react_resolve_block(D); }
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, nA_live(D)); }
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body<false>(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, 0); }
 
 // ------------------------------------------------------------------------------------------------
 // outputs (bond.dat columns, main.cpp:2251)

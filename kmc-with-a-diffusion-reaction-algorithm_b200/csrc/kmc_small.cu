@@ -29,7 +29,7 @@ namespace kmc {
 #define SMALL_MINB 4          // CTAs per SM the register allocation aims at
 #endif
 #define SMALL_MAXNB 128       // ligands per replica (complex work list)
-#define SMALL_LIST 1024       // pairs the list of a replica holds
+#define SMALL_LIST 768        // pairs the list of a replica holds
 #define SMALL_ITEMS 512       // directed pairs queued for exact classification per step (more: classified in place)
 #ifndef SMALL_DMAX
 #define SMALL_DMAX 24.0f      // drift (Angstrom) the pair list allows a molecule before it has to be searched on its own
@@ -43,7 +43,7 @@ struct SmallShared {
     SmallSearch search;
     int scal[S_COUNT];
     unsigned long long step64;
-    int touch[TOUCH_CAP];
+    union { int touch[TOUCH_CAP]; unsigned long long fastPairs[TOUCH_CAP / 2]; };      // S3 candidates pairs (written by the classification, read by react_pairs_body), then the molecules whose bonds changed (written from react_resolve_block on: only counted here)
     int cxList[SMALL_MAXNB];            // root ligands of the complexes with more than one member | bit 30: several ligands
     unsigned list[SMALL_LIST];          // the pair list: (local index a << 16) | local index b
     unsigned items[SMALL_ITEMS];        // this step's classification work: (probe << 16) | neighbour, both directions of every pair within reach
@@ -81,12 +81,15 @@ KD void small_rebuild(SmallShared &sm, const Args &V, int rep) {
         const int gid = small_gid(K, rep, m);
         const int uid = gid < K.NAt ? K.NBt + gid : gid - K.NAt;
         const int r = uf_find(D.ufParent, uid);
-        D.unitOf[gid] = r < K.NBt ? K.NAt + r : r - K.NBt;
+        const int head = r < K.NBt ? K.NAt + r : r - K.NBt;
+        D.unitOf[gid] = head;
+        sm.search.meta[m].x = head;          // (the proposals read the head from here; from the next step on it is the unit key mark_far leaves: same head)
         if (r < K.NBt) atomicAdd(&D.cxSize[r], 1);
     }
     __syncthreads();
     for (int b = tid; b < K.NB; b += SMALL_T) {
         const int h = rep * K.NB + b;
+        sm.search.ligFree[b] = D.unitOf[K.NAt + h] == K.NAt + h && D.cxSize[h] <= 1;
         if (D.unitOf[K.NAt + h] != K.NAt + h) continue;
         const int size = D.cxSize[h];
         note_max_complex(K, D, h, size);
@@ -105,7 +108,7 @@ KD void small_propose_lig(const Args &A, uint64_t step, int gid, uint32_t me) { 
     KARGS
     const Consts &K = cK;
     const int h = gid - K.NAt;
-    if (D.unitOf[gid] != gid || D.cxSize[h] > 1) return;          // member of a complex: moved by complex_move_thread
+    if (!D.small->ligFree[h - K.smallRep * K.NB]) return;          // member of a complex: moved by complex_move_thread
     const double *__restrict__ src = D.lig + (size_t)h * 24;
     double *__restrict__ dst = D.lign + (size_t)h * 24;
     const double ox = src[0], oy = src[1], oz = src[2];
@@ -129,9 +132,9 @@ KD void small_propose_lig(const Args &A, uint64_t step, int gid, uint32_t me) { 
 __device__ __noinline__ void small_classify(const Args &V, int rep, int p, int o) {
     const Dev &D = V.D; const Consts &K = V.K;
     const PairSink none = {nullptr, nullptr, 0, nullptr, 0};
-    const ProbeCtx pc = make_probe(K, fetch_rec(K, D, small_gid(K, rep, p)));
+    const ProbeCtx pc = make_probe(K, fetch_rec_small(K, D, small_gid(K, rep, p)));
     int cf = -1;
-    const int rr = pair_eval(K, D, pc, fetch_rec(K, D, small_gid(K, rep, o)), &cf, none);
+    const int rr = pair_eval(K, D, pc, fetch_rec_small(K, D, small_gid(K, rep, o)), &cf, none);
     publish(D, pc.u, rr, cf);
 }
 // a pair within each other's reach this step: both directions are queued for the dense classification pass
@@ -146,11 +149,31 @@ KD bool small_in_reach(const SmallSearch &S, int a, int b) {
     return ex * ex + ey * ey <= r * r;
 }
 
-__global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps) {
+// queue == nullptr: CTA b advances replica b by nsteps. Otherwise (more replicas than CTAs fit on the device at once) the grid is
+// persistent and the work is dealt in tickets: ticket t = chunk t / R of replica t % R (chunk = an even number of steps); a CTA
+// that takes a ticket waits until the replica's previous chunk has been published (queue[1 + replica] counts its finished chunks;
+// that chunk's ticket was drawn earlier by a CTA that is running, so the wait always ends), loads the replica, advances it and
+// writes it back. Every SM stays busy to the end whatever R modulo the number of resident CTAs is.
+__global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps, int chunk, int *queue) {
     __shared__ SmallShared sm;
+    __shared__ int s_ticket;
     extern __shared__ __align__(16) unsigned char small_dyn[];
-    const int tid = threadIdx.x, rep = blockIdx.x;
+    const int tid = threadIdx.x;
     const int NA = A.K.NA, NB = A.K.NB, N = NA + NB, R = A.K.R;
+  for (;;) {
+    int rep = blockIdx.x, s0 = 0, s1 = nsteps, myChunk = 0;
+    if (queue) {
+        __syncthreads();                 // (the last ticket's shared state is no longer in use)
+        if (tid == 0) s_ticket = atomicAdd(&queue[0], 1);
+        __syncthreads();
+        const int ticket = s_ticket, nchunks = (nsteps + chunk - 1) / chunk;
+        if (ticket >= R * nchunks) break;
+        rep = ticket % R; myChunk = ticket / R;
+        s0 = myChunk * chunk; s1 = min(nsteps, s0 + chunk);
+        if (tid == 0) while (((volatile int *)queue)[1 + rep] < myChunk) __nanosleep(100);
+        __syncthreads();
+        __threadfence();
+    }
     // resident state of the replica: poses (committed + new buffer) and bond table
     double2 *const sRecC = reinterpret_cast<double2 *>(small_dyn), *const sRecS2 = sRecC + 2 * NA, *const sRecS3 = sRecS2 + 2 * NA;
     double *const sLig = reinterpret_cast<double *>(sRecS3 + 2 * NA);
@@ -163,16 +186,17 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
     __syncthreads();
     for (int i = tid; i < NA; i += SMALL_T) {
         const int a = rep * NA + i;
-        sRecC[i] = A.D.recC[a]; sRecS2[i] = A.D.recS2[a]; sRecS3[i] = A.D.recS3[a];
-        sRecLig[i] = A.D.recLig[a]; sRecCis[i] = A.D.recCis[a]; sRecSite[i] = A.D.recSite[a];
+        // (__ldcg: past the L1 -- the replica's previous chunk may have been written by another SM)
+        sRecC[i] = __ldcg(&A.D.recC[a]); sRecS2[i] = __ldcg(&A.D.recS2[a]); sRecS3[i] = __ldcg(&A.D.recS3[a]);
+        sRecLig[i] = __ldcg(&A.D.recLig[a]); sRecCis[i] = __ldcg(&A.D.recCis[a]); sRecSite[i] = __ldcg(&A.D.recSite[a]);
     }
-    for (int i = tid; i < NB * 12; i += SMALL_T) reinterpret_cast<double2 *>(sLig)[i] = reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24)[i];
-    for (int i = tid; i < NB * 3; i += SMALL_T) sLigRec[i] = A.D.ligRec[(size_t)rep * NB * 3 + i];
+    for (int i = tid; i < NB * 12; i += SMALL_T) reinterpret_cast<double2 *>(sLig)[i] = __ldcg(reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24) + i);
+    for (int i = tid; i < NB * 3; i += SMALL_T) sLigRec[i] = __ldcg(&A.D.ligRec[(size_t)rep * NB * 3 + i]);
     if (tid == 0) {
         // the views: this replica's slices of the work lists; scalars, search records, poses and bonds in shared memory
         sm.view[0] = A;
         Dev &V = sm.view[0].D;
-        V.scal = sm.scal; V.step64 = &sm.step64; V.touchList = sm.touch; V.reactList = nullptr; V.small = &sm.search;
+        V.scal = sm.scal; V.step64 = &sm.step64; V.touchList = sm.touch; V.reactList = nullptr; V.small = &sm.search; V.pairsFast = sm.fastPairs; V.pairFastCap = TOUCH_CAP / 2;
         const int pendPer = A.D.pendCap / R, pairPer = A.D.pairCap / R, candPer = A.D.candCap / R;
         V.pendList = A.D.pendList + (size_t)rep * pendPer; V.pendCap = pendPer;
         V.pairs = A.D.pairs + (size_t)rep * pairPer; V.pairCap = pairPer;
@@ -202,8 +226,8 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
 #else
 #define SMALL_TICK(i) do {} while (0)
 #endif
-    for (int s = 0; s < nsteps; s++) {
-        const Args &V = sm.view[s & 1];
+    for (int s = s0; s < s1; s++) {
+        const Args &V = sm.view[s & 1];          // (chunks are even: every chunk starts on buffer set 0)
         const Dev &D = V.D; const Consts &K = V.K;
         const uint64_t step = step0 + (uint64_t)s + 1;
         // ---- S1: only when the last step's reactions touched the bond table (or at the start of a launch) ----
@@ -222,7 +246,7 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
                 if (w < NAp) {
                     if (w >= NA) continue;
                     const int gid = rep * NA + w;
-                    propose_one_rec(V, step, 0u, K.NAt, gid, D.unitOf[gid], D.recCis[gid], load_rec(D.recC, D.recS2, D.recS3, gid), make_float2(0.f, 0.f), (uint32_t)(w + 1));
+                    propose_one_rec(V, step, 0u, K.NAt, gid, S.meta[w].x & UNIT_MASK, D.recCis[gid], load_rec(D.recC, D.recS2, D.recS3, gid), make_float2(0.f, 0.f), (uint32_t)(w + 1));
                 } else if (w < NAp + NBp) {
                     if (w - NAp < NB) small_propose_lig(V, step, K.NAt + rep * NB + (w - NAp), (uint32_t)(NA + w - NAp + 1));
                 } else { const int e = sm.cxList[w - NAp - NBp]; complex_move_thread(V, e & 0x3fffffff, !(e & 0x40000000), step, 0u); }
@@ -237,6 +261,9 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         if (!sm.listValid || S.nspec > SMALL_SPEC_MAX) {
             __syncthreads();             // (everyone has read nspec)
             if (tid == 0) { S.nspec = 0; sm.nlist = 0; sm.listValid = 1; }
+#ifdef SMALL_TIMING
+            if (tid == 0) tacc[7] += 1;
+#endif
             __syncthreads();
             const int half = N / 2;
             for (int m = tid; m < N; m += SMALL_T) {
@@ -299,18 +326,18 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         if (sm.scal[S_NCAND_RL] | sm.scal[S_NCAND_CIS]) { react_resolve_block(D); __syncthreads(); }
         SMALL_TICK(5);
         if (tid == 0) S.nspec = 0;          // (the special molecules of the NEXT step register during its proposals)
-        finish_body(K, D, tid, SMALL_T, rep * NA, (rep + 1) * NA);
+        finish_body<true>(K, D, tid, SMALL_T, rep * NA, (rep + 1) * NA);
         __syncthreads();
         SMALL_TICK(6);
     }
 #ifdef SMALL_TIMING
     if (tid == 0 && rep == 0 && nsteps >= 1000)          // (diagnostic build only) cycles per step: S1 | proposals | list | classify | pending + S3 pairs | S3 resolve | finish
-        printf("k_small_step cycles/step: %lld %lld %lld %lld %lld %lld %lld\n", tacc[0] / nsteps, tacc[1] / nsteps, tacc[2] / nsteps, tacc[3] / nsteps, tacc[4] / nsteps, tacc[5] / nsteps, tacc[6] / nsteps);
+        printf("k_small_step cycles/step: %lld %lld %lld %lld %lld %lld %lld; %lld list rebuilds in %d steps, last list %d pairs\n", tacc[0] / nsteps, tacc[1] / nsteps, tacc[2] / nsteps, tacc[3] / nsteps, tacc[4] / nsteps, tacc[5] / nsteps, tacc[6] / nsteps, tacc[7], nsteps, sm.nlist);
 #endif
     // the committed state goes back to the global arrays: into the buffers the host regards as committed after this launch
     // (it swaps its pointers when the step count is odd)
     {
-        const int cb = nsteps & 1;
+        const int cb = (s1 - s0) & 1;          // (odd only in the last chunk of an odd launch)
         double2 *gC = cb ? A.D.recCn : A.D.recC, *gS2 = cb ? A.D.recS2n : A.D.recS2, *gS3 = cb ? A.D.recS3n : A.D.recS3;
         double *gL = cb ? A.D.lign : A.D.lig;
         for (int i = tid; i < NA; i += SMALL_T) {
@@ -323,8 +350,13 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
     }
     if (tid == 0) {
         if (sm.scal[S_OVERFLOW]) atomicOr(&A.D.scal[S_OVERFLOW], sm.scal[S_OVERFLOW]);
-        if (rep == 0) A.D.step64[0] = step0 + (unsigned long long)nsteps;
+        if (rep == 0 && s1 == nsteps) A.D.step64[0] = step0 + (unsigned long long)nsteps;
     }
+    if (!queue) break;
+    __threadfence();                     // this chunk's state is out before the replica's next chunk may start
+    __syncthreads();
+    if (tid == 0) atomicExch(&queue[1 + rep], myChunk + 1);
+  }
 }
 
 }  // namespace kmc

@@ -64,6 +64,20 @@ def test_fused_from_random_start_and_long_launch(monkeypatch):
     assert fused.series(0)["step"] == 5000
 
 
+def test_fused_ticket_queue_for_large_ensembles(monkeypatch):
+    """More replicas than CTAs fit on the device: a persistent grid deals the replicas in 64-step chunks through a ticket queue.
+    Forced here with a grid of 3 CTAs for 7 replicas; odd launch lengths, launches shorter and longer than a chunk."""
+    monkeypatch.setenv("KMC_SMALL_GRID", "3")
+    fused, general = _pair_of_paths(monkeypatch, lambda: apply_regime(kmc_b200.default_params(box=(2500.0, 2500.0, 400.0), seed=23, n_replicas=7), "hot"))
+    monkeypatch.delenv("KMC_SMALL_GRID")
+    fused.init_random(seed=4)
+    general.set_packed(*fused.get_packed())
+    for chunk in (5, 64, 333, 1, 1000, 129):
+        fused.step(chunk); general.step(chunk)
+        _same(fused, general, 7)
+    assert fused.series(3)["bond_num"] > 0 and fused.series(0)["step"] == 5 + 64 + 333 + 1 + 1000 + 129
+
+
 def test_fused_small_odd_sizes_against_oracle():
     """odd molecule count (the all-pairs schedule differs for odd and even N), more molecules than threads, crowded box"""
     for na, nb, box in ((31, 10, (900.0, 900.0, 300.0)), (170, 71, (3000.0, 3000.0, 400.0))):
