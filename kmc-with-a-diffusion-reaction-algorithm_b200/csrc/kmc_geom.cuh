@@ -83,9 +83,7 @@ KD void rotz(double c, double s, double x, double y, double ox, double oy, doubl
 
 // full Euler matrix, main.cpp:946-956
 struct Rot3 { double t[3][3]; };
-KD Rot3 euler(const Consts &K, double theta, double phi, double psai) {
-    double ct, st, cp, sp, cs, ss;
-    KMC_SINCOS(K, theta, &st, &ct); KMC_SINCOS(K, phi, &sp, &cp); KMC_SINCOS(K, psai, &ss, &cs);
+KD Rot3 euler_sc(double st, double ct, double sp, double cp, double ss, double cs) {
     Rot3 r;
     r.t[0][0] = sub(mul(cs, cp), mul(mul(ct, sp), ss));
     r.t[0][1] = sub(mul(-ss, cp), mul(mul(ct, sp), cs));
@@ -97,6 +95,11 @@ KD Rot3 euler(const Consts &K, double theta, double phi, double psai) {
     r.t[2][1] = mul(cs, st);
     r.t[2][2] = ct;
     return r;
+}
+KD Rot3 euler(const Consts &K, double theta, double phi, double psai) {
+    double ct, st, cp, sp, cs, ss;
+    KMC_SINCOS(K, theta, &st, &ct); KMC_SINCOS(K, phi, &sp, &cp); KMC_SINCOS(K, psai, &ss, &cs);
+    return euler_sc(st, ct, sp, cp, ss, cs);
 }
 KD void rot3_about(const Rot3 &r, const double s[3], const double c[3], double q[3]) {
     double dx = sub(s[0], c[0]), dy = sub(s[1], c[1]), dz = sub(s[2], c[2]);

@@ -318,6 +318,7 @@ KD void rec_prefetch(const Consts &K, const Dev &D, RecStage &S, int tile, int n
         if (D.refA) __pipeline_memcpy_async(&S.ref[t], &D.refA[gid], 4);          // strips: the reference id keys the random stream
     }
 }
+template <bool SMALL = false>          // SMALL: called by the fused small-system kernel (compact Philox, see philox4x32_10)
 KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc, uint32_t me);
 KD void propose_rec_body(const Args &A) {
     KARGS
@@ -339,11 +340,12 @@ KD void propose_rec_body(const Args &A) {
         const int gid = tile * REC_TILE + threadIdx.x, t = threadIdx.x;
         if (gid < nLive) {
             Rec ra; ra.cx = S.c[t].x; ra.cy = S.c[t].y; ra.s2x = S.s2[t].x; ra.s2y = S.s2[t].y; ra.s3x = S.s3[t].x; ra.s3y = S.s3[t].y;
-            propose_one_rec(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase == 1 ? S.bc[t] : make_float2(0.f, 0.f), D.refA ? S.ref[t] : ref_id(K, D, gid));
+            propose_one_rec<false>(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase == 1 ? S.bc[t] : make_float2(0.f, 0.f), D.refA ? S.ref[t] : ref_id(K, D, gid));
         }
     }
     __pipeline_wait_prior(0);
 }
+template <bool SMALL>
 KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive, int gid, int head, int p, Rec ra, float2 bc, uint32_t me) {
     KARGS
     const Consts &K = cK;
@@ -352,8 +354,8 @@ KD void propose_one_rec(const Args &A, uint64_t step, unsigned stamp, int nLive,
     const uint64_t seed = seed_of(cK, rep);
     {
         const int a = gid;
-        double u0, u1; keyed_uniform2(seed, me, 0, step, 0, u0, u1);
-        const double u2 = keyed_uniform(seed, me, 0, step, 2);
+        double u0, u1; keyed_uniform2<SMALL>(seed, me, 0, step, 0, u0, u1);
+        const double u2 = keyed_uniform<SMALL>(seed, me, 0, step, 2);
         const double phai = mul(mul(u1, 2.0), K.pai);
         double sp, cp; KMC_SINCOS(K, phai, &sp, &cp);
         if (p < 0) {
@@ -1819,12 +1821,13 @@ KD void pend_resolve_block(const Dev &D, int n) {
 // one thread per pre-selected pair (receptor a, neighbour v), final poses: geometric tests of main.cpp:1882-1915 /
 // 1960-1981 / 2014-2035; candidates whose keyed draw succeeds are appended (a failed draw never changes anything,
 // main.cpp:1921/1987/2041); the ordered, first-come-first-served application happens in k_react_resolve
+template <bool SMALL = false>
 KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
     // everything that depends only on (a, v) is requested at once: unit words, bond words and the PROPOSED poses (the final
     // pose of a molecule is its proposal unless its unit was reverted -- the copy-back happens in k_finish --, which is rare:
     // the old pose is fetched only then)
     // (fused small-system step: the unit key written with this step's proposal carries the head)
-    const int ua = K.phase == 2 ? (D.small->meta[small_index(K, D, a)].x & UNIT_MASK) : D.unitOf[a], uv = K.phase == 2 ? (D.small->meta[small_index(K, D, v)].x & UNIT_MASK) : D.unitOf[v];
+    const int ua = SMALL ? (D.small->meta[small_index(K, D, a)].x & UNIT_MASK) : D.unitOf[a], uv = SMALL ? (D.small->meta[small_index(K, D, v)].x & UNIT_MASK) : D.unitOf[v];
     Rec ra = load_rec(D.recCn, D.recS2n, D.recS3n, a);
     if (v >= K.NAt) {
         const int h = v - K.NAt;
@@ -1843,7 +1846,7 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
         const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
         for (int s = 0; s < 3; s++) {
             if (!ok[s]) continue;
-            if (keyed_uniform(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
+            if (keyed_uniform<SMALL>(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
                 int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
                 if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
                 else atomicOr(&D.scal[S_OVERFLOW], 1);
@@ -1859,8 +1862,8 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
         if (!cis_geometry_ok(K, ra, rb)) return;
         const uint64_t seed = seed_of(K, replica_of_gid(K, a));
         const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
-        const bool okMono = keyed_uniform(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
-        const bool okCis = keyed_uniform(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
+        const bool okMono = keyed_uniform<SMALL>(seed, me, j, step, SLOT_MONO_CIS_ON) < K.pMonoCisOn;
+        const bool okCis = keyed_uniform<SMALL>(seed, me, j, step, SLOT_CIS_ON) < K.pCisOn;
         if (okMono || okCis) {
             int q = atomicAdd(&D.scal[S_NCAND_CIS], 1);
             if (q < D.candCap) D.candCis[q] = ((unsigned long long)a << 32) | ((unsigned long long)v << 2) | (okMono ? 1u : 0u) | (okCis ? 2u : 0u);
@@ -1870,6 +1873,7 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
 }
 // work items: the list pairs k_pairs_eval found within reaction reach (sparse path: D.reactList, a dense list, one thread per
 // entry), then the pairs collected by the tile kernel / the special entries (D.pairs).
+template <bool SMALL = false>
 KD void react_pairs_body(const Consts &K, const Dev &D, int tid, int nth) {
     const uint64_t step = D.step64[0];
     const int nl = D.reactList ? min(D.scal[S_NREACT], 2 * D.survCap) : 0;
@@ -1877,12 +1881,12 @@ KD void react_pairs_body(const Consts &K, const Dev &D, int tid, int nth) {
         const int it = D.reactList[q];
         const int2 w = D.surv[it >> 1];
         const int a = w.x & ~GHOST_BIT, b = w.y & ~GHOST_BIT;
-        if (it & 1) react_pair(K, D, step, b, a); else react_pair(K, D, step, a, b);
+        if (it & 1) react_pair<SMALL>(K, D, step, b, a); else react_pair<SMALL>(K, D, step, a, b);
     }
     const int np = min(D.scal[S_NPAIR], D.pairFastCap + D.pairCap);
     for (int i = tid; i < np; i += nth) {
         const unsigned long long pr = i < D.pairFastCap ? D.pairsFast[i] : D.pairs[i - D.pairFastCap];
-        react_pair(K, D, step, (int)(pr >> 32), (int)(pr & 0xffffffffu));
+        react_pair<SMALL>(K, D, step, (int)(pr >> 32), (int)(pr & 0xffffffffu));
     }
 }
 
@@ -1937,12 +1941,13 @@ KD void react_resolve_block(const Dev &D) {
 // S3c, main.cpp:2062-2141, for receptor a with ligand h / cis partner p (-1 none). Keyed draws make the three sequential loops order
 // free: a thread owns the R-L bond of its receptor and the cis bond it is the lower index of; it re-derives the partner's R-L
 // outcome from the partner's own keyed draw instead of waiting for it.
+template <bool SMALL = false>
 KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, int p) {
     const uint64_t seed = seed_of(K, replica_of_gid(K, a));
     const uint32_t me = ref_id(K, D, a);
     bool boundAfter = false;
     if (h >= 0) {
-        if (keyed_uniform(seed, me, 0, step, SLOT_RL_OFF) < K.pOff) {
+        if (keyed_uniform<SMALL>(seed, me, 0, step, SLOT_RL_OFF) < K.pOff) {
             int s = D.recSite[a];
             D.recLig[a] = -1; D.recSite[a] = -1; D.ligRec[h * 3 + s] = -1;
             atomicAdd(&D.events[EV_RL_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, K.NAt + h);
@@ -1951,12 +1956,12 @@ KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, i
     if (p > a) {
         const uint32_t pid = ref_id(K, D, p);
         // partner's ligand state after ITS R-L dissociation trial: -1 already cleared, else apply its draw
-        bool pBoundAfter = D.recLig[p] >= 0 && !(keyed_uniform(seed, pid, 0, step, SLOT_RL_OFF) < K.pOff);
+        bool pBoundAfter = D.recLig[p] >= 0 && !(keyed_uniform<SMALL>(seed, pid, 0, step, SLOT_RL_OFF) < K.pOff);
         bool inComplex = boundAfter || pBoundAfter;
         uint32_t slot = inComplex ? SLOT_CIS_OFF : SLOT_MONO_CIS_OFF;
         double P = inComplex ? K.pCisOff : K.pMonoCisOff;
         // drawn from both ends: the lower index first, the partner only if the bond survived
-        if (keyed_uniform(seed, me, 0, step, slot) < P || keyed_uniform(seed, pid, 0, step, slot) < P) {
+        if (keyed_uniform<SMALL>(seed, me, 0, step, slot) < P || keyed_uniform<SMALL>(seed, pid, 0, step, slot) < P) {
             D.recCis[a] = -1; D.recCis[p] = -1;
             atomicAdd(&D.events[inComplex ? EV_CIS_OFF : EV_MONO_OFF], 1ULL); touch_molecule(D, a); touch_molecule(D, p);
         }
@@ -1989,7 +1994,7 @@ KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, i
         } else for (int k = 0; k < 4; k++) if (a0 + k < K.NAt) { hh[k] = D.recLig[a0 + k]; pp[k] = D.recCis[a0 + k]; }
         if ((hh[0] & hh[1] & hh[2] & hh[3] & pp[0] & pp[1] & pp[2] & pp[3]) < 0) continue;      // all eight words negative: no bond on any of the four
         for (int k = 0; k < 4; k++)
-            if ((!RANGED || a0 + k >= aBeg) && a0 + k < aEnd && (hh[k] >= 0 || pp[k] >= 0)) dissociate(K, D, step, a0 + k, hh[k], pp[k]);
+            if ((!RANGED || a0 + k >= aBeg) && a0 + k < aEnd && (hh[k] >= 0 || pp[k] >= 0)) dissociate<RANGED>(K, D, step, a0 + k, hh[k], pp[k]);
     }
 }
 
@@ -2004,7 +2009,7 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
 #ifndef RPTHREADS
 #define RPTHREADS 64
 #endif
-__global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) { KARGS react_pairs_body(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) { KARGS react_pairs_body<false>(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void k_react_resolve(const __grid_constant__ Args A) { KARGS react_resolve_block(D); }
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body<false>(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, 0); }
 

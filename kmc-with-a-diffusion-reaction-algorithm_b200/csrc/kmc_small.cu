@@ -114,7 +114,7 @@ KD void small_propose_lig(const Args &A, uint64_t step, int gid, uint32_t me) { 
     const double ox = src[0], oy = src[1], oz = src[2];
     const uint64_t seed = seed_of(K, replica_of_gid(K, gid));
     double u0, u1, u2, u3, u4, u5;
-    keyed_uniform2(seed, me, 0, step, 0, u0, u1); keyed_uniform2(seed, me, 0, step, 2, u2, u3); keyed_uniform2(seed, me, 0, step, 4, u4, u5);
+    keyed_uniform2<true>(seed, me, 0, step, 0, u0, u1); keyed_uniform2<true>(seed, me, 0, step, 2, u2, u3); keyed_uniform2<true>(seed, me, 0, step, 4, u4, u5);
     LigMove M; lig_move_setup(K, M, ox, oy, oz, u0, u1, u2, u3, u4, u5);
 #pragma unroll 1
     for (int q = 1; q < 8; q++) {
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
                 if (w < NAp) {
                     if (w >= NA) continue;
                     const int gid = rep * NA + w;
-                    propose_one_rec(V, step, 0u, K.NAt, gid, S.meta[w].x & UNIT_MASK, D.recCis[gid], load_rec(D.recC, D.recS2, D.recS3, gid), make_float2(0.f, 0.f), (uint32_t)(w + 1));
+                    propose_one_rec<true>(V, step, 0u, K.NAt, gid, S.meta[w].x & UNIT_MASK, D.recCis[gid], load_rec(D.recC, D.recS2, D.recS3, gid), make_float2(0.f, 0.f), (uint32_t)(w + 1));
                 } else if (w < NAp + NBp) {
                     if (w - NAp < NB) small_propose_lig(V, step, K.NAt + rep * NB + (w - NAp), (uint32_t)(NA + w - NAp + 1));
                 } else { const int e = sm.cxList[w - NAp - NBp]; complex_move_thread(V, e & 0x3fffffff, !(e & 0x40000000), step, 0u); }
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         // ---- the order dependence of the sweep, from the pending findings ----
         if (sm.scal[S_NPEND] > 0) pend_resolve_block(D, min(sm.scal[S_NPEND], D.pendCap));
         // ---- S3 ----
-        react_pairs_body(K, D, tid, SMALL_T);
+        react_pairs_body<true>(K, D, tid, SMALL_T);
         __syncthreads();
         SMALL_TICK(4);
         if (sm.scal[S_NCAND_RL] | sm.scal[S_NCAND_CIS]) { react_resolve_block(D); __syncthreads(); }
