@@ -60,10 +60,10 @@ struct Rec { double cx, cy, s2x, s2y, s3x, s3y; };
 struct Lig { double p[8][3]; };
 
 // L*round(x/L) (main.cpp:597-598 and its siblings). Away from the box edge the quotient rounds to (+-)0 and the product is
-// (+-)0, which the following subtraction ignores: the division is skipped there (|x| < 0.49 L, x != 0 keeps even the sign of a
+// (+-)0, which the following subtraction ignores: the division is skipped there (|x| < 0.4999 L: the correctly rounded quotient is then below 0.5 and rounds to 0; x != 0 keeps even the sign of a
 // zero coordinate as the reference computes it).
 KD double wrap_offset(double x, double L) {
-    if (x != 0.0 && fabs(x) < 0.49 * L) return 0.0;
+    if (x != 0.0 && fabs(x) < 0.4999 * L) return 0.0;
     return mul(L, round(dvd(x, L)));
 }
 // receptor bead z (main.cpp:301): (j*2-2)*rA, j = 1..4

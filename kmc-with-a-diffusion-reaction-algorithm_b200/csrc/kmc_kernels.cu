@@ -1838,14 +1838,15 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
         if (la >= 0) return;
         if (rejA) ra = load_rec(D.recC, D.recS2, D.recS3, a);
         if (rejV) load_lig(D.lig, h, b);
-        bool any = false;
-        bool ok[3];
-        for (int s = 0; s < 3; s++) { ok[s] = occ[s] < 0 && rl_geometry_ok(K, ra, b, s); any |= ok[s]; }
-        if (!any) return;
+        int okMask = 0;          // (SMALL: the three sites as a loop, one copy of the geometry test in the instruction stream)
+#pragma unroll (SMALL ? 1 : 3)
+        for (int s = 0; s < 3; s++) if (occ[s] < 0 && rl_geometry_ok(K, ra, b, s)) okMask |= 1 << s;
+        if (!okMask) return;
         const uint64_t seed = seed_of(K, replica_of_gid(K, a));
         const uint32_t me = ref_id(K, D, a), j = ref_id(K, D, v);
+#pragma unroll (SMALL ? 1 : 3)
         for (int s = 0; s < 3; s++) {
-            if (!ok[s]) continue;
+            if (!(okMask >> s & 1)) continue;
             if (keyed_uniform<SMALL>(seed, me, 4 * j + (uint32_t)(s + 2), step, SLOT_RL_ON) < K.pOn) {
                 int q = atomicAdd(&D.scal[S_NCAND_RL], 1);
                 if (q < D.candCap) D.candRL[q] = ((unsigned long long)a << 32) | ((unsigned long long)h << 2) | (unsigned)s;
