@@ -4,7 +4,7 @@
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cu"
 #include "kmc_small.cu"
-#define KMC_NKERNELS 22
+#define KMC_NKERNELS 23
 #define MON_EVERY 256
 
 #include <algorithm>
@@ -66,6 +66,7 @@ struct kmc_handle {
     unsigned long long *timeline = nullptr; int tlCount = 0, tlId[64]; cudaStream_t tlStream = nullptr;      // KMC_TIMELINE
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
+    bool cxGroups = true;            // small multi-ligand complexes by groups of 8 lanes on a shared-memory copy (KMC_CX_GROUPS=0: one thread each, on global memory)
     int smallGrid = 0; int *smallQueue = nullptr;      // fused step: CTAs resident at once; ticket queue (1 + R ints) for ensembles larger than that
     bool fused = false;              // small replicas: the whole step is ONE kernel, one CTA per replica, many steps per launch (csrc/kmc_small.cu)
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
@@ -84,10 +85,10 @@ struct kmc_handle {
 static const char *const g_kernel_names[KMC_NKERNELS] = {
     "k_cx_rebuild", "k_uf_hook", "k_uf_flatten", "k_cx_build", "k_propose_rec",
     "k_propose_complex", "k_scan_reduce", "k_scan_sums", "k_scan_down", "k_grid_scatter",
-    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small", "k_step_begin", "k_small_step"};
+    "k_resolve_tiles", "k_pend_resolve", "k_react_pairs", "k_react_resolve", "k_finish", "k_series", "k_pairs_eval", "k_special_pairs", "k_propose_lig", "k_propose_complex_small", "k_step_begin", "k_small_step", "k_propose_complex_multi"};
 enum { KID_UF_INIT = 0, KID_UF_HOOK, KID_UF_FLATTEN, KID_CX_BUILD, KID_PROPOSE_SIMPLE, KID_PROPOSE_COMPLEX,
        KID_SCAN_REDUCE, KID_SCAN_SUMS, KID_SCAN_DOWN, KID_GRID_SCATTER, KID_RESOLVE, KID_PEND_RESOLVE,
-       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL, KID_STEP_BEGIN, KID_SMALL_STEP };
+       KID_REACT_PAIRS, KID_REACT_RESOLVE, KID_FINISH, KID_SERIES, KID_PAIRS_EVAL, KID_SPECIAL, KID_PROPOSE_LIG, KID_PROPOSE_COMPLEX_SMALL, KID_STEP_BEGIN, KID_SMALL_STEP, KID_PROPOSE_COMPLEX_MULTI };
 
 static cudaEvent_t take_event(kmc_handle *h) {
     if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
@@ -286,6 +287,7 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     if (p->min_image != 0) return fail(KMC_ERR_INVALID, "min_image = 1 is not implemented: the reference computes plain Euclidean distances (main.cpp:642-646), which is what 0 selects");
     h->nSM = std::max(prop.multiProcessorCount, 1);
     if (const char *o = getenv("KMC_FORK")) h->forkMask = atoi(o);
+    if (const char *o = getenv("KMC_CX_GROUPS")) h->cxGroups = atoi(o) != 0;
     if (getenv("KMC_TIMELINE")) { void *q = nullptr; if (cudaMalloc(&q, 128 * sizeof(unsigned long long)) == cudaSuccess) { h->allocs.push_back(q); h->timeline = (unsigned long long *)q; } }
     fill_consts(*p, h->K);
     const Consts &K = h->K;
@@ -589,7 +591,8 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
     h->tlStream = s2;
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), h->nSM * 12), 32 * CX_WARPS, 0, s2>>>(A)));      // (large complexes: rare, first)
-    LAUNCH(KID_PROPOSE_COMPLEX_SMALL, (k_propose_complex_small<<<std::min(nblk(NBt, 128), h->nSM * 16), 128, 0, s2>>>(A)));
+    if (h->cxGroups) LAUNCH(KID_PROPOSE_COMPLEX_MULTI, (k_propose_complex_multi<<<std::min(nblk(NBt, CX_GROUPS), h->nSM * 8), CX_G * CX_GROUPS, 0, s2>>>(A)));      // (small complexes with several ligands: 8 lanes each)
+    LAUNCH(KID_PROPOSE_COMPLEX_SMALL, (k_propose_complex_small<<<std::min(nblk(NBt, 128), h->nSM * 16), 128, 0, s2>>>(A, h->cxGroups ? 0 : 1)));
     h->tlStream = nullptr;
     if (fork || forkC) {
         cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);

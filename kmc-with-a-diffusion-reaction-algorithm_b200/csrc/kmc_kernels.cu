@@ -518,21 +518,28 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
 // order matters (wrap centre, rotation centre: main.cpp:1007-1008, 1049-1067) are accumulated by lane 0 in row order.
 // A member handle `m` is a slot of the cache (canonical breadth-first order); complexes with more members than the cache holds
 // take the same code through accessors that go to global memory (handle = gid).
-#define CX_CAP 40          // members cached per complex
-#define CX_WARPS 4         // complexes per CTA
+#define CX_CAP 40          // members cached per complex (one warp per complex: complexes of more than CX_SMALL members)
+#define CX_WARPS 4         // of those, per CTA
+#define CX_GCAP CX_SMALL   // members cached per small complex with several ligands: GROUPS of CX_G lanes, CX_GROUPS of them per CTA
+#define CX_G 8
+#define CX_GROUPS 16
+// a group of G consecutive lanes of a warp (G = 32: the warp) works on one complex
+template <int G> KD unsigned grp_mask() { return G == 32 ? 0xffffffffu : ((G == 32 ? 0u : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) & ~(G - 1))); }
+template <int G> KD void grp_sync() { __syncwarp(grp_mask<G>()); }
+template <int G, class T> KD T grp_bcast(T v) { return __shfl_sync(grp_mask<G>(), v, 0, G); }      // the value of the group's lane 0
 
-struct CxShared {          // per warp
-    double pose[CX_CAP][24];             // receptor: cx,cy,s2x,s2y,s3x,s3y ; ligand: 8 points x 3
-    int gid[CX_CAP];
-    short lig[CX_CAP], cis[CX_CAP], site[CX_CAP];   // receptor: slot of its ligand / cis partner (-1 none), ligand site 0..2
-    short rec3[CX_CAP][3];               // ligand: slot of the receptor on site s (-1 none)
-    unsigned char moved[CX_CAP];
-    int row[CX_CAP];                     // working order (handles), permuted by the shuffles
-    int draw[CX_CAP];                    // the rand() values of one shuffle, drawn by all lanes at once
+template <int CAP> struct CxSharedT {          // per group
+    double pose[CAP][24];             // receptor: cx,cy,s2x,s2y,s3x,s3y ; ligand: 8 points x 3
+    int gid[CAP];
+    short lig[CAP], cis[CAP], site[CAP];   // receptor: slot of its ligand / cis partner (-1 none), ligand site 0..2
+    short rec3[CAP][3];               // ligand: slot of the receptor on site s (-1 none)
+    unsigned char moved[CAP];
+    int row[CAP];                     // working order (handles), permuted by the shuffles
+    int draw[CAP];                    // the rand() values of one shuffle, drawn by all lanes at once
 };
 
-struct CxLocal {           // accessors on the shared-memory copy; handle = slot
-    CxShared &S; const Consts &K; int NAt;
+template <int CAP> struct CxLocalT {           // accessors on the shared-memory copy; handle = slot
+    CxSharedT<CAP> &S; const Consts &K; int NAt;
     KD bool is_rec(int m) const { return S.gid[m] < NAt; }
     KD int recLig(int m) const { return S.lig[m]; }
     KD int recSite(int m) const { return S.site[m]; }
@@ -707,23 +714,23 @@ template <class Cx> KD void align_complex(const Cx &C, int *row, int size, int n
 // run one member per lane -- pass 0 and pass 4 (every receptor is re-snapped onto ITS ligand, ligands are not touched),
 // pass 5 (every ligand-free cis partner is rebuilt from ITS one partner) -- and the Philox draws of a shuffle are made by all
 // lanes; the order-dependent parts (the swaps of a shuffle, passes 1-3 with their moved[] flags and the goto) stay on lane 0.
-KD void shuffle_row_warp(CxShared &S, int size, uint64_t seed, uint32_t root, uint32_t &cnt, uint64_t step, int lane) {
+template <int G, int CAP> KD void shuffle_row_warp(CxSharedT<CAP> &S, int size, uint64_t seed, uint32_t root, uint32_t &cnt, uint64_t step, int lane) {
     const int n = size - 1;
-    for (int i = 1 + lane; i < n; i += 32) S.draw[i] = keyed_rand31(seed, root, cnt + (uint32_t)(i - 1), step) % (i + 1);
+    for (int i = 1 + lane; i < n; i += G) S.draw[i] = keyed_rand31(seed, root, cnt + (uint32_t)(i - 1), step) % (i + 1);
     if (n > 1) cnt += (uint32_t)(n - 1);
-    __syncwarp();
+    grp_sync<G>();
     if (lane == 0)
         for (int i = 1; i < n; i++) { const int j = S.draw[i]; if (i != j) { const int t = S.row[i]; S.row[i] = S.row[j]; S.row[j] = t; } }
-    __syncwarp();
+    grp_sync<G>();
 }
-KD void align_complex_warp(const CxLocal &C, CxShared &S, int size, int nB, uint64_t seed, uint32_t me, uint64_t step, int lane) {
+template <int G, int CAP> KD void align_complex_warp(const CxLocalT<CAP> &C, CxSharedT<CAP> &S, int size, int nB, uint64_t seed, uint32_t me, uint64_t step, int lane) {
     const Consts &K = C.K;
-    if (nB == 1) { if (lane == 0) align_complex(C, S.row, size, nB, 0, seed, me, step); __syncwarp(); return; }
+    if (nB == 1) { if (lane == 0) align_complex(C, S.row, size, nB, 0, seed, me, step); grp_sync<G>(); return; }
     uint32_t cnt = 0;
-    shuffle_row_warp(S, size, seed, me, cnt, step, lane);                   // pass 0 (order free: see above)
-    for (int i = lane; i < size; i += 32) { const int a = S.row[i]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }
-    __syncwarp();
-    shuffle_row_warp(S, size, seed, me, cnt, step, lane);                   // pass 1
+    shuffle_row_warp<G, CAP>(S, size, seed, me, cnt, step, lane);                   // pass 0 (order free: see above)
+    for (int i = lane; i < size; i += G) { const int a = S.row[i]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }
+    grp_sync<G>();
+    shuffle_row_warp<G, CAP>(S, size, seed, me, cnt, step, lane);                   // pass 1
     if (lane == 0)
         for (int i = 0; i < size; i++) {
             const int a = S.row[i];
@@ -734,11 +741,11 @@ KD void align_complex_warp(const CxLocal &C, CxShared &S, int size, int nB, uint
                 if (cis_misaligned(K, r1, r2)) { snap_cis(K, r1, r2); C.put(a, r1); }
             }
         }
-    __syncwarp();
+    grp_sync<G>();
     // passes 2 and 3 (goto lable4, main.cpp:1628 -> 1438): lane 0 runs the state machine, every lane takes part in the shuffles
     int resume = 0; int i = 0, s = 0, h = 0, a1 = 0;
     for (;;) {
-        if (!resume) { shuffle_row_warp(S, size, seed, me, cnt, step, lane); i = 0; }
+        if (!resume) { shuffle_row_warp<G, CAP>(S, size, seed, me, cnt, step, lane); i = 0; }
         if (lane == 0) {
             bool rs = resume != 0;
             for (; i < size; i++) {
@@ -755,8 +762,8 @@ KD void align_complex_warp(const CxLocal &C, CxShared &S, int size, int nB, uint
                 }
             }
         }
-        __syncwarp();
-        shuffle_row_warp(S, size, seed, me, cnt, step, lane);               // pass 3
+        grp_sync<G>();
+        shuffle_row_warp<G, CAP>(S, size, seed, me, cnt, step, lane);               // pass 3
         resume = 0;
         if (lane == 0) {
             for (i = 0; i < size; i++) {
@@ -770,17 +777,17 @@ KD void align_complex_warp(const CxLocal &C, CxShared &S, int size, int nB, uint
                 if (resume) break;
             }
         }
-        resume = __shfl_sync(0xffffffffu, resume, 0);
+        resume = grp_bcast<G>(resume);
         if (!resume) break;
     }
-    __syncwarp();
-    for (int q = lane; q < size; q += 32) { const int a = S.row[q]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }   // pass 4
-    __syncwarp();
-    for (int q = lane; q < size; q += 32) {                                                                                              // pass 5
+    grp_sync<G>();
+    for (int q = lane; q < size; q += G) { const int a = S.row[q]; if (C.is_rec(a) && resnap_rec_to_its_ligand(C, a)) C.set_moved(a); }   // pass 4
+    grp_sync<G>();
+    for (int q = lane; q < size; q += G) {                                                                                              // pass 5
         const int a = S.row[q];
         if (C.is_rec(a) && C.recLig(a) >= 0 && C.recCis(a) >= 0 && C.recLig(C.recCis(a)) < 0) resnap_cis_partner(C, a, C.recCis(a));
     }
-    __syncwarp();
+    grp_sync<G>();
 }
 
 // rigid move of one member given the unit's shift / wrap / rotation (main.cpp:993-1026, 1035-1070, 1103-1128 for one molecule)
@@ -962,11 +969,12 @@ KD void complex_move_thread(const Args &A, int h0, bool maybeSingle, uint64_t st
 }
 // small complexes (the bulk of an oligomerised membrane: 2-12 members): one THREAD per complex. The alignment is a serial,
 // branchy algorithm; a warp per complex leaves 31 of 32 lanes idle in it, a thread per complex runs 32 of them per warp.
-__global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_constant__ Args A) {
+__global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_constant__ Args A, int withMulti) {
     KARGS
     const Consts &K = cK;
-    // two lists back to back: single-ligand complexes, padded to a whole number of warps, then the multi-ligand ones
-    const int n1 = D.scal[S_NCX], n1pad = (n1 + 31) & ~31, ncx = n1pad + D.scal[S_NCX_MULTI];
+    // two lists back to back: single-ligand complexes, padded to a whole number of warps, then (unless k_propose_complex_multi
+    // takes them) the multi-ligand ones
+    const int n1 = D.scal[S_NCX], n1pad = (n1 + 31) & ~31, ncx = n1pad + (withMulti ? D.scal[S_NCX_MULTI] : 0);
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < ncx; ci += gridDim.x * blockDim.x) {
@@ -975,24 +983,29 @@ __global__ void __launch_bounds__(128) k_propose_complex_small(const __grid_cons
     }
 }
 
-__global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __grid_constant__ Args A) {
+// G lanes per complex, NG complexes per CTA, CAP members cached; LIST 2: the large complexes (one warp each), LIST 1: the small
+// complexes with several ligands (S2f: shuffles and passes) -- a serial algorithm on dependent gathers when one thread runs it on
+// global memory (402 us for 94 000 two-ligand complexes); here the group loads the members side by side into shared memory,
+// lane 0 runs the order-dependent parts there, the order-free passes and the draws of a shuffle go one member per lane
+template <int G, int NG, int CAP, int LIST>
+KD void propose_complex_groups(const Args &A) {
     KARGS
-    __shared__ CxShared SH[CX_WARPS];
+    __shared__ CxSharedT<CAP> SH[NG];
     const uint64_t step = D.step64[0];
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const Consts &K = cK;
-    const int ncx = D.scal[S_NCX_BIG];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warp = blockIdx.x * CX_WARPS + wib, nwarps = gridDim.x * CX_WARPS;
-    CxShared &S = SH[wib];
+    const int ncx = D.scal[LIST == 2 ? S_NCX_BIG : S_NCX_MULTI];
+    const int lane = threadIdx.x & (G - 1), wib = threadIdx.x / G;
+    const int warp = blockIdx.x * NG + wib, nwarps = gridDim.x * NG;
+    CxSharedT<CAP> &S = SH[wib];
     for (int ci = warp; ci < ncx; ci += nwarps) {
-        const int h0 = D.cxRoots[K.NBt - 1 - ci], rootGid = K.NAt + h0;
+        const int h0 = LIST == 2 ? D.cxRoots[K.NBt - 1 - ci] : D.cxRoots[K.NBt + ci], rootGid = K.NAt + h0;
         const int size = D.cxSize[h0];
         const int *rowIn = D.members + D.cxOff[h0];
         int *rowOut = D.rowWork + D.cxOff[h0];
         const uint64_t seed = seed_of(cK, replica_of_gid(K, K.NAt + h0));
         const uint32_t me = ref_id(K, D, rootGid);
-        const bool cached = size <= CX_CAP;
+        const bool cached = size <= CAP;
         int nB = 0;
         for (int i = 0; i < size; i++) nB += rowIn[i] >= K.NAt;          // (uniform across the warp, tiny)
         const int nA = size - nB;
@@ -1005,10 +1018,10 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
         const double shx = mul(amp, cp), shy = mul(amp, sp);
         const double psai = mul(sub(mul(2.0, u2), 1.0), nB == 1 ? K.rotBond : 0.0);
         double ss, cs; KMC_SINCOS(K, psai, &ss, &cs);
-        __syncwarp();
+        grp_sync<G>();
         if (cached) {
             // load: every lane its members (old pose + the bonds inside the complex as slots), translated by the shift
-            for (int i = lane; i < size; i += 32) {
+            for (int i = lane; i < size; i += G) {
                 const int m = rowIn[i];
                 S.gid[i] = m; S.row[i] = i; S.moved[i] = 0;
                 double *p = S.pose[i];
@@ -1024,16 +1037,16 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 }
                 shift_pose(p, m < K.NAt, shx, shy, false);
             }
-            __syncwarp();
+            grp_sync<G>();
             double PBx = 0, PBy = 0;
             if (lane == 0) {                                             // wrap centre: sum in row order (main.cpp:1007-1008, 1022-1023)
                 for (int i = 0; i < size; i++) { PBx = add(PBx, S.pose[i][0]); PBy = add(PBy, S.pose[i][1]); }
                 PBx = mul(K.Lx, round(dvd(dvd(PBx, (double)(nA + nB)), K.Lx)));
                 PBy = mul(K.Ly, round(dvd(dvd(PBy, (double)(nA + nB)), K.Ly)));
             }
-            PBx = __shfl_sync(0xffffffffu, PBx, 0); PBy = __shfl_sync(0xffffffffu, PBy, 0);
-            for (int i = lane; i < size; i += 32) shift_pose(S.pose[i], S.gid[i] < K.NAt, PBx, PBy, true);
-            __syncwarp();
+            PBx = grp_bcast<G>(PBx); PBy = grp_bcast<G>(PBy);
+            for (int i = lane; i < size; i += G) shift_pose(S.pose[i], S.gid[i] < K.NAt, PBx, PBy, true);
+            grp_sync<G>();
             double cmx = 0, cmy = 0, cmz = 0;
             if (lane == 0) {                                             // rotation centre: bead by bead in row order (main.cpp:1048-1068)
                 for (int i = 0; i < size; i++) {
@@ -1044,13 +1057,13 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
                 const double nbeads = (double)(4 * nA + 4 * nB);
                 cmx = dvd(cmx, nbeads); cmy = dvd(cmy, nbeads); cmz = dvd(cmz, nbeads);
             }
-            cmx = __shfl_sync(0xffffffffu, cmx, 0); cmy = __shfl_sync(0xffffffffu, cmy, 0); cmz = __shfl_sync(0xffffffffu, cmz, 0);
-            for (int i = lane; i < size; i += 32) rotate_pose(S.pose[i], S.gid[i] < K.NAt, cs, ss, cmx, cmy, cmz);
-            __syncwarp();
-            { CxLocal C{S, K, K.NAt}; align_complex_warp(C, S, size, nB, seed, me, step, lane); }     // the root ligand is slot 0
+            cmx = grp_bcast<G>(cmx); cmy = grp_bcast<G>(cmy); cmz = grp_bcast<G>(cmz);
+            for (int i = lane; i < size; i += G) rotate_pose(S.pose[i], S.gid[i] < K.NAt, cs, ss, cmx, cmy, cmz);
+            grp_sync<G>();
+            { CxLocalT<CAP> C{S, K, K.NAt}; align_complex_warp<G, CAP>(C, S, size, nB, seed, me, step, lane); }     // the root ligand is slot 0
             // store: new poses, the working row (cluster.log order), far flags + grid histogram, order keys
             const int ckey = unit_key(K, rootGid, D.lig[(size_t)h0 * 24], D.lig[(size_t)h0 * 24 + 1]);
-            for (int i = lane; i < size; i += 32) {
+            for (int i = lane; i < size; i += G) {
                 const int m = S.gid[i]; const double *p = S.pose[i];
                 rowOut[i] = S.gid[S.row[i]];
                 if (K.mode) D.ukey[m] = ckey;
@@ -1066,9 +1079,11 @@ __global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __gr
             }
         } else if (lane == 0) complex_move_serial(A, h0, size, nB, step, stamp, u0, u1, u2);      // larger than the cache
         if (lane == 0) { D.unitRes[rootGid] = 0; D.pendCnt[rootGid] = 0; }
-        __syncwarp();
+        grp_sync<G>();
     }
 }
+__global__ void __launch_bounds__(32 * CX_WARPS, 6) k_propose_complex(const __grid_constant__ Args A) { propose_complex_groups<32, CX_WARPS, CX_CAP, 2>(A); }
+__global__ void __launch_bounds__(CX_G * CX_GROUPS) k_propose_complex_multi(const __grid_constant__ Args A) { propose_complex_groups<CX_G, CX_GROUPS, CX_GCAP, 1>(A); }
 
 // ------------------------------------------------------------------------------------------------
 // neighbour grid: counting sort of molecule centres by cell (old centre; far movers get a second,
