@@ -23,6 +23,7 @@ enum Scalar {
     S_NCX_BIG,            // complexes with more than CX_SMALL members: listed from the END of the first half of cxRoots[] (one warp each)
     S_NCX_MULTI,          // small complexes with several ligands: listed in the second half of cxRoots[] (S_NCX counts the single-ligand ones)
     S_NREACT,             // entries of reactList this step
+    S_REC_TICKET,         // k_propose_rec: tiles handed out beyond the first one per CTA (dynamic schedule)
     S_NTOUCH,             // endpoints of the bonds formed / broken in the last step's S3 (touchList): their complexes are updated incrementally
     S_COUNT = 24
 };

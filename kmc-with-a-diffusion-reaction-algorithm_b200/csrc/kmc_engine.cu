@@ -164,6 +164,23 @@ static double sq_threshold(double c) {
     return T;
 }
 
+// AreSame(sqrt(q), t), i.e. fabs(sqrt(q) - t) < 1e-8 (main.cpp:2368-2371), as a window on q: sqrt is correctly rounded and monotone
+// and the rounded difference is monotone in its first operand, so the q that pass form an interval; its two ends are found by
+// stepping through the neighbouring doubles with the predicate itself. w[0] > w[1] (not available) if the search does not settle.
+static void same_window(double t, double w[2]) {
+    auto ok = [&](double q) { return fabs(sqrt(q) - t) < 1.0E-8; };
+    w[0] = 1; w[1] = 0;
+    if (!(t > 1.0E-6) || !ok(t * t)) return;
+    double lo = (t - 1.0E-8) * (t - 1.0E-8), hi = (t + 1.0E-8) * (t + 1.0E-8);
+    int guard = 0;
+    while (ok(lo) && ++guard < 100000) lo = nextafter(lo, 0.0);
+    while (!ok(lo) && ++guard < 200000) lo = nextafter(lo, INFINITY);
+    while (ok(hi) && ++guard < 300000) hi = nextafter(hi, INFINITY);
+    while (!ok(hi) && ++guard < 400000) hi = nextafter(hi, 0.0);
+    if (guard >= 100000 || !ok(lo) || !ok(hi) || ok(nextafter(lo, 0.0)) || ok(nextafter(hi, INFINITY)) || !(lo <= t * t && t * t <= hi)) return;
+    w[0] = lo; w[1] = hi;
+}
+
 // derived constants with the reference's own expressions (host doubles, no contraction: see build flags)
 static void fill_consts(const kmc_params &P, Consts &K) {
     memset(&K, 0, sizeof K);
@@ -179,6 +196,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     K.ovAA2 = sq_threshold(K.ovAA); K.ovAB2 = sq_threshold(K.ovAB); K.ovBB2 = sq_threshold(K.ovBB);
     K.rlD1 = P.bond_dist_cut / 2 + P.rA + P.rB; K.rlD2 = P.bond_dist_cut / 2;
     K.cisD1 = P.cis_dist_cut / 2 + P.rA + P.rA; K.cisD2 = P.cis_dist_cut / 2;
+    same_window(K.rlD1, K.wRL1); same_window(K.rlD2, K.wRL2); same_window(K.cisD1, K.wCis1); same_window(K.cisD2, K.wCis2);
     K.fRL1 = (P.bond_dist_cut / 2 + P.rA) / P.rB; K.fRL3 = (P.bond_dist_cut / 2 + 2 * P.rA) / P.rB; K.fRL2 = (P.bond_dist_cut / 2) / P.rB;
     K.fC1 = (P.cis_dist_cut / 2 + P.rA) / P.rA; K.fC3 = (P.cis_dist_cut / 2) / P.rA; K.fC2 = (P.cis_dist_cut / 2 + 2 * P.rA) / P.rA;
     K.fSeat = (P.bond_dist_cut / 2 + P.rB * 2 / sqrt(3) + P.rB) / P.rA;
@@ -586,16 +604,18 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
     const int forkMask = h->profiling ? 0 : h->forkMask;     // bit0: receptor/ligand proposals side by side (measured slower than back to back), bit1: special entries, bit2: complexes
     const bool fork = forkMask & 1, fork2 = forkMask & 2, forkC = forkMask & 5;                       // bit2: only the complexes on a side branch
     cudaStream_t s1 = fork ? h->side[0] : st, s2 = forkC ? h->side[1] : st;
-    if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(s1, h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
+    if (fork || forkC) { cudaEventRecord(h->evFork[0], st); cudaStreamWaitEvent(h->side[0], h->evFork[0], 0); cudaStreamWaitEvent(s2, h->evFork[0], 0); }
     LAUNCH(KID_PROPOSE_SIMPLE, (k_propose_rec<<<std::min(nblk(std::max(NAt, 1), REC_TILE), h->nSM * RECMINB), REC_TILE, 0, st>>>(A)));
     LAUNCH(KID_PROPOSE_LIG, (k_propose_lig<<<nblk(NBt, B), B, 0, s1>>>(A)));
     h->tlStream = s2;
     LAUNCH(KID_PROPOSE_COMPLEX, (k_propose_complex<<<std::min(nblk(NBt, CX_WARPS), h->nSM * 12), 32 * CX_WARPS, 0, s2>>>(A)));      // (large complexes: rare, first)
-    if (h->cxGroups) LAUNCH(KID_PROPOSE_COMPLEX_MULTI, (k_propose_complex_multi<<<std::min(nblk(NBt, CX_GROUPS), h->nSM * 8), CX_G * CX_GROUPS, 0, s2>>>(A)));      // (small complexes with several ligands: 8 lanes each)
     LAUNCH(KID_PROPOSE_COMPLEX_SMALL, (k_propose_complex_small<<<std::min(nblk(NBt, 128), h->nSM * 16), 128, 0, s2>>>(A, h->cxGroups ? 0 : 1)));
+    // small complexes with several ligands: 8 lanes each, next to the thread-per-complex kernel when the ligand proposals do not use that branch
+    cudaStream_t s4 = (forkC && !fork) ? h->side[0] : s2;
+    if (h->cxGroups) { h->tlStream = s4; LAUNCH(KID_PROPOSE_COMPLEX_MULTI, (k_propose_complex_multi<<<std::min(nblk(NBt, CX_GROUPS), h->nSM * 32), CX_G * CX_GROUPS, 0, s4>>>(A))); }
     h->tlStream = nullptr;
     if (fork || forkC) {
-        cudaEventRecord(h->evJoin[0], s1); cudaEventRecord(h->evJoin[1], s2);
+        cudaEventRecord(h->evJoin[0], h->side[0]); cudaEventRecord(h->evJoin[1], s2);
         cudaStreamWaitEvent(st, h->evJoin[0], 0); cudaStreamWaitEvent(st, h->evJoin[1], 0);
     }
     if (build) {

@@ -36,6 +36,7 @@ struct Consts {
     double ovAA2, ovAB2, ovBB2;               // exact squared thresholds: sqrt_rn(d2) < ov  <=>  d2 < ov2 (see sq_threshold)
     double rlD1, rlD2;                        // bondCut/2+rA+rB, bondCut/2      main.cpp:1215
     double cisD1, cisD2;                      // cisCut/2+rA+rA, cisCut/2        main.cpp:780-781
+    double wRL1[2], wRL2[2], wCis1[2], wCis2[2];   // AreSame(sqrt(q), D) <=> w[0] <= q <= w[1]: the exact windows of the squared distance for the four alignment lengths above (same_window, host); w[0] > w[1] = not available, take the square root
     double fRL1, fRL3, fRL2;                  // (bondCut/2+rA)/rB, (bondCut/2+2rA)/rB, (bondCut/2)/rB   1217-1227
     double fC1, fC3, fC2;                     // (cisCut/2+rA)/rA, (cisCut/2)/rA, (cisCut/2+2rA)/rA      787-797
     double fSeat;                             // (bondCut/2 + rB*2/sqrt(3) + rB)/rA                      1491
@@ -138,26 +139,35 @@ KD bool hit_lig_lig(const Consts &K, const Lig &a, const Lig &b) {
 }
 
 // ---- alignment predicates and snaps ----
-// main.cpp:1205-1215: ligand site index s = 0..2 (reference j = s+2)
-KD bool rl_misaligned(const Consts &K, const Lig &b, int s, const Rec &a) {
-    double d2 = dist2d(b.p[5 + s][0], b.p[5 + s][1], a.s2x, a.s2y);
-    double d1 = dist2d(b.p[1 + s][0], b.p[1 + s][1], a.cx, a.cy);
-    return !are_same(d1, K.rlD1) || !are_same(d2, K.rlD2);
+// AreSame(dist2d(a, b), D) (main.cpp:2368-2371 on the distances of 1205-1215 / 1245-1255) without the square root: sqrt is
+// correctly rounded and monotone and |s - D| < 1e-8 holds on an interval of s, so the test is a window on the squared distance
+// q, computed exactly on the host (kmc_engine.cu: same_window). The alignment code evaluates it dozens of times per complex.
+KD bool same_dist(const double w[2], double D, double ax, double ay, double bx, double by) {
+    const double q = add(sq(sub(ax, bx)), sq(sub(ay, by)));
+    if (w[0] > w[1]) return are_same(sqrt(q), D);
+    return q >= w[0] && q <= w[1];
 }
+// main.cpp:1205-1215: ligand site s (reference j = s+2) given by its site point (sx, sy) and its bead (bx, by)
+KD bool rl_misaligned(const Consts &K, double sx, double sy, double bx, double by, const Rec &a) {
+    const bool same2 = same_dist(K.wRL2, K.rlD2, sx, sy, a.s2x, a.s2y);
+    const bool same1 = same_dist(K.wRL1, K.rlD1, bx, by, a.cx, a.cy);
+    return !same1 || !same2;
+}
+KD bool rl_misaligned(const Consts &K, const Lig &b, int s, const Rec &a) { return rl_misaligned(K, b.p[5 + s][0], b.p[5 + s][1], b.p[1 + s][0], b.p[1 + s][1], a); }
 // main.cpp:1245-1255
 KD bool cis_misaligned(const Consts &K, const Rec &a1, const Rec &a2) {
-    double d2 = dist2d(a1.s3x, a1.s3y, a2.s3x, a2.s3y);
-    double d1 = dist2d(a1.cx, a1.cy, a2.cx, a2.cy);
-    return !are_same(d1, K.cisD1) || !are_same(d2, K.cisD2);
+    const bool same2 = same_dist(K.wCis2, K.cisD2, a1.s3x, a1.s3y, a2.s3x, a2.s3y);
+    const bool same1 = same_dist(K.wCis1, K.cisD1, a1.cx, a1.cy, a2.cx, a2.cy);
+    return !same1 || !same2;
 }
-// main.cpp:1216-1228: receptor rebuilt on the bead->site axis of ligand site s
-KD void snap_rec_to_lig(const Consts &K, Rec &a, const Lig &b, int s) {
-    double ux = sub(b.p[5 + s][0], b.p[1 + s][0]), uy = sub(b.p[5 + s][1], b.p[1 + s][1]);
-    double sx = b.p[5 + s][0], sy = b.p[5 + s][1];
+// main.cpp:1216-1228: receptor rebuilt on the bead->site axis of a ligand site (site point (sx, sy), bead (bx, by))
+KD void snap_rec_to_lig(const Consts &K, Rec &a, double sx, double sy, double bx, double by) {
+    double ux = sub(sx, bx), uy = sub(sy, by);
     a.cx = add(mul(K.fRL1, ux), sx);  a.cy = add(mul(K.fRL1, uy), sy);
     a.s3x = add(mul(K.fRL3, ux), sx); a.s3y = add(mul(K.fRL3, uy), sy);
     a.s2x = add(mul(K.fRL2, ux), sx); a.s2y = add(mul(K.fRL2, uy), sy);
 }
+KD void snap_rec_to_lig(const Consts &K, Rec &a, const Lig &b, int s) { snap_rec_to_lig(K, a, b.p[5 + s][0], b.p[5 + s][1], b.p[1 + s][0], b.p[1 + s][1]); }
 // main.cpp:786-798 / 1256-1268: dst rebuilt from the centre->site-3 axis of src
 KD void snap_cis(const Consts &K, Rec &dst, const Rec &src) {
     double ux = sub(src.s3x, src.cx), uy = sub(src.s3y, src.cy);

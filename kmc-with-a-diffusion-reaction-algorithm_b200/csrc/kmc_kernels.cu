@@ -119,7 +119,7 @@ __global__ void k_step_begin(const __grid_constant__ Args A, int begin) {
     if (begin) {
         D.step64[0] += 1; D.scal[S_EPOCH] += 1;
         if (D.scal[S_NSPEC] > D.scal[S_NSPEC_MAX]) D.scal[S_NSPEC_MAX] = D.scal[S_NSPEC];
-        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0; D.scal[S_NREACT] = 0;
+        D.scal[S_NFAR] = 0; D.scal[S_NPEND] = 0; D.scal[S_NPAIR] = 0; D.scal[S_NSPEC] = 0; D.scal[S_NCAND_RL] = 0; D.scal[S_NCAND_CIS] = 0; D.scal[S_NREJ] = 0; D.scal[S_NREACT] = 0; D.scal[S_REC_TICKET] = 0;
         if (cK.phase == 0) D.scal[S_NSURV] = 0;          // (a reuse step keeps the pair list of the last build step)
     }
     const int nt = D.scal[S_NTOUCH];
@@ -328,11 +328,22 @@ KD void propose_rec_body(const Args &A) {
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int nLive = nA_live(D);
     const int ntiles = (nLive + REC_TILE - 1) / REC_TILE;          // (live receptors only: a strip's capacity padding costs nothing)
+    // Tiles are handed out dynamically (the first one is the CTA's own index, the following ones come from a ticket counter that
+    // k_step_begin resets): a CTA that becomes resident late -- the complex kernels of the side branches share the SMs -- simply
+    // takes fewer tiles, where a static stride would leave its share of the tiles for the very end of the kernel.
+#ifndef RECDYN
+#define RECDYN 1
+#endif
+    __shared__ int s_next;
     int tile = blockIdx.x;
+    if (threadIdx.x == 0) s_next = RECDYN ? gridDim.x + atomicAdd(&D.scal[S_REC_TICKET], 1) : tile + gridDim.x;
     if (tile < ntiles) rec_prefetch(K, D, ST[0], tile, nLive);
     __pipeline_commit();
-    for (int it = 0; tile < ntiles; it++, tile += gridDim.x) {
-        const int next = tile + gridDim.x;
+    __syncthreads();
+    int next = s_next;
+    for (int it = 0; tile < ntiles; it++) {
+        if (RECDYN) __syncthreads();                          // (everyone has read s_next)
+        if (RECDYN && threadIdx.x == 0) s_next = gridDim.x + atomicAdd(&D.scal[S_REC_TICKET], 1);      // the tile after the next one: its latency hides behind this tile's arithmetic
         if (next < ntiles) rec_prefetch(K, D, ST[(it + 1) & 1], next, nLive);
         __pipeline_commit();
         __pipeline_wait_prior(1);                 // everything but the newest group has landed: this tile's slot is ready
@@ -342,6 +353,7 @@ KD void propose_rec_body(const Args &A) {
             Rec ra; ra.cx = S.c[t].x; ra.cy = S.c[t].y; ra.s2x = S.s2[t].x; ra.s2y = S.s2[t].y; ra.s3x = S.s3[t].x; ra.s3y = S.s3[t].y;
             propose_one_rec<false>(A, step, stamp, nLive, gid, S.head[t], S.cis[t], ra, K.phase == 1 ? S.bc[t] : make_float2(0.f, 0.f), D.refA ? S.ref[t] : ref_id(K, D, gid));
         }
+        if (RECDYN) { __syncthreads(); tile = next; next = s_next; } else { tile = next; next = tile + gridDim.x; }
     }
     __pipeline_wait_prior(0);
 }
@@ -522,7 +534,7 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
 #define CX_WARPS 4         // of those, per CTA
 #define CX_GCAP CX_SMALL   // members cached per small complex with several ligands: GROUPS of CX_G lanes, CX_GROUPS of them per CTA
 #define CX_G 8
-#define CX_GROUPS 16
+#define CX_GROUPS 4          // (one warp, 10 KB of shared memory per CTA: an idle launch -- a membrane without such complexes -- does not keep the streaming kernels' CTAs waiting for shared memory)
 // a group of G consecutive lanes of a warp (G = 32: the warp) works on one complex
 template <int G> KD unsigned grp_mask() { return G == 32 ? 0xffffffffu : ((G == 32 ? 0u : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) & ~(G - 1))); }
 template <int G> KD void grp_sync() { __syncwarp(grp_mask<G>()); }
@@ -550,6 +562,7 @@ template <int CAP> struct CxLocalT {           // accessors on the shared-memory
     KD Rec rec(int m) const { const double *p = S.pose[m]; Rec r = {p[0], p[1], p[2], p[3], p[4], p[5]}; return r; }
     KD void put(int m, const Rec &r) const { double *p = S.pose[m]; p[0] = r.cx; p[1] = r.cy; p[2] = r.s2x; p[3] = r.s2y; p[4] = r.s3x; p[5] = r.s3y; }
     KD void lig(int m, Lig &l) const { const double *p = S.pose[m]; for (int q = 0; q < 24; q++) (&l.p[0][0])[q] = p[q]; }
+    KD void lig_site(int m, int s, double &sx, double &sy, double &bx, double &by) const { const double *p = S.pose[m]; sx = p[(5 + s) * 3]; sy = p[(5 + s) * 3 + 1]; bx = p[(1 + s) * 3]; by = p[(1 + s) * 3 + 1]; }
     KD void put(int m, const Lig &l) const { double *p = S.pose[m]; for (int q = 0; q < 24; q++) p[q] = (&l.p[0][0])[q]; }
 };
 struct CxGlobal {          // accessors straight on the nxt arrays; handle = gid
@@ -564,6 +577,7 @@ struct CxGlobal {          // accessors straight on the nxt arrays; handle = gid
     KD Rec rec(int m) const { return load_rec(D.recCn, D.recS2n, D.recS3n, m); }
     KD void put(int m, const Rec &r) const { store_rec(D.recCn, D.recS2n, D.recS3n, m, r); }
     KD void lig(int m, Lig &l) const { load_lig(D.lign, m - NAt, l); }
+    KD void lig_site(int m, int s, double &sx, double &sy, double &bx, double &by) const { const double *p = D.lign + (size_t)(m - NAt) * 24; sx = p[(5 + s) * 3]; sy = p[(5 + s) * 3 + 1]; bx = p[(1 + s) * 3]; by = p[(1 + s) * 3 + 1]; }
     KD void put(int m, const Lig &l) const { store_lig(D.lign, m - NAt, l); }
 };
 
@@ -571,10 +585,10 @@ struct CxGlobal {          // accessors straight on the nxt arrays; handle = gid
 template <class Cx> KD bool resnap_rec_to_its_ligand(const Cx &C, int a) {
     const int h = C.recLig(a); if (h < 0) return false;
     const int s = C.recSite(a);
-    Lig b; C.lig(h, b);
+    double sx, sy, bx, by; C.lig_site(h, s, sx, sy, bx, by);          // (the test and the snap only read the site point and its bead)
     Rec r = C.rec(a);
-    if (!rl_misaligned(C.K, b, s, r)) return false;
-    snap_rec_to_lig(C.K, r, b, s); C.put(a, r);
+    if (!rl_misaligned(C.K, sx, sy, bx, by, r)) return false;
+    snap_rec_to_lig(C.K, r, sx, sy, bx, by); C.put(a, r);
     return true;
 }
 // main.cpp:1548-1578, 1699-1728: re-snap the cis partner of a from a's axis if misaligned
@@ -614,8 +628,8 @@ template <class Cx> KD bool bridge_candidate(const Cx &C, int h, int s) {       
     return C.recLig(a2) >= 0 && !C.moved(h);
 }
 template <class Cx> KD bool lig_site_misaligned(const Cx &C, int h, int s, int a1) {
-    Lig b; C.lig(h, b); const Rec r = C.rec(a1);
-    return rl_misaligned(C.K, b, s, r);
+    double sx, sy, bx, by; C.lig_site(h, s, sx, sy, bx, by);
+    return rl_misaligned(C.K, sx, sy, bx, by, C.rec(a1));
 }
 // std::random_shuffle(&row[1], &row[size]) with rand() (libstdc++): the last member never moves (main.cpp:1285)
 KD void shuffle_row(int *row, int size, uint64_t seed, uint32_t root, uint32_t &cnt, uint64_t step) {

@@ -23,7 +23,8 @@ for r in rows:
         ie = hdr.index("Instructions Executed"); te = hdr.index("Thread Instructions Executed"); sm = hdr.index("# Samples")
         key = (cur_file, int(r[0]))
         a = agg.setdefault(key, [0, 0, 0, r[1].strip()[:110]])
-        a[0] += int(r[ie] or 0); a[1] += int(r[te] or 0); a[2] += int(r[sm] or 0)
+        num = lambda x: int(x) if x.lstrip("-").isdigit() and x != "-" else 0
+        a[0] += num(r[ie]); a[1] += num(r[te]); a[2] += num(r[sm])
 tot = sum(a[0] for a in agg.values()) or 1
 tots = sum(a[2] for a in agg.values()) or 1
 print("total warp instructions %d, samples %d" % (tot, tots))
