@@ -193,7 +193,7 @@ def extras_single_gpu(kmc_b200, args, local, M, na, nb):
         out["config_1e5"] = {"error": str(ex)[:200]}
     # configs[2]: 1024 replicas of the default system in one handle
     try:
-        out["ensemble1024"] = ensemble_measure(kmc_b200, 1024, local, args.seed, steps=1000)
+        out["ensemble1024"] = ensemble_measure(kmc_b200, 1024, local, args.seed, steps=2000)
     except Exception as ex:
         out["ensemble1024"] = {"error": str(ex)[:200]}
     return out
@@ -458,7 +458,7 @@ def ensemble_workload(args, kmc_b200, torch, dist, rank, world, local, allmax):
     from kmc_b200.sharding import replica_range
     total = 1024
     lo, hi = replica_range(rank, world, total)
-    S = max(args.mc_steps, 500)
+    S = max(args.mc_steps, 2000)
     k = kmc_b200.Kmc(kmc_b200.default_params(n_replicas=hi - lo, seed=args.seed + lo, device=local))
     k.init_random(seed=args.seed + 1 + lo)
     for _ in range(args.warmup):
@@ -488,7 +488,8 @@ def ensemble_workload(args, kmc_b200, torch, dist, rank, world, local, allmax):
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "ensemble1024: 1024 independent replicas of the reference's default system (150 receptors + 50 ligands, paper parameters), "
                                        "%d per GPU, no inter-GPU communication (BASELINE configs[2])" % (hi - lo), "mc_steps_per_step": S,
-                           "us_per_mc_step": 1e3 * ms_max / args.steps / S, "l2": "L2 resident by nature (47 MB of state): launch-latency bound, reported against launch latency",
+                           "us_per_mc_step": 1e3 * ms_max / args.steps / S, "step_path": k.path(),
+                           "l2": "state resident in shared memory for the length of a launch (fused step: one CTA per replica, the whole time step in one kernel, %d steps per launch); not an HBM-bound workload" % S,
                            "timing": "CUDA events on the library stream"},
                 "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": value * B_ALG_STEP / 1e9, "peak": peak * world, "peak_source": peak_src, "unit": "GB/s",
                              "frac": value * B_ALG_STEP / 1e9 / (peak * world), "traffic": None},
