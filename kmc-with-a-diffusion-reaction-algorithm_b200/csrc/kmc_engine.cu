@@ -67,6 +67,7 @@ struct kmc_handle {
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 6;                // KMC_FORK, read once at kmc_create
     bool cxGroups = true;            // small multi-ligand complexes by groups of 8 lanes on a shared-memory copy (KMC_CX_GROUPS=0: one thread each, on global memory)
+    int smallSlots = 1;              // replicas per CTA of the fused step (1, or 4 in lockstep for ensembles that fill the device)
     int smallGrid = 0; int *smallQueue = nullptr;      // fused step: CTAs resident at once; ticket queue (1 + R ints) for ensembles larger than that
     bool fused = false;              // small replicas: the whole step is ONE kernel, one CTA per replica, many steps per launch (csrc/kmc_small.cu)
     // in-flight monitoring of long kmc_step calls: every MON_EVERY steps the device scalars are copied to pinned host memory
@@ -316,13 +317,20 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     // systems that fit a CTA's shared-memory records take the fused step (KMC_FUSED=0, or an explicit KMC_RESOLVE, keeps the general path)
     h->fused = K.NA + K.NB <= SMALL_MAXN && K.NB <= SMALL_MAXNB && std::max(p->box[0], p->box[1]) <= 2.0e5 &&
                !(getenv("KMC_FUSED") && atoi(getenv("KMC_FUSED")) == 0) && !getenv("KMC_RESOLVE");
-    if (h->fused) {          // (poses and bond table of a replica live in the shared memory of its CTA)
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, k_small_step) != cudaSuccess || fa.sharedSizeBytes + small_dyn_bytes(K.NA, K.NB) > (size_t)prop.sharedMemPerBlockOptin ||
-            cudaFuncSetAttribute(k_small_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_dyn_bytes(K.NA, K.NB)) != cudaSuccess) { h->fused = false; cudaGetLastError(); }
-        int per = 0;
-        if (h->fused && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_small_step, SMALL_T, small_dyn_bytes(K.NA, K.NB)) != cudaSuccess || per < 1)) { h->fused = false; cudaGetLastError(); }
-        h->smallGrid = per * h->nSM;
+    if (h->fused) {          // (poses, bond table, lists and views of a replica live in the shared memory of its CTA)
+        const size_t per = sizeof(SmallShared) + small_dyn_bytes(K.NA, K.NB);
+        int occ1 = 0, occ4 = 0;
+        bool ok1 = per <= (size_t)prop.sharedMemPerBlockOptin && cudaFuncSetAttribute(k_small_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per) == cudaSuccess &&
+                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_small_step<1>, SMALL_T, per) == cudaSuccess && occ1 >= 1;
+        bool ok4 = ok1 && 4 * per + 64 <= (size_t)prop.sharedMemPerBlockOptin && cudaFuncSetAttribute(k_small_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per)) == cudaSuccess &&
+                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_small_step<4>, 4 * SMALL_T, 4 * per) == cudaSuccess && occ4 >= 1;
+        cudaGetLastError();
+        if (!ok1) h->fused = false;
+        h->smallGrid = occ1 * h->nSM;
+        // ensembles that fill the device: four replicas per CTA in lockstep (one CTA per SM), see k_small_step
+        h->smallSlots = (ok4 && K.R >= 4 * occ4 * h->nSM) ? 4 : 1;
+        if (const char *o = getenv("KMC_SMALL_SLOTS")) { const int v = atoi(o); if (v == 1 || (v == 4 && ok4)) h->smallSlots = v; }
+        if (h->smallSlots == 4) h->smallGrid = occ4 * h->nSM;
         if (const char *o = getenv("KMC_SMALL_GRID")) h->smallGrid = std::max(1, atoi(o));          // (tests: force the ticket path on a small ensemble)
         if (h->fused && dalloc(h, &h->smallQueue, (size_t)K.R + 1) != cudaSuccess) return fail(KMC_ERR_CUDA, "device allocation failed");
     }
@@ -724,10 +732,14 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
             const int chunk = (int)std::min<int64_t>(left, 8192);
             Args A{h->D, h->K};
             A.K.phase = 2;
-            if (h->R > h->smallGrid) {          // more replicas than resident CTAs: persistent grid, replicas dealt in chunks of 64 steps
-                CK(cudaMemsetAsync(h->smallQueue, 0, sizeof(int) * (size_t)(1 + h->R), st));
-                LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->smallGrid, SMALL_T, small_dyn_bytes(h->NA, h->NB), st>>>(A, (unsigned long long)h->step_done, chunk, 64, h->smallQueue)));
-            } else LAUNCH(KID_SMALL_STEP, (k_small_step<<<h->R, SMALL_T, small_dyn_bytes(h->NA, h->NB), st>>>(A, (unsigned long long)h->step_done, chunk, chunk, nullptr)));
+            const int slots = h->smallSlots, groups = (h->R + slots - 1) / slots;
+            const size_t dyn = slots * (sizeof(SmallShared) + small_dyn_bytes(h->NA, h->NB));
+            const bool tickets = groups > h->smallGrid;          // more replica groups than resident CTAs: persistent grid, groups dealt in chunks of 64 steps
+            if (tickets) CK(cudaMemsetAsync(h->smallQueue, 0, sizeof(int) * (size_t)(1 + groups), st));
+            const int grid = tickets ? h->smallGrid : groups, ch = tickets ? 64 : chunk;
+            int *q = tickets ? h->smallQueue : nullptr;
+            if (slots == 4) LAUNCH(KID_SMALL_STEP, (k_small_step<4><<<grid, 4 * SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
+            else LAUNCH(KID_SMALL_STEP, (k_small_step<1><<<grid, SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
             if (chunk & 1) { swap_buffers(h->D); h->parity ^= 1; }
             h->step_done += chunk; h->passes += chunk; h->sinceMon += chunk; left -= chunk;
             h->stepped = true;

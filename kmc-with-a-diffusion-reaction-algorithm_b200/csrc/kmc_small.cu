@@ -47,19 +47,22 @@ struct SmallShared {
     int cxList[SMALL_MAXNB];            // root ligands of the complexes with more than one member | bit 30: several ligands
     unsigned list[SMALL_LIST];          // the pair list: (local index a << 16) | local index b
     unsigned items[SMALL_ITEMS];        // this step's classification work: (probe << 16) | neighbour, both directions of every pair within reach
-    int ncx, nlist, listValid, nitems;
+    int ncx, nlist, listValid, nitems, building;
 };
 
 // dynamic shared memory of k_small_step for replicas of NA receptors + NB ligands
-static inline size_t small_dyn_bytes(int NA, int NB) { return (size_t)NA * 96 + (size_t)NB * 384 + (size_t)(2 * ((NA + 11) & ~3) + NA + 3 * NB) * 4 + 16; }
+__host__ __device__ inline size_t small_dyn_bytes(int NA, int NB) { return ((size_t)NA * 96 + (size_t)NB * 384 + (size_t)(2 * ((NA + 11) & ~3) + NA + 3 * NB) * 4 + 31) & ~(size_t)15; }
+// ... of a CTA that holds `slots` replicas (the per-replica lists and views are carved from dynamic shared memory as well)
+
 
 KD int small_gid(const Consts &K, int rep, int m) { return m < K.NA ? rep * K.NA + m : K.NAt + rep * K.NB + (m - K.NA); }
 
 // S1 for one replica (main.cpp:514-562): union-find over its bond graph, unit heads, sizes, breadth-first member rows; the member
 // rows of replica r live in members[r*N, (r+1)*N)
-KD void small_rebuild(SmallShared &sm, const Args &V, int rep) {
+// (todo = false: a slot of a multi-replica CTA that has nothing to re-derive only keeps the CTA's barriers company)
+KD void small_rebuild(SmallShared &sm, const Args &V, int rep, int tid, bool todo) {
     const Dev &D = V.D; const Consts &K = V.K;
-    const int N = K.NA + K.NB, tid = threadIdx.x;
+    const int N = todo ? K.NA + K.NB : 0, NA_ = todo ? K.NA : 0, NB_ = todo ? K.NB : 0;
     for (int m = tid; m < N; m += SMALL_T) {
         const int gid = small_gid(K, rep, m);
         const int uid = gid < K.NAt ? K.NBt + gid : gid - K.NAt;
@@ -67,9 +70,9 @@ KD void small_rebuild(SmallShared &sm, const Args &V, int rep) {
         if (gid >= K.NAt) { D.cxSize[gid - K.NAt] = 0; D.cxOff[gid - K.NAt] = -1; }
     }
     __syncthreads();                    // (every thread has read the touch counters that sent it here)
-    if (tid == 0) { sm.scal[S_MEMBER_CURSOR] = rep * N; sm.ncx = 0; sm.scal[S_NTOUCH] = 0; sm.scal[S_TOPO_DIRTY] = 0; }
+    if (tid == 0 && todo) { sm.scal[S_MEMBER_CURSOR] = rep * N; sm.ncx = 0; sm.scal[S_NTOUCH] = 0; sm.scal[S_TOPO_DIRTY] = 0; }
     __syncthreads();
-    for (int m = tid; m < K.NA; m += SMALL_T) {
+    for (int m = tid; m < NA_; m += SMALL_T) {
         const int a = rep * K.NA + m, ua = K.NBt + a;
         const int l = D.recLig[a];
         if (l >= 0) uf_union(D.ufParent, ua, l);
@@ -87,7 +90,7 @@ KD void small_rebuild(SmallShared &sm, const Args &V, int rep) {
         if (r < K.NBt) atomicAdd(&D.cxSize[r], 1);
     }
     __syncthreads();
-    for (int b = tid; b < K.NB; b += SMALL_T) {
+    for (int b = tid; b < NB_; b += SMALL_T) {
         const int h = rep * K.NB + b;
         sm.search.ligFree[b] = D.unitOf[K.NAt + h] == K.NAt + h && D.cxSize[h] <= 1;
         if (D.unitOf[K.NAt + h] != K.NAt + h) continue;
@@ -149,33 +152,45 @@ KD bool small_in_reach(const SmallSearch &S, int a, int b) {
     return ex * ex + ey * ey <= r * r;
 }
 
-// queue == nullptr: CTA b advances replica b by nsteps. Otherwise (more replicas than CTAs fit on the device at once) the grid is
-// persistent and the work is dealt in tickets: ticket t = chunk t / R of replica t % R (chunk = an even number of steps); a CTA
-// that takes a ticket waits until the replica's previous chunk has been published (queue[1 + replica] counts its finished chunks;
-// that chunk's ticket was drawn earlier by a CTA that is running, so the wait always ends), loads the replica, advances it and
-// writes it back. Every SM stays busy to the end whatever R modulo the number of resident CTAs is.
-__global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps, int chunk, int *queue) {
-    __shared__ SmallShared sm;
+// SLOTS replicas per CTA, SMALL_T threads each (slot = threadIdx.x / SMALL_T). SLOTS = 1: one replica per CTA, up to four CTAs per
+// SM, each in its own stage of the step. SLOTS = 4: the four replicas an SM can hold advance in LOCKSTEP -- the barriers between
+// the stages are CTA wide --, so all warps of the SM run the same stage and share its instruction lines (the kernel is bound by
+// its instruction-cache footprint); used for ensembles that fill the device.
+// queue == nullptr: CTA b advances replicas [b SLOTS, (b+1) SLOTS) by nsteps. Otherwise (more replicas than the device holds at
+// once) the grid is persistent and the work is dealt in tickets: ticket t = chunk t / G of replica group t % G (chunk = an even
+// number of steps); a CTA that takes a ticket waits until the group's previous chunk has been published (queue[1 + group] counts
+// its finished chunks; that chunk's ticket was drawn earlier by a CTA that is running, so the wait always ends), loads the
+// replicas, advances them and writes them back. Every SM stays busy to the end whatever G modulo the resident CTAs is.
+template <int SLOTS>
+__global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps, int chunk, int *queue) {
     __shared__ int s_ticket;
     extern __shared__ __align__(16) unsigned char small_dyn[];
-    const int tid = threadIdx.x;
-    const int NA = A.K.NA, NB = A.K.NB, N = NA + NB, R = A.K.R;
+    // (the slots' thread numbering is rotated by one warp per slot: stages with a handful of work items run on "warp 0" of every
+    // slot, and in lockstep those would otherwise be the CTA's warps 0, 4, 8, 12 -- all on the same warp scheduler)
+    const int slot = threadIdx.x / SMALL_T, tid = (threadIdx.x + 32 * slot) & (SMALL_T - 1);
+    const int NA = A.K.NA, NB = A.K.NB, N = NA + NB, R = A.K.R, G = (R + SLOTS - 1) / SLOTS;
+    SmallShared *const SM = reinterpret_cast<SmallShared *>(small_dyn);          // [SLOTS], then the slots' pose / bond regions
+    SmallShared &sm = SM[slot];
+    unsigned char *const myDyn = small_dyn + (size_t)SLOTS * sizeof(SmallShared) + (size_t)slot * small_dyn_bytes(NA, NB);
   for (;;) {
-    int rep = blockIdx.x, s0 = 0, s1 = nsteps, myChunk = 0;
+    int group = blockIdx.x, s0 = 0, s1 = nsteps, myChunk = 0;
     if (queue) {
         __syncthreads();                 // (the last ticket's shared state is no longer in use)
-        if (tid == 0) s_ticket = atomicAdd(&queue[0], 1);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&queue[0], 1);
         __syncthreads();
         const int ticket = s_ticket, nchunks = (nsteps + chunk - 1) / chunk;
-        if (ticket >= R * nchunks) break;
-        rep = ticket % R; myChunk = ticket / R;
+        if (ticket >= G * nchunks) break;
+        group = ticket % G; myChunk = ticket / G;
         s0 = myChunk * chunk; s1 = min(nsteps, s0 + chunk);
-        if (tid == 0) while (((volatile int *)queue)[1 + rep] < myChunk) __nanosleep(100);
+        if (threadIdx.x == 0) while (((volatile int *)queue)[1 + group] < myChunk) __nanosleep(100);
         __syncthreads();
         __threadfence();
     }
+    const int rep = group * SLOTS + slot;
+    const bool active = rep < R;         // (the last group of an ensemble may be short: its spare slots only keep the barriers company)
+    const int NAa = active ? NA : 0, NBa = active ? NB : 0;
     // resident state of the replica: poses (committed + new buffer) and bond table
-    double2 *const sRecC = reinterpret_cast<double2 *>(small_dyn), *const sRecS2 = sRecC + 2 * NA, *const sRecS3 = sRecS2 + 2 * NA;
+    double2 *const sRecC = reinterpret_cast<double2 *>(myDyn), *const sRecS2 = sRecC + 2 * NA, *const sRecS3 = sRecS2 + 2 * NA;
     double *const sLig = reinterpret_cast<double *>(sRecS3 + 2 * NA);
     int *const sBond = reinterpret_cast<int *>(sLig + 2 * (size_t)NB * 24);
     // (finish_body reads the bond words of four consecutive receptors as one 16-byte load at GLOBAL indices that are multiples
@@ -184,45 +199,49 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
     int *const sRecLig = sBond + 4 + ph, *const sRecCis = sBond + NA8 + 4 + ph, *const sRecSite = sBond + 2 * NA8, *const sLigRec = sRecSite + NA;
     for (int i = tid; i < 2 * NA8; i += SMALL_T) sBond[i] = -1;
     __syncthreads();
-    for (int i = tid; i < NA; i += SMALL_T) {
+    for (int i = tid; i < NAa; i += SMALL_T) {
         const int a = rep * NA + i;
         // (__ldcg: past the L1 -- the replica's previous chunk may have been written by another SM)
         sRecC[i] = __ldcg(&A.D.recC[a]); sRecS2[i] = __ldcg(&A.D.recS2[a]); sRecS3[i] = __ldcg(&A.D.recS3[a]);
         sRecLig[i] = __ldcg(&A.D.recLig[a]); sRecCis[i] = __ldcg(&A.D.recCis[a]); sRecSite[i] = __ldcg(&A.D.recSite[a]);
     }
-    for (int i = tid; i < NB * 12; i += SMALL_T) reinterpret_cast<double2 *>(sLig)[i] = __ldcg(reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24) + i);
-    for (int i = tid; i < NB * 3; i += SMALL_T) sLigRec[i] = __ldcg(&A.D.ligRec[(size_t)rep * NB * 3 + i]);
+    for (int i = tid; i < NBa * 12; i += SMALL_T) reinterpret_cast<double2 *>(sLig)[i] = __ldcg(reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24) + i);
+    for (int i = tid; i < NBa * 3; i += SMALL_T) sLigRec[i] = __ldcg(&A.D.ligRec[(size_t)rep * NB * 3 + i]);
     if (tid == 0) {
         // the views: this replica's slices of the work lists; scalars, search records, poses and bonds in shared memory
+        const int repv = active ? rep : 0;          // (a spare slot gets a well-formed view of replica 0 that it never uses)
         sm.view[0] = A;
         Dev &V = sm.view[0].D;
         V.scal = sm.scal; V.step64 = &sm.step64; V.touchList = sm.touch; V.reactList = nullptr; V.small = &sm.search; V.pairsFast = sm.fastPairs; V.pairFastCap = TOUCH_CAP / 2;
         const int pendPer = A.D.pendCap / R, pairPer = A.D.pairCap / R, candPer = A.D.candCap / R;
-        V.pendList = A.D.pendList + (size_t)rep * pendPer; V.pendCap = pendPer;
-        V.pairs = A.D.pairs + (size_t)rep * pairPer; V.pairCap = pairPer;
-        V.candRL = A.D.candRL + (size_t)rep * 2 * candPer; V.candCis = A.D.candCis + (size_t)rep * 2 * candPer; V.candCap = candPer;
-        V.rejList = A.D.rejList + (size_t)rep * N; V.rejPartner = A.D.rejPartner + (size_t)rep * N;
-        const ptrdiff_t a0 = (ptrdiff_t)rep * NA, b0 = (ptrdiff_t)rep * NB;
+        V.pendList = A.D.pendList + (size_t)repv * pendPer; V.pendCap = pendPer;
+        V.pairs = A.D.pairs + (size_t)repv * pairPer; V.pairCap = pairPer;
+        V.candRL = A.D.candRL + (size_t)repv * 2 * candPer; V.candCis = A.D.candCis + (size_t)repv * 2 * candPer; V.candCap = candPer;
+        V.rejList = A.D.rejList + (size_t)repv * N; V.rejPartner = A.D.rejPartner + (size_t)repv * N;
+        const ptrdiff_t a0 = (ptrdiff_t)repv * NA, b0 = (ptrdiff_t)repv * NB;
         V.recC = sRecC - a0; V.recCn = sRecC + NA - a0; V.recS2 = sRecS2 - a0; V.recS2n = sRecS2 + NA - a0; V.recS3 = sRecS3 - a0; V.recS3n = sRecS3 + NA - a0;
         V.lig = sLig - b0 * 24; V.lign = sLig + (ptrdiff_t)NB * 24 - b0 * 24;
         V.recLig = sRecLig - a0; V.recCis = sRecCis - a0; V.recSite = sRecSite - a0; V.ligRec = sLigRec - b0 * 3;
-        sm.view[0].K.smallRep = rep;
+        sm.view[0].K.smallRep = repv;
         sm.view[1] = sm.view[0];
         Dev &W = sm.view[1].D;           // S4 (main.cpp:2164-2202) is a pointer swap: odd steps of the launch see the buffers exchanged
         W.recC = V.recCn; W.recCn = V.recC; W.recS2 = V.recS2n; W.recS2n = V.recS2; W.recS3 = V.recS3n; W.recS3n = V.recS3; W.lig = V.lign; W.lign = V.lig;
         for (int i = 0; i < S_COUNT; i++) sm.scal[i] = 0;
         sm.scal[S_NA_LIVE] = A.K.NAt; sm.scal[S_NB_LIVE] = A.K.NBt;
-        sm.scal[S_TOPO_DIRTY] = 1;       // the complex tables are re-derived at the start of every launch
-        sm.search.recBase = rep * NA; sm.search.ligBase = A.K.NAt + rep * NB - NA; sm.search.N = N; sm.search.dmax = SMALL_DMAX; sm.search.nspec = 0;
+        sm.scal[S_TOPO_DIRTY] = active;  // the complex tables are re-derived at the start of every launch
+        sm.search.recBase = repv * NA; sm.search.ligBase = A.K.NAt + repv * NB - NA; sm.search.N = N; sm.search.dmax = SMALL_DMAX; sm.search.nspec = 0;
         sm.search.share[0] = search_share(A.K, false); sm.search.share[1] = search_share(A.K, true);
-        sm.listValid = 0; sm.nlist = 0;
+        sm.listValid = active ? 0 : 1; sm.nlist = 0; sm.ncx = 0; sm.nitems = 0;
     }
     for (int m = tid; m < N; m += SMALL_T) sm.search.ref[m] = make_float2(0.f, 0.f);
     __syncthreads();
     SmallSearch &S = sm.search;
+    // a condition of one slot that guards a stage with barriers inside becomes a condition of the CTA (the barrier of
+    // __syncthreads_or is spared when the CTA holds one replica)
+    auto any_slot = [&](bool mine) -> bool { return SLOTS == 1 ? mine : (__syncthreads_or(mine) != 0); };
 #ifdef SMALL_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define SMALL_TICK(i) do { if (tid == 0) { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
+#define SMALL_TICK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
 #else
 #define SMALL_TICK(i) do {} while (0)
 #endif
@@ -231,7 +250,10 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         const Dev &D = V.D; const Consts &K = V.K;
         const uint64_t step = step0 + (uint64_t)s + 1;
         // ---- S1: only when the last step's reactions touched the bond table (or at the start of a launch) ----
-        if (sm.scal[S_NTOUCH] > 0 || sm.scal[S_TOPO_DIRTY]) small_rebuild(sm, V, rep);
+        {
+            const bool dirty = active && (sm.scal[S_NTOUCH] > 0 || sm.scal[S_TOPO_DIRTY]);
+            if (any_slot(dirty)) small_rebuild(sm, V, rep, tid, dirty);
+        }
         if (tid == 0) {                  // (nothing below reads these before the next barrier; nobody still reads the last step's values: barrier at its end)
             sm.step64 = step;
             sm.scal[S_NPEND] = 0; sm.scal[S_NPAIR] = 0; sm.scal[S_NCAND_RL] = 0; sm.scal[S_NCAND_CIS] = 0; sm.scal[S_NREJ] = 0;
@@ -240,7 +262,7 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         SMALL_TICK(0);
         // ---- S2 proposals: every molecule is proposed by exactly one thread (a unit head, or the thread of its complex) ----
         // (work index: receptors, ligands from the next multiple of 32 on -- a warp runs ONE of the code paths --, then the complexes)
-        {
+        if (active) {
             const int NAp = (NA + 31) & ~31, NBp = (NB + 31) & ~31, nw = NAp + NBp + sm.ncx;
             for (int w = tid; w < nw; w += SMALL_T) {
                 if (w < NAp) {
@@ -258,42 +280,71 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         // by the list while all its poses lie within dmax of its centre at build time (ref): listed are all pairs with
         // |ref_a - ref_b| <= share(a) + share(b) + 2 dmax ----
         bool useList = true;
-        if (!sm.listValid || S.nspec > SMALL_SPEC_MAX) {
-            __syncthreads();             // (everyone has read nspec)
-            if (tid == 0) { S.nspec = 0; sm.nlist = 0; sm.listValid = 1; }
+        {
+            const bool build = active && (!sm.listValid || S.nspec > SMALL_SPEC_MAX);
+            if (SLOTS > 1 && tid == 0) sm.building = build;
+            if (any_slot(build)) {
+                if (SLOTS == 1) __syncthreads();             // (everyone has read nspec; any_slot was that barrier otherwise)
+                if (tid == 0 && build) { S.nspec = 0; sm.nlist = 0; sm.listValid = 1; }
 #ifdef SMALL_TIMING
-            if (tid == 0) tacc[7] += 1;
+                if (threadIdx.x == 0) tacc[7] += 1;
 #endif
-            __syncthreads();
-            const int half = N / 2;
-            for (int m = tid; m < N; m += SMALL_T) {
-                const float4 me = S.cen[m];
-                S.ref[m] = make_float2(me.x, me.y);
-                const bool special = me.w > S.dmax;          // (this step's own move is already too long: periodic wrap, alignment snap)
-                S.isSpec[m] = special;
-                if (special) { const int i = atomicAdd(&S.nspec, 1); if (i < SMALL_SPEC) S.spec[i] = m; }
-                const float rm = me.z - me.w + 2.f * S.dmax + 0.0625f;          // the share alone (+ margins), plus both allowances
-                const int dmax_ = (2 * half == N && m >= half) ? half - 1 : half;      // even N: the pair (m, m + N/2) is listed by its lower member
-                int j = m;
+                __syncthreads();
+                // the scans of the replicas that rebuild (usually one of the CTA's) are spread over ALL threads of the CTA: a task
+                // is a quarter of one molecule's cyclic scan range (at most 32 neighbours); hits are collected in a bit mask so
+                // that the scan itself is a loop without side effects (the loads of several iterations are in flight together)
+                for (int k = 0; k < SLOTS; k++) {
+                    if (SLOTS > 1 ? !SM[k].building : !build) continue;
+                    SmallShared &B = SM[k]; SmallSearch &Sk = B.search;
+                    const int half = N / 2, len = (half + 3) / 4;
+                    for (int task = threadIdx.x; task < 4 * N; task += SMALL_T * SLOTS) {
+                        const int m = task >> 2, q = task & 3;
+                        const float4 me = Sk.cen[m];
+                        if (q == 0) {
+                            Sk.ref[m] = make_float2(me.x, me.y);
+                            const bool special = me.w > Sk.dmax;          // (this step's own move is already too long: periodic wrap, alignment snap)
+                            Sk.isSpec[m] = special;
+                            if (special) { const int i = atomicAdd(&Sk.nspec, 1); if (i < SMALL_SPEC) Sk.spec[i] = m; }
+                        }
+                        const float rm = me.z - me.w + 2.f * Sk.dmax + 0.0625f;          // the share alone (+ margins), plus both allowances
+                        const int dmax_ = (2 * half == N && m >= half) ? half - 1 : half;      // even N: the pair (m, m + N/2) is listed by its lower member
+                        const int dlo = 1 + q * len, cnt = min(dmax_, dlo + len - 1) - dlo + 1;          // neighbours m + dlo ... (cyclic), cnt <= 32
+                        if (cnt <= 0) continue;
+                        int a0 = m + dlo; if (a0 >= N) a0 -= N;
+                        const int n1 = min(cnt, N - a0);
+                        unsigned mask = 0;
 #pragma unroll 4
-                for (int d = 1; d <= dmax_; d++) {
-                    j = j + 1 == N ? 0 : j + 1;
-                    const float4 o = S.cen[j];
-                    const float ex = o.x - me.x, ey = o.y - me.y, r = rm + (o.z - o.w);
-                    if (ex * ex + ey * ey <= r * r) {
-                        const int slot = atomicAdd(&sm.nlist, 1);
-                        if (slot < SMALL_LIST) sm.list[slot] = ((unsigned)m << 16) | (unsigned)j;
+                        for (int i = 0; i < n1; i++) {
+                            const float4 o = Sk.cen[a0 + i];
+                            const float ex = o.x - me.x, ey = o.y - me.y, r = rm + (o.z - o.w);
+                            mask |= (ex * ex + ey * ey <= r * r ? 1u : 0u) << i;
+                        }
+#pragma unroll 4
+                        for (int i = n1; i < cnt; i++) {
+                            const float4 o = Sk.cen[i - n1];
+                            const float ex = o.x - me.x, ey = o.y - me.y, r = rm + (o.z - o.w);
+                            mask |= (ex * ex + ey * ey <= r * r ? 1u : 0u) << i;
+                        }
+                        while (mask) {
+                            const int i = __ffs(mask) - 1; mask &= mask - 1;
+                            int j = a0 + i; if (j >= N) j -= N;
+                            const int slot_ = atomicAdd(&B.nlist, 1);
+                            if (slot_ < SMALL_LIST) B.list[slot_] = ((unsigned)m << 16) | (unsigned)j;
+                        }
                     }
                 }
+                __syncthreads();
+                if (build) {
+                    useList = sm.nlist <= SMALL_LIST && S.nspec <= SMALL_SPEC;      // else too crowded for the list: every pair, in place (and the next step tries again)
+                    if (tid == 0) sm.listValid = useList;                           // (read again only after the next barrier)
+                }
             }
-            __syncthreads();
-            useList = sm.nlist <= SMALL_LIST && S.nspec <= SMALL_SPEC;      // else too crowded for the list: every pair, in place (and the next step tries again)
-            if (tid == 0) sm.listValid = useList;                           // (read again only after the next barrier)
         }
         SMALL_TICK(2);
         // ---- S2g: list pairs (both members inside their allowance) + every pair of a special molecule: those within reach this
         // step are queued, then classified exactly by a dense pass (one directed pair per thread) ----
-        if (!useList) {                  // (a replica too crowded for the list: every pair)
+        if (!active) {}
+        else if (!useList) {                  // (a replica too crowded for the list: every pair)
             for (int m = tid; m < N; m += SMALL_T)
                 for (int j = m + 1; j < N; j++) if (small_in_reach(S, m, j)) small_queue_pair(V, sm, rep, m, j);
         } else {
@@ -317,21 +368,29 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         }
         __syncthreads();
         SMALL_TICK(3);
-        // ---- the order dependence of the sweep, from the pending findings ----
-        if (sm.scal[S_NPEND] > 0) pend_resolve_block(D, min(sm.scal[S_NPEND], D.pendCap));
+        // ---- the order dependence of the sweep, from the pending findings (the whole CTA settles one replica after the other) ----
+        for (int k = 0; k < SLOTS; k++) {
+            const int np = SM[k].scal[S_NPEND];
+            if (np > 0) { const Dev &Dk = SM[k].view[s & 1].D; pend_resolve_block(Dk, min(np, Dk.pendCap)); }
+        }
         // ---- S3 ----
-        react_pairs_body<true>(K, D, tid, SMALL_T);
+        if (active) react_pairs_body<true>(K, D, tid, SMALL_T);
         __syncthreads();
         SMALL_TICK(4);
-        if (sm.scal[S_NCAND_RL] | sm.scal[S_NCAND_CIS]) { react_resolve_block(D); __syncthreads(); }
+        {
+            bool any = false;
+            for (int k = 0; k < SLOTS; k++)
+                if (SM[k].scal[S_NCAND_RL] | SM[k].scal[S_NCAND_CIS]) { react_resolve_block(SM[k].view[s & 1].D); any = true; }
+            if (any) __syncthreads();
+        }
         SMALL_TICK(5);
         if (tid == 0) S.nspec = 0;          // (the special molecules of the NEXT step register during its proposals)
-        finish_body<true>(K, D, tid, SMALL_T, rep * NA, (rep + 1) * NA);
+        if (active) finish_body<true>(K, D, tid, SMALL_T, rep * NA, (rep + 1) * NA);
         __syncthreads();
         SMALL_TICK(6);
     }
 #ifdef SMALL_TIMING
-    if (tid == 0 && rep == 0 && nsteps >= 1000)          // (diagnostic build only) cycles per step: S1 | proposals | list | classify | pending + S3 pairs | S3 resolve | finish
+    if (threadIdx.x == 0 && rep == 0 && nsteps >= 1000)          // (diagnostic build only) cycles per step: S1 | proposals | list | classify | pending + S3 pairs | S3 resolve | finish
         printf("k_small_step cycles/step: %lld %lld %lld %lld %lld %lld %lld; %lld list rebuilds in %d steps, last list %d pairs\n", tacc[0] / nsteps, tacc[1] / nsteps, tacc[2] / nsteps, tacc[3] / nsteps, tacc[4] / nsteps, tacc[5] / nsteps, tacc[6] / nsteps, tacc[7], nsteps, sm.nlist);
 #endif
     // the committed state goes back to the global arrays: into the buffers the host regards as committed after this launch
@@ -340,13 +399,13 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
         const int cb = (s1 - s0) & 1;          // (odd only in the last chunk of an odd launch)
         double2 *gC = cb ? A.D.recCn : A.D.recC, *gS2 = cb ? A.D.recS2n : A.D.recS2, *gS3 = cb ? A.D.recS3n : A.D.recS3;
         double *gL = cb ? A.D.lign : A.D.lig;
-        for (int i = tid; i < NA; i += SMALL_T) {
+        for (int i = tid; i < NAa; i += SMALL_T) {
             const int a = rep * NA + i;
             gC[a] = sRecC[cb * NA + i]; gS2[a] = sRecS2[cb * NA + i]; gS3[a] = sRecS3[cb * NA + i];
             A.D.recLig[a] = sRecLig[i]; A.D.recCis[a] = sRecCis[i]; A.D.recSite[a] = sRecSite[i];
         }
-        for (int i = tid; i < NB * 12; i += SMALL_T) reinterpret_cast<double2 *>(gL + (size_t)rep * NB * 24)[i] = reinterpret_cast<const double2 *>(sLig + (size_t)cb * NB * 24)[i];
-        for (int i = tid; i < NB * 3; i += SMALL_T) A.D.ligRec[(size_t)rep * NB * 3 + i] = sLigRec[i];
+        for (int i = tid; i < NBa * 12; i += SMALL_T) reinterpret_cast<double2 *>(gL + (size_t)rep * NB * 24)[i] = reinterpret_cast<const double2 *>(sLig + (size_t)cb * NB * 24)[i];
+        for (int i = tid; i < NBa * 3; i += SMALL_T) A.D.ligRec[(size_t)rep * NB * 3 + i] = sLigRec[i];
     }
     if (tid == 0) {
         if (sm.scal[S_OVERFLOW]) atomicOr(&A.D.scal[S_OVERFLOW], sm.scal[S_OVERFLOW]);
@@ -355,7 +414,7 @@ __global__ void __launch_bounds__(SMALL_T, SMALL_MINB) k_small_step(const __grid
     if (!queue) break;
     __threadfence();                     // this chunk's state is out before the replica's next chunk may start
     __syncthreads();
-    if (tid == 0) atomicExch(&queue[1 + rep], myChunk + 1);
+    if (threadIdx.x == 0) atomicExch(&queue[1 + group], myChunk + 1);
   }
 }
 

@@ -78,6 +78,22 @@ def test_fused_ticket_queue_for_large_ensembles(monkeypatch):
     assert fused.series(3)["bond_num"] > 0 and fused.series(0)["step"] == 5 + 64 + 333 + 1 + 1000 + 129
 
 
+@pytest.mark.parametrize("grid", [None, "1"])
+def test_fused_four_replicas_per_cta_in_lockstep(monkeypatch, grid):
+    """Ensembles that fill the device advance four replicas per CTA in lockstep (k_small_step<4>). Forced here on 7 replicas: two
+    groups, the second one with a spare slot; with a grid of one CTA the groups go through the ticket queue as well."""
+    monkeypatch.setenv("KMC_SMALL_SLOTS", "4")
+    if grid: monkeypatch.setenv("KMC_SMALL_GRID", grid)
+    fused, general = _pair_of_paths(monkeypatch, lambda: apply_regime(kmc_b200.default_params(box=(2500.0, 2500.0, 400.0), seed=29, n_replicas=7), "hot"))
+    monkeypatch.delenv("KMC_SMALL_SLOTS"); monkeypatch.delenv("KMC_SMALL_GRID", raising=False)
+    fused.init_random(seed=6)
+    general.set_packed(*fused.get_packed())
+    for chunk in (3, 64, 500, 1, 1200):
+        fused.step(chunk); general.step(chunk)
+        _same(fused, general, 7)
+    assert fused.series(6)["bond_num"] > 0 and fused.events()["reverted"] > 0
+
+
 def test_fused_small_odd_sizes_against_oracle():
     """odd molecule count (the all-pairs schedule differs for odd and even N), more molecules than threads, crowded box"""
     for na, nb, box in ((31, 10, (900.0, 900.0, 300.0)), (170, 71, (3000.0, 3000.0, 400.0))):
