@@ -149,6 +149,11 @@ int kmc_get_accept(kmc_handle *h, int32_t replica, int32_t *accepted);
  * list, [13] special entries (far movers / drifted molecules of a list-reuse step), [14] pending findings, [15] pre-selected
  * reaction pairs */
 int kmc_get_events(kmc_handle *h, int64_t *ev);
+/* Pure host arithmetic (no device): the alignment passes test AreSame(distance, D), i.e. fabs(sqrt(q) - D) < 1e-8 (main.cpp:2368-2371
+ * on the distances of 1205-1215 / 1245-1255), dozens of times per complex. sqrt is correctly rounded and monotone, so the squared
+ * distances q that pass form an interval; the kernels compare q with its two ends instead of taking the root. window[0..1] = that
+ * interval for the length D (ends included); returns 1 if it could not be established (the kernels then take the root). */
+int kmc_alignment_window(double length, double *window);
 /* which implementation of the step the handle uses: 0 = the general multi-kernel path (one CUDA graph per step), 1 = the fused
  * small-system step (csrc/kmc_small.cu: replicas of at most 512 molecules, one CTA per replica, the whole step in one kernel,
  * many steps per launch). Chosen at kmc_create; the two give bit-identical results. KMC_FUSED=0 in the environment forces 0. */

@@ -948,6 +948,12 @@ extern "C" int kmc_get_accept(kmc_handle *h, int32_t rep, int32_t *accepted) {
     return KMC_OK;
 }
 
+extern "C" int kmc_alignment_window(double length, double *window) {
+    if (!window) return KMC_ERR_INVALID;
+    same_window(length, window);
+    return window[0] <= window[1] ? KMC_OK : 1;
+}
+
 extern "C" int kmc_get_step_path(kmc_handle *h) { return h ? (h->fused ? 1 : 0) : KMC_ERR_INVALID; }
 
 extern "C" int kmc_get_live_counts(kmc_handle *h, int32_t *n_rec, int32_t *n_lig) {

@@ -1827,16 +1827,10 @@ KD bool pend_sweep(const Dev &D, int n, int first, int stride) {
 }
 // the fixed point by ONE CTA (short lists: a few hundred findings per step on the 1.25e6-molecule membrane)
 KD void pend_resolve_block(const Dev &D, int n) {
-    __shared__ int changed;
     for (int sweep = 0; sweep <= n; sweep++) {
-        if (threadIdx.x == 0) changed = 0;
-        __syncthreads();
-        if (pend_sweep(D, n, threadIdx.x, blockDim.x)) changed = 1;
+        const bool changed = pend_sweep(D, n, threadIdx.x, blockDim.x);
         __threadfence();
-        __syncthreads();
-        const bool again = changed != 0;
-        __syncthreads();
-        if (!again) break;
+        if (!__syncthreads_or(changed)) break;          // (one barrier per sweep: it also carries the "anything decided?" vote)
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {           // cannot happen: the pending findings always settle
         const int u = D.pendList[i].x;

@@ -37,7 +37,7 @@ class Series(C.Structure):
 
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
-           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_get_step_path", "kmc_write_bond_dat",
+           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_get_step_path", "kmc_alignment_window", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_timeline_print", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_halo_width", "kmc_strip_unique_id",
            "kmc_strip_comm_init", "kmc_strip_refresh", "kmc_strip_refresh_local", "kmc_strip_get_series", "kmc_strip_get_oligomer_hist",
@@ -90,6 +90,7 @@ def lib():
         L.kmc_get_events.argtypes = [vp, vp]
         L.kmc_get_live_counts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.kmc_get_step_path.argtypes = [vp]
+        L.kmc_alignment_window.argtypes = [C.c_double, C.POINTER(C.c_double)]
         L.kmc_strip_configure.argtypes = [vp, i32, i32, C.c_double]
         L.kmc_strip_load_global.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64]
         L.kmc_strip_begin_refresh.argtypes = [vp]
@@ -172,6 +173,12 @@ def strip_refresh_local(handles, refresh_every=0):
     rc = lib().kmc_strip_refresh_local(arr, len(handles), refresh_every)
     if rc < 0:
         raise KmcError("kmc_strip_refresh_local failed (%d): %s" % (rc, "; ".join(lib().kmc_last_error(k.h).decode() for k in handles)))
+
+
+def alignment_window(length):
+    """[lo, hi] of squared distances q with fabs(sqrt(q) - length) < 1e-8 (host arithmetic; None if not available)"""
+    w = (C.c_double * 2)()
+    return (w[0], w[1]) if lib().kmc_alignment_window(length, w) == 0 else None
 
 
 def scaled_box(n_total, z=1000.0):

@@ -124,3 +124,27 @@ def test_every_entry_point_is_documented_in_integration_md():
     families = [m[:-1] for m in re.findall(r"kmc_[a-z_]+\*", doc)]          # e.g. kmc_strip_*, kmc_profile*
     missing = sorted(d for d in declared if d not in doc and not any(d.startswith(f) for f in families))
     assert not missing, missing
+
+
+def test_alignment_windows_equal_the_square_root_test():
+    """The kernels replace AreSame(sqrt(q), D) (main.cpp:2368-2371 on the alignment distances of 1205-1215 / 1245-1255) by a window
+    on the squared distance q. Host arithmetic only: for the four alignment lengths of the default parameters (and a few odd ones)
+    the window must agree with the square-root test on every double within 4096 ulps of either end, and on a coarse sweep beyond."""
+    import numpy as np
+    import kmc_b200
+    p = kmc_b200.default_params()
+    lengths = [p.bond_dist_cut / 2 + p.rA + p.rB, p.bond_dist_cut / 2, p.cis_dist_cut / 2 + p.rA + p.rA, p.cis_dist_cut / 2, 1.0, 0.37, 123.456, 1e4 / 3]
+    for D in lengths:
+        w = kmc_b200.alignment_window(D)
+        assert w is not None and w[0] < D * D < w[1]
+        for edge in w:
+            q = np.full(8193, edge)
+            for i in range(4096):                                   # neighbouring doubles on both sides of the edge
+                q[4095 - i] = np.nextafter(q[4096 - i], 0.0)
+                q[4097 + i] = np.nextafter(q[4096 + i], np.inf)
+            ref = np.abs(np.sqrt(q) - D) < 1.0e-8                    # numpy's float64 sqrt is correctly rounded, like C's and CUDA's
+            got = (q >= w[0]) & (q <= w[1])
+            assert np.array_equal(ref, got), D
+        q = np.linspace(0.0, 4 * D * D, 20001)
+        assert np.array_equal(np.abs(np.sqrt(q) - D) < 1.0e-8, (q >= w[0]) & (q <= w[1]))
+    assert kmc_b200.alignment_window(0.0) is None                    # degenerate length: the kernels keep the square root
