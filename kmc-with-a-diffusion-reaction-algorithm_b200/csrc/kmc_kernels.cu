@@ -328,11 +328,12 @@ KD void propose_rec_body(const Args &A) {
     const unsigned stamp = (unsigned)D.scal[S_EPOCH];
     const int nLive = nA_live(D);
     const int ntiles = (nLive + REC_TILE - 1) / REC_TILE;          // (live receptors only: a strip's capacity padding costs nothing)
-    // Tiles are handed out dynamically (the first one is the CTA's own index, the following ones come from a ticket counter that
-    // k_step_begin resets): a CTA that becomes resident late -- the complex kernels of the side branches share the SMs -- simply
-    // takes fewer tiles, where a static stride would leave its share of the tiles for the very end of the kernel.
+    // RECDYN = 1 hands the tiles out dynamically (the first one is the CTA's own index, the following ones come from a ticket
+    // counter that k_step_begin resets), so that a CTA that becomes resident late -- the complex kernels of the side branches share
+    // the SMs -- takes fewer tiles. Measured on the membrane bench: no gain in the step (0.1537 vs 0.1550 ms), +1.2 us in the kernel
+    // (two barriers per tile), so the static stride stays the default.
 #ifndef RECDYN
-#define RECDYN 1
+#define RECDYN 0
 #endif
     __shared__ int s_next;
     int tile = blockIdx.x;
