@@ -49,6 +49,7 @@ struct kmc_handle {
     // between reuse them (phase 1); sinceBuild = steps taken since the last rebuild, 0 = the next step must rebuild
     int listEvery = 1, sinceBuild = 0, cellHeadCap = 0;
     bool adapt = true, adapted = false;      // kmc_sync may fall back to a rebuild every step (see there)
+    int adaptLevel = 0; bool adaptSkip = false;      // back-off taken so far (0 none, 1 wide list every 4th step, 2 rebuild every step); ignore the next snapshot
     unsigned epoch = 0;
     cudaGraphExec_t gexec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [phase][buffer parity]
     int parity = 0, launches_per_step[2] = {0, 0};
@@ -229,6 +230,7 @@ static void fill_consts(const kmc_params &P, Consts &K) {
     K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
     K.ncx = (int)ceil((P.box[0] + 2 * edge) / edge); K.ncy = (int)ceil((P.box[1] + 2 * edge) / edge);
     K.cellInv = 1.0 / edge;
+    K.keyX0 = K.gx0; K.keyY0 = K.gy0; K.keyInv = K.cellInv;
     const float maxc = (float)(std::max(P.box[0], P.box[1]) + 2 * edge);
     K.cutMargin = 0.05f + 2 * (nextafterf(maxc, INFINITY) - maxc);
 }
@@ -687,11 +689,39 @@ static int ensure_graphs(kmc_handle *h) {
 // of a rotating complex swing 10-30 A per step) makes every reuse step walk the stale grid once per such molecule; from
 // NT/64 special entries per step on, rebuilding every step is the cheaper exact path; the graphs are captured again with
 // the new constants. KMC_ADAPT=0 disables it.
+// coarser cells for a wider list: the arrays were sized for the finer grid the handle started with
+static void regrid(kmc_handle *h, double edge) {
+    Consts &K = h->K; const kmc_params &P = h->P;
+    if (edge <= 1.0 / K.cellInv) return;
+    K.gx0 = -P.box[0] / 2 - edge; K.gy0 = -P.box[1] / 2 - edge;
+    K.ncx = (int)ceil((P.box[0] + 2 * edge) / edge); K.ncy = (int)ceil((P.box[1] + 2 * edge) / edge);
+    K.cellInv = 1.0 / edge;
+    const float maxc = (float)(std::max(P.box[0], P.box[1]) + 2 * edge);
+    K.cutMargin = 0.05f + 2 * (nextafterf(maxc, INFINITY) - maxc);
+    h->D.ncell = K.R * K.ncx * K.ncy;
+    h->scanBlocks = (h->D.ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;
+}
 static int examine_scalars(kmc_handle *h, const int *scal) {
-    const int nspec = std::max(scal[S_NSPEC], scal[S_NSPEC_MAX]);
-    if (h->listEvery > 1 && h->adapt && nspec > std::max(h->NT / 64, 64)) {
-        h->listEvery = 1; h->sinceBuild = 0; h->adapted = true;
-        h->K.drift = 0; if (!getenv("KMC_SKIN")) h->K.skin = 24.0;
+    const int nspec = h->adaptSkip ? 0 : std::max(scal[S_NSPEC], scal[S_NSPEC_MAX]);
+    h->adaptSkip = false;
+    const int adaptMin = getenv("KMC_ADAPT_MIN") ? atoi(getenv("KMC_ADAPT_MIN")) : 64;          // (tests lower it to meet the back-off on a small system)
+    if (h->listEvery > 1 && h->adapt && nspec > std::max(h->NT / 64, adaptMin)) {
+        // Level 1 (a single membrane, not strips): many molecules outrun a 12 A skin -- members of rotating complexes swing 10-30 A
+        // per step -- but a list built with a 30 A skin and 60 A of drift allowance, rebuilt every 4th step on coarser cells, still
+        // beats rebuilding every step (oligomerised membrane: 0.47 against 0.52 ms per step). Level 2, if even that setting makes
+        // more than NT/64 special entries per step: rebuild every step.
+        const double wide = std::max({h->K.reachLL, h->K.reachOn, h->K.reachCis}) + 2 * 30.0 + 2 * 60.0;          // cut radius of the wide list
+        const double pairsPerMolecule = 0.5 * 3.14159265 * wide * wide * h->NT / ((double)h->K.R * h->K.Lx * h->K.Ly);   // (the list holds 8 per molecule)
+        const bool level1 = h->adaptLevel == 0 && !h->strip_on && pairsPerMolecule <= 3.0 && !getenv("KMC_SKIN") && !getenv("KMC_DRIFT") && !getenv("KMC_REUSE");
+        if (level1) {
+            h->adaptLevel = 1; h->listEvery = 4; h->K.skin = 30.0; h->K.drift = 60.0;
+            regrid(h, std::max({h->K.reachLL, h->K.reachOn, h->K.reachCis}) + 2 * h->K.skin + 2 * h->K.drift + 1.0);
+        } else {
+            h->adaptLevel = 2; h->listEvery = 1;
+            h->K.drift = 0; if (!getenv("KMC_SKIN")) h->K.skin = 24.0;
+        }
+        h->sinceBuild = 0; h->adapted = true; h->adaptSkip = true;          // (a snapshot taken before the switch says nothing about the new setting)
+        cudaMemsetAsync(h->D.scal + S_NSPEC_MAX, 0, sizeof(int), h->stream); cudaMemsetAsync(h->D.scal + S_NSPEC, 0, sizeof(int), h->stream);
         for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) { cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]); h->gexec[p >> 1][p & 1] = nullptr; }
     }
     int ovf = scal[S_OVERFLOW];
@@ -929,7 +959,7 @@ extern "C" int kmc_get_oligomer_hist(kmc_handle *h, int32_t rep, int64_t *hist, 
 
 extern "C" int kmc_get_grid(kmc_handle *h, double *x0, double *y0, double *inv_edge, int32_t *ncx, int32_t *ncy) {
     if (!h) return KMC_ERR_INVALID;
-    if (x0) *x0 = h->K.gx0; if (y0) *y0 = h->K.gy0; if (inv_edge) *inv_edge = h->K.cellInv;
+    if (x0) *x0 = h->K.keyX0; if (y0) *y0 = h->K.keyY0; if (inv_edge) *inv_edge = h->K.keyInv;          // (the cells the production order colours)
     if (ncx) *ncx = h->K.ncx; if (ncy) *ncy = h->K.ncy;
     return KMC_OK;
 }

@@ -49,6 +49,7 @@ struct Consts {
     int smallRep;                             // phase 2: the replica this CTA's view stands for (spares the hot path every division by NA / NB)
     float cutMargin;                          // slack of the fp32 distance cut of k_cells_cut (covers the rounding of coordinates to fp32)
     double gx0, gy0, cellInv; int ncx, ncy;   // neighbour grid
+    double keyX0, keyY0, keyInv;              // the cells whose 2x2 colouring orders the sweep in production mode: the neighbour grid as it was when the handle was set up (the neighbour grid itself may be re-laid later: list-reuse back-off)
     int tileEdge;                             // k_resolve_tiles: cells per tile edge
     int NA, NB, R, mode;                      // per-replica sizes, replicas
     int NAt, NBt, NT;                         // totals (capacities of the receptor / ligand blocks; live counts are device scalars)

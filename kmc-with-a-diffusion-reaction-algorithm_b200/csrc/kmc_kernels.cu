@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_cx_rebuild(const __grid_constant__ Args
 KD bool unit_before(int v, int u) { return (unsigned)v < (unsigned)u; }
 KD int unit_key(const Consts &K, int head, double hx, double hy) {
     if (K.mode == 0) return head;
-    const int cx = (int)floor((hash_x(K, hx) - K.gx0) * K.cellInv), cy = (int)floor((hy - K.gy0) * K.cellInv);
+    const int cx = (int)floor((hash_x(K, hx) - K.keyX0) * K.keyInv), cy = (int)floor((hy - K.keyY0) * K.keyInv);
     return (int)((unsigned)head | ((unsigned)((cx & 1) | ((cy & 1) << 1)) << 30));
 }
 

@@ -140,7 +140,7 @@ extern "C" int kmc_strip_configure(kmc_handle *h, int32_t rank, int32_t nranks, 
     h->strip_on = true; h->strip_W = halo_width; h->strip_lo = -K.Lx / 2 + rank * width; h->strip_hi = h->strip_lo + width;
     if (nranks > 1) {        // the grid only has to cover the strip and its halos (in the periodic frame of the strip)
         const double edge = 1.0 / K.cellInv;
-        K.gx0 = h->strip_lo - halo_width - 2 * edge;
+        K.gx0 = h->strip_lo - halo_width - 2 * edge; K.keyX0 = K.gx0;
         K.ncx = (int)ceil((width + 2 * halo_width + 4 * edge) / edge);
         const int ncell = K.ncx * K.ncy;
         h->scanBlocks = (ncell + 1 + SCAN_TILE - 1) / SCAN_TILE;

@@ -266,6 +266,27 @@ def test_list_reuse_backs_off_when_molecules_outrun_their_entries(golden_dir, mo
     k.close()
 
 
+def test_list_reuse_first_back_off_level_is_exact(golden_dir, monkeypatch):
+    """Without tuning knobs in the environment the first back-off is a WIDER list (30 A skin, 60 A drift allowance, rebuilt every 4th
+    step on coarser cells) rather than a rebuild every step. Met here on the 200-molecule hot state with the trigger lowered; the
+    switch re-lays the neighbour grid in the middle of a run and must not change a bit."""
+    monkeypatch.setenv("KMC_FUSED", "0"); monkeypatch.setenv("KMC_RESOLVE", "cells"); monkeypatch.setenv("KMC_ADAPT_MIN", "2")
+    g = load_golden_state(os.path.join(golden_dir, "hot200_step40000.npz"))
+    o, k = make_pair(150, 50, (4000.0, 4000.0, 400.0), "hot", seed=41)          # (the reference-evolved state in a wider box: the wide list is only taken where it stays short)
+    assert k.path() == "general"
+    o.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    k.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    o.step(15); k.step(15)                         # (a reuse step: builds are steps 1, 7, 13)
+    before = k.events()
+    assert before["special_entries"] > 2
+    k.sync()                                       # the back-off is decided here
+    lockstep(o, k, 400, 1, "adapt-level-1", per_step_accept=True)
+    after = k.events()
+    assert after["list_pairs"] > 1.5 * before["list_pairs"]      # the wide list, not the every-step rebuild (whose steps have no special entries at all)
+    lockstep(o, k, 1600, 100, "adapt-level-1")
+    k.close()
+
+
 def test_full_size_membrane_properties(monkeypatch):
     """BASELINE configs[3] size on one GPU (1e6 molecules, default density), where the oracle is too slow to follow: the
     size-independent properties the domain offers. (a) Exactness of the list reuse at full size: a handle that rebuilds its
