@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
     auto any_slot = [&](bool mine) -> bool { return SLOTS == 1 ? mine : (__syncthreads_or(mine) != 0); };
 #ifdef SMALL_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define SMALL_TICK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
+#define SMALL_TICK(i) do { asm volatile("" ::: "memory"); if (threadIdx.x == 0) { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } asm volatile("" ::: "memory"); } while (0)
 #else
 #define SMALL_TICK(i) do {} while (0)
 #endif
@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
                 if (SLOTS == 1) __syncthreads();             // (everyone has read nspec; any_slot was that barrier otherwise)
                 if (tid == 0 && build) { S.nspec = 0; sm.nlist = 0; sm.listValid = 1; }
 #ifdef SMALL_TIMING
-                if (threadIdx.x == 0) tacc[7] += 1;
 #endif
                 __syncthreads();
                 // the scans of the replicas that rebuild (usually one of the CTA's) are spread over ALL threads of the CTA: a task
@@ -362,6 +361,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
             }
         }
         __syncthreads();
+        SMALL_TICK(7);
         {
             const int ni = min(sm.nitems, SMALL_ITEMS);
             for (int q = tid; q < ni; q += SMALL_T) small_classify(V, rep, (int)(sm.items[q] >> 16), (int)(sm.items[q] & 0xffffu));
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
     }
 #ifdef SMALL_TIMING
     if (threadIdx.x == 0 && rep == 0 && nsteps >= 1000)          // (diagnostic build only) cycles per step: S1 | proposals | list | classify | pending + S3 pairs | S3 resolve | finish
-        printf("k_small_step cycles/step: %lld %lld %lld %lld %lld %lld %lld; %lld list rebuilds in %d steps, last list %d pairs\n", tacc[0] / nsteps, tacc[1] / nsteps, tacc[2] / nsteps, tacc[3] / nsteps, tacc[4] / nsteps, tacc[5] / nsteps, tacc[6] / nsteps, tacc[7], nsteps, sm.nlist);
+        printf("k_small_step cycles/step: S1 %lld | proposals %lld | list %lld | queue %lld | classify %lld | pending + S3 pairs %lld | S3 resolve %lld | finish %lld; last list %d pairs\n", tacc[0] / nsteps, tacc[1] / nsteps, tacc[2] / nsteps, tacc[7] / nsteps, tacc[3] / nsteps, tacc[4] / nsteps, tacc[5] / nsteps, tacc[6] / nsteps, sm.nlist);
 #endif
     // the committed state goes back to the global arrays: into the buffers the host regards as committed after this launch
     // (it swaps its pointers when the step count is odd)
