@@ -481,8 +481,14 @@ def ensemble_workload(args, kmc_b200, torch, dist, rank, world, local, allmax):
         dist.barrier()
     k.sync()
     ev0 = k.events()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     ms = sum(k.step_timed(S) for _ in range(args.steps))
     k.sync()
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
     if dist is not None:
         dist.barrier()
     ev1 = k.events()
@@ -510,7 +516,7 @@ def ensemble_workload(args, kmc_b200, torch, dist, rank, world, local, allmax):
                 "cpu_baseline": None,
                 "e2e": {"value": 200.0 * total * S / e2e_s, "unit": "molecule-moves/s", "h2d_bytes_per_step": int(len(states) * 3 * 25 * 201 * 8), "d2h_bytes_per_step": int(64 * (hi - lo)),
                         "note": "kmc_set_state of 8 replicas + S steps + kmc_get_series of every replica"},
-                "gpu_launches": ev1["launches"] - ev0["launches"],
+                "gpu_launches": ev1["launches"] - ev0["launches"], "clocks": sampler.result() if sampler else None,
                 "series_replica0": rows[0]}
         print(json.dumps(line))
     if dist is not None:
