@@ -94,6 +94,25 @@ def test_fused_four_replicas_per_cta_in_lockstep(monkeypatch, grid):
     assert fused.series(6)["bond_num"] > 0 and fused.events()["reverted"] > 0
 
 
+def test_four_slot_kernel_against_oracle_with_spare_slots(golden_dir, monkeypatch):
+    """the lockstep kernel on ONE system (three spare slots that only keep the barriers company), per-step against the oracle from the
+    reference-evolved state that sits before a lay-down and `goto lable4` back edges (main.cpp:1141-1189, 1628 -> 1438)"""
+    monkeypatch.setenv("KMC_SMALL_SLOTS", "4")
+    g = load_golden_state(os.path.join(golden_dir, "hot200_step180900_goto.npz"))
+    o = pyoracle.Oracle(apply_regime(pyoracle.default_params(box=tuple(g["params"]["box"]), use_grid=1, stream_mode=1, seed=g["params"]["keyed_seed"]), "hot"))
+    k = kmc_b200.Kmc(apply_regime(kmc_b200.default_params(box=tuple(g["params"]["box"]), seed=g["params"]["keyed_seed"]), "hot"))
+    assert k.path() == "fused"
+    for x in (o, k):
+        x.set_state(g["R"], g["status"], g["res_nei"], step_done=g["step"], max_complex=g["max_complex"])
+    ev0 = o.events().copy()
+    for step in range(300):
+        o.step(1); k.step(1)
+        assert np.array_equal(o.accepted()[1:], k.accepted()[1:]), step
+    compare_states(o.get_state(), k.get_state(), "four-slot goto window")
+    assert o.results() == k.complexes()
+    assert o.events()[9] - ev0[9] >= 1, "goto lable4 not taken inside the window"
+
+
 def test_fused_small_odd_sizes_against_oracle():
     """odd molecule count (the all-pairs schedule differs for odd and even N), more molecules than threads, crowded box"""
     for na, nb, box in ((31, 10, (900.0, 900.0, 300.0)), (170, 71, (3000.0, 3000.0, 400.0))):
