@@ -36,7 +36,7 @@ struct kmc_handle {
     Consts K;
     Dev D;
     cudaStream_t stream = nullptr, side[2] = {nullptr, nullptr};      // side streams: forked branches of the step (graph)
-    cudaEvent_t evFork[2] = {nullptr, nullptr}, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evFork[3] = {nullptr, nullptr, nullptr}, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int R = 1, NA = 0, NB = 0, N = 0, NAt = 0, NBt = 0, NT = 0;
     int64_t step_done = 0;
@@ -66,7 +66,7 @@ struct kmc_handle {
     int cxBlocks = 0;                // grid of the cooperative rebuild kernel
     unsigned long long *timeline = nullptr; int tlCount = 0, tlId[64]; cudaStream_t tlStream = nullptr;      // KMC_TIMELINE
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
-    int forkMask = 6;                // KMC_FORK, read once at kmc_create
+    int forkMask = 14;               // KMC_FORK, read once at kmc_create (bit 3: the restore of rejected units beside S3)
     bool cxGroups = true;            // small multi-ligand complexes by groups of 8 lanes on a shared-memory copy (KMC_CX_GROUPS=0: one thread each, on global memory)
     int smallSlots = 1;              // replicas per CTA of the fused step (1, or 4 in lockstep for ensembles that fill the device)
     int smallGrid = 0; int *smallQueue = nullptr;      // fused step: CTAs resident at once; ticket queue (1 + R ints) for ensembles larger than that
@@ -651,10 +651,21 @@ static void issue_step(kmc_handle *h, const Args &A, cudaStream_t st) {
         }
     } else LAUNCH(KID_RESOLVE, (k_resolve_tiles<<<h->nTiles, TTHREADS, 0, st>>>(A)));
     LAUNCH(KID_PEND_RESOLVE, (k_pend_resolve<<<1, 1024, 0, st>>>(A)));
+    // the rejected units get their old poses back on a side branch (it needs the settled decisions, nothing of S3), next to S3
+    const bool forkR = (forkMask & 8) != 0;
+    cudaStream_t s5 = forkR ? h->side[1] : st;
+    if (forkR) {
+        cudaEventRecord(h->evFork[2], st); cudaStreamWaitEvent(s5, h->evFork[2], 0);
+        h->tlStream = s5;
+        LAUNCH(KID_FINISH, (k_finish<<<std::min(nblk(NT / 256 + 1, 128), h->nSM * 2), 128, 0, s5>>>(A, 1)));
+        h->tlStream = nullptr;
+        cudaEventRecord(h->evJoin[3], s5);
+    }
     // S3
     LAUNCH(KID_REACT_PAIRS, (k_react_pairs<<<std::min(nblk(NT / 16 + 1, RPTHREADS) + h->nSM, h->nSM * 32), RPTHREADS, 0, st>>>(A)));
     LAUNCH(KID_REACT_RESOLVE, (k_react_resolve<<<1, 1024, 0, st>>>(A)));
-    LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max((NAt + 3) / 4, 1), 256), 256, 0, st>>>(A)));
+    LAUNCH(KID_FINISH, (k_finish<<<nblk(std::max((NAt + 3) / 4, 1), 256), 256, 0, st>>>(A, forkR ? 2 : 3)));
+    if (forkR) cudaStreamWaitEvent(st, h->evJoin[3], 0);
 }
 static void swap_buffers(Dev &D) { std::swap(D.recC, D.recCn); std::swap(D.recS2, D.recS2n); std::swap(D.recS3, D.recS3n); std::swap(D.lig, D.lign); }
 

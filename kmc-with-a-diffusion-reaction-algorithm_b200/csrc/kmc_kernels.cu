@@ -1998,10 +1998,12 @@ KD void dissociate(const Consts &K, const Dev &D, uint64_t step, int a, int h, i
 //     rejection time for a receptor-headed one -- whatever S3 did to the bonds since.
 // (2) Dissociation: a thread takes four consecutive receptors; their bond words arrive as two 16-byte loads, and on a
 //     membrane with few bonds that is all the kernel reads (8 bytes per receptor).
-template <bool RANGED>          // RANGED: receptors [aBeg, aEnd) take their dissociation trials here (a replica, fused small-system step); else all live ones
+// PARTS: 1 = the restore of the rejected units, 2 = the dissociation trials, 3 = both. (The restore needs nothing of S3: the step
+// graph runs it on a side branch next to k_react_pairs / k_react_resolve, the trials after them.)
+template <bool RANGED, int PARTS = 3>          // RANGED: receptors [aBeg, aEnd) take their dissociation trials here (a replica, fused small-system step); else all live ones
 KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, int aEnd) {
     if (!RANGED) { aBeg = 0; aEnd = nA_live(D); }
-    const int nrej = min(D.scal[S_NREJ], K.NT);
+    const int nrej = (PARTS & 1) ? min(D.scal[S_NREJ], K.NT) : 0;
     if (tid == 0 && nrej) atomicAdd(&D.events[EV_REVERTED], (unsigned long long)nrej);
     for (int i = tid; i < nrej; i += nth) {
         const int u = D.rejList[i];
@@ -2010,6 +2012,7 @@ KD void finish_body(const Consts &K, const Dev &D, int tid, int nth, int aBeg, i
         if (size <= 1) restore_pose(K, D, u);
         else { const int *row = D.members + D.cxOff[h]; for (int q = 0; q < size; q++) restore_pose(K, D, row[q]); }
     }
+    if (!(PARTS & 2)) return;
     const uint64_t step = D.step64[0];
     for (int a0 = (aBeg & ~3) + tid * 4; a0 < aEnd; a0 += nth * 4) {
         int hh[4] = {-1, -1, -1, -1}, pp[4] = {-1, -1, -1, -1};
@@ -2036,7 +2039,11 @@ __global__ void __launch_bounds__(1024) k_pend_resolve(const __grid_constant__ A
 #endif
 __global__ void __launch_bounds__(RPTHREADS) k_react_pairs(const __grid_constant__ Args A) { KARGS react_pairs_body<false>(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void k_react_resolve(const __grid_constant__ Args A) { KARGS react_resolve_block(D); }
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A) { KARGS finish_body<false>(cK, D, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, 0); }
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Args A, int parts) {
+    KARGS
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (parts == 3) finish_body<false, 3>(cK, D, tid, nth, 0, 0); else if (parts == 1) finish_body<false, 1>(cK, D, tid, nth, 0, 0); else finish_body<false, 2>(cK, D, tid, nth, 0, 0);
+}
 
 // ------------------------------------------------------------------------------------------------
 // outputs (bond.dat columns, main.cpp:2251)
