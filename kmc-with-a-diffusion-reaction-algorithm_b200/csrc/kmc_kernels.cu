@@ -1858,7 +1858,8 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
         const int la = D.recLig[a];
         const int occ[3] = {D.ligRec[h * 3], D.ligRec[h * 3 + 1], D.ligRec[h * 3 + 2]};
         Lig b; load_lig(D.lign, h, b);
-        const bool rejA = D.unitRes[ua] & 1, rejV = D.unitRes[uv] & 1;
+        const bool anyRej = !SMALL || D.scal[S_NREJ] > 0;          // (fused small-system step: the replica's own count, in shared memory -- most steps reject nothing and skip the two global loads)
+        const bool rejA = anyRej && (D.unitRes[ua] & 1), rejV = anyRej && (D.unitRes[uv] & 1);
         if (la >= 0) return;
         if (rejA) ra = load_rec(D.recC, D.recS2, D.recS3, a);
         if (rejV) load_lig(D.lig, h, b);
@@ -1880,7 +1881,8 @@ KD void react_pair(const Consts &K, const Dev &D, uint64_t step, int a, int v) {
     } else {
         const int ca = D.recCis[a], cv = D.recCis[v];
         Rec rb = load_rec(D.recCn, D.recS2n, D.recS3n, v);
-        const bool rejA = D.unitRes[ua] & 1, rejV = D.unitRes[uv] & 1;
+        const bool anyRej = !SMALL || D.scal[S_NREJ] > 0;          // (fused small-system step: the replica's own count, in shared memory -- most steps reject nothing and skip the two global loads)
+        const bool rejA = anyRej && (D.unitRes[ua] & 1), rejV = anyRej && (D.unitRes[uv] & 1);
         if (ca >= 0 || cv >= 0) return;
         if (rejA) ra = load_rec(D.recC, D.recS2, D.recS3, a);
         if (rejV) rb = load_rec(D.recC, D.recS2, D.recS3, v);
