@@ -23,7 +23,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-o", LIB] + SRC
-    for k in ("TS", "TTHREADS", "TCAP", "NSURV", "TMINB", "KMC_TILE_TIMING", "CTHREADS", "CSURV", "CMINB", "PMINB", "PTHREADS", "RECMINB", "LIGMINB", "PE_CHUNK", "RP_CHUNK", "RPTHREADS", "SMALL_T", "SMALL_MINB", "SMALL_TIMING", "SMALL_DMAX", "SMALL_SPEC_MAX", "RECDYN"):          # tile-kernel tuning knobs (experiments only)
+    for k in ("TS", "TTHREADS", "TCAP", "NSURV", "TMINB", "KMC_TILE_TIMING", "CTHREADS", "CSURV", "CMINB", "PMINB", "PTHREADS", "RECMINB", "LIGMINB", "PE_CHUNK", "RP_CHUNK", "RPTHREADS", "SMALL_T", "SMALL_MINB", "SMALL_TIMING", "SMALL_DMAX", "SMALL_SPEC_MAX", "RECDYN", "CX_G", "CX_GROUPS"):          # tile-kernel tuning knobs (experiments only)
         if os.environ.get("KMC_" + k):
             cmd.insert(1, "-D%s=%s" % (k, os.environ["KMC_" + k]))
     if verbose:

@@ -534,8 +534,12 @@ __global__ void __launch_bounds__(LIG_TILE, LIGMINB) k_propose_lig(const __grid_
 #define CX_CAP 40          // members cached per complex (one warp per complex: complexes of more than CX_SMALL members)
 #define CX_WARPS 4         // of those, per CTA
 #define CX_GCAP CX_SMALL   // members cached per small complex with several ligands: GROUPS of CX_G lanes, CX_GROUPS of them per CTA
+#ifndef CX_G
 #define CX_G 8
-#define CX_GROUPS 4          // (one warp, 10 KB of shared memory per CTA: an idle launch -- a membrane without such complexes -- does not keep the streaming kernels' CTAs waiting for shared memory)
+#endif
+#ifndef CX_GROUPS
+#define CX_GROUPS (32 / CX_G)         // (one warp per CTA: an idle launch -- a membrane without such complexes -- does not keep the streaming kernels' CTAs waiting for shared memory)
+#endif
 // a group of G consecutive lanes of a warp (G = 32: the warp) works on one complex
 template <int G> KD unsigned grp_mask() { return G == 32 ? 0xffffffffu : ((G == 32 ? 0u : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) & ~(G - 1))); }
 template <int G> KD void grp_sync() { __syncwarp(grp_mask<G>()); }
