@@ -32,7 +32,7 @@ namespace kmc {
 #define SMALL_LIST 768        // pairs the list of a replica holds
 #define SMALL_ITEMS 512       // directed pairs queued for exact classification per step (more: classified in place)
 #ifndef SMALL_DMAX
-#define SMALL_DMAX 24.0f      // drift (Angstrom) the pair list allows a molecule before it has to be searched on its own
+#define SMALL_DMAX 64.0f      // drift (Angstrom) the pair list allows a molecule before it has to be searched on its own (24 / 48 / 64 / 100: 29.8 / 28.0 / 27.9 / 28.2 us per step at 1 024 replicas); halved by a replica whose list overflows
 #endif
 #ifndef SMALL_SPEC_MAX
 #define SMALL_SPEC_MAX 6      // more molecules than this outside their allowance: the list is rebuilt
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
                 __syncthreads();
                 if (build) {
                     useList = sm.nlist <= SMALL_LIST && S.nspec <= SMALL_SPEC;      // else too crowded for the list: every pair, in place (and the next step tries again)
-                    if (tid == 0) sm.listValid = useList;                           // (read again only after the next barrier)
+                    if (tid == 0) { sm.listValid = useList; if (!useList) S.dmax = fmaxf(8.f, 0.5f * S.dmax); }      // (read again only after the next barrier; a denser replica settles on a shorter allowance)
                 }
             }
         }
