@@ -1,20 +1,25 @@
-// csrc/kmc_small.cu -- the whole time step (main.cpp:461-2202) of a SMALL system as one kernel: one CTA per replica, many
-// steps per launch (BASELINE configs[2]: ensembles of the reference's default 200-molecule system).
+// csrc/kmc_small.cu -- the whole time step (main.cpp:461-2202) of a SMALL system as one kernel, many steps per launch
+// (BASELINE configs[2]: ensembles of the reference's default 200-molecule system).
 //
 // The general path (kmc_kernels.cu) spends one CUDA-graph node per stage: 13 dependent nodes per step, ~30 us for a system
 // whose arithmetic takes a microsecond. Here the stages of a step are separated by __syncthreads() instead of kernel
-// boundaries, a replica never leaves its SM, and nothing crosses between replicas, so the launch covers any number of steps.
+// boundaries, a replica never leaves its SM, and nothing crosses between replicas, so a launch covers any number of steps.
 //
 // It is the SAME step: every stage calls the device functions of kmc_kernels.cu (propose_one_rec, lig_move_*,
-// complex_move_thread, pair_eval/publish, pend_sweep, react_pair, react_resolve_block, finish_body) through a per-replica VIEW of
-// the device state -- a copy of Args in shared memory whose work lists point at this replica's slices of the global lists and
-// whose scalars (list lengths, step counter) live in shared memory. Only the neighbour search differs: a replica's CTA cuts ALL
-// pairs of its molecules with an fp32 test on per-molecule search records (old centre, reach share + displacement of this
-// step) held in shared memory, so there is no grid, no far-mover bookkeeping and no list reuse; the pairs that survive are
-// classified by the same pair_eval as everywhere else. For the length of a launch the replica's poses (both buffers) and its
-// bond table live in the CTA's shared memory: the view's pose / bond pointers are shifted so that indexing them with the
-// molecule's GLOBAL index lands in the shared arrays -- the device functions neither know nor care. Results are bit-identical to the general path (tests/test_gpu_small.py)
-// and to the oracle (every small-system test of tests/test_gpu_replay.py runs through this kernel).
+// complex_move_thread, pair_eval / publish, pend_sweep, react_pair, react_resolve_block, finish_body) through a per-replica VIEW
+// of the device state -- a copy of Args in shared memory whose work lists point at this replica's slices of the global lists and
+// whose scalars (list lengths, step counter) live in shared memory. For the length of a launch the replica's poses (both
+// buffers) and its bond table live in shared memory too: the view's pose / bond pointers are SHIFTED so that indexing them with
+// a molecule's global index lands in the shared arrays -- the device functions neither know nor care.
+//
+// Only the neighbour search differs: no grid, no far movers, no ghosts. Per molecule an fp32 search record in shared memory (old
+// centre, share of the reach + this step's displacement); a pair list built with a drift allowance per molecule and rebuilt when
+// too many molecules have left theirs; a molecule that may be outside its allowance this step (periodic wrap, alignment snap) is
+// cut against every other molecule by the whole CTA. Pairs within reach are queued and classified by the same pair_eval as
+// everywhere else, one directed pair per thread.
+//
+// Results are bit-identical to the general path (tests/test_gpu_small.py, tools/fused_long_check.py) and to the oracle (every
+// small-system test of tests/test_gpu_replay.py runs through this kernel). DESIGN.md section 3b has the measurements.
 #pragma once
 #ifdef SMALL_TIMING
 #include <cstdio>
@@ -52,8 +57,7 @@ struct SmallShared {
 
 // dynamic shared memory of k_small_step for replicas of NA receptors + NB ligands
 __host__ __device__ inline size_t small_dyn_bytes(int NA, int NB) { return ((size_t)NA * 96 + (size_t)NB * 384 + (size_t)(2 * ((NA + 11) & ~3) + NA + 3 * NB) * 4 + 31) & ~(size_t)15; }
-// ... of a CTA that holds `slots` replicas (the per-replica lists and views are carved from dynamic shared memory as well)
-
+// (a CTA that holds `slots` replicas takes slots x (sizeof(SmallShared) + small_dyn_bytes): lists and views are dynamic as well)
 
 KD int small_gid(const Consts &K, int rep, int m) { return m < K.NA ? rep * K.NA + m : K.NAt + rep * K.NB + (m - K.NA); }
 
