@@ -112,6 +112,13 @@ int kmc_get_state(kmc_handle *h, int32_t replica, double *R_x, double *R_y, doub
 int kmc_get_packed(kmc_handle *h, double *rec_pose, double *lig_pose, int32_t *rec_lig, int32_t *rec_site, int32_t *rec_cis);
 int kmc_set_packed(kmc_handle *h, const double *rec_pose, const double *lig_pose, const int32_t *rec_lig,
                    const int32_t *rec_site, const int32_t *rec_cis, int64_t step_done);
+/* kmc_get_packed without waiting: the state as it stands after the steps enqueued so far is copied into a device-side snapshot on
+ * the handle's stream -- kmc_step may be called again at once -- and moved to the caller's buffers (PINNED host memory, else the
+ * copy is not asynchronous) on a copy stream of the handle. The buffers are complete when kmc_snapshot_wait returns. One snapshot
+ * in flight per handle: a second call queues behind the first. (The reference writes its records every 5000 steps, main.cpp:2206:
+ * this is how those leave the device while the next 5000 steps already run.) */
+int kmc_get_packed_async(kmc_handle *h, double *rec_pose, double *lig_pose, int32_t *rec_lig, int32_t *rec_site, int32_t *rec_cis);
+int kmc_snapshot_wait(kmc_handle *h);
 
 /* Advance n time steps (main.cpp:461-2202 each). Asynchronous on the handle's stream except for the
  * conflict-resolution count it reads back each step; kmc_sync waits for completion. */

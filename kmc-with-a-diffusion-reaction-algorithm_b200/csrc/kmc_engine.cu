@@ -55,6 +55,9 @@ struct kmc_handle {
     int parity = 0, launches_per_step[2] = {0, 0};
     bool use_graph = true;
     double *stageRec = nullptr; int *stageInt = nullptr;      // device staging of kmc_set_packed / kmc_get_packed
+    // kmc_get_packed_async: device-side snapshot (taken on the handle's stream) + copy stream that moves it to the host while stepping goes on
+    double *snapRec = nullptr, *snapLig = nullptr; int *snapInt = nullptr;
+    cudaStream_t copyStream = nullptr; cudaEvent_t evSnap = nullptr, evSnapDone = nullptr; bool snapPending = false;
     // strips
     bool strip_on = false; double strip_W = 0, strip_lo = 0, strip_hi = 0; int64_t strip_refreshes = 0;
     double strip_t[3] = {0, 0, 0};             // KMC_STRIP_TIMING: accumulated wall-clock of the refresh phases (us)
@@ -278,6 +281,9 @@ extern "C" void kmc_destroy(kmc_handle *h) {
     for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto ev : h->evpool) cudaEventDestroy(ev);
     for (int p = 0; p < 4; p++) if (h->gexec[p >> 1][p & 1]) cudaGraphExecDestroy(h->gexec[p >> 1][p & 1]);
+    if (h->copyStream) { cudaStreamSynchronize(h->copyStream); cudaStreamDestroy(h->copyStream); }
+    if (h->evSnap) cudaEventDestroy(h->evSnap);
+    if (h->evSnapDone) cudaEventDestroy(h->evSnapDone);
     if (h->monHost) cudaFreeHost(h->monHost);
     if (h->monEvent) cudaEventDestroy(h->monEvent);
     for (auto e : h->evFork) if (e) cudaEventDestroy(e);
@@ -555,6 +561,44 @@ extern "C" int kmc_get_packed(kmc_handle *h, double *rec_pose, double *lig_pose,
     if (rec_lig) CK(cudaMemcpyAsync(rec_lig, D.recLig, sizeof(int) * NAt, cudaMemcpyDeviceToHost, st));
     if (rec_cis) CK(cudaMemcpyAsync(rec_cis, D.recCis, sizeof(int) * NAt, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return KMC_OK;
+}
+
+// The committed state is copied into a device-side snapshot on the handle's stream (a few tens of microseconds; stepping may go
+// on at once) and crosses PCIe from there on a copy stream of its own: the result of one batch travels while the next one computes.
+extern "C" int kmc_get_packed_async(kmc_handle *h, double *rec_pose, double *lig_pose, int32_t *rec_lig, int32_t *rec_site, int32_t *rec_cis) {
+    if (!h) return KMC_ERR_INVALID;
+    int rc = select_device(h); if (rc) return rc;
+    Dev &D = h->D; const int NAt = h->NAt, NBt = h->NBt; cudaStream_t st = h->stream;
+    if (!h->copyStream) {
+        bool ok = cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->evSnap, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&h->evSnapDone, cudaEventDisableTiming) == cudaSuccess && dalloc(h, &h->snapRec, (size_t)std::max(NAt, 1) * 6) == cudaSuccess &&
+                  dalloc(h, &h->snapLig, (size_t)std::max(NBt, 1) * 24) == cudaSuccess && dalloc(h, &h->snapInt, (size_t)std::max(NAt, 1) * 3) == cudaSuccess;
+        if (!ok) { h->err = "kmc_get_packed_async: cannot set up the snapshot buffers"; return KMC_ERR_CUDA; }
+    }
+    if (h->snapPending) CK(cudaStreamWaitEvent(st, h->evSnapDone, 0));          // (the previous snapshot must have left the device buffers)
+    const Args A{D, h->K};
+    LAUNCH(KID_SERIES, (k_pack_get<<<nblk(std::max(NAt, 1), 256), 256, 0, st>>>(A, rec_pose ? h->snapRec : nullptr, rec_site ? h->snapInt : nullptr)));
+    if (lig_pose) CK(cudaMemcpyAsync(h->snapLig, D.lig, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyDeviceToDevice, st));
+    if (rec_lig) CK(cudaMemcpyAsync(h->snapInt + NAt, D.recLig, sizeof(int) * NAt, cudaMemcpyDeviceToDevice, st));
+    if (rec_cis) CK(cudaMemcpyAsync(h->snapInt + 2 * (size_t)NAt, D.recCis, sizeof(int) * NAt, cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(h->evSnap, st));
+    CK(cudaStreamWaitEvent(h->copyStream, h->evSnap, 0));
+    if (rec_pose) CK(cudaMemcpyAsync(rec_pose, h->snapRec, sizeof(double) * 6 * (size_t)NAt, cudaMemcpyDeviceToHost, h->copyStream));
+    if (lig_pose) CK(cudaMemcpyAsync(lig_pose, h->snapLig, sizeof(double) * 24 * (size_t)NBt, cudaMemcpyDeviceToHost, h->copyStream));
+    if (rec_site) CK(cudaMemcpyAsync(rec_site, h->snapInt, sizeof(int) * NAt, cudaMemcpyDeviceToHost, h->copyStream));
+    if (rec_lig) CK(cudaMemcpyAsync(rec_lig, h->snapInt + NAt, sizeof(int) * NAt, cudaMemcpyDeviceToHost, h->copyStream));
+    if (rec_cis) CK(cudaMemcpyAsync(rec_cis, h->snapInt + 2 * (size_t)NAt, sizeof(int) * NAt, cudaMemcpyDeviceToHost, h->copyStream));
+    CK(cudaEventRecord(h->evSnapDone, h->copyStream));
+    h->snapPending = true;
+    return KMC_OK;
+}
+extern "C" int kmc_snapshot_wait(kmc_handle *h) {
+    if (!h) return KMC_ERR_INVALID;
+    if (!h->snapPending) return KMC_OK;
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaEventSynchronize(h->evSnapDone));
+    h->snapPending = false;
     return KMC_OK;
 }
 

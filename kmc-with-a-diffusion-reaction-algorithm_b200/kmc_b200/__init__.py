@@ -37,7 +37,7 @@ class Series(C.Structure):
 
 EXPORTS = ["kmc_abi_version", "kmc_default_params", "kmc_create", "kmc_destroy", "kmc_last_error", "kmc_init_random",
            "kmc_set_state", "kmc_get_state", "kmc_get_packed", "kmc_set_packed", "kmc_step", "kmc_sync", "kmc_get_series",
-           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_get_step_path", "kmc_alignment_window", "kmc_write_bond_dat",
+           "kmc_get_complexes", "kmc_get_complex_labels", "kmc_get_oligomer_hist", "kmc_get_accept", "kmc_get_events", "kmc_get_live_counts", "kmc_get_step_path", "kmc_alignment_window", "kmc_get_packed_async", "kmc_snapshot_wait", "kmc_write_bond_dat",
            "kmc_write_cluster_log", "kmc_run", "kmc_step_timed", "kmc_profile", "kmc_profile_get", "kmc_timeline_print", "kmc_format_bond_dat", "kmc_format_cluster_log", "kmc_get_grid", "kmc_strip_configure", "kmc_strip_load_global",
            "kmc_strip_begin_refresh", "kmc_strip_message", "kmc_strip_rebuild", "kmc_strip_halo_width", "kmc_strip_unique_id",
            "kmc_strip_comm_init", "kmc_strip_refresh", "kmc_strip_refresh_local", "kmc_strip_get_series", "kmc_strip_get_oligomer_hist",
@@ -79,6 +79,8 @@ def lib():
         L.kmc_get_state.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.kmc_get_packed.argtypes = [vp, vp, vp, vp, vp, vp]
         L.kmc_set_packed.argtypes = [vp, vp, vp, vp, vp, vp, i64]
+        L.kmc_get_packed_async.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.kmc_snapshot_wait.argtypes = [vp]
         L.kmc_step.argtypes = [vp, i64]
         L.kmc_sync.argtypes = [vp]
         L.kmc_get_series.argtypes = [vp, i32, C.POINTER(Series)]
@@ -300,6 +302,16 @@ class Kmc:
             rl = np.zeros(r * self.na, dtype=np.int32); rs = np.zeros_like(rl); rc = np.zeros_like(rl)
         self._ck(lib().kmc_get_packed(self.h, rec.ctypes.data, lig.ctypes.data, rl.ctypes.data, rs.ctypes.data, rc.ctypes.data))
         return rec, lig, rl, rs, rc
+
+    def get_packed_async(self, out):
+        """starts the transfer of the state as it stands after the steps enqueued so far into `out` (five preallocated arrays in PINNED
+        host memory); stepping may continue at once; snapshot_wait() completes the arrays"""
+        rec, lig, rl, rs, rc = out
+        self._ck(lib().kmc_get_packed_async(self.h, rec.ctypes.data, lig.ctypes.data, rl.ctypes.data, rs.ctypes.data, rc.ctypes.data))
+        return out
+
+    def snapshot_wait(self):
+        self._ck(lib().kmc_snapshot_wait(self.h))
 
     def set_packed(self, rec, lig, rl=None, rs=None, rc=None, step_done=0):
         rec = np.ascontiguousarray(rec, dtype=np.float64); lig = np.ascontiguousarray(lig, dtype=np.float64)

@@ -166,6 +166,32 @@ def test_gpu_against_keyed_reference_directly(golden_dir):
         assert (s["bond_num"], s["bond_num_rl"], s["bond_num_cis"], s["bond_num_mono_cis"]) == (fr["bond_num"], fr["bond_num_rl"], fr["bond_num_cis"], fr["bond_num_mono_cis"])
 
 
+def test_asynchronous_snapshot_is_the_state_at_the_time_of_the_call():
+    """kmc_get_packed_async: a device-side snapshot taken on the handle's stream crosses PCIe on a copy stream while the next steps
+    already run. It must hold the state after the steps enqueued BEFORE the call -- not what the following steps make of it --, and
+    a second snapshot queued behind the first must not disturb it. Membrane (general path) and ensemble (fused step)."""
+    import torch
+    for kw in (dict(box=kmc_b200.scaled_box(40000), n_receptor=30000, n_ligand=10000), dict(n_replicas=24)):
+        a = kmc_b200.Kmc(apply_regime(kmc_b200.default_params(seed=6, **kw), "hot"))
+        b = kmc_b200.Kmc(apply_regime(kmc_b200.default_params(seed=6, **kw), "hot"))
+        a.init_random(seed=3, sort_cells=True)
+        b.set_packed(*a.get_packed())
+        pinned = lambda arrs: [torch.from_numpy(x.copy()).pin_memory().numpy() for x in arrs]
+        out1, out2 = pinned(a.get_packed()), pinned(a.get_packed())
+        a.step(60); a.get_packed_async(out1); a.step(45); a.get_packed_async(out2); a.step(10)
+        a.snapshot_wait()
+        b.step(60)
+        for x, y in zip(out1, b.get_packed()):
+            assert np.array_equal(x, y)
+        b.step(45)
+        for x, y in zip(out2, b.get_packed()):
+            assert np.array_equal(x, y)
+        b.step(10)
+        for x, y in zip(a.get_packed(), b.get_packed()):
+            assert np.array_equal(x, y)
+        a.close(); b.close()
+
+
 def test_errors_are_reported_not_swallowed():
     """bad input must come back as an error code with a message (the reference checks nothing)"""
     k = kmc_b200.Kmc(kmc_b200.default_params())
