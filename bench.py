@@ -450,7 +450,7 @@ def main():
                              "kernels_ms_per_mc_step": {n: round(v[0] / (3 * S), 4) for n, v in sorted(prof.items(), key=lambda kv: -kv[1][0]) if v[1]}},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "molecule-moves/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
-                        "note": "bytes per rank (max over ranks); every rank moves its own slab" if ds is not None else "whole state in and out"},
+                        "note": "bytes per rank (max over ranks); every rank moves its own slab" if ds is not None else "whole state in and out every batch; pipelined: the download of batch i (kmc_get_packed_async) overlaps batch i + 1, all transfers inside the timed region"},
                 "gpu_launches": ev1["launches"] - ev0["launches"],
                 "work_lists_last_step": {q: evp[q] for q in ("list_pairs", "special_entries", "pending_findings", "reaction_pairs")},
                 "events_in_timed_region": {q: ev1[q] - ev0[q] for q in ("rl_on", "mono_cis_on", "cis_on", "rl_off", "reverted", "rebuilds")},
