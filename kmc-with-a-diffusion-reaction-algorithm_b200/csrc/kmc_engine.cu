@@ -71,6 +71,7 @@ struct kmc_handle {
     int nSM = 148;                   // multiprocessors of the device (cudaDeviceProp): persistent grids are sized from it
     int forkMask = 14;               // KMC_FORK, read once at kmc_create (bit 3: the restore of rejected units beside S3)
     bool cxGroups = true;            // small multi-ligand complexes by groups of 8 lanes on a shared-memory copy (KMC_CX_GROUPS=0: one thread each, on global memory)
+    bool smallWide = false;          // fused step with 256 threads per replica (ensembles of at most one replica per SM)
     int smallSlots = 1;              // replicas per CTA of the fused step (1, or 4 in lockstep for ensembles that fill the device)
     int smallGrid = 0; int *smallQueue = nullptr;      // fused step: CTAs resident at once; ticket queue (1 + R ints) for ensembles larger than that
     bool fused = false;              // small replicas: the whole step is ONE kernel, one CTA per replica, many steps per launch (csrc/kmc_small.cu)
@@ -328,12 +329,16 @@ extern "C" int kmc_create(const kmc_params *p, kmc_handle **out) {
     if (h->fused) {          // (poses, bond table, lists and views of a replica live in the shared memory of its CTA)
         const size_t per = sizeof(SmallShared) + small_dyn_bytes(K.NA, K.NB);
         int occ1 = 0, occ4 = 0;
-        bool ok1 = per <= (size_t)prop.sharedMemPerBlockOptin && cudaFuncSetAttribute(k_small_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per) == cudaSuccess &&
-                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_small_step<1>, SMALL_T, per) == cudaSuccess && occ1 >= 1;
-        bool ok4 = ok1 && 4 * per + 64 <= (size_t)prop.sharedMemPerBlockOptin && cudaFuncSetAttribute(k_small_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per)) == cudaSuccess &&
-                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_small_step<4>, 4 * SMALL_T, 4 * per) == cudaSuccess && occ4 >= 1;
+        bool ok1 = per <= (size_t)prop.sharedMemPerBlockOptin && cudaFuncSetAttribute(k_small_step<1, SMALL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per) == cudaSuccess &&
+                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_small_step<1, SMALL_T>, SMALL_T, per) == cudaSuccess && occ1 >= 1;
+        bool ok4 = ok1 && 4 * per + 64 <= (size_t)prop.sharedMemPerBlockOptin && cudaFuncSetAttribute(k_small_step<4, SMALL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per)) == cudaSuccess &&
+                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_small_step<4, SMALL_T>, 4 * SMALL_T, 4 * per) == cudaSuccess && occ4 >= 1;
         cudaGetLastError();
         if (!ok1) h->fused = false;
+        // at most one replica per SM: a wide CTA (a molecule per thread, registers uncapped)
+        h->smallWide = ok1 && K.R <= h->nSM && cudaFuncSetAttribute(k_small_step<1, 2 * SMALL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per) == cudaSuccess &&
+                       !(getenv("KMC_SMALL_WIDE") && atoi(getenv("KMC_SMALL_WIDE")) == 0);
+        cudaGetLastError();
         h->smallGrid = occ1 * h->nSM;
         // ensembles that fill the device: four replicas per CTA in lockstep (one CTA per SM), see k_small_step
         h->smallSlots = (ok4 && K.R >= 4 * occ4 * h->nSM) ? 4 : 1;
@@ -823,8 +828,9 @@ extern "C" int kmc_step(kmc_handle *h, int64_t n) {
             if (tickets) CK(cudaMemsetAsync(h->smallQueue, 0, sizeof(int) * (size_t)(1 + groups), st));
             const int grid = tickets ? h->smallGrid : groups, ch = tickets ? 64 : chunk;
             int *q = tickets ? h->smallQueue : nullptr;
-            if (slots == 4) LAUNCH(KID_SMALL_STEP, (k_small_step<4><<<grid, 4 * SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
-            else LAUNCH(KID_SMALL_STEP, (k_small_step<1><<<grid, SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
+            if (slots == 4) LAUNCH(KID_SMALL_STEP, (k_small_step<4, SMALL_T><<<grid, 4 * SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
+            else if (h->smallWide && !tickets) LAUNCH(KID_SMALL_STEP, (k_small_step<1, 2 * SMALL_T><<<grid, 2 * SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
+            else LAUNCH(KID_SMALL_STEP, (k_small_step<1, SMALL_T><<<grid, SMALL_T, dyn, st>>>(A, (unsigned long long)h->step_done, chunk, ch, q)));
             if (chunk & 1) { swap_buffers(h->D); h->parity ^= 1; }
             h->step_done += chunk; h->passes += chunk; h->sinceMon += chunk; left -= chunk;
             h->stepped = true;

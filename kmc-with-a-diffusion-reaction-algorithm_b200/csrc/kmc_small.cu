@@ -64,10 +64,10 @@ KD int small_gid(const Consts &K, int rep, int m) { return m < K.NA ? rep * K.NA
 // S1 for one replica (main.cpp:514-562): union-find over its bond graph, unit heads, sizes, breadth-first member rows; the member
 // rows of replica r live in members[r*N, (r+1)*N)
 // (todo = false: a slot of a multi-replica CTA that has nothing to re-derive only keeps the CTA's barriers company)
-KD void small_rebuild(SmallShared &sm, const Args &V, int rep, int tid, bool todo) {
+template <int T> KD void small_rebuild(SmallShared &sm, const Args &V, int rep, int tid, bool todo) {
     const Dev &D = V.D; const Consts &K = V.K;
     const int N = todo ? K.NA + K.NB : 0, NA_ = todo ? K.NA : 0, NB_ = todo ? K.NB : 0;
-    for (int m = tid; m < N; m += SMALL_T) {
+    for (int m = tid; m < N; m += T) {
         const int gid = small_gid(K, rep, m);
         const int uid = gid < K.NAt ? K.NBt + gid : gid - K.NAt;
         D.ufParent[uid] = uid; D.bfsMark[gid] = 0;
@@ -76,7 +76,7 @@ KD void small_rebuild(SmallShared &sm, const Args &V, int rep, int tid, bool tod
     __syncthreads();                    // (every thread has read the touch counters that sent it here)
     if (tid == 0 && todo) { sm.scal[S_MEMBER_CURSOR] = rep * N; sm.ncx = 0; sm.scal[S_NTOUCH] = 0; sm.scal[S_TOPO_DIRTY] = 0; }
     __syncthreads();
-    for (int m = tid; m < NA_; m += SMALL_T) {
+    for (int m = tid; m < NA_; m += T) {
         const int a = rep * K.NA + m, ua = K.NBt + a;
         const int l = D.recLig[a];
         if (l >= 0) uf_union(D.ufParent, ua, l);
@@ -84,7 +84,7 @@ KD void small_rebuild(SmallShared &sm, const Args &V, int rep, int tid, bool tod
         if (c > a) uf_union(D.ufParent, ua, K.NBt + c);
     }
     __syncthreads();
-    for (int m = tid; m < N; m += SMALL_T) {
+    for (int m = tid; m < N; m += T) {
         const int gid = small_gid(K, rep, m);
         const int uid = gid < K.NAt ? K.NBt + gid : gid - K.NAt;
         const int r = uf_find(D.ufParent, uid);
@@ -94,7 +94,7 @@ KD void small_rebuild(SmallShared &sm, const Args &V, int rep, int tid, bool tod
         if (r < K.NBt) atomicAdd(&D.cxSize[r], 1);
     }
     __syncthreads();
-    for (int b = tid; b < NB_; b += SMALL_T) {
+    for (int b = tid; b < NB_; b += T) {
         const int h = rep * K.NB + b;
         sm.search.ligFree[b] = D.unitOf[K.NAt + h] == K.NAt + h && D.cxSize[h] <= 1;
         if (D.unitOf[K.NAt + h] != K.NAt + h) continue;
@@ -156,8 +156,9 @@ KD bool small_in_reach(const SmallSearch &S, int a, int b) {
     return ex * ex + ey * ey <= r * r;
 }
 
-// SLOTS replicas per CTA, SMALL_T threads each (slot = threadIdx.x / SMALL_T). SLOTS = 1: one replica per CTA, up to four CTAs per
-// SM, each in its own stage of the step. SLOTS = 4: the four replicas an SM can hold advance in LOCKSTEP -- the barriers between
+// SLOTS replicas per CTA, T threads each (slot = threadIdx.x / T). SLOTS = 1: one replica per CTA, up to four CTAs per SM, each
+// in its own stage of the step (T = 128); ensembles of at most one replica per SM take T = 256 -- a molecule per thread, no
+// register cap: 7.3 instead of 8.8 us per step for one system, 9.9 instead of 12.3 us for 128 replicas. SLOTS = 4: the four replicas an SM can hold advance in LOCKSTEP -- the barriers between
 // the stages are CTA wide --, so all warps of the SM run the same stage and share its instruction lines (the kernel is bound by
 // its instruction-cache footprint); used for ensembles that fill the device.
 // queue == nullptr: CTA b advances replicas [b SLOTS, (b+1) SLOTS) by nsteps. Otherwise (more replicas than the device holds at
@@ -165,13 +166,13 @@ KD bool small_in_reach(const SmallSearch &S, int a, int b) {
 // number of steps); a CTA that takes a ticket waits until the group's previous chunk has been published (queue[1 + group] counts
 // its finished chunks; that chunk's ticket was drawn earlier by a CTA that is running, so the wait always ends), loads the
 // replicas, advances them and writes them back. Every SM stays busy to the end whatever G modulo the resident CTAs is.
-template <int SLOTS>
-__global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps, int chunk, int *queue) {
+template <int SLOTS, int T>
+__global__ void __launch_bounds__(T * SLOTS, (SLOTS == 1 && T == 128) ? SMALL_MINB : 1) k_small_step(const __grid_constant__ Args A, unsigned long long step0, int nsteps, int chunk, int *queue) {
     __shared__ int s_ticket;
     extern __shared__ __align__(16) unsigned char small_dyn[];
     // (the slots' thread numbering is rotated by one warp per slot: stages with a handful of work items run on "warp 0" of every
     // slot, and in lockstep those would otherwise be the CTA's warps 0, 4, 8, 12 -- all on the same warp scheduler)
-    const int slot = threadIdx.x / SMALL_T, tid = (threadIdx.x + 32 * slot) & (SMALL_T - 1);
+    const int slot = threadIdx.x / T, tid = (threadIdx.x + 32 * slot) & (T - 1);
     const int NA = A.K.NA, NB = A.K.NB, N = NA + NB, R = A.K.R, G = (R + SLOTS - 1) / SLOTS;
     SmallShared *const SM = reinterpret_cast<SmallShared *>(small_dyn);          // [SLOTS], then the slots' pose / bond regions
     SmallShared &sm = SM[slot];
@@ -201,16 +202,16 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
     // of four: the shared copies start at the same phase, with four spare words on either side)
     const int ph = (rep * NA) & 3, NA8 = (NA + 11) & ~3;
     int *const sRecLig = sBond + 4 + ph, *const sRecCis = sBond + NA8 + 4 + ph, *const sRecSite = sBond + 2 * NA8, *const sLigRec = sRecSite + NA;
-    for (int i = tid; i < 2 * NA8; i += SMALL_T) sBond[i] = -1;
+    for (int i = tid; i < 2 * NA8; i += T) sBond[i] = -1;
     __syncthreads();
-    for (int i = tid; i < NAa; i += SMALL_T) {
+    for (int i = tid; i < NAa; i += T) {
         const int a = rep * NA + i;
         // (__ldcg: past the L1 -- the replica's previous chunk may have been written by another SM)
         sRecC[i] = __ldcg(&A.D.recC[a]); sRecS2[i] = __ldcg(&A.D.recS2[a]); sRecS3[i] = __ldcg(&A.D.recS3[a]);
         sRecLig[i] = __ldcg(&A.D.recLig[a]); sRecCis[i] = __ldcg(&A.D.recCis[a]); sRecSite[i] = __ldcg(&A.D.recSite[a]);
     }
-    for (int i = tid; i < NBa * 12; i += SMALL_T) reinterpret_cast<double2 *>(sLig)[i] = __ldcg(reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24) + i);
-    for (int i = tid; i < NBa * 3; i += SMALL_T) sLigRec[i] = __ldcg(&A.D.ligRec[(size_t)rep * NB * 3 + i]);
+    for (int i = tid; i < NBa * 12; i += T) reinterpret_cast<double2 *>(sLig)[i] = __ldcg(reinterpret_cast<const double2 *>(A.D.lig + (size_t)rep * NB * 24) + i);
+    for (int i = tid; i < NBa * 3; i += T) sLigRec[i] = __ldcg(&A.D.ligRec[(size_t)rep * NB * 3 + i]);
     if (tid == 0) {
         // the views: this replica's slices of the work lists; scalars, search records, poses and bonds in shared memory
         const int repv = active ? rep : 0;          // (a spare slot gets a well-formed view of replica 0 that it never uses)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         sm.search.share[0] = search_share(A.K, false); sm.search.share[1] = search_share(A.K, true);
         sm.listValid = active ? 0 : 1; sm.nlist = 0; sm.ncx = 0; sm.nitems = 0;
     }
-    for (int m = tid; m < N; m += SMALL_T) sm.search.ref[m] = make_float2(0.f, 0.f);
+    for (int m = tid; m < N; m += T) sm.search.ref[m] = make_float2(0.f, 0.f);
     __syncthreads();
     SmallSearch &S = sm.search;
     // a condition of one slot that guards a stage with barriers inside becomes a condition of the CTA (the barrier of
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         // ---- S1: only when the last step's reactions touched the bond table (or at the start of a launch) ----
         {
             const bool dirty = active && (sm.scal[S_NTOUCH] > 0 || sm.scal[S_TOPO_DIRTY]);
-            if (any_slot(dirty)) small_rebuild(sm, V, rep, tid, dirty);
+            if (any_slot(dirty)) small_rebuild<T>(sm, V, rep, tid, dirty);
         }
         if (tid == 0) {                  // (nothing below reads these before the next barrier; nobody still reads the last step's values: barrier at its end)
             sm.step64 = step;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         // (work index: receptors, ligands from the next multiple of 32 on -- a warp runs ONE of the code paths --, then the complexes)
         if (active) {
             const int NAp = (NA + 31) & ~31, NBp = (NB + 31) & ~31, nw = NAp + NBp + sm.ncx;
-            for (int w = tid; w < nw; w += SMALL_T) {
+            for (int w = tid; w < nw; w += T) {
                 if (w < NAp) {
                     if (w >= NA) continue;
                     const int gid = rep * NA + w;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
                     if (SLOTS > 1 ? !SM[k].building : !build) continue;
                     SmallShared &B = SM[k]; SmallSearch &Sk = B.search;
                     const int half = N / 2, len = (half + 3) / 4;
-                    for (int task = threadIdx.x; task < 4 * N; task += SMALL_T * SLOTS) {
+                    for (int task = threadIdx.x; task < 4 * N; task += T * SLOTS) {
                         const int m = task >> 2, q = task & 3;
                         const float4 me = Sk.cen[m];
                         if (q == 0) {
@@ -348,11 +349,11 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         // step are queued, then classified exactly by a dense pass (one directed pair per thread) ----
         if (!active) {}
         else if (!useList) {                  // (a replica too crowded for the list: every pair)
-            for (int m = tid; m < N; m += SMALL_T)
+            for (int m = tid; m < N; m += T)
                 for (int j = m + 1; j < N; j++) if (small_in_reach(S, m, j)) small_queue_pair(V, sm, rep, m, j);
         } else {
             const int nl = sm.nlist;
-            for (int q = tid; q < nl; q += SMALL_T) {
+            for (int q = tid; q < nl; q += T) {
                 const unsigned w = sm.list[q];
                 const int a = (int)(w >> 16), b = (int)(w & 0xffffu);
                 if (!(S.isSpec[a] | S.isSpec[b]) && small_in_reach(S, a, b)) small_queue_pair(V, sm, rep, a, b);
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
             const int nsp = S.nspec;
             for (int k = 0; k < nsp; k++) {
                 const int f = S.spec[k];
-                for (int t = tid; t < N; t += SMALL_T)
+                for (int t = tid; t < N; t += T)
                     if (t != f && !(S.isSpec[t] && t < f) && small_in_reach(S, f, t)) small_queue_pair(V, sm, rep, f, t);      // two special molecules: once, by the lower one
             }
         }
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         SMALL_TICK(7);
         {
             const int ni = min(sm.nitems, SMALL_ITEMS);
-            for (int q = tid; q < ni; q += SMALL_T) small_classify(V, rep, (int)(sm.items[q] >> 16), (int)(sm.items[q] & 0xffffu));
+            for (int q = tid; q < ni; q += T) small_classify(V, rep, (int)(sm.items[q] >> 16), (int)(sm.items[q] & 0xffffu));
         }
         __syncthreads();
         SMALL_TICK(3);
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
             if (np > 0) { const Dev &Dk = SM[k].view[s & 1].D; pend_resolve_block(Dk, min(np, Dk.pendCap)); }
         }
         // ---- S3 ----
-        if (active) react_pairs_body<true>(K, D, tid, SMALL_T);
+        if (active) react_pairs_body<true>(K, D, tid, T);
         __syncthreads();
         SMALL_TICK(4);
         {
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         }
         SMALL_TICK(5);
         if (tid == 0) S.nspec = 0;          // (the special molecules of the NEXT step register during its proposals)
-        if (active) finish_body<true>(K, D, tid, SMALL_T, rep * NA, (rep + 1) * NA);
+        if (active) finish_body<true>(K, D, tid, T, rep * NA, (rep + 1) * NA);
         __syncthreads();
         SMALL_TICK(6);
     }
@@ -403,13 +404,13 @@ __global__ void __launch_bounds__(SMALL_T * SLOTS, SLOTS == 1 ? SMALL_MINB : 1) 
         const int cb = (s1 - s0) & 1;          // (odd only in the last chunk of an odd launch)
         double2 *gC = cb ? A.D.recCn : A.D.recC, *gS2 = cb ? A.D.recS2n : A.D.recS2, *gS3 = cb ? A.D.recS3n : A.D.recS3;
         double *gL = cb ? A.D.lign : A.D.lig;
-        for (int i = tid; i < NAa; i += SMALL_T) {
+        for (int i = tid; i < NAa; i += T) {
             const int a = rep * NA + i;
             gC[a] = sRecC[cb * NA + i]; gS2[a] = sRecS2[cb * NA + i]; gS3[a] = sRecS3[cb * NA + i];
             A.D.recLig[a] = sRecLig[i]; A.D.recCis[a] = sRecCis[i]; A.D.recSite[a] = sRecSite[i];
         }
-        for (int i = tid; i < NBa * 12; i += SMALL_T) reinterpret_cast<double2 *>(gL + (size_t)rep * NB * 24)[i] = reinterpret_cast<const double2 *>(sLig + (size_t)cb * NB * 24)[i];
-        for (int i = tid; i < NBa * 3; i += SMALL_T) A.D.ligRec[(size_t)rep * NB * 3 + i] = sLigRec[i];
+        for (int i = tid; i < NBa * 12; i += T) reinterpret_cast<double2 *>(gL + (size_t)rep * NB * 24)[i] = reinterpret_cast<const double2 *>(sLig + (size_t)cb * NB * 24)[i];
+        for (int i = tid; i < NBa * 3; i += T) A.D.ligRec[(size_t)rep * NB * 3 + i] = sLigRec[i];
     }
     if (tid == 0) {
         if (sm.scal[S_OVERFLOW]) atomicOr(&A.D.scal[S_OVERFLOW], sm.scal[S_OVERFLOW]);
